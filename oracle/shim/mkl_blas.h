@@ -1,0 +1,2 @@
+/* Forwarding stub: the reference includes <mkl_blas.h> (include/lpm.h:18-23); everything lives in mkl.h. Test infrastructure only. */
+#include "mkl.h"
