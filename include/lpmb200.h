@@ -1,0 +1,174 @@
+/*
+ * lpmb200.h -- C ABI of the B200-native LPM hot path (liblpmb200.so).
+ *
+ * Plain C: opaque context, plain pointers and sizes, int status codes (0 = ok; the text of
+ * the last error is returned by lpmb_last_error()).  There is NO CPU fallback: every compute
+ * entry point fails (non-zero) when no CUDA device is usable.
+ *
+ * What each group replaces in the reference (ymlasu/LPM-C, paths relative to its root):
+ *
+ *   topology / CSR container   src/neighbor.c:9-141 (searchNormalNeighbor, searchAFEMNeighbor:
+ *                              neighbors, nsign, conn, nb_conn, K_pointer, IK/JK sizing)
+ *   matrix import/export       the 3-array 1-based symmetric-upper CSR K_global/IK/JK that
+ *                              src/stiffness.c:441-515 writes and src/solver.c:206 consumes
+ *   lpmb_solve_cg              solverCG(), src/solver.c:188-270 (MKL RCI dcg + mkl_sparse_d_mv)
+ *   lpmb_fd_stiffness          calcStiffness{2,3}DFiniteDifference(6), src/stiffness.c:271-516
+ *   lpmb_calc_kntv             calcKnTv(), src/stiffness.c:11-268
+ *   lpmb_bond_force            computeBondForceGeneral(plmode,t), src/constitutive.c:88-146
+ *                              (+ computeStress, src/lpm_basic.c:53-125, + switchStateV(2))
+ *   lpmb_compute_dl            computedL(), src/lpm_basic.c:252-291
+ *   lpmb_switch_state          switchStateV(flag), src/constitutive.c:10-85
+ *   lpmb_update_rr             updateRR(), src/stiffness.c:519-534
+ *   lpmb_update_damage         updateDamageGeneral(), src/constitutive.c:149-164 ->
+ *                              updateDuctileDamagePwiseNonlocal (:1757-1862), updateBrittleDamage (:1437-1526)
+ *   lpmb_update_crack          updateCrack(), src/constitutive.c:1399-1434
+ *   lpmb_apply_disp_bc_mask    the effect of setDispBC_stiffnessUpdate{2,3}D, src/boundary.c:72-281,
+ *                              as a DoF mask applied inside the solve (K is never edited)
+ *
+ * The reference-named drop-in entry points (void solverCG(void) ... on the reference's process
+ * globals) live in liblpmc_dropin (lpm-c_b200/csrc/dropin.c) and are thin wrappers over this ABI;
+ * INTEGRATION.md shows how the reference links against them.
+ *
+ * Host array layouts are the reference's logical layouts, flattened row-major:
+ *   per-bond      [nparticle][nneighbors]            (reference: T **a, a[i][j])
+ *   per-particle  [nparticle][c]                      (xyz: c=3, stress_tensor: c=6, ...)
+ *   DoF vectors   [nparticle*dim] interleaved         (residual, Pex, disp), Pin: [nparticle*3]
+ * Device layouts are slot-major / component-major -- conversion happens on the
+ * device inside lpmb_field_set / lpmb_field_get.
+ */
+#ifndef LPMB200_H
+#define LPMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lpmb_ctx lpmb_ctx;
+
+#define LPMB_OK 0
+#define LPMB_ERR_CUDA 1
+#define LPMB_ERR_ARG 2
+#define LPMB_ERR_STATE 3
+#define LPMB_ERR_NOTCONVERGED 4
+#define LPMB_ERR_UNSUPPORTED 5
+
+/* model-level constants mirrored from include/lpm.h:34-51 */
+#define LPMB_EPS 1e-6      /* EPS: FD perturbation coefficient / "is zero" threshold */
+#define LPMB_TOLITER 1e-4  /* TOLITER */
+
+/* lattice ids, src/lpmc_project.c:70-75 */
+enum { LPMB_LATTICE_SQUARE = 0, LPMB_LATTICE_HEX = 1, LPMB_LATTICE_SC = 2, LPMB_LATTICE_FCC = 3, LPMB_LATTICE_BCC = 4 };
+
+const char *lpmb_last_error(void);
+int lpmb_version(void);
+/* number of usable CUDA devices (0 on a CPU-only host; never an error) */
+int lpmb_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* nconn_max = nneighbors_AFEM + 1 (row length of the reference's conn[][]). */
+int lpmb_create(lpmb_ctx **out, int device, int nparticle, int dim, int lattice, int nneighbors, int nconn_max);
+void lpmb_destroy(lpmb_ctx *ctx);
+int lpmb_synchronize(lpmb_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long lpmb_launch_count(lpmb_ctx *ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on */
+void *lpmb_stream(lpmb_ctx *ctx);
+
+/* scalar parameters by reference name: radius, particle_volume, J2_H, J2_xi, damage_L,
+ * damage_threshold, damagec_A, damageb_A, critical_bstrain, dtime, ... ; ints: nbreak, plmode */
+int lpmb_set_param(lpmb_ctx *ctx, const char *name, double value);
+int lpmb_get_param(lpmb_ctx *ctx, const char *name, double *value);
+
+/* ---- fields (named arrays; names are the reference's global names) ------------------------- */
+/* host -> device / device -> host, host layout as documented above.  `count` = number of
+ * elements in the host array (checked).  3-slot state arrays are addressed per slot:
+ * "dLp0","dLp1","dLp2","J2_alpha0".., "J2_beta0"..(6 comps), "damage_D0","damage_D1",
+ * "damage_nonlocal0/1", "damage_local0/1". */
+int lpmb_field_set(lpmb_ctx *ctx, const char *name, const void *host, size_t count);
+int lpmb_field_get(lpmb_ctx *ctx, const char *name, void *host, size_t count);
+/* raw device pointer + element count of a field (device layout; for zero-copy harnesses) */
+int lpmb_field_device(lpmb_ctx *ctx, const char *name, void **dptr, size_t *count);
+
+/* ---- topology ------------------------------------------------------------------------------ */
+/* Uploads neighbors/nsign ([N][nn], -1 padded, ascending j as neighbor.c:16-41 produces) and
+ * derives nb_initial, mirror slots and opposite-bond slots on the device. */
+int lpmb_set_neighbors(lpmb_ctx *ctx, const int *neighbors, const int *nsign);
+/* Uploads conn ([N][nconn_max], sorted ascending, -1 padded) and builds the block pattern,
+ * K_pointer (64-bit offsets) and the SELL-32 slices. */
+int lpmb_set_connectivity(lpmb_ctx *ctx, const int *conn);
+/* O(N) device builder of the same lists from xyz (cell grid): bit-identical to
+ * searchNormalNeighbor + searchAFEMNeighbor for lattices without duplicates.  Also fills
+ * distance_initial, cs{x,y,z}_initial.  cutoff1/cutoff2 = neighbor1_cutoff/neighbor2_cutoff. */
+int lpmb_build_topology(lpmb_ctx *ctx, double cutoff1, double cutoff2);
+/* sizes of the reference CSR for this connectivity */
+int lpmb_csr_sizes(lpmb_ctx *ctx, long long *nnz_upper, long long *nblocks);
+/* K_pointer as the reference lays it out: [N+1][2] ints (fails if nnz_upper > INT_MAX) */
+int lpmb_get_k_pointer(lpmb_ctx *ctx, int *k_pointer);
+
+/* ---- stiffness matrix ---------------------------------------------------------------------- */
+/* import the reference's symmetric-upper 1-based CSR (host arrays) into the device matrix */
+int lpmb_matrix_from_upper_csr(lpmb_ctx *ctx, const double *K_global, long long nnz);
+/* export the device matrix as the reference's K_global / IK / JK (any pointer may be NULL) */
+int lpmb_matrix_to_upper_csr(lpmb_ctx *ctx, double *K_global, int *IK, int *JK);
+/* FD elastic tangent (forward difference, h = EPS*radius), symmetrised as stiffness.c:441-481.
+ * emulate_side_effects != 0 also leaves dL, cs*, dL_total, TdL_total, F, Pin as the reference's
+ * single-threaded assembly leaves them. */
+int lpmb_fd_stiffness(lpmb_ctx *ctx, int emulate_side_effects);
+/* fill every stored block with a deterministic, symmetric, diagonally dominant test pattern
+ * (bench utility: lets the SpMV be timed at sizes where no reference matrix exists yet) */
+int lpmb_matrix_fill_test_pattern(lpmb_ctx *ctx);
+/* y = K x on host DoF vectors (interleaved); for tests and the SpMV micro-benchmark */
+int lpmb_spmv_host(lpmb_ctx *ctx, const double *x, double *y);
+/* repeat y = K x `reps` times on device-resident vectors, returns mean milliseconds per SpMV
+ * measured with CUDA events on the context stream.  variant: 0 = default kernel */
+int lpmb_spmv_bench(lpmb_ctx *ctx, int reps, int variant, double *ms_per_spmv);
+/* algorithmic bytes one SpMV moves: nblk*(8 d^2+4) + 4 (N+1) + 16 d N */
+long long lpmb_spmv_bytes(lpmb_ctx *ctx);
+/* bytes the device format actually streams (SELL padding included) */
+long long lpmb_spmv_bytes_stored(lpmb_ctx *ctx);
+
+/* ---- linear solve -------------------------------------------------------------------------- */
+/* DoF mask: 1 = free, 0 = constrained (dispBC_index[k] && fix_index[k]); NULL = all free. */
+int lpmb_set_dof_mask(lpmb_ctx *ctx, const int *dispBC_index, const int *fix_index);
+/* Unpreconditioned CG, x0 = 0, stop when ||r||^2 <= rel*||r0||^2 + abs or maxit iterations
+ * (solver.c:217-222: rel=1e-8, abs=1e-12, maxit=n).  rhs/disp are host DoF vectors.
+ * use_mask != 0 solves the BC-modified system without editing K.
+ * Returns LPMB_ERR_NOTCONVERGED (disp still written) when maxit is hit. */
+int lpmb_solve_cg(lpmb_ctx *ctx, const double *rhs, double *disp, double rel, double abs_tol, int maxit,
+                  int use_mask, int *iterations);
+/* same, entirely on device fields "residual" -> "disp"; optionally xyz += disp (solver.c:263-267) */
+int lpmb_solve_cg_device(lpmb_ctx *ctx, double rel, double abs_tol, int maxit, int use_mask, int update_xyz,
+                         int *iterations);
+
+/* ---- constitutive path --------------------------------------------------------------------- */
+int lpmb_calc_kntv(lpmb_ctx *ctx, const double *Ce, int ntype);
+int lpmb_compute_dl(lpmb_ctx *ctx);
+int lpmb_bond_force(lpmb_ctx *ctx, int plmode, int load_indicator);
+int lpmb_switch_state(lpmb_ctx *ctx, int flag);
+/* residual = dispBC_index*(Pex-Pin); returns ||residual||_2 and ||reaction||_2 (either may be NULL) */
+int lpmb_update_rr(lpmb_ctx *ctx, double *norm_residual, double *norm_reaction);
+/* returns the number of newly broken bonds in *broken; broken (i, neighbor) pairs are appended to
+ * pairs[2*k], pairs[2*k+1] in the reference's logging order, up to max_pairs (may be NULL) */
+int lpmb_update_damage(lpmb_ctx *ctx, int plmode, int *broken, int *pairs, int max_pairs);
+int lpmb_update_crack(lpmb_ctx *ctx);
+
+/* ---- one Newton iteration, device resident (lpmc_project.c:426-464) ------------------------ */
+/* switchStateV(0); masked CG solve; xyz += disp; computeBondForceGeneral(plmode); updateRR; norm */
+int lpmb_newton_iteration(lpmb_ctx *ctx, int plmode, int load_indicator, double rel, double abs_tol, int maxit,
+                          int *cg_iterations, double *norm_residual);
+
+/* ---- multi-GPU (one process per GPU; particle slabs = contiguous index ranges) ------------- */
+/* 128-byte NCCL unique id; rank 0 creates it, the harness broadcasts it. */
+int lpmb_dist_unique_id(void *id128);
+int lpmb_dist_init(lpmb_ctx *ctx, const void *id128, int rank, int world);
+/* declare this rank's slab: owned rows [row0,row1) of a global lattice of nglobal particles; local
+ * indices 0..nown-1 are owned, halo_lo/halo_hi particles follow (received from rank-1 / rank+1). */
+int lpmb_dist_set_slab(lpmb_ctx *ctx, long long nglobal, long long row0, long long row1, int halo_lo, int halo_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

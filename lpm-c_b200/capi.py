@@ -1,0 +1,290 @@
+"""ctypes binding of include/lpmb200.h (liblpmb200.so).  Host-side plumbing only.
+
+Every method forwards to one C-ABI entry point; errors raise LPMBError carrying
+lpmb_last_error().  There is deliberately no fallback: without the built library the import
+fails, and without a GPU `Context(...)` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+lib_path = _HERE / "liblpmb200.so"
+HEADER = _HERE.parent / "include" / "lpmb200.h"
+
+
+class LPMBError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lpmb error {code}: {msg}")
+        self.code = code
+
+
+if not lib_path.exists():
+    raise ImportError(f"{lib_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a). The CUDA library is the product; there is no fallback.")
+lib = C.CDLL(str(lib_path))
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_vp = C.c_void_p
+
+lib.lpmb_last_error.restype = C.c_char_p
+lib.lpmb_launch_count.restype = C.c_longlong
+lib.lpmb_launch_count.argtypes = [c_vp]
+lib.lpmb_stream.restype = c_vp
+lib.lpmb_stream.argtypes = [c_vp]
+lib.lpmb_spmv_bytes.restype = C.c_longlong
+lib.lpmb_spmv_bytes.argtypes = [c_vp]
+lib.lpmb_spmv_bytes_stored.restype = C.c_longlong
+lib.lpmb_spmv_bytes_stored.argtypes = [c_vp]
+lib.lpmb_destroy.restype = None
+lib.lpmb_destroy.argtypes = [c_vp]
+lib.lpmb_create.argtypes = [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+lib.lpmb_set_param.argtypes = [c_vp, C.c_char_p, C.c_double]
+lib.lpmb_get_param.argtypes = [c_vp, C.c_char_p, c_dp]
+lib.lpmb_field_set.argtypes = [c_vp, C.c_char_p, c_vp, C.c_size_t]
+lib.lpmb_field_get.argtypes = [c_vp, C.c_char_p, c_vp, C.c_size_t]
+lib.lpmb_field_device.argtypes = [c_vp, C.c_char_p, C.POINTER(c_vp), C.POINTER(C.c_size_t)]
+lib.lpmb_set_neighbors.argtypes = [c_vp, c_vp, c_vp]
+lib.lpmb_set_connectivity.argtypes = [c_vp, c_vp]
+lib.lpmb_build_topology.argtypes = [c_vp, C.c_double, C.c_double]
+lib.lpmb_csr_sizes.argtypes = [c_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+lib.lpmb_get_k_pointer.argtypes = [c_vp, c_vp]
+lib.lpmb_matrix_from_upper_csr.argtypes = [c_vp, c_vp, C.c_longlong]
+lib.lpmb_matrix_to_upper_csr.argtypes = [c_vp, c_vp, c_vp, c_vp]
+lib.lpmb_fd_stiffness.argtypes = [c_vp, C.c_int]
+lib.lpmb_matrix_fill_test_pattern.argtypes = [c_vp]
+lib.lpmb_spmv_host.argtypes = [c_vp, c_vp, c_vp]
+lib.lpmb_spmv_bench.argtypes = [c_vp, C.c_int, C.c_int, c_dp]
+lib.lpmb_set_dof_mask.argtypes = [c_vp, c_vp, c_vp]
+lib.lpmb_solve_cg.argtypes = [c_vp, c_vp, c_vp, C.c_double, C.c_double, C.c_int, C.c_int, c_ip]
+lib.lpmb_solve_cg_device.argtypes = [c_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_ip]
+lib.lpmb_calc_kntv.argtypes = [c_vp, c_vp, C.c_int]
+lib.lpmb_compute_dl.argtypes = [c_vp]
+lib.lpmb_bond_force.argtypes = [c_vp, C.c_int, C.c_int]
+lib.lpmb_switch_state.argtypes = [c_vp, C.c_int]
+lib.lpmb_update_rr.argtypes = [c_vp, c_dp, c_dp]
+lib.lpmb_update_damage.argtypes = [c_vp, C.c_int, c_ip, c_vp, C.c_int]
+lib.lpmb_update_crack.argtypes = [c_vp]
+lib.lpmb_newton_iteration.argtypes = [c_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_ip, c_dp]
+lib.lpmb_dist_unique_id.argtypes = [c_vp]
+lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
+lib.lpmb_dist_set_slab.argtypes = [c_vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
+lib.lpmb_synchronize.argtypes = [c_vp]
+
+
+def declared_symbols() -> list[str]:
+    """every function name declared in include/lpmb200.h (used by the CPU symbol test)"""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lpmb_[a-z0-9_]+)\s*\(", text)))
+
+
+def device_count() -> int:
+    return int(lib.lpmb_device_count())
+
+
+def _check(rc: int, ok=(0,)):
+    if rc not in ok:
+        raise LPMBError(rc, lib.lpmb_last_error().decode())
+    return rc
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# host dtype of the integer fields (everything else is float64)
+_INT_FIELDS = {"neighbors", "nsign", "mirror", "oppslot", "type", "pl_flag", "nb", "nb_initial", "dispBC_index",
+               "fix_index"}
+
+NOTCONVERGED = 4
+
+
+class Context:
+    """One device context = one particle system (or one slab of it) resident in HBM."""
+
+    def __init__(self, nparticle: int, dim: int, lattice: int, nneighbors: int, nconn_max: int, device: int = 0):
+        self._h = c_vp()
+        _check(lib.lpmb_create(C.byref(self._h), device, nparticle, dim, lattice, nneighbors, nconn_max))
+        self.N, self.dim, self.lattice, self.nn, self.nconn = nparticle, dim, lattice, nneighbors, nconn_max
+
+    def close(self):
+        if self._h:
+            lib.lpmb_destroy(self._h)
+            self._h = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters / fields
+    def set_param(self, name: str, v: float):
+        _check(lib.lpmb_set_param(self._h, name.encode(), float(v)))
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            self.set_param(k, v)
+
+    def set_field(self, name: str, arr):
+        a = _i32(arr) if name in _INT_FIELDS else _f64(arr)
+        _check(lib.lpmb_field_set(self._h, name.encode(), a.ctypes.data, a.size))
+
+    def _shape(self, name: str):
+        N, nn, dim = self.N, self.nn, self.dim
+        comps = {"xyz": 3, "xyz_initial": 3, "xyz_temp": 3, "dL_total": 2, "TdL_total": 2, "ddL_total": 2,
+                 "TddL_total": 2, "stress_tensor": 6, "strain_tensor": 6, "J2_beta0": 6, "J2_beta1": 6, "J2_beta2": 6}
+        if name in comps:
+            return (N, comps[name])
+        if name in ("residual", "Pex", "Pex_temp", "disp", "dispBC_index", "fix_index"):
+            return (N * dim,)
+        if name == "Pin":
+            return (N * 3,)
+        bond = {"distance", "distance_initial", "csx", "csy", "csz", "csx_initial", "csy_initial", "csz_initial", "dL",
+                "dL_ave", "ddL", "ddLp", "Kn", "Tv", "F", "F_temp", "bond_stress", "damage_broken", "damage_w", "dLp0",
+                "dLp1", "dLp2", "damage_D0", "damage_D1", "neighbors", "nsign", "mirror", "oppslot"}
+        if name in bond:
+            return (N, nn)
+        return (N,)
+
+    def get_field(self, name: str) -> np.ndarray:
+        out = np.empty(self._shape(name), dtype=np.int32 if name in _INT_FIELDS else np.float64)
+        _check(lib.lpmb_field_get(self._h, name.encode(), out.ctypes.data, out.size))
+        return out
+
+    # -- topology
+    def set_neighbors(self, neighbors, nsign):
+        a, b = _i32(neighbors), _i32(nsign)
+        assert a.shape == (self.N, self.nn) and b.shape == a.shape
+        _check(lib.lpmb_set_neighbors(self._h, a.ctypes.data, b.ctypes.data))
+
+    def set_connectivity(self, conn):
+        a = _i32(conn)
+        assert a.shape == (self.N, self.nconn), (a.shape, self.N, self.nconn)
+        _check(lib.lpmb_set_connectivity(self._h, a.ctypes.data))
+
+    def build_topology(self, cutoff1: float, cutoff2: float):
+        _check(lib.lpmb_build_topology(self._h, cutoff1, cutoff2))
+
+    def csr_sizes(self):
+        nnz, nblk = C.c_longlong(), C.c_longlong()
+        _check(lib.lpmb_csr_sizes(self._h, C.byref(nnz), C.byref(nblk)))
+        return nnz.value, nblk.value
+
+    def k_pointer(self) -> np.ndarray:
+        out = np.empty((self.N + 1, 2), dtype=np.int32)
+        _check(lib.lpmb_get_k_pointer(self._h, out.ctypes.data))
+        return out
+
+    # -- matrix
+    def matrix_from_upper_csr(self, K_global):
+        a = _f64(K_global)
+        _check(lib.lpmb_matrix_from_upper_csr(self._h, a.ctypes.data, a.size))
+
+    def matrix_to_upper_csr(self):
+        nnz, _ = self.csr_sizes()
+        K = np.empty(nnz, dtype=np.float64)
+        JK = np.empty(nnz, dtype=np.int32)
+        IK = np.empty(self.N * self.dim + 1, dtype=np.int32)
+        _check(lib.lpmb_matrix_to_upper_csr(self._h, K.ctypes.data, IK.ctypes.data, JK.ctypes.data))
+        return K, IK, JK
+
+    def fd_stiffness(self, emulate_side_effects: bool = False):
+        _check(lib.lpmb_fd_stiffness(self._h, int(emulate_side_effects)))
+
+    def fill_test_pattern(self):
+        _check(lib.lpmb_matrix_fill_test_pattern(self._h))
+
+    def spmv(self, x) -> np.ndarray:
+        x = _f64(x)
+        y = np.empty_like(x)
+        _check(lib.lpmb_spmv_host(self._h, x.ctypes.data, y.ctypes.data))
+        return y
+
+    def spmv_bench(self, reps: int = 20, variant: int = 0) -> float:
+        ms = C.c_double()
+        _check(lib.lpmb_spmv_bench(self._h, reps, variant, C.byref(ms)))
+        return ms.value
+
+    def spmv_bytes(self) -> int:
+        return int(lib.lpmb_spmv_bytes(self._h))
+
+    def spmv_bytes_stored(self) -> int:
+        return int(lib.lpmb_spmv_bytes_stored(self._h))
+
+    # -- solve
+    def set_dof_mask(self, dispBC_index=None, fix_index=None):
+        a = _i32(dispBC_index) if dispBC_index is not None else None
+        b = _i32(fix_index) if fix_index is not None else None
+        _check(lib.lpmb_set_dof_mask(self._h, a.ctypes.data if a is not None else None,
+                                     b.ctypes.data if b is not None else None))
+
+    def solve_cg(self, rhs, rel=1e-8, abs_tol=1e-12, maxit=None, use_mask=False):
+        b = _f64(rhs)
+        x = np.empty_like(b)
+        it = C.c_int()
+        rc = _check(lib.lpmb_solve_cg(self._h, b.ctypes.data, x.ctypes.data, rel, abs_tol,
+                                      int(maxit or b.size), int(use_mask), C.byref(it)), ok=(0, NOTCONVERGED))
+        return x, it.value, rc == 0
+
+    def solve_cg_device(self, rel=1e-8, abs_tol=1e-12, maxit=None, use_mask=True, update_xyz=True):
+        it = C.c_int()
+        rc = _check(lib.lpmb_solve_cg_device(self._h, rel, abs_tol, int(maxit or self.N * self.dim), int(use_mask),
+                                             int(update_xyz), C.byref(it)), ok=(0, NOTCONVERGED))
+        return it.value, rc == 0
+
+    # -- constitutive path
+    def calc_kntv(self, Ce):
+        a = _f64(Ce)
+        _check(lib.lpmb_calc_kntv(self._h, a.ctypes.data, a.shape[0]))
+
+    def compute_dl(self):
+        _check(lib.lpmb_compute_dl(self._h))
+
+    def bond_force(self, plmode: int, load_indicator: int = 1):
+        _check(lib.lpmb_bond_force(self._h, plmode, load_indicator))
+
+    def switch_state(self, flag: int):
+        _check(lib.lpmb_switch_state(self._h, flag))
+
+    def update_rr(self):
+        a, b = C.c_double(), C.c_double()
+        _check(lib.lpmb_update_rr(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def update_damage(self, plmode: int, max_pairs: int = 4096):
+        broken = C.c_int()
+        pairs = np.full((max_pairs, 2), -1, dtype=np.int32)
+        _check(lib.lpmb_update_damage(self._h, plmode, C.byref(broken), pairs.ctypes.data, max_pairs))
+        return broken.value, pairs[: min(broken.value, max_pairs)]
+
+    def update_crack(self):
+        _check(lib.lpmb_update_crack(self._h))
+
+    def newton_iteration(self, plmode: int, load_indicator: int = 1, rel=1e-8, abs_tol=1e-12, maxit=None):
+        it, nr = C.c_int(), C.c_double()
+        _check(lib.lpmb_newton_iteration(self._h, plmode, load_indicator, rel, abs_tol,
+                                         int(maxit or self.N * self.dim), C.byref(it), C.byref(nr)),
+               ok=(0, NOTCONVERGED))
+        return it.value, nr.value
+
+    def synchronize(self):
+        _check(lib.lpmb_synchronize(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib.lpmb_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib.lpmb_stream(self._h) or 0)

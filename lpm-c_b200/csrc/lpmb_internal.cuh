@@ -1,0 +1,141 @@
+// lpmb_internal.cuh -- context, field registry and launch helpers shared by all translation units.
+// Not part of the C ABI (include/lpmb200.h is).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lpmb200.h"
+
+#define LPMB_SLICE 32  // SELL slice height = warp size; also the padding quantum of every SoA array
+
+void lpmb_set_error(const char *fmt, ...);
+
+#define LPMB_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            lpmb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+            return LPMB_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define LPMB_TRY(call)              \
+    do {                            \
+        int r__ = (call);           \
+        if (r__ != LPMB_OK)         \
+            return r__;             \
+    } while (0)
+
+#define LPMB_REQUIRE(cond, code, ...)  \
+    do {                               \
+        if (!(cond)) {                 \
+            lpmb_set_error(__VA_ARGS__); \
+            return (code);             \
+        }                              \
+    } while (0)
+
+// ---- field registry ---------------------------------------------------------------------------
+// Device layouts (Np = N rounded up to a multiple of 32):
+//   FK_BOND   [nn][Np]     host [N][nn]        slot-major: thread i reads slot j at j*Np+i (coalesced)
+//   FK_PART   [c][Np]      host [N][c]         component-major
+//   FK_DOF    [dim][Np]    host [N*dim]        component-major copy of an interleaved DoF vector
+//   FK_PIN    [3][Np]      host [N*3]          Pin keeps NDIM=3 stride even in 2-D (stiffness.c:527)
+//   FK_RAW    [count]      host [count]        no re-layout
+enum FieldKind { FK_BOND = 0, FK_PART = 1, FK_DOF = 2, FK_PIN = 3, FK_RAW = 4 };
+enum FieldType { FT_F64 = 0, FT_I32 = 1, FT_I8 = 2 };
+
+struct Field {
+    void *d = nullptr;
+    FieldKind kind = FK_RAW;
+    FieldType type = FT_F64;
+    int comps = 1;       // rows of the device layout (nn for bonds, c for parts, dim for dofs)
+    size_t count = 0;    // device elements
+    size_t elem() const { return type == FT_F64 ? 8 : (type == FT_I32 ? 4 : 1); }
+};
+
+struct SellMatrix {
+    int D = 3;                 // block dimension (dim)
+    int nslices = 0;
+    long long kunits = 0;      // sum of slice widths
+    long long nblocks = 0;     // sum nb_conn (algorithmic block count)
+    long long nnz_upper = 0;   // K_pointer[N][1]
+    long long *sptr = nullptr; // [nslices+1] offsets in k-units
+    int *col = nullptr;        // [kunits][32] block column (pad: own row, value 0)
+    double *val = nullptr;     // [kunits][D*D][32]
+    int *nbc = nullptr;        // [Np] nb_conn
+    int *k0 = nullptr;         // [Np] K_pointer[i][0]
+    long long *kp = nullptr;   // [N+1] K_pointer[i][1] (64-bit)
+    bool pattern_ready = false;
+    bool values_ready = false;
+};
+
+struct CGWork {
+    double *r = nullptr, *p = nullptr, *ap = nullptr, *x = nullptr;  // [D][Np] each
+    double *partials = nullptr;                                       // [2][max_blocks]
+    double *scal = nullptr;                                           // device scalars (see lpmb_solver.cu)
+    double *h_scal = nullptr;                                         // pinned mirror
+    int max_blocks = 0;
+};
+
+struct lpmb_ctx {
+    int device = 0;
+    int N = 0, Np = 0, dim = 3, lattice = 2, nn = 0, nconn = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::map<std::string, Field> fields;
+    std::map<std::string, double> params;
+    SellMatrix K;
+    CGWork cg;
+    double *mask = nullptr;      // [dim][Np] 1.0 free / 0.0 constrained (nullptr = all free)
+    void *staging = nullptr;     // device staging for host<->device re-layout
+    size_t staging_bytes = 0;
+    void *h_staging = nullptr;   // pinned host staging
+    size_t h_staging_bytes = 0;
+    // multi-GPU
+    void *nccl = nullptr;
+    int rank = 0, world = 1;
+};
+
+// registry helpers (lpmb_ctx.cu)
+Field *lpmb_field(lpmb_ctx *c, const char *name);
+int lpmb_field_alloc(lpmb_ctx *c, const char *name, FieldKind kind, FieldType type, int comps);
+int lpmb_ensure_staging(lpmb_ctx *c, size_t bytes);
+int lpmb_ensure_h_staging(lpmb_ctx *c, size_t bytes);
+template <typename T>
+static inline T *fptr(lpmb_ctx *c, const char *name)
+{
+    Field *f = lpmb_field(c, name);
+    return f ? reinterpret_cast<T *>(f->d) : nullptr;
+}
+static inline double param(lpmb_ctx *c, const char *name, double dflt = 0.0)
+{
+    auto it = c->params.find(name);
+    return it == c->params.end() ? dflt : it->second;
+}
+
+static inline int lpmb_blocks(long long work, int threads) { return (int)((work + threads - 1) / threads); }
+
+#define LPMB_LAUNCH_CHECK(c)                                                                   \
+    do {                                                                                       \
+        (c)->launches++;                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            lpmb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return LPMB_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+int lpmb_upload_soa_f64(lpmb_ctx *c, const double *host, double *d_dst, int comps);
+int lpmb_download_soa_f64(lpmb_ctx *c, const double *d_src, double *host, int comps);
+
+// solver-side entry points used across TUs
+int lpmb_cg_alloc(lpmb_ctx *c);
+int lpmb_matrix_alloc_values(lpmb_ctx *c);

@@ -1,0 +1,847 @@
+// lpmb_solver.cu -- block-sparse stiffness container (SELL-32, d x d blocks), SpMV and CG.
+//
+// Replaces solverCG() (reference src/solver.c:188-270: MKL RCI dcg + mkl_sparse_d_mv on the
+// symmetric-upper, 1-based scalar CSR that src/stiffness.c:441-515 fills) and the CSR container of
+// src/neighbor.c:114-134.
+//
+// Device format.  The block pattern is conn[][] (neighbor.c:84-112): block row i has nb_conn[i]
+// d x d blocks at block columns conn[i][0..nb_conn) (ascending).  Rows are grouped in slices of 32
+// (one warp); slice s is padded to the widest of its rows (w_s) and stored k-major:
+//     col[(sptr[s]+k)*32 + lane]                       int32 block column
+//     val[((sptr[s]+k)*d*d + (r*d+q))*32 + lane]       fp64, row r / column q of the block
+// so for every k a warp reads d*d fully coalesced 256-byte lines of values and one 128-byte line
+// of indices, and each lane owns one block row (no cross-lane reduction).  Padding entries carry
+// value 0 and the row's own column index.  Both triangles are stored (the reference stores the
+// upper one): algorithmic traffic per SpMV = nblk*(8 d^2+4) + 4(N+1) + 16 d N bytes.
+//
+// Vectors are component-major [d][Np] so the x-gather of 32 neighbouring block columns is three
+// contiguous 256-byte reads on a lattice ordering.
+#include <climits>
+
+#include "lpmb_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// pattern construction
+// ---------------------------------------------------------------------------------------------
+__global__ void conn_count_kernel(const int *__restrict__ conn, int N, int nconn, int *__restrict__ nbc, int *__restrict__ k0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    int n = 0, ge = 0;
+    for (int k = 0; k < nconn; k++) {
+        const int cidx = conn[(size_t)i * nconn + k];
+        if (cidx != -1) {
+            n++;
+            if (cidx >= i)
+                ge++;
+        }
+    }
+    nbc[i] = n;
+    k0[i] = ge;
+}
+
+__global__ void sell_fill_col_kernel(const int *__restrict__ conn, int N, int nconn, const int *__restrict__ nbc,
+                                     const long long *__restrict__ sptr, int nslices, int *__restrict__ col)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;  // padded row
+    const int s = row >> 5, lane = row & 31;
+    if (s >= nslices)
+        return;
+    const long long k0 = sptr[s], k1 = sptr[s + 1];
+    const int n = row < N ? nbc[row] : 0;
+    const int self = row < N ? row : 0;
+    for (long long k = k0; k < k1; k++) {
+        const int kk = (int)(k - k0);
+        col[k * 32 + lane] = kk < n ? conn[(size_t)row * nconn + kk] : self;
+    }
+}
+
+static int build_pattern(lpmb_ctx *c, const int *d_conn)
+{
+    SellMatrix &K = c->K;
+    const int N = c->N, Np = c->Np, D = c->dim;
+    cudaFree(K.sptr); cudaFree(K.col); cudaFree(K.val); cudaFree(K.nbc); cudaFree(K.k0); cudaFree(K.kp);
+    K.sptr = nullptr; K.col = nullptr; K.val = nullptr; K.nbc = nullptr; K.k0 = nullptr; K.kp = nullptr;
+    K.pattern_ready = K.values_ready = false;
+    K.nslices = Np / 32;
+    LPMB_CUDA(cudaMalloc(&K.nbc, (size_t)Np * sizeof(int)));
+    LPMB_CUDA(cudaMalloc(&K.k0, (size_t)Np * sizeof(int)));
+    LPMB_CUDA(cudaMemsetAsync(K.nbc, 0, (size_t)Np * sizeof(int), c->stream));
+    LPMB_CUDA(cudaMemsetAsync(K.k0, 0, (size_t)Np * sizeof(int), c->stream));
+    conn_count_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(d_conn, N, c->nconn, K.nbc, K.k0);
+    LPMB_LAUNCH_CHECK(c);
+    // prefix sums on the host (set-up only): slice offsets and the reference's K_pointer[i][1]
+    std::vector<int> h_nbc(Np), h_k0(Np);
+    LPMB_CUDA(cudaMemcpyAsync(h_nbc.data(), K.nbc, (size_t)Np * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaMemcpyAsync(h_k0.data(), K.k0, (size_t)Np * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<long long> h_sptr(K.nslices + 1), h_kp((size_t)N + 1);
+    long long acc = 0, nblk = 0;
+    for (int s = 0; s < K.nslices; s++) {
+        h_sptr[s] = acc;
+        int w = 0;
+        for (int l = 0; l < 32; l++) {
+            w = h_nbc[s * 32 + l] > w ? h_nbc[s * 32 + l] : w;
+            nblk += h_nbc[s * 32 + l];
+        }
+        acc += w;
+    }
+    h_sptr[K.nslices] = acc;
+    K.kunits = acc;
+    K.nblocks = nblk;
+    // K_pointer[i+1][1] = K_pointer[i][1] + dim*dim*K0 - (dim==3 ? 3 : 1)   (neighbor.c:126-129)
+    long long p = 0;
+    for (int i = 0; i < N; i++) {
+        h_kp[i] = p;
+        p += (long long)D * D * h_k0[i] - (D == 3 ? 3 : 1);
+    }
+    h_kp[N] = p;
+    K.nnz_upper = p;
+    LPMB_CUDA(cudaMalloc(&K.sptr, (size_t)(K.nslices + 1) * sizeof(long long)));
+    LPMB_CUDA(cudaMalloc(&K.kp, ((size_t)N + 1) * sizeof(long long)));
+    LPMB_CUDA(cudaMemcpyAsync(K.sptr, h_sptr.data(), (size_t)(K.nslices + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMemcpyAsync(K.kp, h_kp.data(), ((size_t)N + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMalloc(&K.col, (size_t)K.kunits * 32 * sizeof(int)));
+    sell_fill_col_kernel<<<lpmb_blocks(Np, 128), 128, 0, c->stream>>>(d_conn, N, c->nconn, K.nbc, K.sptr, K.nslices, K.col);
+    LPMB_LAUNCH_CHECK(c);
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    K.pattern_ready = true;
+    return LPMB_OK;
+}
+
+int lpmb_matrix_alloc_values(lpmb_ctx *c)
+{
+    SellMatrix &K = c->K;
+    LPMB_REQUIRE(K.pattern_ready, LPMB_ERR_STATE, "stiffness pattern not set (call lpmb_set_connectivity / lpmb_build_topology first)");
+    if (!K.val) {
+        const size_t bytes = (size_t)K.kunits * K.D * K.D * 32 * sizeof(double);
+        LPMB_CUDA(cudaMalloc(&K.val, bytes));
+        LPMB_CUDA(cudaMemsetAsync(K.val, 0, bytes, c->stream));
+    }
+    return LPMB_OK;
+}
+
+// device-resident conn (the O(N) topology builder hands its result over without a host trip)
+int lpmb_set_connectivity_device(lpmb_ctx *c, const int *d_conn) { return build_pattern(c, d_conn); }
+
+extern "C" int lpmb_set_connectivity(lpmb_ctx *c, const int *conn)
+{
+    LPMB_REQUIRE(c && conn, LPMB_ERR_ARG, "lpmb_set_connectivity: null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->N * c->nconn * sizeof(int);
+    LPMB_TRY(lpmb_ensure_staging(c, bytes));
+    LPMB_CUDA(cudaMemcpyAsync(c->staging, conn, bytes, cudaMemcpyHostToDevice, c->stream));
+    return build_pattern(c, (const int *)c->staging);
+}
+
+extern "C" int lpmb_csr_sizes(lpmb_ctx *c, long long *nnz_upper, long long *nblocks)
+{
+    LPMB_REQUIRE(c && c->K.pattern_ready, LPMB_ERR_STATE, "stiffness pattern not set");
+    if (nnz_upper)
+        *nnz_upper = c->K.nnz_upper;
+    if (nblocks)
+        *nblocks = c->K.nblocks;
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_get_k_pointer(lpmb_ctx *c, int *k_pointer)
+{
+    LPMB_REQUIRE(c && k_pointer && c->K.pattern_ready, LPMB_ERR_STATE, "stiffness pattern not set");
+    LPMB_REQUIRE(c->K.nnz_upper <= INT_MAX, LPMB_ERR_UNSUPPORTED, "nnz_upper=%lld does not fit the reference's 32-bit K_pointer", c->K.nnz_upper);
+    const int N = c->N;
+    std::vector<long long> kp((size_t)N + 1);
+    std::vector<int> k0(N);
+    LPMB_CUDA(cudaMemcpy(kp.data(), c->K.kp, ((size_t)N + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
+    LPMB_CUDA(cudaMemcpy(k0.data(), c->K.k0, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i <= N; i++) {
+        k_pointer[2 * i] = i < N ? k0[i] : 0;
+        k_pointer[2 * i + 1] = (int)kp[i];
+    }
+    return LPMB_OK;
+}
+
+extern "C" long long lpmb_spmv_bytes(lpmb_ctx *c)
+{
+    if (!c || !c->K.pattern_ready)
+        return 0;
+    const long long d = c->dim;
+    return c->K.nblocks * (8 * d * d + 4) + 4LL * (c->N + 1) + 16LL * d * c->N;
+}
+
+extern "C" long long lpmb_spmv_bytes_stored(lpmb_ctx *c)
+{
+    if (!c || !c->K.pattern_ready)
+        return 0;
+    const long long d = c->dim;
+    return c->K.kunits * 32 * (8 * d * d + 4) + 8LL * (c->K.nslices + 1) + 16LL * d * c->Np;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference CSR <-> SELL (Appendix B of SURVEY.md; stiffness.c:441-515, neighbor.c:114-130)
+//   row r of particle i starts at P_i + r*d*K0 - r(r-1)/2 and holds (d-r) diagonal-block entries
+//   followed by d entries per upper neighbour m=1..K0-1 at  start + m*d - r + q.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long row_start(long long P, int r, int D, int K0)
+{
+    return P + (long long)r * D * K0 - (long long)(r * (r - 1) / 2);
+}
+
+// position of block column `target` in (sorted) block row `row`, or -1
+__device__ __forceinline__ int find_in_row(const int *__restrict__ col, const long long *__restrict__ sptr, const int *__restrict__ nbc,
+                                           int row, int target)
+{
+    const long long base = sptr[row >> 5] * 32 + (row & 31);
+    int lo = 0, hi = nbc[row] - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = col[base + (long long)mid * 32];
+        if (v == target)
+            return mid;
+        if (v < target)
+            lo = mid + 1;
+        else
+            hi = mid - 1;
+    }
+    return -1;
+}
+
+template <int D>
+__global__ void csr_upper_to_sell_kernel(const double *__restrict__ Kg, const long long *__restrict__ kp, const int *__restrict__ k0,
+                                         const int *__restrict__ nbc, const long long *__restrict__ sptr, const int *__restrict__ col,
+                                         double *__restrict__ val, int N, int nslices)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = row >> 5, lane = row & 31;
+    if (s >= nslices)
+        return;
+    const long long ka = sptr[s], kb = sptr[s + 1];
+    const int n = row < N ? nbc[row] : 0;
+    const int K0i = row < N ? k0[row] : 0;
+    const long long Pi = row < N ? kp[row] : 0;
+    const int first_ge = n - K0i;  // index of the self block within the row
+    for (long long k = ka; k < kb; k++) {
+        const int kk = (int)(k - ka);
+        double b[D * D];
+#pragma unroll
+        for (int e = 0; e < D * D; e++)
+            b[e] = 0.0;
+        if (kk < n) {
+            const int cidx = col[k * 32 + lane];
+            if (cidx == row) {
+#pragma unroll
+                for (int r = 0; r < D; r++)
+#pragma unroll
+                    for (int q = 0; q < D; q++) {
+                        const int lo = r < q ? r : q, hi = r < q ? q : r;
+                        b[r * D + q] = Kg[row_start(Pi, lo, D, K0i) + (hi - lo)];
+                    }
+            } else if (cidx > row) {
+                const int m = kk - first_ge;
+#pragma unroll
+                for (int r = 0; r < D; r++)
+#pragma unroll
+                    for (int q = 0; q < D; q++)
+                        b[r * D + q] = Kg[row_start(Pi, r, D, K0i) + (long long)m * D - r + q];
+            } else {
+                // transpose of block (cidx,row) stored with particle cidx
+                const int pos = find_in_row(col, sptr, nbc, cidx, row);
+                const int K0c = k0[cidx];
+                const int m = pos - (nbc[cidx] - K0c);
+                const long long Pc = kp[cidx];
+#pragma unroll
+                for (int r = 0; r < D; r++)
+#pragma unroll
+                    for (int q = 0; q < D; q++)
+                        b[r * D + q] = Kg[row_start(Pc, q, D, K0c) + (long long)m * D - q + r];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < D * D; e++)
+            val[(k * D * D + e) * 32 + lane] = b[e];
+    }
+}
+
+template <int D>
+__global__ void sell_to_csr_upper_kernel(const double *__restrict__ val, const long long *__restrict__ kp, const int *__restrict__ k0,
+                                         const int *__restrict__ nbc, const long long *__restrict__ sptr, const int *__restrict__ col,
+                                         double *__restrict__ Kg, int *__restrict__ JK, int *__restrict__ IK, int N)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N)
+        return;
+    const int s = row >> 5, lane = row & 31;
+    const long long ka = sptr[s];
+    const int n = nbc[row], K0i = k0[row];
+    const long long Pi = kp[row];
+    const int first_ge = n - K0i;
+    if (IK) {
+#pragma unroll
+        for (int r = 0; r < D; r++)
+            IK[D * row + r] = (int)(row_start(Pi, r, D, K0i) + 1);
+        if (row == N - 1)
+            IK[D * N] = (int)(kp[N] + 1);
+    }
+    for (int kk = first_ge; kk < n; kk++) {
+        const long long k = ka + kk;
+        const int cidx = col[k * 32 + lane];
+        const int m = kk - first_ge;
+#pragma unroll
+        for (int r = 0; r < D; r++)
+#pragma unroll
+            for (int q = 0; q < D; q++) {
+                long long off;
+                if (m == 0) {
+                    if (q < r)
+                        continue;
+                    off = row_start(Pi, r, D, K0i) + (q - r);
+                } else {
+                    off = row_start(Pi, r, D, K0i) + (long long)m * D - r + q;
+                }
+                if (Kg)
+                    Kg[off] = val[(k * D * D + r * D + q) * 32 + lane];
+                if (JK)
+                    JK[off] = D * cidx + q + 1;
+            }
+    }
+}
+
+extern "C" int lpmb_matrix_from_upper_csr(lpmb_ctx *c, const double *K_global, long long nnz)
+{
+    LPMB_REQUIRE(c && K_global, LPMB_ERR_ARG, "lpmb_matrix_from_upper_csr: null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_TRY(lpmb_matrix_alloc_values(c));
+    SellMatrix &K = c->K;
+    LPMB_REQUIRE(nnz == K.nnz_upper, LPMB_ERR_ARG, "K_global has %lld entries, connectivity implies %lld", nnz, K.nnz_upper);
+    LPMB_TRY(lpmb_ensure_staging(c, (size_t)nnz * sizeof(double)));
+    LPMB_CUDA(cudaMemcpyAsync(c->staging, K_global, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int blocks = lpmb_blocks(c->Np, 128);
+    if (c->dim == 3)
+        csr_upper_to_sell_kernel<3><<<blocks, 128, 0, c->stream>>>((const double *)c->staging, K.kp, K.k0, K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
+    else
+        csr_upper_to_sell_kernel<2><<<blocks, 128, 0, c->stream>>>((const double *)c->staging, K.kp, K.k0, K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
+    LPMB_LAUNCH_CHECK(c);
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    K.values_ready = true;
+    return LPMB_OK;
+}
+
+// K_ij = -(1 + ((i+j) & 7)/8) * [[1,.1,.2],[.1,1,.3],[.2,.3,1]] off the diagonal, diagonal block 80*I: symmetric,
+// strictly diagonally dominant (<= 61 blocks per row), so CG on it converges.
+template <int D>
+__global__ void fill_test_pattern_kernel(const int *__restrict__ nbc, const long long *__restrict__ sptr, const int *__restrict__ col,
+                                         double *__restrict__ val, int N, int nslices)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = row >> 5, lane = row & 31;
+    if (s >= nslices)
+        return;
+    const long long ka = sptr[s], kb = sptr[s + 1];
+    const int n = row < N ? nbc[row] : 0;
+    for (long long k = ka; k < kb; k++) {
+        const int kk = (int)(k - ka);
+        const int cidx = col[k * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < D; r++)
+#pragma unroll
+            for (int q = 0; q < D; q++) {
+                double v = 0.0;
+                if (kk < n) {
+                    if (cidx == row)
+                        v = (r == q) ? 80.0 * D : 0.0;
+                    else {
+                        const double base = (r == q) ? 1.0 : 0.1 * (r + q);
+                        v = -(1.0 + (double)((row + cidx) & 7) / 8.0) * base;
+                    }
+                }
+                val[(k * D * D + r * D + q) * 32 + lane] = v;
+            }
+    }
+}
+
+extern "C" int lpmb_matrix_fill_test_pattern(lpmb_ctx *c)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_TRY(lpmb_matrix_alloc_values(c));
+    SellMatrix &K = c->K;
+    const int blocks = lpmb_blocks(c->Np, 128);
+    if (c->dim == 3)
+        fill_test_pattern_kernel<3><<<blocks, 128, 0, c->stream>>>(K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
+    else
+        fill_test_pattern_kernel<2><<<blocks, 128, 0, c->stream>>>(K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
+    LPMB_LAUNCH_CHECK(c);
+    K.values_ready = true;
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_matrix_to_upper_csr(lpmb_ctx *c, double *K_global, int *IK, int *JK)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    SellMatrix &K = c->K;
+    LPMB_REQUIRE(K.pattern_ready, LPMB_ERR_STATE, "stiffness pattern not set");
+    LPMB_REQUIRE(!K_global || K.values_ready, LPMB_ERR_STATE, "stiffness values not computed yet");
+    LPMB_REQUIRE(K.nnz_upper <= INT_MAX, LPMB_ERR_UNSUPPORTED,
+                 "nnz_upper=%lld exceeds the reference's 32-bit IK/JK; keep the matrix on the device", K.nnz_upper);
+    const size_t nnz = (size_t)K.nnz_upper, n = (size_t)c->dim * c->N;
+    const size_t bytes = nnz * 8 + nnz * 4 + (n + 1) * 4 + 64;
+    LPMB_TRY(lpmb_ensure_staging(c, bytes));
+    double *dK = (double *)c->staging;
+    int *dJK = (int *)((char *)c->staging + nnz * 8);
+    int *dIK = dJK + nnz;
+    const int blocks = lpmb_blocks(c->N, 128);
+    if (c->dim == 3)
+        sell_to_csr_upper_kernel<3><<<blocks, 128, 0, c->stream>>>(K.val, K.kp, K.k0, K.nbc, K.sptr, K.col, K_global ? dK : nullptr, JK ? dJK : nullptr, IK ? dIK : nullptr, c->N);
+    else
+        sell_to_csr_upper_kernel<2><<<blocks, 128, 0, c->stream>>>(K.val, K.kp, K.k0, K.nbc, K.sptr, K.col, K_global ? dK : nullptr, JK ? dJK : nullptr, IK ? dIK : nullptr, c->N);
+    LPMB_LAUNCH_CHECK(c);
+    if (K_global)
+        LPMB_CUDA(cudaMemcpyAsync(K_global, dK, nnz * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (JK)
+        LPMB_CUDA(cudaMemcpyAsync(JK, dJK, nnz * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (IK)
+        LPMB_CUDA(cudaMemcpyAsync(IK, dIK, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    return LPMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMV
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (fixed shuffle tree, fixed warp order); result valid in thread 0.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *smem /* >= THREADS/32 */)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0)
+        smem[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; i++)
+            t += smem[i];
+    }
+    return t;
+}
+
+// Every block reduces the same `n` partial sums in the same order -> identical value in every block.
+template <int THREADS>
+__device__ __forceinline__ double reduce_partials(const double *__restrict__ part, int n, double *smem)
+{
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += THREADS)
+        v += part[i];
+    double t = block_sum<THREADS>(v, smem);
+    __shared__ double bcast;
+    if (threadIdx.x == 0)
+        bcast = t;
+    __syncthreads();
+    return bcast;
+}
+
+// scalars kept on the device between CG kernels
+enum { S_RR0 = 0, S_RR1 = 1, S_THRESH = 2, S_PAP = 3, S_ALPHA = 4, S_BETA = 5, S_ITER = 6, S_DONE = 7, S_RRINIT = 8, S_COUNT = 16 };
+
+#define SPMV_THREADS 128
+
+// y = [mask .*] (K x); optionally partial[blockIdx] = sum over this block's rows of x.y
+// Warp per slice, lane per block row; grid-stride over slices.
+template <int D, bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_sell_kernel(int nslices, const long long *__restrict__ sptr, const int *__restrict__ col, const double *__restrict__ val,
+                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ mask, int Np,
+                 double *__restrict__ partials, const double *__restrict__ scal)
+{
+    __shared__ double red[SPMV_THREADS / 32];
+    if (DOT && scal && scal[S_DONE] != 0.0)
+        return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * SPMV_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * SPMV_THREADS) >> 5;
+    double dot = 0.0;
+    for (int s = warp; s < nslices; s += nwarps) {
+        const long long ka = sptr[s], kb = sptr[s + 1];
+        double acc[D];
+#pragma unroll
+        for (int r = 0; r < D; r++)
+            acc[r] = 0.0;
+        const int *cp = col + ka * 32 + lane;
+        const double *vp = val + ka * (D * D * 32) + lane;
+#pragma unroll 2
+        for (long long k = ka; k < kb; k++, cp += 32, vp += D * D * 32) {
+            const int cidx = __ldcs(cp);
+            double a[D * D];
+#pragma unroll
+            for (int e = 0; e < D * D; e++)
+                a[e] = __ldcs(vp + e * 32);
+            double xv[D];
+#pragma unroll
+            for (int q = 0; q < D; q++)
+                xv[q] = __ldg(x + (size_t)q * Np + cidx);
+#pragma unroll
+            for (int r = 0; r < D; r++)
+#pragma unroll
+                for (int q = 0; q < D; q++)
+                    acc[r] = fma(a[r * D + q], xv[q], acc[r]);
+        }
+        const int row = s * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < D; r++) {
+            double v = acc[r];
+            if (mask)
+                v *= mask[(size_t)r * Np + row];
+            y[(size_t)r * Np + row] = v;
+            if (DOT)
+                dot = fma(v, x[(size_t)r * Np + row], dot);
+        }
+    }
+    if (DOT) {
+        const double t = block_sum<SPMV_THREADS>(dot, red);
+        if (threadIdx.x == 0)
+            partials[blockIdx.x] = t;
+    }
+}
+
+static int spmv_grid(lpmb_ctx *c)
+{
+    // persistent-ish: at most 16 CTAs of 4 warps per SM, never more CTAs than slices/4
+    const int want = (c->K.nslices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
+    const int cap = c->sm_count * 16;
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+static int launch_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, bool use_mask)
+{
+    SellMatrix &K = c->K;
+    const int grid = spmv_grid(c);
+    const double *m = use_mask ? c->mask : nullptr;
+    if (c->dim == 3) {
+        if (dot)
+            spmv_sell_kernel<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
+        else
+            spmv_sell_kernel<3, false><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, nullptr, nullptr);
+    } else {
+        if (dot)
+            spmv_sell_kernel<2, true><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
+        else
+            spmv_sell_kernel<2, false><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, nullptr, nullptr);
+    }
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CG vector kernels (fused, deterministic two-stage reductions, scalars stay on the device)
+// ---------------------------------------------------------------------------------------------
+#define VEC_THREADS 256
+
+// r = [mask .*] b ; p = r ; x = 0 ; partials = r.r
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_init_kernel(const double *__restrict__ b, const double *__restrict__ mask, double *__restrict__ r, double *__restrict__ p,
+               double *__restrict__ x, size_t n, double *__restrict__ partials)
+{
+    __shared__ double red[VEC_THREADS / 32];
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VEC_THREADS) {
+        double v = b[i];
+        if (mask)
+            v *= mask[i];
+        r[i] = v;
+        p[i] = v;
+        x[i] = 0.0;
+        s = fma(v, v, s);
+    }
+    const double t = block_sum<VEC_THREADS>(s, red);
+    if (threadIdx.x == 0)
+        partials[blockIdx.x] = t;
+}
+
+// rr0 = sum partials; threshold = rel*rr0 + abs (MKL: dpar[3] = dpar[0]*dpar[2] + dpar[1], squared norms)
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_init_scalars_kernel(const double *__restrict__ partials, int nparts, double rel, double abs_tol, double *__restrict__ scal)
+{
+    __shared__ double red[VEC_THREADS / 32];
+    const double rr = reduce_partials<VEC_THREADS>(partials, nparts, red);
+    if (threadIdx.x == 0) {
+        scal[S_RR0] = rr;
+        scal[S_RR1] = rr;
+        scal[S_RRINIT] = rr;
+        scal[S_THRESH] = rel * rr + abs_tol;
+        scal[S_ITER] = 0.0;
+        scal[S_DONE] = (rr <= rel * rr + abs_tol) ? 1.0 : 0.0;
+        scal[S_PAP] = scal[S_ALPHA] = scal[S_BETA] = 0.0;
+    }
+}
+
+// alpha = rr/pAp ; x += alpha p ; r -= alpha Ap ; partials_rr = r.r
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_update_kernel(const double *__restrict__ p, const double *__restrict__ ap, double *__restrict__ x, double *__restrict__ r, size_t n,
+                 const double *__restrict__ partials_pap, int nparts_pap, double *__restrict__ partials_rr, double *__restrict__ scal,
+                 int parity)
+{
+    __shared__ double red[VEC_THREADS / 32];
+    if (scal[S_DONE] != 0.0)
+        return;
+    const double pap = reduce_partials<VEC_THREADS>(partials_pap, nparts_pap, red);
+    const double alpha = scal[S_RR0 + parity] / pap;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VEC_THREADS) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double rv = fma(-alpha, ap[i], r[i]);
+        r[i] = rv;
+        s = fma(rv, rv, s);
+    }
+    const double t = block_sum<VEC_THREADS>(s, red);
+    if (threadIdx.x == 0) {
+        partials_rr[blockIdx.x] = t;
+        if (blockIdx.x == 0) {
+            scal[S_PAP] = pap;
+            scal[S_ALPHA] = alpha;
+        }
+    }
+}
+
+// rr' = sum partials ; iter++ ; stop test rr' <= threshold (solver.c:218,221-222) or iter >= maxit ;
+// beta = rr'/rr ; p = r + beta p
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_direction_kernel(const double *__restrict__ r, double *__restrict__ p, size_t n, const double *__restrict__ partials_rr, int nparts,
+                    double *__restrict__ scal, int parity, int maxit)
+{
+    __shared__ double red[VEC_THREADS / 32];
+    if (scal[S_DONE] != 0.0)
+        return;
+    const double rr_new = reduce_partials<VEC_THREADS>(partials_rr, nparts, red);
+    const double rr_old = scal[S_RR0 + parity];
+    const double iter = scal[S_ITER] + 1.0;
+    const bool conv = rr_new <= scal[S_THRESH];
+    const bool stop = conv || iter >= (double)maxit;
+    // all blocks have read the scalars they need before block 0 may overwrite them
+    // (S_RR0+parity / S_ITER / S_DONE are only written below, after every read above in this
+    // block; other blocks read S_ITER/S_DONE possibly after this write -> write into the
+    // *other* parity slot and keep S_ITER/S_DONE updates for a trailing single-block kernel)
+    if (!stop) {
+        const double beta = rr_new / rr_old;
+        for (size_t i = (size_t)blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VEC_THREADS)
+            p[i] = fma(beta, p[i], r[i]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        scal[S_RR0 + (parity ^ 1)] = rr_new;
+}
+
+// single-thread bookkeeping after the direction kernel: iteration counter, stop flag, beta
+__global__ void cg_bookkeep_kernel(double *__restrict__ scal, int parity, int maxit)
+{
+    if (scal[S_DONE] != 0.0)
+        return;
+    const double rr_new = scal[S_RR0 + (parity ^ 1)], rr_old = scal[S_RR0 + parity];
+    const double iter = scal[S_ITER] + 1.0;
+    scal[S_ITER] = iter;
+    scal[S_BETA] = rr_new / rr_old;
+    if (rr_new <= scal[S_THRESH])
+        scal[S_DONE] = 1.0;
+    else if (iter >= (double)maxit)
+        scal[S_DONE] = 2.0;
+}
+
+__global__ void __launch_bounds__(VEC_THREADS)
+axpy_xyz_kernel(const double *__restrict__ disp, double *__restrict__ xyz, int dim, int Np)
+{
+    const size_t n = (size_t)dim * Np;
+    for (size_t i = (size_t)blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VEC_THREADS)
+        xyz[i] += disp[i];
+}
+
+int lpmb_cg_alloc(lpmb_ctx *c)
+{
+    CGWork &w = c->cg;
+    if (w.r)
+        return LPMB_OK;
+    const size_t n = (size_t)c->dim * c->Np;
+    LPMB_CUDA(cudaMalloc(&w.r, n * 8));
+    LPMB_CUDA(cudaMalloc(&w.p, n * 8));
+    LPMB_CUDA(cudaMalloc(&w.ap, n * 8));
+    LPMB_CUDA(cudaMalloc(&w.x, n * 8));
+    LPMB_CUDA(cudaMemsetAsync(w.r, 0, n * 8, c->stream));
+    LPMB_CUDA(cudaMemsetAsync(w.p, 0, n * 8, c->stream));
+    LPMB_CUDA(cudaMemsetAsync(w.ap, 0, n * 8, c->stream));
+    LPMB_CUDA(cudaMemsetAsync(w.x, 0, n * 8, c->stream));
+    w.max_blocks = c->sm_count * 16;
+    LPMB_CUDA(cudaMalloc(&w.partials, (size_t)2 * w.max_blocks * 8));
+    LPMB_CUDA(cudaMalloc(&w.scal, S_COUNT * 8));
+    LPMB_CUDA(cudaMemsetAsync(w.scal, 0, S_COUNT * 8, c->stream));
+    LPMB_CUDA(cudaMallocHost(&w.h_scal, S_COUNT * 8));
+    return LPMB_OK;
+}
+
+static int vec_grid(lpmb_ctx *c, size_t n)
+{
+    const long long want = (long long)((n + VEC_THREADS - 1) / VEC_THREADS);
+    const int cap = c->sm_count * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// CG on device vectors: b (component-major [dim][Np]) -> c->cg.x.  Mirrors solver.c:209-255.
+static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, int maxit, bool use_mask, int *iterations)
+{
+    CGWork &w = c->cg;
+    const size_t n = (size_t)c->dim * c->Np;
+    const int vg = vec_grid(c, n), sg = spmv_grid(c);
+    double *part_a = w.partials, *part_b = w.partials + w.max_blocks;
+    const double *m = use_mask ? c->mask : nullptr;
+    cg_init_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(d_b, m, w.r, w.p, w.x, n, part_a);
+    LPMB_LAUNCH_CHECK(c);
+    cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, rel, abs_tol, w.scal);
+    LPMB_LAUNCH_CHECK(c);
+    const int batch = 16;
+    int parity = 0, issued = 0;
+    for (;;) {
+        for (int b = 0; b < batch && issued < maxit; b++, issued++) {
+            LPMB_TRY(launch_spmv(c, w.p, w.ap, true, use_mask));  // partials -> part_a (w.partials)
+            cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, part_a, sg, part_b, w.scal, parity);
+            LPMB_LAUNCH_CHECK(c);
+            cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, part_b, vg, w.scal, parity, maxit);
+            LPMB_LAUNCH_CHECK(c);
+            cg_bookkeep_kernel<<<1, 1, 0, c->stream>>>(w.scal, parity, maxit);
+            LPMB_LAUNCH_CHECK(c);
+            parity ^= 1;
+        }
+        LPMB_CUDA(cudaMemcpyAsync(w.h_scal, w.scal, S_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (w.h_scal[S_DONE] != 0.0 || issued >= maxit)
+            break;
+    }
+    if (iterations)
+        *iterations = (int)w.h_scal[S_ITER];
+    return w.h_scal[S_DONE] == 1.0 ? LPMB_OK : LPMB_ERR_NOTCONVERGED;
+}
+
+__global__ void mask_build_kernel(const int *__restrict__ bc, const int *__restrict__ fix, double *__restrict__ mask, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const bool constrained = (bc && bc[i] == 0) || (fix && fix[i] == 0);  // boundary.c:182,214,247
+        mask[i] = constrained ? 0.0 : 1.0;
+    }
+}
+
+// mask from the device fields dispBC_index / fix_index
+int lpmb_refresh_mask(lpmb_ctx *c)
+{
+    const size_t n = (size_t)c->dim * c->Np;
+    if (!c->mask)
+        LPMB_CUDA(cudaMalloc(&c->mask, n * 8));
+    const int *bc = fptr<int>(c, "dispBC_index"), *fix = fptr<int>(c, "fix_index");
+    LPMB_REQUIRE(bc && fix, LPMB_ERR_STATE, "BC index fields missing");
+    mask_build_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(bc, fix, c->mask, n);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_set_dof_mask(lpmb_ctx *c, const int *dispBC_index, const int *fix_index)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->dim * c->N;
+    if (dispBC_index)
+        LPMB_TRY(lpmb_field_set(c, "dispBC_index", dispBC_index, n));
+    if (fix_index)
+        LPMB_TRY(lpmb_field_set(c, "fix_index", fix_index, n));
+    return lpmb_refresh_mask(c);
+}
+
+extern "C" int lpmb_solve_cg_device(lpmb_ctx *c, double rel, double abs_tol, int maxit, int use_mask, int update_xyz, int *iterations)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
+    LPMB_REQUIRE(!use_mask || c->mask, LPMB_ERR_STATE, "DoF mask requested but not set");
+    LPMB_TRY(lpmb_cg_alloc(c));
+    const double *b = fptr<double>(c, "residual");
+    double *disp = fptr<double>(c, "disp");
+    LPMB_REQUIRE(b && disp, LPMB_ERR_STATE, "residual/disp fields missing");
+    const int rc = cg_run(c, b, rel, abs_tol, maxit, use_mask != 0, iterations);
+    if (rc != LPMB_OK && rc != LPMB_ERR_NOTCONVERGED)
+        return rc;
+    const size_t n = (size_t)c->dim * c->Np;
+    LPMB_CUDA(cudaMemcpyAsync(disp, c->cg.x, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (update_xyz) {
+        // xyz[i][j] += disp[dim*i+j], j < dim (solver.c:263-267); xyz is [3][Np], disp is [dim][Np]
+        axpy_xyz_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(disp, fptr<double>(c, "xyz"), c->dim, c->Np);
+        LPMB_LAUNCH_CHECK(c);
+    }
+    return rc;
+}
+
+extern "C" int lpmb_solve_cg(lpmb_ctx *c, const double *rhs, double *disp, double rel, double abs_tol, int maxit, int use_mask,
+                             int *iterations)
+{
+    LPMB_REQUIRE(c && rhs && disp, LPMB_ERR_ARG, "lpmb_solve_cg: null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->dim * c->N;
+    LPMB_TRY(lpmb_field_set(c, "residual", rhs, n));
+    const int rc = lpmb_solve_cg_device(c, rel, abs_tol, maxit, use_mask, 0, iterations);
+    if (rc != LPMB_OK && rc != LPMB_ERR_NOTCONVERGED)
+        return rc;
+    LPMB_TRY(lpmb_field_get(c, "disp", disp, n));
+    return rc;
+}
+
+extern "C" int lpmb_spmv_host(lpmb_ctx *c, const double *x, double *y)
+{
+    LPMB_REQUIRE(c && x && y, LPMB_ERR_ARG, "lpmb_spmv_host: null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
+    LPMB_TRY(lpmb_cg_alloc(c));
+    LPMB_TRY(lpmb_upload_soa_f64(c, x, c->cg.p, c->dim));
+    LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
+    LPMB_TRY(lpmb_download_soa_f64(c, c->cg.ap, y, c->dim));
+    return LPMB_OK;
+}
+
+__global__ void fill_sin_kernel(double *__restrict__ x, int dim, int N, int Np)
+{
+    // x_k = sin(1e-3 k) on the interleaved DoF index k = dim*i + comp
+    const size_t n = (size_t)dim * Np;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int comp = (int)(e / Np), i = (int)(e % Np);
+        x[e] = i < N ? sin(1e-3 * (double)((size_t)dim * i + comp)) : 0.0;
+    }
+}
+
+extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_per_spmv)
+{
+    LPMB_REQUIRE(c && reps > 0 && ms_per_spmv, LPMB_ERR_ARG, "lpmb_spmv_bench: bad argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
+    LPMB_REQUIRE(variant == 0, LPMB_ERR_ARG, "unknown SpMV variant %d", variant);
+    LPMB_TRY(lpmb_cg_alloc(c));
+    fill_sin_kernel<<<vec_grid(c, (size_t)c->dim * c->Np), VEC_THREADS, 0, c->stream>>>(c->cg.p, c->dim, c->N, c->Np);
+    LPMB_LAUNCH_CHECK(c);
+    cudaEvent_t e0, e1;
+    LPMB_CUDA(cudaEventCreate(&e0));
+    LPMB_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; i++)
+        LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
+    LPMB_CUDA(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < reps; i++)
+        LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
+    LPMB_CUDA(cudaEventRecord(e1, c->stream));
+    LPMB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LPMB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_spmv = (double)ms / reps;
+    return LPMB_OK;
+}

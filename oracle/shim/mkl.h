@@ -104,6 +104,8 @@ int lpmb_shim_get_threads(void);
 long lpmb_shim_spmv_calls(void);
 double lpmb_shim_spmv_seconds(void);
 void lpmb_shim_reset_counters(void);
+/* iteration count reported by the most recent dcg_get() (solver.c:253) */
+int lpmb_shim_last_itercount(void);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,8 @@
 static int g_threads = 1;
 static long g_spmv_calls = 0;
 static double g_spmv_seconds = 0.0;
+static int g_last_itercount = -1;
+int lpmb_shim_last_itercount(void) { return g_last_itercount; }
 
 void lpmb_shim_set_threads(int threads) { g_threads = threads < 1 ? 1 : threads; }
 int lpmb_shim_get_threads(void) { return g_threads; }
@@ -430,6 +432,7 @@ void dcg_get(const MKL_INT *n, const double *x, const double *b, const MKL_INT *
     (void)dpar;
     (void)tmp;
     *itercount = ipar[3];
+    g_last_itercount = ipar[3];
 }
 
 /* ---------------------------------------------------------------- PARDISO */

@@ -1,0 +1,126 @@
+"""GPU parity: stiffness container, SpMV and CG (lpmb_solver.cu) against the oracle.
+
+Reference path: solverCG(), src/solver.c:188-270, on the symmetric-upper 1-based CSR that
+src/stiffness.c:441-515 fills.  Tolerances (fp64): container round trip bit-exact; SpMV 1e-13
+relative; CG same iteration count and disp within 1e-10 relative (north_star asks 1e-9).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def full_from_upper(K, IK, JK, n):
+    U = sp.csr_matrix((K, JK - 1, IK - 1), shape=(n, n))
+    return (U + sp.triu(U, 1).T).tocsr()
+
+
+@pytest.fixture(scope="module")
+def ctx6(lpm, golden):
+    c = lpm.Context(216, 3, 2, 18, 61)
+    c.set_connectivity(golden["setup.conn"])
+    yield c
+    c.close()
+
+
+def test_csr_layout_bit_exact(ctx6, golden):
+    """K_pointer / IK / JK reproduce neighbor.c:114-130 + stiffness.c:486-515 exactly"""
+    nnz, nblk = ctx6.csr_sizes()
+    assert nnz == int(golden["setup.K_pointer"][-1, 1])
+    assert nblk == int(golden["setup.nb_conn"].sum())
+    assert np.array_equal(ctx6.k_pointer(), golden["setup.K_pointer"])
+    ctx6.matrix_from_upper_csr(golden["s1.fd.K_global"])
+    K, IK, JK = ctx6.matrix_to_upper_csr()
+    assert np.array_equal(IK, golden["s1.fd.IK"])
+    assert np.array_equal(JK, golden["s1.fd.JK"])
+    assert np.array_equal(K, golden["s1.fd.K_global"])  # import -> SELL -> export is lossless
+
+
+def test_spmv_matches_reference_matrix(ctx6, golden):
+    Kbc = golden["s1.n0.K_bc"]
+    ctx6.matrix_from_upper_csr(Kbc)
+    A = full_from_upper(Kbc, golden["s1.fd.IK"], golden["s1.fd.JK"], 648)
+    rng = np.random.default_rng(20240607)
+    for _ in range(3):
+        x = rng.standard_normal(648)
+        y = ctx6.spmv(x)
+        yr = A @ x
+        assert np.abs(y - yr).max() <= 1e-13 * np.abs(yr).max()
+
+
+@pytest.mark.parametrize("tag", ["s1.n0", "s1.n1", "s1.n2", "s2.n0"])
+def test_cg_matches_reference_solve(ctx6, golden, tag):
+    """same K (BC-modified by the reference's boundary.c), same rhs -> same iteration count, same disp"""
+    ctx6.matrix_from_upper_csr(golden[f"{tag}.K_bc"])
+    x, iters, ok = ctx6.solve_cg(golden[f"{tag}.rhs"])
+    assert ok
+    assert iters == int(golden[f"{tag}.cg_iters"][0])
+    ref = golden[f"{tag}.disp"]
+    assert np.linalg.norm(x - ref) <= 1e-10 * np.linalg.norm(ref)
+
+
+def test_masked_cg_equals_bc_modified_matrix(ctx6, golden):
+    """DoF masking inside the solve == the reference's row/column zeroing + norm_diag on the diagonal
+    (boundary.c:159-281): constrained DoFs never enter the Krylov space (rhs 0, x0 = 0)."""
+    ctx6.matrix_from_upper_csr(golden["s1.fd.K_global"])          # un-modified tangent
+    ctx6.set_dof_mask(golden["s1.bc.dispBC_index"], golden["s1.bc.fix_index"])
+    x, iters, ok = ctx6.solve_cg(golden["s1.rr.residual"], use_mask=True)
+    assert ok and iters == int(golden["s1.n0.cg_iters"][0])
+    ref = golden["s1.n0.disp"]
+    assert np.linalg.norm(x - ref) <= 1e-10 * np.linalg.norm(ref)
+    assert np.all(x[golden["s1.bc.dispBC_index"] == 0] == 0.0)
+
+
+def test_cg_zero_rhs_and_maxit(ctx6, golden):
+    ctx6.matrix_from_upper_csr(golden["s1.n0.K_bc"])
+    x, iters, ok = ctx6.solve_cg(np.zeros(648))
+    assert ok and iters == 0 and not x.any()
+    x, iters, ok = ctx6.solve_cg(golden["s1.n0.rhs"], maxit=5)
+    assert not ok and iters == 5
+
+
+def test_default_case_solves_like_reference(lpm, ref_c1):
+    """C1 (21^3, n=27 783, nnz_upper=2 203 713): 80 then 106 CG iterations"""
+    r = ref_c1["ref"]
+    L = r.lib
+    c = lpm.Context(r.N, 3, 2, 18, 61)
+    c.set_connectivity(r.get("conn"))
+    for expect in (80, 106):
+        L.switchStateV(0)
+        L.setDispBC_stiffnessUpdate3D()
+        Kbc, rhs = r.get("K_global"), r.get("residual")
+        c.matrix_from_upper_csr(Kbc)
+        x, iters, ok = c.solve_cg(rhs)
+        L.solverCG()
+        assert ok and iters == expect == L.lpmb_shim_last_itercount()
+        ref = r.get("disp")
+        assert np.linalg.norm(x - ref) <= 1e-10 * np.linalg.norm(ref)
+        L.computeBondForceGeneral(0, 1)
+        L.updateRR()
+    c.close()
+
+
+def test_large_lattice_properties(lpm):
+    """size-independent properties at 64^3 (262 144 particles): symmetry x.(Ky) = y.(Kx), linearity,
+    and CG residual ||b - Kx|| <= 1.01e-4 ||b|| on the SPD test pattern"""
+    lat = lpm.lattice.sc_block(64)
+    N = lat["xyz"].shape[0]
+    c = lpm.Context(N, 3, 2, 18, 61)
+    c.set_connectivity(lat["conn"])
+    nnz, nblk = c.csr_sizes()
+    assert nblk == int(lat["nb_conn"].sum())
+    assert nnz == int(lpm.lattice.k_pointer(lat["conn"], 3)[-1, 1])
+    c.fill_test_pattern()
+    rng = np.random.default_rng(20240607)
+    x, y = rng.standard_normal(3 * N), rng.standard_normal(3 * N)
+    Kx, Ky = c.spmv(x), c.spmv(y)
+    assert abs(x @ Ky - y @ Kx) <= 1e-12 * abs(x @ Ky)
+    Kxy = c.spmv(2.0 * x - 3.0 * y)
+    assert np.abs(Kxy - (2.0 * Kx - 3.0 * Ky)).max() <= 1e-11 * np.abs(Kxy).max()
+    b = rng.standard_normal(3 * N)
+    sol, iters, ok = c.solve_cg(b)
+    assert ok and 0 < iters < 200
+    r = b - c.spmv(sol)
+    assert np.linalg.norm(r) <= 1.01e-4 * np.linalg.norm(b)
+    c.close()
