@@ -1,0 +1,870 @@
+// lpmb_bond.cu -- bond-wise constitutive update (compiled with -fmad=false: strict IEEE, so every
+// + - * / sqrt reproduces the reference's gcc -ffp-contract=off evaluation bit for bit).
+//
+// Replaces, in the reference:
+//   computeBondForceGeneral(plmode,t)        src/constitutive.c:88-146   (dispatch + computeStress + switchStateV(2))
+//   computeBondForceElastic(ii)              src/constitutive.c:228-283  (plmode 6)
+//   computeBondForceIncrementalUpdating(ii)  src/constitutive.c:167-225  (plmode 4, predictor)
+//   computeBondForceJ2mixedLinear3D(ii)      src/constitutive.c:466-686  (plmode 0)
+//   computeStress()                          src/lpm_basic.c:53-125
+//   computedL()                              src/lpm_basic.c:252-291
+//   switchStateV(flag)                       src/constitutive.c:10-85
+//   updateRR()                               src/stiffness.c:519-534
+//   updateCrack()                            src/constitutive.c:1399-1434
+//
+// Structure.  The reference evaluates, for every particle ii, the geometry / return map of ii AND
+// of each of its neighbours (19x redundant); each of those evaluations is a pure function of the
+// slot-[0] state and xyz, so here every particle is evaluated once, in passes:
+//   geometry -> [return map -> geometry] -> force (+Pin) -> stress -> state switch
+// one thread per particle, per-bond arrays slot-major ([slot][Np]) so that a warp reads 32
+// consecutive doubles per slot; neighbour quantities (positions, dilatation sums, mirror-bond
+// stretch) are gathered through L2.  No atomics: every particle owns its outputs.
+#include "lpmb_internal.cuh"
+
+#define BT 128  // threads per block for the particle-parallel kernels
+
+struct BondView {
+    int N, Np, nn, dim;
+    const int *nbr;             // [nn][Np]
+    const signed char *nsign;   // [nn][Np]
+    const signed char *mirror;  // [nn][Np] slot of the reverse bond in the neighbour's list
+    const signed char *opp;     // [nn][Np] slot of the geometrically opposite bond (or -1)
+    const int *nbi;             // nb_initial
+    int *nb;
+    const double *xyz;          // [3][Np]
+};
+
+static int make_view(lpmb_ctx *c, BondView &v)
+{
+    v.N = c->N;
+    v.Np = c->Np;
+    v.nn = c->nn;
+    v.dim = c->dim;
+    v.nbr = fptr<int>(c, "neighbors");
+    v.nsign = fptr<signed char>(c, "nsign");
+    v.mirror = fptr<signed char>(c, "mirror");
+    v.opp = fptr<signed char>(c, "oppslot");
+    v.nbi = fptr<int>(c, "nb_initial");
+    v.nb = fptr<int>(c, "nb");
+    v.xyz = fptr<double>(c, "xyz");
+    LPMB_REQUIRE(v.nbr && v.nsign && v.mirror && v.opp && v.nbi && v.nb && v.xyz, LPMB_ERR_STATE, "topology fields missing");
+    return LPMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// topology derived data: nb_initial, mirror slot, opposite-bond slot
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT)
+derive_topology_kernel(int N, int Np, int nn, const int *__restrict__ nbr, int *__restrict__ nbi, int *__restrict__ nb,
+                       signed char *__restrict__ mirror)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= N)
+        return;
+    int n = 0;
+    for (int j = 0; j < nn; j++) {
+        const int nj = nbr[(size_t)j * Np + i];
+        signed char mj = -1;
+        if (nj >= 0) {
+            n++;
+            // constitutive.c:654-658: the slot jj with neighbors[neighbors[i][j]][jj] == i (last match wins)
+            for (int jj = 0; jj < nn; jj++)
+                if (nbr[(size_t)jj * Np + nj] == i)
+                    mj = (signed char)jj;
+        }
+        mirror[(size_t)j * Np + i] = mj;
+    }
+    nbi[i] = n;
+    nb[i] = n;
+}
+
+// lpm_basic.c:77-89 / constitutive.c:546-558: first m < nb_initial with cs_initial[m] == -cs_initial[j] (per
+// component within EPS); -1 if none.  Depends only on the initial geometry -> computed once.
+__global__ void __launch_bounds__(BT)
+derive_opposite_kernel(int N, int Np, const int *__restrict__ nbi, const double *__restrict__ cx0, const double *__restrict__ cy0,
+                       const double *__restrict__ cz0, signed char *__restrict__ opp)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= N)
+        return;
+    const int n = nbi[i];
+    for (int j = 0; j < n; j++) {
+        const double ax = cx0[(size_t)j * Np + i], ay = cy0[(size_t)j * Np + i], az = cz0[(size_t)j * Np + i];
+        signed char o = -1;
+        for (int m = 0; m < n; m++) {
+            if (fabs(cx0[(size_t)m * Np + i] + ax) < LPMB_EPS && fabs(cy0[(size_t)m * Np + i] + ay) < LPMB_EPS &&
+                fabs(cz0[(size_t)m * Np + i] + az) < LPMB_EPS) {
+                o = (signed char)m;
+                break;
+            }
+        }
+        opp[(size_t)j * Np + i] = o;
+    }
+}
+
+// searchNormalNeighbor's geometric by-products (neighbor.c:23-26,34-37) from xyz for given lists
+__global__ void __launch_bounds__(BT)
+initial_geometry_kernel(int N, int Np, const int *__restrict__ nbr, const int *__restrict__ nbi, const double *__restrict__ xyz,
+                        double *__restrict__ L0, double *__restrict__ cx0, double *__restrict__ cy0, double *__restrict__ cz0)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double xi = xyz[i], yi = xyz[(size_t)Np + i], zi = xyz[(size_t)2 * Np + i];
+    const int n = nbi[i];
+    for (int j = 0; j < n; j++) {
+        const int nj = nbr[(size_t)j * Np + i];
+        // dis = sqrt(pow(xj-xi,2)+pow(yj-yi,2)+pow(zj-zi,2)); cs = (xi-xj)/dis
+        const double dx = xyz[nj] - xi, dy = xyz[(size_t)Np + nj] - yi, dz = xyz[(size_t)2 * Np + nj] - zi;
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        const size_t e = (size_t)j * Np + i;
+        L0[e] = dis;
+        cx0[e] = (xi - xyz[nj]) / dis;
+        cy0[e] = (yi - xyz[(size_t)Np + nj]) / dis;
+        cz0[e] = (zi - xyz[(size_t)2 * Np + nj]) / dis;
+    }
+}
+
+int lpmb_derive_topology(lpmb_ctx *c, bool initial_geometry)
+{
+    int *nbr = fptr<int>(c, "neighbors");
+    int *nbi = fptr<int>(c, "nb_initial"), *nb = fptr<int>(c, "nb");
+    signed char *mirror = fptr<signed char>(c, "mirror"), *opp = fptr<signed char>(c, "oppslot");
+    LPMB_REQUIRE(nbr && nbi && nb && mirror && opp, LPMB_ERR_STATE, "topology fields missing");
+    const int g = lpmb_blocks(c->N, BT);
+    derive_topology_kernel<<<g, BT, 0, c->stream>>>(c->N, c->Np, c->nn, nbr, nbi, nb, mirror);
+    LPMB_LAUNCH_CHECK(c);
+    double *L0 = fptr<double>(c, "distance_initial"), *cx0 = fptr<double>(c, "csx_initial"), *cy0 = fptr<double>(c, "csy_initial"),
+           *cz0 = fptr<double>(c, "csz_initial");
+    if (initial_geometry) {
+        initial_geometry_kernel<<<g, BT, 0, c->stream>>>(c->N, c->Np, nbr, nbi, fptr<double>(c, "xyz"), L0, cx0, cy0, cz0);
+        LPMB_LAUNCH_CHECK(c);
+    }
+    derive_opposite_kernel<<<g, BT, 0, c->stream>>>(c->N, c->Np, nbi, cx0, cy0, cz0, opp);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_set_neighbors(lpmb_ctx *c, const int *neighbors, const int *nsign)
+{
+    LPMB_REQUIRE(c && neighbors && nsign, LPMB_ERR_ARG, "lpmb_set_neighbors: null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    const size_t cnt = (size_t)c->N * c->nn;
+    LPMB_TRY(lpmb_field_set(c, "neighbors", neighbors, cnt));
+    LPMB_TRY(lpmb_field_set(c, "nsign", nsign, cnt));
+    LPMB_REQUIRE(lpmb_field(c, "xyz"), LPMB_ERR_STATE, "xyz missing");
+    // distance_initial / cs*_initial are taken from the current xyz (= xyz_initial at set-up time) unless the
+    // caller uploaded them already
+    const bool have_geo = c->fields.count("distance_initial") && c->fields.count("csx_initial");
+    return lpmb_derive_topology(c, !have_geo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry pass  G(i; dLp*)   constitutive.c:241-260 / 495-515 / 625-645, lpm_basic.c:252-291
+// ---------------------------------------------------------------------------------------------
+// mode 0: dL = ((dis - L0) - dLp) * broken                  (all constitutive laws)
+// mode 1: computedL(): dL = (dis - L0) - dLp, also writes distance[]
+template <int MODE>
+__global__ void __launch_bounds__(BT)
+geometry_kernel(BondView v, const double *__restrict__ L0, const double *__restrict__ dLp, const double *__restrict__ broken,
+                const double *__restrict__ Tv, double *__restrict__ dL, double *__restrict__ csx, double *__restrict__ csy,
+                double *__restrict__ csz, double *__restrict__ dLt, double *__restrict__ TdLt, double *__restrict__ distance)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const double xi = v.xyz[i], yi = v.xyz[Np + i], zi = v.xyz[2 * Np + i];
+    double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+    const int n = v.nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const double dx = xi - v.xyz[nj], dy = yi - v.xyz[Np + nj], dz = zi - v.xyz[2 * Np + nj];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        double d = dis - L0[e];
+        d -= dLp[e];
+        if (MODE == 0)
+            d *= broken[e];
+        else
+            distance[e] = dis;
+        dL[e] = d;
+        const double td = Tv[e] * d;
+        if (v.nsign[e] == 0) {
+            t0 += d;
+            T0 += td;
+        } else {
+            t1 += d;
+            T1 += td;
+        }
+        csx[e] = dx / dis;
+        csy[e] = dy / dis;
+        csz[e] = dz / dis;
+    }
+    dLt[i] = t0;
+    dLt[Np + i] = t1;
+    TdLt[i] = T0;
+    TdLt[Np + i] = T1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bond force + internal force (owner pass)
+// ---------------------------------------------------------------------------------------------
+// LAW 6 (elastic, constitutive.c:267-279):  F = (2Kn dL + .5(TdLt_i+TdLt_j) + .5 Tv (dLt_i+dLt_j)) * broken
+// LAW 0 (J2,      constitutive.c:652-667):  dL_ave = .5 (dL_ij + dL_ji);  F = (2Kn dL_ave + ...) * damage_w
+template <int LAW>
+__global__ void __launch_bounds__(BT)
+force_kernel(BondView v, const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ scale /* broken | w */,
+             const double *__restrict__ dL, const double *__restrict__ dLt, const double *__restrict__ TdLt,
+             const double *__restrict__ csx, const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ dL_ave,
+             double *__restrict__ F, double *__restrict__ Pin)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const double dLt_i0 = dLt[i], dLt_i1 = dLt[Np + i], TdLt_i0 = TdLt[i], TdLt_i1 = TdLt[Np + i];
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    const int n = v.nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const int s = v.nsign[e];
+        const double dLt_i = s ? dLt_i1 : dLt_i0, TdLt_i = s ? TdLt_i1 : TdLt_i0;
+        const double dLt_j = dLt[(size_t)s * Np + nj], TdLt_j = TdLt[(size_t)s * Np + nj];
+        double stretch;
+        if (LAW == 0) {
+            const int mj = v.mirror[e];
+            if (mj >= 0) {
+                stretch = 0.5 * (dL[e] + dL[(size_t)mj * Np + nj]);
+                dL_ave[e] = stretch;
+            } else {
+                stretch = dL_ave[e];
+            }
+        } else {
+            stretch = dL[e];
+        }
+        double f = 2.0 * Kn[e] * stretch + 0.5 * (TdLt_i + TdLt_j) + 0.5 * Tv[e] * (dLt_i + dLt_j);
+        f *= scale[e];
+        F[e] = f;
+        p0 += csx[e] * f;
+        p1 += csy[e] * f;
+        p2 += csz[e] * f;
+    }
+    Pin[i] = p0;
+    Pin[Np + i] = p1;
+    Pin[2 * Np + i] = p2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// predictor (plmode 4)  constitutive.c:167-225
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT)
+predictor_geometry_kernel(BondView v, const double *__restrict__ xyz_temp, const double *__restrict__ broken, const double *__restrict__ Tv,
+                          double *__restrict__ ddL, double *__restrict__ ddLt, double *__restrict__ TddLt)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const double xi = v.xyz[i], yi = v.xyz[Np + i], zi = v.xyz[2 * Np + i];
+    const double xt = xyz_temp[i], yt = xyz_temp[Np + i], zt = xyz_temp[2 * Np + i];
+    double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+    const int n = v.nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const double ax = xt - xyz_temp[nj], ay = yt - xyz_temp[Np + nj], az = zt - xyz_temp[2 * Np + nj];
+        const double dis0 = sqrt(ax * ax + ay * ay + az * az);
+        const double bx = xi - v.xyz[nj], by = yi - v.xyz[Np + nj], bz = zi - v.xyz[2 * Np + nj];
+        const double dis1 = sqrt(bx * bx + by * by + bz * bz);
+        const double d = broken[e] * (dis1 - dis0);
+        ddL[e] = d;
+        const double td = Tv[e] * d;
+        if (v.nsign[e] == 0) {
+            t0 += d;
+            T0 += td;
+        } else {
+            t1 += d;
+            T1 += td;
+        }
+    }
+    ddLt[i] = t0;
+    ddLt[Np + i] = t1;
+    TddLt[i] = T0;
+    TddLt[Np + i] = T1;
+}
+
+__global__ void __launch_bounds__(BT)
+predictor_force_kernel(BondView v, const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ broken,
+                       const double *__restrict__ F_temp, const double *__restrict__ ddL, const double *__restrict__ ddLt,
+                       const double *__restrict__ TddLt, const double *__restrict__ csx, const double *__restrict__ csy,
+                       const double *__restrict__ csz, double *__restrict__ F, double *__restrict__ Pin)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    const int n = v.nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const int s = v.nsign[e];
+        const size_t si = (size_t)s * Np + i, sj = (size_t)s * Np + nj;
+        double f = F_temp[e] + 2.0 * Kn[e] * ddL[e] + 0.5 * (TddLt[si] + TddLt[sj]) + 0.5 * Tv[e] * (ddLt[si] + ddLt[sj]);
+        f *= broken[e];
+        F[e] = f;
+        p0 += csx[e] * f;  // stale cs* on purpose (constitutive.c:197-199 are commented out)
+        p1 += csy[e] * f;
+        p2 += csz[e] * f;
+    }
+    Pin[i] = p0;
+    Pin[Np + i] = p1;
+    Pin[2 * Np + i] = p2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// opposite-bond factor (lpm_basic.c:72-90, constitutive.c:541-559)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double opp_flag(int nb_i, int nn, int o, const double *__restrict__ broken, size_t Np, int i)
+{
+    if (nb_i == nn)
+        return 0.5;
+    if (o < 0)
+        return 1.0;
+    return broken[(size_t)o * Np + i] <= LPMB_EPS ? 1.0 : 0.5;
+}
+
+// ---------------------------------------------------------------------------------------------
+// J2 mixed linear hardening, return map per particle   constitutive.c:518-622
+// reads slot-[0] state (dLp0, J2_beta0, J2_alpha0), writes slot-[2] (dLp2 = broken * (dLp0 + ddLp)),
+// J2_beta2, J2_alpha2, J2_dlambda, ddLp, pl_flag
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT)
+j2_return_map_kernel(BondView v, double V, double J2_H, double J2_xi, const double *__restrict__ Ce /* [ntype][3] */, const int *__restrict__ type,
+                     const double *__restrict__ sigmay, const double *__restrict__ Kn, const double *__restrict__ Tv,
+                     const double *__restrict__ w, const double *__restrict__ broken, const double *__restrict__ L0,
+                     const double *__restrict__ dL, const double *__restrict__ dLt, const double *__restrict__ TdLt,
+                     const double *__restrict__ csx, const double *__restrict__ csy, const double *__restrict__ csz,
+                     const double *__restrict__ dLp0, const double *__restrict__ beta0, const double *__restrict__ alpha0,
+                     double *__restrict__ dLp2, double *__restrict__ beta2, double *__restrict__ alpha2, double *__restrict__ ddLp,
+                     double *__restrict__ dlambda, int *__restrict__ pl_flag)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int n = v.nbi[i], nb_i = v.nb[i];
+    const double dLt0 = dLt[i], dLt1 = dLt[Np + i], TdLt0 = TdLt[i], TdLt1 = TdLt[Np + i];
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int s = v.nsign[e];
+        double Fij = 2.0 * Kn[e] * dL[e] + (s ? TdLt1 : TdLt0) + Tv[e] * (s ? dLt1 : dLt0);
+        Fij *= w[e];
+        const double of = opp_flag(nb_i, v.nn, v.opp[e], broken, Np, i);
+        const double cx = csx[e], cy = csy[e], cz = csz[e];
+        const double pre = of / V * L0[e] * Fij;
+        st[0] += pre * cx * cx;
+        st[1] += pre * cy * cy;
+        st[2] += pre * cz * cz;
+        st[3] += pre * cy * cz;
+        st[4] += pre * cx * cz;
+        st[5] += pre * cx * cy;
+    }
+    const double temp = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+    st[0] -= temp;
+    st[1] -= temp;
+    st[2] -= temp;
+    double beta[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        beta[q] = beta0[(size_t)q * Np + i];
+        st[q] -= beta[q];
+    }
+    double seq = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        if (q < 3)
+            seq += st[q] * st[q];
+        else
+            seq += 2.0 * st[q] * st[q];
+    }
+    seq = sqrt(3.0 / 2.0 * seq);
+    double alpha = alpha0[i];
+    double dl = 0.0;
+    const double yield_func = seq - (sigmay[i] + (1.0 - J2_xi) * J2_H * alpha);
+    if (yield_func > 0.0) {
+        pl_flag[i] = 1;
+        dl = yield_func / (3 * Ce[3 * type[i] + 2] + J2_H);
+    }
+    alpha += dl;
+    double dpl[6] = {0, 0, 0, 0, 0, 0};
+    if (fabs(seq) > LPMB_EPS) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            dpl[q] = dl * 1.5 * st[q] / seq;
+            beta[q] += 2. / 3. * J2_xi * J2_H * dpl[q];
+        }
+    }
+    for (int j = 0; j < v.nn; j++) {
+        const size_t e = (size_t)j * Np + i;
+        double xd = dLp0[e];
+        if (j < n) {
+            const double cx = csx[e], cy = csy[e], cz = csz[e];
+            double dd = L0[e] * (dpl[0] * cx * cx + dpl[1] * cy * cy + dpl[2] * cz * cz + 2 * dpl[3] * cy * cz + 2 * dpl[4] * cx * cz +
+                                 2 * dpl[5] * cx * cy);
+            dd *= broken[e];
+            ddLp[e] = dd;
+            xd += dd;
+        }
+        dLp2[e] = broken[e] * xd;  // constitutive.c:670-671
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        beta2[(size_t)q * Np + i] = beta[q];
+    alpha2[i] = alpha;
+    dlambda[i] = dl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stress   lpm_basic.c:53-125
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT)
+stress_kernel(BondView v, double V, const double *__restrict__ L0, const double *__restrict__ F, const double *__restrict__ broken,
+              const double *__restrict__ csx, const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ stress,
+              double *__restrict__ seq_out, double *__restrict__ sm_out, double *__restrict__ triax, double *__restrict__ bond_stress)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int n = v.nbi[i], nb_i = v.nb[i];
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const double of = opp_flag(nb_i, v.nn, v.opp[e], broken, Np, i);
+        const double cx = csx[e], cy = csy[e], cz = csz[e];
+        const double pre = of / V * L0[e] * F[e];
+        st[0] += pre * cx * cx;
+        st[1] += pre * cy * cy;
+        st[2] += pre * cz * cz;
+        st[3] += pre * cy * cz;
+        st[4] += pre * cx * cz;
+        st[5] += pre * cx * cy;
+    }
+    double seq = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        stress[(size_t)q * Np + i] = st[q];
+        if (q < 3)
+            seq += st[q] * st[q];
+        else
+            seq += 2.0 * st[q] * st[q];
+    }
+    seq = sqrt(3.0 / 2.0 * seq);
+    const double sm = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+    seq_out[i] = seq;
+    sm_out[i] = sm;
+    if (seq > LPMB_EPS)
+        triax[i] = sm / seq;  // keeps the previous value otherwise (lpm_basic.c:111-112)
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const double cx = csx[e], cy = csy[e], cz = csz[e];
+        bond_stress[e] = (st[0] * cx * cx + st[1] * cy * cy + st[2] * cz * cz + 2 * st[3] * cy * cz + 2 * st[4] * cx * cz + 2 * st[5] * cx * cy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// updateCrack   constitutive.c:1399-1434
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT)
+update_crack_kernel(BondView v, const double *__restrict__ broken, const double *__restrict__ w, const double *__restrict__ csx,
+                    const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ F, double *__restrict__ Pin,
+                    double *__restrict__ damage_visual, int *__restrict__ fix_index)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int n = v.nbi[i];
+    int nbv = n;
+    double vis = 0.0, p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        if (broken[e] <= LPMB_EPS)
+            nbv -= 1;
+        vis += broken[e];
+        const double f = F[e] * w[e];  // scaled again on purpose
+        F[e] = f;
+        p0 += csx[e] * f;
+        p1 += csy[e] * f;
+        p2 += csz[e] * f;
+    }
+    v.nb[i] = nbv;
+    Pin[i] = p0;
+    Pin[Np + i] = p1;
+    Pin[2 * Np + i] = p2;
+    if (nbv < 1)
+        for (int k = 0; k < v.dim; k++)
+            fix_index[(size_t)k * Np + i] = 0;
+    damage_visual[i] = 1 - vis / n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// updateRR + norms   stiffness.c:519-534, lpmc_project.c:412-413
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// residual[k] = dispBC_index[k] * (Pex[k] - Pin[k]); partial sums of residual^2 and of Pin^2 over constrained DoFs
+__global__ void __launch_bounds__(256)
+update_rr_kernel(int dim, int Np, int N, const int *__restrict__ bc, const double *__restrict__ Pex, const double *__restrict__ Pin,
+                 double *__restrict__ residual, double *__restrict__ partials /* [2][grid] */)
+{
+    __shared__ double red[2][8];
+    double s_res = 0.0, s_rea = 0.0;
+    const size_t n = (size_t)dim * Np;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (size_t)gridDim.x * 256) {
+        const int i = (int)(e % Np);
+        if (i >= N)
+            continue;
+        const int b = bc[e];
+        const double pin = Pin[e];  // Pin is [3][Np]; the first dim components line up with the DoF layout
+        const double r = b * (Pex[e] - pin);
+        residual[e] = r;
+        s_res += r * r;
+        if (b == 0)
+            s_rea += pin * pin;
+    }
+    s_res = warp_sum_d(s_res);
+    s_rea = warp_sum_d(s_rea);
+    const int wdx = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[0][wdx] = s_res;
+        red[1][wdx] = s_rea;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b2 = 0;
+        for (int k = 0; k < 8; k++) {
+            a += red[0][k];
+            b2 += red[1][k];
+        }
+        partials[blockIdx.x] = a;
+        partials[gridDim.x + blockIdx.x] = b2;
+    }
+}
+
+__global__ void finish_rr_kernel(const double *__restrict__ partials, int nparts, double *__restrict__ out2)
+{
+    // single block, fixed order
+    __shared__ double red[2][8];
+    double a = 0, b = 0;
+    for (int k = threadIdx.x; k < nparts; k += 256) {
+        a += partials[k];
+        b += partials[nparts + k];
+    }
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    const int wdx = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[0][wdx] = a;
+        red[1][wdx] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0, y = 0;
+        for (int k = 0; k < 8; k++) {
+            x += red[0][k];
+            y += red[1][k];
+        }
+        out2[0] = sqrt(x);
+        out2[1] = sqrt(y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side orchestration
+// ---------------------------------------------------------------------------------------------
+static int copy_field(lpmb_ctx *c, const char *dst, const char *src)
+{
+    Field *d = lpmb_field(c, dst), *s = lpmb_field(c, src);
+    LPMB_REQUIRE(d && s && d->count == s->count && d->elem() == s->elem(), LPMB_ERR_STATE, "copy_field %s <- %s: mismatch", dst, src);
+    LPMB_CUDA(cudaMemcpyAsync(d->d, s->d, d->count * d->elem(), cudaMemcpyDeviceToDevice, c->stream));
+    return LPMB_OK;
+}
+
+// switchStateV   constitutive.c:10-85.  (cp_* state joins when the crystal-plasticity law is built.)
+extern "C" int lpmb_switch_state(lpmb_ctx *c, int flag)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    if (flag == 0) {  // [0] := [1]
+        LPMB_TRY(copy_field(c, "dLp0", "dLp1"));
+        LPMB_TRY(copy_field(c, "damage_D0", "damage_D1"));
+        LPMB_TRY(copy_field(c, "J2_beta0", "J2_beta1"));
+        LPMB_TRY(copy_field(c, "J2_alpha0", "J2_alpha1"));
+        LPMB_TRY(copy_field(c, "J2_beta_eq0", "J2_beta_eq1"));
+        LPMB_TRY(copy_field(c, "damage_local0", "damage_local1"));
+        LPMB_TRY(copy_field(c, "damage_nonlocal0", "damage_nonlocal1"));
+    } else if (flag == 1) {  // [1] := [0]
+        LPMB_TRY(copy_field(c, "dLp1", "dLp0"));
+        LPMB_TRY(copy_field(c, "damage_D1", "damage_D0"));
+        LPMB_TRY(copy_field(c, "J2_beta1", "J2_beta0"));
+        LPMB_TRY(copy_field(c, "J2_alpha1", "J2_alpha0"));
+        LPMB_TRY(copy_field(c, "J2_beta_eq1", "J2_beta_eq0"));
+        LPMB_TRY(copy_field(c, "damage_local1", "damage_local0"));
+        LPMB_TRY(copy_field(c, "damage_nonlocal1", "damage_nonlocal0"));
+    } else if (flag == 2) {  // [0] := [2] (no damage_* here, constitutive.c:63-84)
+        LPMB_TRY(copy_field(c, "dLp0", "dLp2"));
+        LPMB_TRY(copy_field(c, "J2_beta0", "J2_beta2"));
+        LPMB_TRY(copy_field(c, "J2_alpha0", "J2_alpha2"));
+        LPMB_TRY(copy_field(c, "J2_beta_eq0", "J2_beta_eq2"));
+    } else {
+        lpmb_set_error("switchStateV: flag %d", flag);
+        return LPMB_ERR_ARG;
+    }
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_compute_dl(lpmb_ctx *c)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    geometry_kernel<1><<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(
+        v, fptr<double>(c, "distance_initial"), fptr<double>(c, "dLp0"), fptr<double>(c, "damage_broken"), fptr<double>(c, "Tv"),
+        fptr<double>(c, "dL"), fptr<double>(c, "csx"), fptr<double>(c, "csy"), fptr<double>(c, "csz"), fptr<double>(c, "dL_total"),
+        fptr<double>(c, "TdL_total"), fptr<double>(c, "distance"));
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+static int run_geometry(lpmb_ctx *c, BondView &v, const char *dLp_slot)
+{
+    geometry_kernel<0><<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(
+        v, fptr<double>(c, "distance_initial"), fptr<double>(c, dLp_slot), fptr<double>(c, "damage_broken"), fptr<double>(c, "Tv"),
+        fptr<double>(c, "dL"), fptr<double>(c, "csx"), fptr<double>(c, "csy"), fptr<double>(c, "csz"), fptr<double>(c, "dL_total"),
+        fptr<double>(c, "TdL_total"), nullptr);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+int lpmb_compute_stress(lpmb_ctx *c)
+{
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    stress_kernel<<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(
+        v, param(c, "particle_volume"), fptr<double>(c, "distance_initial"), fptr<double>(c, "F"), fptr<double>(c, "damage_broken"),
+        fptr<double>(c, "csx"), fptr<double>(c, "csy"), fptr<double>(c, "csz"), fptr<double>(c, "stress_tensor"),
+        fptr<double>(c, "J2_stresseq"), fptr<double>(c, "J2_stressm"), fptr<double>(c, "J2_triaxiality"), fptr<double>(c, "bond_stress"));
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+// computeBondForceGeneral(plmode, t)   constitutive.c:88-146
+extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
+{
+    (void)load_indicator;  // only the plmode-3 law reads it
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(c->params.count("particle_volume"), LPMB_ERR_STATE, "parameter particle_volume not set");
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    const int g = lpmb_blocks(c->N, BT);
+    double *Kn = fptr<double>(c, "Kn"), *Tv = fptr<double>(c, "Tv"), *broken = fptr<double>(c, "damage_broken"), *w = fptr<double>(c, "damage_w");
+    double *dL = fptr<double>(c, "dL"), *dLt = fptr<double>(c, "dL_total"), *TdLt = fptr<double>(c, "TdL_total");
+    double *csx = fptr<double>(c, "csx"), *csy = fptr<double>(c, "csy"), *csz = fptr<double>(c, "csz");
+    double *F = fptr<double>(c, "F"), *Pin = fptr<double>(c, "Pin"), *dL_ave = fptr<double>(c, "dL_ave");
+    if (plmode == 6) {
+        LPMB_TRY(run_geometry(c, v, "dLp0"));
+        force_kernel<6><<<g, BT, 0, c->stream>>>(v, Kn, Tv, broken, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
+        LPMB_LAUNCH_CHECK(c);
+    } else if (plmode == 4) {
+        double *ddL = fptr<double>(c, "ddL"), *ddLt = fptr<double>(c, "ddL_total"), *TddLt = fptr<double>(c, "TddL_total");
+        predictor_geometry_kernel<<<g, BT, 0, c->stream>>>(v, fptr<double>(c, "xyz_temp"), broken, Tv, ddL, ddLt, TddLt);
+        LPMB_LAUNCH_CHECK(c);
+        predictor_force_kernel<<<g, BT, 0, c->stream>>>(v, Kn, Tv, broken, fptr<double>(c, "F_temp"), ddL, ddLt, TddLt, csx, csy, csz, F, Pin);
+        LPMB_LAUNCH_CHECK(c);
+    } else if (plmode == 0) {
+        LPMB_REQUIRE(c->params.count("J2_H") && c->params.count("J2_xi"), LPMB_ERR_STATE, "J2_H / J2_xi not set");
+        Field *ce = lpmb_field(c, "Ce");
+        LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+        LPMB_TRY(run_geometry(c, v, "dLp0"));
+        j2_return_map_kernel<<<g, BT, 0, c->stream>>>(
+            v, param(c, "particle_volume"), param(c, "J2_H"), param(c, "J2_xi"), (const double *)ce->d, fptr<int>(c, "type"),
+            fptr<double>(c, "sigmay"), Kn, Tv, w, broken, fptr<double>(c, "distance_initial"), dL, dLt, TdLt, csx, csy, csz,
+            fptr<double>(c, "dLp0"), fptr<double>(c, "J2_beta0"), fptr<double>(c, "J2_alpha0"), fptr<double>(c, "dLp2"),
+            fptr<double>(c, "J2_beta2"), fptr<double>(c, "J2_alpha2"), fptr<double>(c, "ddLp"), fptr<double>(c, "J2_dlambda"),
+            fptr<int>(c, "pl_flag"));
+        LPMB_LAUNCH_CHECK(c);
+        LPMB_TRY(run_geometry(c, v, "dLp2"));
+        force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
+        LPMB_LAUNCH_CHECK(c);
+    } else {
+        lpmb_set_error("computeBondForceGeneral: plmode %d is not built (0, 4, 6 are)", plmode);
+        return LPMB_ERR_UNSUPPORTED;
+    }
+    LPMB_TRY(lpmb_compute_stress(c));
+    return lpmb_switch_state(c, 2);
+}
+
+extern "C" int lpmb_update_crack(lpmb_ctx *c)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    update_crack_kernel<<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(
+        v, fptr<double>(c, "damage_broken"), fptr<double>(c, "damage_w"), fptr<double>(c, "csx"), fptr<double>(c, "csy"),
+        fptr<double>(c, "csz"), fptr<double>(c, "F"), fptr<double>(c, "Pin"), fptr<double>(c, "damage_visual"), fptr<int>(c, "fix_index"));
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_update_rr(lpmb_ctx *c, double *norm_residual, double *norm_reaction)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_TRY(lpmb_cg_alloc(c));
+    const int grid = c->sm_count * 4;
+    LPMB_REQUIRE(2 * grid + 2 <= 2 * c->cg.max_blocks, LPMB_ERR_STATE, "partials buffer too small");
+    double *partials = c->cg.partials;
+    update_rr_kernel<<<grid, 256, 0, c->stream>>>(c->dim, c->Np, c->N, fptr<int>(c, "dispBC_index"), fptr<double>(c, "Pex"),
+                                                    fptr<double>(c, "Pin"), fptr<double>(c, "residual"), partials);
+    LPMB_LAUNCH_CHECK(c);
+    double *out2 = c->cg.scal + 12;
+    finish_rr_kernel<<<1, 256, 0, c->stream>>>(partials, grid, out2);
+    LPMB_LAUNCH_CHECK(c);
+    if (norm_residual || norm_reaction) {
+        LPMB_CUDA(cudaMemcpyAsync(c->cg.h_scal + 12, out2, 16, cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (norm_residual)
+            *norm_residual = c->cg.h_scal[12];
+        if (norm_reaction)
+            *norm_reaction = c->cg.h_scal[13];
+    }
+    return LPMB_OK;
+}
+
+// calcKnTv   stiffness.c:11-268: KnTve[type] = (radius) * M_lattice * Ce[type]; per bond by shell
+__global__ void __launch_bounds__(BT)
+kntv_kernel(BondView v, int lattice, const double *__restrict__ KnTve /* [ntype][3] */, const int *__restrict__ type,
+            double *__restrict__ Kn, double *__restrict__ Tv)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int n = v.nbi[i], ti = type[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int s = v.nsign[e];
+        if (lattice == LPMB_LATTICE_SC) {  // stiffness.c:192-201: average of the two end particles' types
+            const int tj = type[v.nbr[e]];
+            Kn[e] = 0.5 * (KnTve[3 * ti + s] + KnTve[3 * tj + s]);
+            Tv[e] = 0.5 * (KnTve[3 * ti + 2] + KnTve[3 * tj + 2]);
+        } else if (lattice == LPMB_LATTICE_HEX) {  // stiffness.c:58-65 (2 columns)
+            Kn[e] = KnTve[3 * ti + 0];
+            Tv[e] = KnTve[3 * ti + 1];
+        } else {  // square, FCC, BCC: stiffness.c:25-41, 218-234, 250-266
+            Kn[e] = KnTve[3 * ti + s];
+            Tv[e] = KnTve[3 * ti + 2];
+        }
+    }
+}
+
+extern "C" int lpmb_calc_kntv(lpmb_ctx *c, const double *Ce, int ntype)
+{
+    LPMB_REQUIRE(c && Ce && ntype > 0, LPMB_ERR_ARG, "lpmb_calc_kntv: bad argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(c->params.count("radius"), LPMB_ERR_STATE, "parameter radius not set");
+    const double radius = param(c, "radius");
+    // the 3x3 (2x2) constant maps of stiffness.c:17-20, 51-53, 179-182, 210-213, 242-245; the product is
+    // evaluated like the reference's row-major dgemm: alpha * (sum_p M[r][p] * Ce[p])
+    std::vector<double> knt((size_t)ntype * 3, 0.0);
+    for (int k = 0; k < ntype; k++) {
+        const double *ce = Ce + 3 * k;
+        double M[9];
+        double alpha = radius;
+        int rows = 3;
+        switch (c->lattice) {
+        case LPMB_LATTICE_SQUARE: {
+            const double m[9] = {1 / 2.0, -1 / 2.0, 0.0, 0.0, 0.0, 1 / 2.0, 0.0, 1.0 / 12.0, -1.0 / 12.0};
+            memcpy(M, m, sizeof(m));
+            alpha = 1.0;
+            break;
+        }
+        case LPMB_LATTICE_HEX: {
+            const double m[9] = {sqrt(3.0) / 12.0, -sqrt(3.0) / 12.0, 0, -sqrt(3.0) / 144.0, sqrt(3.0) / 48.0, 0, 0, 0, 0};
+            memcpy(M, m, sizeof(m));
+            alpha = 1.0;
+            rows = 2;
+            break;
+        }
+        case LPMB_LATTICE_SC: {
+            const double m[9] = {1, -1, -1, 0, 0, 1, 0, 1.0 / 18.0, -1.0 / 18.0};
+            memcpy(M, m, sizeof(m));
+            break;
+        }
+        case LPMB_LATTICE_FCC: {
+            const double m[9] = {0, 0, sqrt(2.0), sqrt(2.0) / 4.0, -sqrt(2.0) / 4.0, -sqrt(2.0) / 4.0, 0, sqrt(2.0) / 24.0, -sqrt(2.0) / 24.0};
+            memcpy(M, m, sizeof(m));
+            break;
+        }
+        case LPMB_LATTICE_BCC: {
+            const double m[9] = {0., 0., sqrt(3.0), 1. / sqrt(3.0), -1. / sqrt(3.0), 0., 0., sqrt(3.0) / 14.0, sqrt(3.0) / 14.0};
+            memcpy(M, m, sizeof(m));
+            break;
+        }
+        default:
+            lpmb_set_error("calcKnTv: lattice %d", c->lattice);
+            return LPMB_ERR_ARG;
+        }
+        for (int r = 0; r < rows; r++) {
+            double s = 0.0;
+            if (rows == 2) {
+                for (int p = 0; p < 2; p++)
+                    s += M[r * 3 + p] * ce[p];
+            } else {
+                for (int p = 0; p < 3; p++)
+                    s += M[r * 3 + p] * ce[p];
+            }
+            knt[3 * k + r] = alpha * s;
+        }
+    }
+    // Ce and KnTve live as small raw device fields
+    for (const char *nm : {"Ce", "KnTve"}) {
+        auto it = c->fields.find(nm);
+        if (it != c->fields.end() && it->second.count != (size_t)ntype * 3) {
+            cudaFree(it->second.d);
+            c->fields.erase(it);
+        }
+        if (!c->fields.count(nm)) {
+            Field f;
+            f.kind = FK_RAW;
+            f.type = FT_F64;
+            f.comps = 3;
+            f.count = (size_t)ntype * 3;
+            LPMB_CUDA(cudaMalloc(&f.d, f.count * 8));
+            c->fields[nm] = f;
+        }
+    }
+    LPMB_CUDA(cudaMemcpyAsync(c->fields["Ce"].d, Ce, (size_t)ntype * 24, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMemcpyAsync(c->fields["KnTve"].d, knt.data(), (size_t)ntype * 24, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    kntv_kernel<<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(v, c->lattice, (const double *)c->fields["KnTve"].d, fptr<int>(c, "type"),
+                                                           fptr<double>(c, "Kn"), fptr<double>(c, "Tv"));
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}

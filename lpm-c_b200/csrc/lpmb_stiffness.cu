@@ -1,0 +1,480 @@
+// lpmb_stiffness.cu -- finite-difference elastic tangent, assembled straight into the device block
+// matrix (compiled with -fmad=false: strict IEEE, bit-compatible with the reference's arithmetic).
+//
+// Replaces calcStiffness{2,3}DFiniteDifference(6), reference src/stiffness.c:271-516:
+//   for every particle i: base computeBondForceElastic(i) (src/constitutive.c:228-283), then for every
+//   conn particle c and coordinate r: xyz[c][r] += EPS*radius, re-evaluate, restore;
+//   A_i[c][s][r] = (Pin_i^pert[s] - Pin_i^base[s]) / EPS / radius       (stiffness.c:419-427)
+//   K_ii = upper triangle of A_i[i];  K_ij = 0.5*A_i[j] + 0.5*A_j[i]^T   (stiffness.c:441-481)
+//
+// Design.  One CTA per particle i, one thread per perturbation (c,r) (<= 183 in 3-D).  The bond star
+// of i -- i, its <= nn neighbours and *their* bond lists with neighbour positions, L0, dLp, Tv,
+// damage_broken -- is staged once in shared memory (~21 KB) together with the unperturbed bond
+// stretches / direction cosines / dilatation sums.  A perturbation of c only changes the bonds that
+// touch c, so each thread recomputes (with exactly the reference's expressions and summation order)
+// only the star members whose bond list contains c -- found in O(1) from a 64-bit "affected" mask per
+// star member -- and takes the cached unperturbed sums otherwise.  Unaffected quantities are pure
+// functions of unchanged inputs, so the result equals the reference's brute-force re-evaluation of
+// all 19x18 bonds bit for bit, at ~1/100 of its sqrt/div count.  The 3x3 (2x2) blocks A_i[c] go to
+// row i of the SELL matrix; a second kernel symmetrises pairs in place (no atomics: every (i,j>i)
+// pair is owned by one thread).
+#include "lpmb_internal.cuh"
+
+template <int D, int NN>
+struct StarSmem {
+    int sid[NN + 1];                 // star member particle ids (0 = owner), -1 = none
+    int nbi[NN + 1];                 // nb_initial of each member
+    unsigned long long amask[NN + 1];// bit q set <=> conn[i][q] is the member itself or one of its neighbours
+    double pos[NN + 1][3];
+    int nid[NN + 1][NN];
+    double npos[NN + 1][NN][3];
+    double L0[NN + 1][NN], dLp[NN + 1][NN], brk[NN + 1][NN], Tv[NN + 1][NN];
+    signed char sg[NN + 1][NN];
+    double bt[NN + 1][2], bT[NN + 1][2];  // unperturbed dL_total / TdL_total
+    double bdL[NN], bcs[NN][3];           // unperturbed owner bond stretch / direction cosines
+    double Kn[NN];
+    int conn[64];
+    int nbc;
+    double base_pin[3];
+};
+
+template <int D, int NN, int T>
+__global__ void __launch_bounds__(T)
+fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const int *__restrict__ nbr, const signed char *__restrict__ nsign,
+                    const int *__restrict__ nbi_g, const double *__restrict__ xyz, const double *__restrict__ L0g,
+                    const double *__restrict__ dLp0g, const double *__restrict__ brkg, const double *__restrict__ Tvg,
+                    const double *__restrict__ Kng, const long long *__restrict__ sptr, const int *__restrict__ col,
+                    const int *__restrict__ nbc_g, double *__restrict__ val, double *__restrict__ F_side, double *__restrict__ Pin_side)
+{
+    extern __shared__ unsigned char smem_raw[];
+    StarSmem<D, NN> &S = *reinterpret_cast<StarSmem<D, NN> *>(smem_raw);
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x;
+    const size_t Npz = Np;
+    const long long krow = sptr[i >> 5];
+    const int lane_i = i & 31;
+
+    // ---- stage the star ----
+    if (tid == 0) {
+        S.nbc = nbc_g[i];
+        S.sid[0] = i;
+    }
+    if (tid < NN) {
+        const int nj = (tid < nbi_g[i]) ? nbr[(size_t)tid * Npz + i] : -1;
+        S.sid[tid + 1] = nj;
+    }
+    if (tid < 64)
+        S.conn[tid] = (tid < nbc_g[i]) ? col[(krow + tid) * 32 + lane_i] : -1;
+    if (tid < NN + 1)
+        S.amask[tid] = 0ull;
+    __syncthreads();
+    if (tid < NN + 1) {
+        const int pid = S.sid[tid];
+        S.nbi[tid] = pid >= 0 ? nbi_g[pid] : 0;
+        if (pid >= 0) {
+            S.pos[tid][0] = xyz[pid];
+            S.pos[tid][1] = xyz[Npz + pid];
+            S.pos[tid][2] = xyz[2 * Npz + pid];
+        }
+    }
+    __syncthreads();
+    const int nbc = S.nbc;
+    for (int e = tid; e < (NN + 1) * NN; e += T) {
+        const int a = e / NN, m = e % NN;
+        const int pid = S.sid[a];
+        int nj = -1;
+        if (pid >= 0 && m < S.nbi[a]) {
+            const size_t g = (size_t)m * Npz + pid;
+            nj = nbr[g];
+            S.npos[a][m][0] = xyz[nj];
+            S.npos[a][m][1] = xyz[Npz + nj];
+            S.npos[a][m][2] = xyz[2 * Npz + nj];
+            S.L0[a][m] = L0g[g];
+            S.dLp[a][m] = dLp0g[g];
+            S.brk[a][m] = brkg[g];
+            S.Tv[a][m] = Tvg[g];
+            S.sg[a][m] = nsign[g];
+            if (a == 0)
+                S.Kn[m] = Kng[g];
+        }
+        S.nid[a][m] = nj;
+        // affected mask: position of nj (and of the member itself) in conn[i]
+        if (nj >= 0) {
+            int lo = 0, hi = nbc - 1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1, v = S.conn[mid];
+                if (v == nj) {
+                    atomicOr(&S.amask[a], 1ull << mid);
+                    break;
+                }
+                if (v < nj)
+                    lo = mid + 1;
+                else
+                    hi = mid - 1;
+            }
+        }
+        if (m == 0 && pid >= 0) {
+            int lo = 0, hi = nbc - 1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1, v = S.conn[mid];
+                if (v == pid) {
+                    atomicOr(&S.amask[a], 1ull << mid);
+                    break;
+                }
+                if (v < pid)
+                    lo = mid + 1;
+                else
+                    hi = mid - 1;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- unperturbed geometry of every star member (constitutive.c:241-260) ----
+    if (tid < NN + 1 && S.sid[tid] >= 0) {
+        const int a = tid;
+        double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+        for (int m = 0; m < S.nbi[a]; m++) {
+            const double dx = S.pos[a][0] - S.npos[a][m][0], dy = S.pos[a][1] - S.npos[a][m][1], dz = S.pos[a][2] - S.npos[a][m][2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            double d = dis - S.L0[a][m];
+            d -= S.dLp[a][m];
+            d *= S.brk[a][m];
+            const double td = S.Tv[a][m] * d;
+            if (S.sg[a][m] == 0) {
+                t0 += d;
+                T0 += td;
+            } else {
+                t1 += d;
+                T1 += td;
+            }
+            if (a == 0) {
+                S.bdL[m] = d;
+                S.bcs[m][0] = dx / dis;
+                S.bcs[m][1] = dy / dis;
+                S.bcs[m][2] = dz / dis;
+            }
+        }
+        S.bt[a][0] = t0;
+        S.bt[a][1] = t1;
+        S.bT[a][0] = T0;
+        S.bT[a][1] = T1;
+    }
+    __syncthreads();
+    // ---- base internal force (constitutive.c:264-279) ----
+    if (tid == 0) {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        for (int m = 0; m < S.nbi[0]; m++) {
+            const int s = S.sg[0][m];
+            double f = 2.0 * S.Kn[m] * S.bdL[m] + 0.5 * (S.bT[0][s] + S.bT[m + 1][s]) + 0.5 * S.Tv[0][m] * (S.bt[0][s] + S.bt[m + 1][s]);
+            f *= S.brk[0][m];
+            p0 += S.bcs[m][0] * f;
+            p1 += S.bcs[m][1] * f;
+            p2 += S.bcs[m][2] * f;
+        }
+        S.base_pin[0] = p0;
+        S.base_pin[1] = p1;
+        S.base_pin[2] = p2;
+    }
+    __syncthreads();
+
+    // ---- one perturbation per thread ----
+    const int p = tid;
+    if (p >= D * nbc)
+        return;
+    const int q = p / D, r = p % D;
+    const int c = S.conn[q];
+    const unsigned long long bit = 1ull << q;
+    const int n0 = S.nbi[0];
+
+    // owner sums
+    double ti[2], Ti[2];
+    const bool own_aff = (S.amask[0] & bit) != 0ull;
+    double opos[3] = {S.pos[0][0], S.pos[0][1], S.pos[0][2]};
+    if (c == i)
+        opos[r] = opos[r] + h;
+    if (own_aff) {
+        double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+        for (int m = 0; m < n0; m++) {
+            double np[3] = {S.npos[0][m][0], S.npos[0][m][1], S.npos[0][m][2]};
+            if (S.nid[0][m] == c)
+                np[r] = np[r] + h;
+            const double dx = opos[0] - np[0], dy = opos[1] - np[1], dz = opos[2] - np[2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            double d = dis - S.L0[0][m];
+            d -= S.dLp[0][m];
+            d *= S.brk[0][m];
+            const double td = S.Tv[0][m] * d;
+            if (S.sg[0][m] == 0) {
+                t0 += d;
+                T0 += td;
+            } else {
+                t1 += d;
+                T1 += td;
+            }
+        }
+        ti[0] = t0;
+        ti[1] = t1;
+        Ti[0] = T0;
+        Ti[1] = T1;
+    } else {
+        ti[0] = S.bt[0][0];
+        ti[1] = S.bt[0][1];
+        Ti[0] = S.bT[0][0];
+        Ti[1] = S.bT[0][1];
+    }
+
+    const bool last = (p == D * nbc - 1) && (F_side != nullptr);
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    for (int m = 0; m < n0; m++) {
+        const int a = m + 1;
+        const int s = S.sg[0][m];
+        // neighbour's shell-s sums
+        double tj, Tj;
+        if (S.amask[a] & bit) {
+            double apos[3] = {S.pos[a][0], S.pos[a][1], S.pos[a][2]};
+            if (S.sid[a] == c)
+                apos[r] = apos[r] + h;
+            double t = 0, TT = 0;
+            const int na = S.nbi[a];
+            for (int mm = 0; mm < na; mm++) {
+                if (S.sg[a][mm] != s)
+                    continue;
+                double np[3] = {S.npos[a][mm][0], S.npos[a][mm][1], S.npos[a][mm][2]};
+                if (S.nid[a][mm] == c)
+                    np[r] = np[r] + h;
+                const double dx = apos[0] - np[0], dy = apos[1] - np[1], dz = apos[2] - np[2];
+                const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+                double d = dis - S.L0[a][mm];
+                d -= S.dLp[a][mm];
+                d *= S.brk[a][mm];
+                t += d;
+                TT += S.Tv[a][mm] * d;
+            }
+            tj = t;
+            Tj = TT;
+        } else {
+            tj = S.bt[a][s];
+            Tj = S.bT[a][s];
+        }
+        // owner's bond m
+        double d, cx, cy, cz;
+        if (own_aff) {
+            double np[3] = {S.npos[0][m][0], S.npos[0][m][1], S.npos[0][m][2]};
+            if (S.nid[0][m] == c)
+                np[r] = np[r] + h;
+            const double dx = opos[0] - np[0], dy = opos[1] - np[1], dz = opos[2] - np[2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            d = dis - S.L0[0][m];
+            d -= S.dLp[0][m];
+            d *= S.brk[0][m];
+            cx = dx / dis;
+            cy = dy / dis;
+            cz = dz / dis;
+        } else {
+            d = S.bdL[m];
+            cx = S.bcs[m][0];
+            cy = S.bcs[m][1];
+            cz = S.bcs[m][2];
+        }
+        double f = 2.0 * S.Kn[m] * d + 0.5 * (Ti[s] + Tj) + 0.5 * S.Tv[0][m] * (ti[s] + tj);
+        f *= S.brk[0][m];
+        p0 += cx * f;
+        p1 += cy * f;
+        p2 += cz * f;
+        if (last)
+            F_side[(size_t)m * Npz + i] = f;
+    }
+    if (last) {
+        Pin_side[i] = p0;
+        Pin_side[Npz + i] = p1;
+        Pin_side[2 * Npz + i] = p2;
+    }
+    // A_i[c][s][r] = (Pin_pert[s] - Pin_base[s]) / EPS / radius -> element (row s, col r) of block (i,c)
+    const long long k = krow + q;
+    const double pp[3] = {p0, p1, p2};
+#pragma unroll
+    for (int s = 0; s < D; s++) {
+        const double kv = (pp[s] - S.base_pin[s]) / eps / radius;
+        val[(k * D * D + s * D + r) * 32 + lane_i] = kv;
+    }
+}
+
+// position of block column `target` in (sorted) block row `row`, or -1
+__device__ __forceinline__ int find_col(const int *__restrict__ col, const long long *__restrict__ sptr, const int *__restrict__ nbc, int row,
+                                        int target)
+{
+    const long long base = sptr[row >> 5] * 32 + (row & 31);
+    int lo = 0, hi = nbc[row] - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = col[base + (long long)mid * 32];
+        if (v == target)
+            return mid;
+        if (v < target)
+            lo = mid + 1;
+        else
+            hi = mid - 1;
+    }
+    return -1;
+}
+
+// K_ij = 0.5*A_i[j] + 0.5*A_j[i]^T for j > i (both copies written); diagonal block: lower := upper.
+template <int D>
+__global__ void symmetrize_kernel(int N, const long long *__restrict__ sptr, const int *__restrict__ col, const int *__restrict__ nbc,
+                                  double *__restrict__ val)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N)
+        return;
+    const long long ka = sptr[row >> 5];
+    const int lane = row & 31;
+    const int n = nbc[row];
+    for (int kk = 0; kk < n; kk++) {
+        const long long k = ka + kk;
+        const int cidx = col[k * 32 + lane];
+        if (cidx < row)
+            continue;
+        double *a = val + (k * D * D) * 32 + lane;
+        if (cidx == row) {
+#pragma unroll
+            for (int r = 1; r < D; r++)
+#pragma unroll
+                for (int s = 0; s < r; s++)
+                    a[(r * D + s) * 32] = a[(s * D + r) * 32];
+            continue;
+        }
+        const int pos = find_col(col, sptr, nbc, cidx, row);
+        if (pos < 0)
+            continue;  // asymmetric pattern: cannot happen for conn built by neighbor.c
+        double *b = val + ((sptr[cidx >> 5] + pos) * D * D) * 32 + (cidx & 31);
+        // read both blocks completely first, then write (in-place safe)
+        double A[D * D], B[D * D];
+#pragma unroll
+        for (int e = 0; e < D * D; e++) {
+            A[e] = a[e * 32];
+            B[e] = b[e * 32];
+        }
+#pragma unroll
+        for (int r = 0; r < D; r++)
+#pragma unroll
+            for (int s = 0; s < D; s++) {
+                const double kv = 0.5 * A[r * D + s] + 0.5 * B[s * D + r];
+                a[(r * D + s) * 32] = kv;
+                b[(s * D + r) * 32] = kv;
+            }
+    }
+}
+
+// after the (single-threaded) reference assembly, dL / cs* / dL_total / TdL_total of
+// particle p hold the values of the LAST evaluation that touched p: the evaluation of particle
+// m(p) = max({p} U {intact neighbours whose own bond to p is intact}) with its last conn particle
+// displaced by +h in the last coordinate.
+template <int D>
+__global__ void __launch_bounds__(128)
+fd_side_effects_kernel(int N, int Np, double h, const int *__restrict__ nbr, const signed char *__restrict__ nsign,
+                       const signed char *__restrict__ mirror, const int *__restrict__ nbi_g, const double *__restrict__ xyz,
+                       const double *__restrict__ L0, const double *__restrict__ dLp0, const double *__restrict__ brk, const double *__restrict__ Tv,
+                       const long long *__restrict__ sptr, const int *__restrict__ col, const int *__restrict__ nbc, double *__restrict__ dL,
+                       double *__restrict__ csx, double *__restrict__ csy, double *__restrict__ csz, double *__restrict__ dLt, double *__restrict__ TdLt)
+{
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= N)
+        return;
+    const size_t Npz = Np;
+    const int n = nbi_g[p];
+    int m = p;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Npz + p;
+        const int nj = nbr[e];
+        const int mj = mirror[e];
+        // p is in the star of nj iff nj's own bond to p is intact (constitutive.c:233-237)
+        if (mj >= 0 && brk[(size_t)mj * Npz + nj] > LPMB_EPS && nj > m)
+            m = nj;
+    }
+    if (nbc[m] <= 0)
+        return;
+    const int c = col[(sptr[m >> 5] + nbc[m] - 1) * 32 + (m & 31)];
+    double pp[3] = {xyz[p], xyz[Npz + p], xyz[2 * Npz + p]};
+    if (p == c)
+        pp[D - 1] = pp[D - 1] + h;
+    double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Npz + p;
+        const int nj = nbr[e];
+        double np[3] = {xyz[nj], xyz[Npz + nj], xyz[2 * Npz + nj]};
+        if (nj == c)
+            np[D - 1] = np[D - 1] + h;
+        const double dx = pp[0] - np[0], dy = pp[1] - np[1], dz = pp[2] - np[2];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        double d = dis - L0[e];
+        d -= dLp0[e];
+        d *= brk[e];
+        dL[e] = d;
+        const double td = Tv[e] * d;
+        if (nsign[e] == 0) {
+            t0 += d;
+            T0 += td;
+        } else {
+            t1 += d;
+            T1 += td;
+        }
+        csx[e] = dx / dis;
+        csy[e] = dy / dis;
+        csz[e] = dz / dis;
+    }
+    dLt[p] = t0;
+    dLt[Npz + p] = t1;
+    TdLt[p] = T0;
+    TdLt[Npz + p] = T1;
+}
+
+extern "C" int lpmb_fd_stiffness(lpmb_ctx *c, int emulate_side_effects)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(c->params.count("radius"), LPMB_ERR_STATE, "parameter radius not set");
+    LPMB_TRY(lpmb_matrix_alloc_values(c));
+    SellMatrix &K = c->K;
+    const double radius = param(c, "radius");
+    const double eps = LPMB_EPS;
+    const double h = eps * radius;  // stiffness.c:419: xtemp + EPS * radius
+    const int *nbr = fptr<int>(c, "neighbors");
+    const signed char *nsign = fptr<signed char>(c, "nsign"), *mirror = fptr<signed char>(c, "mirror");
+    const int *nbi = fptr<int>(c, "nb_initial");
+    const double *xyz = fptr<double>(c, "xyz");
+    const double *L0 = fptr<double>(c, "distance_initial"), *dLp0 = fptr<double>(c, "dLp0"), *brk = fptr<double>(c, "damage_broken");
+    const double *Tv = fptr<double>(c, "Tv"), *Kn = fptr<double>(c, "Kn");
+    double *F = fptr<double>(c, "F"), *Pin = fptr<double>(c, "Pin");
+    LPMB_REQUIRE(nbr && nsign && mirror && nbi && xyz && L0 && dLp0 && brk && Tv && Kn && F && Pin, LPMB_ERR_STATE, "fields missing");
+    double *Fs = emulate_side_effects ? F : nullptr, *Ps = emulate_side_effects ? Pin : nullptr;
+    if (c->dim == 3) {
+        LPMB_REQUIRE(c->nn <= 18 && c->nconn <= 64, LPMB_ERR_UNSUPPORTED, "fd_stiffness<3>: nn=%d nconn=%d", c->nn, c->nconn);
+        const size_t smem = sizeof(StarSmem<3, 18>);
+        auto kern = fd_stiffness_kernel<3, 18, 192>;
+        LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<c->N, 192, smem, c->stream>>>(c->N, c->Np, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, K.val, Fs, Ps);
+        LPMB_LAUNCH_CHECK(c);
+        symmetrize_kernel<3><<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, K.sptr, K.col, K.nbc, K.val);
+        LPMB_LAUNCH_CHECK(c);
+    } else {
+        LPMB_REQUIRE(c->nn <= 12 && c->nconn <= 32, LPMB_ERR_UNSUPPORTED, "fd_stiffness<2>: nn=%d nconn=%d", c->nn, c->nconn);
+        const size_t smem = sizeof(StarSmem<2, 12>);
+        auto kern = fd_stiffness_kernel<2, 12, 64>;
+        LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<c->N, 64, smem, c->stream>>>(c->N, c->Np, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, K.val, Fs, Ps);
+        LPMB_LAUNCH_CHECK(c);
+        symmetrize_kernel<2><<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, K.sptr, K.col, K.nbc, K.val);
+        LPMB_LAUNCH_CHECK(c);
+    }
+    K.values_ready = true;
+    if (emulate_side_effects) {
+        double *dL = fptr<double>(c, "dL"), *csx = fptr<double>(c, "csx"), *csy = fptr<double>(c, "csy"), *csz = fptr<double>(c, "csz");
+        double *dLt = fptr<double>(c, "dL_total"), *TdLt = fptr<double>(c, "TdL_total");
+        if (c->dim == 3)
+            fd_side_effects_kernel<3><<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, c->Np, h, nbr, nsign, mirror, nbi, xyz, L0, dLp0, brk, Tv, K.sptr, K.col, K.nbc, dL, csx, csy, csz, dLt, TdLt);
+        else
+            fd_side_effects_kernel<2><<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, c->Np, h, nbr, nsign, mirror, nbi, xyz, L0, dLp0, brk, Tv, K.sptr, K.col, K.nbc, dL, csx, csy, csz, dLt, TdLt);
+        LPMB_LAUNCH_CHECK(c);
+    }
+    return LPMB_OK;
+}
