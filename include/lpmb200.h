@@ -160,6 +160,15 @@ int lpmb_update_crack(lpmb_ctx *ctx);
 int lpmb_newton_iteration(lpmb_ctx *ctx, int plmode, int load_indicator, double rel, double abs_tol, int maxit,
                           int *cg_iterations, double *norm_residual);
 
+/* ---- device-resident driver helpers -------------------------------------------------------- */
+/* dst := src for two fields of identical shape (the driver's xyz_temp/F_temp/Pex_temp copies,
+ * lpmc_project.c:387-389) */
+int lpmb_field_copy(lpmb_ctx *ctx, const char *dst, const char *src);
+/* setDispBC / setForceBC for one table entry, src/boundary.c:12-70, applied to the resident
+ * xyz / dispBC_index / Pex (axis is 'x', 'y' or 'z') */
+int lpmb_apply_disp_bc(lpmb_ctx *ctx, int type, char axis, double step);
+int lpmb_apply_force_bc(lpmb_ctx *ctx, int type, double step_x, double step_y, double step_z);
+
 /* ---- multi-GPU (one process per GPU; particle slabs = contiguous index ranges) ------------- */
 /* 128-byte NCCL unique id; rank 0 creates it, the harness broadcasts it. */
 int lpmb_dist_unique_id(void *id128);

@@ -75,6 +75,9 @@ lib.lpmb_dist_unique_id.argtypes = [c_vp]
 lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
 lib.lpmb_dist_set_slab.argtypes = [c_vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
 lib.lpmb_synchronize.argtypes = [c_vp]
+lib.lpmb_field_copy.argtypes = [c_vp, C.c_char_p, C.c_char_p]
+lib.lpmb_apply_disp_bc.argtypes = [c_vp, C.c_int, C.c_char, C.c_double]
+lib.lpmb_apply_force_bc.argtypes = [c_vp, C.c_int, C.c_double, C.c_double, C.c_double]
 
 
 def declared_symbols() -> list[str]:
@@ -277,6 +280,15 @@ class Context:
                                          int(maxit or self.N * self.dim), C.byref(it), C.byref(nr)),
                ok=(0, NOTCONVERGED))
         return it.value, nr.value
+
+    def copy_field(self, dst: str, src: str):
+        _check(lib.lpmb_field_copy(self._h, dst.encode(), src.encode()))
+
+    def apply_disp_bc(self, type_: int, axis: str, step: float):
+        _check(lib.lpmb_apply_disp_bc(self._h, type_, axis.encode(), step))
+
+    def apply_force_bc(self, type_: int, sx: float, sy: float, sz: float):
+        _check(lib.lpmb_apply_force_bc(self._h, type_, sx, sy, sz))
 
     def synchronize(self):
         _check(lib.lpmb_synchronize(self._h))

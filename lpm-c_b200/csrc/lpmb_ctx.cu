@@ -341,6 +341,7 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
         return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    lpmb_grid_release(c);
     for (auto &kv : c->fields)
         cudaFree(kv.second.d);
     cudaFree(c->K.sptr);

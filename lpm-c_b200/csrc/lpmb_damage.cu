@@ -1,0 +1,293 @@
+// lpmb_damage.cu -- damage accumulation and bond breaking (compiled -fmad=false).
+//
+// Replaces, in the reference:
+//   updateDamageGeneral(file, step, plmode)       src/constitutive.c:149-164
+//   updateDuctileDamagePwiseNonlocal(file, step)  src/constitutive.c:1757-1862  (plmode 0)
+//   updateBrittleDamage(file, step, nbreak)       src/constitutive.c:1437-1526  (plmode 6)
+//
+// Nonlocal law: D_i += sum_j phi(d_ij) V Ddot_j / sum_j phi(d_ij) V over ALL particles with
+// d_ij < 3*damage_L in the initial configuration (self included).  The reference does this as an
+// O(N^2) all-pairs loop; here the candidates come from the uniform cell grid (lpmb_topology.cu) built
+// over xyz_initial with cell size 3*damage_L, i.e. 27 cells per particle.  The Gaussian uses exp(), so
+// this kernel is compared at 1e-12 relative, not bit for bit.
+#include "lpmb_internal.cuh"
+
+#define DT 128
+#define LPMB_PI 3.14159265358979323846
+
+__global__ void __launch_bounds__(DT)
+nonlocal_damage_kernel(int N, int Np, CellGrid g, const double *__restrict__ x0 /* xyz_initial */, double L, double thr, double Ac, double V,
+                       const double *__restrict__ dlambda, const double *__restrict__ triax, double *__restrict__ Dn /* damage_nonlocal[.][0] */)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    double Di = Dn[i];
+    if (Di > thr) {  // constitutive.c:1802-1807: frozen, clamped
+        if (Di > 1.0)
+            Dn[i] = 1.0;
+        return;
+    }
+    const double xi = x0[i], yi = x0[(size_t)Np + i], zi = x0[(size_t)2 * Np + i];
+    const double inv = 1.0 / g.cell;
+    int cx = (int)floor((xi - g.ox) * inv), cy = (int)floor((yi - g.oy) * inv), cz = (int)floor((zi - g.oz) * inv);
+    cx = cx < 0 ? 0 : (cx >= g.nx ? g.nx - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= g.ny ? g.ny - 1 : cy);
+    cz = cz < 0 ? 0 : (cz >= g.nz ? g.nz - 1 : cz);
+    const double cut = 3 * L;
+    double Ddot = 0, A = 0;
+    for (int dz = -1; dz <= 1; dz++) {
+        const int z = cz + dz;
+        if (z < 0 || z >= g.nz)
+            continue;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int y = cy + dy;
+            if (y < 0 || y >= g.ny)
+                continue;
+            for (int dx = -1; dx <= 1; dx++) {
+                const int x = cx + dx;
+                if (x < 0 || x >= g.nx)
+                    continue;
+                const int cidx = x + g.nx * (y + g.ny * z);
+                for (int t = g.start[cidx]; t < g.start[cidx + 1]; t++) {
+                    const int j = g.items[t];
+                    const double ax = x0[j] - xi, ay = x0[(size_t)Np + j] - yi, az = x0[(size_t)2 * Np + j] - zi;
+                    const double dis = sqrt(ax * ax + ay * ay + az * az);
+                    if (dis < cut) {
+                        double DdotLocal = 0;
+                        const double f = (1.0 + Ac * triax[j]);
+                        if (f > 0.0)
+                            DdotLocal = dlambda[j] * (1.0 + Ac * triax[j]);
+                        // DAM_PHI(x) = 1.0 / damage_L / sqrt(2*PI) * exp(-0.5*x*x / damage_L / damage_L)   (lpm.h:51)
+                        const double phi = 1.0 / L / sqrt(2 * LPMB_PI) * exp(-0.5 * dis * dis / L / L);
+                        Ddot += DdotLocal * phi * V;
+                        A += phi * V;
+                    }
+                }
+            }
+        }
+    }
+    if (Ddot > 0.0)
+        Dn[i] = Di + 1.0 / A * Ddot;
+}
+
+// constitutive.c:1828-1858 fused per bond: break if either end is beyond the threshold, then
+// damage_D = max(D_i, D_j) on intact bonds and damage_w = 1 - damage_D.
+__global__ void __launch_bounds__(DT)
+nonlocal_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, double thr, const double *__restrict__ Dn,
+                      double *__restrict__ broken, double *__restrict__ dD0, double *__restrict__ w, signed char *__restrict__ newly,
+                      int *__restrict__ count)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double Di = Dn[i];
+    const int n = nbi[i];
+    int k = 0;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const double Dj = Dn[nbr[e]];
+        double b = broken[e], d = dD0[e];
+        signed char nw = 0;
+        if (Di > thr || Dj > thr) {
+            if (fabs(b) > LPMB_EPS) {
+                b = 0.0;
+                d = 1.0;
+                nw = 1;
+                k++;
+            }
+        }
+        if (fabs(b) > LPMB_EPS)
+            d = Di < Dj ? Dj : Di;  // MAX(x,y) ((x) < (y) ? (y) : (x))
+        broken[e] = b;
+        dD0[e] = d;
+        w[e] = 1.0 - d;
+        newly[e] = nw;
+    }
+    if (k)
+        atomicAdd(count, k);
+}
+
+// brittle: candidates with dL/L0 >= critical_bstrain, appended to a device list (order restored on the host)
+__global__ void __launch_bounds__(DT)
+brittle_candidates_kernel(int N, int Np, int nn, const int *__restrict__ nbi, const double *__restrict__ dL, const double *__restrict__ L0,
+                          double crit, int cap, int *__restrict__ count, int *__restrict__ keys, double *__restrict__ strain)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const int n = nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const double s = dL[e] / L0[e];
+        if (s >= crit) {
+            const int slot = atomicAdd(count, 1);
+            if (slot < cap) {
+                keys[slot] = i * nn + j;
+                strain[slot] = s;
+            }
+        }
+    }
+}
+
+__global__ void brittle_apply_kernel(int nbreak, int nn, int Np, const int *__restrict__ keys, double *__restrict__ broken, double *__restrict__ dD0,
+                                     double *__restrict__ w)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbreak)
+        return;
+    const int i = keys[t] / nn, j = keys[t] % nn;
+    const size_t e = (size_t)j * Np + i;
+    dD0[e] = 1.0;
+    w[e] = 0.0;
+    broken[e] = 0.0;
+}
+
+extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int *pairs, int max_pairs)
+{
+    LPMB_REQUIRE(c && broken_out, LPMB_ERR_ARG, "lpmb_update_damage: null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    *broken_out = 0;
+    const int N = c->N, Np = c->Np, nn = c->nn;
+    const int g = lpmb_blocks(N, DT);
+    int *nbi = fptr<int>(c, "nb_initial"), *nbr = fptr<int>(c, "neighbors");
+    double *broken = fptr<double>(c, "damage_broken"), *dD0 = fptr<double>(c, "damage_D0"), *w = fptr<double>(c, "damage_w");
+    LPMB_REQUIRE(nbi && nbr && broken && dD0 && w, LPMB_ERR_STATE, "fields missing");
+    int *d_count;
+    LPMB_CUDA(cudaMalloc(&d_count, sizeof(int)));
+    LPMB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
+    int rc = LPMB_OK;
+    if (plmode == 0) {
+        for (const char *p : {"damage_L", "damage_threshold", "damagec_A", "particle_volume"})
+            if (!c->params.count(p)) {
+                cudaFree(d_count);
+                lpmb_set_error("parameter %s not set", p);
+                return LPMB_ERR_STATE;
+            }
+        const double L = param(c, "damage_L"), thr = param(c, "damage_threshold");
+        CellGrid *grid = nullptr;
+        const double *x0 = fptr<double>(c, "xyz_initial");
+        // (re)built every call (once per load step): the topology builder shares the per-context grid slot
+        rc = lpmb_grid_build(c, x0, 3 * L * 1.0000001, &grid);
+        if (rc != LPMB_OK) {
+            cudaFree(d_count);
+            return rc;
+        }
+        nonlocal_damage_kernel<<<g, DT, 0, c->stream>>>(N, Np, *grid, x0, L, thr, param(c, "damagec_A"), param(c, "particle_volume"),
+                                                        fptr<double>(c, "J2_dlambda"), fptr<double>(c, "J2_triaxiality"),
+                                                        fptr<double>(c, "damage_nonlocal0"));
+        LPMB_LAUNCH_CHECK(c);
+        signed char *newly = nullptr;
+        LPMB_CUDA(cudaMalloc(&newly, (size_t)nn * Np));
+        nonlocal_break_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, thr, fptr<double>(c, "damage_nonlocal0"), broken, dD0, w, newly, d_count);
+        LPMB_LAUNCH_CHECK(c);
+        int k = 0;
+        LPMB_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        *broken_out = k;
+        if (k > 0 && pairs && max_pairs > 0) {
+            // reference logging order: i ascending, then slot j ascending (constitutive.c:1829-1845)
+            std::vector<signed char> hn((size_t)nn * Np);
+            std::vector<int> hnbr((size_t)nn * Np);
+            LPMB_CUDA(cudaMemcpy(hn.data(), newly, hn.size(), cudaMemcpyDeviceToHost));
+            LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            int t = 0;
+            for (int i = 0; i < N && t < max_pairs; i++)
+                for (int j = 0; j < nn && t < max_pairs; j++)
+                    if (hn[(size_t)j * Np + i]) {
+                        pairs[2 * t] = i;
+                        pairs[2 * t + 1] = hnbr[(size_t)j * Np + i];
+                        t++;
+                    }
+        }
+        cudaFree(newly);
+    } else if (plmode == 6) {
+        LPMB_REQUIRE(c->params.count("critical_bstrain") && c->params.count("nbreak"), LPMB_ERR_STATE, "critical_bstrain / nbreak not set");
+        const int cap = 1 << 16;
+        int *keys;
+        double *strain;
+        LPMB_CUDA(cudaMalloc(&keys, cap * sizeof(int)));
+        LPMB_CUDA(cudaMalloc(&strain, cap * sizeof(double)));
+        brittle_candidates_kernel<<<g, DT, 0, c->stream>>>(N, Np, nn, nbi, fptr<double>(c, "dL"), fptr<double>(c, "distance_initial"),
+                                                           param(c, "critical_bstrain"), cap, d_count, keys, strain);
+        LPMB_LAUNCH_CHECK(c);
+        int k = 0;
+        LPMB_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (k > cap) {
+            cudaFree(keys);
+            cudaFree(strain);
+            cudaFree(d_count);
+            lpmb_set_error("updateBrittleDamage: %d candidate bonds (the reference's b_cr[] holds 400, constitutive.c:1444)", k);
+            return LPMB_ERR_UNSUPPORTED;
+        }
+        *broken_out = k;  // the reference returns the candidate count even when it breaks only nbreak of them
+        if (k > 0) {
+            std::vector<int> hk(k);
+            std::vector<double> hs(k);
+            LPMB_CUDA(cudaMemcpy(hk.data(), keys, k * sizeof(int), cudaMemcpyDeviceToHost));
+            LPMB_CUDA(cudaMemcpy(hs.data(), strain, k * sizeof(double), cudaMemcpyDeviceToHost));
+            // restore the reference's scan order (i, then j ascending == key ascending)
+            std::vector<int> ord(k);
+            for (int t = 0; t < k; t++)
+                ord[t] = t;
+            for (int a = 1; a < k; a++) {  // insertion sort by key (k is tiny)
+                const int v = ord[a];
+                int b = a - 1;
+                while (b >= 0 && hk[ord[b]] > hk[v]) {
+                    ord[b + 1] = ord[b];
+                    b--;
+                }
+                ord[b + 1] = v;
+            }
+            std::vector<int> bi(k);
+            std::vector<double> bs(k);
+            for (int t = 0; t < k; t++) {
+                bi[t] = hk[ord[t]];
+                bs[t] = hs[ord[t]];
+            }
+            const int nbreak = (int)param(c, "nbreak");
+            int first = 0;
+            if (k > nbreak) {
+                // the reference's shell sort, verbatim in behaviour (not stable: ties resolved exactly as there)
+                for (int r = k / 2; r >= 1; r = r / 2)
+                    for (int a = r; a < k; ++a) {
+                        const int ti = bi[a];
+                        const double tb = bs[a];
+                        int b = a - r;
+                        while (b >= 0 && bs[b] > tb) {
+                            bs[b + r] = bs[b];
+                            bi[b + r] = bi[b];
+                            b = b - r;
+                        }
+                        bs[b + r] = tb;
+                        bi[b + r] = ti;
+                    }
+                first = k - nbreak;
+            }
+            const int nb = k - first;
+            LPMB_CUDA(cudaMemcpy(keys, bi.data() + first, nb * sizeof(int), cudaMemcpyHostToDevice));
+            brittle_apply_kernel<<<lpmb_blocks(nb, 128), 128, 0, c->stream>>>(nb, nn, Np, keys, broken, dD0, w);
+            c->launches++;
+            if (pairs && max_pairs > 0) {
+                std::vector<int> hnbr((size_t)nn * Np);
+                LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                for (int t = 0; t < nb && t < max_pairs; t++) {
+                    const int i = bi[first + t] / nn, j = bi[first + t] % nn;
+                    pairs[2 * t] = i;
+                    pairs[2 * t + 1] = hnbr[(size_t)j * Np + i];
+                }
+            }
+        }
+        cudaFree(keys);
+        cudaFree(strain);
+    } else if (plmode == 5) {
+        cudaFree(d_count);
+        lpmb_set_error("updateDamageGeneral: plmode 5 (updateDuctileDamageBwiseLocal) is not built (0 and 6 are)");
+        return LPMB_ERR_UNSUPPORTED;
+    }
+    // any other plmode: the reference's dispatcher does nothing and returns 0 (constitutive.c:149-164)
+    cudaFree(d_count);
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}

@@ -136,6 +136,21 @@ static inline int lpmb_blocks(long long work, int threads) { return (int)((work 
 int lpmb_upload_soa_f64(lpmb_ctx *c, const double *host, double *d_dst, int comps);
 int lpmb_download_soa_f64(lpmb_ctx *c, const double *d_src, double *host, int comps);
 
+// uniform cell grid (lpmb_topology.cu), shared by the neighbour search and the nonlocal damage gather
+struct CellGrid {
+    double ox = 0, oy = 0, oz = 0, cell = 1;
+    int nx = 1, ny = 1, nz = 1;
+    int *start = nullptr;  // [ncells+1]
+    int *items = nullptr;  // [N] particle ids, ascending inside each cell
+    long long ncells = 0;
+};
+int lpmb_grid_build(lpmb_ctx *c, const double *d_xyz, double cell_size, CellGrid **out);
+void lpmb_grid_release(lpmb_ctx *c);
+int lpmb_set_connectivity_device(lpmb_ctx *c, const int *d_conn);
+int lpmb_derive_topology(lpmb_ctx *c, bool initial_geometry);
+int lpmb_compute_stress(lpmb_ctx *c);
+int lpmb_refresh_mask(lpmb_ctx *c);
+
 // solver-side entry points used across TUs
 int lpmb_cg_alloc(lpmb_ctx *c);
 int lpmb_matrix_alloc_values(lpmb_ctx *c);

@@ -6,9 +6,6 @@
     lpmb_set_error(name ": not implemented in this build");           \
     return LPMB_ERR_UNSUPPORTED
 
-extern "C" int lpmb_build_topology(lpmb_ctx *, double, double) { LPMB_STUB("lpmb_build_topology"); }
-extern "C" int lpmb_update_damage(lpmb_ctx *, int, int *, int *, int) { LPMB_STUB("lpmb_update_damage"); }
-extern "C" int lpmb_newton_iteration(lpmb_ctx *, int, int, double, double, int, int *, double *) { LPMB_STUB("lpmb_newton_iteration"); }
 extern "C" int lpmb_dist_unique_id(void *) { LPMB_STUB("lpmb_dist_unique_id"); }
 extern "C" int lpmb_dist_init(lpmb_ctx *, const void *, int, int) { LPMB_STUB("lpmb_dist_init"); }
 extern "C" int lpmb_dist_set_slab(lpmb_ctx *, long long, long long, long long, int, int) { LPMB_STUB("lpmb_dist_set_slab"); }

@@ -1,0 +1,136 @@
+"""GPU parity at trajectory level: whole load steps run device-resident (lpm-c_b200/driver.py over the C
+ABI: FD tangent -> BCs -> predictor -> Newton loop with masked CG -> nonlocal damage -> crack update)
+against the reference's own run of the same steps.
+
+Tolerance: north_star asks 1e-9 relative on displacements, bond forces and reaction forces.  CG stops at
+1e-4 relative residual and the summation order inside SpMV/dot products differs from the oracle's, so
+agreement is not bit-exact here; measured ~1e-12."""
+import numpy as np
+import pytest
+
+from helpers import get_slots, make_ctx, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def test_two_plastic_load_steps_match_golden(lpm, golden):
+    g = golden
+    c = make_ctx(lpm, g)
+    c.compute_dl()
+    dbp, fbp = [(1, "z", 0.0)], [(2, 0.0, 0.0, -2000.0)]
+    for step in (1, 2):
+        log = lpm.driver.load_step(c, 0, dbp, fbp)
+        assert log.newton_iterations == int(g["newton_counts"][step - 1])
+        assert log.cg_iterations[0] == int(g[f"s{step}.n0.cg_iters"][0])
+        assert log.broken == int(g[f"s{step}.dam.broken"][0]) == 0
+        s = f"s{step}.crack"
+        u_ref = g[f"{s}.xyz"] - g["setup.xyz"]
+        u = c.get_field("xyz") - g["setup.xyz"]
+        assert rel_err(u, u_ref) <= TOL
+        assert rel_err(c.get_field("F"), g[f"{s}.F"]) <= TOL
+        assert rel_err(c.get_field("Pin"), g[f"{s}.Pin"]) <= TOL
+        assert rel_err(c.get_field("stress_tensor"), g[f"{s}.stress_tensor"]) <= TOL
+        assert rel_err(c.get_field("damage_w"), g[f"{s}.damage_w"]) <= TOL
+        assert rel_err(get_slots(c, "damage_nonlocal", 2), g[f"{s}.damage_nonlocal"]) <= TOL
+        assert rel_err(get_slots(c, "dLp", 3), g[f"s{step}.commit.dLp"]) <= TOL
+        assert rel_err(get_slots(c, "J2_alpha", 3), g[f"s{step}.commit.J2_alpha"]) <= TOL
+        # reaction force = Pin on the constrained DoFs (stiffness.c:530-531)
+        bc = g[f"s{step}.bc.dispBC_index"].reshape(-1, 3)
+        rea = c.get_field("Pin").reshape(-1, 3)[bc == 0]
+        rea_ref = g[f"{s}.Pin"].reshape(-1, 3)[bc == 0]
+        assert rel_err(rea, rea_ref) <= TOL
+    assert g["s2.crack.damage_w"].min() < 1.0       # damage really accumulated
+    c.close()
+
+
+def test_nonlocal_damage_kernel(lpm, golden):
+    """updateDuctileDamagePwiseNonlocal (constitutive.c:1757-1862) from the reference's own inputs; exp()
+    differs from glibc by <= 1-2 ulp, hence 1e-12 instead of bit-exact"""
+    from helpers import put_state
+    g = golden
+    c = make_ctx(lpm, g)
+    put_state(c, g, "s1.n2.bf")
+    # inputs at the time of the call = state after the last Newton iteration of step 1; the fixture keeps the
+    # first three iterations only, so take dlambda / triaxiality from the reference's post-damage snapshot
+    for n in ("J2_dlambda", "J2_triaxiality", "damage_broken"):
+        c.set_field(n, g[f"s1.dam.{n}"])
+    c.set_field("damage_nonlocal0", np.zeros(216))
+    c.set_field("damage_D0", np.zeros((216, 18)))
+    broken, pairs = c.update_damage(0)
+    assert broken == 0 and len(pairs) == 0
+    assert rel_err(c.get_field("damage_nonlocal0"), g["s1.dam.damage_nonlocal"][:, 0]) <= 1e-12
+    assert rel_err(c.get_field("damage_w"), g["s1.dam.damage_w"]) <= 1e-12
+    assert rel_err(c.get_field("damage_D0"), g["s1.dam.damage_D"][:, :, 0]) <= 1e-12
+    c.close()
+
+
+def test_nonlocal_damage_breaks_bonds_like_reference(lpm, ref):
+    """force damage over the threshold at one particle: same broken set, same log order, same weights"""
+    r = ref
+    r.setup_sc(box=(-0.2, 2.7, -0.2, 2.7, -0.2, 2.7), top_z=2.5)
+    N = r.N
+    rng = np.random.default_rng(20240607)
+    dl = np.abs(rng.standard_normal(N)) * 1e-3
+    dl[100] = 2.0                                   # pushes D over damage_threshold=0.9 around particle 100
+    tri = rng.standard_normal(N) * 0.3
+    r.put("J2_dlambda", dl)
+    r.put("J2_triaxiality", tri)
+    c = lpm.Context(N, 3, 2, 18, 61)
+    c.set_params(radius=r.gd("radius"), particle_volume=r.gd("particle_volume"), damage_L=r.gd("damage_L"),
+                 damage_threshold=r.gd("damage_threshold"), damagec_A=r.gd("damagec_A"))
+    c.set_field("xyz", r.get("xyz"))
+    c.set_field("xyz_initial", r.get("xyz_initial"))
+    c.set_neighbors(r.get("neighbors"), r.get("nsign"))
+    c.set_field("J2_dlambda", dl)
+    c.set_field("J2_triaxiality", tri)
+    import tempfile, os
+    with tempfile.NamedTemporaryFile(delete=False) as f:
+        path = f.name
+    k_ref = r.lib.updateDamageGeneral(path.encode(), 1, 0)
+    lines = [tuple(map(int, ln.split())) for ln in open(path).read().splitlines()[1:] if ln.strip()]
+    os.unlink(path)
+    k, pairs = c.update_damage(0)
+    assert k == k_ref > 0
+    assert [tuple(p) for p in pairs] == lines
+    assert np.array_equal(c.get_field("damage_broken"), r.get("damage_broken"))
+    assert rel_err(c.get_field("damage_w"), r.get("damage_w")) <= 1e-12
+    assert rel_err(c.get_field("damage_nonlocal0"), r.get("damage_nonlocal")[:, 0]) <= 1e-12
+    c.close()
+
+
+def test_default_case_first_steps_vs_reference(lpm, ref):
+    """C1 (default driver, 21^3): three load steps device-resident vs the reference run side by side"""
+    r = ref
+    r.setup_sc()
+    N = r.N
+    c = lpm.Context(N, 3, 2, 18, 61)
+    c.set_params(radius=r.gd("radius"), particle_volume=r.gd("particle_volume"), J2_H=r.gd("J2_H"), J2_xi=r.gd("J2_xi"),
+                 damage_L=r.gd("damage_L"), damage_threshold=r.gd("damage_threshold"), damagec_A=r.gd("damagec_A"))
+    xyz0 = r.get("xyz_initial")
+    c.set_field("xyz", r.get("xyz"))
+    c.set_field("xyz_initial", xyz0)
+    c.build_topology(r.gd("neighbor1_cutoff"), r.gd("neighbor2_cutoff"))
+    c.set_field("type", r.get("type"))
+    c.set_field("sigmay", r.get("sigmay"))
+    c.calc_kntv(r.get("Ce"))
+    c.compute_dl()
+    dbp, fbp = [(1, "z", 0.0)], [(2, 0.0, 0.0, -2000.0)]
+    expect_newton = [2, 2, 1]                     # 2 2 1 1 1 ...
+    expect_cg_first = 80
+    for step in range(1, 4):
+        ni_ref, _ = r.load_step(step, dbp, fbp)
+        log = lpm.driver.load_step(c, 0, dbp, fbp)
+        assert log.newton_iterations == ni_ref == expect_newton[step - 1]
+        if step == 1:
+            assert log.cg_iterations[:2] == [expect_cg_first, 106]
+        u, u_ref = c.get_field("xyz") - xyz0, r.get("xyz") - xyz0
+        assert rel_err(u, u_ref) <= TOL
+        assert rel_err(c.get_field("F"), r.get("F")) <= TOL
+        assert rel_err(c.get_field("Pin"), r.get("Pin")) <= TOL
+    # known answer: mean z-displacement of the loaded (type 2 = bottom? no: type 1 top fixed, type 2 loaded) layer
+    typ = r.get("type")
+    uz = (c.get_field("xyz") - xyz0)[typ == 2, 2]
+    assert np.isfinite(uz).all()
+    c.close()
