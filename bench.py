@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- Newton iterations / second of the LPM hot path on B200, with the SpMV HBM roofline.
+
+Metric (BASELINE.json): "Newton iters/sec + PCG SpMV HBM GB/s at 1/2/4/8 B200 vs MKL host CPU".
+  value     = Newton iterations / s, whole job, state resident in HBM
+  roofline  = the CG SpMV (dominant kernel) against the measured HBM peak
+  e2e       = the same Newton iteration through the C ABI with HOST buffers (H2D + D2H every step)
+  step      = one pass of the reference's Newton loop body (src/lpmc_project.c:426-464):
+              switchStateV(0); displacement-BC treatment of K/residual; solverCG (+ xyz += disp);
+              computeBondForceGeneral(plmode 0: J2 elastoplastic); computeStress; updateRR; ||residual||.
+              Every step replays Newton iteration 0 of load step 1 from the same snapshot, so all steps
+              do identical work (the snapshot restore is inside the timed region; it is two device copies).
+  workload  = BASELINE.json configs[4] ("C5"): examples/CT_sc_ductile_nonlocal.c physics (E=115e3, nu=0.28,
+              sigma_y=955, H=2401.8, damagec_A=400, damage_L=0.6, threshold 0.85) on a synthetic simple-cubic
+              block of n^3 particles (n=216 -> 10 077 696 particles, 30.2M DoF), bottom z-layer fixed in z,
+              top z-layer displaced in z (displacement control like the CT example).
+
+Launch:  python bench.py --gpus N --steps K --warmup W      (N>1: under torchrun, one rank per GPU)
+         python bench.py --impl reference ...               (the reference's own CPU code, see below)
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "newton_iterations_per_second"
+UNIT = "Newton it/s"
+
+# C5 family physics (examples/CT_sc_ductile_nonlocal.c:171,195-202,230-235) on radius 0.25
+PHYS = dict(radius=0.25, E0=115e3, mu0=0.28, sigmay=955.0, J2_xi=0.0, J2_H=2401.8, damagec_A=400.0, damage_L=0.6,
+            damage_threshold=0.85, damageb_A=10.0, nbreak=20, critical_bstrain=1.0e-2)
+STRAIN_STEP = 1.0e-2   # top layer displaced by 1 % of the block height (plastic from the first iteration)
+
+
+def peaks():
+    try:
+        p = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def build_workload(lpm, n: int, device: int):
+    """set up the n^3 block on the device: lattice -> O(N) topology -> material -> first FD tangent -> BCs ->
+    predictor -> residual; snapshot for replay"""
+    t0 = time.time()
+    h = 2 * PHYS["radius"]
+    N = n ** 3
+    i = np.arange(N, dtype=np.int64)
+    xyz = np.empty((N, 3))
+    xyz[:, 0] = h * (i % n)
+    xyz[:, 1] = h * ((i // n) % n)
+    xyz[:, 2] = h * (i // (n * n))
+    typ = np.zeros(N, dtype=np.int32)
+    typ[i // (n * n) == n - 1] = 1      # top layer   (type 1: displaced)
+    typ[i // (n * n) == 0] = 2          # bottom layer (type 2: fixed in z)
+    c = lpm.Context(N, 3, 2, 18, 61, device=device)
+    E0, mu0 = PHYS["E0"], PHYS["mu0"]
+    C11 = E0 * (1.0 - mu0) / (1.0 + mu0) / (1.0 - 2.0 * mu0)
+    C12 = E0 * mu0 / (1.0 + mu0) / (1.0 - 2.0 * mu0)
+    C44 = E0 / 2.0 / (1.0 + mu0)
+    c.set_params(radius=PHYS["radius"], particle_volume=h ** 3, J2_H=PHYS["J2_H"], J2_xi=PHYS["J2_xi"],
+                 damage_L=PHYS["damage_L"], damage_threshold=PHYS["damage_threshold"], damagec_A=PHYS["damagec_A"],
+                 nbreak=PHYS["nbreak"], critical_bstrain=PHYS["critical_bstrain"])
+    c.set_field("xyz", xyz)
+    c.set_field("xyz_initial", xyz)
+    del xyz
+    c.build_topology(h, np.sqrt(2.0) * h)
+    c.set_field("type", typ)
+    c.set_field("sigmay", np.full(N, PHYS["sigmay"]))
+    c.calc_kntv(np.tile([C11, C12, C44], (3, 1)))
+    c.compute_dl()
+    t1 = time.time()
+    # load step 1 up to the first Newton iteration (lpmc_project.c:387-414)
+    c.copy_field("xyz_temp", "xyz")
+    c.copy_field("F_temp", "F")
+    c.copy_field("Pex_temp", "Pex")
+    c.fd_stiffness(False)
+    c.synchronize()
+    t2 = time.time()
+    c.apply_disp_bc(2, "z", 0.0)
+    c.apply_disp_bc(1, "z", STRAIN_STEP * h * (n - 1))
+    c.bond_force(4)
+    nr, nf = c.update_rr()
+    c.copy_field("xyz_save", "xyz")
+    c.copy_field("residual_save", "residual")
+    c.synchronize()
+    info = {"N": N, "n": n, "setup_s": round(t1 - t0, 2), "fd_assembly_s": round(t2 - t1, 3), "norm_residual0": nr,
+            "norm_reaction0": nf}
+    return c, info
+
+
+def one_step(c):
+    c.copy_field("xyz", "xyz_save")
+    c.copy_field("residual", "residual_save")
+    return c.newton_iteration(0, 1)
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lpm = importlib.import_module("lpm-c_b200")
+    if lpm.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    if world > 1:
+        from importlib import import_module
+        return import_module("lpm-c_b200.dist_bench").run(args, lpm, dist, rank, world, local)
+
+    n = args.n
+    c, info = build_workload(lpm, n, local)
+    N = info["N"]
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        c.synchronize()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        it, nr = one_step(c)
+    barrier()
+    c.set_profiling(True)
+    launches0 = c.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(c.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    iters = []
+    for _ in range(args.steps):
+        it, nr = one_step(c)
+        iters.append(it)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = c.launches - launches0
+    spmv_ms, spmv_calls = c.get_profile()
+    c.set_profiling(False)
+    ms_per_step = ms_total / args.steps
+    value = 1000.0 / ms_per_step
+    spmv_avg_ms = spmv_ms / max(1, spmv_calls)
+    alg_bytes = c.spmv_bytes()
+    achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(ROOT / "profiles" / "spmv_dram_traffic.json"))
+        if int(prof.get("n", -1)) == n:
+            traffic = prof["dram_bytes_per_launch"]
+    except Exception:
+        pass
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    nd = 3 * N
+    h_xyz = torch.empty((N, 3), dtype=torch.float64, pin_memory=True).numpy()
+    h_res = torch.empty(nd, dtype=torch.float64, pin_memory=True).numpy()
+    h_bc = torch.empty(nd, dtype=torch.int32, pin_memory=True).numpy()
+    h_fix = torch.empty(nd, dtype=torch.int32, pin_memory=True).numpy()
+    o_xyz = torch.empty((N, 3), dtype=torch.float64, pin_memory=True).numpy()
+    o_disp = torch.empty(nd, dtype=torch.float64, pin_memory=True).numpy()
+    o_pin = torch.empty(nd, dtype=torch.float64, pin_memory=True).numpy()
+    o_res = torch.empty(nd, dtype=torch.float64, pin_memory=True).numpy()
+    h_xyz[:] = c.get_field("xyz_save")
+    h_res[:] = c.get_field("residual_save")
+    h_bc[:] = c.get_field("dispBC_index")
+    h_fix[:] = c.get_field("fix_index")
+    capi = importlib.import_module("lpm-c_b200.capi")
+
+    def e2e_step():
+        for nm, a in (("xyz", h_xyz), ("residual", h_res), ("dispBC_index", h_bc), ("fix_index", h_fix)):
+            capi._check(capi.lib.lpmb_field_set(c._h, nm.encode(), a.ctypes.data, a.size))
+        it, nr = c.newton_iteration(0, 1)
+        for nm, a in (("xyz", o_xyz), ("disp", o_disp), ("Pin", o_pin), ("residual", o_res)):
+            capi._check(capi.lib.lpmb_field_get(c._h, nm.encode(), a.ctypes.data, a.size))
+        return it, nr
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        it_e, nr_e = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = h_xyz.nbytes + h_res.nbytes + h_bc.nbytes + h_fix.nbytes
+    d2h = o_xyz.nbytes + o_disp.nbytes + o_pin.nbytes + o_res.nbytes
+    assert np.isfinite(o_xyz).all() and np.isfinite(nr_e)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {n}^3 lattice, "
+                               f"{N} particles, {nd} DoF; Newton iteration 0 of load step 1 replayed from a snapshot",
+                   "lattice_n": n, "particles": N, "dof": nd, "cg_iterations_per_step": iters,
+                   "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
+                   "l2": "inputs larger than L2 (matrix %.1f GB)" % (c.spmv_bytes_stored() / 1e9),
+                   "setup_s": info["setup_s"], "fd_assembly_s": info["fd_assembly_s"], "parallelism": "1 GPU"},
+        "roofline": {"bound": "hbm", "kernel": "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap)", "achieved": achieved,
+                     "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                     "stored_bytes_per_launch": c.spmv_bytes_stored(), "avg_launch_ms": spmv_avg_ms,
+                     "launches_timed": spmv_calls, "share_of_step": spmv_ms / ms_total},
+        "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference_sample(args, n_full=n)
+    c.close()
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: int = 1) -> dict:
+    """The reference's OWN functions (oracle/_ref = its unmodified sources + open MKL stand-in, NOT Intel MKL)
+    timed on the host cores on a bounded sample of the workload: the same physics / BCs / Newton iteration on an
+    m^3 block, extrapolated to n_full^3 with the per-particle cost and the measured CG-iterations ~ n law."""
+    from oracle import ref as oref
+    if not oref.available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    m = args.cpu_sample_n
+    cores = args.cpu_threads or (os.cpu_count() or 1)
+    steps = steps or args.cpu_steps
+    r = oref.RefLPM.instance()
+    r.threads(cores)
+    hi = 0.5 * (m - 1)
+    for extra in (0.0, 0.25, -0.2):
+        box = (-0.2, hi + extra, -0.2, hi + extra, -0.2, hi + extra)
+        r.setup_sc(box=box, radius=PHYS["radius"], E0=PHYS["E0"], mu0=PHYS["mu0"],
+                   plmode=0, sigmay=PHYS["sigmay"], J2_xi=PHYS["J2_xi"], J2_H=PHYS["J2_H"], nbreak=PHYS["nbreak"],
+                   critical_bstrain=PHYS["critical_bstrain"], damageb_A=PHYS["damageb_A"], damagec_A=PHYS["damagec_A"],
+                   damage_threshold=PHYS["damage_threshold"], damage_L=PHYS["damage_L"], top_z="auto")
+        if r.N == m ** 3:
+            break
+    N = r.N
+    L = r.lib
+    height = float(r.get("xyz")[:, 2].max() - r.get("xyz")[:, 2].min())
+    # reference types from setup_sc: 1 = top layer, 2 = bottom layer; same BCs as the GPU arm
+    L.omp_set_num_threads(3)   # the author's nt_force for the racy FD assembly (lpmc_project.c:57,391)
+    t0 = time.perf_counter()
+    r.begin_step([(2, "z", 0.0), (1, "z", STRAIN_STEP * height)], [])
+    t_fd = time.perf_counter() - t0
+    L.omp_set_num_threads(cores)
+    xyz_s, res_s = r.get("xyz"), r.get("residual")
+    times, t_solve, its = [], [], []
+
+    def timed_solve():
+        a = time.perf_counter()
+        L.solverCG()
+        t_solve.append(time.perf_counter() - a)
+        its.append(L.lpmb_shim_last_itercount())
+
+    for k in range(warmup + steps):
+        r.put("xyz", xyz_s)
+        r.put("residual", res_s)
+        a = time.perf_counter()
+        r.newton_iteration(hooks={"solve": timed_solve})
+        if k >= warmup:
+            times.append(time.perf_counter() - a)
+    t_step = float(np.mean(times))
+    t_cg = float(np.mean(t_solve[warmup:]))
+    it_s = int(its[-1])
+    scale_n = (n_full ** 3) / N
+    t_full = t_cg * scale_n * (n_full / m) + (t_step - t_cg) * scale_n
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": (f"reference's own switchStateV/setDispBC_stiffnessUpdate3D/solverCG/computeBondForceGeneral(0)/updateRR "
+                       f"(unmodified sources + open MKL stand-in, not Intel MKL) on an SC {m}^3 block ({N} particles): "
+                       f"{t_step:.3f} s per Newton iteration ({it_s} CG its, solverCG {t_cg:.3f} s), {steps} timed; "
+                       f"extrapolated to {n_full}^3 as t_cg*(N/Ns)*(n/m) + t_rest*(N/Ns) (CG iterations grow ~ n)"),
+            "sample_newton_it_per_s": 1.0 / t_step, "sample_particles": N, "sample_cg_iterations": it_s,
+            "sample_fd_assembly_s_3threads": t_fd}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    base = cpu_reference_sample(args, n_full=args.n, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    if base["value"] is None:
+        print(json.dumps({"impl": "reference", "unavailable": base["sample"]}), flush=True)
+        return
+    N = args.n ** 3
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {args.n}^3 lattice, {N} particles; "
+                                  "Newton iteration 0 of load step 1", "lattice_n": args.n, "particles": N,
+                      "parallelism": f"{base['cores']} host threads (OpenMP)"},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("LPMB_BENCH_N", 216)), help="lattice points per side")
+    ap.add_argument("--cpu-sample-n", type=int, default=40)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,11 @@ long long lpmb_spmv_bytes(lpmb_ctx *ctx);
 /* bytes the device format actually streams (SELL padding included) */
 long long lpmb_spmv_bytes_stored(lpmb_ctx *ctx);
 
+/* live profiling of the dominant kernel: when on, every CG SpMV launch is bracketed by CUDA events on
+ * the context stream; lpmb_get_profile returns the accumulated device time and launch count */
+int lpmb_set_profiling(lpmb_ctx *ctx, int on);
+int lpmb_get_profile(lpmb_ctx *ctx, double *spmv_ms_total, long long *spmv_calls);
+
 /* ---- linear solve -------------------------------------------------------------------------- */
 /* DoF mask: 1 = free, 0 = constrained (dispBC_index[k] && fix_index[k]); NULL = all free. */
 int lpmb_set_dof_mask(lpmb_ctx *ctx, const int *dispBC_index, const int *fix_index);

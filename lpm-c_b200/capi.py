@@ -75,6 +75,8 @@ lib.lpmb_dist_unique_id.argtypes = [c_vp]
 lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
 lib.lpmb_dist_set_slab.argtypes = [c_vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
 lib.lpmb_synchronize.argtypes = [c_vp]
+lib.lpmb_set_profiling.argtypes = [c_vp, C.c_int]
+lib.lpmb_get_profile.argtypes = [c_vp, c_dp, C.POINTER(C.c_longlong)]
 lib.lpmb_field_copy.argtypes = [c_vp, C.c_char_p, C.c_char_p]
 lib.lpmb_apply_disp_bc.argtypes = [c_vp, C.c_int, C.c_char, C.c_double]
 lib.lpmb_apply_force_bc.argtypes = [c_vp, C.c_int, C.c_double, C.c_double, C.c_double]
@@ -145,11 +147,11 @@ class Context:
 
     def _shape(self, name: str):
         N, nn, dim = self.N, self.nn, self.dim
-        comps = {"xyz": 3, "xyz_initial": 3, "xyz_temp": 3, "dL_total": 2, "TdL_total": 2, "ddL_total": 2,
+        comps = {"xyz": 3, "xyz_initial": 3, "xyz_temp": 3, "xyz_save": 3, "dL_total": 2, "TdL_total": 2, "ddL_total": 2,
                  "TddL_total": 2, "stress_tensor": 6, "strain_tensor": 6, "J2_beta0": 6, "J2_beta1": 6, "J2_beta2": 6}
         if name in comps:
             return (N, comps[name])
-        if name in ("residual", "Pex", "Pex_temp", "disp", "dispBC_index", "fix_index"):
+        if name in ("residual", "residual_save", "Pex", "Pex_temp", "disp", "dispBC_index", "fix_index"):
             return (N * dim,)
         if name == "Pin":
             return (N * 3,)
@@ -280,6 +282,14 @@ class Context:
                                          int(maxit or self.N * self.dim), C.byref(it), C.byref(nr)),
                ok=(0, NOTCONVERGED))
         return it.value, nr.value
+
+    def set_profiling(self, on: bool = True):
+        _check(lib.lpmb_set_profiling(self._h, int(on)))
+
+    def get_profile(self):
+        ms, calls = C.c_double(), C.c_longlong()
+        _check(lib.lpmb_get_profile(self._h, C.byref(ms), C.byref(calls)))
+        return ms.value, calls.value
 
     def copy_field(self, dst: str, src: str):
         _check(lib.lpmb_field_copy(self._h, dst.encode(), src.encode()))

@@ -74,6 +74,8 @@ static const FieldSpec kSpecs[] = {
     {"disp", FK_DOF, FT_F64, -1, 0},
     {"dispBC_index", FK_DOF, FT_I32, -1, 1}, {"fix_index", FK_DOF, FT_I32, -1, 1},
     {"Pin", FK_PIN, FT_F64, 3, 0},
+    // snapshots used by harnesses to replay an iteration from the same state
+    {"xyz_save", FK_PART, FT_F64, 3, 0}, {"residual_save", FK_DOF, FT_F64, -1, 0},
 };
 
 static const FieldSpec *find_spec(const char *name)
@@ -342,6 +344,8 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     lpmb_grid_release(c);
+    for (auto &e : c->prof_events)
+        cudaEventDestroy(e);
     for (auto &kv : c->fields)
         cudaFree(kv.second.d);
     cudaFree(c->K.sptr);

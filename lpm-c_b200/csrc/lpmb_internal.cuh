@@ -102,6 +102,11 @@ struct lpmb_ctx {
     // multi-GPU
     void *nccl = nullptr;
     int rank = 0, world = 1;
+    // optional live profiling of the dominant kernel (CUDA events around every CG SpMV launch)
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    double prof_spmv_ms = 0.0;
+    long long prof_spmv_calls = 0;
 };
 
 // registry helpers (lpmb_ctx.cu)

@@ -706,9 +706,19 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     LPMB_LAUNCH_CHECK(c);
     const int batch = 16;
     int parity = 0, issued = 0;
+    if (c->profile && c->prof_events.empty()) {
+        c->prof_events.resize(2 * batch);
+        for (auto &e : c->prof_events)
+            LPMB_CUDA(cudaEventCreate(&e));
+    }
     for (;;) {
+        const int issued0 = issued;
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
+            if (c->profile)
+                LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b], c->stream));
             LPMB_TRY(launch_spmv(c, w.p, w.ap, true, use_mask));  // partials -> part_a (w.partials)
+            if (c->profile)
+                LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b + 1], c->stream));
             cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, part_a, sg, part_b, w.scal, parity);
             LPMB_LAUNCH_CHECK(c);
             cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, part_b, vg, w.scal, parity, maxit);
@@ -719,6 +729,16 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
         }
         LPMB_CUDA(cudaMemcpyAsync(w.h_scal, w.scal, S_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
         LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->profile) {
+            // only launches that did work count (after convergence the kernels return immediately)
+            const int done_iters = (int)w.h_scal[S_ITER];
+            for (int b = 0; issued0 + b < issued && issued0 + b < done_iters; b++) {
+                float ms = 0.f;
+                LPMB_CUDA(cudaEventElapsedTime(&ms, c->prof_events[2 * b], c->prof_events[2 * b + 1]));
+                c->prof_spmv_ms += ms;
+                c->prof_spmv_calls++;
+            }
+        }
         if (w.h_scal[S_DONE] != 0.0 || issued >= maxit)
             break;
     }
@@ -795,6 +815,25 @@ extern "C" int lpmb_solve_cg(lpmb_ctx *c, const double *rhs, double *disp, doubl
         return rc;
     LPMB_TRY(lpmb_field_get(c, "disp", disp, n));
     return rc;
+}
+
+extern "C" int lpmb_set_profiling(lpmb_ctx *c, int on)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    c->profile = on != 0;
+    c->prof_spmv_ms = 0.0;
+    c->prof_spmv_calls = 0;
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_get_profile(lpmb_ctx *c, double *spmv_ms_total, long long *spmv_calls)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    if (spmv_ms_total)
+        *spmv_ms_total = c->prof_spmv_ms;
+    if (spmv_calls)
+        *spmv_calls = c->prof_spmv_calls;
+    return LPMB_OK;
 }
 
 extern "C" int lpmb_spmv_host(lpmb_ctx *c, const double *x, double *y)

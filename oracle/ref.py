@@ -295,6 +295,8 @@ class RefLPM:
         radius = self.gd("radius")
         if top_z is None:
             top_z = self.darr("box", 6)[5] - 0.2
+        elif top_z == "auto":  # other boxes: the actual top lattice layer
+            top_z = float(self.d2("xyz", N, 3)[:, 2].max())
         ntype = 0
         self.set_ptr("type", L.allocInt1D(N, ntype))
         ntype += 1

@@ -36,16 +36,41 @@ void lpmb_shim_reset_counters(void)
 
 /* ------------------------------------------------------------------ CBLAS */
 
+/* Pairwise (cascade) summation, base blocks of 32 summed left to right: rounding error grows like
+ * log2(n)*eps instead of n*eps.  MKL's own ddot is blocked/vectorised (not a naive loop) and its
+ * exact order is unknowable here; a naive loop would put ~n*eps = 3e-12 of noise into every CG dot
+ * product at n = 27 783, which CG amplifies to ~4e-9 in the bond forces after three load steps --
+ * i.e. the oracle's own rounding noise would dominate the 1e-9 parity budget.  LPMB_SHIM_DOT=naive
+ * restores the plain loop (used to measure exactly that sensitivity). */
+static int g_dot_naive = -1;
+static double dot_pairwise(const int n, const double *a, const double *b)
+{
+    if (n <= 32) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++)
+            s += a[i] * b[i];
+        return s;
+    }
+    const int h = (n / 2 + 31) & ~31;
+    return dot_pairwise(h, a, b) + dot_pairwise(n - h, a + h, b + h);
+}
+
 static double dot_n(const int n, const double *a, const double *b)
 {
     double s = 0.0;
+    if (g_dot_naive < 0) {
+        const char *e = getenv("LPMB_SHIM_DOT");
+        g_dot_naive = (e && strcmp(e, "naive") == 0) ? 1 : 0;
+    }
     if (g_threads > 1) {
 #pragma omp parallel for reduction(+ : s) num_threads(g_threads) schedule(static)
         for (int i = 0; i < n; i++)
             s += a[i] * b[i];
-    } else {
+    } else if (g_dot_naive) {
         for (int i = 0; i < n; i++)
             s += a[i] * b[i];
+    } else {
+        s = dot_pairwise(n, a, b);
     }
     return s;
 }
