@@ -99,13 +99,16 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def build_workload(lpm, n: int, device: int):
-    """set up the n^3 block on the device: lattice -> O(N) topology -> material -> first FD tangent -> BCs ->
-    predictor -> residual; snapshot for replay"""
+def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None = None):
+    """set up the n^3 block (or this rank's slab of it: owned layers + ghosts, see lpm-c_b200/partition.py) on the
+    device: lattice -> O(N) topology -> material -> first FD tangent -> BCs -> predictor -> residual; snapshot"""
     t0 = time.time()
     h = 2 * PHYS["radius"]
-    N = n ** 3
-    i = np.arange(N, dtype=np.int64)
+    if slab is None:
+        first, N = 0, n ** 3
+    else:
+        first, N = slab.first_global, slab.n_local
+    i = np.arange(first, first + N, dtype=np.int64)   # global particle indices, x fastest / z slowest
     xyz = np.empty((N, 3))
     xyz[:, 0] = h * (i % n)
     xyz[:, 1] = h * ((i // n) % n)
@@ -114,6 +117,9 @@ def build_workload(lpm, n: int, device: int):
     typ[i // (n * n) == n - 1] = 1      # top layer   (type 1: displaced)
     typ[i // (n * n) == 0] = 2          # bottom layer (type 2: fixed in z)
     c = lpm.Context(N, 3, 2, 18, 61, device=device)
+    if slab is not None:
+        c.dist_init(unique_id, slab.rank, slab.world)
+        c.dist_set_slab(*slab.set_slab_args())
     E0, mu0 = PHYS["E0"], PHYS["mu0"]
     C11 = E0 * (1.0 - mu0) / (1.0 + mu0) / (1.0 - 2.0 * mu0)
     C12 = E0 * mu0 / (1.0 + mu0) / (1.0 - 2.0 * mu0)
@@ -170,7 +176,7 @@ def gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     if world > 1:
         from importlib import import_module
-        return import_module("lpm-c_b200.dist_bench").run(args, lpm, dist, rank, world, local)
+        return import_module("lpm-c_b200.dist_bench").run(args, lpm, dist, rank, world, local, sys.modules[__name__])
 
     n = args.n
     c, info = build_workload(lpm, n, local)

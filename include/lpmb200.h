@@ -178,9 +178,16 @@ int lpmb_apply_force_bc(lpmb_ctx *ctx, int type, double step_x, double step_y, d
 /* 128-byte NCCL unique id; rank 0 creates it, the harness broadcasts it. */
 int lpmb_dist_unique_id(void *id128);
 int lpmb_dist_init(lpmb_ctx *ctx, const void *id128, int rank, int world);
-/* declare this rank's slab: owned rows [row0,row1) of a global lattice of nglobal particles; local
- * indices 0..nown-1 are owned, halo_lo/halo_hi particles follow (received from rank-1 / rank+1). */
-int lpmb_dist_set_slab(lpmb_ctx *ctx, long long nglobal, long long row0, long long row1, int halo_lo, int halo_hi);
+/* Declare this rank's slab.  The context holds [ghost_lo | owned | ghost_hi] in global particle order
+ * (a contiguous index range = z-slab + 4 ghost lattice layers on each inner side); owned = local
+ * indices [own0, own1).  narrow_* = particle counts exchanged with rank-1 (lo) / rank+1 (hi) on every
+ * CG iteration (2 layers: the reach of conn); wide exchanges fill all ghosts (recv counts = own0 and
+ * N-own1), wide_send_* = what the neighbours expect from this rank.  After this call SpMV / dot
+ * products / norms run on owned rows only and the CG all-reduces its scalars. */
+int lpmb_dist_set_slab(lpmb_ctx *ctx, int own0, int own1, int narrow_recv_lo, int narrow_recv_hi, int narrow_send_lo,
+                       int narrow_send_hi, int wide_send_lo, int wide_send_hi);
+/* halo exchange of one named fp64 field (wide != 0: all ghosts, else the narrow CG halo) */
+int lpmb_dist_exchange_field(lpmb_ctx *ctx, const char *name, int wide);
 
 #ifdef __cplusplus
 }

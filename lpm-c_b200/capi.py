@@ -73,7 +73,8 @@ lib.lpmb_update_crack.argtypes = [c_vp]
 lib.lpmb_newton_iteration.argtypes = [c_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, c_ip, c_dp]
 lib.lpmb_dist_unique_id.argtypes = [c_vp]
 lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
-lib.lpmb_dist_set_slab.argtypes = [c_vp, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
+lib.lpmb_dist_set_slab.argtypes = [c_vp] + [C.c_int] * 8
+lib.lpmb_dist_exchange_field.argtypes = [c_vp, C.c_char_p, C.c_int]
 lib.lpmb_synchronize.argtypes = [c_vp]
 lib.lpmb_set_profiling.argtypes = [c_vp, C.c_int]
 lib.lpmb_get_profile.argtypes = [c_vp, c_dp, C.POINTER(C.c_longlong)]
@@ -282,6 +283,23 @@ class Context:
                                          int(maxit or self.N * self.dim), C.byref(it), C.byref(nr)),
                ok=(0, NOTCONVERGED))
         return it.value, nr.value
+
+    # -- multi-GPU
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib.lpmb_dist_unique_id(buf))
+        return buf.raw
+
+    def dist_init(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == 128
+        _check(lib.lpmb_dist_init(self._h, unique_id, rank, world))
+
+    def dist_set_slab(self, own0, own1, nrl, nrh, nsl, nsh, wsl, wsh):
+        _check(lib.lpmb_dist_set_slab(self._h, own0, own1, nrl, nrh, nsl, nsh, wsl, wsh))
+
+    def dist_exchange_field(self, name: str, wide: bool = True):
+        _check(lib.lpmb_dist_exchange_field(self._h, name.encode(), int(wide)))
 
     def set_profiling(self, on: bool = True):
         _check(lib.lpmb_set_profiling(self._h, int(on)))

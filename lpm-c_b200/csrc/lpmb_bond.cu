@@ -525,8 +525,8 @@ __device__ __forceinline__ double warp_sum_d(double v)
 
 // residual[k] = dispBC_index[k] * (Pex[k] - Pin[k]); partial sums of residual^2 and of Pin^2 over constrained DoFs
 __global__ void __launch_bounds__(256)
-update_rr_kernel(int dim, int Np, int N, const int *__restrict__ bc, const double *__restrict__ Pex, const double *__restrict__ Pin,
-                 double *__restrict__ residual, double *__restrict__ partials /* [2][grid] */)
+update_rr_kernel(int dim, int Np, int N, int own0, int own1, const int *__restrict__ bc, const double *__restrict__ Pex,
+                 const double *__restrict__ Pin, double *__restrict__ residual, double *__restrict__ partials /* [2][grid] */)
 {
     __shared__ double red[2][8];
     double s_res = 0.0, s_rea = 0.0;
@@ -539,6 +539,8 @@ update_rr_kernel(int dim, int Np, int N, const int *__restrict__ bc, const doubl
         const double pin = Pin[e];  // Pin is [3][Np]; the first dim components line up with the DoF layout
         const double r = b * (Pex[e] - pin);
         residual[e] = r;
+        if (i < own0 || i >= own1)
+            continue;  // ghost rows (multi-GPU) belong to the neighbouring slab's norm
         s_res += r * r;
         if (b == 0)
             s_rea += pin * pin;
@@ -585,8 +587,8 @@ __global__ void finish_rr_kernel(const double *__restrict__ partials, int nparts
             x += red[0][k];
             y += red[1][k];
         }
-        out2[0] = sqrt(x);
-        out2[1] = sqrt(y);
+        out2[0] = x;  // squared norms; the square root is taken after the (optional) all-reduce
+        out2[1] = y;
     }
 }
 
@@ -738,19 +740,20 @@ extern "C" int lpmb_update_rr(lpmb_ctx *c, double *norm_residual, double *norm_r
     const int grid = c->sm_count * 4;
     LPMB_REQUIRE(2 * grid + 2 <= 2 * c->cg.max_blocks, LPMB_ERR_STATE, "partials buffer too small");
     double *partials = c->cg.partials;
-    update_rr_kernel<<<grid, 256, 0, c->stream>>>(c->dim, c->Np, c->N, fptr<int>(c, "dispBC_index"), fptr<double>(c, "Pex"),
-                                                    fptr<double>(c, "Pin"), fptr<double>(c, "residual"), partials);
+    update_rr_kernel<<<grid, 256, 0, c->stream>>>(c->dim, c->Np, c->N, lpmb_own0(c), lpmb_own1(c), fptr<int>(c, "dispBC_index"),
+                                                    fptr<double>(c, "Pex"), fptr<double>(c, "Pin"), fptr<double>(c, "residual"), partials);
     LPMB_LAUNCH_CHECK(c);
     double *out2 = c->cg.scal + 12;
     finish_rr_kernel<<<1, 256, 0, c->stream>>>(partials, grid, out2);
     LPMB_LAUNCH_CHECK(c);
+    LPMB_TRY(lpmb_dist_allreduce_sum(c, out2, 2));
     if (norm_residual || norm_reaction) {
         LPMB_CUDA(cudaMemcpyAsync(c->cg.h_scal + 12, out2, 16, cudaMemcpyDeviceToHost, c->stream));
         LPMB_CUDA(cudaStreamSynchronize(c->stream));
         if (norm_residual)
-            *norm_residual = c->cg.h_scal[12];
+            *norm_residual = sqrt(c->cg.h_scal[12]);
         if (norm_reaction)
-            *norm_reaction = c->cg.h_scal[13];
+            *norm_reaction = sqrt(c->cg.h_scal[13]);
     }
     return LPMB_OK;
 }

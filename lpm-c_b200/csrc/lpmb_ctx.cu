@@ -344,6 +344,7 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     lpmb_grid_release(c);
+    lpmb_dist_release(c);
     for (auto &e : c->prof_events)
         cudaEventDestroy(e);
     for (auto &kv : c->fields)

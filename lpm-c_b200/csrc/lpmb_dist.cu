@@ -1,0 +1,170 @@
+// lpmb_dist.cu -- particle-slab decomposition across the GPUs of one box: NCCL over NVLink for exactly
+// two patterns (north_star): nearest-slab halo exchange and scalar all-reduce.
+//
+// The reference is a single address space (no MPI/NCCL anywhere); its particle
+// order is z-slowest (src/initialization.c:266-284), so contiguous index ranges are z-slabs.  One
+// process per GPU holds [ghost_lo | owned | ghost_hi] -- a contiguous sub-lattice in global order, so
+// the same topology builder / kernels run unchanged on it.  Ghosts are 4 lattice layers deep: rows in
+// the 2 layers next to the owned range have complete 2-hop stars and are computed redundantly (their
+// FD-tangent rows are needed for the symmetrisation K_ij = (A_i[j] + A_j[i]^T)/2, their dilatation
+// sums and plastic state for the owned bond forces), the outer 2 layers only supply positions.
+//   * every CG iteration: the search direction p is exchanged 2 layers deep (conn reach) and the two
+//     dot products are all-reduced (8 bytes each);
+//   * once per Newton iteration: xyz is exchanged 4 layers deep after xyz += disp;
+//   * once per load step: J2_dlambda / J2_triaxiality / damage_nonlocal before / inside the damage update.
+// libnccl is dlopen'ed at lpmb_dist_init time (torch's bundled copy when the process already loaded
+// it), so single-GPU users of liblpmb200.so carry no NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "lpmb_internal.cuh"
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.lib)
+        return LPMB_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+        h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    LPMB_REQUIRE(h, LPMB_ERR_UNSUPPORTED, "cannot load libnccl.so.2: %s", dlerror());
+#define LPMB_SYM(field, name)                                                     \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                   \
+    LPMB_REQUIRE(g_nccl.field, LPMB_ERR_UNSUPPORTED, "libnccl lacks %s", name)
+    LPMB_SYM(GetUniqueId, "ncclGetUniqueId");
+    LPMB_SYM(CommInitRank, "ncclCommInitRank");
+    LPMB_SYM(CommDestroy, "ncclCommDestroy");
+    LPMB_SYM(AllReduce, "ncclAllReduce");
+    LPMB_SYM(Send, "ncclSend");
+    LPMB_SYM(Recv, "ncclRecv");
+    LPMB_SYM(GroupStart, "ncclGroupStart");
+    LPMB_SYM(GroupEnd, "ncclGroupEnd");
+    LPMB_SYM(GetErrorString, "ncclGetErrorString");
+#undef LPMB_SYM
+    g_nccl.lib = h;
+    return LPMB_OK;
+}
+
+#define LPMB_NCCL(call)                                                                                  \
+    do {                                                                                                 \
+        ncclResult_t r__ = (call);                                                                       \
+        if (r__ != ncclSuccess) {                                                                        \
+            lpmb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__));    \
+            return LPMB_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+extern "C" int lpmb_dist_unique_id(void *id128)
+{
+    LPMB_REQUIRE(id128, LPMB_ERR_ARG, "null id buffer");
+    LPMB_TRY(load_nccl());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    LPMB_NCCL(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId *>(id128)));
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_dist_init(lpmb_ctx *c, const void *id128, int rank, int world)
+{
+    LPMB_REQUIRE(c && id128 && world >= 1 && rank >= 0 && rank < world, LPMB_ERR_ARG, "lpmb_dist_init: bad argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_TRY(load_nccl());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm;
+    LPMB_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+    c->nccl = comm;
+    c->rank = rank;
+    c->world = world;
+    return LPMB_OK;
+}
+
+void lpmb_dist_release(lpmb_ctx *c)
+{
+    if (c->nccl && g_nccl.CommDestroy)
+        g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(c->nccl));
+    c->nccl = nullptr;
+}
+
+extern "C" int lpmb_dist_set_slab(lpmb_ctx *c, int own0, int own1, int narrow_recv_lo, int narrow_recv_hi, int narrow_send_lo,
+                                  int narrow_send_hi, int wide_send_lo, int wide_send_hi)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_REQUIRE(0 <= own0 && own0 < own1 && own1 <= c->N, LPMB_ERR_ARG, "owned range [%d,%d) outside 0..%d", own0, own1, c->N);
+    LPMB_REQUIRE(narrow_recv_lo <= own0 && narrow_recv_hi <= c->N - own1, LPMB_ERR_ARG, "narrow halo larger than the ghost region");
+    LPMB_REQUIRE(narrow_send_lo <= own1 - own0 && narrow_send_hi <= own1 - own0 && wide_send_lo <= own1 - own0 && wide_send_hi <= own1 - own0,
+                 LPMB_ERR_ARG, "send counts exceed the owned range");
+    c->own0 = own0;
+    c->own1 = own1;
+    c->narrow_recv_lo = narrow_recv_lo;
+    c->narrow_recv_hi = narrow_recv_hi;
+    c->narrow_send_lo = narrow_send_lo;
+    c->narrow_send_hi = narrow_send_hi;
+    c->wide_send_lo = wide_send_lo;
+    c->wide_send_hi = wide_send_hi;
+    return LPMB_OK;
+}
+
+// Halo exchange of a component-major [comps][Np] fp64 array with rank-1 and rank+1.
+//   to rank-1: my first send_lo owned particles  -> its upper ghosts (nearest to its owned range)
+//   to rank+1: my last  send_hi owned particles  -> its lower ghosts
+int lpmb_dist_exchange(lpmb_ctx *c, double *v, int comps, bool wide)
+{
+    if (c->world <= 1)
+        return LPMB_OK;
+    LPMB_REQUIRE(c->nccl, LPMB_ERR_STATE, "lpmb_dist_init not called");
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->nccl);
+    const int own0 = lpmb_own0(c), own1 = lpmb_own1(c);
+    const int recv_lo = wide ? own0 : c->narrow_recv_lo, recv_hi = wide ? c->N - own1 : c->narrow_recv_hi;
+    const int send_lo = wide ? c->wide_send_lo : c->narrow_send_lo, send_hi = wide ? c->wide_send_hi : c->narrow_send_hi;
+    LPMB_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < comps; k++) {
+        double *base = v + (size_t)k * c->Np;
+        if (c->rank > 0) {
+            if (send_lo > 0)
+                LPMB_NCCL(g_nccl.Send(base + own0, send_lo, ncclDouble, c->rank - 1, comm, c->stream));
+            if (recv_lo > 0)
+                LPMB_NCCL(g_nccl.Recv(base + own0 - recv_lo, recv_lo, ncclDouble, c->rank - 1, comm, c->stream));
+        }
+        if (c->rank < c->world - 1) {
+            if (send_hi > 0)
+                LPMB_NCCL(g_nccl.Send(base + own1 - send_hi, send_hi, ncclDouble, c->rank + 1, comm, c->stream));
+            if (recv_hi > 0)
+                LPMB_NCCL(g_nccl.Recv(base + own1, recv_hi, ncclDouble, c->rank + 1, comm, c->stream));
+        }
+    }
+    LPMB_NCCL(g_nccl.GroupEnd());
+    return LPMB_OK;
+}
+
+int lpmb_dist_allreduce_sum(lpmb_ctx *c, double *d_buf, int count)
+{
+    if (c->world <= 1)
+        return LPMB_OK;
+    LPMB_REQUIRE(c->nccl, LPMB_ERR_STATE, "lpmb_dist_init not called");
+    LPMB_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, reinterpret_cast<ncclComm_t>(c->nccl), c->stream));
+    return LPMB_OK;
+}
+
+// exchange a named per-particle / DoF fp64 field (harness + damage path)
+extern "C" int lpmb_dist_exchange_field(lpmb_ctx *c, const char *name, int wide)
+{
+    LPMB_REQUIRE(c && name, LPMB_ERR_ARG, "null argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    Field *f = lpmb_field(c, name);
+    LPMB_REQUIRE(f && f->type == FT_F64 && f->kind != FK_RAW, LPMB_ERR_ARG, "field %s cannot be exchanged", name);
+    return lpmb_dist_exchange(c, (double *)f->d, f->comps, wide != 0);
+}

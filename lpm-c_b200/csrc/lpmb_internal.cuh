@@ -102,6 +102,12 @@ struct lpmb_ctx {
     // multi-GPU
     void *nccl = nullptr;
     int rank = 0, world = 1;
+    // slab decomposition: local particles are [ghost_lo | owned | ghost_hi] in global index order;
+    // owned = [own0, own1).  narrow = ghost particles next to the owned range that the CG exchanges
+    // every iteration (conn reach: 2 lattice layers); wide = all ghosts (4 layers: positions / state).
+    int own0 = 0, own1 = -1;
+    int narrow_recv_lo = 0, narrow_recv_hi = 0, narrow_send_lo = 0, narrow_send_hi = 0;
+    int wide_send_lo = 0, wide_send_hi = 0;
     // optional live profiling of the dominant kernel (CUDA events around every CG SpMV launch)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
@@ -155,6 +161,13 @@ int lpmb_set_connectivity_device(lpmb_ctx *c, const int *d_conn);
 int lpmb_derive_topology(lpmb_ctx *c, bool initial_geometry);
 int lpmb_compute_stress(lpmb_ctx *c);
 int lpmb_refresh_mask(lpmb_ctx *c);
+
+// multi-GPU helpers (lpmb_dist.cu); all are no-ops when world == 1
+static inline int lpmb_own0(const lpmb_ctx *c) { return c->own0; }
+static inline int lpmb_own1(const lpmb_ctx *c) { return c->own1 < 0 ? c->N : c->own1; }
+int lpmb_dist_exchange(lpmb_ctx *c, double *v, int comps, bool wide);   // halo exchange of a [comps][Np] array
+int lpmb_dist_allreduce_sum(lpmb_ctx *c, double *d_buf, int count);     // in-stream, in place
+void lpmb_dist_release(lpmb_ctx *c);
 
 // solver-side entry points used across TUs
 int lpmb_cg_alloc(lpmb_ctx *c);

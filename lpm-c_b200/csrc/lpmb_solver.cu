@@ -460,7 +460,7 @@ enum { S_RR0 = 0, S_RR1 = 1, S_THRESH = 2, S_PAP = 3, S_ALPHA = 4, S_BETA = 5, S
 // Warp per slice, lane per block row; grid-stride over slices.
 template <int D, bool DOT>
 __global__ void __launch_bounds__(SPMV_THREADS)
-spmv_sell_kernel(int nslices, const long long *__restrict__ sptr, const int *__restrict__ col, const double *__restrict__ val,
+spmv_sell_kernel(int s_begin, int s_end, const long long *__restrict__ sptr, const int *__restrict__ col, const double *__restrict__ val,
                  const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ mask, int Np,
                  double *__restrict__ partials, const double *__restrict__ scal)
 {
@@ -471,7 +471,7 @@ spmv_sell_kernel(int nslices, const long long *__restrict__ sptr, const int *__r
     const int warp = (blockIdx.x * SPMV_THREADS + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * SPMV_THREADS) >> 5;
     double dot = 0.0;
-    for (int s = warp; s < nslices; s += nwarps) {
+    for (int s = s_begin + warp; s < s_end; s += nwarps) {
         const long long ka = sptr[s], kb = sptr[s + 1];
         double acc[D];
 #pragma unroll
@@ -514,10 +514,15 @@ spmv_sell_kernel(int nslices, const long long *__restrict__ sptr, const int *__r
     }
 }
 
+// slices that contain owned rows (all of them on a single GPU)
+static inline int slice_begin(lpmb_ctx *c) { return lpmb_own0(c) / 32; }
+static inline int slice_end(lpmb_ctx *c) { return (lpmb_own1(c) + 31) / 32; }
+
 static int spmv_grid(lpmb_ctx *c)
 {
     // persistent-ish: at most 16 CTAs of 4 warps per SM, never more CTAs than slices/4
-    const int want = (c->K.nslices + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
+    const int ns = slice_end(c) - slice_begin(c);
+    const int want = (ns + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
     const int cap = c->sm_count * 16;
     return want < cap ? (want > 0 ? want : 1) : cap;
 }
@@ -526,17 +531,18 @@ static int launch_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, bool u
 {
     SellMatrix &K = c->K;
     const int grid = spmv_grid(c);
+    const int sb = slice_begin(c), se = slice_end(c);
     const double *m = use_mask ? c->mask : nullptr;
     if (c->dim == 3) {
         if (dot)
-            spmv_sell_kernel<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
+            spmv_sell_kernel<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
         else
-            spmv_sell_kernel<3, false><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, nullptr, nullptr);
+            spmv_sell_kernel<3, false><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, nullptr, nullptr);
     } else {
         if (dot)
-            spmv_sell_kernel<2, true><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
+            spmv_sell_kernel<2, true><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
         else
-            spmv_sell_kernel<2, false><<<grid, SPMV_THREADS, 0, c->stream>>>(K.nslices, K.sptr, K.col, K.val, x, y, m, c->Np, nullptr, nullptr);
+            spmv_sell_kernel<2, false><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, nullptr, nullptr);
     }
     LPMB_LAUNCH_CHECK(c);
     return LPMB_OK;
@@ -692,17 +698,44 @@ static int vec_grid(lpmb_ctx *c, size_t n)
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// sum `nparts` per-block partials into out[0] (single block, fixed order) -- used when the scalar must be
+// all-reduced across ranks before the next kernel consumes it
+__global__ void __launch_bounds__(VEC_THREADS)
+reduce_to_scalar_kernel(const double *__restrict__ partials, int nparts, double *__restrict__ out, const double *__restrict__ scal)
+{
+    __shared__ double red[VEC_THREADS / 32];
+    if (scal && scal[S_DONE] != 0.0)
+        return;
+    const double t = reduce_partials<VEC_THREADS>(partials, nparts, red);
+    if (threadIdx.x == 0)
+        out[0] = t;
+}
+
 // CG on device vectors: b (component-major [dim][Np]) -> c->cg.x.  Mirrors solver.c:209-255.
+// Multi-GPU (world > 1): ghost DoFs are masked out, p is halo-exchanged before every SpMV and the two
+// dot products are all-reduced (the per-block partials are first folded to one scalar per rank).
 static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, int maxit, bool use_mask, int *iterations)
 {
     CGWork &w = c->cg;
     const size_t n = (size_t)c->dim * c->Np;
+    const bool dist = c->world > 1;
+    if (dist)
+        use_mask = true;  // the mask also zeroes the ghost DoFs (lpmb_refresh_mask)
     const int vg = vec_grid(c, n), sg = spmv_grid(c);
     double *part_a = w.partials, *part_b = w.partials + w.max_blocks;
+    double *red_a = w.scal + 10, *red_b = w.scal + 11;  // per-rank scalars that get all-reduced
     const double *m = use_mask ? c->mask : nullptr;
+    LPMB_REQUIRE(!use_mask || m, LPMB_ERR_STATE, "DoF mask not built");
     cg_init_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(d_b, m, w.r, w.p, w.x, n, part_a);
     LPMB_LAUNCH_CHECK(c);
-    cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, rel, abs_tol, w.scal);
+    if (dist) {
+        reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, red_a, nullptr);
+        LPMB_LAUNCH_CHECK(c);
+        LPMB_TRY(lpmb_dist_allreduce_sum(c, red_a, 1));
+        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(red_a, 1, rel, abs_tol, w.scal);
+    } else {
+        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, rel, abs_tol, w.scal);
+    }
     LPMB_LAUNCH_CHECK(c);
     const int batch = 16;
     int parity = 0, issued = 0;
@@ -714,15 +747,30 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     for (;;) {
         const int issued0 = issued;
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
+            if (dist)
+                LPMB_TRY(lpmb_dist_exchange(c, w.p, c->dim, false));
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b], c->stream));
             LPMB_TRY(launch_spmv(c, w.p, w.ap, true, use_mask));  // partials -> part_a (w.partials)
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b + 1], c->stream));
-            cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, part_a, sg, part_b, w.scal, parity);
-            LPMB_LAUNCH_CHECK(c);
-            cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, part_b, vg, w.scal, parity, maxit);
-            LPMB_LAUNCH_CHECK(c);
+            if (dist) {
+                reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, sg, red_a, w.scal);
+                LPMB_LAUNCH_CHECK(c);
+                LPMB_TRY(lpmb_dist_allreduce_sum(c, red_a, 1));
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, red_a, 1, part_b, w.scal, parity);
+                LPMB_LAUNCH_CHECK(c);
+                reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_b, vg, red_b, w.scal);
+                LPMB_LAUNCH_CHECK(c);
+                LPMB_TRY(lpmb_dist_allreduce_sum(c, red_b, 1));
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, red_b, 1, w.scal, parity, maxit);
+                LPMB_LAUNCH_CHECK(c);
+            } else {
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, part_a, sg, part_b, w.scal, parity);
+                LPMB_LAUNCH_CHECK(c);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, part_b, vg, w.scal, parity, maxit);
+                LPMB_LAUNCH_CHECK(c);
+            }
             cg_bookkeep_kernel<<<1, 1, 0, c->stream>>>(w.scal, parity, maxit);
             LPMB_LAUNCH_CHECK(c);
             parity ^= 1;
@@ -747,11 +795,14 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     return w.h_scal[S_DONE] == 1.0 ? LPMB_OK : LPMB_ERR_NOTCONVERGED;
 }
 
-__global__ void mask_build_kernel(const int *__restrict__ bc, const int *__restrict__ fix, double *__restrict__ mask, size_t n)
+__global__ void mask_build_kernel(const int *__restrict__ bc, const int *__restrict__ fix, double *__restrict__ mask, size_t n, int Np,
+                                  int own0, int own1)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int part = (int)(i % Np);
         const bool constrained = (bc && bc[i] == 0) || (fix && fix[i] == 0);  // boundary.c:182,214,247
-        mask[i] = constrained ? 0.0 : 1.0;
+        const bool owned = part >= own0 && part < own1;                       // ghosts / padding never enter the Krylov space
+        mask[i] = (constrained || !owned) ? 0.0 : 1.0;
     }
 }
 
@@ -763,7 +814,7 @@ int lpmb_refresh_mask(lpmb_ctx *c)
         LPMB_CUDA(cudaMalloc(&c->mask, n * 8));
     const int *bc = fptr<int>(c, "dispBC_index"), *fix = fptr<int>(c, "fix_index");
     LPMB_REQUIRE(bc && fix, LPMB_ERR_STATE, "BC index fields missing");
-    mask_build_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(bc, fix, c->mask, n);
+    mask_build_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(bc, fix, c->mask, n, c->Np, lpmb_own0(c), lpmb_own1(c));
     LPMB_LAUNCH_CHECK(c);
     return LPMB_OK;
 }
@@ -785,6 +836,8 @@ extern "C" int lpmb_solve_cg_device(lpmb_ctx *c, double rel, double abs_tol, int
     LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
+    if (c->world > 1 && !c->mask)
+        LPMB_TRY(lpmb_refresh_mask(c));
     LPMB_REQUIRE(!use_mask || c->mask, LPMB_ERR_STATE, "DoF mask requested but not set");
     LPMB_TRY(lpmb_cg_alloc(c));
     const double *b = fptr<double>(c, "residual");
@@ -799,6 +852,8 @@ extern "C" int lpmb_solve_cg_device(lpmb_ctx *c, double rel, double abs_tol, int
         // xyz[i][j] += disp[dim*i+j], j < dim (solver.c:263-267); xyz is [3][Np], disp is [dim][Np]
         axpy_xyz_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(disp, fptr<double>(c, "xyz"), c->dim, c->Np);
         LPMB_LAUNCH_CHECK(c);
+        // ghosts beyond the narrow CG halo did not follow the iteration: refresh all ghost positions
+        LPMB_TRY(lpmb_dist_exchange(c, fptr<double>(c, "xyz"), 3, true));
     }
     return rc;
 }

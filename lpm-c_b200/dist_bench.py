@@ -1,0 +1,133 @@
+"""Multi-GPU arm of bench.py: strong scaling of the same n^3 workload over particle slabs.
+
+One process per GPU (torchrun).  torch.distributed is plumbing only: it carries the 128-byte NCCL unique id
+to the ranks, provides the barrier and the max-over-ranks of the device-measured time.  The data path --
+SpMV halo exchange and CG dot-product all-reduce -- is NCCL inside liblpmb200.so (csrc/lpmb_dist.cu).
+"""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+
+def run(args, lpm, dist, rank, world, local, bench):
+    import torch
+    from . import partition
+
+    n = args.n
+    slab = partition.make_slab(n, n * n, rank, world)
+    # rank 0 creates the NCCL id; torch.distributed ships it
+    uid = [lpm.Context.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0])
+    hbm_peak, peak_src = bench.peaks()
+
+    def barrier():
+        c.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        it, nr = bench.one_step(c)
+    barrier()
+    c.set_profiling(True)
+    launches0 = c.launches
+    sampler = bench.ClockSampler(local)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(c.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    iters = []
+    for _ in range(args.steps):
+        it, nr = bench.one_step(c)
+        iters.append(it)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_local = e0.elapsed_time(e1)
+    t = torch.tensor([ms_local], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    launches = c.launches - launches0
+    spmv_ms, spmv_calls = c.get_profile()
+    c.set_profiling(False)
+    spmv_avg_ms = spmv_ms / max(1, spmv_calls)
+    # per-rank SpMV bytes: only the slices holding owned rows are streamed
+    own_frac = (slab.own1 - slab.own0) / slab.n_local
+    alg_bytes_rank = int(c.spmv_bytes() * own_frac)
+    achieved = alg_bytes_rank / (spmv_avg_ms * 1e-3) / 1e9
+    stats = torch.tensor([spmv_avg_ms, achieved, float(launches)], dtype=torch.float64, device=f"cuda:{local}")
+    gathered = [torch.zeros_like(stats) for _ in range(world)]
+    dist.all_gather(gathered, stats)
+
+    # end to end: every rank uploads its slab's inputs from pinned host memory and reads its results back
+    N = slab.n_local
+    nd = 3 * N
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    h_xyz, h_res = pin((N, 3), torch.float64), pin(nd, torch.float64)
+    h_bc, h_fix = pin(nd, torch.int32), pin(nd, torch.int32)
+    o_xyz, o_disp, o_pin, o_res = pin((N, 3), torch.float64), pin(nd, torch.float64), pin(nd, torch.float64), pin(nd, torch.float64)
+    h_xyz[:] = c.get_field("xyz_save")
+    h_res[:] = c.get_field("residual_save")
+    h_bc[:] = c.get_field("dispBC_index")
+    h_fix[:] = c.get_field("fix_index")
+
+    def e2e_step():
+        c.set_field("xyz", h_xyz)
+        c.set_field("residual", h_res)
+        c.set_field("dispBC_index", h_bc)
+        c.set_field("fix_index", h_fix)
+        r = c.newton_iteration(0, 1)
+        o_xyz[:] = c.get_field("xyz")
+        o_disp[:] = c.get_field("disp")
+        o_pin[:] = c.get_field("Pin")
+        o_res[:] = c.get_field("residual")
+        return r
+
+    import time
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = h_xyz.nbytes + h_res.nbytes + h_bc.nbytes + h_fix.nbytes
+    d2h = o_xyz.nbytes + o_disp.nbytes + o_pin.nbytes + o_res.nbytes
+    bytes_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        Ng = n ** 3
+        per_rank = [{"rank": r, "spmv_ms": float(g[0]), "spmv_GBs": float(g[1]), "launches": int(g[2])} for r, g in enumerate(gathered)]
+        worst = min(per_rank, key=lambda d: d["spmv_GBs"])
+        out = {
+            "metric": bench.METRIC, "value": 1000.0 / ms_per_step, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {n}^3 lattice, {Ng} particles, "
+                                   f"{3 * Ng} DoF; Newton iteration 0 of load step 1 replayed from a snapshot",
+                       "lattice_n": n, "particles": Ng, "dof": 3 * Ng, "cg_iterations_per_step": iters,
+                       "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
+                       "l2": "inputs larger than L2 (per-rank matrix %.1f GB)" % (c.spmv_bytes_stored() * own_frac / 1e9),
+                       "parallelism": f"{world} z-slabs (owned layers per rank {slab.z1 - slab.z0}, 4 ghost layers), NCCL halo exchange "
+                                      "of p (2 layers) + all-reduce of 2 scalars per CG iteration"},
+            "roofline": {"bound": "hbm", "kernel": "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap), slowest rank", "achieved": worst["spmv_GBs"],
+                         "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": worst["spmv_GBs"] / hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes_rank, "avg_launch_ms": worst["spmv_ms"], "per_rank": per_rank,
+                         "share_of_step": float(spmv_ms / ms_local)},
+            "e2e": {"value": 1.0 / e2e_s, "unit": bench.UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
+                    "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps},
+            "gpu_launches": int(sum(d["launches"] for d in per_rank)),
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    c.close()
+    dist.barrier()
+    dist.destroy_process_group()
