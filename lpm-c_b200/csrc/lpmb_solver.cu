@@ -459,7 +459,7 @@ enum { S_RR0 = 0, S_RR1 = 1, S_THRESH = 2, S_PAP = 3, S_ALPHA = 4, S_BETA = 5, S
 // y = [mask .*] (K x); optionally partial[blockIdx] = sum over this block's rows of x.y
 // Warp per slice, lane per block row; grid-stride over slices.
 template <int D, bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS)
+__global__ void __launch_bounds__(SPMV_THREADS, 16)
 spmv_sell_kernel(int s_begin, int s_end, const long long *__restrict__ sptr, const int *__restrict__ col, const double *__restrict__ val,
                  const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ mask, int Np,
                  double *__restrict__ partials, const double *__restrict__ scal)
