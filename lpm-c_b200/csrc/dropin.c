@@ -1,0 +1,493 @@
+/*
+ * dropin.c -- the reference's hot-path entry points (stiffness.h, solver.h, constitutive.h) on the B200.
+ *
+ * Plain C host code: marshals the reference's process globals (jagged T** / T*** arrays defined by the
+ * driver, src/lpmc_project.c:19-45, declared in include/lpm.h:55-81) to the C ABI of liblpmb200.so
+ * (include/lpmb200.h) and back.  No numerics happen here; every computation is a CUDA kernel behind
+ * that ABI, and a missing GPU / failed call prints the library's error and exits (the reference's
+ * own convention for fatal errors: solver.c:50-84, constitutive.c:1216-1221).
+ *
+ * Ownership contract.  The driver owns every array.  Arrays that only the host code
+ * writes between our calls (xyz, xyz_temp, F_temp, Pex, dispBC_index, fix_index, residual, K_global, type,
+ * sigmay, Ce and the scalar parameters) are uploaded on entry of every function that reads them; arrays
+ * that only these functions write are authoritative on the device after the first call and are copied
+ * back to the host globals on return from every function that changes them, so the unchanged writers
+ * (data_handler.c), computeStrain() and the driver's own memcpys always see current values.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "lpmb200.h"
+#include "lpmc_dropin.h"
+
+/* ---- the reference's globals this layer touches (include/lpm.h:55-81); defined by the driver ---- */
+#define NDIM 3
+extern int ntype, nparticle, nneighbors, dim, lattice, nneighbors_AFEM, plmode, nslipSys, nbreak;
+extern int *IK, *JK, *type, *dispBC_index, *fix_index, *pl_flag, *nb, *nb_initial, *nb_conn;
+extern int **neighbors, **K_pointer, **conn, **nsign;
+extern double radius, particle_volume, J2_H, J2_xi, damage_L, damage_threshold, damageb_A, damagec_A, critical_bstrain, dtime;
+extern double *K_global, *residual, *Pin, *Pex, *disp, *sigmay, *reaction_force, *damage_visual;
+extern double *J2_dlambda, *J2_stresseq, *J2_stressm, *J2_triaxiality;
+extern double **xyz, **xyz_initial, **xyz_temp, **distance, **distance_initial, **KnTve, **F, **csx, **csy, **csz;
+extern double **dL_total, **TdL_total, **csx_initial, **csy_initial, **csz_initial, **Ce, **stress_tensor;
+extern double **dL_ave, **ddL_total, **TddL_total, **F_temp, **ddLp, **dL, **ddL, **bond_stress, **damage_broken, **damage_w;
+extern double **Kn, **Tv, **J2_alpha, **damage_local, **damage_nonlocal, **J2_beta_eq;
+extern double ***dLp, ***J2_beta, ***damage_D;
+
+static lpmb_ctx *g_ctx = NULL;
+static double *g_buf = NULL; /* flat staging for one array */
+static size_t g_buf_bytes = 0;
+static int g_device_bc = 0;
+static int g_state_uploaded = 0;
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        int rc__ = (call);                                                                     \
+        if (rc__ != LPMB_OK) {                                                                 \
+            fprintf(stderr, "lpmc_dropin: %s failed (%d): %s\n", #call, rc__, lpmb_last_error()); \
+            exit(1);                                                                           \
+        }                                                                                      \
+    } while (0)
+
+static void *buf(size_t bytes)
+{
+    if (bytes > g_buf_bytes) {
+        free(g_buf);
+        g_buf = (double *)malloc(bytes);
+        g_buf_bytes = bytes;
+        if (!g_buf) {
+            fprintf(stderr, "lpmc_dropin: out of host memory (%zu bytes)\n", bytes);
+            exit(1);
+        }
+    }
+    return g_buf;
+}
+
+/* ---- jagged <-> flat marshalling ---- */
+static void up_d2(const char *name, double **a, int rows, int cols)
+{
+    double *b = (double *)buf((size_t)rows * cols * sizeof(double));
+    for (int i = 0; i < rows; i++)
+        memcpy(b + (size_t)i * cols, a[i], sizeof(double) * cols);
+    CK(lpmb_field_set(g_ctx, name, b, (size_t)rows * cols));
+}
+static void down_d2(const char *name, double **a, int rows, int cols)
+{
+    double *b = (double *)buf((size_t)rows * cols * sizeof(double));
+    CK(lpmb_field_get(g_ctx, name, b, (size_t)rows * cols));
+    for (int i = 0; i < rows; i++)
+        memcpy(a[i], b + (size_t)i * cols, sizeof(double) * cols);
+}
+static void up_i2(const char *name, int **a, int rows, int cols)
+{
+    int *b = (int *)buf((size_t)rows * cols * sizeof(int));
+    for (int i = 0; i < rows; i++)
+        memcpy(b + (size_t)i * cols, a[i], sizeof(int) * cols);
+    CK(lpmb_field_set(g_ctx, name, b, (size_t)rows * cols));
+}
+/* one slot of a T*** state array a[rows][cols][slot] <-> device field "<name><slot>" */
+static void up_slot(const char *name, double ***a, int rows, int cols, int slot)
+{
+    char fn[64];
+    snprintf(fn, sizeof fn, "%s%d", name, slot);
+    double *b = (double *)buf((size_t)rows * cols * sizeof(double));
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < cols; j++)
+            b[(size_t)i * cols + j] = a[i][j][slot];
+    CK(lpmb_field_set(g_ctx, fn, b, (size_t)rows * cols));
+}
+static void down_slot(const char *name, double ***a, int rows, int cols, int slot)
+{
+    char fn[64];
+    snprintf(fn, sizeof fn, "%s%d", name, slot);
+    double *b = (double *)buf((size_t)rows * cols * sizeof(double));
+    CK(lpmb_field_get(g_ctx, fn, b, (size_t)rows * cols));
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < cols; j++)
+            a[i][j][slot] = b[(size_t)i * cols + j];
+}
+/* one slot of a T** per-particle state array a[rows][slot] */
+static void up_pslot(const char *name, double **a, int rows, int slot)
+{
+    char fn[64];
+    snprintf(fn, sizeof fn, "%s%d", name, slot);
+    double *b = (double *)buf((size_t)rows * sizeof(double));
+    for (int i = 0; i < rows; i++)
+        b[i] = a[i][slot];
+    CK(lpmb_field_set(g_ctx, fn, b, (size_t)rows));
+}
+static void down_pslot(const char *name, double **a, int rows, int slot)
+{
+    char fn[64];
+    snprintf(fn, sizeof fn, "%s%d", name, slot);
+    double *b = (double *)buf((size_t)rows * sizeof(double));
+    CK(lpmb_field_get(g_ctx, fn, b, (size_t)rows));
+    for (int i = 0; i < rows; i++)
+        a[i][slot] = b[i];
+}
+#define UP1D(name, ptr, n) CK(lpmb_field_set(g_ctx, name, ptr, (size_t)(n)))
+#define DOWN1D(name, ptr, n) CK(lpmb_field_get(g_ctx, name, ptr, (size_t)(n)))
+
+static void set_params(void)
+{
+    CK(lpmb_set_param(g_ctx, "radius", radius));
+    CK(lpmb_set_param(g_ctx, "particle_volume", particle_volume));
+    CK(lpmb_set_param(g_ctx, "J2_H", J2_H));
+    CK(lpmb_set_param(g_ctx, "J2_xi", J2_xi));
+    CK(lpmb_set_param(g_ctx, "damage_L", damage_L));
+    CK(lpmb_set_param(g_ctx, "damage_threshold", damage_threshold));
+    CK(lpmb_set_param(g_ctx, "damagec_A", damagec_A));
+    CK(lpmb_set_param(g_ctx, "damageb_A", damageb_A));
+    CK(lpmb_set_param(g_ctx, "critical_bstrain", critical_bstrain));
+    CK(lpmb_set_param(g_ctx, "nbreak", (double)nbreak));
+    CK(lpmb_set_param(g_ctx, "dtime", dtime));
+}
+
+/* host-owned inputs that the driver / boundary.c may have changed since our last call */
+static void up_host_owned(void)
+{
+    const int N = nparticle;
+    set_params();
+    up_d2("xyz", xyz, N, 3);
+    UP1D("dispBC_index", dispBC_index, (size_t)dim * N);
+    UP1D("fix_index", fix_index, (size_t)dim * N);
+    UP1D("Pex", Pex, (size_t)dim * N);
+}
+
+/* first call: create the context from the reference's set-up (createCuboid / searchNormalNeighbor /
+ * searchAFEMNeighbor / initMatrices have run) and upload every array these functions read */
+static void ensure_ctx(void)
+{
+    if (g_ctx)
+        return;
+    const char *dev = getenv("LPMB_DEVICE");
+    const char *dbc = getenv("LPMB_DROPIN_DEVICE_BC");
+    g_device_bc = dbc && atoi(dbc) != 0;
+    CK(lpmb_create(&g_ctx, dev ? atoi(dev) : 0, nparticle, dim, lattice, nneighbors, nneighbors_AFEM + 1));
+    const int N = nparticle, nn = nneighbors;
+    set_params();
+    up_d2("xyz", xyz, N, 3);
+    up_d2("xyz_initial", xyz_initial, N, 3);
+    up_d2("distance_initial", distance_initial, N, nn);
+    up_d2("csx_initial", csx_initial, N, nn);
+    up_d2("csy_initial", csy_initial, N, nn);
+    up_d2("csz_initial", csz_initial, N, nn);
+    {   /* neighbors + nsign in one call (derives nb_initial, mirror and opposite-bond slots) */
+        int *a = (int *)malloc((size_t)N * nn * sizeof(int)), *b = (int *)malloc((size_t)N * nn * sizeof(int));
+        for (int i = 0; i < N; i++) {
+            memcpy(a + (size_t)i * nn, neighbors[i], sizeof(int) * nn);
+            memcpy(b + (size_t)i * nn, nsign[i], sizeof(int) * nn);
+        }
+        CK(lpmb_set_neighbors(g_ctx, a, b));
+        free(a);
+        free(b);
+    }
+    {
+        const int nc = nneighbors_AFEM + 1;
+        int *a = (int *)malloc((size_t)N * nc * sizeof(int));
+        for (int i = 0; i < N; i++)
+            memcpy(a + (size_t)i * nc, conn[i], sizeof(int) * nc);
+        CK(lpmb_set_connectivity(g_ctx, a));
+        free(a);
+        long long nnz = 0;
+        CK(lpmb_csr_sizes(g_ctx, &nnz, NULL));
+        if (nnz != (long long)K_pointer[N][1]) {
+            fprintf(stderr, "lpmc_dropin: CSR size mismatch (device %lld, reference %d)\n", nnz, K_pointer[N][1]);
+            exit(1);
+        }
+    }
+}
+
+/* state arrays that exist on the host before the first force evaluation (initial cracks set damage_broken,
+ * drivers may pre-set anything): uploaded once, device-authoritative afterwards */
+static void ensure_state(void)
+{
+    ensure_ctx();
+    if (g_state_uploaded)
+        return;
+    g_state_uploaded = 1;
+    const int N = nparticle, nn = nneighbors;
+    UP1D("nb", nb, N);
+    UP1D("type", type, N);
+    UP1D("sigmay", sigmay, N);
+    UP1D("pl_flag", pl_flag, N);
+    up_d2("Kn", Kn, N, nn);
+    up_d2("Tv", Tv, N, nn);
+    up_d2("damage_broken", damage_broken, N, nn);
+    up_d2("damage_w", damage_w, N, nn);
+    up_d2("F", F, N, nn);
+    up_d2("dL", dL, N, nn);
+    up_d2("dL_ave", dL_ave, N, nn);
+    up_d2("csx", csx, N, nn);
+    up_d2("csy", csy, N, nn);
+    up_d2("csz", csz, N, nn);
+    up_d2("dL_total", dL_total, N, 2);
+    up_d2("TdL_total", TdL_total, N, 2);
+    UP1D("J2_triaxiality", J2_triaxiality, N);
+    UP1D("J2_dlambda", J2_dlambda, N);
+    UP1D("Pin", Pin, (size_t)NDIM * N);
+    for (int s = 0; s < 3; s++) {
+        up_slot("dLp", dLp, N, nn, s);
+        up_slot("J2_beta", J2_beta, N, 2 * NDIM, s);
+        up_pslot("J2_alpha", J2_alpha, N, s);
+        up_pslot("J2_beta_eq", J2_beta_eq, N, s);
+    }
+    for (int s = 0; s < 2; s++) {
+        up_slot("damage_D", damage_D, N, nn, s);
+        up_pslot("damage_local", damage_local, N, s);
+        up_pslot("damage_nonlocal", damage_nonlocal, N, s);
+    }
+    {   /* Ce [ntype][3] (calcKnTv may not have been called by a custom driver) */
+        double *ce = (double *)malloc((size_t)ntype * 3 * sizeof(double));
+        for (int k = 0; k < ntype; k++)
+            memcpy(ce + 3 * k, Ce[k], 3 * sizeof(double));
+        CK(lpmb_calc_kntv(g_ctx, ce, ntype));
+        free(ce);
+        /* keep whatever Kn/Tv the host holds (identical when calcKnTv() was ours) */
+        up_d2("Kn", Kn, N, nn);
+        up_d2("Tv", Tv, N, nn);
+    }
+}
+
+static void down_slots(int s)
+{
+    const int N = nparticle, nn = nneighbors;
+    down_slot("dLp", dLp, N, nn, s);
+    down_slot("J2_beta", J2_beta, N, 2 * NDIM, s);
+    down_pslot("J2_alpha", J2_alpha, N, s);
+    down_pslot("J2_beta_eq", J2_beta_eq, N, s);
+}
+
+/* ------------------------------------------------------------------------------------ stiffness.h */
+void calcKnTv()
+{
+    ensure_ctx();
+    const int N = nparticle, nn = nneighbors;
+    UP1D("type", type, N);
+    double *ce = (double *)malloc((size_t)ntype * 3 * sizeof(double));
+    for (int k = 0; k < ntype; k++)
+        memcpy(ce + 3 * k, Ce[k], 3 * sizeof(double));
+    CK(lpmb_calc_kntv(g_ctx, ce, ntype));
+    /* the reference allocates KnTve here (stiffness.c:16,50,147,209,240) */
+    double *knt = (double *)malloc((size_t)ntype * 3 * sizeof(double));
+    CK(lpmb_field_get(g_ctx, "KnTve", knt, (size_t)ntype * 3));
+    KnTve = (double **)malloc(sizeof(double *) * ntype);
+    for (int k = 0; k < ntype; k++) {
+        KnTve[k] = (double *)malloc(sizeof(double) * 3);
+        memcpy(KnTve[k], knt + 3 * k, 3 * sizeof(double));
+    }
+    free(knt);
+    free(ce);
+    down_d2("Kn", Kn, N, nn);
+    down_d2("Tv", Tv, N, nn);
+}
+
+void updateRR()
+{
+    ensure_state();
+    const int N = nparticle;
+    UP1D("dispBC_index", dispBC_index, (size_t)dim * N);
+    UP1D("Pex", Pex, (size_t)dim * N);
+    CK(lpmb_update_rr(g_ctx, NULL, NULL));
+    DOWN1D("residual", residual, (size_t)dim * N);
+    /* reaction_force: Pin of the constrained DoFs in ascending DoF order (stiffness.c:529-531) */
+    int ii = 0;
+    for (int i = 0; i < N; i++)
+        for (int k = 0; k < dim; k++)
+            if (dispBC_index[dim * i + k] == 0)
+                reaction_force[ii++] = Pin[NDIM * i + k];
+}
+
+static void fd_stiffness(int mode)
+{
+    if (mode != 6) {
+        fprintf(stderr, "lpmc_dropin: calcStiffness*FiniteDifference(%d): only the elastic tangent (6) exists, as in the reference\n", mode);
+        exit(1);
+    }
+    ensure_state();
+    const int N = nparticle, nn = nneighbors;
+    set_params();
+    up_d2("xyz", xyz, N, 3);
+    CK(lpmb_fd_stiffness(g_ctx, 1));
+    CK(lpmb_matrix_to_upper_csr(g_ctx, K_global, IK, JK));
+    /* what the reference's assembly leaves behind */
+    down_d2("dL", dL, N, nn);
+    down_d2("csx", csx, N, nn);
+    down_d2("csy", csy, N, nn);
+    down_d2("csz", csz, N, nn);
+    down_d2("dL_total", dL_total, N, 2);
+    down_d2("TdL_total", TdL_total, N, 2);
+    down_d2("F", F, N, nn);
+    DOWN1D("Pin", Pin, (size_t)NDIM * N);
+}
+void calcStiffness2DFiniteDifference(int mode) { fd_stiffness(mode); }
+void calcStiffness3DFiniteDifference(int mode) { fd_stiffness(mode); }
+
+/* ---------------------------------------------------------------------------------------- solver.h */
+static void solve(double rel, double abs_tol, const char *who)
+{
+    ensure_state();
+    const int N = nparticle, n = dim * nparticle;
+    int iters = 0, rc;
+    if (g_device_bc) {
+        CK(lpmb_set_dof_mask(g_ctx, dispBC_index, fix_index));
+        rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 1, &iters);
+    } else {
+        CK(lpmb_matrix_from_upper_csr(g_ctx, K_global, (long long)K_pointer[N][1]));
+        rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 0, &iters);
+    }
+    if (rc == LPMB_OK)
+        printf("The system has been solved after %d iterations\n", iters); /* solver.c:254 */
+    else if (rc == LPMB_ERR_NOTCONVERGED)
+        printf("The computation FAILED as the solver has returned the ERROR code %d\n", -1); /* solver.c:258 */
+    else {
+        fprintf(stderr, "lpmc_dropin: %s failed (%d): %s\n", who, rc, lpmb_last_error());
+        exit(1);
+    }
+    for (int i = 0; i < N; i++) /* solver.c:263-267 */
+        for (int j = 0; j < dim; j++)
+            xyz[i][j] += disp[dim * i + j];
+}
+void solverCG() { solve(1e-8, 1e-12, "solverCG"); }
+void solverPARDISO()
+{
+    /* a sparse direct factorisation is out of scope; the same CG run to 1e-12 relative residual */
+    solve(1e-24, 0.0, "solverPARDISO");
+}
+
+/* ---------------------------------------------------------------------------------- constitutive.h */
+void switchStateV(int conv_flag)
+{
+    ensure_state();
+    CK(lpmb_switch_state(g_ctx, conv_flag));
+    const int N = nparticle, nn = nneighbors;
+    const int dst = conv_flag == 1 ? 1 : 0;
+    down_slots(dst);
+    if (conv_flag != 2) {
+        down_slot("damage_D", damage_D, N, nn, dst);
+        down_pslot("damage_local", damage_local, N, dst);
+        down_pslot("damage_nonlocal", damage_nonlocal, N, dst);
+    }
+}
+
+void computeBondForceGeneral(int mode, int temp)
+{
+    ensure_state();
+    const int N = nparticle, nn = nneighbors;
+    up_host_owned();
+    if (mode == 4) {
+        up_d2("xyz_temp", xyz_temp, N, 3);
+        up_d2("F_temp", F_temp, N, nn);
+    }
+    CK(lpmb_bond_force(g_ctx, mode, temp));
+    down_d2("F", F, N, nn);
+    DOWN1D("Pin", Pin, (size_t)NDIM * N);
+    down_d2("stress_tensor", stress_tensor, N, 2 * NDIM);
+    DOWN1D("J2_stresseq", J2_stresseq, N);
+    DOWN1D("J2_stressm", J2_stressm, N);
+    DOWN1D("J2_triaxiality", J2_triaxiality, N);
+    down_d2("bond_stress", bond_stress, N, nn);
+    if (mode == 4) {
+        down_d2("ddL", ddL, N, nn);
+        down_d2("ddL_total", ddL_total, N, 2);
+        down_d2("TddL_total", TddL_total, N, 2);
+    } else {
+        down_d2("dL", dL, N, nn);
+        down_d2("csx", csx, N, nn);
+        down_d2("csy", csy, N, nn);
+        down_d2("csz", csz, N, nn);
+        down_d2("dL_total", dL_total, N, 2);
+        down_d2("TdL_total", TdL_total, N, 2);
+    }
+    if (mode == 0) {
+        down_d2("dL_ave", dL_ave, N, nn);
+        down_d2("ddLp", ddLp, N, nn);
+        DOWN1D("J2_dlambda", J2_dlambda, N);
+        DOWN1D("pl_flag", pl_flag, N);
+        down_slots(2);
+    }
+    down_slots(0); /* switchStateV(2) ran inside (constitutive.c:145) */
+}
+
+static int damage(const char *dataName, int tstep, int mode)
+{
+    ensure_state();
+    set_params();
+    const int N = nparticle, nn = nneighbors;
+    int broken = 0;
+    const int cap = 1 << 16;
+    int *pairs = (int *)malloc(sizeof(int) * 2 * cap);
+    CK(lpmb_update_damage(g_ctx, mode, &broken, pairs, cap));
+    if (mode == 0 || mode == 6) {
+        FILE *fpt = fopen(dataName, "a+"); /* constitutive.c:1440-1442,1481,1761-1763,1841 */
+        if (fpt) {
+            fprintf(fpt, "TIMESTEP ");
+            fprintf(fpt, "%d\n", tstep);
+            int logged = broken;
+            if (mode == 6 && broken > nbreak)
+                logged = nbreak;
+            for (int k = 0; k < logged && k < cap; k++)
+                fprintf(fpt, "%d %d \n", pairs[2 * k], pairs[2 * k + 1]);
+            fclose(fpt);
+        }
+        down_d2("damage_broken", damage_broken, N, nn);
+        down_d2("damage_w", damage_w, N, nn);
+        down_slot("damage_D", damage_D, N, nn, 0);
+        if (mode == 0)
+            down_pslot("damage_nonlocal", damage_nonlocal, N, 0);
+    }
+    free(pairs);
+    return broken;
+}
+int updateDamageGeneral(const char *dataName, int tstep, int mode) { return damage(dataName, tstep, mode); }
+int updateDuctileDamagePwiseNonlocal(const char *dataName, int tstep) { return damage(dataName, tstep, 0); }
+int updateBrittleDamage(const char *dataName, int tstep, int nbreak_arg)
+{
+    const int saved = nbreak;
+    nbreak = nbreak_arg;
+    const int k = damage(dataName, tstep, 6);
+    nbreak = saved;
+    return k;
+}
+
+void updateCrack()
+{
+    ensure_state();
+    const int N = nparticle, nn = nneighbors;
+    UP1D("fix_index", fix_index, (size_t)dim * N);
+    CK(lpmb_update_crack(g_ctx));
+    DOWN1D("nb", nb, N);
+    down_d2("F", F, N, nn);
+    DOWN1D("Pin", Pin, (size_t)NDIM * N);
+    DOWN1D("damage_visual", damage_visual, N);
+    DOWN1D("fix_index", fix_index, (size_t)dim * N);
+}
+
+/* ---- entry points whose laws are not built: keep the symbols, fail loudly ---- */
+static void not_built(const char *what)
+{
+    fprintf(stderr, "lpmc_dropin: %s is not available in the B200 build (no CPU fallback)\n", what);
+    exit(1);
+}
+void computeCab() { not_built("computeCab (crystal plasticity)"); }
+void computeBondForceElastic(int i) { (void)i; not_built("computeBondForceElastic(i): per-particle evaluation is internal to the GPU assembly"); }
+void computeBondForceJ2mixedLinear3D(int ii) { (void)ii; not_built("computeBondForceJ2mixedLinear3D(ii): use computeBondForceGeneral(0, t)"); }
+void computeBondForceJ2nonlinearIso(int ii) { (void)ii; not_built("computeBondForceJ2nonlinearIso (plmode 5)"); }
+void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe (plmode 1)"); }
+void computeBondForceIncrementalUpdating(int ii) { (void)ii; not_built("computeBondForceIncrementalUpdating(ii): use computeBondForceGeneral(4, t)"); }
+void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap (plmode 3)"); }
+int updateDuctileDamageBwiseLocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamageBwiseLocal"); return 0; }
+int updateDuctileDamagePwiseLocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamagePwiseLocal"); return 0; }
+int updateDuctileDamageBwiseNonlocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamageBwiseNonlocal"); return 0; }
+
+void lpmc_dropin_shutdown(void)
+{
+    if (g_ctx)
+        lpmb_destroy(g_ctx);
+    g_ctx = NULL;
+    free(g_buf);
+    g_buf = NULL;
+    g_buf_bytes = 0;
+}

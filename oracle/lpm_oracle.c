@@ -1,0 +1,618 @@
+/*
+ * oracle/lpm_oracle.c -- CPU restatement ("port") of LPM-C's hot path on flat arrays.
+ *
+ * TEST INFRASTRUCTURE ONLY: used by tests/ as a checker (and available to bench.py's cpu_baseline leg);
+ * never linked, imported or executed by the product path.  Every function cites the reference lines it
+ * follows.  It is pinned (tests/test_oracle_port.py) bit-for-bit against the reference's own functions
+ * running from oracle/_ref (the unmodified sources) on the committed golden case, and its CG reproduces the
+ * reference's iteration counts (80 / 106 on the default case).
+ *
+ * Layouts are the reference's logical ones, flattened row-major: per-bond a[i*nn+j], per-particle a[i*c+k],
+ * DoF vectors v[dim*i+k], Pin[3*i+k]; three-slot state as separate arrays.  Strict IEEE: compile with
+ * -ffp-contract=off (oracle/Makefile).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EPS 1e-6     /* include/lpm.h:42 */
+#define PI 3.14159265358979323846
+
+static double dot_pairwise(int n, const double *a, const double *b);
+
+/* ------------------------------------------------------------------ neighbor.c:9-46 (O(N^2) as there) */
+int oracle_search_neighbors(int N, const double *xyz, double cutoff1, double cutoff2, int nn, int *neighbors, int *nsign, int *nb,
+                            double *dist0, double *csx0, double *csy0, double *csz0)
+{
+    int overflow = 0;
+    for (long k = 0; k < (long)N * nn; k++) {
+        neighbors[k] = -1;
+        nsign[k] = -1;
+    }
+#pragma omp parallel for schedule(static) reduction(| : overflow)
+    for (int i = 0; i < N; i++) {
+        int idx = 0;
+        for (int j = 0; j < N; j++) {
+            const double dx = xyz[3 * j] - xyz[3 * i], dy = xyz[3 * j + 1] - xyz[3 * i + 1], dz = xyz[3 * j + 2] - xyz[3 * i + 2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            int s = -1;
+            if ((dis < 1.01 * cutoff1) && (j != i))
+                s = 0;
+            else if ((dis > 1.01 * cutoff1) && (dis < 1.01 * cutoff2))
+                s = 1;
+            if (s < 0)
+                continue;
+            if (idx >= nn) {
+                overflow = 1;
+                continue;
+            }
+            const long e = (long)i * nn + idx;
+            csx0[e] = (xyz[3 * i] - xyz[3 * j]) / dis;
+            csy0[e] = (xyz[3 * i + 1] - xyz[3 * j + 1]) / dis;
+            csz0[e] = (xyz[3 * i + 2] - xyz[3 * j + 2]) / dis;
+            dist0[e] = dis;
+            nsign[e] = s;
+            neighbors[e] = j;
+            idx++;
+        }
+        nb[i] = idx;
+    }
+    return overflow;
+}
+
+static int cmp_int(const void *a, const void *b) { return (*(const int *)a > *(const int *)b) - (*(const int *)a < *(const int *)b); }
+
+/* ------------------------------------------------------------------ neighbor.c:49-130 */
+/* conn[i] = sorted unique( {j} U N1(j) for first-shell j, {j} U N2(j) for second-shell j ); K_pointer (64-bit) */
+int oracle_afem_conn(int N, int nn, int nconn, int dim, const int *neighbors, const int *nsign, const int *nb, int *conn, int *nb_conn,
+                     long long *kp0, long long *kp1)
+{
+    int overflow = 0;
+    int *tmp = (int *)malloc(sizeof(int) * (size_t)nn * (nn + 1));
+    for (int i = 0; i < N; i++) {
+        int n = 0;
+        for (int j = 0; j < nb[i]; j++) {
+            const int nj = neighbors[(long)i * nn + j], s = nsign[(long)i * nn + j];
+            tmp[n++] = nj;
+            for (int m = 0; m < nb[nj]; m++)
+                if (nsign[(long)nj * nn + m] == s)
+                    tmp[n++] = neighbors[(long)nj * nn + m];
+        }
+        qsort(tmp, n, sizeof(int), cmp_int);
+        int u = 0;
+        for (int k = 0; k < n; k++)
+            if (k == 0 || tmp[k] != tmp[k - 1]) {
+                if (u < nconn)
+                    conn[(long)i * nconn + u] = tmp[k];
+                else
+                    overflow = 1;
+                u++;
+            }
+        nb_conn[i] = u < nconn ? u : nconn;
+        for (int k = nb_conn[i]; k < nconn; k++)
+            conn[(long)i * nconn + k] = -1;
+    }
+    free(tmp);
+    kp1[0] = 0;
+    for (int i = 0; i < N; i++) {
+        int ge = 0;
+        for (int j = 0; j < nb_conn[i]; j++)
+            if (conn[(long)i * nconn + j] >= i)
+                ge++;
+        kp0[i] = ge;
+        kp1[i + 1] = kp1[i] + (long long)dim * dim * ge - (dim == 3 ? 3 : 1);
+    }
+    kp0[N] = 0;
+    return overflow;
+}
+
+/* ------------------------------------------------------------------ geometry pass G(i; dLp*) */
+/* constitutive.c:241-260 / 495-515 / 625-645 (apply_broken=1) and lpm_basic.c:252-291 (apply_broken=0, writes distance) */
+void oracle_geometry(int N, int nn, const double *xyz, const int *neighbors, const int *nsign, const int *nbi, const double *L0,
+                     const double *dLp, const double *broken, const double *Tv, int apply_broken, double *dL, double *csx, double *csy,
+                     double *csz, double *dLt, double *TdLt, double *distance)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        dLt[2 * i] = dLt[2 * i + 1] = TdLt[2 * i] = TdLt[2 * i + 1] = 0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e];
+            const double dx = xyz[3 * i] - xyz[3 * nj], dy = xyz[3 * i + 1] - xyz[3 * nj + 1], dz = xyz[3 * i + 2] - xyz[3 * nj + 2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            if (distance)
+                distance[e] = dis;
+            dL[e] = dis - L0[e];
+            dL[e] -= dLp[e];
+            if (apply_broken)
+                dL[e] *= broken[e];
+            dLt[2 * i + nsign[e]] += dL[e];
+            TdLt[2 * i + nsign[e]] += Tv[e] * dL[e];
+            csx[e] = dx / dis;
+            csy[e] = dy / dis;
+            csz[e] = dz / dis;
+        }
+    }
+}
+
+/* owner pass: law 6 = elastic (constitutive.c:264-279), law 0 = J2 average stretch (constitutive.c:648-667) */
+void oracle_force(int N, int nn, int law, const int *neighbors, const int *nsign, const int *nbi, const double *Kn, const double *Tv,
+                  const double *scale, const double *dL, const double *dLt, const double *TdLt, const double *csx, const double *csy,
+                  const double *csz, double *dL_ave, double *F, double *Pin)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e], s = nsign[e];
+            double stretch = dL[e];
+            if (law == 0) {
+                for (int jj = 0; jj < nn; jj++)
+                    if (neighbors[(long)nj * nn + jj] == i)
+                        dL_ave[e] = 0.5 * (dL[e] + dL[(long)nj * nn + jj]);
+                stretch = dL_ave[e];
+            }
+            F[e] = 2.0 * Kn[e] * stretch + 0.5 * (TdLt[2 * i + s] + TdLt[2 * nj + s]) + 0.5 * Tv[e] * (dLt[2 * i + s] + dLt[2 * nj + s]);
+            F[e] *= scale[e];
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ constitutive.c:167-225 (predictor, plmode 4) */
+void oracle_predictor(int N, int nn, const double *xyz, const double *xyz_temp, const int *neighbors, const int *nsign, const int *nbi,
+                      const double *Kn, const double *Tv, const double *broken, const double *F_temp, const double *csx, const double *csy,
+                      const double *csz, double *ddL, double *ddLt, double *TddLt, double *F, double *Pin)
+{
+    for (int i = 0; i < N; i++) {
+        ddLt[2 * i] = ddLt[2 * i + 1] = TddLt[2 * i] = TddLt[2 * i + 1] = 0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e];
+            const double ax = xyz_temp[3 * i] - xyz_temp[3 * nj], ay = xyz_temp[3 * i + 1] - xyz_temp[3 * nj + 1], az = xyz_temp[3 * i + 2] - xyz_temp[3 * nj + 2];
+            const double dis0 = sqrt(ax * ax + ay * ay + az * az);
+            const double bx = xyz[3 * i] - xyz[3 * nj], by = xyz[3 * i + 1] - xyz[3 * nj + 1], bz = xyz[3 * i + 2] - xyz[3 * nj + 2];
+            const double dis1 = sqrt(bx * bx + by * by + bz * bz);
+            ddL[e] = broken[e] * (dis1 - dis0);
+            ddLt[2 * i + nsign[e]] += ddL[e];
+            TddLt[2 * i + nsign[e]] += Tv[e] * ddL[e];
+        }
+    }
+    for (int i = 0; i < N; i++) {
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e], s = nsign[e];
+            F[e] = F_temp[e] + 2.0 * Kn[e] * ddL[e] + 0.5 * (TddLt[2 * i + s] + TddLt[2 * nj + s]) + 0.5 * Tv[e] * (ddLt[2 * i + s] + ddLt[2 * nj + s]);
+            F[e] *= broken[e];
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+    }
+}
+
+/* opposite-bond factor: lpm_basic.c:72-90, constitutive.c:541-559 */
+static double opp_flag(int i, int j, int nn, int nneighbors, const int *nb, const int *nbi, const double *cx0, const double *cy0,
+                       const double *cz0, const double *broken)
+{
+    if (nb[i] == nneighbors)
+        return 0.5;
+    for (int m = 0; m < nbi[i]; m++) {
+        const long a = (long)i * nn + m, b = (long)i * nn + j;
+        if (fabs(cx0[a] + cx0[b]) < EPS && fabs(cy0[a] + cy0[b]) < EPS && fabs(cz0[a] + cz0[b]) < EPS)
+            return broken[a] <= EPS ? 1.0 : 0.5;
+    }
+    return 1.0;
+}
+
+/* ------------------------------------------------------------------ constitutive.c:518-622, 669-675 (J2 return map, once per particle) */
+void oracle_j2_return_map(int N, int nn, double V, double J2_H, double J2_xi, const double *Ce, const int *type, const double *sigmay,
+                          const int *nsign, const int *nb, const int *nbi, const double *Kn, const double *Tv, const double *w,
+                          const double *broken, const double *L0, const double *cx0, const double *cy0, const double *cz0, const double *dL,
+                          const double *dLt, const double *TdLt, const double *csx, const double *csy, const double *csz, const double *dLp0,
+                          const double *beta0, const double *alpha0, double *dLp2, double *beta2, double *alpha2, double *ddLp,
+                          double *dlambda, int *pl_flag)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        double st[6] = {0}, dpl[6] = {0};
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            double Fij = 2.0 * Kn[e] * dL[e] + TdLt[2 * i + nsign[e]] + Tv[e] * dLt[2 * i + nsign[e]];
+            Fij *= w[e];
+            const double of = opp_flag(i, j, nn, nn, nb, nbi, cx0, cy0, cz0, broken);
+            st[0] += of / V * L0[e] * Fij * csx[e] * csx[e];
+            st[1] += of / V * L0[e] * Fij * csy[e] * csy[e];
+            st[2] += of / V * L0[e] * Fij * csz[e] * csz[e];
+            st[3] += of / V * L0[e] * Fij * csy[e] * csz[e];
+            st[4] += of / V * L0[e] * Fij * csx[e] * csz[e];
+            st[5] += of / V * L0[e] * Fij * csx[e] * csy[e];
+        }
+        const double temp = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+        for (int q = 0; q < 3; q++)
+            st[q] -= temp;
+        double beta[6];
+        for (int q = 0; q < 6; q++) {
+            beta[q] = beta0[6 * i + q];
+            st[q] -= beta[q];
+        }
+        double seq = 0.0;
+        for (int q = 0; q < 6; q++)
+            seq += (q < 3 ? 1.0 : 2.0) * st[q] * st[q];
+        seq = sqrt(3.0 / 2.0 * seq);
+        double alpha = alpha0[i], dl = 0.0;
+        const double yf = seq - (sigmay[i] + (1.0 - J2_xi) * J2_H * alpha);
+        if (yf > 0.0) {
+            pl_flag[i] = 1;
+            dl = yf / (3 * Ce[3 * type[i] + 2] + J2_H);
+        }
+        alpha += dl;
+        for (int q = 0; q < 6; q++)
+            if (fabs(seq) > EPS) {
+                dpl[q] = dl * 1.5 * st[q] / seq;
+                beta[q] += 2. / 3. * J2_xi * J2_H * dpl[q];
+            }
+        for (int j = 0; j < nn; j++) {
+            const long e = (long)i * nn + j;
+            double xd = dLp0[e];
+            if (j < nbi[i]) {
+                ddLp[e] = L0[e] * (dpl[0] * csx[e] * csx[e] + dpl[1] * csy[e] * csy[e] + dpl[2] * csz[e] * csz[e] + 2 * dpl[3] * csy[e] * csz[e] +
+                                   2 * dpl[4] * csx[e] * csz[e] + 2 * dpl[5] * csx[e] * csy[e]);
+                ddLp[e] *= broken[e];
+                xd += ddLp[e];
+            }
+            dLp2[e] = broken[e] * xd;
+        }
+        for (int q = 0; q < 6; q++)
+            beta2[6 * i + q] = beta[q];
+        alpha2[i] = alpha;
+        dlambda[i] = dl;
+    }
+}
+
+/* ------------------------------------------------------------------ lpm_basic.c:53-125 */
+void oracle_stress(int N, int nn, double V, const int *nb, const int *nbi, const double *L0, const double *cx0, const double *cy0,
+                   const double *cz0, const double *broken, const double *F, const double *csx, const double *csy, const double *csz,
+                   double *stress, double *seq_out, double *sm_out, double *triax, double *bond_stress)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        double *st = stress + 6 * (long)i;
+        memset(st, 0, 6 * sizeof(double));
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const double of = opp_flag(i, j, nn, nn, nb, nbi, cx0, cy0, cz0, broken);
+            st[0] += of / V * L0[e] * F[e] * csx[e] * csx[e];
+            st[1] += of / V * L0[e] * F[e] * csy[e] * csy[e];
+            st[2] += of / V * L0[e] * F[e] * csz[e] * csz[e];
+            st[3] += of / V * L0[e] * F[e] * csy[e] * csz[e];
+            st[4] += of / V * L0[e] * F[e] * csx[e] * csz[e];
+            st[5] += of / V * L0[e] * F[e] * csx[e] * csy[e];
+        }
+        double seq = 0.0;
+        for (int q = 0; q < 6; q++)
+            seq += (q < 3 ? 1.0 : 2.0) * st[q] * st[q];
+        seq_out[i] = sqrt(3.0 / 2.0 * seq);
+        sm_out[i] = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+        if (seq_out[i] > EPS)
+            triax[i] = sm_out[i] / seq_out[i];
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            bond_stress[e] = (st[0] * csx[e] * csx[e] + st[1] * csy[e] * csy[e] + st[2] * csz[e] * csz[e] + 2 * st[3] * csy[e] * csz[e] +
+                              2 * st[4] * csx[e] * csz[e] + 2 * st[5] * csx[e] * csy[e]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ stiffness.c:519-534 */
+int oracle_update_rr(int N, int dim, const int *bc, const double *Pex, const double *Pin, double *residual, double *reaction)
+{
+    int ii = 0;
+    for (int i = 0; i < N; i++)
+        for (int k = 0; k < dim; k++) {
+            residual[dim * i + k] = bc[dim * i + k] * (Pex[dim * i + k] - Pin[3 * i + k]);
+            if (bc[dim * i + k] == 0)
+                reaction[ii++] = Pin[3 * i + k];
+        }
+    return ii;
+}
+
+/* ------------------------------------------------------------------ stiffness.c:271-516: FD tangent, brute force as there */
+/* elastic internal force of particle ii with the CURRENT xyz (constitutive.c:228-283); scratch holds the per-particle sums */
+static void elastic_pin(int ii, int nn, const double *xyz, const int *neighbors, const int *nsign, const int *nbi, const double *L0,
+                        const double *dLp0, const double *broken, const double *Kn, const double *Tv, double *dL, double *csx, double *csy,
+                        double *csz, double *dLt, double *TdLt, double *Fout, double *pin)
+{
+    for (int k = -1; k < nbi[ii]; k++) {
+        int i = ii;
+        if (k >= 0) {
+            if (!(broken[(long)ii * nn + k] > EPS))
+                continue;
+            i = neighbors[(long)ii * nn + k];
+        }
+        dLt[2 * i] = dLt[2 * i + 1] = TdLt[2 * i] = TdLt[2 * i + 1] = 0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e];
+            const double dx = xyz[3 * i] - xyz[3 * nj], dy = xyz[3 * i + 1] - xyz[3 * nj + 1], dz = xyz[3 * i + 2] - xyz[3 * nj + 2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            dL[e] = dis - L0[e];
+            dL[e] -= dLp0[e];
+            dL[e] *= broken[e];
+            dLt[2 * i + nsign[e]] += dL[e];
+            TdLt[2 * i + nsign[e]] += Tv[e] * dL[e];
+            csx[e] = dx / dis;
+            csy[e] = dy / dis;
+            csz[e] = dz / dis;
+        }
+    }
+    pin[0] = pin[1] = pin[2] = 0.0;
+    for (int j = 0; j < nbi[ii]; j++) {
+        const long e = (long)ii * nn + j;
+        const int nj = neighbors[e], s = nsign[e];
+        double f = 2.0 * Kn[e] * dL[e] + 0.5 * (TdLt[2 * ii + s] + TdLt[2 * nj + s]) + 0.5 * Tv[e] * (dLt[2 * ii + s] + dLt[2 * nj + s]);
+        f *= broken[e];
+        Fout[e] = f;
+        pin[0] += csx[e] * f;
+        pin[1] += csy[e] * f;
+        pin[2] += csz[e] * f;
+    }
+}
+
+/* serial, single pass over particles exactly like the reference run with one thread; leaves the same side effects
+ * in dL, cs*, dLt, TdLt, F, Pin.  K / JK / IK are the 1-based symmetric-upper CSR. */
+void oracle_fd_stiffness(int N, int nn, int nconn, int dim, double radius, double *xyz, const int *neighbors, const int *nsign, const int *nbi,
+                         const double *L0, const double *dLp0, const double *broken, const double *Kn, const double *Tv, const int *conn,
+                         const int *nb_conn, const long long *kp0, const long long *kp1, double *K, int *JK, int *IK, double *dL, double *csx,
+                         double *csy, double *csz, double *dLt, double *TdLt, double *F, double *Pin)
+{
+    const int D = dim;
+    memset(K, 0, sizeof(double) * (size_t)kp1[N]);
+    double *Kl = (double *)malloc(sizeof(double) * 3 * nconn * 3);
+    for (int i = 0; i < N; i++) {
+        const int nc = nb_conn[i];
+        double base[3], pin[3];
+        elastic_pin(i, nn, xyz, neighbors, nsign, nbi, L0, dLp0, broken, Kn, Tv, dL, csx, csy, csz, dLt, TdLt, F, base);
+        memcpy(Pin + 3 * i, base, sizeof base);
+        for (int jID = 0; jID < nc; jID++)
+            for (int r = 0; r < D; r++) {
+                const int c = conn[(long)i * nconn + jID];
+                const double xt = xyz[3 * c + r];
+                xyz[3 * c + r] = xt + EPS * radius;
+                elastic_pin(i, nn, xyz, neighbors, nsign, nbi, L0, dLp0, broken, Kn, Tv, dL, csx, csy, csz, dLt, TdLt, F, pin);
+                memcpy(Pin + 3 * i, pin, sizeof pin);
+                xyz[3 * c + r] = xt;
+                for (int s = 0; s < D; s++)
+                    Kl[(r * nc + jID) * 3 + s] = (pin[s] - base[s]) / EPS / radius;
+            }
+        const long long P = kp1[i];
+        const int K0 = (int)kp0[i];
+#define ROWSTART(PP, r, KK) ((PP) + (long long)(r) * D * (KK) - (long long)((r) * ((r)-1) / 2))
+        int num1 = 0;
+        for (int jID = 0; jID < nc; jID++) {
+            const int jj = conn[(long)i * nconn + jID];
+            double kll[3][3];
+            for (int r = 0; r < D; r++)
+                for (int s = 0; s < D; s++)
+                    kll[r][s] = Kl[(s * nc + jID) * 3 + r];
+            if (jj == i) {
+                for (int r = 0; r < D; r++)
+                    for (int s = r; s < D; s++) {
+                        K[ROWSTART(P, r, K0) + (s - r)] += kll[r][s];
+                        JK[ROWSTART(P, r, K0) + (s - r)] = D * jj + s + 1;
+                    }
+            } else if (jj > i) {
+                num1++;
+                for (int r = 0; r < D; r++)
+                    for (int s = 0; s < D; s++) {
+                        K[ROWSTART(P, r, K0) + (long long)num1 * D - r + s] += 0.5 * kll[r][s];
+                        JK[ROWSTART(P, r, K0) + (long long)num1 * D - r + s] = D * jj + s + 1;
+                    }
+            } else {
+                int num2 = 0;
+                const long long Pj = kp1[jj];
+                const int K0j = (int)kp0[jj];
+                for (int k = 0; k < nb_conn[jj]; k++) {
+                    if (conn[(long)jj * nconn + k] <= jj)
+                        continue;
+                    num2++;
+                    if (conn[(long)jj * nconn + k] == i)
+                        for (int r = 0; r < D; r++)
+                            for (int s = 0; s < D; s++)
+                                K[ROWSTART(Pj, r, K0j) + (long long)num2 * D - r + s] += 0.5 * kll[s][r];
+                }
+            }
+        }
+        for (int r = 0; r < D; r++)
+            IK[D * i + r] = (int)(ROWSTART(P, r, K0) + 1);
+    }
+    IK[D * N] = (int)(kp1[N] + 1);
+    free(Kl);
+}
+
+/* ------------------------------------------------------------------ boundary.c:159-281 (and 2-D twin :72-157) */
+void oracle_bc_stiffness_update(int N, int nconn, int dim, const int *bc, const int *fix, const int *conn, const int *nb_conn,
+                                const long long *kp0, const long long *kp1, double *K, double *residual)
+{
+    const int D = dim;
+    /* norm_diag = cblas_dnrm2(diag) (boundary.c:168-176); the open shim sums pairwise above 4096 entries */
+    double *diag = (double *)malloc(sizeof(double) * (size_t)N * D);
+    for (int i = 0; i < N; i++)
+        for (int r = 0; r < D; r++)
+            diag[D * i + r] = K[ROWSTART(kp1[i], r, (int)kp0[i])];
+    double s2 = 0.0;
+    if (N * D > 4096)
+        s2 = dot_pairwise(N * D, diag, diag);
+    else
+        for (int k = 0; k < N * D; k++)
+            s2 += diag[k] * diag[k];
+    free(diag);
+    const double norm_diag = sqrt(s2);
+    for (int i = 0; i < N; i++)
+        for (int a = 0; a < D; a++) {
+            if (!(bc[D * i + a] == 0 || fix[D * i + a] == 0))
+                continue;
+            const long long P = kp1[i];
+            const int K0 = (int)kp0[i];
+            /* own block rows: column a of rows r<a, the whole row a */
+            for (int r = 0; r < a; r++)
+                K[ROWSTART(P, r, K0) + (a - r)] = 0.0;
+            const long long rs = ROWSTART(P, a, K0), re = (a + 1 < D) ? ROWSTART(P, a + 1, K0) : kp1[i + 1];
+            for (long long kk = rs; kk < re; kk++)
+                K[kk] = 0.0;
+            K[rs] = norm_diag;
+            /* column a of particle i inside the rows of lower-index conn particles */
+            for (int j = 0; j < nb_conn[i]; j++) {
+                const int cj = conn[(long)i * nconn + j];
+                if (cj >= i)
+                    continue;
+                int num2 = 0;
+                for (int k = 0; k < nb_conn[cj]; k++) {
+                    if (conn[(long)cj * nconn + k] <= cj)
+                        continue;
+                    num2++;
+                    if (conn[(long)cj * nconn + k] == i)
+                        for (int r = 0; r < D; r++)
+                            K[ROWSTART(kp1[cj], r, (int)kp0[cj]) + (long long)num2 * D - r + a] = 0.0;
+                }
+            }
+            residual[D * i + a] = 0.0;
+        }
+}
+
+/* ------------------------------------------------------------------ solver.c:188-270 with the shim's documented RCI-CG */
+static double dot_pairwise(int n, const double *a, const double *b)
+{
+    if (n <= 32) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++)
+            s += a[i] * b[i];
+        return s;
+    }
+    const int h = (n / 2 + 31) & ~31;
+    return dot_pairwise(h, a, b) + dot_pairwise(n - h, a + h, b + h);
+}
+
+static void spmv_sym_upper(int n, const int *IK, const int *JK, const double *K, const double *x, double *y)
+{
+    memset(y, 0, sizeof(double) * n);
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = IK[i] - 1; k < IK[i + 1] - 1; k++) {
+            const int j = JK[k] - 1;
+            s += K[k] * x[j];
+            if (j != i)
+                y[j] += 1.0 * (K[k] * x[i]);
+        }
+        y[i] += 1.0 * s;
+    }
+}
+
+/* x0 = 0; stop when ||r||^2 <= rel*||r0||^2 + abs (squared norms) or maxit.  Returns the iteration count. */
+int oracle_cg(int n, const int *IK, const int *JK, const double *K, const double *b, double *x, double rel, double abs_tol, int maxit)
+{
+    double *p = (double *)malloc(sizeof(double) * n * 3), *ap = p + n, *r = p + 2 * n;
+    memset(x, 0, sizeof(double) * n);
+    memcpy(r, b, sizeof(double) * n);
+    memcpy(p, b, sizeof(double) * n);
+    double rr = dot_pairwise(n, r, r);
+    const double thresh = rel * rr + abs_tol;
+    int it = 0;
+    if (rr > thresh)
+        while (it < maxit) {
+            spmv_sym_upper(n, IK, JK, K, p, ap);
+            const double alpha = rr / dot_pairwise(n, p, ap);
+            for (int i = 0; i < n; i++)
+                x[i] += alpha * p[i];
+            for (int i = 0; i < n; i++)
+                r[i] += -alpha * ap[i];
+            const double rr_new = dot_pairwise(n, r, r);
+            it++;
+            if (rr_new <= thresh)
+                break;
+            const double beta = rr_new / rr;
+            for (int i = 0; i < n; i++)
+                p[i] = r[i] + beta * p[i];
+            rr = rr_new;
+        }
+    free(p);
+    return it;
+}
+
+/* ------------------------------------------------------------------ constitutive.c:1757-1862 (O(N^2) as there) */
+int oracle_damage_nonlocal(int N, int nn, double L, double thr, double Ac, double V, const double *xyz0, const int *neighbors, const int *nbi,
+                           const double *dlambda, const double *triax, double *Dn, double *broken, double *dD0, double *w)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; i++) {
+        if (Dn[i] > thr) {
+            if (Dn[i] > 1.0)
+                Dn[i] = 1.0;
+            continue;
+        }
+        double Ddot = 0, A = 0;
+        for (int j = 0; j < N; j++) {
+            const double dx = xyz0[3 * j] - xyz0[3 * i], dy = xyz0[3 * j + 1] - xyz0[3 * i + 1], dz = xyz0[3 * j + 2] - xyz0[3 * i + 2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            if (dis < 3 * L) {
+                double DdotLocal = 0;
+                const double f = (1.0 + Ac * triax[j]);
+                if (f > 0.0)
+                    DdotLocal = dlambda[j] * (1.0 + Ac * triax[j]);
+                const double phi = 1.0 / L / sqrt(2 * PI) * exp(-0.5 * dis * dis / L / L);
+                Ddot += DdotLocal * phi * V;
+                A += phi * V;
+            }
+        }
+        if (Ddot > 0.0)
+            Dn[i] += 1.0 / A * Ddot;
+    }
+    int k = 0;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            if (Dn[i] > thr || Dn[neighbors[e]] > thr)
+                if (fabs(broken[e]) > EPS) {
+                    broken[e] = 0.0;
+                    dD0[e] = 1.0;
+                    k++;
+                }
+        }
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            if (fabs(broken[e]) > EPS)
+                dD0[e] = Dn[i] < Dn[neighbors[e]] ? Dn[neighbors[e]] : Dn[i];
+            w[e] = 1.0 - dD0[e];
+        }
+    return k;
+}
+
+/* ------------------------------------------------------------------ constitutive.c:1399-1434 */
+void oracle_update_crack(int N, int nn, int dim, const int *nbi, const double *broken, const double *w, const double *csx, const double *csy,
+                         const double *csz, double *F, double *Pin, int *nb, double *damage_visual, int *fix_index)
+{
+    for (int i = 0; i < N; i++) {
+        nb[i] = nbi[i];
+        damage_visual[i] = 0.0;
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            if (broken[e] <= EPS)
+                nb[i] -= 1;
+            damage_visual[i] += broken[e];
+            F[e] *= w[e];
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+        if (nb[i] < 1)
+            for (int k = 0; k < dim; k++)
+                fix_index[dim * i + k] = 0;
+        damage_visual[i] = 1 - damage_visual[i] / nbi[i];
+    }
+}

@@ -24,3 +24,25 @@ def test_no_cpu_fallback_without_device(lpm):
 
 def test_version(lpm):
     assert lpm.lib.lpmb_version() >= 100
+
+
+def test_dropin_exports_every_reference_entry_point():
+    """liblpmc_dropin.so defines every function declared in include/lpmc_dropin.h (= the reference's stiffness.h,
+    solver.h, constitutive.h).  It cannot be dlopen'ed on its own -- it references the driver's globals -- so the
+    dynamic symbol table is read instead."""
+    import re
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    so = root / "lpm-c_b200" / "liblpmc_dropin.so"
+    assert so.exists(), "run __graft_entry__.build()"
+    text = re.sub(r"/\*.*?\*/", "", (root / "include" / "lpmc_dropin.h").read_text(), flags=re.S)
+    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)) - {"defined"}
+    out = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True, check=True).stdout
+    defined = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = sorted(declared - defined)
+    assert not missing, missing
+    assert {"solverCG", "calcStiffness3DFiniteDifference", "computeBondForceGeneral", "updateRR", "switchStateV"} <= defined
+    # and it needs the reference's globals from the driver it is linked into
+    undef = subprocess.run(["nm", "-D", "--undefined-only", str(so)], capture_output=True, text=True, check=True).stdout
+    assert " xyz" in undef and " K_global" in undef
