@@ -211,7 +211,8 @@ static void ensure_state(void)
     const int N = nparticle, nn = nneighbors;
     UP1D("nb", nb, N);
     UP1D("type", type, N);
-    UP1D("sigmay", sigmay, N);
+    if (sigmay) /* allocated by the driver only for the plastic laws (lpmc_project.c:210) */
+        UP1D("sigmay", sigmay, N);
     UP1D("pl_flag", pl_flag, N);
     up_d2("Kn", Kn, N, nn);
     up_d2("Tv", Tv, N, nn);

@@ -90,8 +90,8 @@ def test_brittle_example_matches_cpu_reference(tmp_path, name):
         pytest.skip("example binaries not built")
     dg, dc = tmp_path / "gpu", tmp_path / "cpu"
     dg.mkdir(); dc.mkdir()
-    _run(cpu, dc, 150, threads=os.cpu_count())
-    _run(gpu, dg, 300)
+    _run(cpu, dc, 60, threads=os.cpu_count())
+    _run(gpu, dg, 90)
     assert "lpmc_dropin:" not in (dg / "run.log").read_text()
     nf, wf = _compare_tables(_table(dg / "result_force.txt"), _table(dc / "result_force.txt"), 1e-6, "force")
     nd, wd = _compare_tables(_table(dg / "result_disp.txt"), _table(dc / "result_disp.txt"), 1e-6, "disp")
