@@ -373,8 +373,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lattice-n", dest="n", type=int, default=int(os.environ.get("LPMB_BENCH_N", 216)), help="lattice points per side")
-    ap.add_argument("--cpu-sample-n", type=int, default=40)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-n", type=int, default=48)   # 110 592 particles: ~1 s per reference Newton iteration
+    ap.add_argument("--cpu-steps", type=int, default=10)      # => ~10-15 s of timed CPU work
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
