@@ -160,6 +160,14 @@ int lpmb_update_rr(lpmb_ctx *ctx, double *norm_residual, double *norm_reaction);
 int lpmb_update_damage(lpmb_ctx *ctx, int plmode, int *broken, int *pairs, int max_pairs);
 int lpmb_update_crack(lpmb_ctx *ctx);
 
+/* ---- crystal plasticity (plmode 1) ---------------------------------------------------------- */
+/* schmid_tensor[nslipSys][6] as slipSysDefine3D builds it (src/initialization.c:563-827); also sets the
+ * parameter nslipSys that sizes the cp_* fields.  Parameters read by the law: cp_h0, cp_taus0, cp_tau00
+ * (= cp_taus[0], cp_tau0[0]), cp_q, cp_eta, cp_p, cp_maxloop, dtime. */
+int lpmb_set_schmid_tensor(lpmb_ctx *ctx, const double *schmid_tensor, int nslipSys);
+/* computeCab(), src/constitutive.c:1864-1917: fills the field cp_Cab [N][nslipSys^2] */
+int lpmb_compute_cab(lpmb_ctx *ctx);
+
 /* ---- one Newton iteration, device resident (lpmc_project.c:426-464) ------------------------ */
 /* switchStateV(0); masked CG solve; xyz += disp; computeBondForceGeneral(plmode); updateRR; norm */
 int lpmb_newton_iteration(lpmb_ctx *ctx, int plmode, int load_indicator, double rel, double abs_tol, int maxit,

@@ -76,6 +76,8 @@ lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
 lib.lpmb_dist_set_slab.argtypes = [c_vp] + [C.c_int] * 8
 lib.lpmb_dist_exchange_field.argtypes = [c_vp, C.c_char_p, C.c_int]
 lib.lpmb_synchronize.argtypes = [c_vp]
+lib.lpmb_set_schmid_tensor.argtypes = [c_vp, c_vp, C.c_int]
+lib.lpmb_compute_cab.argtypes = [c_vp]
 lib.lpmb_set_profiling.argtypes = [c_vp, C.c_int]
 lib.lpmb_get_profile.argtypes = [c_vp, c_dp, C.POINTER(C.c_longlong)]
 lib.lpmb_field_copy.argtypes = [c_vp, C.c_char_p, C.c_char_p]
@@ -109,7 +111,7 @@ def _i32(a):
 
 
 # host dtype of the integer fields (everything else is float64)
-_INT_FIELDS = {"neighbors", "nsign", "mirror", "oppslot", "type", "pl_flag", "nb", "nb_initial", "dispBC_index",
+_INT_FIELDS = {"cp_Jact", "neighbors", "nsign", "mirror", "oppslot", "type", "pl_flag", "nb", "nb_initial", "dispBC_index",
                "fix_index"}
 
 NOTCONVERGED = 4
@@ -152,6 +154,11 @@ class Context:
                  "TddL_total": 2, "stress_tensor": 6, "strain_tensor": 6, "J2_beta0": 6, "J2_beta1": 6, "J2_beta2": 6}
         if name in comps:
             return (N, comps[name])
+        S = getattr(self, "nslip", 0)
+        if name == "cp_Cab":
+            return (N, S * S)
+        if name in ("cp_RSS", "cp_Jact", "cp_dgy", "cp_dA_single") or name[:-1] in ("cp_gy", "cp_A_single"):
+            return (N, S)
         if name in ("residual", "residual_save", "Pex", "Pex_temp", "disp", "dispBC_index", "fix_index"):
             return (N * dim,)
         if name == "Pin":
@@ -283,6 +290,15 @@ class Context:
                                          int(maxit or self.N * self.dim), C.byref(it), C.byref(nr)),
                ok=(0, NOTCONVERGED))
         return it.value, nr.value
+
+    # -- crystal plasticity
+    def set_schmid_tensor(self, schmid):
+        a = _f64(schmid)
+        self.nslip = a.shape[0]
+        _check(lib.lpmb_set_schmid_tensor(self._h, a.ctypes.data, a.shape[0]))
+
+    def compute_cab(self):
+        _check(lib.lpmb_compute_cab(self._h))
 
     # -- multi-GPU
     @staticmethod

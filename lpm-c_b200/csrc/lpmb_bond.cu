@@ -633,6 +633,14 @@ extern "C" int lpmb_switch_state(lpmb_ctx *c, int flag)
         lpmb_set_error("switchStateV: flag %d", flag);
         return LPMB_ERR_ARG;
     }
+    // crystal-plasticity state joins when slip systems are defined (nslipSys > 0, constitutive.c:25-35,50-60,74-82)
+    if (param(c, "nslipSys", 0.0) > 0.0) {
+        static const char *dst[3] = {"0", "1", "0"}, *src[3] = {"1", "0", "2"};
+        for (const char *base : {"cp_gy", "cp_A_single", "cp_A"}) {
+            const std::string d = std::string(base) + dst[flag], s2 = std::string(base) + src[flag];
+            LPMB_TRY(copy_field(c, d.c_str(), s2.c_str()));
+        }
+    }
     return LPMB_OK;
 }
 
@@ -711,8 +719,15 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         LPMB_TRY(run_geometry(c, v, "dLp2"));
         force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
         LPMB_LAUNCH_CHECK(c);
+    } else if (plmode == 1) {
+        // crystal plasticity (constitutive.c:866-1396): geometry -> Miehe return map -> geometry -> averaged force
+        LPMB_TRY(run_geometry(c, v, "dLp0"));
+        LPMB_TRY(lpmb_cp_return_map(c));
+        LPMB_TRY(run_geometry(c, v, "dLp2"));
+        force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
+        LPMB_LAUNCH_CHECK(c);
     } else {
-        lpmb_set_error("computeBondForceGeneral: plmode %d is not built (0, 4, 6 are)", plmode);
+        lpmb_set_error("computeBondForceGeneral: plmode %d is not built (0, 1, 4, 6 are)", plmode);
         return LPMB_ERR_UNSUPPORTED;
     }
     LPMB_TRY(lpmb_compute_stress(c));

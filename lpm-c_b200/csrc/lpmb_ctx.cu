@@ -74,6 +74,12 @@ static const FieldSpec kSpecs[] = {
     {"disp", FK_DOF, FT_F64, -1, 0},
     {"dispBC_index", FK_DOF, FT_I32, -1, 1}, {"fix_index", FK_DOF, FT_I32, -1, 1},
     {"Pin", FK_PIN, FT_F64, 3, 0},
+    // crystal plasticity (slipSysDefine3D, initialization.c:570,817-826): comps -2 = nslipSys, -3 = nslipSys^2
+    {"cp_gy0", FK_PART, FT_F64, -2, 0}, {"cp_gy1", FK_PART, FT_F64, -2, 0}, {"cp_gy2", FK_PART, FT_F64, -2, 0},
+    {"cp_A_single0", FK_PART, FT_F64, -2, 0}, {"cp_A_single1", FK_PART, FT_F64, -2, 0}, {"cp_A_single2", FK_PART, FT_F64, -2, 0},
+    {"cp_A0", FK_PART, FT_F64, 1, 0}, {"cp_A1", FK_PART, FT_F64, 1, 0}, {"cp_A2", FK_PART, FT_F64, 1, 0},
+    {"cp_Cab", FK_PART, FT_F64, -3, 0}, {"cp_RSS", FK_PART, FT_F64, -2, 0}, {"cp_Jact", FK_PART, FT_I32, -2, 0},
+    {"cp_dgy", FK_PART, FT_F64, -2, 0}, {"cp_dA", FK_PART, FT_F64, 1, 0}, {"cp_dA_single", FK_PART, FT_F64, -2, 0},
     // snapshots used by harnesses to replay an iteration from the same state
     {"xyz_save", FK_PART, FT_F64, 3, 0}, {"residual_save", FK_DOF, FT_F64, -1, 0},
 };
@@ -119,7 +125,19 @@ Field *lpmb_field(lpmb_ctx *c, const char *name)
         lpmb_set_error("unknown field '%s'", name);
         return nullptr;
     }
-    int comps = s->comps == 0 ? c->nn : (s->comps < 0 ? c->dim : s->comps);
+    int comps = s->comps;
+    if (s->comps == 0)
+        comps = c->nn;
+    else if (s->comps == -1)
+        comps = c->dim;
+    else if (s->comps <= -2) {
+        const int S = (int)param(c, "nslipSys", 0.0);
+        if (S <= 0) {
+            lpmb_set_error("field '%s' needs nslipSys (lpmb_set_schmid_tensor) first", name);
+            return nullptr;
+        }
+        comps = s->comps == -2 ? S : S * S;
+    }
     if (lpmb_field_alloc(c, name, s->kind, s->type, comps) != LPMB_OK)
         return nullptr;
     Field *f = &c->fields[name];
@@ -207,6 +225,24 @@ __global__ void to_host_layout(const TD *__restrict__ in, TH *__restrict__ out, 
 
 static size_t host_elem(const Field &f) { return f.type == FT_F64 ? 8 : 4; }  // int8 fields are int on the host
 
+// element-wise variants for rows too wide for a shared-memory tile (set-up data only)
+__global__ void wide_to_device(const double *__restrict__ in, double *__restrict__ out, int N, int Np, int C)
+{
+    const size_t total = (size_t)N * C;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t comp = e / N, i = e % N;  // consecutive threads -> consecutive particles of one component
+        out[comp * Np + i] = in[i * C + comp];
+    }
+}
+__global__ void wide_to_host(const double *__restrict__ in, double *__restrict__ out, int N, int Np, int C)
+{
+    const size_t total = (size_t)N * C;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t comp = e / N, i = e % N;
+        out[i * C + comp] = in[comp * Np + i];
+    }
+}
+
 // host [N][comps] doubles -> device [comps][Np] (not a registered field: CG vectors, masks, ...)
 int lpmb_upload_soa_f64(lpmb_ctx *c, const double *host, double *d_dst, int comps)
 {
@@ -248,7 +284,10 @@ extern "C" int lpmb_field_set(lpmb_ctx *c, const char *name, const void *host, s
     LPMB_CUDA(cudaMemcpyAsync(c->staging, host, bytes, cudaMemcpyHostToDevice, c->stream));
     const int blocks = c->Np / 32;
     const size_t smem = (size_t)32 * f->comps * host_elem(*f);
-    if (f->type == FT_F64)
+    if (smem > 40 * 1024) {  // very wide rows (cp_Cab: nslipSys^2 components): plain element-wise re-layout
+        LPMB_REQUIRE(f->type == FT_F64, LPMB_ERR_UNSUPPORTED, "wide integer field %s", name);
+        wide_to_device<<<4 * c->sm_count, 256, 0, c->stream>>>((const double *)c->staging, (double *)f->d, c->N, c->Np, f->comps);
+    } else if (f->type == FT_F64)
         to_device_layout<double, double><<<blocks, 256, smem, c->stream>>>((const double *)c->staging, (double *)f->d, c->N, c->Np, f->comps);
     else if (f->type == FT_I32)
         to_device_layout<int, int><<<blocks, 256, smem, c->stream>>>((const int *)c->staging, (int *)f->d, c->N, c->Np, f->comps);
@@ -278,7 +317,10 @@ extern "C" int lpmb_field_get(lpmb_ctx *c, const char *name, void *host, size_t 
     LPMB_TRY(lpmb_ensure_staging(c, bytes));
     const int blocks = c->Np / 32;
     const size_t smem = (size_t)32 * f->comps * host_elem(*f);
-    if (f->type == FT_F64)
+    if (smem > 40 * 1024) {
+        LPMB_REQUIRE(f->type == FT_F64, LPMB_ERR_UNSUPPORTED, "wide integer field %s", name);
+        wide_to_host<<<4 * c->sm_count, 256, 0, c->stream>>>((const double *)f->d, (double *)c->staging, c->N, c->Np, f->comps);
+    } else if (f->type == FT_F64)
         to_host_layout<double, double><<<blocks, 256, smem, c->stream>>>((const double *)f->d, (double *)c->staging, c->N, c->Np, f->comps);
     else if (f->type == FT_I32)
         to_host_layout<int, int><<<blocks, 256, smem, c->stream>>>((const int *)f->d, (int *)c->staging, c->N, c->Np, f->comps);

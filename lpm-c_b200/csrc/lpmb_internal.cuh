@@ -161,6 +161,7 @@ int lpmb_set_connectivity_device(lpmb_ctx *c, const int *d_conn);
 int lpmb_derive_topology(lpmb_ctx *c, bool initial_geometry);
 int lpmb_compute_stress(lpmb_ctx *c);
 int lpmb_refresh_mask(lpmb_ctx *c);
+int lpmb_cp_return_map(lpmb_ctx *c);
 
 // multi-GPU helpers (lpmb_dist.cu); all are no-ops when world == 1
 static inline int lpmb_own0(const lpmb_ctx *c) { return c->own0; }

@@ -288,6 +288,87 @@ class RefLPM:
         self._finish_sc(E0, mu0, plmode, sigmay, J2_xi, J2_H, nbreak, critical_bstrain, damageb_A, damagec_A,
                         damage_threshold, damage_L, dtime, top_z)
 
+    def setup_fcc(self, box=(0.0, 10.0, 0.0, 10.0, 0.0, 10.0), radius=0.3, C11=107.3e3, C12=60.8e3, C44=28.3e3,
+                  cp_tau0=1.6, cp_taus=30.0, cp_h0=100.0, cp_p=4.0, cp_q=1.0, cp_eta=1000.0, cp_maxloop=10, dtime=0.1,
+                  top_z=None):
+        """Re-play the set-up of examples/FCC_Al_R0.3_001_tension.c (:62-229, :339-345 of the default driver for the
+        call order): FCC lattice, Al elastic constants, crystal plasticity (plmode 1, 24 slip systems).  That example
+        does not compile against the reference's current src/ (SURVEY section 2), its library functions do.
+        Types: 1 top layer, 2 x-line, 3 y-line, 4 top fix point, 5 lower layer (:160-164)."""
+        L = self.lib
+        self.si("lattice", 3)
+        self.si("dim", 3)
+        self.sd("radius", radius)
+        pbc = self.iarr("pbc", 3)
+        pbc[0] = pbc[1] = pbc[2] = 0
+        self.si("eulerflag", 0)
+        for a in ("angle1", "angle2", "angle3"):
+            self.sd(a, 0.0)
+        b = self.darr("box", 6)
+        for k in range(6):
+            b[k] = box[k]
+        self.sd("box_x", b[1] - b[0])
+        self.sd("box_y", b[3] - b[2])
+        self.sd("box_z", b[5] - b[4])
+        L.createCuboid()
+        L.moveParticle((C.c_double * 3)(-0.0, -0.0, -0.0))
+        L.initMatrices()
+        N = self.N
+        self.set_d2("xyz_initial", self.d2("xyz", N, 3))
+        L.searchNormalNeighbor()
+        L.searchAFEMNeighbor()
+        if top_z is None:
+            top_z = box[5]
+        ntype = 0
+        self.set_ptr("type", L.allocInt1D(N, ntype))
+        ntype += 1
+        r = radius
+        for args in ((-100.0, 100.0, -100.0, 100.0, top_z - 1.2 * r, 100.0), (-100.0, 1.2 * r, -100.0, 100.0, top_z - 1.2 * r, 100.0),
+                     (-100.0, 100.0, -100.0, 1.2 * r, top_z - 1.2 * r, 100.0), (-100.0, 1.2 * r, -100.0, 1.2 * r, top_z - 1.2 * r, 100.0),
+                     (-100.0, 100.0, -100.0, 100.0, -100.0, 1.2 * r)):
+            L.setTypeRect(*args, ntype)
+            ntype += 1
+        self.si("ntype", ntype)
+        self.set_ptr("Ce", L.allocDouble2D(ntype, 3, 0.0))
+        self.set_d2("Ce", np.tile(np.array([C11, C12, C44]), (ntype, 1)))
+        self.si("plmode", 1)
+        self.sd("cp_maxloop", cp_maxloop)
+        t0, ts = self.darr("cp_tau0", 3), self.darr("cp_taus", 3)
+        t0[0], t0[1], t0[2] = cp_tau0, 0.0, 0.0
+        ts[0], ts[1], ts[2] = cp_taus, 0.0, 0.0
+        self.sd("cp_h0", cp_h0)
+        self.sd("cp_p", cp_p)
+        self.sd("cp_q", cp_q)
+        self.sd("cp_eta", cp_eta)
+        self.sd("dtime", dtime)
+        self.si("nbreak", 20)
+        self.sd("critical_bstrain", 1.0e-2)
+        self.sd("damage_threshold", 0.9)
+        self.sd("damage_L", 0.5)
+        L.calcKnTv()
+        L.computedL()
+        L.slipSysDefine3D()
+        L.computeCab()
+
+    # crystal-plasticity arrays (allocated by slipSysDefine3D, initialization.c:570,817-826)
+    def get_cp(self, name: str) -> np.ndarray:
+        N, S = self.N, self.gi("nslipSys")
+        if name in ("cp_gy", "cp_A_single"):
+            return self.d3(name, N, S, 3)
+        if name == "cp_A":
+            return self.d2(name, N, 3)
+        if name == "cp_Cab":
+            return self.d2(name, N, S * S)
+        if name in ("cp_RSS", "cp_dgy", "cp_dA_single"):
+            return self.d2(name, N, S)
+        if name == "cp_Jact":
+            return self.i2(name, N, S)
+        if name == "cp_dA":
+            return self.d1(name, N)
+        if name == "schmid_tensor":
+            return self.d2(name, S, 6)
+        raise KeyError(name)
+
     def _finish_sc(self, E0, mu0, plmode, sigmay, J2_xi, J2_H, nbreak, critical_bstrain, damageb_A, damagec_A,
                    damage_threshold, damage_L, dtime, top_z):
         L = self.lib
