@@ -22,9 +22,10 @@
  *   constitutive.h:22-27       int updateDamageGeneral / updateBrittleDamage / updateDuctileDamagePwiseNonlocal
  *                                                                  lpmb_update_damage (+ the broken-bond log file)
  *   constitutive.h:29          void updateCrack()                  lpmb_update_crack
- *   constitutive.h:11,15-20,24-26  computeCab, the per-particle computeBondForce*(int), the unused damage
- *                              variants: symbols kept, fail loudly (exit 1) -- nothing in the drivers calls them
- *                              once stiffness.c is replaced, and the laws behind them are not built yet
+ *   constitutive.h:11          void computeCab()                   lpmb_set_schmid_tensor + lpmb_compute_cab
+ *   constitutive.h:15-20,24-26 the per-particle computeBondForce*(int) and the unused damage variants: symbols
+ *                              kept, fail loudly (exit 1) -- nothing in the drivers calls them once stiffness.c
+ *                              is replaced (use computeBondForceGeneral), plmode 3 / 5 are not built
  *
  * Declarations use empty parameter lists exactly like the reference's headers (the default driver
  * even calls updateRR(ni++), lpmc_project.c:462 -- harmless under the SysV x86-64 ABI).

@@ -35,12 +35,18 @@ extern double **dL_total, **TdL_total, **csx_initial, **csy_initial, **csz_initi
 extern double **dL_ave, **ddL_total, **TddL_total, **F_temp, **ddLp, **dL, **ddL, **bond_stress, **damage_broken, **damage_w;
 extern double **Kn, **Tv, **J2_alpha, **damage_local, **damage_nonlocal, **J2_beta_eq;
 extern double ***dLp, ***J2_beta, ***damage_D;
+/* crystal plasticity (allocated by slipSysDefine3D, initialization.c:570,817-826) */
+extern double cp_tau0[3], cp_taus[3], cp_eta, cp_p, cp_h0, cp_q, cp_maxloop;
+extern double **schmid_tensor, **cp_RSS, **cp_Cab, **cp_A, **cp_dgy, **cp_dA_single, *cp_dA;
+extern int **cp_Jact;
+extern double ***cp_gy, ***cp_A_single;
 
 static lpmb_ctx *g_ctx = NULL;
 static double *g_buf = NULL; /* flat staging for one array */
 static size_t g_buf_bytes = 0;
 static int g_device_bc = 0;
 static int g_state_uploaded = 0;
+static int g_cp_ready = 0;
 
 #define CK(call)                                                                               \
     do {                                                                                       \
@@ -143,6 +149,45 @@ static void set_params(void)
     CK(lpmb_set_param(g_ctx, "critical_bstrain", critical_bstrain));
     CK(lpmb_set_param(g_ctx, "nbreak", (double)nbreak));
     CK(lpmb_set_param(g_ctx, "dtime", dtime));
+    if (nslipSys > 0) {
+        CK(lpmb_set_param(g_ctx, "cp_h0", cp_h0));
+        CK(lpmb_set_param(g_ctx, "cp_taus0", cp_taus[0]));
+        CK(lpmb_set_param(g_ctx, "cp_tau00", cp_tau0[0]));
+        CK(lpmb_set_param(g_ctx, "cp_q", cp_q));
+        CK(lpmb_set_param(g_ctx, "cp_eta", cp_eta));
+        CK(lpmb_set_param(g_ctx, "cp_p", cp_p));
+        CK(lpmb_set_param(g_ctx, "cp_maxloop", cp_maxloop));
+    }
+}
+
+/* crystal-plasticity set-up data and state: uploaded once slip systems exist (slipSysDefine3D has run) */
+static void ensure_cp(void)
+{
+    if (g_cp_ready || nslipSys <= 0)
+        return;
+    g_cp_ready = 1;
+    const int N = nparticle, S = nslipSys;
+    double *sch = (double *)malloc(sizeof(double) * S * 6);
+    for (int m = 0; m < S; m++)
+        memcpy(sch + 6 * m, schmid_tensor[m], 6 * sizeof(double));
+    CK(lpmb_set_schmid_tensor(g_ctx, sch, S));
+    free(sch);
+    up_d2("cp_Cab", cp_Cab, N, S * S);
+    for (int s = 0; s < 3; s++) {
+        up_slot("cp_gy", cp_gy, N, S, s);
+        up_slot("cp_A_single", cp_A_single, N, S, s);
+        up_pslot("cp_A", cp_A, N, s);
+    }
+}
+
+static void down_cp_slots(int s)
+{
+    if (nslipSys <= 0)
+        return;
+    const int N = nparticle, S = nslipSys;
+    down_slot("cp_gy", cp_gy, N, S, s);
+    down_slot("cp_A_single", cp_A_single, N, S, s);
+    down_pslot("cp_A", cp_A, N, s);
 }
 
 /* host-owned inputs that the driver / boundary.c may have changed since our last call */
@@ -362,10 +407,13 @@ void solverPARDISO()
 void switchStateV(int conv_flag)
 {
     ensure_state();
+    ensure_cp();
     CK(lpmb_switch_state(g_ctx, conv_flag));
     const int N = nparticle, nn = nneighbors;
     const int dst = conv_flag == 1 ? 1 : 0;
+    ensure_cp();
     down_slots(dst);
+    down_cp_slots(dst);
     if (conv_flag != 2) {
         down_slot("damage_D", damage_D, N, nn, dst);
         down_pslot("damage_local", damage_local, N, dst);
@@ -382,6 +430,8 @@ void computeBondForceGeneral(int mode, int temp)
         up_d2("xyz_temp", xyz_temp, N, 3);
         up_d2("F_temp", F_temp, N, nn);
     }
+    if (mode == 1)
+        ensure_cp();
     CK(lpmb_bond_force(g_ctx, mode, temp));
     down_d2("F", F, N, nn);
     DOWN1D("Pin", Pin, (size_t)NDIM * N);
@@ -409,7 +459,26 @@ void computeBondForceGeneral(int mode, int temp)
         DOWN1D("pl_flag", pl_flag, N);
         down_slots(2);
     }
+    if (mode == 1) {
+        const int S = nslipSys;
+        down_d2("dL_ave", dL_ave, N, nn);
+        down_d2("ddLp", ddLp, N, nn);
+        DOWN1D("pl_flag", pl_flag, N);
+        down_d2("cp_RSS", cp_RSS, N, S);
+        down_d2("cp_dgy", cp_dgy, N, S);
+        down_d2("cp_dA_single", cp_dA_single, N, S);
+        DOWN1D("cp_dA", cp_dA, N);
+        {
+            int *b = (int *)buf((size_t)N * S * sizeof(int));
+            CK(lpmb_field_get(g_ctx, "cp_Jact", b, (size_t)N * S));
+            for (int i = 0; i < N; i++)
+                memcpy(cp_Jact[i], b + (size_t)i * S, sizeof(int) * S);
+        }
+        down_slots(2);
+        down_cp_slots(2);
+    }
     down_slots(0); /* switchStateV(2) ran inside (constitutive.c:145) */
+    down_cp_slots(0);
 }
 
 static int damage(const char *dataName, int tstep, int mode)
@@ -472,11 +541,29 @@ static void not_built(const char *what)
     fprintf(stderr, "lpmc_dropin: %s is not available in the B200 build (no CPU fallback)\n", what);
     exit(1);
 }
-void computeCab() { not_built("computeCab (crystal plasticity)"); }
+void computeCab()
+{
+    ensure_state(); /* Kn, Tv, cs*, damage_broken, nb (calcKnTv and computedL have run: lpmc_project.c:339-345) */
+    const int N = nparticle, nn = nneighbors, S = nslipSys;
+    if (S <= 0)
+        return;
+    set_params();
+    up_d2("distance", distance, N, nn);
+    up_d2("csx", csx, N, nn);
+    up_d2("csy", csy, N, nn);
+    up_d2("csz", csz, N, nn);
+    double *sch = (double *)malloc(sizeof(double) * S * 6);
+    for (int m = 0; m < S; m++)
+        memcpy(sch + 6 * m, schmid_tensor[m], 6 * sizeof(double));
+    CK(lpmb_set_schmid_tensor(g_ctx, sch, S));
+    free(sch);
+    CK(lpmb_compute_cab(g_ctx));
+    down_d2("cp_Cab", cp_Cab, N, S * S);
+}
 void computeBondForceElastic(int i) { (void)i; not_built("computeBondForceElastic(i): per-particle evaluation is internal to the GPU assembly"); }
 void computeBondForceJ2mixedLinear3D(int ii) { (void)ii; not_built("computeBondForceJ2mixedLinear3D(ii): use computeBondForceGeneral(0, t)"); }
 void computeBondForceJ2nonlinearIso(int ii) { (void)ii; not_built("computeBondForceJ2nonlinearIso (plmode 5)"); }
-void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe (plmode 1)"); }
+void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe(ii): use computeBondForceGeneral(1, t)"); }
 void computeBondForceIncrementalUpdating(int ii) { (void)ii; not_built("computeBondForceIncrementalUpdating(ii): use computeBondForceGeneral(4, t)"); }
 void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap (plmode 3)"); }
 int updateDuctileDamageBwiseLocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamageBwiseLocal"); return 0; }

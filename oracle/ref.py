@@ -24,7 +24,9 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-REF_SO = HERE / "_ref" / "liblpmc_ref.so"
+# LPMB_REF_SO selects another build of the same driver TU, e.g. _ref/liblpmc_b200host.so = the reference's host code
+# linked against the GPU drop-in library instead of its own stiffness.c / solver.c / constitutive.c
+REF_SO = Path(os.environ.get("LPMB_REF_SO", HERE / "_ref" / "liblpmc_ref.so"))
 
 c_dp = C.POINTER(C.c_double)
 c_dpp = C.POINTER(c_dp)

@@ -123,7 +123,8 @@ def main():
         g[f"{s}.commit.dLp"] = r.get("dLp")
         g[f"{s}.commit.J2_alpha"] = r.get("J2_alpha")
     g["newton_counts"] = np.array(newton_counts)
-    out = Path(__file__).resolve().parent / "sc6_j2.npz"
+    import os
+    out = Path(os.environ.get("LPMB_GOLDEN_OUT", Path(__file__).resolve().parent / "sc6_j2.npz"))
     np.savez_compressed(out, **g)
     print("wrote", out, out.stat().st_size / 1e6, "MB; newton iterations per step:", newton_counts)
 

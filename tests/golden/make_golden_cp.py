@@ -67,7 +67,8 @@ def main():
         L.switchStateV(1)
         state(r, f"{s}.end", g)
     g["newton_counts"] = np.array(counts)
-    out = Path(__file__).resolve().parent / "fcc_cp.npz"
+    import os
+    out = Path(os.environ.get("LPMB_GOLDEN_OUT", Path(__file__).resolve().parent / "fcc_cp.npz"))
     np.savez_compressed(out, **g)
     print("wrote", out, round(out.stat().st_size / 1e6, 2), "MB; newton iterations per step:", counts)
 

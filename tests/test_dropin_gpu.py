@@ -102,3 +102,53 @@ def test_brittle_example_matches_cpu_reference(tmp_path, name):
     last = max(k for k, ln in enumerate(bc) if ln.startswith("TIMESTEP"))
     assert bg[:last] == bc[:last], "broken-bond logs diverge"
     print(f"{name}: {nf} force records agree to {wf:.1e}, {nd} disp records to {wd:.1e}, {last} broken-bond log lines identical")
+
+
+def _regen(script, tmp_path, out_name):
+    """run a golden generator with the reference's HOST code + GPU drop-in library instead of the all-CPU build"""
+    import sys
+    host = REFDIR / "liblpmc_b200host.so"
+    if not host.exists():
+        pytest.skip("oracle/_ref/liblpmc_b200host.so not built")
+    out = tmp_path / out_name
+    env = dict(os.environ, LPMB_REF_SO=str(host), LPMB_GOLDEN_OUT=str(out))
+    r = subprocess.run([sys.executable, str(GOLD / script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return np.load(out)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def test_dropin_replays_j2_golden_case(tmp_path):
+    """the generator of tests/golden/sc6_j2.npz, re-run with every hot-path call going through liblpmc_dropin.so:
+    same Newton / CG iteration counts, first-call outputs bit-exact, later states within 1e-9"""
+    new = _regen("make_golden.py", tmp_path, "sc6.npz")
+    old = np.load(GOLD / "sc6_j2.npz")
+    assert list(new["newton_counts"]) == list(old["newton_counts"])
+    for k in ("s1.fd.K_global", "s1.fd.IK", "s1.fd.JK", "s1.fd.Pin", "s1.fd.dL", "s1.pred.F", "s1.pred.Pin", "s1.rr.residual", "s1.n0.K_bc"):
+        assert np.array_equal(new[k], old[k]), k
+    for t in ("s1.n0", "s1.n1", "s2.n0"):
+        assert int(new[f"{t}.cg_iters"][0]) == int(old[f"{t}.cg_iters"][0])
+        assert _rel(new[f"{t}.disp"], old[f"{t}.disp"]) <= 1e-10
+        assert _rel(new[f"{t}.bf.F"], old[f"{t}.bf.F"]) <= 1e-9
+        assert _rel(new[f"{t}.bf.dLp"], old[f"{t}.bf.dLp"]) <= 1e-9
+    for k in ("s2.crack.F", "s2.crack.xyz", "s2.crack.stress_tensor", "s2.crack.damage_w", "s2.commit.dLp", "s2.commit.J2_alpha",
+              "s2.dam.damage_nonlocal"):
+        assert _rel(new[k], old[k]) <= 1e-9, k
+    assert np.array_equal(new["s2.crack.nb"], old["s2.crack.nb"])
+
+
+def test_dropin_replays_crystal_plasticity_golden_case(tmp_path):
+    """same for tests/golden/fcc_cp.npz: computeCab() + computeBondForceGeneral(1, .) through the drop-in layer"""
+    new = _regen("make_golden_cp.py", tmp_path, "fcc.npz")
+    old = np.load(GOLD / "fcc_cp.npz")
+    assert list(new["newton_counts"]) == list(old["newton_counts"])
+    assert np.array_equal(new["setup.cp_Cab"], old["setup.cp_Cab"])
+    for s in ("s1.end", "s2.end"):
+        assert np.array_equal(new[f"{s}.cp_Jact"], old[f"{s}.cp_Jact"])
+        for n in ("F", "stress_tensor", "cp_A", "cp_gy", "cp_A_single", "dLp"):
+            assert _rel(new[f"{s}.{n}"], old[f"{s}.{n}"]) <= 1e-8, (s, n)
+        assert _rel(new[f"{s}.xyz"] - old["setup.xyz"], old[f"{s}.xyz"] - old["setup.xyz"]) <= 1e-9
