@@ -76,11 +76,12 @@ nonlocal_damage_kernel(int N, int Np, CellGrid g, const double *__restrict__ x0 
 __global__ void __launch_bounds__(DT)
 nonlocal_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, double thr, const double *__restrict__ Dn,
                       double *__restrict__ broken, double *__restrict__ dD0, double *__restrict__ w, signed char *__restrict__ newly,
-                      int *__restrict__ count)
+                      int *__restrict__ count, int own0, int own1)
 {
     const int i = blockIdx.x * DT + threadIdx.x;
     if (i >= N)
         return;
+    const bool owned = i >= own0 && i < own1;  // ghost bonds (multi-GPU) are updated too but counted by their owner
     const double Di = Dn[i];
     const int n = nbi[i];
     int k = 0;
@@ -104,7 +105,7 @@ nonlocal_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__r
         w[e] = 1.0 - d;
         newly[e] = nw;
     }
-    if (k)
+    if (k && owned)
         atomicAdd(count, k);
 }
 
@@ -173,17 +174,32 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
             cudaFree(d_count);
             return rc;
         }
+        // multi-GPU: the Gaussian reaches 3*damage_L beyond the owned slab -> refresh the ghosts' inputs first
+        LPMB_TRY(lpmb_dist_exchange(c, fptr<double>(c, "J2_dlambda"), 1, true));
+        LPMB_TRY(lpmb_dist_exchange(c, fptr<double>(c, "J2_triaxiality"), 1, true));
         nonlocal_damage_kernel<<<g, DT, 0, c->stream>>>(N, Np, *grid, x0, L, thr, param(c, "damagec_A"), param(c, "particle_volume"),
                                                         fptr<double>(c, "J2_dlambda"), fptr<double>(c, "J2_triaxiality"),
                                                         fptr<double>(c, "damage_nonlocal0"));
         LPMB_LAUNCH_CHECK(c);
         signed char *newly = nullptr;
         LPMB_CUDA(cudaMalloc(&newly, (size_t)nn * Np));
-        nonlocal_break_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, thr, fptr<double>(c, "damage_nonlocal0"), broken, dD0, w, newly, d_count);
+        // ... and the ghosts' damage itself (their own Gaussian would reach beyond the local block)
+        LPMB_TRY(lpmb_dist_exchange(c, fptr<double>(c, "damage_nonlocal0"), 1, true));
+        nonlocal_break_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, thr, fptr<double>(c, "damage_nonlocal0"), broken, dD0, w, newly, d_count,
+                                                       lpmb_own0(c), lpmb_own1(c));
         LPMB_LAUNCH_CHECK(c);
         int k = 0;
         LPMB_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->world > 1) {  // global count of newly broken bonds
+            LPMB_TRY(lpmb_cg_alloc(c));
+            double kd = (double)k;
+            LPMB_CUDA(cudaMemcpyAsync(c->cg.scal + 9, &kd, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            LPMB_TRY(lpmb_dist_allreduce_sum(c, c->cg.scal + 9, 1));
+            LPMB_CUDA(cudaMemcpyAsync(&kd, c->cg.scal + 9, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            LPMB_CUDA(cudaStreamSynchronize(c->stream));
+            k = (int)(kd + 0.5);
+        }
         *broken_out = k;
         if (k > 0 && pairs && max_pairs > 0) {
             // reference logging order: i ascending, then slot j ascending (constitutive.c:1829-1845)
@@ -202,6 +218,7 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
         }
         cudaFree(newly);
     } else if (plmode == 6) {
+        LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "brittle damage (global selection of the nbreak largest strains) is single-GPU only");
         LPMB_REQUIRE(c->params.count("critical_bstrain") && c->params.count("nbreak"), LPMB_ERR_STATE, "critical_bstrain / nbreak not set");
         const int cap = 1 << 16;
         int *keys;

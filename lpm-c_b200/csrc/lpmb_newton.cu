@@ -58,10 +58,10 @@ __global__ void disp_bc_kernel(int N, int Np, const int *__restrict__ type, int 
     bc[(size_t)axis * Np + i] = 0;
 }
 
-__global__ void count_type_kernel(int N, const int *__restrict__ type, int t, int *__restrict__ count)
+__global__ void count_type_kernel(int N, const int *__restrict__ type, int t, int *__restrict__ count, int own0, int own1)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool hit = i < N && type[i] == t;
+    const bool hit = i < N && i >= own0 && i < own1 && type[i] == t;
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if ((threadIdx.x & 31) == 0 && m)
         atomicAdd(count, __popc(m));
@@ -99,11 +99,19 @@ extern "C" int lpmb_apply_force_bc(lpmb_ctx *c, int type, double step_x, double 
     LPMB_TRY(lpmb_cg_alloc(c));
     int *d_count = reinterpret_cast<int *>(c->cg.scal + 14);
     LPMB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
-    count_type_kernel<<<lpmb_blocks(c->N, 256), 256, 0, c->stream>>>(c->N, fptr<int>(c, "type"), type, d_count);
+    count_type_kernel<<<lpmb_blocks(c->N, 256), 256, 0, c->stream>>>(c->N, fptr<int>(c, "type"), type, d_count, lpmb_own0(c), lpmb_own1(c));
     LPMB_LAUNCH_CHECK(c);
     int n = 0;
     LPMB_CUDA(cudaMemcpyAsync(&n, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->world > 1) {  // the load is shared by all particles of that type in the whole lattice (boundary.c:53-58)
+        double nd = (double)n;
+        LPMB_CUDA(cudaMemcpyAsync(c->cg.scal + 9, &nd, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LPMB_TRY(lpmb_dist_allreduce_sum(c, c->cg.scal + 9, 1));
+        LPMB_CUDA(cudaMemcpyAsync(&nd, c->cg.scal + 9, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        n = (int)(nd + 0.5);
+    }
     if (n == 0)
         return LPMB_OK;
     // boundary.c:63-66: step / sum_forceBC (double / int)

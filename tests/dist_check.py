@@ -31,8 +31,13 @@ def main():
         it, nr = c.newton_iteration(0, 1)
         its.append(it)
         nrs.append(nr)
+    # end of the load step: nonlocal damage (Gaussian gather across the slab boundary), crack update, commit
+    broken, _ = c.update_damage(0)
+    c.update_crack()
+    c.switch_state(1)
     own = slice(slab.own0, slab.own1)
-    mine = {k: torch.from_numpy(np.ascontiguousarray(c.get_field(k)[own])).cuda() for k in ("xyz", "F", "stress_tensor", "dLp0")}
+    KEYS = ("xyz", "F", "stress_tensor", "dLp0", "damage_nonlocal0", "damage_w", "damage_broken", "Pin")
+    mine = {k: torch.from_numpy(np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own])).cuda() for k in KEYS}
     gathered = {}
     for k, t in mine.items():
         sizes = [None] * world
@@ -50,12 +55,16 @@ def main():
             it, nr = c1.newton_iteration(0, 1)
             its1.append(it)
             nrs1.append(nr)
-        print(f"world={world} n={n}: CG iterations dist {its} single {its1}; residual norms dist {nrs} single {nrs1}")
-        ok &= its == its1
+        broken1, _ = c1.update_damage(0)
+        c1.update_crack()
+        c1.switch_state(1)
+        print(f"world={world} n={n}: CG iterations dist {its} single {its1}; residual norms dist {nrs} single {nrs1}; "
+              f"broken bonds dist {broken} single {broken1}")
+        ok &= its == its1 and broken == broken1
         ok &= all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(nrs, nrs1))
         x0 = c1.get_field("xyz_initial")
         for k in gathered:
-            ref = c1.get_field(k)
+            ref = c1.get_field(k).reshape(n ** 3, -1)
             a, b = gathered[k], ref
             if k == "xyz":
                 a, b = a - x0, b - x0
