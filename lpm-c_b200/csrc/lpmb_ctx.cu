@@ -387,6 +387,7 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaStreamSynchronize(c->stream);
     lpmb_grid_release(c);
     lpmb_dist_release(c);
+    lpmb_sym_release(c);
     for (auto &e : c->prof_events)
         cudaEventDestroy(e);
     for (auto &kv : c->fields)

@@ -76,6 +76,20 @@ struct SellMatrix {
     bool values_ready = false;
 };
 
+// Symmetric acceleration structure for the SpMV (lpmb_symspmv.cu): only blocks with column >= row are
+// streamed from HBM; the transposed (lower) contributions are gathered from the partner rows' upper blocks,
+// which a strip-ordered slice schedule keeps L2-resident.
+struct SymMatrix {
+    bool ready = false;
+    long long ukunits = 0, lkunits = 0;
+    long long *usptr = nullptr, *lsptr = nullptr;  // [nslices+1]
+    int *ucol = nullptr;                            // [ukunits+1][32]
+    double *uval = nullptr;                         // [ukunits+1][D*D][32] (last unit = zeros, padding target)
+    int *lcol = nullptr, *lpos = nullptr;           // [lkunits][32]: partner row j, position of block (j,i) in uval
+    int *order = nullptr;                           // slice processing order
+    int norder = 0;
+};
+
 struct CGWork {
     double *r = nullptr, *p = nullptr, *ap = nullptr, *x = nullptr;  // [D][Np] each
     double *partials = nullptr;                                       // [2][max_blocks]
@@ -109,6 +123,7 @@ struct lpmb_ctx {
     int narrow_recv_lo = 0, narrow_recv_hi = 0, narrow_send_lo = 0, narrow_send_hi = 0;
     int wide_send_lo = 0, wide_send_hi = 0;
     // optional live profiling of the dominant kernel (CUDA events around every CG SpMV launch)
+    SymMatrix sym;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
     double prof_spmv_ms = 0.0;
@@ -169,6 +184,12 @@ static inline int lpmb_own1(const lpmb_ctx *c) { return c->own1 < 0 ? c->N : c->
 int lpmb_dist_exchange(lpmb_ctx *c, double *v, int comps, bool wide);   // halo exchange of a [comps][Np] array
 int lpmb_dist_allreduce_sum(lpmb_ctx *c, double *d_buf, int count);     // in-stream, in place
 void lpmb_dist_release(lpmb_ctx *c);
+
+// symmetric SpMV (lpmb_symspmv.cu)
+int lpmb_sym_build(lpmb_ctx *c);
+void lpmb_sym_release(lpmb_ctx *c);
+int lpmb_sym_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int grid);
+long long lpmb_sym_bytes(lpmb_ctx *c);
 
 // solver-side entry points used across TUs
 int lpmb_cg_alloc(lpmb_ctx *c);

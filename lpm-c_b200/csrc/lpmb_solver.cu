@@ -173,6 +173,8 @@ extern "C" long long lpmb_spmv_bytes_stored(lpmb_ctx *c)
 {
     if (!c || !c->K.pattern_ready)
         return 0;
+    if (param(c, "spmv_symmetric", 0.0) != 0.0 && c->sym.usptr)
+        return lpmb_sym_bytes(c);
     const long long d = c->dim;
     return c->K.kunits * 32 * (8 * d * d + 4) + 8LL * (c->K.nslices + 1) + 16LL * d * c->Np;
 }
@@ -323,6 +325,7 @@ extern "C" int lpmb_matrix_from_upper_csr(lpmb_ctx *c, const double *K_global, l
     LPMB_LAUNCH_CHECK(c);
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
     K.values_ready = true;
+    c->sym.ready = false;  // the symmetric acceleration structure mirrors these values
     return LPMB_OK;
 }
 
@@ -372,6 +375,7 @@ extern "C" int lpmb_matrix_fill_test_pattern(lpmb_ctx *c)
         fill_test_pattern_kernel<2><<<blocks, 128, 0, c->stream>>>(K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
     LPMB_LAUNCH_CHECK(c);
     K.values_ready = true;
+    c->sym.ready = false;  // the symmetric acceleration structure mirrors these values
     return LPMB_OK;
 }
 
@@ -533,6 +537,12 @@ static int launch_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, bool u
     const int grid = spmv_grid(c);
     const int sb = slice_begin(c), se = slice_end(c);
     const double *m = use_mask ? c->mask : nullptr;
+    if (param(c, "spmv_symmetric", 0.0) != 0.0) {
+        // upper-triangle streaming variant (lpmb_symspmv.cu); the structure mirrors K.val and is rebuilt lazily
+        if (!c->sym.ready)
+            LPMB_TRY(lpmb_sym_build(c));
+        return lpmb_sym_spmv(c, x, y, dot, m, c->cg.partials, dot ? c->cg.scal : nullptr, grid);
+    }
     if (c->dim == 3) {
         if (dot)
             spmv_sell_kernel<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
@@ -918,7 +928,9 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
     LPMB_REQUIRE(c && reps > 0 && ms_per_spmv, LPMB_ERR_ARG, "lpmb_spmv_bench: bad argument");
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
-    LPMB_REQUIRE(variant == 0, LPMB_ERR_ARG, "unknown SpMV variant %d", variant);
+    LPMB_REQUIRE(variant == 0 || variant == 1, LPMB_ERR_ARG, "unknown SpMV variant %d (0 = full SELL, 1 = symmetric upper)", variant);
+    const double saved_variant = param(c, "spmv_symmetric", 0.0);
+    c->params["spmv_symmetric"] = (double)variant;
     LPMB_TRY(lpmb_cg_alloc(c));
     fill_sin_kernel<<<vec_grid(c, (size_t)c->dim * c->Np), VEC_THREADS, 0, c->stream>>>(c->cg.p, c->dim, c->N, c->Np);
     LPMB_LAUNCH_CHECK(c);
@@ -937,5 +949,6 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_per_spmv = (double)ms / reps;
+    c->params["spmv_symmetric"] = saved_variant;
     return LPMB_OK;
 }
