@@ -123,8 +123,18 @@ int lpmb_matrix_fill_test_pattern(lpmb_ctx *ctx);
 /* y = K x on host DoF vectors (interleaved); for tests and the SpMV micro-benchmark */
 int lpmb_spmv_host(lpmb_ctx *ctx, const double *x, double *y);
 /* repeat y = K x `reps` times on device-resident vectors, returns mean milliseconds per SpMV
- * measured with CUDA events on the context stream.  variant: 0 = default kernel */
+ * measured with CUDA events on the context stream.  variant: 0 = full-format SELL kernel, 1 = experimental
+ * L2-mediated symmetric storage, 2 = brick-blocked symmetric kernel (needs lpmb_matrix_enable_bricks) */
 int lpmb_spmv_bench(lpmb_ctx *ctx, int reps, int variant, double *ms_per_spmv);
+/* Brick-blocked symmetric SpMV (lpmb_brick.cu): K is symmetric (stiffness.c:441-481 keeps one triangle), so
+ * every block is streamed from HBM once and used for both of its contributions inside one CTA; about half the
+ * bytes of the full format per CG iteration.  Needs radius, xyz_initial and the connectivity; applies to
+ * axis-aligned simple-cubic 3-D lattices on a single GPU and returns LPMB_ERR_UNSUPPORTED (nothing enabled)
+ * otherwise.  Once on, lpmb_solve_cg* / lpmb_newton_iteration / lpmb_spmv_host use it; on = 0 releases it.
+ * Particle numbering at the ABI is unchanged (the brick order is internal to the solve). */
+int lpmb_matrix_enable_bricks(lpmb_ctx *ctx, int on);
+/* bytes one brick SpMV moves (matrix + staging + vectors); 0 when bricks are off */
+long long lpmb_spmv_bytes_bricks(lpmb_ctx *ctx);
 /* algorithmic bytes one SpMV moves: nblk*(8 d^2+4) + 4 (N+1) + 16 d N */
 long long lpmb_spmv_bytes(lpmb_ctx *ctx);
 /* bytes the device format actually streams (SELL padding included) */

@@ -41,6 +41,9 @@ lib.lpmb_spmv_bytes.restype = C.c_longlong
 lib.lpmb_spmv_bytes.argtypes = [c_vp]
 lib.lpmb_spmv_bytes_stored.restype = C.c_longlong
 lib.lpmb_spmv_bytes_stored.argtypes = [c_vp]
+lib.lpmb_spmv_bytes_bricks.restype = C.c_longlong
+lib.lpmb_spmv_bytes_bricks.argtypes = [c_vp]
+lib.lpmb_matrix_enable_bricks.argtypes = [c_vp, C.c_int]
 lib.lpmb_destroy.restype = None
 lib.lpmb_destroy.argtypes = [c_vp]
 lib.lpmb_create.argtypes = [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -234,6 +237,13 @@ class Context:
 
     def spmv_bytes_stored(self) -> int:
         return int(lib.lpmb_spmv_bytes_stored(self._h))
+
+    def enable_bricks(self, on: bool = True):
+        """brick-blocked symmetric SpMV for the CG (include/lpmb200.h); raises if the lattice is not eligible"""
+        _check(lib.lpmb_matrix_enable_bricks(self._h, 1 if on else 0))
+
+    def spmv_bytes_bricks(self) -> int:
+        return int(lib.lpmb_spmv_bytes_bricks(self._h))
 
     # -- solve
     def set_dof_mask(self, dispBC_index=None, fix_index=None):

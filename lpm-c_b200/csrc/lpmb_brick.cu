@@ -1,0 +1,627 @@
+// lpmb_brick.cu -- brick-blocked symmetric SpMV: every stored block is fetched from HBM once and used for
+// BOTH of its contributions on the same SM.
+//
+// Why.  K is symmetric (stiffness.c:441-481 keeps one triangle); the default SELL kernel streams both triangles
+// (61 blocks * 76 B per interior SC particle) and already runs at the HBM roofline, so the only way to make a CG
+// iteration faster is to move fewer bytes.  Re-using a block through L2 does not work on this chip (measured,
+// lpmb_symspmv.cu); re-using it inside one CTA does.
+//
+// How.  Particles are regrouped (internally only; the ABI keeps the reference's numbering) into bricks of 8x8x8
+// lattice sites = 512 rows = one CTA of 512 threads, thread r <-> row r.  A pair {i,j} is owned by the end point
+// from which the displacement j-i lies in the positive half space (dz>0, or dz=0 & dy>0, or dz=dy=0 & dx>0), so
+// ownership does not depend on any numbering.  Displacements are grouped in classes (30 positive ones + the
+// diagonal for the simple-cubic 2-hop stencil); the brick stores, class-major and coalesced over r, the 3x3
+// block K_{i,i+d} and the (permuted) column index.  For each class, thread r loads its block once and forms
+//        own[r]      += K   x_j        (registers)
+//        acc[i+d]    += K^T x_i        (shared memory, indexed by the target's position in the brick's
+//                                       12 x 12 x 10 extended box)
+// A class is a translation, so within a class all targets are distinct: plain shared-memory read-modify-write,
+// one __syncthreads per class, fixed summation order -> deterministic, no atomics.  Contributions that land
+// outside the brick are written to a per-brick staging box and folded in by a second, tiny gather kernel that
+// visits the (at most 11) source bricks of a row in a fixed order; it also applies the DoF mask and produces the
+// p.Ap partials.  Traffic per interior SC particle: 31*(72+4) B of matrix + ~110 B staging + vectors = 2.55 KB
+// instead of 4.69 KB.
+//
+// Scope of this first version: axis-aligned simple-cubic lattices in 3-D on one GPU (what the headline workload
+// is); anything else keeps the full-format kernel.  Enabled explicitly with lpmb_matrix_enable_bricks().
+#include <algorithm>
+
+#include "lpmb_internal.cuh"
+
+#define BE 8               // brick edge (lattice sites)
+#define BR 512             // rows per brick = BE^3 = threads per CTA
+#define EXX 12             // extended box: x,y in [-2, BE+2), z in [0, BE+2)
+#define EXY 12
+#define EXZ 10
+#define NSLOT (EXX * EXY * EXZ)
+#define MAXCLS 32
+
+struct BrickMatrix {
+    bool enabled = false, pattern_ready = false, values_ready = false;
+    int nbx = 0, nby = 0, nbz = 0, nbricks = 0, ncls = 0;
+    long long P = 0;                 // permuted, padded vector length per component = nbricks * BR
+    double q = 0, ox = 0, oy = 0, oz = 0;
+    int *perm = nullptr;             // [P] permuted row -> original particle (-1 = padding)
+    int *inv = nullptr;              // [Np] original particle -> permuted row
+    int *ic = nullptr;               // [3][Np] integer lattice coordinates
+    double *bval = nullptr;          // [nbricks][ncls][9][BR]
+    double *stage = nullptr;         // [nbricks][3][NSLOT]
+    double *ypart = nullptr;         // [3][P]
+    double *r = nullptr, *p = nullptr, *ap = nullptr, *x = nullptr, *b = nullptr, *mask = nullptr;  // CG vectors [3][P]
+    int cls_d[MAXCLS][3];            // displacement of each class (class 0 = diagonal)
+    int key2cls[125];
+};
+
+static std::map<lpmb_ctx *, BrickMatrix> g_bricks;
+
+__constant__ int c_cls_off[MAXCLS];  // slot offset dx + EXX (dy + EXY dz) of each class
+__constant__ int c_key2cls[125];
+
+void lpmb_brick_release(lpmb_ctx *c)
+{
+    auto it = g_bricks.find(c);
+    if (it == g_bricks.end())
+        return;
+    BrickMatrix &B = it->second;
+    cudaFree(B.perm); cudaFree(B.inv); cudaFree(B.ic); cudaFree(B.bval); cudaFree(B.stage); cudaFree(B.ypart);
+    cudaFree(B.r); cudaFree(B.p); cudaFree(B.ap); cudaFree(B.x); cudaFree(B.b); cudaFree(B.mask);
+    g_bricks.erase(it);
+}
+
+void lpmb_brick_touch(lpmb_ctx *c)
+{
+    auto it = g_bricks.find(c);
+    if (it != g_bricks.end())
+        it->second.values_ready = false;
+}
+
+bool lpmb_brick_active(lpmb_ctx *c)
+{
+    auto it = g_bricks.find(c);
+    return it != g_bricks.end() && it->second.enabled && c->world == 1;
+}
+
+// ---- set-up kernels ------------------------------------------------------------------------------
+// integer lattice coordinates of every particle; max deviation from the lattice (alignment check)
+__global__ void brick_quantize_kernel(int N, int Np, const double *__restrict__ x0, double ox, double oy, double oz, double q,
+                                      int *__restrict__ ic /* [3][Np] */, double *__restrict__ maxdev)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double dev = 0.0;
+    if (i < N) {
+        const double fx = (x0[i] - ox) / q, fy = (x0[(size_t)Np + i] - oy) / q, fz = (x0[(size_t)2 * Np + i] - oz) / q;
+        const double rx = rint(fx), ry = rint(fy), rz = rint(fz);
+        ic[i] = (int)rx;
+        ic[(size_t)Np + i] = (int)ry;
+        ic[(size_t)2 * Np + i] = (int)rz;
+        dev = fmax(fabs(fx - rx), fmax(fabs(fy - ry), fabs(fz - rz)));
+    }
+    // warp max, then one atomicMax on the bit pattern (non-negative doubles order like unsigned integers)
+    for (int o = 16; o > 0; o >>= 1)
+        dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long *>(maxdev), (unsigned long long)__double_as_longlong(dev));
+}
+
+__global__ void brick_count_kernel(int N, int Np, const int *__restrict__ ic, int nbx, int nby, int *__restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const int b = (ic[i] / BE) + nbx * ((ic[(size_t)Np + i] / BE) + nby * (ic[(size_t)2 * Np + i] / BE));
+    atomicAdd(&count[b], 1);
+}
+
+// row of particle i inside its brick = its local lattice position (bricks are addressed geometrically, so the
+// permutation is a pure function of the coordinates: deterministic)
+__global__ void brick_place_kernel(int N, int Np, const int *__restrict__ ic, int nbx, int nby, int *__restrict__ perm, int *__restrict__ inv,
+                                   int *__restrict__ clash)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const int ix = ic[i], iy = ic[(size_t)Np + i], iz = ic[(size_t)2 * Np + i];
+    const int b = (ix / BE) + nbx * ((iy / BE) + nby * (iz / BE));
+    const int lx = ix % BE, ly = iy % BE, lz = iz % BE;
+    const int r = lx + BE * (ly + BE * lz);
+    const long long prow = (long long)b * BR + r;
+    if (atomicCAS(&perm[prow], -1, i) != -1)
+        atomicExch(clash, 1);  // two particles on one lattice site
+    inv[i] = (int)prow;
+}
+
+// which displacement keys occur (key = (dx+2) + 5 (dy+2) + 25 (dz+2)); flags[125], flags[125] = out-of-reach seen
+__global__ void brick_keys_kernel(int N, int Np, const int *__restrict__ ic, const long long *__restrict__ sptr, const int *__restrict__ col,
+                                  const int *__restrict__ nbc, int *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const long long base = sptr[i >> 5] * 32 + (i & 31);
+    for (int k = 0; k < nbc[i]; k++) {
+        const int j = col[base + (long long)k * 32];
+        const int dx = ic[j] - ic[i], dy = ic[(size_t)Np + j] - ic[(size_t)Np + i], dz = ic[(size_t)2 * Np + j] - ic[(size_t)2 * Np + i];
+        if (dx < -2 || dx > 2 || dy < -2 || dy > 2 || dz < -2 || dz > 2)
+            flags[125] = 1;
+        else
+            flags[(dx + 2) + 5 * (dy + 2) + 25 * (dz + 2)] = 1;
+    }
+}
+
+__global__ void brick_fill_kernel(int N, int Np, const int *__restrict__ ic, const int *__restrict__ inv, const long long *__restrict__ sptr,
+                                  const int *__restrict__ col, const double *__restrict__ val, const int *__restrict__ nbc, int ncls,
+                                  double *__restrict__ bval)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const long long prow = inv[i];
+    const long long b = prow / BR;
+    const int r = (int)(prow % BR);
+    const long long kbase = sptr[i >> 5];
+    const int lane = i & 31;
+    for (int k = 0; k < nbc[i]; k++) {
+        const int j = col[(kbase + k) * 32 + lane];
+        const int dx = ic[j] - ic[i], dy = ic[(size_t)Np + j] - ic[(size_t)Np + i], dz = ic[(size_t)2 * Np + j] - ic[(size_t)2 * Np + i];
+        const int u = c_key2cls[(dx + 2) + 5 * (dy + 2) + 25 * (dz + 2)];
+        if (u < 0)
+            continue;  // negative half space: owned by the other end point
+#pragma unroll
+        for (int e = 0; e < 9; e++)
+            bval[((b * ncls + u) * 9 + e) * BR + r] = val[((kbase + k) * 9 + e) * 32 + lane];
+    }
+}
+
+// original-order [3][Np] <-> permuted [3][P]
+__global__ void brick_to_perm_kernel(long long P, int Np, const int *__restrict__ perm, const double *__restrict__ src, double *__restrict__ dst,
+                                     double fill)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * P)
+        return;
+    const int comp = (int)(t / P);
+    const long long prow = t % P;
+    const int i = perm[prow];
+    dst[t] = i >= 0 ? src[(size_t)comp * Np + i] : fill;
+}
+
+__global__ void brick_from_perm_kernel(int N, int Np, long long P, const int *__restrict__ inv, const double *__restrict__ src, double *__restrict__ dst)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3LL * N)
+        return;
+    const int comp = (int)(t / N), i = (int)(t % N);
+    dst[(size_t)comp * Np + i] = src[(size_t)comp * P + inv[i]];
+}
+
+// ---- the SpMV ------------------------------------------------------------------------------------
+// One persistent CTA per SM walks over bricks.  The 36 KB class tiles ([9][512] doubles, contiguous in HBM) are
+// streamed into a 4-deep shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier transaction counts),
+// issued by one thread and running ahead across brick boundaries, so ~147 KB per SM are in flight regardless of
+// the per-class barrier.  x of the brick's extended box lives in shared memory too: x_j and the transposed
+// target share the same slot index, so the kernel needs no column indices at all (absent blocks are zero).
+#define NST 4
+#define TILE_DOUBLES (9 * BR)
+#define TILE_BYTES (TILE_DOUBLES * 8)
+
+struct BrickSmem {
+    double tile[NST][9][BR];
+    double acc[3][NSLOT];
+    double xs[3][NSLOT];
+    unsigned long long full[NST];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(BR, 1)
+brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P, const double *__restrict__ bval, const double *__restrict__ x,
+                  double *__restrict__ ypart, double *__restrict__ stage, const double *__restrict__ scal)
+{
+    extern __shared__ __align__(128) unsigned char brick_smem_raw[];
+    BrickSmem &S = *reinterpret_cast<BrickSmem *>(brick_smem_raw);
+    if (scal && scal[7] != 0.0)  // S_DONE
+        return;
+    const int r = threadIdx.x;
+    const int lx = r & 7, ly = (r >> 3) & 7, lz = r >> 6;
+    const int myslot = (lx + 2) + EXX * ((ly + 2) + EXY * lz);
+    const int nloc = (int)blockIdx.x < nbricks ? (nbricks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const long long ntiles = (long long)nloc * ncls;
+    if (r == 0) {
+        for (int s = 0; s < NST; s++)
+            mbar_init(&S.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long t) {
+        const int s = (int)(t % NST);
+        const long long brick = blockIdx.x + (t / ncls) * (long long)gridDim.x;
+        const int u = (int)(t % ncls);
+        mbar_expect_tx(&S.full[s], TILE_BYTES);
+        bulk_g2s(&S.tile[s][0][0], bval + (brick * ncls + u) * (long long)TILE_DOUBLES, TILE_BYTES, &S.full[s]);
+    };
+    if (r == 0)
+        for (long long t = 0; t < NST && t < ntiles; t++)
+            issue(t);
+    long long t = 0;
+    for (int lb = 0; lb < nloc; lb++) {
+        const long long brick = blockIdx.x + (long long)lb * gridDim.x;
+        const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+        // x over the extended box (zero outside the lattice), accumulators to zero
+        for (int s = r; s < NSLOT; s += BR) {
+            const int gx = bx * BE + (s % EXX) - 2, gy = by * BE + ((s / EXX) % EXY) - 2, gz = bz * BE + s / (EXX * EXY);
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+            if (gx >= 0 && gx < nbx * BE && gy >= 0 && gy < nby * BE && gz < nbz * BE) {
+                const long long src = ((gx >> 3) + (long long)nbx * ((gy >> 3) + (long long)nby * (gz >> 3))) * BR + ((gx & 7) + BE * ((gy & 7) + BE * (gz & 7)));
+                v0 = x[src];
+                v1 = x[P + src];
+                v2 = x[2 * P + src];
+            }
+            S.xs[0][s] = v0;
+            S.xs[1][s] = v1;
+            S.xs[2][s] = v2;
+            S.acc[0][s] = S.acc[1][s] = S.acc[2][s] = 0.0;
+        }
+        __syncthreads();
+        const double xi0 = S.xs[0][myslot], xi1 = S.xs[1][myslot], xi2 = S.xs[2][myslot];
+        double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+        for (int u = 0; u < ncls; u++, t++) {
+            const int st = (int)(t % NST);
+            mbar_wait(&S.full[st], (unsigned)((t / NST) & 1));
+            double a[9];
+#pragma unroll
+            for (int e = 0; e < 9; e++)
+                a[e] = S.tile[st][e][r];
+            const int slot = myslot + c_cls_off[u];
+            const double xj0 = S.xs[0][slot], xj1 = S.xs[1][slot], xj2 = S.xs[2][slot];
+            o0 = fma(a[0], xj0, fma(a[1], xj1, fma(a[2], xj2, o0)));
+            o1 = fma(a[3], xj0, fma(a[4], xj1, fma(a[5], xj2, o1)));
+            o2 = fma(a[6], xj0, fma(a[7], xj1, fma(a[8], xj2, o2)));
+            if (u > 0) {  // class 0 is the diagonal block: no transposed partner
+                S.acc[0][slot] += fma(a[0], xi0, fma(a[3], xi1, a[6] * xi2));
+                S.acc[1][slot] += fma(a[1], xi0, fma(a[4], xi1, a[7] * xi2));
+                S.acc[2][slot] += fma(a[2], xi0, fma(a[5], xi1, a[8] * xi2));
+            }
+            __syncthreads();  // tile consumed by everybody; the next class may hit the same slots
+            if (r == 0 && t + NST < ntiles)
+                issue(t + NST);
+        }
+        const long long prow = brick * BR + r;
+        ypart[prow] = o0 + S.acc[0][myslot];
+        ypart[P + prow] = o1 + S.acc[1][myslot];
+        ypart[2 * P + prow] = o2 + S.acc[2][myslot];
+        // contributions that left the brick (all written every launch: the gather kernel reads all of them)
+        double *sg = stage + brick * 3 * NSLOT;
+        for (int s = r; s < NSLOT; s += BR) {
+            const int ex = s % EXX, ey = (s / EXX) % EXY, ez = s / (EXX * EXY);
+            const bool own = ex >= 2 && ex < BE + 2 && ey >= 2 && ey < BE + 2 && ez < BE;
+            if (!own) {
+                sg[s] = S.acc[0][s];
+                sg[NSLOT + s] = S.acc[1][s];
+                sg[2 * NSLOT + s] = S.acc[2][s];
+            }
+        }
+        __syncthreads();  // before the next brick's prologue overwrites xs / acc
+    }
+}
+
+// y = mask .* (ypart + contributions staged by neighbouring bricks), partial dot products x.y
+template <bool DOT>
+__global__ void __launch_bounds__(256)
+brick_gather_kernel(long long P, int nbx, int nby, int nbz, const double *__restrict__ ypart, const double *__restrict__ stage,
+                    const double *__restrict__ mask, const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partials,
+                    const double *__restrict__ scal)
+{
+    __shared__ double red[8];
+    if (DOT && scal && scal[7] != 0.0)
+        return;
+    double dot = 0.0;
+    for (long long prow = (long long)blockIdx.x * 256 + threadIdx.x; prow < P; prow += (long long)gridDim.x * 256) {
+        const long long b = prow / BR;
+        const int r = (int)(prow % BR);
+        const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((long long)nbx * nby));
+        const int lx = r & 7, ly = (r >> 3) & 7, lz = r >> 6;
+        double v0 = ypart[prow], v1 = ypart[P + prow], v2 = ypart[2 * P + prow];
+        // source bricks in a fixed order: dbz in {-1,0}, dby in {-1,0,+1}, dbx in {-1,0,+1}, own brick excluded.
+        // The brick at offset db sees this row in its extended box iff the row lies within 2 sites of that side.
+        for (int dbz = -1; dbz <= 0; dbz++) {
+            if (dbz == -1 && lz >= 2)
+                continue;
+            const int sz = bz + dbz;
+            if (sz < 0)
+                continue;
+            for (int dby = -1; dby <= 1; dby++) {
+                if ((dby == -1 && ly >= 2) || (dby == 1 && ly < BE - 2))
+                    continue;
+                const int sy = by + dby;
+                if (sy < 0 || sy >= nby)
+                    continue;
+                for (int dbx = -1; dbx <= 1; dbx++) {
+                    if ((dbx == -1 && lx >= 2) || (dbx == 1 && lx < BE - 2))
+                        continue;
+                    if (dbx == 0 && dby == 0 && dbz == 0)
+                        continue;
+                    const int sx = bx + dbx;
+                    if (sx < 0 || sx >= nbx)
+                        continue;
+                    const int ex = lx - BE * dbx + 2, ey = ly - BE * dby + 2, ez = lz - BE * dbz;
+                    const long long sb = sx + (long long)nbx * (sy + (long long)nby * sz);
+                    const int s = ex + EXX * (ey + EXY * ez);
+                    const double *sg = stage + sb * 3 * NSLOT;
+                    v0 += sg[s];
+                    v1 += sg[NSLOT + s];
+                    v2 += sg[2 * NSLOT + s];
+                }
+            }
+        }
+        if (mask) {
+            v0 *= mask[prow];
+            v1 *= mask[P + prow];
+            v2 *= mask[2 * P + prow];
+        }
+        if (DOT)
+            dot = fma(v0, x[prow], fma(v1, x[P + prow], fma(v2, x[2 * P + prow], dot)));
+        y[prow] = v0;
+        y[P + prow] = v1;
+        y[2 * P + prow] = v2;
+    }
+    if (DOT) {
+        for (int o = 16; o > 0; o >>= 1)
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if ((threadIdx.x & 31) == 0)
+            red[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tsum = 0.0;
+            for (int k = 0; k < 8; k++)
+                tsum += red[k];
+            partials[blockIdx.x] = tsum;
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+static int brick_upload_tables(const BrickMatrix &B)
+{
+    int off[MAXCLS] = {0};
+    for (int u = 0; u < B.ncls; u++)
+        off[u] = B.cls_d[u][0] + EXX * (B.cls_d[u][1] + EXY * B.cls_d[u][2]);
+    LPMB_CUDA(cudaMemcpyToSymbol(c_cls_off, off, sizeof(off)));
+    LPMB_CUDA(cudaMemcpyToSymbol(c_key2cls, B.key2cls, sizeof(int) * 125));
+    return LPMB_OK;
+}
+
+static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
+{
+    LPMB_REQUIRE(c->dim == 3 && c->lattice == LPMB_LATTICE_SC, LPMB_ERR_UNSUPPORTED, "brick SpMV: simple-cubic 3-D lattices only");
+    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "brick SpMV: single GPU only in this version");
+    LPMB_REQUIRE(c->params.count("radius") && c->fields.count("xyz_initial") && c->K.pattern_ready, LPMB_ERR_STATE,
+                 "brick SpMV needs radius, xyz_initial and the connectivity");
+    const int N = c->N, Np = c->Np;
+    const double *x0 = fptr<double>(c, "xyz_initial");
+    B.q = 2.0 * param(c, "radius");
+    // lattice origin = component-wise minimum
+    std::vector<double> hx((size_t)3 * Np);
+    LPMB_CUDA(cudaMemcpy(hx.data(), x0, hx.size() * 8, cudaMemcpyDeviceToHost));
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < N; i++) {
+            lo[k] = std::min(lo[k], hx[(size_t)k * Np + i]);
+            hi[k] = std::max(hi[k], hx[(size_t)k * Np + i]);
+        }
+    hx.clear();
+    hx.shrink_to_fit();
+    B.ox = lo[0];
+    B.oy = lo[1];
+    B.oz = lo[2];
+    const int nx = (int)llround((hi[0] - lo[0]) / B.q) + 1, ny = (int)llround((hi[1] - lo[1]) / B.q) + 1, nz = (int)llround((hi[2] - lo[2]) / B.q) + 1;
+    B.nbx = (nx + BE - 1) / BE;
+    B.nby = (ny + BE - 1) / BE;
+    B.nbz = (nz + BE - 1) / BE;
+    B.nbricks = B.nbx * B.nby * B.nbz;
+    B.P = (long long)B.nbricks * BR;
+    LPMB_REQUIRE(B.P < (1LL << 31), LPMB_ERR_UNSUPPORTED, "brick SpMV: %lld padded rows exceed 32-bit indices", B.P);
+    int *ic;
+    double *d_dev;
+    LPMB_CUDA(cudaMalloc(&ic, (size_t)3 * Np * sizeof(int)));
+    LPMB_CUDA(cudaMalloc(&d_dev, sizeof(double)));
+    LPMB_CUDA(cudaMemset(d_dev, 0, sizeof(double)));
+    brick_quantize_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, x0, B.ox, B.oy, B.oz, B.q, ic, d_dev);
+    LPMB_LAUNCH_CHECK(c);
+    double dev = 0.0;
+    LPMB_CUDA(cudaMemcpyAsync(&dev, d_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_dev);
+    if (dev > 1e-6) {
+        cudaFree(ic);
+        lpmb_set_error("brick SpMV: particles are not on an axis-aligned lattice of spacing %g (max deviation %g)", B.q, dev);
+        return LPMB_ERR_UNSUPPORTED;
+    }
+    LPMB_CUDA(cudaMalloc(&B.perm, (size_t)B.P * sizeof(int)));
+    LPMB_CUDA(cudaMemset(B.perm, 0xff, (size_t)B.P * sizeof(int)));
+    LPMB_CUDA(cudaMalloc(&B.inv, (size_t)Np * sizeof(int)));
+    int *d_flags;
+    LPMB_CUDA(cudaMalloc(&d_flags, 128 * sizeof(int)));
+    LPMB_CUDA(cudaMemset(d_flags, 0, 128 * sizeof(int)));
+    brick_place_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, ic, B.nbx, B.nby, B.perm, B.inv, d_flags + 126);
+    LPMB_LAUNCH_CHECK(c);
+    brick_keys_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, ic, c->K.sptr, c->K.col, c->K.nbc, d_flags);
+    LPMB_LAUNCH_CHECK(c);
+    int flags[128];
+    LPMB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_flags);
+    if (flags[125] || flags[126]) {
+        cudaFree(ic);
+        lpmb_set_error(flags[126] ? "brick SpMV: two particles share a lattice site" : "brick SpMV: a conn entry reaches further than 2 lattice steps");
+        return LPMB_ERR_UNSUPPORTED;
+    }
+    // classes: 0 = diagonal, then the positive half space in key order
+    B.ncls = 0;
+    for (int k = 0; k < 125; k++)
+        B.key2cls[k] = -1;
+    auto add_class = [&](int dx, int dy, int dz) {
+        const int key = (dx + 2) + 5 * (dy + 2) + 25 * (dz + 2);
+        B.key2cls[key] = B.ncls;
+        B.cls_d[B.ncls][0] = dx;
+        B.cls_d[B.ncls][1] = dy;
+        B.cls_d[B.ncls][2] = dz;
+        B.ncls++;
+    };
+    add_class(0, 0, 0);
+    for (int dz = 0; dz <= 2; dz++)
+        for (int dy = -2; dy <= 2; dy++)
+            for (int dx = -2; dx <= 2; dx++) {
+                const bool positive = dz > 0 || (dz == 0 && dy > 0) || (dz == 0 && dy == 0 && dx > 0);
+                if (positive && flags[(dx + 2) + 5 * (dy + 2) + 25 * (dz + 2)]) {
+                    if (B.ncls >= MAXCLS) {
+                        cudaFree(ic);
+                        lpmb_set_error("brick SpMV: more than %d displacement classes", MAXCLS);
+                        return LPMB_ERR_UNSUPPORTED;
+                    }
+                    add_class(dx, dy, dz);
+                }
+            }
+    LPMB_TRY(brick_upload_tables(B));
+    const size_t nent = (size_t)B.nbricks * B.ncls * BR;
+    LPMB_CUDA(cudaMalloc(&B.bval, nent * 9 * sizeof(double)));
+    LPMB_CUDA(cudaMalloc(&B.stage, (size_t)B.nbricks * 3 * NSLOT * sizeof(double)));
+    LPMB_CUDA(cudaMemset(B.stage, 0, (size_t)B.nbricks * 3 * NSLOT * sizeof(double)));
+    for (double **v : {&B.ypart, &B.r, &B.p, &B.ap, &B.x, &B.b, &B.mask}) {
+        LPMB_CUDA(cudaMalloc(v, (size_t)3 * B.P * sizeof(double)));
+        LPMB_CUDA(cudaMemset(*v, 0, (size_t)3 * B.P * sizeof(double)));
+    }
+    B.ic = ic;
+    B.pattern_ready = true;
+    return LPMB_OK;
+}
+
+static int brick_fill_values(lpmb_ctx *c, BrickMatrix &B)
+{
+    const size_t nent = (size_t)B.nbricks * B.ncls * BR;
+    LPMB_CUDA(cudaMemsetAsync(B.bval, 0, nent * 9 * sizeof(double), c->stream));
+    LPMB_TRY(brick_upload_tables(B));
+    brick_fill_kernel<<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, c->Np, B.ic, B.inv, c->K.sptr, c->K.col,
+                                                                     c->K.val, c->K.nbc, B.ncls, B.bval);
+    LPMB_LAUNCH_CHECK(c);
+    B.values_ready = true;
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_matrix_enable_bricks(lpmb_ctx *c, int on)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    if (!on) {
+        lpmb_brick_release(c);
+        return LPMB_OK;
+    }
+    BrickMatrix &B = g_bricks[c];
+    if (!B.pattern_ready) {
+        const int rc = brick_build_pattern(c, B);
+        if (rc != LPMB_OK) {
+            lpmb_brick_release(c);
+            return rc;
+        }
+    }
+    B.enabled = true;
+    return LPMB_OK;
+}
+
+extern "C" long long lpmb_spmv_bytes_bricks(lpmb_ctx *c) { return c ? lpmb_brick_bytes(c) : 0; }
+
+long long lpmb_brick_bytes(lpmb_ctx *c)
+{
+    auto it = g_bricks.find(c);
+    if (it == g_bricks.end())
+        return 0;
+    const BrickMatrix &B = it->second;
+    const long long nent = (long long)B.nbricks * B.ncls * BR;
+    const long long halo = (long long)B.nbricks * (NSLOT - BR) * 3 * 8;
+    return nent * 72 + 2 * halo + 3 * B.P * 8 * 4;  // matrix + staging (w+r) + x, ypart (w+r), y
+}
+
+// make sure the brick values mirror K.val
+int lpmb_brick_prepare(lpmb_ctx *c)
+{
+    BrickMatrix &B = g_bricks[c];
+    LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
+    if (!B.values_ready)
+        LPMB_TRY(brick_fill_values(c, B));
+    return LPMB_OK;
+}
+
+// CG work vectors in the permuted space
+void lpmb_brick_vectors(lpmb_ctx *c, double **r, double **p, double **ap, double **x, double **b, double **mask, long long *P)
+{
+    BrickMatrix &B = g_bricks[c];
+    *r = B.r;
+    *p = B.p;
+    *ap = B.ap;
+    *x = B.x;
+    *b = B.b;
+    *mask = B.mask;
+    *P = B.P;
+}
+
+int lpmb_brick_to_perm(lpmb_ctx *c, const double *src, double *dst)
+{
+    BrickMatrix &B = g_bricks[c];
+    brick_to_perm_kernel<<<lpmb_blocks(3 * B.P, 256), 256, 0, c->stream>>>(B.P, c->Np, B.perm, src, dst, 0.0);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+int lpmb_brick_from_perm(lpmb_ctx *c, const double *src, double *dst)
+{
+    BrickMatrix &B = g_bricks[c];
+    brick_from_perm_kernel<<<lpmb_blocks(3LL * c->N, 256), 256, 0, c->stream>>>(c->N, c->Np, B.P, B.inv, src, dst);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+// y = [mask .*] K x in the permuted space (+ p.Ap partials into `partials`, one per block of the gather grid)
+int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid)
+{
+    BrickMatrix &B = g_bricks[c];
+    static bool attr_set = false;
+    if (!attr_set) {
+        LPMB_CUDA(cudaFuncSetAttribute(brick_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
+        attr_set = true;
+    }
+    const int grid = B.nbricks < c->sm_count ? B.nbricks : c->sm_count;
+    brick_spmv_kernel<<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, x, B.ypart, B.stage,
+                                                                  dot ? scal : nullptr);
+    LPMB_LAUNCH_CHECK(c);
+    if (dot)
+        brick_gather_kernel<true><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, partials, scal);
+    else
+        brick_gather_kernel<false><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, nullptr, nullptr);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}

@@ -191,6 +191,17 @@ void lpmb_sym_release(lpmb_ctx *c);
 int lpmb_sym_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int grid);
 long long lpmb_sym_bytes(lpmb_ctx *c);
 
+// brick-blocked symmetric SpMV (lpmb_brick.cu): optional, single GPU, simple-cubic 3-D
+void lpmb_brick_release(lpmb_ctx *c);
+void lpmb_brick_touch(lpmb_ctx *c);   // K.val changed
+bool lpmb_brick_active(lpmb_ctx *c);
+int lpmb_brick_prepare(lpmb_ctx *c);
+void lpmb_brick_vectors(lpmb_ctx *c, double **r, double **p, double **ap, double **x, double **b, double **mask, long long *P);
+int lpmb_brick_to_perm(lpmb_ctx *c, const double *src, double *dst);
+int lpmb_brick_from_perm(lpmb_ctx *c, const double *src, double *dst);
+int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid);
+long long lpmb_brick_bytes(lpmb_ctx *c);
+
 // solver-side entry points used across TUs
 int lpmb_cg_alloc(lpmb_ctx *c);
 int lpmb_matrix_alloc_values(lpmb_ctx *c);

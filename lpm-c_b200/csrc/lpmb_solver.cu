@@ -325,7 +325,8 @@ extern "C" int lpmb_matrix_from_upper_csr(lpmb_ctx *c, const double *K_global, l
     LPMB_LAUNCH_CHECK(c);
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
     K.values_ready = true;
-    c->sym.ready = false;  // the symmetric acceleration structure mirrors these values
+    c->sym.ready = false;  // the symmetric acceleration structures mirror these values
+    lpmb_brick_touch(c);
     return LPMB_OK;
 }
 
@@ -375,7 +376,8 @@ extern "C" int lpmb_matrix_fill_test_pattern(lpmb_ctx *c)
         fill_test_pattern_kernel<2><<<blocks, 128, 0, c->stream>>>(K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
     LPMB_LAUNCH_CHECK(c);
     K.values_ready = true;
-    c->sym.ready = false;  // the symmetric acceleration structure mirrors these values
+    c->sym.ready = false;  // the symmetric acceleration structures mirror these values
+    lpmb_brick_touch(c);
     return LPMB_OK;
 }
 
@@ -727,16 +729,33 @@ reduce_to_scalar_kernel(const double *__restrict__ partials, int nparts, double 
 static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, int maxit, bool use_mask, int *iterations)
 {
     CGWork &w = c->cg;
-    const size_t n = (size_t)c->dim * c->Np;
+    size_t n = (size_t)c->dim * c->Np;
     const bool dist = c->world > 1;
     if (dist)
         use_mask = true;  // the mask also zeroes the ghost DoFs (lpmb_refresh_mask)
-    const int vg = vec_grid(c, n), sg = spmv_grid(c);
     double *part_a = w.partials, *part_b = w.partials + w.max_blocks;
     double *red_a = w.scal + 10, *red_b = w.scal + 11;  // per-rank scalars that get all-reduced
     const double *m = use_mask ? c->mask : nullptr;
     LPMB_REQUIRE(!use_mask || m, LPMB_ERR_STATE, "DoF mask not built");
-    cg_init_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(d_b, m, w.r, w.p, w.x, n, part_a);
+    // work vectors: the context's own, or -- brick-blocked symmetric SpMV (lpmb_brick.cu) -- the brick-ordered
+    // ones; the iteration below is the same, only the numbering of the unknowns differs
+    double *vr = w.r, *vp = w.p, *vap = w.ap, *vx = w.x;
+    const bool brick = lpmb_brick_active(c);
+    if (brick) {
+        double *vb, *vm;
+        long long P;
+        LPMB_TRY(lpmb_brick_prepare(c));
+        lpmb_brick_vectors(c, &vr, &vp, &vap, &vx, &vb, &vm, &P);
+        LPMB_TRY(lpmb_brick_to_perm(c, d_b, vb));
+        if (m) {
+            LPMB_TRY(lpmb_brick_to_perm(c, m, vm));
+            m = vm;
+        }
+        d_b = vb;
+        n = (size_t)3 * P;
+    }
+    const int vg = vec_grid(c, n), sg = brick ? vg : spmv_grid(c);
+    cg_init_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(d_b, m, vr, vp, vx, n, part_a);
     LPMB_LAUNCH_CHECK(c);
     if (dist) {
         reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, red_a, nullptr);
@@ -758,27 +777,30 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
         const int issued0 = issued;
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
             if (dist)
-                LPMB_TRY(lpmb_dist_exchange(c, w.p, c->dim, false));
+                LPMB_TRY(lpmb_dist_exchange(c, vp, c->dim, false));
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b], c->stream));
-            LPMB_TRY(launch_spmv(c, w.p, w.ap, true, use_mask));  // partials -> part_a (w.partials)
+            if (brick)
+                LPMB_TRY(lpmb_brick_spmv(c, vp, vap, true, m, part_a, w.scal, sg));
+            else
+                LPMB_TRY(launch_spmv(c, vp, vap, true, use_mask));  // partials -> part_a (w.partials)
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b + 1], c->stream));
             if (dist) {
                 reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, sg, red_a, w.scal);
                 LPMB_LAUNCH_CHECK(c);
                 LPMB_TRY(lpmb_dist_allreduce_sum(c, red_a, 1));
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, red_a, 1, part_b, w.scal, parity);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, red_a, 1, part_b, w.scal, parity);
                 LPMB_LAUNCH_CHECK(c);
                 reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_b, vg, red_b, w.scal);
                 LPMB_LAUNCH_CHECK(c);
                 LPMB_TRY(lpmb_dist_allreduce_sum(c, red_b, 1));
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, red_b, 1, w.scal, parity, maxit);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, red_b, 1, w.scal, parity, maxit);
                 LPMB_LAUNCH_CHECK(c);
             } else {
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, part_a, sg, part_b, w.scal, parity);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, part_a, sg, part_b, w.scal, parity);
                 LPMB_LAUNCH_CHECK(c);
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.p, n, part_b, vg, w.scal, parity, maxit);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, part_b, vg, w.scal, parity, maxit);
                 LPMB_LAUNCH_CHECK(c);
             }
             cg_bookkeep_kernel<<<1, 1, 0, c->stream>>>(w.scal, parity, maxit);
@@ -800,6 +822,8 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
         if (w.h_scal[S_DONE] != 0.0 || issued >= maxit)
             break;
     }
+    if (brick)
+        LPMB_TRY(lpmb_brick_from_perm(c, vx, w.x));
     if (iterations)
         *iterations = (int)w.h_scal[S_ITER];
     return w.h_scal[S_DONE] == 1.0 ? LPMB_OK : LPMB_ERR_NOTCONVERGED;
@@ -908,7 +932,16 @@ extern "C" int lpmb_spmv_host(lpmb_ctx *c, const double *x, double *y)
     LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
     LPMB_TRY(lpmb_cg_alloc(c));
     LPMB_TRY(lpmb_upload_soa_f64(c, x, c->cg.p, c->dim));
-    LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
+    if (lpmb_brick_active(c)) {
+        double *vr, *vp, *vap, *vx, *vb, *vm;
+        long long P;
+        LPMB_TRY(lpmb_brick_prepare(c));
+        lpmb_brick_vectors(c, &vr, &vp, &vap, &vx, &vb, &vm, &P);
+        LPMB_TRY(lpmb_brick_to_perm(c, c->cg.p, vp));
+        LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, vec_grid(c, (size_t)3 * P)));
+        LPMB_TRY(lpmb_brick_from_perm(c, vap, c->cg.ap));
+    } else
+        LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
     LPMB_TRY(lpmb_download_soa_f64(c, c->cg.ap, y, c->dim));
     return LPMB_OK;
 }
@@ -928,7 +961,35 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
     LPMB_REQUIRE(c && reps > 0 && ms_per_spmv, LPMB_ERR_ARG, "lpmb_spmv_bench: bad argument");
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
-    LPMB_REQUIRE(variant == 0 || variant == 1, LPMB_ERR_ARG, "unknown SpMV variant %d (0 = full SELL, 1 = symmetric upper)", variant);
+    LPMB_REQUIRE(variant >= 0 && variant <= 2, LPMB_ERR_ARG, "unknown SpMV variant %d (0 = full SELL, 1 = symmetric upper, 2 = bricks)", variant);
+    if (variant == 2) {
+        LPMB_REQUIRE(lpmb_brick_active(c), LPMB_ERR_STATE, "brick SpMV not enabled (lpmb_matrix_enable_bricks)");
+        LPMB_TRY(lpmb_cg_alloc(c));
+        double *vr, *vp, *vap, *vx, *vb, *vm;
+        long long P;
+        LPMB_TRY(lpmb_brick_prepare(c));
+        lpmb_brick_vectors(c, &vr, &vp, &vap, &vx, &vb, &vm, &P);
+        fill_sin_kernel<<<vec_grid(c, (size_t)c->dim * c->Np), VEC_THREADS, 0, c->stream>>>(c->cg.p, c->dim, c->N, c->Np);
+        LPMB_LAUNCH_CHECK(c);
+        LPMB_TRY(lpmb_brick_to_perm(c, c->cg.p, vp));
+        const int gg = vec_grid(c, (size_t)3 * P);
+        cudaEvent_t e0, e1;
+        LPMB_CUDA(cudaEventCreate(&e0));
+        LPMB_CUDA(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; i++)
+            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg));
+        LPMB_CUDA(cudaEventRecord(e0, c->stream));
+        for (int i = 0; i < reps; i++)
+            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg));
+        LPMB_CUDA(cudaEventRecord(e1, c->stream));
+        LPMB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        LPMB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_per_spmv = (double)ms / reps;
+        return LPMB_OK;
+    }
     const double saved_variant = param(c, "spmv_symmetric", 0.0);
     c->params["spmv_symmetric"] = (double)variant;
     LPMB_TRY(lpmb_cg_alloc(c));
