@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None = None):
+def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None = None, bricks: bool = True):
     """set up the n^3 block (or this rank's slab of it: owned layers + ghosts, see lpm-c_b200/partition.py) on the
     device: lattice -> O(N) topology -> material -> first FD tangent -> BCs -> predictor -> residual; snapshot"""
     t0 = time.time()
@@ -149,9 +149,11 @@ def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None 
     nr, nf = c.update_rr()
     c.copy_field("xyz_save", "xyz")
     c.copy_field("residual_save", "residual")
+    if bricks:
+        c.enable_bricks(True)   # brick-blocked symmetric SpMV for the CG (lpmb_brick.cu); SC lattice: eligible
     c.synchronize()
     info = {"N": N, "n": n, "setup_s": round(t1 - t0, 2), "fd_assembly_s": round(t2 - t1, 3), "norm_residual0": nr,
-            "norm_reaction0": nf}
+            "norm_reaction0": nf, "bricks": bool(bricks)}
     return c, info
 
 
@@ -179,7 +181,7 @@ def gpu_arm(args):
         return import_module("lpm-c_b200.dist_bench").run(args, lpm, dist, rank, world, local, sys.modules[__name__])
 
     n = args.n
-    c, info = build_workload(lpm, n, local)
+    c, info = build_workload(lpm, n, local, bricks=args.spmv == "bricks")
     N = info["N"]
     hbm_peak, peak_src = peaks()
 
@@ -213,13 +215,19 @@ def gpu_arm(args):
     ms_per_step = ms_total / args.steps
     value = 1000.0 / ms_per_step
     spmv_avg_ms = spmv_ms / max(1, spmv_calls)
-    alg_bytes = c.spmv_bytes()
+    # achieved GB/s is computed from the bytes of the representation that is streamed -- the brick
+    # format stores each symmetric block once -- and the full-format (both triangles) figure is reported beside it
+    full_bytes = c.spmv_bytes()
+    alg_bytes = c.spmv_bytes_bricks() if info["bricks"] else full_bytes
     achieved = alg_bytes / (spmv_avg_ms * 1e-3) / 1e9
+    kernel = ("brick_spmv_kernel + brick_gather_kernel<true> (symmetric CG SpMV + fused mask and p.Ap)" if info["bricks"]
+              else "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap)")
     traffic = None
     try:
         prof = json.load(open(ROOT / "profiles" / "spmv_dram_traffic.json"))
-        if int(prof.get("n", -1)) == n:
-            traffic = prof["dram_bytes_per_launch"]
+        key = "bricks" if info["bricks"] else "full"
+        if int(prof[key].get("n", -1)) == n:
+            traffic = prof[key]["dram_bytes_per_launch"]
     except Exception:
         pass
 
@@ -269,10 +277,12 @@ def gpu_arm(args):
                    "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
                    "l2": "inputs larger than L2 (matrix %.1f GB)" % (c.spmv_bytes_stored() / 1e9),
                    "setup_s": info["setup_s"], "fd_assembly_s": info["fd_assembly_s"], "parallelism": "1 GPU"},
-        "roofline": {"bound": "hbm", "kernel": "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved,
+                     "full_format_equivalent_gbs": full_bytes / (spmv_avg_ms * 1e-3) / 1e9,
+                     "full_format_bytes_per_launch": full_bytes,
                      "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                     "stored_bytes_per_launch": c.spmv_bytes_stored(), "avg_launch_ms": spmv_avg_ms,
+                     "stored_bytes_per_launch": alg_bytes if info["bricks"] else c.spmv_bytes_stored(), "avg_launch_ms": spmv_avg_ms,
                      "launches_timed": spmv_calls, "share_of_step": spmv_ms / ms_total},
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps},
@@ -377,6 +387,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)      # => ~10-15 s of timed CPU work
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spmv", default="bricks", choices=["bricks", "full"],
+                    help="CG SpMV kernel: brick-blocked symmetric (default) or the full-format SELL kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

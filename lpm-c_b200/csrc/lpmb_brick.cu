@@ -78,12 +78,12 @@ void lpmb_brick_touch(lpmb_ctx *c)
 bool lpmb_brick_active(lpmb_ctx *c)
 {
     auto it = g_bricks.find(c);
-    return it != g_bricks.end() && it->second.enabled && c->world == 1;
+    return it != g_bricks.end() && it->second.enabled;
 }
 
 // ---- set-up kernels ------------------------------------------------------------------------------
 // integer lattice coordinates of every particle; max deviation from the lattice (alignment check)
-__global__ void brick_quantize_kernel(int N, int Np, const double *__restrict__ x0, double ox, double oy, double oz, double q,
+__global__ void brick_quantize_kernel(int N, int Np, const double *__restrict__ x0, double ox, double oy, double oz, double q, int nzdom,
                                       int *__restrict__ ic /* [3][Np] */, double *__restrict__ maxdev)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,9 +91,10 @@ __global__ void brick_quantize_kernel(int N, int Np, const double *__restrict__ 
     if (i < N) {
         const double fx = (x0[i] - ox) / q, fy = (x0[(size_t)Np + i] - oy) / q, fz = (x0[(size_t)2 * Np + i] - oz) / q;
         const double rx = rint(fx), ry = rint(fy), rz = rint(fz);
+        const bool inside = rz >= 0.0 && rz < (double)nzdom;  // slab runs: ghost layers beyond the CG halo carry no row
         ic[i] = (int)rx;
         ic[(size_t)Np + i] = (int)ry;
-        ic[(size_t)2 * Np + i] = (int)rz;
+        ic[(size_t)2 * Np + i] = inside ? (int)rz : -1;
         dev = fmax(fabs(fx - rx), fmax(fabs(fy - ry), fabs(fz - rz)));
     }
     // warp max, then one atomicMax on the bit pattern (non-negative doubles order like unsigned integers)
@@ -101,15 +102,6 @@ __global__ void brick_quantize_kernel(int N, int Np, const double *__restrict__ 
         dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
     if ((threadIdx.x & 31) == 0)
         atomicMax(reinterpret_cast<unsigned long long *>(maxdev), (unsigned long long)__double_as_longlong(dev));
-}
-
-__global__ void brick_count_kernel(int N, int Np, const int *__restrict__ ic, int nbx, int nby, int *__restrict__ count)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N)
-        return;
-    const int b = (ic[i] / BE) + nbx * ((ic[(size_t)Np + i] / BE) + nby * (ic[(size_t)2 * Np + i] / BE));
-    atomicAdd(&count[b], 1);
 }
 
 // row of particle i inside its brick = its local lattice position (bricks are addressed geometrically, so the
@@ -121,6 +113,10 @@ __global__ void brick_place_kernel(int N, int Np, const int *__restrict__ ic, in
     if (i >= N)
         return;
     const int ix = ic[i], iy = ic[(size_t)Np + i], iz = ic[(size_t)2 * Np + i];
+    if (iz < 0) {
+        inv[i] = -1;
+        return;
+    }
     const int b = (ix / BE) + nbx * ((iy / BE) + nby * (iz / BE));
     const int lx = ix % BE, ly = iy % BE, lz = iz % BE;
     const int r = lx + BE * (ly + BE * lz);
@@ -138,8 +134,12 @@ __global__ void brick_keys_kernel(int N, int Np, const int *__restrict__ ic, con
     if (i >= N)
         return;
     const long long base = sptr[i >> 5] * 32 + (i & 31);
+    if (ic[(size_t)2 * Np + i] < 0)
+        return;
     for (int k = 0; k < nbc[i]; k++) {
         const int j = col[base + (long long)k * 32];
+        if (ic[(size_t)2 * Np + j] < 0)
+            continue;
         const int dx = ic[j] - ic[i], dy = ic[(size_t)Np + j] - ic[(size_t)Np + i], dz = ic[(size_t)2 * Np + j] - ic[(size_t)2 * Np + i];
         if (dx < -2 || dx > 2 || dy < -2 || dy > 2 || dz < -2 || dz > 2)
             flags[125] = 1;
@@ -156,12 +156,16 @@ __global__ void brick_fill_kernel(int N, int Np, const int *__restrict__ ic, con
     if (i >= N)
         return;
     const long long prow = inv[i];
+    if (prow < 0)
+        return;
     const long long b = prow / BR;
     const int r = (int)(prow % BR);
     const long long kbase = sptr[i >> 5];
     const int lane = i & 31;
     for (int k = 0; k < nbc[i]; k++) {
         const int j = col[(kbase + k) * 32 + lane];
+        if (inv[j] < 0)
+            continue;  // neighbour outside the slab's CG halo
         const int dx = ic[j] - ic[i], dy = ic[(size_t)Np + j] - ic[(size_t)Np + i], dz = ic[(size_t)2 * Np + j] - ic[(size_t)2 * Np + i];
         const int u = c_key2cls[(dx + 2) + 5 * (dy + 2) + 25 * (dz + 2)];
         if (u < 0)
@@ -191,7 +195,24 @@ __global__ void brick_from_perm_kernel(int N, int Np, long long P, const int *__
     if (t >= 3LL * N)
         return;
     const int comp = (int)(t / N), i = (int)(t % N);
-    dst[(size_t)comp * Np + i] = src[(size_t)comp * P + inv[i]];
+    dst[(size_t)comp * Np + i] = inv[i] >= 0 ? src[(size_t)comp * P + inv[i]] : 0.0;
+}
+
+// halo rows only: [i0, i0+count) of the original numbering, permuted <-> original (slab runs)
+__global__ void brick_range_kernel(int i0, int count, int Np, long long P, const int *__restrict__ inv, double *__restrict__ perm_vec,
+                                   double *__restrict__ orig_vec, int to_perm)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * count)
+        return;
+    const int comp = t / count, i = i0 + t % count;
+    const long long prow = inv[i];
+    if (to_perm) {
+        if (prow >= 0)
+            perm_vec[(size_t)comp * P + prow] = orig_vec[(size_t)comp * Np + i];
+    } else {
+        orig_vec[(size_t)comp * Np + i] = prow >= 0 ? perm_vec[(size_t)comp * P + prow] : 0.0;
+    }
 }
 
 // ---- the SpMV ------------------------------------------------------------------------------------
@@ -419,13 +440,13 @@ static int brick_upload_tables(const BrickMatrix &B)
 static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
 {
     LPMB_REQUIRE(c->dim == 3 && c->lattice == LPMB_LATTICE_SC, LPMB_ERR_UNSUPPORTED, "brick SpMV: simple-cubic 3-D lattices only");
-    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "brick SpMV: single GPU only in this version");
     LPMB_REQUIRE(c->params.count("radius") && c->fields.count("xyz_initial") && c->K.pattern_ready, LPMB_ERR_STATE,
                  "brick SpMV needs radius, xyz_initial and the connectivity");
     const int N = c->N, Np = c->Np;
     const double *x0 = fptr<double>(c, "xyz_initial");
     B.q = 2.0 * param(c, "radius");
-    // lattice origin = component-wise minimum
+    // lattice origin = component-wise minimum.  Slab runs (world > 1): rows exist only for the owned z-layers plus the
+    // CG halo (2 layers); the outer, position-only ghost layers are left out.
     std::vector<double> hx((size_t)3 * Np);
     LPMB_CUDA(cudaMemcpy(hx.data(), x0, hx.size() * 8, cudaMemcpyDeviceToHost));
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -434,6 +455,20 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
             lo[k] = std::min(lo[k], hx[(size_t)k * Np + i]);
             hi[k] = std::max(hi[k], hx[(size_t)k * Np + i]);
         }
+    if (c->world > 1) {
+        const int own0 = lpmb_own0(c), own1 = lpmb_own1(c);
+        LPMB_REQUIRE(own1 > own0, LPMB_ERR_STATE, "brick SpMV: empty slab");
+        double zl = 1e300, zh = -1e300;
+        for (int i = own0; i < own1; i++) {
+            zl = std::min(zl, hx[(size_t)2 * Np + i]);
+            zh = std::max(zh, hx[(size_t)2 * Np + i]);
+        }
+        lo[2] = std::max(lo[2], zl - 2.0 * B.q * (1.0 + 1e-9));
+        hi[2] = std::min(hi[2], zh + 2.0 * B.q * (1.0 + 1e-9));
+        // snap to the lattice planes actually present
+        lo[2] = zl - B.q * std::floor((zl - lo[2]) / B.q + 1e-6);
+        hi[2] = zh + B.q * std::floor((hi[2] - zh) / B.q + 1e-6);
+    }
     hx.clear();
     hx.shrink_to_fit();
     B.ox = lo[0];
@@ -451,7 +486,7 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
     LPMB_CUDA(cudaMalloc(&ic, (size_t)3 * Np * sizeof(int)));
     LPMB_CUDA(cudaMalloc(&d_dev, sizeof(double)));
     LPMB_CUDA(cudaMemset(d_dev, 0, sizeof(double)));
-    brick_quantize_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, x0, B.ox, B.oy, B.oz, B.q, ic, d_dev);
+    brick_quantize_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, x0, B.ox, B.oy, B.oz, B.q, nz, ic, d_dev);
     LPMB_LAUNCH_CHECK(c);
     double dev = 0.0;
     LPMB_CUDA(cudaMemcpyAsync(&dev, d_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -472,6 +507,20 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
     LPMB_LAUNCH_CHECK(c);
     brick_keys_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, ic, c->K.sptr, c->K.col, c->K.nbc, d_flags);
     LPMB_LAUNCH_CHECK(c);
+    if (c->world > 1) {
+        // every owned particle and every CG-halo particle must have a row (holds for z-slabs made of whole layers)
+        const int i0 = lpmb_own0(c) - (c->rank > 0 ? c->narrow_recv_lo : 0), i1 = lpmb_own1(c) + (c->rank < c->world - 1 ? c->narrow_recv_hi : 0);
+        std::vector<int> hinv((size_t)(i1 - i0));
+        LPMB_CUDA(cudaMemcpyAsync(hinv.data(), B.inv + i0, hinv.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int v : hinv)
+            if (v < 0) {
+                cudaFree(ic);
+                cudaFree(d_flags);
+                lpmb_set_error("brick SpMV: the slab is not a stack of whole z-layers (a halo particle lies outside owned +- 2 layers)");
+                return LPMB_ERR_UNSUPPORTED;
+            }
+    }
     int flags[128];
     LPMB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
@@ -602,6 +651,32 @@ int lpmb_brick_from_perm(lpmb_ctx *c, const double *src, double *dst)
     BrickMatrix &B = g_bricks[c];
     brick_from_perm_kernel<<<lpmb_blocks(3LL * c->N, 256), 256, 0, c->stream>>>(c->N, c->Np, B.P, B.inv, src, dst);
     LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+// slab runs: halo exchange of a brick-ordered vector, staged through the context's original-order CG vector
+int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec)
+{
+    if (c->world <= 1)
+        return LPMB_OK;
+    BrickMatrix &B = g_bricks[c];
+    const int own0 = lpmb_own0(c), own1 = lpmb_own1(c);
+    auto range = [&](int i0, int count, int to_perm) -> int {
+        if (count <= 0)
+            return LPMB_OK;
+        brick_range_kernel<<<lpmb_blocks(3LL * count, 256), 256, 0, c->stream>>>(i0, count, c->Np, B.P, B.inv, perm_vec, c->cg.p, to_perm);
+        LPMB_LAUNCH_CHECK(c);
+        return LPMB_OK;
+    };
+    if (c->rank > 0)
+        LPMB_TRY(range(own0, c->narrow_send_lo, 0));
+    if (c->rank < c->world - 1)
+        LPMB_TRY(range(own1 - c->narrow_send_hi, c->narrow_send_hi, 0));
+    LPMB_TRY(lpmb_dist_exchange(c, c->cg.p, 3, false));
+    if (c->rank > 0)
+        LPMB_TRY(range(own0 - c->narrow_recv_lo, c->narrow_recv_lo, 1));
+    if (c->rank < c->world - 1)
+        LPMB_TRY(range(own1, c->narrow_recv_hi, 1));
     return LPMB_OK;
 }
 

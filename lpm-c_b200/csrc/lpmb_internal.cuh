@@ -201,6 +201,7 @@ int lpmb_brick_to_perm(lpmb_ctx *c, const double *src, double *dst);
 int lpmb_brick_from_perm(lpmb_ctx *c, const double *src, double *dst);
 int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid);
 long long lpmb_brick_bytes(lpmb_ctx *c);
+int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec);
 
 // solver-side entry points used across TUs
 int lpmb_cg_alloc(lpmb_ctx *c);

@@ -777,7 +777,7 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
         const int issued0 = issued;
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
             if (dist)
-                LPMB_TRY(lpmb_dist_exchange(c, vp, c->dim, false));
+                LPMB_TRY(brick ? lpmb_brick_exchange(c, vp) : lpmb_dist_exchange(c, vp, c->dim, false));
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b], c->stream));
             if (brick)

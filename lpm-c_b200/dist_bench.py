@@ -20,7 +20,7 @@ def run(args, lpm, dist, rank, world, local, bench):
     # rank 0 creates the NCCL id; torch.distributed ships it
     uid = [lpm.Context.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0])
+    c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0], bricks=args.spmv == "bricks")
     hbm_peak, peak_src = bench.peaks()
 
     def barrier():
@@ -56,7 +56,10 @@ def run(args, lpm, dist, rank, world, local, bench):
     spmv_avg_ms = spmv_ms / max(1, spmv_calls)
     # per-rank SpMV bytes: only the slices holding owned rows are streamed
     own_frac = (slab.own1 - slab.own0) / slab.n_local
-    alg_bytes_rank = int(c.spmv_bytes() * own_frac)
+    # (brick kernel: every brick of owned +- 2 layers is streamed, lpmb_spmv_bytes_bricks counts exactly that)
+    alg_bytes_rank = c.spmv_bytes_bricks() if info["bricks"] else int(c.spmv_bytes() * own_frac)
+    kernel = ("brick_spmv_kernel + brick_gather_kernel<true> (symmetric CG SpMV + fused mask and p.Ap)" if info["bricks"]
+              else "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap)")
     achieved = alg_bytes_rank / (spmv_avg_ms * 1e-3) / 1e9
     stats = torch.tensor([spmv_avg_ms, achieved, float(launches)], dtype=torch.float64, device=f"cuda:{local}")
     gathered = [torch.zeros_like(stats) for _ in range(world)]
@@ -118,7 +121,7 @@ def run(args, lpm, dist, rank, world, local, bench):
                        "l2": "inputs larger than L2 (per-rank matrix %.1f GB)" % (c.spmv_bytes_stored() * own_frac / 1e9),
                        "parallelism": f"{world} z-slabs (owned layers per rank {slab.z1 - slab.z0}, 4 ghost layers), NCCL halo exchange "
                                       "of p (2 layers) + all-reduce of 2 scalars per CG iteration"},
-            "roofline": {"bound": "hbm", "kernel": "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap), slowest rank", "achieved": worst["spmv_GBs"],
+            "roofline": {"bound": "hbm", "kernel": kernel + ", slowest rank", "achieved": worst["spmv_GBs"],
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": worst["spmv_GBs"] / hbm_peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes_rank, "avg_launch_ms": worst["spmv_ms"], "per_rank": per_rank,
                          "share_of_step": float(spmv_ms / ms_local)},

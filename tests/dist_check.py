@@ -48,7 +48,7 @@ def main():
     c.close()
     ok = True
     if rank == 0:
-        c1, info1 = bench.build_workload(lpm, n, local)
+        c1, info1 = bench.build_workload(lpm, n, local, bricks=False)   # full-format SELL kernel as the cross-check
         assert abs(info1["norm_residual0"] - info["norm_residual0"]) <= 1e-12 * info1["norm_residual0"], (info1, info)
         its1, nrs1 = [], []
         for _ in range(2):
