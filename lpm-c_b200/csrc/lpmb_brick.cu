@@ -368,37 +368,32 @@ brick_gather_kernel(long long P, int nbx, int nby, int nbz, const double *__rest
         const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((long long)nbx * nby));
         const int lx = r & 7, ly = (r >> 3) & 7, lz = r >> 6;
         double v0 = ypart[prow], v1 = ypart[P + prow], v2 = ypart[2 * P + prow];
-        // source bricks in a fixed order: dbz in {-1,0}, dby in {-1,0,+1}, dbx in {-1,0,+1}, own brick excluded.
-        // The brick at offset db sees this row in its extended box iff the row lies within 2 sites of that side.
-        for (int dbz = -1; dbz <= 0; dbz++) {
-            if (dbz == -1 && lz >= 2)
-                continue;
-            const int sz = bz + dbz;
-            if (sz < 0)
-                continue;
-            for (int dby = -1; dby <= 1; dby++) {
-                if ((dby == -1 && ly >= 2) || (dby == 1 && ly < BE - 2))
-                    continue;
-                const int sy = by + dby;
-                if (sy < 0 || sy >= nby)
-                    continue;
-                for (int dbx = -1; dbx <= 1; dbx++) {
-                    if ((dbx == -1 && lx >= 2) || (dbx == 1 && lx < BE - 2))
-                        continue;
-                    if (dbx == 0 && dby == 0 && dbz == 0)
-                        continue;
-                    const int sx = bx + dbx;
-                    if (sx < 0 || sx >= nbx)
-                        continue;
-                    const int ex = lx - BE * dbx + 2, ey = ly - BE * dby + 2, ez = lz - BE * dbz;
-                    const long long sb = sx + (long long)nbx * (sy + (long long)nby * sz);
-                    const int s = ex + EXX * (ey + EXY * ez);
-                    const double *sg = stage + sb * 3 * NSLOT;
-                    v0 += sg[s];
-                    v1 += sg[NSLOT + s];
-                    v2 += sg[2 * NSLOT + s];
-                }
-            }
+        // Source bricks: a row within 2 sites of a brick face also sits in the extended box of the brick across that
+        // face (z: only the brick below, because pairs are owned by their lower end point).  With one candidate
+        // offset per axis (fx, fy in {-1,0,+1}, fz in {-1,0}) the sources are the 7 non-empty combinations; all
+        // loads are issued unconditionally from clamped addresses (independent, no divergent latency chains) and
+        // added in a fixed order.
+        const int fx = lx < 2 ? -1 : (lx >= BE - 2 ? 1 : 0), fy = ly < 2 ? -1 : (ly >= BE - 2 ? 1 : 0), fz = lz < 2 ? -1 : 0;
+        const bool okx = fx != 0 && bx + fx >= 0 && bx + fx < nbx, oky = fy != 0 && by + fy >= 0 && by + fy < nby, okz = fz != 0 && bz + fz >= 0;
+        double c0[7], c1[7], c2[7];
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+            const bool ux = k & 1, uy = k & 2, uz = k & 4;
+            const bool ok = (!ux || okx) && (!uy || oky) && (!uz || okz);
+            const int dbx = ux ? fx : 0, dby = uy ? fy : 0, dbz = uz ? fz : 0;
+            const long long sb = ok ? (bx + dbx) + (long long)nbx * ((by + dby) + (long long)nby * (bz + dbz)) : b;
+            const int sl = ok ? (lx - BE * dbx + 2) + EXX * ((ly - BE * dby + 2) + EXY * (lz - BE * dbz)) : 0;
+            const double *sg = stage + sb * 3 * NSLOT + sl;
+            const double w = ok ? 1.0 : 0.0;
+            c0[k - 1] = w * sg[0];
+            c1[k - 1] = w * sg[NSLOT];
+            c2[k - 1] = w * sg[2 * NSLOT];
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            v0 += c0[k];
+            v1 += c1[k];
+            v2 += c2[k];
         }
         if (mask) {
             v0 *= mask[prow];
