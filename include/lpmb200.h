@@ -206,6 +206,12 @@ int lpmb_dist_set_slab(lpmb_ctx *ctx, int own0, int own1, int narrow_recv_lo, in
                        int narrow_send_hi, int wide_send_lo, int wide_send_hi);
 /* halo exchange of one named fp64 field (wide != 0: all ghosts, else the narrow CG halo) */
 int lpmb_dist_exchange_field(lpmb_ctx *ctx, const char *name, int wide);
+/* How the per-CG-iteration traffic of a slab run travels: 0 = single GPU, 1 = NCCL only, 2 = scalar all-reduces
+ * through CUDA-IPC mapped peer memory over NVLink (halo through NCCL), 3 = scalars and the halo push of the search
+ * direction through peer memory (brick SpMV enabled).  lpmb_dist_init maps the peers unless the environment
+ * variable LPMB_NO_PEER is set or a rank cannot map another (then all ranks stay on NCCL together); param
+ * "peer_comm" = 0 switches the fast path off at run time. */
+int lpmb_dist_mode(lpmb_ctx *ctx);
 
 #ifdef __cplusplus
 }

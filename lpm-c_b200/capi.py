@@ -44,6 +44,7 @@ lib.lpmb_spmv_bytes_stored.argtypes = [c_vp]
 lib.lpmb_spmv_bytes_bricks.restype = C.c_longlong
 lib.lpmb_spmv_bytes_bricks.argtypes = [c_vp]
 lib.lpmb_matrix_enable_bricks.argtypes = [c_vp, C.c_int]
+lib.lpmb_dist_mode.argtypes = [c_vp]
 lib.lpmb_destroy.restype = None
 lib.lpmb_destroy.argtypes = [c_vp]
 lib.lpmb_create.argtypes = [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -237,6 +238,10 @@ class Context:
 
     def spmv_bytes_stored(self) -> int:
         return int(lib.lpmb_spmv_bytes_stored(self._h))
+
+    def dist_mode(self) -> int:
+        """0 single GPU, 1 NCCL only, 2 peer-memory scalars, 3 peer-memory scalars + halo push (include/lpmb200.h)"""
+        return int(lib.lpmb_dist_mode(self._h))
 
     def enable_bricks(self, on: bool = True):
         """brick-blocked symmetric SpMV for the CG (include/lpmb200.h); raises if the lattice is not eligible"""

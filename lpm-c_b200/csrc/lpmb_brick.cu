@@ -63,6 +63,7 @@ void lpmb_brick_release(lpmb_ctx *c)
     if (it == g_bricks.end())
         return;
     BrickMatrix &B = it->second;
+    lpmb_peer_halo_release(c);
     cudaFree(B.perm); cudaFree(B.inv); cudaFree(B.ic); cudaFree(B.bval); cudaFree(B.stage); cudaFree(B.ypart);
     cudaFree(B.r); cudaFree(B.p); cudaFree(B.ap); cudaFree(B.x); cudaFree(B.b); cudaFree(B.mask);
     g_bricks.erase(it);
@@ -262,12 +263,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 
 __global__ void __launch_bounds__(BR, 1)
 brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P, const double *__restrict__ bval, const double *__restrict__ x,
-                  double *__restrict__ ypart, double *__restrict__ stage, const double *__restrict__ scal)
+                  double *__restrict__ ypart, double *__restrict__ stage, const double *__restrict__ scal, PeerWait halo_wait)
 {
     extern __shared__ __align__(128) unsigned char brick_smem_raw[];
     BrickSmem &S = *reinterpret_cast<BrickSmem *>(brick_smem_raw);
     if (scal && scal[7] != 0.0)  // S_DONE
         return;
+    lpmb_peer_wait(halo_wait);  // slab runs: the neighbours' pushes of the halo rows of x have landed (lpmb_peer.cu)
     const int r = threadIdx.x;
     const int lx = r & 7, ly = (r >> 3) & 7, lz = r >> 6;
     const int myslot = (lx + 2) + EXX * ((ly + 2) + EXY * lz);
@@ -594,6 +596,9 @@ extern "C" int lpmb_matrix_enable_bricks(lpmb_ctx *c, int on)
         }
     }
     B.enabled = true;
+    // slab runs: let the neighbours push their boundary rows of the search direction straight into B.p (collective)
+    if (c->world > 1)
+        LPMB_TRY(lpmb_peer_halo_setup(c, B.p, B.P, B.inv));
     return LPMB_OK;
 }
 
@@ -676,7 +681,8 @@ int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec)
 }
 
 // y = [mask .*] K x in the permuted space (+ p.Ap partials into `partials`, one per block of the gather grid)
-int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid)
+int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid,
+                    const PeerWait &halo_wait)
 {
     BrickMatrix &B = g_bricks[c];
     static bool attr_set = false;
@@ -686,7 +692,7 @@ int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const dou
     }
     const int grid = B.nbricks < c->sm_count ? B.nbricks : c->sm_count;
     brick_spmv_kernel<<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, x, B.ypart, B.stage,
-                                                                  dot ? scal : nullptr);
+                                                                  dot ? scal : nullptr, halo_wait);
     LPMB_LAUNCH_CHECK(c);
     if (dot)
         brick_gather_kernel<true><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, partials, scal);

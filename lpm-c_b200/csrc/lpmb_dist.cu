@@ -25,6 +25,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -49,6 +50,7 @@ static int load_nccl()
     LPMB_SYM(CommInitRank, "ncclCommInitRank");
     LPMB_SYM(CommDestroy, "ncclCommDestroy");
     LPMB_SYM(AllReduce, "ncclAllReduce");
+    LPMB_SYM(AllGather, "ncclAllGather");
     LPMB_SYM(Send, "ncclSend");
     LPMB_SYM(Recv, "ncclRecv");
     LPMB_SYM(GroupStart, "ncclGroupStart");
@@ -89,11 +91,46 @@ extern "C" int lpmb_dist_init(lpmb_ctx *c, const void *id128, int rank, int worl
     c->nccl = comm;
     c->rank = rank;
     c->world = world;
+    // NVLink peer-memory fast path for the per-CG-iteration traffic (lpmb_peer.cu); NCCL stays for the rest
+    if (world > 1 && !getenv("LPMB_NO_PEER"))
+        LPMB_TRY(lpmb_peer_init(c));
+    return LPMB_OK;
+}
+
+// byte all-gather / neighbour int exchange used by the peer set-up
+int lpmb_dist_allgather_bytes(lpmb_ctx *c, const void *d_send, void *d_recv, size_t bytes_per_rank)
+{
+    LPMB_REQUIRE(c->nccl, LPMB_ERR_STATE, "lpmb_dist_init not called");
+    LPMB_NCCL(g_nccl.AllGather(d_send, d_recv, bytes_per_rank, ncclInt8, reinterpret_cast<ncclComm_t>(c->nccl), c->stream));
+    return LPMB_OK;
+}
+
+// send `to_lo` ints to rank-1 and `to_hi` ints to rank+1, receive `from_lo` / `from_hi` ints from them
+int lpmb_dist_neighbor_ints(lpmb_ctx *c, const int *to_lo, int n_to_lo, const int *to_hi, int n_to_hi, int *from_lo, int n_from_lo, int *from_hi,
+                            int n_from_hi)
+{
+    LPMB_REQUIRE(c->nccl, LPMB_ERR_STATE, "lpmb_dist_init not called");
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->nccl);
+    LPMB_NCCL(g_nccl.GroupStart());
+    if (c->rank > 0) {
+        if (n_to_lo > 0)
+            LPMB_NCCL(g_nccl.Send(to_lo, n_to_lo, ncclInt32, c->rank - 1, comm, c->stream));
+        if (n_from_lo > 0)
+            LPMB_NCCL(g_nccl.Recv(from_lo, n_from_lo, ncclInt32, c->rank - 1, comm, c->stream));
+    }
+    if (c->rank < c->world - 1) {
+        if (n_to_hi > 0)
+            LPMB_NCCL(g_nccl.Send(to_hi, n_to_hi, ncclInt32, c->rank + 1, comm, c->stream));
+        if (n_from_hi > 0)
+            LPMB_NCCL(g_nccl.Recv(from_hi, n_from_hi, ncclInt32, c->rank + 1, comm, c->stream));
+    }
+    LPMB_NCCL(g_nccl.GroupEnd());
     return LPMB_OK;
 }
 
 void lpmb_dist_release(lpmb_ctx *c)
 {
+    lpmb_peer_release(c);
     if (c->nccl && g_nccl.CommDestroy)
         g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(c->nccl));
     c->nccl = nullptr;

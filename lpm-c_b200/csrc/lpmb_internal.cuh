@@ -185,6 +185,54 @@ int lpmb_dist_exchange(lpmb_ctx *c, double *v, int comps, bool wide);   // halo 
 int lpmb_dist_allreduce_sum(lpmb_ctx *c, double *d_buf, int count);     // in-stream, in place
 void lpmb_dist_release(lpmb_ctx *c);
 
+int lpmb_dist_allgather_bytes(lpmb_ctx *c, const void *d_send, void *d_recv, size_t bytes_per_rank);
+int lpmb_dist_neighbor_ints(lpmb_ctx *c, const int *to_lo, int n_to_lo, const int *to_hi, int n_to_hi, int *from_lo, int n_from_lo, int *from_hi,
+                            int n_from_hi);
+
+// NVLink peer-memory fast path (lpmb_peer.cu): CUDA-IPC mapped buffers of the other ranks on the same box.
+//  * scalar all-reduce: every rank stores its partial + a sequence number into every rank's slot array; the consuming
+//    kernel spins (acquire, system scope) until all `world` slots carry the sequence, then sums them in rank order
+//  * halo push (brick-ordered CG vectors): boundary rows are written straight into the neighbour's vector, a flag
+//    follows; the neighbour's SpMV kernel waits for the flag
+#define LPMB_PEER_MAXW 16
+struct PeerWait {              // passed by value to consumer kernels; n == 0 -> nothing to wait for
+    const unsigned long long *seqs = nullptr;
+    unsigned long long seq = 0;
+    int n = 0;
+};
+int lpmb_peer_init(lpmb_ctx *c);
+void lpmb_peer_release(lpmb_ctx *c);
+bool lpmb_peer_ready(lpmb_ctx *c);
+// reduce `nparts` per-block partials to this rank's scalar, publish it to all ranks; *vals (world doubles, local
+// memory) and *wait describe what the consumer kernel has to do.  Skipped on the device when scal[S_DONE] != 0.
+int lpmb_peer_allreduce_publish(lpmb_ctx *c, const double *partials, int nparts, const double *scal, const double **vals, PeerWait *wait);
+int lpmb_peer_halo_setup(lpmb_ctx *c, double *perm_vec, long long P, const int *inv);
+bool lpmb_peer_halo_ready(lpmb_ctx *c);
+int lpmb_peer_halo_push(lpmb_ctx *c, const double *scal, PeerWait *wait);
+void lpmb_peer_halo_release(lpmb_ctx *c);
+
+__device__ __forceinline__ unsigned long long lpmb_ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lpmb_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// thread 0 of the block waits for the peers, then the block proceeds
+__device__ __forceinline__ void lpmb_peer_wait(const PeerWait &w)
+{
+    if (w.n > 0) {
+        if (threadIdx.x == 0)
+            for (int r = 0; r < w.n; r++)
+                while (lpmb_ld_acquire_sys(w.seqs + r) < w.seq) {
+                }
+        __syncthreads();
+    }
+}
+
 // symmetric SpMV (lpmb_symspmv.cu)
 int lpmb_sym_build(lpmb_ctx *c);
 void lpmb_sym_release(lpmb_ctx *c);
@@ -199,7 +247,9 @@ int lpmb_brick_prepare(lpmb_ctx *c);
 void lpmb_brick_vectors(lpmb_ctx *c, double **r, double **p, double **ap, double **x, double **b, double **mask, long long *P);
 int lpmb_brick_to_perm(lpmb_ctx *c, const double *src, double *dst);
 int lpmb_brick_from_perm(lpmb_ctx *c, const double *src, double *dst);
-int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid);
+struct PeerWait;
+int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid,
+                    const PeerWait &halo_wait);
 long long lpmb_brick_bytes(lpmb_ctx *c);
 int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec);
 

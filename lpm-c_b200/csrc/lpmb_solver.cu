@@ -588,9 +588,10 @@ cg_init_kernel(const double *__restrict__ b, const double *__restrict__ mask, do
 
 // rr0 = sum partials; threshold = rel*rr0 + abs (MKL: dpar[3] = dpar[0]*dpar[2] + dpar[1], squared norms)
 __global__ void __launch_bounds__(VEC_THREADS)
-cg_init_scalars_kernel(const double *__restrict__ partials, int nparts, double rel, double abs_tol, double *__restrict__ scal)
+cg_init_scalars_kernel(const double *__restrict__ partials, int nparts, double rel, double abs_tol, double *__restrict__ scal, PeerWait pw)
 {
     __shared__ double red[VEC_THREADS / 32];
+    lpmb_peer_wait(pw);  // slab runs on the peer-memory path: `partials` are the ranks' scalars (lpmb_peer.cu)
     const double rr = reduce_partials<VEC_THREADS>(partials, nparts, red);
     if (threadIdx.x == 0) {
         scal[S_RR0] = rr;
@@ -607,11 +608,12 @@ cg_init_scalars_kernel(const double *__restrict__ partials, int nparts, double r
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_update_kernel(const double *__restrict__ p, const double *__restrict__ ap, double *__restrict__ x, double *__restrict__ r, size_t n,
                  const double *__restrict__ partials_pap, int nparts_pap, double *__restrict__ partials_rr, double *__restrict__ scal,
-                 int parity)
+                 int parity, PeerWait pw)
 {
     __shared__ double red[VEC_THREADS / 32];
     if (scal[S_DONE] != 0.0)
         return;
+    lpmb_peer_wait(pw);
     const double pap = reduce_partials<VEC_THREADS>(partials_pap, nparts_pap, red);
     const double alpha = scal[S_RR0 + parity] / pap;
     double s = 0.0;
@@ -635,11 +637,12 @@ cg_update_kernel(const double *__restrict__ p, const double *__restrict__ ap, do
 // beta = rr'/rr ; p = r + beta p
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_direction_kernel(const double *__restrict__ r, double *__restrict__ p, size_t n, const double *__restrict__ partials_rr, int nparts,
-                    double *__restrict__ scal, int parity, int maxit)
+                    double *__restrict__ scal, int parity, int maxit, PeerWait pw, const double *__restrict__ skip_mask)
 {
     __shared__ double red[VEC_THREADS / 32];
     if (scal[S_DONE] != 0.0)
         return;
+    lpmb_peer_wait(pw);
     const double rr_new = reduce_partials<VEC_THREADS>(partials_rr, nparts, red);
     const double rr_old = scal[S_RR0 + parity];
     const double iter = scal[S_ITER] + 1.0;
@@ -651,8 +654,11 @@ cg_direction_kernel(const double *__restrict__ r, double *__restrict__ p, size_t
     // *other* parity slot and keep S_ITER/S_DONE updates for a trailing single-block kernel)
     if (!stop) {
         const double beta = rr_new / rr_old;
+        // skip_mask (peer halo push only): masked rows keep p -- constrained DoFs stay 0 either way, and the ghost rows
+        // belong to the neighbour, whose push may already be landing (lpmb_peer.cu)
         for (size_t i = (size_t)blockIdx.x * VEC_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * VEC_THREADS)
-            p[i] = fma(beta, p[i], r[i]);
+            if (!skip_mask || skip_mask[i] != 0.0)
+                p[i] = fma(beta, p[i], r[i]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         scal[S_RR0 + (parity ^ 1)] = rr_new;
@@ -757,13 +763,22 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     const int vg = vec_grid(c, n), sg = brick ? vg : spmv_grid(c);
     cg_init_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(d_b, m, vr, vp, vx, n, part_a);
     LPMB_LAUNCH_CHECK(c);
-    if (dist) {
+    // slab runs: scalars through NVLink peer memory when the ranks could map each other (lpmb_peer.cu), else NCCL
+    const bool peer = dist && lpmb_peer_ready(c);
+    const bool peer_halo = peer && brick && lpmb_peer_halo_ready(c);
+    const PeerWait nowait;
+    if (peer) {
+        const double *vals;
+        PeerWait pw;
+        LPMB_TRY(lpmb_peer_allreduce_publish(c, part_a, vg, nullptr, &vals, &pw));
+        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(vals, c->world, rel, abs_tol, w.scal, pw);
+    } else if (dist) {
         reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, red_a, nullptr);
         LPMB_LAUNCH_CHECK(c);
         LPMB_TRY(lpmb_dist_allreduce_sum(c, red_a, 1));
-        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(red_a, 1, rel, abs_tol, w.scal);
+        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(red_a, 1, rel, abs_tol, w.scal, nowait);
     } else {
-        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, rel, abs_tol, w.scal);
+        cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, rel, abs_tol, w.scal, nowait);
     }
     LPMB_LAUNCH_CHECK(c);
     const int batch = 16;
@@ -776,31 +791,43 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     for (;;) {
         const int issued0 = issued;
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
-            if (dist)
+            PeerWait hw;  // what this rank's SpMV has to wait for (peer halo push only)
+            if (peer_halo)
+                LPMB_TRY(lpmb_peer_halo_push(c, w.scal, &hw));
+            else if (dist)
                 LPMB_TRY(brick ? lpmb_brick_exchange(c, vp) : lpmb_dist_exchange(c, vp, c->dim, false));
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b], c->stream));
             if (brick)
-                LPMB_TRY(lpmb_brick_spmv(c, vp, vap, true, m, part_a, w.scal, sg));
+                LPMB_TRY(lpmb_brick_spmv(c, vp, vap, true, m, part_a, w.scal, sg, hw));
             else
                 LPMB_TRY(launch_spmv(c, vp, vap, true, use_mask));  // partials -> part_a (w.partials)
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b + 1], c->stream));
-            if (dist) {
+            if (peer) {
+                const double *vals;
+                PeerWait pw;
+                LPMB_TRY(lpmb_peer_allreduce_publish(c, part_a, sg, w.scal, &vals, &pw));
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, vals, c->world, part_b, w.scal, parity, pw);
+                LPMB_LAUNCH_CHECK(c);
+                LPMB_TRY(lpmb_peer_allreduce_publish(c, part_b, vg, w.scal, &vals, &pw));
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, vals, c->world, w.scal, parity, maxit, pw, peer_halo ? m : nullptr);
+                LPMB_LAUNCH_CHECK(c);
+            } else if (dist) {
                 reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, sg, red_a, w.scal);
                 LPMB_LAUNCH_CHECK(c);
                 LPMB_TRY(lpmb_dist_allreduce_sum(c, red_a, 1));
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, red_a, 1, part_b, w.scal, parity);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, red_a, 1, part_b, w.scal, parity, nowait);
                 LPMB_LAUNCH_CHECK(c);
                 reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_b, vg, red_b, w.scal);
                 LPMB_LAUNCH_CHECK(c);
                 LPMB_TRY(lpmb_dist_allreduce_sum(c, red_b, 1));
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, red_b, 1, w.scal, parity, maxit);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, red_b, 1, w.scal, parity, maxit, nowait, nullptr);
                 LPMB_LAUNCH_CHECK(c);
             } else {
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, part_a, sg, part_b, w.scal, parity);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, part_a, sg, part_b, w.scal, parity, nowait);
                 LPMB_LAUNCH_CHECK(c);
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, part_b, vg, w.scal, parity, maxit);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, part_b, vg, w.scal, parity, maxit, nowait, nullptr);
                 LPMB_LAUNCH_CHECK(c);
             }
             cg_bookkeep_kernel<<<1, 1, 0, c->stream>>>(w.scal, parity, maxit);
@@ -938,7 +965,7 @@ extern "C" int lpmb_spmv_host(lpmb_ctx *c, const double *x, double *y)
         LPMB_TRY(lpmb_brick_prepare(c));
         lpmb_brick_vectors(c, &vr, &vp, &vap, &vx, &vb, &vm, &P);
         LPMB_TRY(lpmb_brick_to_perm(c, c->cg.p, vp));
-        LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, vec_grid(c, (size_t)3 * P)));
+        LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, vec_grid(c, (size_t)3 * P), PeerWait()));
         LPMB_TRY(lpmb_brick_from_perm(c, vap, c->cg.ap));
     } else
         LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
@@ -977,10 +1004,10 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
         LPMB_CUDA(cudaEventCreate(&e0));
         LPMB_CUDA(cudaEventCreate(&e1));
         for (int i = 0; i < 3; i++)
-            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg));
+            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg, PeerWait()));
         LPMB_CUDA(cudaEventRecord(e0, c->stream));
         for (int i = 0; i < reps; i++)
-            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg));
+            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg, PeerWait()));
         LPMB_CUDA(cudaEventRecord(e1, c->stream));
         LPMB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;

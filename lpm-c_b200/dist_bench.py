@@ -22,6 +22,7 @@ def run(args, lpm, dist, rank, world, local, bench):
     dist.broadcast_object_list(uid, src=0)
     c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0], bricks=args.spmv == "bricks")
     hbm_peak, peak_src = bench.peaks()
+    comm_mode = c.dist_mode()
 
     def barrier():
         c.synchronize()
@@ -119,8 +120,10 @@ def run(args, lpm, dist, rank, world, local, bench):
                        "lattice_n": n, "particles": Ng, "dof": 3 * Ng, "cg_iterations_per_step": iters,
                        "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
                        "l2": "inputs larger than L2 (per-rank matrix %.1f GB)" % (c.spmv_bytes_stored() * own_frac / 1e9),
-                       "parallelism": f"{world} z-slabs (owned layers per rank {slab.z1 - slab.z0}, 4 ghost layers), NCCL halo exchange "
-                                      "of p (2 layers) + all-reduce of 2 scalars per CG iteration"},
+                       "parallelism": f"{world} z-slabs (owned layers per rank {slab.z1 - slab.z0}, 4 ghost layers); per CG iteration a halo "
+                                      "exchange of p (2 layers) + all-reduce of 2 scalars",
+                       "comm": {1: "NCCL", 2: "scalars: NVLink peer memory (CUDA IPC); halo: NCCL",
+                                3: "scalars and halo push: NVLink peer memory (CUDA IPC); NCCL only outside the CG loop"}[comm_mode]},
             "roofline": {"bound": "hbm", "kernel": kernel + ", slowest rank", "achieved": worst["spmv_GBs"],
                          "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s", "frac": worst["spmv_GBs"] / hbm_peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes_rank, "avg_launch_ms": worst["spmv_ms"], "per_rank": per_rank,
