@@ -32,6 +32,8 @@
  *
  * Environment:
  *   LPMB_DEVICE=<n>            CUDA device (default 0)
+ *   LPMB_DROPIN_BRICKS=1|0     force the brick-blocked symmetric CG SpMV on / off (default: on from 2^18 particles
+ *                              on axis-aligned simple-cubic 3-D lattices; see lpmb_matrix_enable_bricks)
  *   LPMB_DROPIN_DEVICE_BC=1    solverCG() keeps the tangent on the device and applies the displacement
  *                              BCs as a DoF mask instead of re-uploading the host-edited K_global
  *                              (identical iterates, see tests/test_solver_gpu.py; default off = strict)

@@ -243,6 +243,14 @@ static void ensure_ctx(void)
             exit(1);
         }
     }
+    {   /* brick-blocked symmetric SpMV for the CG (lpmb_brick.cu): pays once the matrix no longer fits L2.
+         * LPMB_DROPIN_BRICKS=1/0 forces it on/off; default: on from 2^18 particles.  Lattices it does not
+         * cover (anything but axis-aligned simple cubic) keep the full-format kernel. */
+        const char *bk = getenv("LPMB_DROPIN_BRICKS");
+        const int want = bk ? atoi(bk) != 0 : (N >= (1 << 18) && dim == 3 && lattice == 2);
+        if (want && lpmb_matrix_enable_bricks(g_ctx, 1) != LPMB_OK)
+            fprintf(stderr, "lpmc_dropin: brick SpMV not used (%s)\n", lpmb_last_error());
+    }
 }
 
 /* state arrays that exist on the host before the first force evaluation (initial cracks set damage_broken,

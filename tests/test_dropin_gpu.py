@@ -20,8 +20,9 @@ REFDIR = ROOT / "oracle" / "_ref"
 GOLD = ROOT / "tests" / "golden"
 
 
-def _run(binary, cwd, timeout, threads=None):
+def _run(binary, cwd, timeout, threads=None, extra_env=None):
     env = dict(os.environ)
+    env.update(extra_env or {})
     if threads:
         env["OMP_NUM_THREADS"] = str(threads)
     with open(cwd / "run.log", "w") as log:
@@ -56,14 +57,17 @@ def _compare_tables(a, b, rtol, what):
     return n, worst
 
 
-def test_default_driver_full_run_matches_reference(tmp_path):
+@pytest.mark.parametrize("bricks", ["0", "1"])
+def test_default_driver_full_run_matches_reference(tmp_path, bricks):
     """src/lpmc_project.c, all 91 cyclic load steps (589 Newton iterations): per-step displacement, reaction force,
-    stress and strain records + the Newton iteration count of every step vs the all-CPU reference run"""
+    stress and strain records + the Newton iteration count of every step vs the all-CPU reference run; once with
+    the full-format CG SpMV and once with the brick-blocked symmetric one (LPMB_DROPIN_BRICKS)"""
     exe = REFDIR / "lpmc_default_b200"
     if not exe.exists() or not (GOLD / "c1_result_disp.txt").exists():
         pytest.skip("oracle/_ref/lpmc_default_b200 or golden result files missing")
-    assert _run(exe, tmp_path, 900), "default driver did not finish"
+    assert _run(exe, tmp_path, 900, extra_env={"LPMB_DROPIN_BRICKS": bricks}), "default driver did not finish"
     log = (tmp_path / "run.log").read_text()
+    assert "brick SpMV not used" not in log
     newton = [int(m) for m in re.findall(r"Loading step \d+ has finished in (\d+) iterations", log)]
     gold_newton = [int(x) for x in (GOLD / "c1_newton_iterations.txt").read_text().split()]
     assert len(newton) == 91
