@@ -7,23 +7,26 @@
 // lpmb_symspmv.cu); re-using it inside one CTA does.
 //
 // How.  Particles are regrouped (internally only; the ABI keeps the reference's numbering) into bricks of 8x8x8
-// lattice sites = 512 rows = one CTA of 512 threads, thread r <-> row r.  A pair {i,j} is owned by the end point
-// from which the displacement j-i lies in the positive half space (dz>0, or dz=0 & dy>0, or dz=dy=0 & dx>0), so
-// ownership does not depend on any numbering.  Displacements are grouped in classes (30 positive ones + the
-// diagonal for the simple-cubic 2-hop stencil); the brick stores, class-major and coalesced over r, the 3x3
-// block K_{i,i+d} and the (permuted) column index.  For each class, thread r loads its block once and forms
-//        own[r]      += K   x_j        (registers)
-//        acc[i+d]    += K^T x_i        (shared memory, indexed by the target's position in the brick's
-//                                       12 x 12 x 10 extended box)
+// lattice sites = 512 rows = one CTA of 512 threads, thread r <-> row r = local lattice position.  A pair {i,j}
+// is owned by the end point from which the displacement j-i lies in the positive half space (dz>0, or dz=0 &
+// dy>0, or dz=dy=0 & dx>0), so ownership does not depend on any numbering.  Displacements are grouped in classes
+// (30 positive ones + the diagonal for the simple-cubic 2-hop stencil); the brick stores, class-major and
+// coalesced over r, only the 3x3 blocks K_{i,i+d} -- no column indices: the neighbour of row r in class u sits
+// at a fixed offset in the brick's 12 x 12 x 10 extended box, absent blocks are zeros.  For each class, thread r
+// takes its block from the shared-memory tile TMA delivered and forms
+//        own[r]      += K   x_j        (registers; x of the extended box is staged in shared memory)
+//        acc[i+d]    += K^T x_i        (shared memory, same slot index as x_j)
 // A class is a translation, so within a class all targets are distinct: plain shared-memory read-modify-write,
 // one __syncthreads per class, fixed summation order -> deterministic, no atomics.  Contributions that land
-// outside the brick are written to a per-brick staging box and folded in by a second, tiny gather kernel that
-// visits the (at most 11) source bricks of a row in a fixed order; it also applies the DoF mask and produces the
-// p.Ap partials.  Traffic per interior SC particle: 31*(72+4) B of matrix + ~110 B staging + vectors = 2.55 KB
-// instead of 4.69 KB.
+// outside the brick are written to a per-brick staging box and folded in by a second, small gather kernel that
+// adds the (at most 7) source bricks of a row in a fixed order; it also applies the DoF mask and produces the
+// p.Ap partials.  Traffic per interior SC particle: 31*72 B of matrix + ~90 B staging + vectors = 2.4 KB instead
+// of 4.69 KB; measured 3.84 ms per SpMV at 216^3 against 6.97 ms for the full format.
 //
-// Scope of this first version: axis-aligned simple-cubic lattices in 3-D on one GPU (what the headline workload
-// is); anything else keeps the full-format kernel.  Enabled explicitly with lpmb_matrix_enable_bricks().
+// Scope: axis-aligned simple-cubic lattices in 3-D (checked on the device; anything else keeps the full-format
+// kernel), one GPU or z-slabs (rows = owned layers +- the 2-layer CG halo; halo rows of the search direction are
+// pushed by the neighbours through peer memory, lpmb_peer.cu, or exchanged with NCCL).  Enabled explicitly with
+// lpmb_matrix_enable_bricks(); the full-format values stay the master copy and are mirrored after every assembly.
 #include <algorithm>
 
 #include "lpmb_internal.cuh"
