@@ -460,7 +460,7 @@ void computeBondForceGeneral(int mode, int temp)
         down_d2("dL_total", dL_total, N, 2);
         down_d2("TdL_total", TdL_total, N, 2);
     }
-    if (mode == 0) {
+    if (mode == 0 || mode == 3) {
         down_d2("dL_ave", dL_ave, N, nn);
         down_d2("ddLp", ddLp, N, nn);
         DOWN1D("J2_dlambda", J2_dlambda, N);

@@ -6,6 +6,7 @@
 //   computeBondForceElastic(ii)              src/constitutive.c:228-283  (plmode 6)
 //   computeBondForceIncrementalUpdating(ii)  src/constitutive.c:167-225  (plmode 4, predictor)
 //   computeBondForceJ2mixedLinear3D(ii)      src/constitutive.c:466-686  (plmode 0)
+//   computeBondForceJ2energyReturnMap(ii,t)  src/constitutive.c:286-463  (plmode 3)
 //   computeStress()                          src/lpm_basic.c:53-125
 //   computedL()                              src/lpm_basic.c:252-291
 //   switchStateV(flag)                       src/constitutive.c:10-85
@@ -212,12 +213,19 @@ geometry_kernel(BondView v, const double *__restrict__ L0, const double *__restr
 // ---------------------------------------------------------------------------------------------
 // LAW 6 (elastic, constitutive.c:267-279):  F = (2Kn dL + .5(TdLt_i+TdLt_j) + .5 Tv (dLt_i+dLt_j)) * broken
 // LAW 0 (J2,      constitutive.c:652-667):  dL_ave = .5 (dL_ij + dL_ji);  F = (2Kn dL_ave + ...) * damage_w
+// LAW 3 (J2 energy, constitutive.c:437-446): as LAW 0 but F *= (1 - damage_D[.][.][0]), which is not zero for a
+//        broken bond -- and the reference only refreshes the dilatation sums of ii and its INTACT neighbours during
+//        call ii (constitutive.c:289-295), so across a broken bond it reads whatever the partner holds at that point
+//        of the serial particle loop: the new sums if an earlier call (the partner's own or one of its intact
+//        neighbours', index < ii) already visited it, else the values from before computeBondForceGeneral.
+//        `prev` holds those old sums so the serial result is reproduced exactly.
 template <int LAW>
 __global__ void __launch_bounds__(BT)
 force_kernel(BondView v, const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ scale /* broken | w */,
              const double *__restrict__ dL, const double *__restrict__ dLt, const double *__restrict__ TdLt,
              const double *__restrict__ csx, const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ dL_ave,
-             double *__restrict__ F, double *__restrict__ Pin)
+             double *__restrict__ F, double *__restrict__ Pin, const double *__restrict__ broken = nullptr,
+             const double *__restrict__ dLt_prev = nullptr, const double *__restrict__ TdLt_prev = nullptr)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
     if (i >= v.N)
@@ -231,9 +239,23 @@ force_kernel(BondView v, const double *__restrict__ Kn, const double *__restrict
         const int nj = v.nbr[e];
         const int s = v.nsign[e];
         const double dLt_i = s ? dLt_i1 : dLt_i0, TdLt_i = s ? TdLt_i1 : TdLt_i0;
-        const double dLt_j = dLt[(size_t)s * Np + nj], TdLt_j = TdLt[(size_t)s * Np + nj];
+        double dLt_j = dLt[(size_t)s * Np + nj], TdLt_j = TdLt[(size_t)s * Np + nj];
+        if (LAW == 3 && broken[e] <= LPMB_EPS) {
+            // first call of the serial loop that refreshes nj: its own, or that of its lowest intact neighbour
+            int first = nj;
+            for (int m = 0; m < v.nn; m++) {
+                const size_t em = (size_t)m * Np + nj;
+                const int q = v.nbr[em];
+                if (q != -1 && broken[em] > LPMB_EPS && q < first)
+                    first = q;
+            }
+            if (first > i) {
+                dLt_j = dLt_prev[(size_t)s * Np + nj];
+                TdLt_j = TdLt_prev[(size_t)s * Np + nj];
+            }
+        }
         double stretch;
-        if (LAW == 0) {
+        if (LAW == 0 || LAW == 3) {
             const int mj = v.mirror[e];
             if (mj >= 0) {
                 stretch = 0.5 * (dL[e] + dL[(size_t)mj * Np + nj]);
@@ -245,7 +267,10 @@ force_kernel(BondView v, const double *__restrict__ Kn, const double *__restrict
             stretch = dL[e];
         }
         double f = 2.0 * Kn[e] * stretch + 0.5 * (TdLt_i + TdLt_j) + 0.5 * Tv[e] * (dLt_i + dLt_j);
-        f *= scale[e];
+        if (LAW == 3)
+            f *= (1.0 - scale[e]);
+        else
+            f *= scale[e];
         F[e] = f;
         p0 += csx[e] * f;
         p1 += csy[e] * f;
@@ -426,6 +451,87 @@ j2_return_map_kernel(BondView v, double V, double J2_H, double J2_xi, const doub
         beta2[(size_t)q * Np + i] = beta[q];
     alpha2[i] = alpha;
     dlambda[i] = dl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// J2 with the distortional-energy return map (plmode 3), per particle   constitutive.c:336-411
+// Scalar equivalent back stress / plastic strain, plastic multiplier by bisection on (0,1) to TOLITER = 1e-4
+// (14 halvings).  Quirks kept: the bond loops run over the first nb[i] slots (the CURRENT intact count, not
+// nb_initial); J2_k is Kn of the last layer-1 bond among them; nb1 counts the layer-1 slots of the initial list.
+// reads slot-[0] (dLp0, J2_beta_eq0, J2_alpha0), writes slot-[2], J2_dlambda, ddLp, pl_flag
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT)
+j2_energy_return_map_kernel(BondView v, double V, double J2_H, double J2_xi, double radius, int load_indicator,
+                            const double *__restrict__ Ce /* [ntype][3] */, const int *__restrict__ type, const double *__restrict__ sigmay,
+                            const double *__restrict__ Kn, const double *__restrict__ broken, const double *__restrict__ dL,
+                            const double *__restrict__ dLt, const double *__restrict__ dLp0, const double *__restrict__ beq0,
+                            const double *__restrict__ alpha0, double *__restrict__ dLp2, double *__restrict__ beq2, double *__restrict__ alpha2,
+                            double *__restrict__ ddLp, double *__restrict__ dlambda_out, int *__restrict__ pl_flag)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int nb_i = v.nb[i];
+    int nb1 = 0;  // countNEqual(neighbors1[i], nneighbors1, -1): layer-1 entries of the initial list
+    for (int j = 0; j < v.nbi[i]; j++)
+        nb1 += v.nsign[(size_t)j * Np + i] == 0;
+    const int nb2 = nb_i - nb1;
+    const double dLt0 = dLt[i], dLt1 = dLt[Np + i];
+    const double c44 = Ce[3 * type[i] + 2];
+    double U_d = 0.0, J2_k = 0.0;
+    const double J2_V = V * nb_i / v.nn;
+    for (int j = 0; j < nb_i; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int s = v.nsign[e];
+        if (s == 0) {
+            U_d += 0.5 * Kn[e] * (dL[e] - dLt0 / nb1) * (dL[e] - dLt0 / nb1);
+            J2_k = Kn[e];
+        } else if (s == 1) {
+            U_d += 0.5 * Kn[e] * (dL[e] - dLt1 / nb2) * (dL[e] - dLt1 / nb2);
+        }
+    }
+    const double J2_sigma = sqrt(6.0 * c44 * U_d / J2_V);
+    const double beq = beq0[i], alpha = alpha0[i], sy = sigmay[i];
+    double dl = 0.0;
+    double yield_func = fabs(load_indicator * J2_sigma - beq) - (sy + (1.0 - J2_xi) * J2_H * alpha);
+    if (yield_func > 0.0) {
+        pl_flag[i] = 1;
+        double a = 0.0, b = 1.0;
+        double ya = yield_func;
+        while ((b - a) > 1e-4 /* TOLITER */) {
+            dl = (a + b) / 2.0;
+            yield_func = fabs(load_indicator * J2_sigma / (1.0 + 0.5 * dl) -
+                              (beq + load_indicator * J2_xi * J2_H * dl * J2_sigma * sqrt(radius / J2_k / c44) / 6.0 / (1.0 + 0.5 * dl))) -
+                         (sy + (1.0 - J2_xi) * J2_H * alpha + (1.0 - J2_xi) * J2_H * dl * J2_sigma * sqrt(radius / J2_k / c44) / 6.0 / (1.0 + 0.5 * dl));
+            if (yield_func * ya < 0.0) {
+                b = dl;
+            } else {
+                a = dl;
+                ya = yield_func;
+            }
+        }
+    }
+    dlambda_out[i] = dl;
+    alpha2[i] = alpha + dl / (1.0 + 0.5 * dl) * sqrt(radius / 6.0 / J2_k * U_d / J2_V);
+    beq2[i] = (beq + load_indicator * J2_xi * J2_H * dl / (1.0 + 0.5 * dl) * sqrt(radius / 6.0 / J2_k * U_d / J2_V));
+    double f_d = 0.0;
+    for (int j = 0; j < v.nn; j++) {
+        const size_t e = (size_t)j * Np + i;
+        double xd = dLp0[e];
+        if (j < nb_i) {
+            const int s = v.nsign[e];
+            if (s == 0)
+                f_d = 2.0 * Kn[e] / (1 + dl / 2.0) * (dL[e] - dLt0 / nb1);
+            if (s == 1)
+                f_d = 2.0 * Kn[e] / (1 + dl / 2.0) * (dL[e] - dLt1 / nb2);
+            double dd = dl * f_d / (4.0 * Kn[e]);
+            dd *= broken[e];
+            ddLp[e] = dd;
+            xd += dd;
+        }
+        dLp2[e] = broken[e] * xd;  // constitutive.c:450-451
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -683,7 +789,6 @@ int lpmb_compute_stress(lpmb_ctx *c)
 // computeBondForceGeneral(plmode, t)   constitutive.c:88-146
 extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
 {
-    (void)load_indicator;  // only the plmode-3 law reads it
     LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(c->params.count("particle_volume"), LPMB_ERR_STATE, "parameter particle_volume not set");
@@ -719,6 +824,29 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         LPMB_TRY(run_geometry(c, v, "dLp2"));
         force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
         LPMB_LAUNCH_CHECK(c);
+    } else if (plmode == 3) {
+        // J2, distortional-energy return map (constitutive.c:286-463): geometry -> return map -> geometry -> force
+        LPMB_REQUIRE(c->params.count("J2_H") && c->params.count("J2_xi") && c->params.count("radius"), LPMB_ERR_STATE, "J2_H / J2_xi / radius not set");
+        Field *ce = lpmb_field(c, "Ce");
+        LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+        // dilatation sums as they are before this call (see force_kernel, LAW 3)
+        if (!lpmb_field(c, "dL_total_prev")) {
+            LPMB_TRY(lpmb_field_alloc(c, "dL_total_prev", FK_PART, FT_F64, 2));
+            LPMB_TRY(lpmb_field_alloc(c, "TdL_total_prev", FK_PART, FT_F64, 2));
+        }
+        LPMB_TRY(copy_field(c, "dL_total_prev", "dL_total"));
+        LPMB_TRY(copy_field(c, "TdL_total_prev", "TdL_total"));
+        LPMB_TRY(run_geometry(c, v, "dLp0"));
+        j2_energy_return_map_kernel<<<g, BT, 0, c->stream>>>(
+            v, param(c, "particle_volume"), param(c, "J2_H"), param(c, "J2_xi"), param(c, "radius"), load_indicator, (const double *)ce->d,
+            fptr<int>(c, "type"), fptr<double>(c, "sigmay"), Kn, broken, dL, dLt, fptr<double>(c, "dLp0"), fptr<double>(c, "J2_beta_eq0"),
+            fptr<double>(c, "J2_alpha0"), fptr<double>(c, "dLp2"), fptr<double>(c, "J2_beta_eq2"), fptr<double>(c, "J2_alpha2"),
+            fptr<double>(c, "ddLp"), fptr<double>(c, "J2_dlambda"), fptr<int>(c, "pl_flag"));
+        LPMB_LAUNCH_CHECK(c);
+        LPMB_TRY(run_geometry(c, v, "dLp2"));
+        force_kernel<3><<<g, BT, 0, c->stream>>>(v, Kn, Tv, fptr<double>(c, "damage_D0"), dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin, broken,
+                                                 fptr<double>(c, "dL_total_prev"), fptr<double>(c, "TdL_total_prev"));
+        LPMB_LAUNCH_CHECK(c);
     } else if (plmode == 1) {
         // crystal plasticity (constitutive.c:866-1396): geometry -> Miehe return map -> geometry -> averaged force
         LPMB_TRY(run_geometry(c, v, "dLp0"));
@@ -727,7 +855,7 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
         LPMB_LAUNCH_CHECK(c);
     } else {
-        lpmb_set_error("computeBondForceGeneral: plmode %d is not built (0, 1, 4, 6 are)", plmode);
+        lpmb_set_error("computeBondForceGeneral: plmode %d is not built (0, 1, 3, 4, 6 are)", plmode);
         return LPMB_ERR_UNSUPPORTED;
     }
     LPMB_TRY(lpmb_compute_stress(c));

@@ -161,3 +161,34 @@ def test_switch_state_semantics(ctx):
     ctx.set_field("dLp1", b)
     ctx.switch_state(0)
     assert_same(ctx.get_field("dLp0"), b)
+
+
+@pytest.mark.parametrize("tag,t", [("s1.n0", 1), ("s1.n1", 1), ("s1.n2", 1), ("s2.n0", -1), ("s2.n1", -1), ("s2.n2", -1)])
+def test_j2_energy_law_bit_exact(lpm, tag, t):
+    """computeBondForceGeneral(3, t) = computeBondForceJ2energyReturnMap (constitutive.c:286-463):
+    bisection return map on the distortional energy; every recorded call of tests/golden/sc6_j2energy.npz is
+    replayed from its complete input state.  Step 2 has broken bonds (nb < nb_initial) and t = -1."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "sc6_j2energy.npz")
+    c = make_ctx(lpm, g)
+    pre = f"{tag}.pre"
+    for n in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "bond_stress", "damage_broken", "damage_w", "dL_total", "TdL_total",
+              "stress_tensor", "J2_dlambda", "J2_stresseq", "J2_stressm", "J2_triaxiality", "xyz", "Pin", "pl_flag", "nb"):
+        c.set_field(n, g[f"{pre}.{n}"])
+    put_slots(c, "dLp", g[f"{pre}.dLp"])
+    put_slots(c, "damage_D", g[f"{pre}.damage_D"])
+    put_slots(c, "J2_alpha", g[f"{pre}.J2_alpha"])
+    put_slots(c, "J2_beta_eq", g[f"{pre}.J2_beta_eq"])
+    c.bond_force(3, t)
+    bf = f"{tag}.bf"
+    for n in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "bond_stress", "dL_total", "TdL_total", "stress_tensor", "J2_dlambda",
+              "J2_stresseq", "J2_stressm", "J2_triaxiality", "pl_flag", "Pin"):
+        assert_same(c.get_field(n), g[f"{bf}.{n}"], n)
+    assert_same(get_slots(c, "dLp", 3), g[f"{bf}.dLp"], "dLp")
+    assert_same(get_slots(c, "J2_alpha", 3), g[f"{bf}.J2_alpha"], "J2_alpha")
+    assert_same(get_slots(c, "J2_beta_eq", 3), g[f"{bf}.J2_beta_eq"], "J2_beta_eq")
+    if tag != "s2.n0":
+        assert (g[f"{bf}.J2_dlambda"] > 0).sum() > 50      # the bisection really ran
+    if tag.startswith("s2"):
+        assert (g[f"{pre}.nb"] < g["setup.nb_initial"]).any()
+    c.close()

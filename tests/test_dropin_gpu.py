@@ -156,3 +156,20 @@ def test_dropin_replays_crystal_plasticity_golden_case(tmp_path):
         for n in ("F", "stress_tensor", "cp_A", "cp_gy", "cp_A_single", "dLp"):
             assert _rel(new[f"{s}.{n}"], old[f"{s}.{n}"]) <= 1e-8, (s, n)
         assert _rel(new[f"{s}.xyz"] - old["setup.xyz"], old[f"{s}.xyz"] - old["setup.xyz"]) <= 1e-9
+
+
+def test_dropin_replays_j2_energy_golden_case(tmp_path):
+    """tests/golden/sc6_j2energy.npz (plmode 3) with every hot-path call going through liblpmc_dropin.so.
+    The first call's inputs come from a GPU CG solve (disp within 1e-10 of the reference's), and the law's plastic
+    multiplier is a bisection result quantised to 2^-14, so F / state are compared to 1e-7, dlambda to one
+    bisection step.  Only step 1: step 2 of the generator breaks bonds by poking damage_broken on the HOST between
+    two calls, which the drop-in layer (device-authoritative state after the first upload, include/lpmc_dropin.h)
+    does not see -- no shipped driver does that."""
+    new = _regen("make_golden_j2e.py", tmp_path, "j2e.npz")
+    old = np.load(GOLD / "sc6_j2energy.npz")
+    assert int(new["newton_counts"][0]) == int(old["newton_counts"][0])
+    for t in ("s1.n0", "s1.n1", "s1.n2"):
+        assert _rel(new[f"{t}.pre.xyz"], old[f"{t}.pre.xyz"]) <= 1e-9
+        assert np.abs(new[f"{t}.bf.J2_dlambda"] - old[f"{t}.bf.J2_dlambda"]).max() <= 2.0 ** -13
+        for k in ("F", "Pin", "dLp", "J2_alpha", "J2_beta_eq", "stress_tensor"):
+            assert _rel(new[f"{t}.bf.{k}"], old[f"{t}.bf.{k}"]) <= 1e-7, (t, k)

@@ -76,6 +76,27 @@ def test_golden_matches_reference_build(golden):
             assert np.array_equal(new[k], golden[k]), k
 
 
+def test_j2_energy_golden_matches_reference_build(tmp_path):
+    """tests/golden/sc6_j2energy.npz (plmode 3) regenerates bit-identically from oracle/_ref"""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    import os, subprocess, sys
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    out = tmp_path / "j2e.npz"
+    subprocess.run([sys.executable, str(gold / "make_golden_j2e.py")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, LPMB_GOLDEN_OUT=str(out)))
+    new, old = np.load(out), np.load(gold / "sc6_j2energy.npz")
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert np.array_equal(new[k], old[k]), k
+    # the law is really exercised: bisection results strictly inside (0, 1), reversed load indicator in step 2
+    dl = old["s1.n0.bf.J2_dlambda"]
+    assert (dl > 0).all() and dl.max() < 1.0
+    assert (old["s2.n1.bf.J2_dlambda"] > 0).sum() > 50
+
+
 def test_golden_internal_consistency(golden):
     g = golden
     assert g["setup.xyz"].shape == (216, 3)
