@@ -168,6 +168,10 @@ int lpmb_update_rr(lpmb_ctx *ctx, double *norm_residual, double *norm_reaction);
 /* returns the number of newly broken bonds in *broken; broken (i, neighbor) pairs are appended to
  * pairs[2*k], pairs[2*k+1] in the reference's logging order, up to max_pairs (may be NULL) */
 int lpmb_update_damage(lpmb_ctx *ctx, int plmode, int *broken, int *pairs, int max_pairs);
+/* computeStrain(), lpm_basic.c:127-249: per-particle weighted-least-squares strain tensor from the elastic bond
+ * stretches dL over the initial bond directions (n x n LU with partial pivoting, n = 3(dim-1)); writes the field
+ * strain_tensor[N][6] in the reference's component order (e11 e22 e33 e23 e13 e12). */
+int lpmb_compute_strain(lpmb_ctx *ctx);
 int lpmb_update_crack(lpmb_ctx *ctx);
 
 /* ---- crystal plasticity (plmode 1) ---------------------------------------------------------- */

@@ -45,6 +45,7 @@ lib.lpmb_spmv_bytes_bricks.restype = C.c_longlong
 lib.lpmb_spmv_bytes_bricks.argtypes = [c_vp]
 lib.lpmb_matrix_enable_bricks.argtypes = [c_vp, C.c_int]
 lib.lpmb_dist_mode.argtypes = [c_vp]
+lib.lpmb_compute_strain.argtypes = [c_vp]
 lib.lpmb_destroy.restype = None
 lib.lpmb_destroy.argtypes = [c_vp]
 lib.lpmb_create.argtypes = [C.POINTER(c_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -281,6 +282,9 @@ class Context:
 
     def bond_force(self, plmode: int, load_indicator: int = 1):
         _check(lib.lpmb_bond_force(self._h, plmode, load_indicator))
+
+    def compute_strain(self):
+        _check(lib.lpmb_compute_strain(self._h))
 
     def switch_state(self, flag: int):
         _check(lib.lpmb_switch_state(self._h, flag))

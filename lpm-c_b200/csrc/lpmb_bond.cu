@@ -9,6 +9,7 @@
 //   computeBondForceJ2energyReturnMap(ii,t)  src/constitutive.c:286-463  (plmode 3)
 //   computeStress()                          src/lpm_basic.c:53-125
 //   computedL()                              src/lpm_basic.c:252-291
+//   computeStrain()                          src/lpm_basic.c:127-249
 //   switchStateV(flag)                       src/constitutive.c:10-85
 //   updateRR()                               src/stiffness.c:519-534
 //   updateCrack()                            src/constitutive.c:1399-1434
@@ -696,6 +697,151 @@ __global__ void finish_rr_kernel(const double *__restrict__ partials, int nparts
         out2[0] = x;  // squared norms; the square root is taken after the (optional) all-reduce
         out2[1] = y;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strain   lpm_basic.c:127-249: per particle, weighted least squares over the initial bond directions
+// (weights 0.1 / 0.9 for the two shells), n x n system (n = 3(dim-1)) solved by LU with partial pivoting
+// (LAPACKE_dgesv, row-major; first row of maximal |a| wins).  Singular system (info > 0): dgesv leaves the right
+// hand side untouched and the reference then stores exactly that (its copy from particle i-1 is overwritten in
+// 3-D; in 2-D it only reaches component [2], which nothing else ever writes); particle 0 is skipped.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(BT)
+strain_kernel(BondView v, const double *__restrict__ xyz0, const double *__restrict__ L0, const double *__restrict__ dL,
+              double *__restrict__ strain)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    constexpr int NS = 3 * (DIM - 1);
+    const size_t Np = v.Np;
+    double r4[DIM][DIM][DIM][DIM], r2[DIM][DIM];
+    for (int k = 0; k < DIM; k++)
+        for (int n = 0; n < DIM; n++) {
+            r2[k][n] = 0.0;
+            for (int m = 0; m < DIM; m++)
+                for (int l = 0; l < DIM; l++)
+                    r4[k][n][m][l] = 0.0;
+        }
+    double xi[DIM];
+    for (int k = 0; k < DIM; k++)
+        xi[k] = xyz0[(size_t)k * Np + i];
+    const int nbi = v.nbi[i];
+    for (int j = 0; j < nbi; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int s = v.nsign[e];
+        if (s != 0 && s != 1)
+            continue;
+        const double w = s == 0 ? 0.1 : 0.9;
+        const int nj = v.nbr[e];
+        const double L = L0[e], d = dL[e];
+        double dx[DIM];
+        for (int k = 0; k < DIM; k++)
+            dx[k] = xyz0[(size_t)k * Np + nj] - xi[k];
+        for (int k = 0; k < DIM; k++)
+            for (int n = 0; n < DIM; n++) {
+                for (int m = 0; m < DIM; m++)
+                    for (int l = 0; l < DIM; l++)
+                        r4[k][n][m][l] += w * dx[k] / L * dx[n] / L * dx[m] / L * dx[l] / L;
+                r2[k][n] += w * d / L * dx[k] / L * dx[n] / L;
+            }
+    }
+    double a[NS * NS], b[NS], b_in[NS];
+    int ii = 0;
+    for (int j = 0; j < DIM; j++)
+        for (int k = 0; k < DIM; k++)
+            for (int m = 0; m < DIM; m++)
+                for (int l = 0; l < DIM; l++)
+                    if (m <= l && j <= k)
+                        a[ii++] = r4[m][l][j][k];
+    ii = 0;
+    for (int j = 0; j < DIM; j++)
+        for (int k = 0; k < DIM; k++)
+            if (j <= k) {
+                b[ii] = r2[j][k];
+                b_in[ii] = r2[j][k];
+                ii++;
+            }
+    int info = 0;
+    for (int k = 0; k < NS; k++) {
+        int p = k;
+        double amax = fabs(a[k * NS + k]);
+        for (int r = k + 1; r < NS; r++) {
+            const double t = fabs(a[r * NS + k]);
+            if (t > amax) {
+                amax = t;
+                p = r;
+            }
+        }
+        if (a[p * NS + k] == 0.0) {
+            if (info == 0)
+                info = k + 1;
+            continue;
+        }
+        if (p != k) {
+            for (int c = 0; c < NS; c++) {
+                const double t = a[k * NS + c];
+                a[k * NS + c] = a[p * NS + c];
+                a[p * NS + c] = t;
+            }
+            const double t = b[k];
+            b[k] = b[p];
+            b[p] = t;
+        }
+        const double piv = a[k * NS + k];
+        for (int r = k + 1; r < NS; r++) {
+            const double l = a[r * NS + k] / piv;
+            a[r * NS + k] = l;
+            if (l != 0.0) {
+                for (int c = k + 1; c < NS; c++)
+                    a[r * NS + c] -= l * a[k * NS + c];
+                b[r] -= l * b[k];
+            }
+        }
+    }
+    if (info != 0) {
+        if (i == 0)
+            return;
+        for (int k = 0; k < NS; k++)
+            b[k] = b_in[k];
+    } else {
+        for (int r = NS - 1; r >= 0; r--) {
+            double t = b[r];
+            for (int c = r + 1; c < NS; c++)
+                t -= a[r * NS + c] * b[c];
+            b[r] = t / a[r * NS + r];
+        }
+    }
+    if (DIM == 2) {
+        strain[i] = b[0];
+        strain[5 * Np + i] = b[1];
+        strain[Np + i] = b[2];
+    } else {
+        strain[i] = b[0];
+        strain[5 * Np + i] = b[1];
+        strain[4 * Np + i] = b[2];
+        strain[Np + i] = b[3];
+        strain[3 * Np + i] = b[4];
+        strain[2 * Np + i] = b[5];
+    }
+}
+
+extern "C" int lpmb_compute_strain(lpmb_ctx *c)
+{
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    const double *x0 = fptr<double>(c, "xyz_initial"), *L0 = fptr<double>(c, "distance_initial"), *dL = fptr<double>(c, "dL");
+    double *strain = fptr<double>(c, "strain_tensor");
+    LPMB_REQUIRE(x0 && L0 && dL && strain, LPMB_ERR_STATE, "computeStrain: fields missing");
+    if (c->dim == 3)
+        strain_kernel<3><<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(v, x0, L0, dL, strain);
+    else
+        strain_kernel<2><<<lpmb_blocks(c->N, BT), BT, 0, c->stream>>>(v, x0, L0, dL, strain);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

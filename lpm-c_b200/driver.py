@@ -13,7 +13,7 @@ this one sets the same quantities through the ABI and keeps the same order of op
     updateRR, norms, tolerance multiplier                 :409-414
     while ||res|| > TOLITER*max(||res||0, ||reaction||0) and ni < MAXITER:   :424
         switchStateV(0); BC; solverCG; computeBondForceGeneral(plmode); updateRR     :428-463
-    [computeStrain -- output only, not on this path]      :466
+    computeStrain (output record; compute_strain=True)     :466
     updateDamageGeneral; updateCrack; switchStateV(1)     :469-471
     if broken: calcStiffness...(6); goto label_broken_bond  :525-541
 """
@@ -35,7 +35,7 @@ class StepLog:
 
 
 def load_step(ctx, plmode: int, disp_bc, force_bc, load_indicator: int = 1, rel=1e-8, abs_tol=1e-12,
-              emulate_side_effects: bool = True, max_iter: int = MAXITER) -> StepLog:
+              emulate_side_effects: bool = True, max_iter: int = MAXITER, compute_strain: bool = False) -> StepLog:
     """One load step.  disp_bc = [(type, axis, step)], force_bc = [(type, sx, sy, sz)] as dBP / fBP rows."""
     log = StepLog()
     ctx.copy_field("xyz_temp", "xyz")
@@ -57,6 +57,8 @@ def load_step(ctx, plmode: int, disp_bc, force_bc, load_indicator: int = 1, rel=
             log.residual_norms.append(nr)
             ni += 1
         log.newton_iterations += ni
+        if compute_strain:
+            ctx.compute_strain()
         broken, _ = ctx.update_damage(plmode)
         ctx.update_crack()
         ctx.switch_state(1)

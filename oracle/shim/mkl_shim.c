@@ -126,7 +126,9 @@ void cblas_dgemm(const CBLAS_LAYOUT layout, const CBLAS_TRANSPOSE transa, const 
 /* ---------------------------------------------------------------- LAPACKE */
 
 /* Row-major LU with partial pivoting (first row of maximal |a| wins, as LAPACK's idamax),
- * A overwritten by L\U, B by the solution; info = k+1 on an exactly zero pivot. */
+ * A overwritten by L\U, B by the solution; info = k+1 on an exactly zero pivot -- and then, as in
+ * LAPACK's dgesv (dgetrf, then dgetrs only if info == 0), B is left exactly as it came in
+ * (computeStrain, lpm_basic.c:209-242, reads it in that case). */
 lapack_int LAPACKE_dgesv(int matrix_layout, lapack_int n, lapack_int nrhs, double *a, lapack_int lda,
                          lapack_int *ipiv, double *b, lapack_int ldb)
 {
@@ -135,6 +137,12 @@ lapack_int LAPACKE_dgesv(int matrix_layout, lapack_int n, lapack_int nrhs, doubl
         abort();
     }
     lapack_int info = 0;
+    double b_in[64];
+    const int keep = n * nrhs <= 64;
+    if (keep)
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < nrhs; j++)
+                b_in[i * nrhs + j] = b[i * ldb + j];
     for (int k = 0; k < n; k++) {
         int p = k;
         double amax = fabs(a[k * lda + k]);
@@ -175,8 +183,13 @@ lapack_int LAPACKE_dgesv(int matrix_layout, lapack_int n, lapack_int nrhs, doubl
             }
         }
     }
-    if (info != 0)
+    if (info != 0) {
+        if (keep)
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < nrhs; j++)
+                    b[i * ldb + j] = b_in[i * nrhs + j];
         return info;
+    }
     for (int j = 0; j < nrhs; j++)
         for (int i = n - 1; i >= 0; i--) {
             double s = b[i * ldb + j];

@@ -111,7 +111,9 @@ def main():
                 g[f"{t}.norm_residual"] = np.array([nr])
             ni += 1
         newton_counts.append(ni)
+        g[f"{s}.strain.dL"] = r.get("dL")
         L.computeStrain()
+        g[f"{s}.strain.strain_tensor"] = r.get("strain_tensor")
         broken = L.updateDamageGeneral(b"/dev/null", step, r.gi("plmode"))
         g[f"{s}.dam.broken"] = np.array([broken])
         state(r, f"{s}.dam", g)

@@ -192,3 +192,13 @@ def test_j2_energy_law_bit_exact(lpm, tag, t):
     if tag.startswith("s2"):
         assert (g[f"{pre}.nb"] < g["setup.nb_initial"]).any()
     c.close()
+
+
+@pytest.mark.parametrize("step", ["s1", "s2"])
+def test_compute_strain_bit_exact(ctx, golden, step):
+    """computeStrain(), lpm_basic.c:127-249 (SURVEY section 8f #4): weighted least squares + 6x6 LU per particle"""
+    ctx.set_field("dL", golden[f"{step}.strain.dL"])
+    ctx.set_field("strain_tensor", np.zeros((216, 6)) if step == "s1" else golden["s1.strain.strain_tensor"])
+    ctx.compute_strain()
+    assert_same(ctx.get_field("strain_tensor"), golden[f"{step}.strain.strain_tensor"], "strain_tensor")
+    assert np.abs(golden[f"{step}.strain.strain_tensor"]).max() > 1e-4
