@@ -592,7 +592,24 @@ extern "C" int lpmb_matrix_enable_bricks(lpmb_ctx *c, int on)
     }
     BrickMatrix &B = g_bricks[c];
     if (!B.pattern_ready) {
-        const int rc = brick_build_pattern(c, B);
+        int rc = brick_build_pattern(c, B);
+        if (c->world > 1) {
+            // collective call: either every slab gets its bricks or none does (a rank that went on alone into the
+            // peer set-up below would wait for the others forever)
+            double *d_fail;
+            LPMB_CUDA(cudaMalloc(&d_fail, sizeof(double)));
+            const double mine = rc == LPMB_OK ? 0.0 : 1.0;
+            double all = 0.0;
+            LPMB_CUDA(cudaMemcpyAsync(d_fail, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            LPMB_TRY(lpmb_dist_allreduce_sum(c, d_fail, 1));
+            LPMB_CUDA(cudaMemcpyAsync(&all, d_fail, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            LPMB_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(d_fail);
+            if (all != 0.0 && rc == LPMB_OK) {
+                lpmb_set_error("brick SpMV: not eligible on %d other rank(s)", (int)all);
+                rc = LPMB_ERR_UNSUPPORTED;
+            }
+        }
         if (rc != LPMB_OK) {
             lpmb_brick_release(c);
             return rc;
