@@ -27,7 +27,7 @@
 extern int ntype, nparticle, nneighbors, dim, lattice, nneighbors_AFEM, plmode, nslipSys, nbreak;
 extern int *IK, *JK, *type, *dispBC_index, *fix_index, *pl_flag, *nb, *nb_initial, *nb_conn;
 extern int **neighbors, **K_pointer, **conn, **nsign;
-extern double radius, particle_volume, J2_H, J2_xi, damage_L, damage_threshold, damageb_A, damagec_A, critical_bstrain, dtime;
+extern double radius, particle_volume, J2_H, J2_xi, J2_C, damage_L, damage_threshold, damageb_A, damagec_A, critical_bstrain, dtime;
 extern double *K_global, *residual, *Pin, *Pex, *disp, *sigmay, *reaction_force, *damage_visual;
 extern double *J2_dlambda, *J2_stresseq, *J2_stressm, *J2_triaxiality;
 extern double **xyz, **xyz_initial, **xyz_temp, **distance, **distance_initial, **KnTve, **F, **csx, **csy, **csz;
@@ -142,6 +142,7 @@ static void set_params(void)
     CK(lpmb_set_param(g_ctx, "particle_volume", particle_volume));
     CK(lpmb_set_param(g_ctx, "J2_H", J2_H));
     CK(lpmb_set_param(g_ctx, "J2_xi", J2_xi));
+    CK(lpmb_set_param(g_ctx, "J2_C", J2_C));
     CK(lpmb_set_param(g_ctx, "damage_L", damage_L));
     CK(lpmb_set_param(g_ctx, "damage_threshold", damage_threshold));
     CK(lpmb_set_param(g_ctx, "damagec_A", damagec_A));
@@ -460,6 +461,11 @@ void computeBondForceGeneral(int mode, int temp)
         down_d2("dL_total", dL_total, N, 2);
         down_d2("TdL_total", TdL_total, N, 2);
     }
+    if (mode == 5) {
+        down_d2("dL_ave", dL_ave, N, nn);
+        down_d2("ddLp", ddLp, N, nn);
+        DOWN1D("J2_dlambda", J2_dlambda, N);
+    }
     if (mode == 0 || mode == 3) {
         down_d2("dL_ave", dL_ave, N, nn);
         down_d2("ddLp", ddLp, N, nn);
@@ -498,8 +504,8 @@ static int damage(const char *dataName, int tstep, int mode)
     const int cap = 1 << 16;
     int *pairs = (int *)malloc(sizeof(int) * 2 * cap);
     CK(lpmb_update_damage(g_ctx, mode, &broken, pairs, cap));
-    if (mode == 0 || mode == 6) {
-        FILE *fpt = fopen(dataName, "a+"); /* constitutive.c:1440-1442,1481,1761-1763,1841 */
+    if (mode == 0 || mode == 5 || mode == 6) {
+        FILE *fpt = fopen(dataName, "a+"); /* constitutive.c:1440-1442,1481,1610-1613,1672,1761-1763,1841 */
         if (fpt) {
             fprintf(fpt, "TIMESTEP ");
             fprintf(fpt, "%d\n", tstep);
@@ -515,6 +521,10 @@ static int damage(const char *dataName, int tstep, int mode)
         down_slot("damage_D", damage_D, N, nn, 0);
         if (mode == 0)
             down_pslot("damage_nonlocal", damage_nonlocal, N, 0);
+        if (mode == 5) {
+            down_pslot("damage_local", damage_local, N, 0);
+            DOWN1D("nb", nb, N);
+        }
     }
     free(pairs);
     return broken;
@@ -570,11 +580,11 @@ void computeCab()
 }
 void computeBondForceElastic(int i) { (void)i; not_built("computeBondForceElastic(i): per-particle evaluation is internal to the GPU assembly"); }
 void computeBondForceJ2mixedLinear3D(int ii) { (void)ii; not_built("computeBondForceJ2mixedLinear3D(ii): use computeBondForceGeneral(0, t)"); }
-void computeBondForceJ2nonlinearIso(int ii) { (void)ii; not_built("computeBondForceJ2nonlinearIso (plmode 5)"); }
+void computeBondForceJ2nonlinearIso(int ii) { (void)ii; not_built("computeBondForceJ2nonlinearIso(ii): use computeBondForceGeneral(5, t)"); }
 void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe(ii): use computeBondForceGeneral(1, t)"); }
 void computeBondForceIncrementalUpdating(int ii) { (void)ii; not_built("computeBondForceIncrementalUpdating(ii): use computeBondForceGeneral(4, t)"); }
-void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap (plmode 3)"); }
-int updateDuctileDamageBwiseLocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamageBwiseLocal"); return 0; }
+void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap(ii, t): use computeBondForceGeneral(3, t)"); }
+int updateDuctileDamageBwiseLocal(const char *d, int t) { return damage(d, t, 5); }
 int updateDuctileDamagePwiseLocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamagePwiseLocal"); return 0; }
 int updateDuctileDamageBwiseNonlocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamageBwiseNonlocal"); return 0; }
 

@@ -7,6 +7,7 @@
 //   computeBondForceIncrementalUpdating(ii)  src/constitutive.c:167-225  (plmode 4, predictor)
 //   computeBondForceJ2mixedLinear3D(ii)      src/constitutive.c:466-686  (plmode 0)
 //   computeBondForceJ2energyReturnMap(ii,t)  src/constitutive.c:286-463  (plmode 3)
+//   computeBondForceJ2nonlinearIso(ii)       src/constitutive.c:689-863  (plmode 5)
 //   computeStress()                          src/lpm_basic.c:53-125
 //   computedL()                              src/lpm_basic.c:252-291
 //   computeStrain()                          src/lpm_basic.c:127-249
@@ -536,6 +537,277 @@ j2_energy_return_map_kernel(BondView v, double V, double J2_H, double J2_xi, dou
 }
 
 // ---------------------------------------------------------------------------------------------
+// J2 with nonlinear isotropic hardening (plmode 5)   constitutive.c:689-863
+//
+// The reference law is order dependent: call ii returns-maps ii AND each of its intact neighbours and writes the
+// new plastic state straight into slot [0], so during one computeBondForceGeneral(5) particle i is updated once per
+// "caller" c in C(i) = {i} u {intact neighbours of i}, in ascending c (the serial particle loop), each time starting
+// from what the previous caller left.  Every one of those updates is a function of i's own state and of xyz only,
+// so the whole chain of particle i can be run by one thread (trajectory kernel); what the callers need from it are
+// snapshots: after the update made during call c, the elastic stretch of the bond towards c and i's dilatation sums
+// (for c's own bond forces, constitutive.c:836-852).  The force kernel then forms F / Pin of ii from its own
+// snapshot (taken at c = ii) and its neighbours' snapshots taken at c = ii.  Across a broken bond the partner is not
+// refreshed by call ii: the reference reads what the partner's latest caller below ii left (or the values from
+// before the call).  F[i] ends up holding the TRIAL forces (:737) of the last caller of i unless that is i itself.
+// SY(x) = 620 + 3300 (1 - exp(-0.4 x)) (lpm.h:50); bisection on (0,1) to TOLITER = 1e-4.
+// ---------------------------------------------------------------------------------------------
+#define ISO_MAXNN 24
+
+__global__ void __launch_bounds__(BT)
+j2iso_trajectory_kernel(BondView v, double V, double J2_C, const double *__restrict__ Ce, const int *__restrict__ type,
+                        const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ broken,
+                        const double *__restrict__ L0, double *__restrict__ dLp0, double *__restrict__ alpha0, double *__restrict__ beta0,
+                        double *__restrict__ dlambda_out, double *__restrict__ ddLp, double *__restrict__ dL, double *__restrict__ dLt,
+                        double *__restrict__ TdLt, double *__restrict__ csx, double *__restrict__ csy, double *__restrict__ csz,
+                        double *__restrict__ F, double *__restrict__ snap_dL /* [nn][Np] */, double *__restrict__ snap_t /* [nn][4][Np] */,
+                        double *__restrict__ self_dL /* [nn][Np] */, double *__restrict__ self_t /* [4][Np] */, int *__restrict__ self_last)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int n = v.nbi[i], nb_i = v.nb[i];
+    double gl[ISO_MAXNN], cx[ISO_MAXNN], cy[ISO_MAXNN], cz[ISO_MAXNN], dlp[ISO_MAXNN], d[ISO_MAXNN];
+    const double xi = v.xyz[i], yi = v.xyz[Np + i], zi = v.xyz[2 * Np + i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const double dx = xi - v.xyz[nj], dy = yi - v.xyz[Np + nj], dz = zi - v.xyz[2 * Np + nj];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        gl[j] = dis - L0[e];
+        cx[j] = dx / dis;
+        cy[j] = dy / dis;
+        cz[j] = dz / dis;
+        dlp[j] = dLp0[e];
+    }
+    double alpha = alpha0[i], beta[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        beta[q] = beta0[(size_t)q * Np + i];
+    const double c44 = Ce[3 * type[i] + 2];
+    const double J2_V = V * nb_i / v.nn;
+    double t0 = 0, t1 = 0, T0 = 0, T1 = 0, dl = 0.0;
+    int last_is_self = 0;
+    auto geometry = [&]() {
+        t0 = t1 = T0 = T1 = 0.0;
+        for (int j = 0; j < n; j++) {
+            const size_t e = (size_t)j * Np + i;
+            double x = gl[j];
+            x -= dlp[j];
+            x *= broken[e];
+            d[j] = x;
+            const double td = Tv[e] * x;
+            if (v.nsign[e] == 0) {
+                t0 += x;
+                T0 += td;
+            } else {
+                t1 += x;
+                T1 += td;
+            }
+        }
+    };
+    // callers in ascending particle index: neighbour slots are ascending (neighbor.c:29,40), i itself slots in between
+    bool self_done = false;
+    for (int s = 0; s <= n; s++) {
+        int caller_slot;  // -1 = i itself
+        if (!self_done && (s == n || v.nbr[(size_t)s * Np + i] > i)) {
+            caller_slot = -1;
+            self_done = true;
+            s--;  // the slot is looked at again after the self call
+        } else {
+            if (s == n)
+                break;
+            caller_slot = s;
+            if (!(broken[(size_t)s * Np + i] > LPMB_EPS))
+                continue;  // not in that particle's list (constitutive.c:694-699)
+        }
+        // (A) elastic stretches with the current plastic stretch   :703-721
+        geometry();
+        // (B) trial force / stress, return map   :729-809
+        double st[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < n; j++) {
+            const size_t e = (size_t)j * Np + i;
+            const int sg = v.nsign[e];
+            double f = 2.0 * Kn[e] * d[j] + (sg ? T1 : T0) + Tv[e] * (sg ? t1 : t0);
+            f *= broken[e];
+            F[e] = f;
+            const double pre = 0.5 / J2_V * L0[e] * f;
+            st[0] += pre * cx[j] * cx[j];
+            st[1] += pre * cy[j] * cy[j];
+            st[2] += pre * cz[j] * cz[j];
+            st[3] += pre * cy[j] * cz[j];
+            st[4] += pre * cx[j] * cz[j];
+            st[5] += pre * cx[j] * cy[j];
+        }
+        const double temp = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+        st[0] -= temp;
+        st[1] -= temp;
+        st[2] -= temp;
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            st[q] -= beta[q];
+        double seq = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            if (q < 3)
+                seq += st[q] * st[q];
+            else
+                seq += 2.0 * st[q] * st[q];
+        }
+        seq = sqrt(3.0 / 2.0 * seq);
+        dl = 0.0;
+        double yield_func = seq - (620.0 + 3300.0 * (1.0 - exp(-0.4 * alpha)));
+        if (yield_func > 0.0) {
+            double a = 0.0, b = 1.0, ya = yield_func;
+            while ((b - a) > 1e-4 /* TOLITER */) {
+                dl = (a + b) / 2.0;
+                // SY(J2_alpha + dlambda) expands, unparenthesised (lpm.h:50), to exp(-0.4 * J2_alpha + dlambda): kept
+                yield_func = seq - 1.5 * dl * (2.0 * c44 + J2_C) - (620.0 + 3300.0 * (1.0 - exp(-0.4 * alpha + dl)));
+                if (yield_func * ya < 0.0) {
+                    b = dl;
+                } else {
+                    a = dl;
+                    ya = yield_func;
+                }
+            }
+        }
+        alpha += dl;
+        double dpl[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            dpl[q] = dl * 1.5 * st[q] / seq;  // no guard for seq == 0 in the reference either (:794)
+            beta[q] += J2_C * dpl[q];
+        }
+        for (int j = 0; j < n; j++) {
+            const size_t e = (size_t)j * Np + i;
+            const double dd = L0[e] * (dpl[0] * cx[j] * cx[j] + dpl[1] * cy[j] * cy[j] + dpl[2] * cz[j] * cz[j] + 2 * dpl[3] * cy[j] * cz[j] +
+                                       2 * dpl[4] * cx[j] * cz[j] + 2 * dpl[5] * cx[j] * cy[j]);
+            ddLp[e] = dd;
+            dlp[j] += dd;
+        }
+        // (C) elastic stretches with the new plastic stretch   :815-831
+        geometry();
+        // what the caller reads in its own force pass
+        if (caller_slot < 0) {
+            for (int j = 0; j < n; j++)
+                self_dL[(size_t)j * Np + i] = d[j];
+            self_t[i] = t0;
+            self_t[Np + i] = t1;
+            self_t[2 * Np + i] = T0;
+            self_t[3 * Np + i] = T1;
+            last_is_self = 1;
+        } else {
+            snap_dL[(size_t)caller_slot * Np + i] = d[caller_slot];
+            double *q = snap_t + (size_t)caller_slot * 4 * Np + i;
+            q[0] = t0;
+            q[Np] = t1;
+            q[2 * Np] = T0;
+            q[3 * Np] = T1;
+            last_is_self = 0;
+        }
+    }
+    // what the serial loop leaves behind
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        dLp0[e] = dlp[j];
+        dL[e] = d[j];
+        csx[e] = cx[j];
+        csy[e] = cy[j];
+        csz[e] = cz[j];
+    }
+    dLt[i] = t0;
+    dLt[Np + i] = t1;
+    TdLt[i] = T0;
+    TdLt[Np + i] = T1;
+    alpha0[i] = alpha;
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        beta0[(size_t)q * Np + i] = beta[q];
+    dlambda_out[i] = dl;
+    self_last[i] = last_is_self;
+}
+
+// bond forces of ii at the moment of its own call   constitutive.c:833-857
+__global__ void __launch_bounds__(BT)
+j2iso_force_kernel(BondView v, const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ w,
+                   const double *__restrict__ broken, const double *__restrict__ snap_dL, const double *__restrict__ snap_t,
+                   const double *__restrict__ self_dL, const double *__restrict__ self_t, const int *__restrict__ self_last,
+                   const double *__restrict__ dL_prev, const double *__restrict__ dLt_prev, const double *__restrict__ TdLt_prev,
+                   const double *__restrict__ csx, const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ dL_ave,
+                   double *__restrict__ F, double *__restrict__ Pin)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const double ti[4] = {self_t[i], self_t[Np + i], self_t[2 * Np + i], self_t[3 * Np + i]};
+    const bool write_F = self_last[i] != 0;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    const int n = v.nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const int s = v.nsign[e];
+        const int mj = v.mirror[e];
+        double dL_j = 0.0, dLt_j, TdLt_j;
+        if (broken[e] > LPMB_EPS && mj >= 0) {
+            // nj was refreshed during this very call: its snapshot for caller i sits at its slot towards i
+            const double *q = snap_t + (size_t)mj * 4 * Np + nj;
+            dL_j = snap_dL[(size_t)mj * Np + nj];
+            dLt_j = q[(size_t)s * Np];
+            TdLt_j = q[(size_t)(2 + s) * Np];
+        } else {
+            // broken bond: nj holds what its latest caller below i left, or the values from before the whole call
+            int best = -2, best_slot = -1;  // -2: none yet; slot -1 = nj itself
+            if (nj < i)
+                best = nj;
+            for (int m = 0; m < v.nn; m++) {
+                const size_t em = (size_t)m * Np + nj;
+                const int q = v.nbr[em];
+                if (q != -1 && broken[em] > LPMB_EPS && q < i && q > best) {
+                    best = q;
+                    best_slot = m;
+                }
+            }
+            if (best == -2) {
+                dLt_j = dLt_prev[(size_t)s * Np + nj];
+                TdLt_j = TdLt_prev[(size_t)s * Np + nj];
+                if (mj >= 0)
+                    dL_j = dL_prev[(size_t)mj * Np + nj];
+            } else if (best_slot < 0) {
+                dLt_j = self_t[(size_t)s * Np + nj];
+                TdLt_j = self_t[(size_t)(2 + s) * Np + nj];
+                if (mj >= 0)
+                    dL_j = self_dL[(size_t)mj * Np + nj];
+            } else {
+                const double *q = snap_t + (size_t)best_slot * 4 * Np + nj;
+                dLt_j = q[(size_t)s * Np];
+                TdLt_j = q[(size_t)(2 + s) * Np];
+                dL_j = 0.0;  // the stretch of a broken bond is 0 in every snapshot (x broken)
+            }
+        }
+        const double dL_i = self_dL[e];
+        double stretch;
+        if (mj >= 0) {
+            stretch = 0.5 * (dL_i + dL_j);
+            dL_ave[e] = stretch;
+        } else {
+            stretch = dL_ave[e];
+        }
+        double f = 2.0 * Kn[e] * stretch + 0.5 * (ti[2 + s] + TdLt_j) + 0.5 * Tv[e] * (ti[s] + dLt_j);
+        f *= w[e];
+        if (write_F)
+            F[e] = f;
+        p0 += csx[e] * f;
+        p1 += csy[e] * f;
+        p2 += csz[e] * f;
+    }
+    Pin[i] = p0;
+    Pin[Np + i] = p1;
+    Pin[2 * Np + i] = p2;
+}
+
+// ---------------------------------------------------------------------------------------------
 // stress   lpm_basic.c:53-125
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BT)
@@ -976,7 +1248,7 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         Field *ce = lpmb_field(c, "Ce");
         LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
         // dilatation sums as they are before this call (see force_kernel, LAW 3)
-        if (!lpmb_field(c, "dL_total_prev")) {
+        if (!c->fields.count("dL_total_prev")) {
             LPMB_TRY(lpmb_field_alloc(c, "dL_total_prev", FK_PART, FT_F64, 2));
             LPMB_TRY(lpmb_field_alloc(c, "TdL_total_prev", FK_PART, FT_F64, 2));
         }
@@ -993,6 +1265,39 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         force_kernel<3><<<g, BT, 0, c->stream>>>(v, Kn, Tv, fptr<double>(c, "damage_D0"), dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin, broken,
                                                  fptr<double>(c, "dL_total_prev"), fptr<double>(c, "TdL_total_prev"));
         LPMB_LAUNCH_CHECK(c);
+    } else if (plmode == 5) {
+        // J2, nonlinear isotropic hardening, in-place serial semantics (constitutive.c:689-863)
+        LPMB_REQUIRE(c->params.count("J2_C"), LPMB_ERR_STATE, "J2_C not set");
+        LPMB_REQUIRE(c->nn <= ISO_MAXNN, LPMB_ERR_UNSUPPORTED, "plmode 5: more than %d neighbours per particle", ISO_MAXNN);
+        LPMB_REQUIRE(c->dim == 3, LPMB_ERR_UNSUPPORTED, "plmode 5 is a 3-D law (constitutive.c:706-708)");
+        Field *ce = lpmb_field(c, "Ce");
+        LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+        if (!c->fields.count("iso_snap_dL")) {
+            LPMB_TRY(lpmb_field_alloc(c, "iso_snap_dL", FK_BOND, FT_F64, c->nn));
+            LPMB_TRY(lpmb_field_alloc(c, "iso_snap_t", FK_PART, FT_F64, 4 * c->nn));
+            LPMB_TRY(lpmb_field_alloc(c, "iso_self_dL", FK_BOND, FT_F64, c->nn));
+            LPMB_TRY(lpmb_field_alloc(c, "iso_self_t", FK_PART, FT_F64, 4));
+            LPMB_TRY(lpmb_field_alloc(c, "iso_self_last", FK_PART, FT_I32, 1));
+            LPMB_TRY(lpmb_field_alloc(c, "dL_prev", FK_BOND, FT_F64, c->nn));
+        }
+        if (!c->fields.count("dL_total_prev")) {
+            LPMB_TRY(lpmb_field_alloc(c, "dL_total_prev", FK_PART, FT_F64, 2));
+            LPMB_TRY(lpmb_field_alloc(c, "TdL_total_prev", FK_PART, FT_F64, 2));
+        }
+        LPMB_TRY(copy_field(c, "dL_total_prev", "dL_total"));
+        LPMB_TRY(copy_field(c, "TdL_total_prev", "TdL_total"));
+        LPMB_TRY(copy_field(c, "dL_prev", "dL"));
+        j2iso_trajectory_kernel<<<g, BT, 0, c->stream>>>(
+            v, param(c, "particle_volume"), param(c, "J2_C"), (const double *)ce->d, fptr<int>(c, "type"), Kn, Tv, broken,
+            fptr<double>(c, "distance_initial"), fptr<double>(c, "dLp0"), fptr<double>(c, "J2_alpha0"), fptr<double>(c, "J2_beta0"),
+            fptr<double>(c, "J2_dlambda"), fptr<double>(c, "ddLp"), dL, dLt, TdLt, csx, csy, csz, F, fptr<double>(c, "iso_snap_dL"),
+            fptr<double>(c, "iso_snap_t"), fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"), fptr<int>(c, "iso_self_last"));
+        LPMB_LAUNCH_CHECK(c);
+        j2iso_force_kernel<<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, broken, fptr<double>(c, "iso_snap_dL"), fptr<double>(c, "iso_snap_t"),
+                                                     fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"), fptr<int>(c, "iso_self_last"),
+                                                     fptr<double>(c, "dL_prev"), fptr<double>(c, "dL_total_prev"), fptr<double>(c, "TdL_total_prev"),
+                                                     csx, csy, csz, dL_ave, F, Pin);
+        LPMB_LAUNCH_CHECK(c);
     } else if (plmode == 1) {
         // crystal plasticity (constitutive.c:866-1396): geometry -> Miehe return map -> geometry -> averaged force
         LPMB_TRY(run_geometry(c, v, "dLp0"));
@@ -1001,7 +1306,7 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
         LPMB_LAUNCH_CHECK(c);
     } else {
-        lpmb_set_error("computeBondForceGeneral: plmode %d is not built (0, 1, 3, 4, 6 are)", plmode);
+        lpmb_set_error("computeBondForceGeneral: plmode %d is not a law of the reference (0, 1, 3, 4, 5, 6 are)", plmode);
         return LPMB_ERR_UNSUPPORTED;
     }
     LPMB_TRY(lpmb_compute_stress(c));

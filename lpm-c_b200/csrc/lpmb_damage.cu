@@ -109,6 +109,80 @@ nonlocal_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__r
         atomicAdd(count, k);
 }
 
+// ---- local bond-wise ductile damage (plmode 5), updateDuctileDamageBwiseLocal, constitutive.c:1607-1695 ------------
+// (1) damage_local += (1 + A triax) dlambda below the threshold (clamped to 1 above it)
+__global__ void __launch_bounds__(DT)
+local_damage_kernel(int N, double thr, double Ac, const double *__restrict__ triax, const double *__restrict__ dlambda, double *__restrict__ dloc)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double f = (1.0 + Ac * triax[i]);
+    double d = dloc[i];
+    if (f > 0.0 && d <= thr)
+        d += f * dlambda[i];
+    else if (d > 1.0)
+        d = 1.0;
+    dloc[i] = d;
+}
+
+// (2) per bond D = (d_i + d_j)/2; an intact bond beyond the threshold breaks (the serial loop marks both directions
+// when it meets the first one, so a bond is counted and logged once, from its lower-numbered end); nb is recounted
+__global__ void __launch_bounds__(DT)
+local_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, double thr, const double *__restrict__ dloc,
+                   double *__restrict__ broken, double *__restrict__ dD0, int *__restrict__ nb, signed char *__restrict__ newly,
+                   int *__restrict__ count)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double di = dloc[i];
+    const int n = nbi[i];
+    int k = 0, left = n;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = nbr[e];
+        double D = 0.5 * (di + dloc[nj]);
+        double b = broken[e];
+        signed char nw = 0;
+        if (D > thr && b > LPMB_EPS) {
+            D = 1.0;
+            b = 0.0;
+            if (i < nj) {
+                nw = 1;
+                k++;
+            }
+        }
+        if (b <= LPMB_EPS)
+            left--;
+        broken[e] = b;
+        dD0[e] = D;
+        newly[e] = nw;
+    }
+    nb[i] = left;
+    if (k)
+        atomicAdd(count, k);
+}
+
+// (3) broken bonds and bonds of fully detached particles carry D = 1; damage_w = 1 - D
+__global__ void __launch_bounds__(DT)
+local_finish_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, const int *__restrict__ nb,
+                    const double *__restrict__ broken, double *__restrict__ dD0, double *__restrict__ w)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const int n = nbi[i], nbi_cur = nb[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        double D = dD0[e];
+        if (fabs(broken[e]) < LPMB_EPS || nbi_cur == 0 || nb[nbr[e]] == 0)
+            D = 1.0;
+        dD0[e] = D;
+        w[e] = 1.0 - D;
+    }
+}
+
 // brittle: candidates with dL/L0 >= critical_bstrain, appended to a device list (order restored on the host)
 __global__ void __launch_bounds__(DT)
 brittle_candidates_kernel(int N, int Np, int nn, const int *__restrict__ nbi, const double *__restrict__ dL, const double *__restrict__ L0,
@@ -299,9 +373,43 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
         cudaFree(keys);
         cudaFree(strain);
     } else if (plmode == 5) {
-        cudaFree(d_count);
-        lpmb_set_error("updateDamageGeneral: plmode 5 (updateDuctileDamageBwiseLocal) is not built (0 and 6 are)");
-        return LPMB_ERR_UNSUPPORTED;
+        if (c->world != 1 || !c->params.count("damage_threshold") || !c->params.count("damagec_A")) {
+            cudaFree(d_count);
+            lpmb_set_error(c->world != 1 ? "updateDuctileDamageBwiseLocal is single-GPU only" : "damage_threshold / damagec_A not set");
+            return c->world != 1 ? LPMB_ERR_UNSUPPORTED : LPMB_ERR_STATE;
+        }
+        const double thr = param(c, "damage_threshold");
+        signed char *newly = nullptr;
+        LPMB_CUDA(cudaMalloc(&newly, (size_t)nn * Np));
+        LPMB_CUDA(cudaMemsetAsync(newly, 0, (size_t)nn * Np, c->stream));
+        local_damage_kernel<<<g, DT, 0, c->stream>>>(N, thr, param(c, "damagec_A"), fptr<double>(c, "J2_triaxiality"), fptr<double>(c, "J2_dlambda"),
+                                                     fptr<double>(c, "damage_local0"));
+        LPMB_LAUNCH_CHECK(c);
+        local_break_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, thr, fptr<double>(c, "damage_local0"), broken, dD0, fptr<int>(c, "nb"), newly,
+                                                    d_count);
+        LPMB_LAUNCH_CHECK(c);
+        local_finish_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, fptr<int>(c, "nb"), broken, dD0, w);
+        LPMB_LAUNCH_CHECK(c);
+        int k = 0;
+        LPMB_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        *broken_out = k;
+        if (k > 0 && pairs && max_pairs > 0) {
+            // reference logging order: i ascending, then slot j ascending (constitutive.c:1644-1676)
+            std::vector<signed char> hn((size_t)nn * Np);
+            std::vector<int> hnbr((size_t)nn * Np);
+            LPMB_CUDA(cudaMemcpy(hn.data(), newly, hn.size(), cudaMemcpyDeviceToHost));
+            LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            int t = 0;
+            for (int i = 0; i < N && t < max_pairs; i++)
+                for (int j = 0; j < nn && t < max_pairs; j++)
+                    if (hn[(size_t)j * Np + i]) {
+                        pairs[2 * t] = i;
+                        pairs[2 * t + 1] = hnbr[(size_t)j * Np + i];
+                        t++;
+                    }
+        }
+        cudaFree(newly);
     }
     // any other plmode: the reference's dispatcher does nothing and returns 0 (constitutive.c:149-164)
     cudaFree(d_count);

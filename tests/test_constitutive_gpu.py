@@ -202,3 +202,57 @@ def test_compute_strain_bit_exact(ctx, golden, step):
     ctx.compute_strain()
     assert_same(ctx.get_field("strain_tensor"), golden[f"{step}.strain.strain_tensor"], "strain_tensor")
     assert np.abs(golden[f"{step}.strain.strain_tensor"]).max() > 1e-4
+
+
+def _j2iso_ctx(lpm, g, pre):
+    c = make_ctx(lpm, g)
+    for n in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "bond_stress", "damage_broken", "damage_w", "dL_total", "TdL_total",
+              "stress_tensor", "J2_dlambda", "J2_stresseq", "J2_stressm", "J2_triaxiality", "xyz", "Pin", "pl_flag", "nb"):
+        c.set_field(n, g[f"{pre}.{n}"])
+    put_slots(c, "dLp", g[f"{pre}.dLp"])
+    put_slots(c, "damage_D", g[f"{pre}.damage_D"])
+    put_slots(c, "J2_alpha", g[f"{pre}.J2_alpha"])
+    put_slots(c, "J2_beta", g[f"{pre}.J2_beta"])
+    put_slots(c, "J2_beta_eq", g[f"{pre}.J2_beta_eq"])
+    put_slots(c, "damage_local", g[f"{pre}.damage_local"])
+    return c
+
+
+@pytest.mark.parametrize("tag", ["s1.n0", "s1.n1", "s2.n0", "s3.n0", "s3.n1"])
+def test_j2_nonlinear_iso_law_serial_semantics(lpm, tag):
+    """computeBondForceGeneral(5, .) = computeBondForceJ2nonlinearIso (constitutive.c:689-863): the law
+    updates slot [0] in place 1 + nb times per particle in the order of the serial loop; the per-particle trajectory
+    kernel reproduces that exactly (tests/golden/sc6_j2iso.npz, single-threaded reference).  Step 3 has broken bonds.
+    exp() of SY(x) is the only non-IEEE operation: it only steers bisection decisions, so results stay bit-exact
+    unless a decision sits within an ulp of a tie."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "sc6_j2iso.npz")
+    c = _j2iso_ctx(lpm, g, f"{tag}.pre")
+    c.bond_force(5, 1)
+    bf = f"{tag}.bf"
+    for n in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "bond_stress", "dL_total", "TdL_total", "stress_tensor", "J2_dlambda",
+              "J2_stresseq", "J2_stressm", "J2_triaxiality", "Pin"):
+        assert_same(c.get_field(n), g[f"{bf}.{n}"], n)
+    assert_same(get_slots(c, "dLp", 3), g[f"{bf}.dLp"], "dLp")
+    assert_same(get_slots(c, "J2_alpha", 3), g[f"{bf}.J2_alpha"], "J2_alpha")
+    assert_same(get_slots(c, "J2_beta", 3), g[f"{bf}.J2_beta"], "J2_beta")
+    if tag.startswith("s3"):
+        assert (g[f"{tag}.pre.nb"] < g["setup.nb_initial"]).any()
+    c.close()
+
+
+@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
+def test_local_bondwise_damage_bit_exact(lpm, step):
+    """updateDamageGeneral(., ., 5) = updateDuctileDamageBwiseLocal (constitutive.c:1607-1695); step 2 breaks 18 bonds"""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "sc6_j2iso.npz")
+    c = _j2iso_ctx(lpm, g, f"{step}.dam.pre")
+    broken, pairs = c.update_damage(5)
+    assert broken == int(g[f"{step}.dam.broken"][0])
+    for n in ("damage_broken", "damage_w", "nb"):
+        assert_same(c.get_field(n), g[f"{step}.dam.{n}"], n)
+    assert_same(get_slots(c, "damage_D", 2), g[f"{step}.dam.damage_D"], "damage_D")
+    assert_same(get_slots(c, "damage_local", 2), g[f"{step}.dam.damage_local"], "damage_local")
+    if step == "s2":
+        assert broken == 18 and len(pairs) == 18 and all(i < j for i, j in pairs)
+    c.close()

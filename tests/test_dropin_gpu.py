@@ -173,3 +173,16 @@ def test_dropin_replays_j2_energy_golden_case(tmp_path):
         assert np.abs(new[f"{t}.bf.J2_dlambda"] - old[f"{t}.bf.J2_dlambda"]).max() <= 2.0 ** -13
         for k in ("F", "Pin", "dLp", "J2_alpha", "J2_beta_eq", "stress_tensor"):
             assert _rel(new[f"{t}.bf.{k}"], old[f"{t}.bf.{k}"]) <= 1e-7, (t, k)
+
+
+def test_dropin_replays_j2_iso_golden_case(tmp_path):
+    """tests/golden/sc6_j2iso.npz (plmode 5) through liblpmc_dropin.so, step 1 (later steps depend on
+    a multiplier field the generator pokes into host memory, which the device-authoritative drop-in does not see).
+    Inputs of the first call come from a GPU CG solve (1e-10), the return maps are bisections quantised to 2^-14."""
+    new = _regen("make_golden_j2iso.py", tmp_path, "j2iso.npz")
+    old = np.load(GOLD / "sc6_j2iso.npz")
+    for t in ("s1.n0", "s1.n1"):
+        assert _rel(new[f"{t}.pre.xyz"], old[f"{t}.pre.xyz"]) <= 1e-9
+        for k in ("F", "Pin", "dL", "stress_tensor"):
+            assert _rel(new[f"{t}.bf.{k}"], old[f"{t}.bf.{k}"]) <= 1e-6, (t, k)
+    assert int(new["s1.dam.broken"][0]) == 0

@@ -97,6 +97,30 @@ def test_j2_energy_golden_matches_reference_build(tmp_path):
     assert (old["s2.n1.bf.J2_dlambda"] > 0).sum() > 50
 
 
+def test_j2_iso_golden_matches_reference_build(tmp_path):
+    """tests/golden/sc6_j2iso.npz (plmode 5 + local bond-wise damage) regenerates bit-identically"""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    import os, subprocess, sys
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    out = tmp_path / "j2iso.npz"
+    subprocess.run([sys.executable, str(gold / "make_golden_j2iso.py")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, LPMB_GOLDEN_OUT=str(out)))
+    new, old = np.load(out), np.load(gold / "sc6_j2iso.npz")
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert np.array_equal(new[k], old[k]), k
+    # the law is active inside the call although its state is wiped afterwards: the elastic stretch it leaves in dL
+    # differs from the purely geometric one; 18 bonds break in step 2
+    x, nbr, L0 = old["s1.n0.bf.xyz"], old["setup.neighbors"], old["setup.distance_initial"]
+    geo = np.linalg.norm(x[:, None, :] - x[np.maximum(nbr, 0)], axis=2) - L0
+    assert np.abs(np.where(nbr >= 0, old["s1.n0.bf.dL"] - geo, 0.0)).max() > 1e-3
+    assert np.abs(old["s1.n0.bf.dLp"]).max() == 0.0           # switchStateV(2) restored the never-written slot [2]
+    assert int(old["s2.dam.broken"][0]) == 18
+
+
 def test_golden_internal_consistency(golden):
     g = golden
     assert g["setup.xyz"].shape == (216, 3)
