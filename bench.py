@@ -296,7 +296,35 @@ def gpu_arm(args):
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+class _QuietStdout:
+    """The reference's solverCG() printf()s a line per solve (solver.c:257): keep the C-level stdout away from this
+    process's stdout, which carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        os.close(self._null)
+        return False
+
+
 def cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: int = 1) -> dict:
+    with _QuietStdout():
+        return _cpu_reference_sample(args, n_full, steps, warmup)
+
+
+def _cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: int = 1) -> dict:
     """The reference's OWN functions (oracle/_ref = its unmodified sources + open MKL stand-in, NOT Intel MKL)
     timed on the host cores on a bounded sample of the workload: the same physics / BCs / Newton iteration on an
     m^3 block, extrapolated to n_full^3 with the per-particle cost and the measured CG-iterations ~ n law."""
