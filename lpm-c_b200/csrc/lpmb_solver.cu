@@ -64,6 +64,7 @@ static int build_pattern(lpmb_ctx *c, const int *d_conn)
     cudaFree(K.sptr); cudaFree(K.col); cudaFree(K.val); cudaFree(K.nbc); cudaFree(K.k0); cudaFree(K.kp);
     K.sptr = nullptr; K.col = nullptr; K.val = nullptr; K.nbc = nullptr; K.k0 = nullptr; K.kp = nullptr;
     K.pattern_ready = K.values_ready = false;
+    lpmb_brick_release(c);  // a brick mirror of the previous pattern is void (re-enable after the new topology)
     K.nslices = Np / 32;
     LPMB_CUDA(cudaMalloc(&K.nbc, (size_t)Np * sizeof(int)));
     LPMB_CUDA(cudaMalloc(&K.k0, (size_t)Np * sizeof(int)));

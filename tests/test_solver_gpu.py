@@ -211,3 +211,32 @@ def test_brick_rejects_unsupported_lattice(lpm, golden):
     x = np.ones(3 * N)
     assert np.isfinite(c.spmv(x)).all()   # full format still in use
     c.close()
+
+
+def test_brick_spmv_on_carved_lattice(lpm):
+    """irregular specimen (notch + hole carved out of an SC block, like the reference's CT geometry): topology from
+    the O(N) device builder, bricks partially filled, rows with short conn lists"""
+    lat = lpm.lattice.sc_block(19, 14, 11, h=0.5)
+    xyz = lat["xyz"]
+    keep = ~((xyz[:, 0] < 4.0) & (np.abs(xyz[:, 1] - 3.25) < 0.4))                      # notch through the thickness
+    keep &= ((xyz[:, 0] - 6.5) ** 2 + (xyz[:, 1] - 4.0) ** 2) > 1.2 ** 2                # pin hole
+    xyz = np.ascontiguousarray(xyz[keep])
+    N = xyz.shape[0]
+    c = lpm.Context(N, 3, 2, 18, 61)
+    c.set_params(radius=0.25)
+    c.set_field("xyz", xyz)
+    c.set_field("xyz_initial", xyz)
+    c.build_topology(0.5, np.sqrt(2.0) * 0.5)
+    c.fill_test_pattern()
+    rng = np.random.default_rng(20240607)
+    x = rng.standard_normal(3 * N)
+    y0 = c.spmv(x)
+    c.enable_bricks(True)
+    y1 = c.spmv(x)
+    assert np.abs(y0 - y1).max() <= 1e-13 * np.abs(y0).max()
+    b = rng.standard_normal(3 * N)
+    d1, it1, ok1 = c.solve_cg(b)
+    c.enable_bricks(False)
+    d0, it0, ok0 = c.solve_cg(b)
+    assert ok0 and ok1 and abs(it0 - it1) <= 1 and np.linalg.norm(d0 - d1) <= 1e-9 * np.linalg.norm(d0)
+    c.close()
