@@ -276,7 +276,9 @@ def gpu_arm(args):
                    "lattice_n": n, "particles": N, "dof": nd, "cg_iterations_per_step": iters,
                    "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
                    "l2": "inputs larger than L2 (matrix %.1f GB)" % (c.spmv_bytes_stored() / 1e9),
-                   "setup_s": info["setup_s"], "fd_assembly_s": info["fd_assembly_s"], "parallelism": "1 GPU"},
+                   "setup_s": info["setup_s"], "fd_assembly_s": info["fd_assembly_s"], "parallelism": "1 GPU",
+                   "spmv_kernel": "brick-blocked symmetric (each block of the symmetric tangent streamed once)" if info["bricks"]
+                                  else "full-format SELL-32 (both triangles)"},
         "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved,
                      "full_format_equivalent_gbs": full_bytes / (spmv_avg_ms * 1e-3) / 1e9,
                      "full_format_bytes_per_launch": full_bytes,
