@@ -566,6 +566,8 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
         LPMB_CUDA(cudaMemset(*v, 0, (size_t)3 * B.P * sizeof(double)));
     }
     B.ic = ic;
+    // 216.6 KB of dynamic shared memory per CTA: opt in on this context's device
+    LPMB_CUDA(cudaFuncSetAttribute(brick_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
     B.pattern_ready = true;
     return LPMB_OK;
 }
@@ -705,11 +707,6 @@ int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const dou
                     const PeerWait &halo_wait)
 {
     BrickMatrix &B = g_bricks[c];
-    static bool attr_set = false;
-    if (!attr_set) {
-        LPMB_CUDA(cudaFuncSetAttribute(brick_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
-        attr_set = true;
-    }
     const int grid = B.nbricks < c->sm_count ? B.nbricks : c->sm_count;
     brick_spmv_kernel<<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, x, B.ypart, B.stage,
                                                                   dot ? scal : nullptr, halo_wait);
