@@ -15,7 +15,13 @@
 // only the star members whose bond list contains c -- found in O(1) from a 64-bit "affected" mask per
 // star member -- and takes the cached unperturbed sums otherwise.  Unaffected quantities are pure
 // functions of unchanged inputs, so the result equals the reference's brute-force re-evaluation of
-// all 19x18 bonds bit for bit, at ~1/100 of its sqrt/div count.  The 3x3 (2x2) blocks A_i[c] go to
+// all 19x18 bonds bit for bit, at ~1/100 of its sqrt/div count.  To keep warps convergent the work is split in two
+// phases: (1) every affected (neighbour a, conn q, coordinate r) triple is a task -- tasks of one neighbour are padded
+// to a multiple of the warp size, so a warp walks one bond list with one skip pattern -- whose perturbed shell sums go
+// to a compact shared-memory table; (2) one thread per perturbation assembles Pin from the table (O(1) lookup by the
+// rank of q in the neighbour's affected mask); only the perturbations that move the owner's own bonds (conn members
+// that are the owner or its neighbours: renumbered to the first two warps) recompute geometry there.
+// The 3x3 (2x2) blocks A_i[c] go to
 // row i of the SELL matrix; a second kernel symmetrises pairs in place (no atomics: every (i,j>i)
 // pair is owned by one thread).
 #include "lpmb_internal.cuh"
@@ -31,11 +37,18 @@ struct StarSmem {
     double L0[NN + 1][NN], dLp[NN + 1][NN], brk[NN + 1][NN], Tv[NN + 1][NN];
     signed char sg[NN + 1][NN];
     double bt[NN + 1][2], bT[NN + 1][2];  // unperturbed dL_total / TdL_total
-    double bdL[NN], bcs[NN][3];           // unperturbed owner bond stretch / direction cosines
+    double bd[NN + 1][NN];                // unperturbed bond stretch of every member (bd[0] = the owner's)
+    double bcs[NN][3];                    // unperturbed owner direction cosines
+    unsigned char cq[NN + 1][NN];         // conn position of member a's neighbour mm (255: not a conn member of i)
+    unsigned char selfq[NN + 1];          // conn position of the member itself
     double Kn[NN];
     int conn[64];
     int nbc;
     double base_pin[3];
+    // phase-1 table: perturbed shell sums (shell of the owner's bond to a) of neighbour a for the rank-th set bit of amask[a]
+    double ptj[NN * (NN + 1) * D], pTj[NN * (NN + 1) * D];
+    int toff[NN + 2];
+    unsigned char qord[64];               // perturbation order: conn members that move the owner's bonds first
 };
 
 template <int D, int NN, int T>
@@ -65,8 +78,10 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
     }
     if (tid < 64)
         S.conn[tid] = (tid < nbc_g[i]) ? col[(krow + tid) * 32 + lane_i] : -1;
-    if (tid < NN + 1)
+    if (tid < NN + 1) {
         S.amask[tid] = 0ull;
+        S.selfq[tid] = 255;
+    }
     __syncthreads();
     if (tid < NN + 1) {
         const int pid = S.sid[tid];
@@ -98,6 +113,7 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
                 S.Kn[m] = Kng[g];
         }
         S.nid[a][m] = nj;
+        S.cq[a][m] = 255;
         // affected mask: position of nj (and of the member itself) in conn[i]
         if (nj >= 0) {
             int lo = 0, hi = nbc - 1;
@@ -105,6 +121,7 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
                 const int mid = (lo + hi) >> 1, v = S.conn[mid];
                 if (v == nj) {
                     atomicOr(&S.amask[a], 1ull << mid);
+                    S.cq[a][m] = (unsigned char)mid;
                     break;
                 }
                 if (v < nj)
@@ -119,6 +136,7 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
                 const int mid = (lo + hi) >> 1, v = S.conn[mid];
                 if (v == pid) {
                     atomicOr(&S.amask[a], 1ull << mid);
+                    S.selfq[a] = (unsigned char)mid;
                     break;
                 }
                 if (v < pid)
@@ -129,16 +147,43 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
         }
     }
     __syncthreads();
-    // ---- unperturbed geometry of every star member (constitutive.c:241-260) ----
+    // ---- unperturbed geometry of every star member (constitutive.c:241-260): one thread per bond, then the
+    //      shell sums by one thread per member in the reference's order ----
+    for (int e = tid; e < (NN + 1) * NN; e += T) {
+        const int a = e / NN, m = e % NN;
+        if (S.sid[a] < 0 || m >= S.nbi[a])
+            continue;
+        const double dx = S.pos[a][0] - S.npos[a][m][0], dy = S.pos[a][1] - S.npos[a][m][1], dz = S.pos[a][2] - S.npos[a][m][2];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        double d = dis - S.L0[a][m];
+        d -= S.dLp[a][m];
+        d *= S.brk[a][m];
+        S.bd[a][m] = d;
+        if (a == 0) {
+            S.bcs[m][0] = dx / dis;
+            S.bcs[m][1] = dy / dis;
+            S.bcs[m][2] = dz / dis;
+        }
+    }
+    if (tid == 0) {
+        int acc = 0;
+        for (int a = 1; a <= S.nbi[0]; a++) {
+            S.toff[a] = acc;
+            acc += __popcll(S.amask[a]);
+        }
+    }
+    if (tid < nbc) {
+        // perturbation order: conn members in the owner's own mask (owner + its neighbours) first
+        const unsigned long long own = S.amask[0], valid = nbc >= 64 ? ~0ull : ((1ull << nbc) - 1ull), bt = 1ull << tid;
+        const int pos = (own & bt) ? __popcll(own & (bt - 1ull)) : __popcll(own & valid) + __popcll(~own & valid & (bt - 1ull));
+        S.qord[pos] = (unsigned char)tid;
+    }
+    __syncthreads();
     if (tid < NN + 1 && S.sid[tid] >= 0) {
         const int a = tid;
         double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
         for (int m = 0; m < S.nbi[a]; m++) {
-            const double dx = S.pos[a][0] - S.npos[a][m][0], dy = S.pos[a][1] - S.npos[a][m][1], dz = S.pos[a][2] - S.npos[a][m][2];
-            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
-            double d = dis - S.L0[a][m];
-            d -= S.dLp[a][m];
-            d *= S.brk[a][m];
+            const double d = S.bd[a][m];
             const double td = S.Tv[a][m] * d;
             if (S.sg[a][m] == 0) {
                 t0 += d;
@@ -147,12 +192,6 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
                 t1 += d;
                 T1 += td;
             }
-            if (a == 0) {
-                S.bdL[m] = d;
-                S.bcs[m][0] = dx / dis;
-                S.bcs[m][1] = dy / dis;
-                S.bcs[m][2] = dz / dis;
-            }
         }
         S.bt[a][0] = t0;
         S.bt[a][1] = t1;
@@ -160,49 +199,158 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
         S.bT[a][1] = T1;
     }
     __syncthreads();
-    // ---- base internal force (constitutive.c:264-279) ----
-    if (tid == 0) {
-        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-        for (int m = 0; m < S.nbi[0]; m++) {
-            const int s = S.sg[0][m];
-            double f = 2.0 * S.Kn[m] * S.bdL[m] + 0.5 * (S.bT[0][s] + S.bT[m + 1][s]) + 0.5 * S.Tv[0][m] * (S.bt[0][s] + S.bt[m + 1][s]);
-            f *= S.brk[0][m];
-            p0 += S.bcs[m][0] * f;
-            p1 += S.bcs[m][1] * f;
-            p2 += S.bcs[m][2] * f;
+
+    // ---- phase 1: perturbed shell sums of the neighbours (only the shell of the owner's bond to a is needed) ----
+    // A perturbation of c changes, in neighbour a's list, either every bond (c == a: "self" tasks, one warp pair) or
+    // exactly one bond (c is a neighbour of a: "one-bond" tasks); unchanged stretches are bit-identical to the
+    // unperturbed ones, so a one-bond task evaluates one bond and re-adds the cached stretches in the reference's
+    // order.  Task slots of one neighbour are padded to TPA, so a warp works on one neighbour.
+    constexpr int TPA = (D == 3) ? 64 : 32;  // >= NN * D
+    const int n0 = S.nbi[0];
+    for (int ts = tid; ts < (n0 + 1) * TPA; ts += T) {
+        if (ts >= n0 * TPA) {
+            // self tasks (a, r), and -- on a thread that has nothing else to do -- the base internal force
+            const int kk = ts - n0 * TPA;
+            if (kk == TPA - 1) {
+                // base internal force (constitutive.c:264-279)
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+                for (int m = 0; m < n0; m++) {
+                    const int s = S.sg[0][m];
+                    double f = 2.0 * S.Kn[m] * S.bd[0][m] + 0.5 * (S.bT[0][s] + S.bT[m + 1][s]) + 0.5 * S.Tv[0][m] * (S.bt[0][s] + S.bt[m + 1][s]);
+                    f *= S.brk[0][m];
+                    q0 += S.bcs[m][0] * f;
+                    q1 += S.bcs[m][1] * f;
+                    q2 += S.bcs[m][2] * f;
+                }
+                S.base_pin[0] = q0;
+                S.base_pin[1] = q1;
+                S.base_pin[2] = q2;
+            }
+            if (kk >= n0 * D)
+                continue;
+            const int a = kk / D + 1, r = kk % D;
+            if (S.selfq[a] == 255)
+                continue;  // (cannot happen for conn built by neighbor.c: every neighbour is a conn member)
+            const int s = S.sg[0][a - 1];
+            double apos[3] = {S.pos[a][0], S.pos[a][1], S.pos[a][2]};
+            apos[r] = apos[r] + h;
+            double t = 0, TT = 0;
+            const int na = S.nbi[a];
+            for (int mm = 0; mm < na; mm++) {
+                if (S.sg[a][mm] != s)
+                    continue;
+                const double dx = apos[0] - S.npos[a][mm][0], dy = apos[1] - S.npos[a][mm][1], dz = apos[2] - S.npos[a][mm][2];
+                const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+                double d = dis - S.L0[a][mm];
+                d -= S.dLp[a][mm];
+                d *= S.brk[a][mm];
+                t += d;
+                TT += S.Tv[a][mm] * d;
+            }
+            const unsigned long long bq = 1ull << S.selfq[a];
+            const int idx = (S.toff[a] + __popcll(S.amask[a] & (bq - 1ull))) * D + r;
+            S.ptj[idx] = t;
+            S.pTj[idx] = TT;
+            continue;
         }
-        S.base_pin[0] = p0;
-        S.base_pin[1] = p1;
-        S.base_pin[2] = p2;
+        // one-bond tasks (a, mm, r)
+        const int a = ts / TPA + 1, kk = ts % TPA;
+        const int na = S.nbi[a];
+        if (kk >= na * D)
+            continue;
+        const int mm = kk / D, r = kk % D;
+        const int qc = S.cq[a][mm];
+        if (qc == 255)
+            continue;  // that neighbour of a is not a conn member of i: never perturbed
+        const int s = S.sg[0][a - 1];
+        double t, TT;
+        if (S.sg[a][mm] != s) {
+            t = S.bt[a][s];  // the moved bond is in the other shell: these sums do not change
+            TT = S.bT[a][s];
+        } else {
+            double np[3] = {S.npos[a][mm][0], S.npos[a][mm][1], S.npos[a][mm][2]};
+            np[r] = np[r] + h;
+            const double dx = S.pos[a][0] - np[0], dy = S.pos[a][1] - np[1], dz = S.pos[a][2] - np[2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            double dn = dis - S.L0[a][mm];
+            dn -= S.dLp[a][mm];
+            dn *= S.brk[a][mm];
+            t = 0;
+            TT = 0;
+            for (int m2 = 0; m2 < na; m2++) {
+                if (S.sg[a][m2] != s)
+                    continue;
+                const double d = m2 == mm ? dn : S.bd[a][m2];
+                t += d;
+                TT += S.Tv[a][m2] * d;
+            }
+        }
+        const unsigned long long bq = 1ull << qc;
+        const int idx = (S.toff[a] + __popcll(S.amask[a] & (bq - 1ull))) * D + r;
+        S.ptj[idx] = t;
+        S.pTj[idx] = TT;
     }
     __syncthreads();
 
-    // ---- one perturbation per thread ----
+    // ---- phase 2: one perturbation per thread ----
     const int p = tid;
     if (p >= D * nbc)
         return;
-    const int q = p / D, r = p % D;
+    const int q = S.qord[p / D], r = p % D;
     const int c = S.conn[q];
     const unsigned long long bit = 1ull << q;
-    const int n0 = S.nbi[0];
 
-    // owner sums
+    // owner: the perturbation moves all of its bonds (c == i), one of them (c is a neighbour) or none
     double ti[2], Ti[2];
+    double od[NN], ocx[NN], ocy[NN], ocz[NN];  // c == i only
+    double dn = 0.0, ncx = 0.0, ncy = 0.0, ncz = 0.0;
+    int mstar = -1;
     const bool own_aff = (S.amask[0] & bit) != 0ull;
-    double opos[3] = {S.pos[0][0], S.pos[0][1], S.pos[0][2]};
-    if (c == i)
+    const bool own_all = c == i;
+    if (own_all) {
+        double opos[3] = {S.pos[0][0], S.pos[0][1], S.pos[0][2]};
         opos[r] = opos[r] + h;
-    if (own_aff) {
         double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
         for (int m = 0; m < n0; m++) {
-            double np[3] = {S.npos[0][m][0], S.npos[0][m][1], S.npos[0][m][2]};
-            if (S.nid[0][m] == c)
-                np[r] = np[r] + h;
-            const double dx = opos[0] - np[0], dy = opos[1] - np[1], dz = opos[2] - np[2];
+            const double dx = opos[0] - S.npos[0][m][0], dy = opos[1] - S.npos[0][m][1], dz = opos[2] - S.npos[0][m][2];
             const double dis = sqrt(dx * dx + dy * dy + dz * dz);
             double d = dis - S.L0[0][m];
             d -= S.dLp[0][m];
             d *= S.brk[0][m];
+            const double td = S.Tv[0][m] * d;
+            if (S.sg[0][m] == 0) {
+                t0 += d;
+                T0 += td;
+            } else {
+                t1 += d;
+                T1 += td;
+            }
+            od[m] = d;
+            ocx[m] = dx / dis;
+            ocy[m] = dy / dis;
+            ocz[m] = dz / dis;
+        }
+        ti[0] = t0;
+        ti[1] = t1;
+        Ti[0] = T0;
+        Ti[1] = T1;
+    } else if (own_aff) {
+        for (int m = 0; m < n0; m++)
+            if (S.nid[0][m] == c)
+                mstar = m;
+        double np[3] = {S.npos[0][mstar][0], S.npos[0][mstar][1], S.npos[0][mstar][2]};
+        np[r] = np[r] + h;
+        const double dx = S.pos[0][0] - np[0], dy = S.pos[0][1] - np[1], dz = S.pos[0][2] - np[2];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        dn = dis - S.L0[0][mstar];
+        dn -= S.dLp[0][mstar];
+        dn *= S.brk[0][mstar];
+        ncx = dx / dis;
+        ncy = dy / dis;
+        ncz = dz / dis;
+        double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+        for (int m = 0; m < n0; m++) {
+            const double d = m == mstar ? dn : S.bd[0][m];
             const double td = S.Tv[0][m] * d;
             if (S.sg[0][m] == 0) {
                 t0 += d;
@@ -223,55 +371,35 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
         Ti[1] = S.bT[0][1];
     }
 
-    const bool last = (p == D * nbc - 1) && (F_side != nullptr);
+    const bool last = (q == nbc - 1) && (r == D - 1) && (F_side != nullptr);
     double p0 = 0.0, p1 = 0.0, p2 = 0.0;
     for (int m = 0; m < n0; m++) {
         const int a = m + 1;
         const int s = S.sg[0][m];
-        // neighbour's shell-s sums
+        // neighbour's shell-s sums: from the phase-1 table if the perturbation touches it
         double tj, Tj;
         if (S.amask[a] & bit) {
-            double apos[3] = {S.pos[a][0], S.pos[a][1], S.pos[a][2]};
-            if (S.sid[a] == c)
-                apos[r] = apos[r] + h;
-            double t = 0, TT = 0;
-            const int na = S.nbi[a];
-            for (int mm = 0; mm < na; mm++) {
-                if (S.sg[a][mm] != s)
-                    continue;
-                double np[3] = {S.npos[a][mm][0], S.npos[a][mm][1], S.npos[a][mm][2]};
-                if (S.nid[a][mm] == c)
-                    np[r] = np[r] + h;
-                const double dx = apos[0] - np[0], dy = apos[1] - np[1], dz = apos[2] - np[2];
-                const double dis = sqrt(dx * dx + dy * dy + dz * dz);
-                double d = dis - S.L0[a][mm];
-                d -= S.dLp[a][mm];
-                d *= S.brk[a][mm];
-                t += d;
-                TT += S.Tv[a][mm] * d;
-            }
-            tj = t;
-            Tj = TT;
+            const int idx = (S.toff[a] + __popcll(S.amask[a] & (bit - 1ull))) * D + r;
+            tj = S.ptj[idx];
+            Tj = S.pTj[idx];
         } else {
             tj = S.bt[a][s];
             Tj = S.bT[a][s];
         }
         // owner's bond m
         double d, cx, cy, cz;
-        if (own_aff) {
-            double np[3] = {S.npos[0][m][0], S.npos[0][m][1], S.npos[0][m][2]};
-            if (S.nid[0][m] == c)
-                np[r] = np[r] + h;
-            const double dx = opos[0] - np[0], dy = opos[1] - np[1], dz = opos[2] - np[2];
-            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
-            d = dis - S.L0[0][m];
-            d -= S.dLp[0][m];
-            d *= S.brk[0][m];
-            cx = dx / dis;
-            cy = dy / dis;
-            cz = dz / dis;
+        if (own_all) {
+            d = od[m];
+            cx = ocx[m];
+            cy = ocy[m];
+            cz = ocz[m];
+        } else if (m == mstar) {
+            d = dn;
+            cx = ncx;
+            cy = ncy;
+            cz = ncz;
         } else {
-            d = S.bdL[m];
+            d = S.bd[0][m];
             cx = S.bcs[m][0];
             cy = S.bcs[m][1];
             cz = S.bcs[m][2];
