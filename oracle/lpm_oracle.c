@@ -5,7 +5,9 @@
  * never linked, imported or executed by the product path.  Every function cites the reference lines it
  * follows.  It is pinned (tests/test_oracle_port.py) bit-for-bit against the reference's own functions
  * running from oracle/_ref (the unmodified sources) on the committed golden case, and its CG reproduces the
- * reference's iteration counts (80 / 106 on the default case).
+ * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the local
+ * bond-wise damage and computeStrain are restated at the end of the file as the reference's literal serial loops and
+ * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz and sc6_j2.npz.
  *
  * Layouts are the reference's logical ones, flattened row-major: per-bond a[i*nn+j], per-particle a[i*c+k],
  * DoF vectors v[dim*i+k], Pin[3*i+k]; three-slot state as separate arrays.  Strict IEEE: compile with
@@ -614,5 +616,384 @@ void oracle_update_crack(int N, int nn, int dim, const int *nbi, const double *b
             for (int k = 0; k < dim; k++)
                 fix_index[dim * i + k] = 0;
         damage_visual[i] = 1 - damage_visual[i] / nbi[i];
+    }
+}
+
+/* ================================================================== rows a8 / f4 of SURVEY section 8 ============
+ * The alternative J2 laws are restated LITERALLY as the reference's serial particle loop (they are order
+ * dependent: plmode 5 updates slot [0] in place, plmode 3 reads stale sums across broken bonds), on flat arrays. */
+
+/* geometry of particle i with an explicit plastic-stretch row, constitutive.c:318-334 / 703-721 (cs optional) */
+static void geom_row(int i, int nn, const double *xyz, const int *neighbors, const int *nsign, const int *nbi, const double *L0,
+                     const double *dlp_row, const double *broken, const double *Tv, double *dL, double *dLt, double *TdLt, double *csx,
+                     double *csy, double *csz)
+{
+    dLt[2 * i] = dLt[2 * i + 1] = TdLt[2 * i] = TdLt[2 * i + 1] = 0;
+    for (int j = 0; j < nbi[i]; j++) {
+        const long e = (long)i * nn + j;
+        const int nj = neighbors[e];
+        const double dx = xyz[3 * i] - xyz[3 * nj], dy = xyz[3 * i + 1] - xyz[3 * nj + 1], dz = xyz[3 * i + 2] - xyz[3 * nj + 2];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        dL[e] = dis - L0[e];
+        dL[e] -= dlp_row[j];
+        dL[e] *= broken[e];
+        dLt[2 * i + nsign[e]] += dL[e];
+        TdLt[2 * i + nsign[e]] += Tv[e] * dL[e];
+        if (csx) {
+            csx[e] = dx / dis;
+            csy[e] = dy / dis;
+            csz[e] = dz / dis;
+        }
+    }
+}
+
+/* list of ii and its intact neighbours, constitutive.c:289-295 / 692-699 */
+static int star_list(int ii, int nn, const int *neighbors, const double *broken, const int *nb, int *out)
+{
+    int s = 0;
+    out[s++] = ii;
+    for (int k = 0; k < nn; k++)
+        if (broken[(long)ii * nn + k] > EPS && neighbors[(long)ii * nn + k] != -1 && s < nb[ii] + 1)
+            out[s++] = neighbors[(long)ii * nn + k];
+    while (s < nb[ii] + 1)
+        out[s++] = ii; /* allocInt1D(nb+1, ii) pre-fills with ii */
+    return nb[ii] + 1;
+}
+
+/* computeBondForceJ2energyReturnMap for all particles in order, constitutive.c:286-463 (plmode 3) */
+void oracle_j2_energy_force(int N, int nn, double V, double radius, double J2_H, double J2_xi, int load_indicator, const double *Ce,
+                            const int *type, const double *sigmay, const double *xyz, const int *neighbors, const int *nsign, const int *nbi,
+                            const int *nb, const double *L0, const double *Kn, const double *Tv, const double *broken, const double *dD0,
+                            const double *dLp0, const double *beq0, const double *alpha0, double *dLp2, double *beq2, double *alpha2,
+                            double *dlambda_out, int *pl_flag, double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt,
+                            double *csx, double *csy, double *csz, double *F, double *Pin)
+{
+    int *tmp = (int *)malloc(sizeof(int) * (nn + 1));
+    double *xdLp = (double *)malloc(sizeof(double) * (nn + 1) * nn), *xa = (double *)malloc(sizeof(double) * (nn + 1));
+    double *xb = (double *)malloc(sizeof(double) * (nn + 1)), *xl = (double *)malloc(sizeof(double) * (nn + 1));
+    for (int ii = 0; ii < N; ii++) {
+        const int cnt = star_list(ii, nn, neighbors, broken, nb, tmp);
+        for (int k = 0; k < cnt; k++) {
+            const int i = tmp[k];
+            for (int j = 0; j < nn; j++)
+                xdLp[k * nn + j] = dLp0[(long)i * nn + j];
+            xb[k] = beq0[i];
+            xa[k] = alpha0[i];
+            xl[k] = 0.0;
+        }
+        for (int k = 0; k < cnt; k++)
+            geom_row(tmp[k], nn, xyz, neighbors, nsign, nbi, L0, xdLp + k * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+        for (int k = 0; k < cnt; k++) {
+            const int i = tmp[k];
+            int nb1 = 0;
+            for (int j = 0; j < nbi[i]; j++) /* countNEqual(neighbors1[i], nneighbors1, -1) */
+                nb1 += nsign[(long)i * nn + j] == 0;
+            const int nb2 = nb[i] - nb1;
+            double U_d = 0.0, J2_k = 0.0;
+            const double J2_V = V * nb[i] / nn;
+            for (int j = 0; j < nb[i]; j++) {
+                const long e = (long)i * nn + j;
+                if (nsign[e] == 0) {
+                    U_d += 0.5 * Kn[e] * (dL[e] - dLt[2 * i] / nb1) * (dL[e] - dLt[2 * i] / nb1);
+                    J2_k = Kn[e];
+                } else if (nsign[e] == 1) {
+                    U_d += 0.5 * Kn[e] * (dL[e] - dLt[2 * i + 1] / nb2) * (dL[e] - dLt[2 * i + 1] / nb2);
+                }
+            }
+            const double c44 = Ce[3 * type[i] + 2];
+            const double J2_sigma = sqrt(6.0 * c44 * U_d / J2_V);
+            double dlambda = 0.0;
+            double yield_func = fabs(load_indicator * J2_sigma - beq0[i]) - (sigmay[i] + (1.0 - J2_xi) * J2_H * alpha0[i]);
+            if (yield_func > 0.0) {
+                pl_flag[i] = 1;
+                double a = 0.0, b = 1.0, ya = yield_func;
+                while ((b - a) > 1e-4) {
+                    dlambda = (a + b) / 2.0;
+                    yield_func = fabs(load_indicator * J2_sigma / (1.0 + 0.5 * dlambda) -
+                                      (beq0[i] + load_indicator * J2_xi * J2_H * dlambda * J2_sigma * sqrt(radius / J2_k / c44) / 6.0 / (1.0 + 0.5 * dlambda))) -
+                                 (sigmay[i] + (1.0 - J2_xi) * J2_H * alpha0[i] +
+                                  (1.0 - J2_xi) * J2_H * dlambda * J2_sigma * sqrt(radius / J2_k / c44) / 6.0 / (1.0 + 0.5 * dlambda));
+                    if (yield_func * ya < 0.0) {
+                        b = dlambda;
+                    } else {
+                        a = dlambda;
+                        ya = yield_func;
+                    }
+                }
+            }
+            xl[k] = dlambda;
+            xa[k] += dlambda / (1.0 + 0.5 * dlambda) * sqrt(radius / 6.0 / J2_k * U_d / J2_V);
+            xb[k] = (xb[k] + load_indicator * J2_xi * J2_H * dlambda / (1.0 + 0.5 * dlambda) * sqrt(radius / 6.0 / J2_k * U_d / J2_V));
+            double f_d = 0.0;
+            for (int j = 0; j < nb[i]; j++) {
+                const long e = (long)i * nn + j;
+                if (nsign[e] == 0)
+                    f_d = 2.0 * Kn[e] / (1 + dlambda / 2.0) * (dL[e] - dLt[2 * i] / nb1);
+                if (nsign[e] == 1)
+                    f_d = 2.0 * Kn[e] / (1 + dlambda / 2.0) * (dL[e] - dLt[2 * i + 1] / nb2);
+                ddLp[e] = dlambda * f_d / (4.0 * Kn[e]);
+                ddLp[e] *= broken[e];
+                xdLp[k * nn + j] += ddLp[e];
+            }
+        }
+        for (int k = 0; k < cnt; k++)
+            geom_row(tmp[k], nn, xyz, neighbors, nsign, nbi, L0, xdLp + k * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+        const int i = ii;
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e], s = nsign[e];
+            for (int jj = 0; jj < nn; jj++)
+                if (neighbors[(long)nj * nn + jj] == i)
+                    dL_ave[e] = 0.5 * (dL[e] + dL[(long)nj * nn + jj]);
+            F[e] = 2.0 * Kn[e] * dL_ave[e] + 0.5 * (TdLt[2 * i + s] + TdLt[2 * nj + s]) + 0.5 * Tv[e] * (dLt[2 * i + s] + dLt[2 * nj + s]);
+            F[e] *= (1.0 - dD0[e]);
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+        for (int j = 0; j < nn; j++)
+            dLp2[(long)i * nn + j] = broken[(long)i * nn + j] * xdLp[j];
+        beq2[i] = xb[0];
+        alpha2[i] = xa[0];
+        dlambda_out[i] = xl[0];
+    }
+    free(tmp);
+    free(xdLp);
+    free(xa);
+    free(xb);
+    free(xl);
+}
+
+/* computeBondForceJ2nonlinearIso for all particles in order, constitutive.c:689-863 (plmode 5); state slot [0] in place.
+ * SY(x) is the macro of lpm.h:50, whose argument is not parenthesised: SY(a + dl) = 620 + 3300 (1 - exp(-0.4 a + dl)). */
+void oracle_j2_iso_force(int N, int nn, double V, double J2_C, const double *Ce, const int *type, const double *xyz, const int *neighbors,
+                         const int *nsign, const int *nbi, const int *nb, const double *L0, const double *Kn, const double *Tv,
+                         const double *broken, const double *w, double *dLp0, double *beta0 /* [N][6] */, double *alpha0, double *dlambda,
+                         double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt, double *csx, double *csy, double *csz, double *F,
+                         double *Pin)
+{
+    int *tmp = (int *)malloc(sizeof(int) * (nn + 1));
+    for (int ii = 0; ii < N; ii++) {
+        const int cnt = star_list(ii, nn, neighbors, broken, nb, tmp);
+        for (int k = 0; k < cnt; k++)
+            geom_row(tmp[k], nn, xyz, neighbors, nsign, nbi, L0, dLp0 + (long)tmp[k] * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+        for (int k = 0; k < cnt; k++) {
+            const int i = tmp[k];
+            const double J2_V = V * nb[i] / nn;
+            double st[6] = {0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < nbi[i]; j++) {
+                const long e = (long)i * nn + j;
+                F[e] = 2.0 * Kn[e] * dL[e] + TdLt[2 * i + nsign[e]] + Tv[e] * dLt[2 * i + nsign[e]];
+                F[e] *= broken[e];
+                st[0] += 0.5 / J2_V * L0[e] * F[e] * csx[e] * csx[e];
+                st[1] += 0.5 / J2_V * L0[e] * F[e] * csy[e] * csy[e];
+                st[2] += 0.5 / J2_V * L0[e] * F[e] * csz[e] * csz[e];
+                st[3] += 0.5 / J2_V * L0[e] * F[e] * csy[e] * csz[e];
+                st[4] += 0.5 / J2_V * L0[e] * F[e] * csx[e] * csz[e];
+                st[5] += 0.5 / J2_V * L0[e] * F[e] * csx[e] * csy[e];
+            }
+            const double temp = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+            for (int j = 0; j < 3; j++)
+                st[j] -= temp;
+            for (int j = 0; j < 6; j++)
+                st[j] -= beta0[6 * i + j];
+            double seq = 0.0;
+            for (int j = 0; j < 6; j++)
+                seq += (j < 3 ? 1.0 : 2.0) * st[j] * st[j];
+            seq = sqrt(3.0 / 2.0 * seq);
+            double dl = 0.0;
+            double yield_func = seq - (620.0 + 3300.0 * (1.0 - exp(-0.4 * alpha0[i])));
+            if (yield_func > 0.0) {
+                double a = 0.0, b = 1.0, ya = yield_func;
+                while ((b - a) > 1e-4) {
+                    dl = (a + b) / 2.0;
+                    yield_func = seq - 1.5 * dl * (2.0 * Ce[3 * type[i] + 2] + J2_C) - (620.0 + 3300.0 * (1.0 - exp(-0.4 * alpha0[i] + dl)));
+                    if (yield_func * ya < 0.0) {
+                        b = dl;
+                    } else {
+                        a = dl;
+                        ya = yield_func;
+                    }
+                }
+            }
+            dlambda[i] = dl;
+            alpha0[i] += dlambda[i];
+            double dpl[6];
+            for (int j = 0; j < 6; j++) {
+                dpl[j] = dl * 1.5 * st[j] / seq;
+                beta0[6 * i + j] += J2_C * dpl[j];
+            }
+            for (int j = 0; j < nbi[i]; j++) {
+                const long e = (long)i * nn + j;
+                ddLp[e] = L0[e] * (dpl[0] * csx[e] * csx[e] + dpl[1] * csy[e] * csy[e] + dpl[2] * csz[e] * csz[e] + 2 * dpl[3] * csy[e] * csz[e] +
+                                   2 * dpl[4] * csx[e] * csz[e] + 2 * dpl[5] * csx[e] * csy[e]);
+                dLp0[e] += ddLp[e];
+            }
+        }
+        for (int k = 0; k < cnt; k++)
+            geom_row(tmp[k], nn, xyz, neighbors, nsign, nbi, L0, dLp0 + (long)tmp[k] * nn, broken, Tv, dL, dLt, TdLt, NULL, NULL, NULL);
+        const int i = ii;
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e], s = nsign[e];
+            for (int jj = 0; jj < nn; jj++)
+                if (neighbors[(long)nj * nn + jj] == i)
+                    dL_ave[e] = 0.5 * (dL[e] + dL[(long)nj * nn + jj]);
+            F[e] = 2.0 * Kn[e] * dL_ave[e] + 0.5 * (TdLt[2 * i + s] + TdLt[2 * nj + s]) + 0.5 * Tv[e] * (dLt[2 * i + s] + dLt[2 * nj + s]);
+            F[e] *= w[e];
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+    }
+    free(tmp);
+}
+
+/* updateDuctileDamageBwiseLocal, constitutive.c:1607-1695; pairs = newly broken (i, neighbour) in logging order */
+int oracle_damage_local_bondwise(int N, int nn, double thr, double Ac, const int *neighbors, const int *nbi, const double *triax,
+                                 const double *dlambda, double *dloc0, double *broken, double *dD0, double *w, int *nb, int *pairs, int max_pairs)
+{
+    for (int i = 0; i < N; i++) {
+        const double f = (1.0 + Ac * triax[i]);
+        if (f > 0.0 && dloc0[i] <= thr)
+            dloc0[i] += f * dlambda[i];
+        else if (dloc0[i] > 1.0)
+            dloc0[i] = 1.0;
+    }
+    int k = 0;
+    for (int i = 0; i < N; i++) {
+        nb[i] = nbi[i];
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e];
+            dD0[e] = 0.5 * (dloc0[i] + dloc0[nj]);
+            if (dD0[e] > thr && broken[e] > EPS) {
+                dD0[e] = 1.0;
+                broken[e] = 0.0;
+                for (int jj = 0; jj < nn; jj++)
+                    if (neighbors[(long)nj * nn + jj] == i) {
+                        dD0[(long)nj * nn + jj] = 1.0;
+                        broken[(long)nj * nn + jj] = 0.0;
+                    }
+                if (k < max_pairs) {
+                    pairs[2 * k] = i;
+                    pairs[2 * k + 1] = nj;
+                }
+                k++;
+            }
+            if (broken[e] <= EPS)
+                nb[i] -= 1;
+        }
+    }
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            if (fabs(broken[e]) < EPS || nb[i] == 0 || nb[neighbors[e]] == 0)
+                dD0[e] = 1.0;
+            w[e] = 1.0 - dD0[e];
+        }
+    return k;
+}
+
+/* computeStrain, lpm_basic.c:127-249, with the LU of oracle/shim's LAPACKE_dgesv (row-major, first maximal pivot;
+ * right-hand side untouched when singular, as LAPACK's dgesv) */
+void oracle_compute_strain(int N, int nn, int dim, const double *xyz0, const int *neighbors, const int *nsign, const int *nbi,
+                           const double *L0, const double *dL, double *strain /* [N][6] */)
+{
+    const int ns = 3 * (dim - 1);
+    for (int i = 0; i < N; i++) {
+        double r4[3][3][3][3] = {{{{0}}}}, r2[3][3] = {{0}};
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int s = nsign[e], nj = neighbors[e];
+            if (s != 0 && s != 1)
+                continue;
+            const double wgt = s == 0 ? 0.1 : 0.9;
+            double dx[3];
+            for (int k = 0; k < dim; k++)
+                dx[k] = xyz0[3 * nj + k] - xyz0[3 * i + k];
+            for (int k = 0; k < dim; k++)
+                for (int n = 0; n < dim; n++) {
+                    for (int m = 0; m < dim; m++)
+                        for (int l = 0; l < dim; l++)
+                            r4[k][n][m][l] += wgt * dx[k] / L0[e] * dx[n] / L0[e] * dx[m] / L0[e] * dx[l] / L0[e];
+                    r2[k][n] += wgt * dL[e] / L0[e] * dx[k] / L0[e] * dx[n] / L0[e];
+                }
+        }
+        double a[36], b[6], b_in[6];
+        int ii = 0;
+        for (int j = 0; j < dim; j++)
+            for (int k = 0; k < dim; k++)
+                for (int m = 0; m < dim; m++)
+                    for (int l = 0; l < dim; l++)
+                        if (m <= l && j <= k)
+                            a[ii++] = r4[m][l][j][k];
+        ii = 0;
+        for (int j = 0; j < dim; j++)
+            for (int k = 0; k < dim; k++)
+                if (j <= k) {
+                    b[ii] = b_in[ii] = r2[j][k];
+                    ii++;
+                }
+        int info = 0;
+        for (int k = 0; k < ns; k++) {
+            int p = k;
+            double amax = fabs(a[k * ns + k]);
+            for (int r = k + 1; r < ns; r++)
+                if (fabs(a[r * ns + k]) > amax) {
+                    amax = fabs(a[r * ns + k]);
+                    p = r;
+                }
+            if (a[p * ns + k] == 0.0) {
+                if (info == 0)
+                    info = k + 1;
+                continue;
+            }
+            if (p != k) {
+                for (int c = 0; c < ns; c++) {
+                    const double t = a[k * ns + c];
+                    a[k * ns + c] = a[p * ns + c];
+                    a[p * ns + c] = t;
+                }
+                const double t = b[k];
+                b[k] = b[p];
+                b[p] = t;
+            }
+            for (int r = k + 1; r < ns; r++) {
+                const double l = a[r * ns + k] / a[k * ns + k];
+                a[r * ns + k] = l;
+                if (l != 0.0) {
+                    for (int c = k + 1; c < ns; c++)
+                        a[r * ns + c] -= l * a[k * ns + c];
+                    b[r] -= l * b[k];
+                }
+            }
+        }
+        if (info != 0) {
+            if (i == 0)
+                continue;
+            memcpy(b, b_in, sizeof(double) * ns);
+        } else {
+            for (int r = ns - 1; r >= 0; r--) {
+                double t = b[r];
+                for (int c = r + 1; c < ns; c++)
+                    t -= a[r * ns + c] * b[c];
+                b[r] = t / a[r * ns + r];
+            }
+        }
+        if (dim == 2) {
+            strain[6 * i] = b[0];
+            strain[6 * i + 5] = b[1];
+            strain[6 * i + 1] = b[2];
+        } else {
+            strain[6 * i] = b[0];
+            strain[6 * i + 5] = b[1];
+            strain[6 * i + 4] = b[2];
+            strain[6 * i + 1] = b[3];
+            strain[6 * i + 3] = b[4];
+            strain[6 * i + 2] = b[5];
+        }
     }
 }

@@ -87,3 +87,121 @@ def test_port_damage_and_crack(port, golden):
     p.updateCrack()
     assert_same(p.F, g["s1.crack.F"], "F"); assert_same(p.Pin, g["s1.crack.Pin"], "Pin")
     assert_same(p.nb, g["s1.crack.nb"], "nb")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# rows a8 / f4: the alternative J2 laws, the local bond-wise damage and computeStrain, restated in lpm_oracle.c as
+# the reference's literal serial loops, against the fixtures produced by the reference itself
+def _lib():
+    import ctypes as C
+    from oracle import port as P
+    if not P.available():
+        pytest.skip("oracle/liblpm_oracle.so not built")
+    lib = C.CDLL(str(P.SO))
+    lib.oracle_damage_local_bondwise.restype = C.c_int
+    return lib, C
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _ptr(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("tag,t", [("s1.n0", 1), ("s1.n2", 1), ("s2.n0", -1), ("s2.n2", -1)])
+def test_port_j2_energy_law_bit_exact(tag, t):
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_j2energy.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    pre, bf = f"{tag}.pre", f"{tag}.bf"
+    f8, i4 = np.float64, np.int32
+    a = {k: _c(g[f"{pre}.{k}"], f8) for k in ("xyz", "damage_broken", "ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin",
+                                              "J2_dlambda")}
+    dLp, alpha, beq, dD = g[f"{pre}.dLp"], g[f"{pre}.J2_alpha"], g[f"{pre}.J2_beta_eq"], g[f"{pre}.damage_D"]
+    dLp0, dLp2 = _c(dLp[..., 0], f8), _c(dLp[..., 2], f8)
+    a0, a2, b0, b2 = _c(alpha[:, 0], f8), _c(alpha[:, 2], f8), _c(beq[:, 0], f8), _c(beq[:, 2], f8)
+    plf, nb = _c(g[f"{pre}.pl_flag"], i4), _c(g[f"{pre}.nb"], i4)
+    cst = {k: _c(g[f"setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial", "type")}
+    cf = {k: _c(g[f"setup.{k}"], f8) for k in ("Ce", "sigmay", "distance_initial", "Kn", "Tv")}
+    lib.oracle_j2_energy_force(C.c_int(N), C.c_int(nn), C.c_double(par["particle_volume"]), C.c_double(par["radius"]), C.c_double(par["J2_H"]),
+                               C.c_double(par["J2_xi"]), C.c_int(t), _ptr(cf["Ce"]), _ptr(cst["type"]), _ptr(cf["sigmay"]), _ptr(a["xyz"]),
+                               _ptr(cst["neighbors"]), _ptr(cst["nsign"]), _ptr(cst["nb_initial"]), _ptr(nb), _ptr(cf["distance_initial"]),
+                               _ptr(cf["Kn"]), _ptr(cf["Tv"]), _ptr(a["damage_broken"]), _ptr(_c(dD[..., 0], f8)), _ptr(dLp0), _ptr(b0), _ptr(a0),
+                               _ptr(dLp2), _ptr(b2), _ptr(a2), _ptr(a["J2_dlambda"]), _ptr(plf), _ptr(a["ddLp"]), _ptr(a["dL"]), _ptr(a["dL_ave"]),
+                               _ptr(a["dL_total"]), _ptr(a["TdL_total"]), _ptr(a["csx"]), _ptr(a["csy"]), _ptr(a["csz"]), _ptr(a["F"]), _ptr(a["Pin"]))
+    for k in ("ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin", "J2_dlambda"):
+        assert_same(a[k], g[f"{bf}.{k}"], k)
+    assert_same(plf, g[f"{bf}.pl_flag"], "pl_flag")
+    assert_same(dLp2, g[f"{bf}.dLp"][..., 2], "dLp[2]")
+    assert_same(a2, g[f"{bf}.J2_alpha"][:, 2], "J2_alpha[2]")
+    assert_same(b2, g[f"{bf}.J2_beta_eq"][:, 2], "J2_beta_eq[2]")
+
+
+@pytest.mark.parametrize("tag", ["s1.n0", "s2.n0", "s3.n0", "s3.n1"])
+def test_port_j2_iso_law_bit_exact(tag):
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_j2iso.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    pre, bf = f"{tag}.pre", f"{tag}.bf"
+    f8, i4 = np.float64, np.int32
+    a = {k: _c(g[f"{pre}.{k}"], f8) for k in ("xyz", "damage_broken", "damage_w", "ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz",
+                                              "F", "Pin", "J2_dlambda")}
+    dLp0 = _c(g[f"{pre}.dLp"][..., 0], f8)
+    beta0 = _c(g[f"{pre}.J2_beta"][..., 0], f8)
+    alpha0 = _c(g[f"{pre}.J2_alpha"][:, 0], f8)
+    nb = _c(g[f"{pre}.nb"], i4)
+    cst = {k: _c(g[f"setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial", "type")}
+    cf = {k: _c(g[f"setup.{k}"], f8) for k in ("Ce", "distance_initial", "Kn", "Tv")}
+    lib.oracle_j2_iso_force(C.c_int(N), C.c_int(nn), C.c_double(par["particle_volume"]), C.c_double(par["J2_C"]), _ptr(cf["Ce"]), _ptr(cst["type"]),
+                            _ptr(a["xyz"]), _ptr(cst["neighbors"]), _ptr(cst["nsign"]), _ptr(cst["nb_initial"]), _ptr(nb),
+                            _ptr(cf["distance_initial"]), _ptr(cf["Kn"]), _ptr(cf["Tv"]), _ptr(a["damage_broken"]), _ptr(a["damage_w"]), _ptr(dLp0),
+                            _ptr(beta0), _ptr(alpha0), _ptr(a["J2_dlambda"]), _ptr(a["ddLp"]), _ptr(a["dL"]), _ptr(a["dL_ave"]), _ptr(a["dL_total"]),
+                            _ptr(a["TdL_total"]), _ptr(a["csx"]), _ptr(a["csy"]), _ptr(a["csz"]), _ptr(a["F"]), _ptr(a["Pin"]))
+    for k in ("ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin", "J2_dlambda"):
+        assert_same(a[k], g[f"{bf}.{k}"], k)
+    assert np.abs(dLp0).max() > 1e-4      # plastic stretch accumulated in place (the reference wipes it afterwards)
+
+
+@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
+def test_port_local_bondwise_damage_bit_exact(step):
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_j2iso.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    pre, out = f"{step}.dam.pre", f"{step}.dam"
+    f8, i4 = np.float64, np.int32
+    dloc0 = _c(g[f"{pre}.damage_local"][:, 0], f8)
+    broken, w, dD0 = _c(g[f"{pre}.damage_broken"], f8), _c(g[f"{pre}.damage_w"], f8), _c(g[f"{pre}.damage_D"][..., 0], f8)
+    nb = _c(g[f"{pre}.nb"], i4)
+    pairs = np.full((64, 2), -1, i4)
+    k = lib.oracle_damage_local_bondwise(C.c_int(N), C.c_int(nn), C.c_double(par["damage_threshold"]), C.c_double(par["damagec_A"]),
+                                         _ptr(_c(g["setup.neighbors"], i4)), _ptr(_c(g["setup.nb_initial"], i4)),
+                                         _ptr(_c(g[f"{pre}.J2_triaxiality"], f8)), _ptr(_c(g[f"{pre}.J2_dlambda"], f8)), _ptr(dloc0), _ptr(broken),
+                                         _ptr(dD0), _ptr(w), _ptr(nb), _ptr(pairs), C.c_int(64))
+    assert k == int(g[f"{out}.broken"][0])
+    assert_same(dloc0, g[f"{out}.damage_local"][:, 0], "damage_local")
+    assert_same(broken, g[f"{out}.damage_broken"], "damage_broken")
+    assert_same(dD0, g[f"{out}.damage_D"][..., 0], "damage_D")
+    assert_same(w, g[f"{out}.damage_w"], "damage_w")
+    assert_same(nb, g[f"{out}.nb"], "nb")
+
+
+@pytest.mark.parametrize("step", ["s1", "s2"])
+def test_port_compute_strain_bit_exact(golden, step):
+    lib, C = _lib()
+    g = golden
+    N, nn = g["setup.neighbors"].shape
+    f8, i4 = np.float64, np.int32
+    strain = np.zeros((N, 6)) if step == "s1" else _c(g["s1.strain.strain_tensor"], f8).copy()
+    lib.oracle_compute_strain(C.c_int(N), C.c_int(nn), C.c_int(3), _ptr(_c(g["setup.xyz"], f8)), _ptr(_c(g["setup.neighbors"], i4)),
+                              _ptr(_c(g["setup.nsign"], i4)), _ptr(_c(g["setup.nb_initial"], i4)), _ptr(_c(g["setup.distance_initial"], f8)),
+                              _ptr(_c(g[f"{step}.strain.dL"], f8)), _ptr(strain))
+    assert_same(strain, g[f"{step}.strain.strain_tensor"], "strain_tensor")
