@@ -23,9 +23,18 @@
  *                                                                  lpmb_update_damage (+ the broken-bond log file)
  *   constitutive.h:29          void updateCrack()                  lpmb_update_crack
  *   constitutive.h:11          void computeCab()                   lpmb_set_schmid_tensor + lpmb_compute_cab
- *   constitutive.h:15-20,24-26 the per-particle computeBondForce*(int) and the unused damage variants: symbols
- *                              kept, fail loudly (exit 1) -- nothing in the drivers calls them once stiffness.c
- *                              is replaced (use computeBondForceGeneral), plmode 3 / 5 are not built
+ *   constitutive.h:25          int updateDuctileDamageBwiseLocal(const char *, int)   lpmb_update_damage (plmode 5)
+ *   constitutive.h:15-20,24,26 the per-particle computeBondForce*(int) and the two damage variants the reference's
+ *                              dispatcher never calls: symbols kept, fail loudly (exit 1) -- nothing in the drivers
+ *                              calls them once stiffness.c is replaced; every law (plmode 0, 1, 3, 4, 5, 6) is
+ *                              reached through computeBondForceGeneral
+ *
+ * State ownership: the arrays these functions write (plastic state slots, damage_broken / damage_D / damage_w, nb,
+ * bond forces ...) are uploaded once, before the first force evaluation -- so initial cracks set by the driver are
+ * honoured -- and are device-authoritative afterwards: every call downloads what it wrote, but a driver that pokes
+ * those arrays on the host BETWEEN calls is not seen (no shipped driver does).  Arrays only the host writes
+ * (xyz, xyz_temp, F_temp, Pex, dispBC_index, fix_index, residual, K_global, type, Ce, parameters) are uploaded on
+ * entry of the call that reads them.
  *
  * Declarations use empty parameter lists exactly like the reference's headers (the default driver
  * even calls updateRR(ni++), lpmc_project.c:462 -- harmless under the SysV x86-64 ABI).
