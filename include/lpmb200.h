@@ -20,7 +20,9 @@
  *   lpmb_switch_state          switchStateV(flag), src/constitutive.c:10-85
  *   lpmb_update_rr             updateRR(), src/stiffness.c:519-534
  *   lpmb_update_damage         updateDamageGeneral(), src/constitutive.c:149-164 ->
- *                              updateDuctileDamagePwiseNonlocal (:1757-1862), updateBrittleDamage (:1437-1526)
+ *                              updateDuctileDamagePwiseNonlocal (:1757-1862), updateBrittleDamage (:1437-1526),
+ *                              updateDuctileDamageBwiseLocal (:1607-1695), updateDuctileDamagePwiseLocal (:1529-1579),
+ *                              updateDuctileDamageBwiseNonlocal (:1698-1753)
  *   lpmb_update_crack          updateCrack(), src/constitutive.c:1399-1434
  *   lpmb_apply_disp_bc_mask    the effect of setDispBC_stiffnessUpdate{2,3}D, src/boundary.c:72-281,
  *                              as a DoF mask applied inside the solve (K is never edited)
@@ -166,7 +168,12 @@ int lpmb_switch_state(lpmb_ctx *ctx, int flag);
 /* residual = dispBC_index*(Pex-Pin); returns ||residual||_2 and ||reaction||_2 (either may be NULL) */
 int lpmb_update_rr(lpmb_ctx *ctx, double *norm_residual, double *norm_reaction);
 /* returns the number of newly broken bonds in *broken; broken (i, neighbor) pairs are appended to
- * pairs[2*k], pairs[2*k+1] in the reference's logging order, up to max_pairs (may be NULL) */
+ * pairs[2*k], pairs[2*k+1] in the reference's logging order, up to max_pairs (may be NULL).
+ * plmode 0 / 5 / 6 select what updateDamageGeneral dispatches to (constitutive.c:149-164); the two laws its
+ * dispatcher keeps commented out (:155-156) are reached with the codes below.  LPMB_DAMAGE_PWISE_LOCAL counts and
+ * reports detached PARTICLES (pairs[2k] = particle, pairs[2k+1] = -1), as the reference logs them (:1562). */
+#define LPMB_DAMAGE_PWISE_LOCAL 100    /* updateDuctileDamagePwiseLocal,    src/constitutive.c:1529-1579 */
+#define LPMB_DAMAGE_BWISE_NONLOCAL 101 /* updateDuctileDamageBwiseNonlocal, src/constitutive.c:1698-1753 */
 int lpmb_update_damage(lpmb_ctx *ctx, int plmode, int *broken, int *pairs, int max_pairs);
 /* computeStrain(), lpm_basic.c:127-249: per-particle weighted-least-squares strain tensor from the elastic bond
  * stretches dL over the initial bond directions (n x n LU with partial pivoting, n = 3(dim-1)); writes the field

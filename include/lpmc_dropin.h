@@ -24,10 +24,12 @@
  *   constitutive.h:29          void updateCrack()                  lpmb_update_crack
  *   constitutive.h:11          void computeCab()                   lpmb_set_schmid_tensor + lpmb_compute_cab
  *   constitutive.h:25          int updateDuctileDamageBwiseLocal(const char *, int)   lpmb_update_damage (plmode 5)
- *   constitutive.h:15-20,24,26 the per-particle computeBondForce*(int) and the two damage variants the reference's
- *                              dispatcher never calls: symbols kept, fail loudly (exit 1) -- nothing in the drivers
- *                              calls them once stiffness.c is replaced; every law (plmode 0, 1, 3, 4, 5, 6) is
- *                              reached through computeBondForceGeneral
+ *   constitutive.h:24,26       int updateDuctileDamagePwiseLocal / updateDuctileDamageBwiseNonlocal(const char *, int)
+ *                              (commented out in the reference's dispatcher, constitutive.c:155-156)
+ *                                                                  lpmb_update_damage (LPMB_DAMAGE_PWISE_LOCAL / _BWISE_NONLOCAL)
+ *   constitutive.h:15-20       the per-particle computeBondForce*(int): symbols kept, fail loudly (exit 1) -- nothing
+ *                              in the drivers calls them once stiffness.c is replaced; every law (plmode 0, 1, 3, 4,
+ *                              5, 6) is reached through computeBondForceGeneral
  *
  * State ownership: the arrays these functions write (plastic state slots, damage_broken / damage_D / damage_w, nb,
  * bond forces ...) are uploaded once, before the first force evaluation -- so initial cracks set by the driver are
@@ -79,6 +81,12 @@ int updateDuctileDamagePwiseLocal(const char *dataName, int tstep);
 int updateDuctileDamageBwiseNonlocal(const char *dataName, int tstep);
 int updateDuctileDamagePwiseNonlocal(const char *dataName, int tstep);
 void updateCrack();
+
+/* Tell the layer that the host copies of device-authoritative state arrays (damage_*, plastic state slots, F, dL,
+ * cs*, nb, J2_dlambda, J2_triaxiality ...) were edited by the caller since the last entry point returned: the next
+ * entry point uploads them again.  Not needed by any shipped driver (they only edit those arrays before the first
+ * force evaluation); test generators that poke state between calls use it. */
+void lpmc_dropin_invalidate_state(void);
 
 /* release the device context (optional; the process exit does it too) */
 void lpmc_dropin_shutdown(void);

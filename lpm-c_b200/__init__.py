@@ -8,4 +8,4 @@ The directory name carries a hyphen, so import it with
     import importlib; lpm = importlib.import_module("lpm-c_b200")
 """
 from .capi import Context, LPMBError, lib, lib_path, device_count  # noqa: F401
-from . import lattice, driver  # noqa: F401
+from . import capi, lattice, driver  # noqa: F401

@@ -120,6 +120,8 @@ _INT_FIELDS = {"cp_Jact", "neighbors", "nsign", "mirror", "oppslot", "type", "pl
                "fix_index"}
 
 NOTCONVERGED = 4
+# lpmb_update_damage codes of the two laws updateDamageGeneral's dispatcher keeps commented out (include/lpmb200.h)
+DAMAGE_PWISE_LOCAL, DAMAGE_BWISE_NONLOCAL = 100, 101
 
 
 class Context:

@@ -504,27 +504,31 @@ static int damage(const char *dataName, int tstep, int mode)
     const int cap = 1 << 16;
     int *pairs = (int *)malloc(sizeof(int) * 2 * cap);
     CK(lpmb_update_damage(g_ctx, mode, &broken, pairs, cap));
-    if (mode == 0 || mode == 5 || mode == 6) {
-        FILE *fpt = fopen(dataName, "a+"); /* constitutive.c:1440-1442,1481,1610-1613,1672,1761-1763,1841 */
+    if (mode == 0 || mode == 5 || mode == 6 || mode == LPMB_DAMAGE_PWISE_LOCAL || mode == LPMB_DAMAGE_BWISE_NONLOCAL) {
+        FILE *fpt = fopen(dataName, "a+"); /* constitutive.c:1440-1442,1481,1532-1536,1562,1610-1613,1672,1701-1705,1739,1761-1763,1841 */
         if (fpt) {
             fprintf(fpt, "TIMESTEP ");
             fprintf(fpt, "%d\n", tstep);
             int logged = broken;
             if (mode == 6 && broken > nbreak)
                 logged = nbreak;
-            for (int k = 0; k < logged && k < cap; k++)
-                fprintf(fpt, "%d %d \n", pairs[2 * k], pairs[2 * k + 1]);
+            for (int k = 0; k < logged && k < cap; k++) {
+                if (mode == LPMB_DAMAGE_PWISE_LOCAL)
+                    fprintf(fpt, "%d \n", pairs[2 * k]); /* detached particles, one index per line */
+                else
+                    fprintf(fpt, "%d %d \n", pairs[2 * k], pairs[2 * k + 1]);
+            }
             fclose(fpt);
         }
         down_d2("damage_broken", damage_broken, N, nn);
         down_d2("damage_w", damage_w, N, nn);
         down_slot("damage_D", damage_D, N, nn, 0);
-        if (mode == 0)
+        if (mode == 0 || mode == LPMB_DAMAGE_BWISE_NONLOCAL)
             down_pslot("damage_nonlocal", damage_nonlocal, N, 0);
-        if (mode == 5) {
+        if (mode == 5 || mode == LPMB_DAMAGE_PWISE_LOCAL)
             down_pslot("damage_local", damage_local, N, 0);
+        if (mode == 5)
             DOWN1D("nb", nb, N);
-        }
     }
     free(pairs);
     return broken;
@@ -585,8 +589,12 @@ void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMi
 void computeBondForceIncrementalUpdating(int ii) { (void)ii; not_built("computeBondForceIncrementalUpdating(ii): use computeBondForceGeneral(4, t)"); }
 void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap(ii, t): use computeBondForceGeneral(3, t)"); }
 int updateDuctileDamageBwiseLocal(const char *d, int t) { return damage(d, t, 5); }
-int updateDuctileDamagePwiseLocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamagePwiseLocal"); return 0; }
-int updateDuctileDamageBwiseNonlocal(const char *d, int t) { (void)d; (void)t; not_built("updateDuctileDamageBwiseNonlocal"); return 0; }
+int updateDuctileDamagePwiseLocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_PWISE_LOCAL); }
+int updateDuctileDamageBwiseNonlocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_BWISE_NONLOCAL); }
+
+/* a driver that edits device-authoritative state on the HOST between two calls (see "State ownership" in
+ * lpmc_dropin.h) announces it here: the next entry point uploads the host arrays again */
+void lpmc_dropin_invalidate_state(void) { g_state_uploaded = 0; }
 
 void lpmc_dropin_shutdown(void)
 {

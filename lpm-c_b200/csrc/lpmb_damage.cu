@@ -4,6 +4,9 @@
 //   updateDamageGeneral(file, step, plmode)       src/constitutive.c:149-164
 //   updateDuctileDamagePwiseNonlocal(file, step)  src/constitutive.c:1757-1862  (plmode 0)
 //   updateBrittleDamage(file, step, nbreak)       src/constitutive.c:1437-1526  (plmode 6)
+//   updateDuctileDamageBwiseLocal(file, step)     src/constitutive.c:1607-1695  (plmode 5)
+//   updateDuctileDamagePwiseLocal(file, step)     src/constitutive.c:1529-1579  (LPMB_DAMAGE_PWISE_LOCAL; commented out in the dispatcher)
+//   updateDuctileDamageBwiseNonlocal(file, step)  src/constitutive.c:1698-1753  (LPMB_DAMAGE_BWISE_NONLOCAL; likewise)
 //
 // Nonlocal law: D_i += sum_j phi(d_ij) V Ddot_j / sum_j phi(d_ij) V over ALL particles with
 // d_ij < 3*damage_L in the initial configuration (self included).  The reference does this as an
@@ -181,6 +184,130 @@ local_finish_kernel(int N, int Np, const int *__restrict__ nbi, const int *__res
         dD0[e] = D;
         w[e] = 1.0 - D;
     }
+}
+
+// ---- particle-wise local ductile damage, updateDuctileDamagePwiseLocal, constitutive.c:1529-1579 -------------------
+// (1) damage_local += (1 + A triax) dlambda at or below the threshold; a particle that is then beyond it (and not
+// already at 1 within EPS) is set to 1: "newly detached".  The serial loop only reads particle i's own values here.
+__global__ void __launch_bounds__(DT)
+pwise_local_damage_kernel(int N, double thr, double Ac, const double *__restrict__ triax, const double *__restrict__ dlambda,
+                          double *__restrict__ dloc, signed char *__restrict__ newp, int *__restrict__ count)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double f = (1.0 + Ac * triax[i]);
+    double d = dloc[i];
+    if (f > 0.0 && d <= thr)
+        d += f * dlambda[i];
+    signed char nw = 0;
+    if (d > thr && fabs(d - 1.0) > LPMB_EPS) {
+        d = 1.0;
+        nw = 1;
+        atomicAdd(count, 1);
+    }
+    dloc[i] = d;
+    newp[i] = nw;
+}
+
+// (2) a newly detached particle zeroes damage_broken on all its bonds and on every slot of a neighbour that lists it
+// (constitutive.c:1551-1565; `mirror` >= 0 says the neighbour does); then damage_D = MAX of the end values, w = 1 - D
+__global__ void __launch_bounds__(DT)
+pwise_local_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, const signed char *__restrict__ mirror,
+                         const double *__restrict__ dloc, const signed char *__restrict__ newp, double *__restrict__ broken,
+                         double *__restrict__ dD0, double *__restrict__ w)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double di = dloc[i];
+    const bool mine = newp[i] != 0;
+    const int n = nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = nbr[e];
+        if (mine || (newp[nj] && mirror[e] >= 0))
+            broken[e] = 0.0;
+        const double dj = dloc[nj];
+        const double D = di < dj ? dj : di;  // MAX(x,y) ((x) < (y) ? (y) : (x))
+        dD0[e] = D;
+        w[e] = 1.0 - D;
+    }
+}
+
+// ---- bond-wise nonlocal ductile damage, updateDuctileDamageBwiseNonlocal, constitutive.c:1698-1753 ------------------
+// (1) Gaussian average over the particle's own bond list: the particle itself enters with weight V (no phi), a
+// neighbour with DAM_PHI(distance_initial) V; frozen / clamped beyond the threshold.  exp() -> compared at 1e-12.
+__global__ void __launch_bounds__(DT)
+bwise_nonlocal_damage_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, const double *__restrict__ L0, double L,
+                             double thr, double Ac, double V, const double *__restrict__ dlambda, const double *__restrict__ triax,
+                             double *__restrict__ Dn)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double Di = Dn[i];
+    if (Di > thr) {
+        if (Di > 1.0)
+            Dn[i] = 1.0;
+        return;
+    }
+    double DdotLocal = 0;
+    double f = (1.0 + Ac * triax[i]);
+    if (f > 0.0)
+        DdotLocal = dlambda[i] * (1.0 + Ac * triax[i]);
+    double Ddot = DdotLocal * V;
+    double A = V;
+    const int n = nbi[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = nbr[e];
+        DdotLocal = 0;
+        f = (1.0 + Ac * triax[nj]);
+        if (f > 0.0)
+            DdotLocal = dlambda[nj] * (1.0 + Ac * triax[nj]);
+        const double x = L0[e];
+        const double phi = 1.0 / L / sqrt(2 * LPMB_PI) * exp(-0.5 * x * x / L / L);
+        Ddot += DdotLocal * phi * V;
+        A += phi * V;
+    }
+    if (Ddot > 0.0)
+        Dn[i] = Di + 1.0 / A * Ddot;
+}
+
+// (2)+(3) fused per bond: an intact bond whose mean end damage is beyond the threshold breaks (D = 1; every direction
+// is counted on its own, as the reference's double loop does); intact bonds carry the mean; w = 1 - D
+__global__ void __launch_bounds__(DT)
+bwise_nonlocal_break_kernel(int N, int Np, const int *__restrict__ nbi, const int *__restrict__ nbr, double thr, const double *__restrict__ Dn,
+                            double *__restrict__ broken, double *__restrict__ dD0, double *__restrict__ w, signed char *__restrict__ newly,
+                            int *__restrict__ count)
+{
+    const int i = blockIdx.x * DT + threadIdx.x;
+    if (i >= N)
+        return;
+    const double Di = Dn[i];
+    const int n = nbi[i];
+    int k = 0;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const double m = 0.5 * (Di + Dn[nbr[e]]);
+        double b = broken[e], d = dD0[e];
+        signed char nw = 0;
+        if (m > thr && fabs(b) > LPMB_EPS) {
+            b = 0.0;
+            d = 1.0;
+            nw = 1;
+            k++;
+        }
+        if (fabs(b) > LPMB_EPS)
+            d = m;
+        broken[e] = b;
+        dD0[e] = d;
+        w[e] = 1.0 - d;
+        newly[e] = nw;
+    }
+    if (k)
+        atomicAdd(count, k);
 }
 
 // brittle: candidates with dL/L0 >= critical_bstrain, appended to a device list (order restored on the host)
@@ -408,6 +535,68 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
                         pairs[2 * t + 1] = hnbr[(size_t)j * Np + i];
                         t++;
                     }
+        }
+        cudaFree(newly);
+    }
+    else if (plmode == LPMB_DAMAGE_PWISE_LOCAL || plmode == LPMB_DAMAGE_BWISE_NONLOCAL) {
+        const bool pw = plmode == LPMB_DAMAGE_PWISE_LOCAL;
+        const bool have = c->params.count("damage_threshold") && c->params.count("damagec_A") &&
+                          (pw || (c->params.count("damage_L") && c->params.count("particle_volume")));
+        const signed char *mirror = fptr<signed char>(c, "mirror");
+        const double *L0 = fptr<double>(c, "distance_initial");
+        if (c->world != 1 || !have || (pw ? !mirror : !L0)) {
+            cudaFree(d_count);
+            lpmb_set_error(c->world != 1 ? "this damage law is single-GPU only" : "damage parameters / topology fields not set");
+            return c->world != 1 ? LPMB_ERR_UNSUPPORTED : LPMB_ERR_STATE;
+        }
+        const double thr = param(c, "damage_threshold"), Ac = param(c, "damagec_A");
+        signed char *newly = nullptr;  // pw: one flag per particle; else one per bond slot
+        const size_t nflag = pw ? (size_t)Np : (size_t)nn * Np;
+        LPMB_CUDA(cudaMalloc(&newly, nflag));
+        LPMB_CUDA(cudaMemsetAsync(newly, 0, nflag, c->stream));
+        if (pw) {
+            pwise_local_damage_kernel<<<g, DT, 0, c->stream>>>(N, thr, Ac, fptr<double>(c, "J2_triaxiality"), fptr<double>(c, "J2_dlambda"),
+                                                               fptr<double>(c, "damage_local0"), newly, d_count);
+            LPMB_LAUNCH_CHECK(c);
+            pwise_local_break_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, mirror, fptr<double>(c, "damage_local0"), newly, broken, dD0, w);
+            LPMB_LAUNCH_CHECK(c);
+        } else {
+            bwise_nonlocal_damage_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, L0, param(c, "damage_L"), thr, Ac, param(c, "particle_volume"),
+                                                                  fptr<double>(c, "J2_dlambda"), fptr<double>(c, "J2_triaxiality"),
+                                                                  fptr<double>(c, "damage_nonlocal0"));
+            LPMB_LAUNCH_CHECK(c);
+            bwise_nonlocal_break_kernel<<<g, DT, 0, c->stream>>>(N, Np, nbi, nbr, thr, fptr<double>(c, "damage_nonlocal0"), broken, dD0, w, newly,
+                                                                 d_count);
+            LPMB_LAUNCH_CHECK(c);
+        }
+        int k = 0;
+        LPMB_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LPMB_CUDA(cudaStreamSynchronize(c->stream));
+        *broken_out = k;
+        if (k > 0 && pairs && max_pairs > 0) {
+            // reference logging order: particle (or i, then slot j) ascending; the particle-wise law logs a single
+            // index per entry (constitutive.c:1562) -> second column -1
+            std::vector<signed char> hn(nflag);
+            LPMB_CUDA(cudaMemcpy(hn.data(), newly, hn.size(), cudaMemcpyDeviceToHost));
+            int t = 0;
+            if (pw) {
+                for (int i = 0; i < N && t < max_pairs; i++)
+                    if (hn[i]) {
+                        pairs[2 * t] = i;
+                        pairs[2 * t + 1] = -1;
+                        t++;
+                    }
+            } else {
+                std::vector<int> hnbr((size_t)nn * Np);
+                LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                for (int i = 0; i < N && t < max_pairs; i++)
+                    for (int j = 0; j < nn && t < max_pairs; j++)
+                        if (hn[(size_t)j * Np + i]) {
+                            pairs[2 * t] = i;
+                            pairs[2 * t + 1] = hnbr[(size_t)j * Np + i];
+                            t++;
+                        }
+            }
         }
         cudaFree(newly);
     }

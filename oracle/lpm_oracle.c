@@ -5,9 +5,9 @@
  * never linked, imported or executed by the product path.  Every function cites the reference lines it
  * follows.  It is pinned (tests/test_oracle_port.py) bit-for-bit against the reference's own functions
  * running from oracle/_ref (the unmodified sources) on the committed golden case, and its CG reproduces the
- * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the local
- * bond-wise damage and computeStrain are restated at the end of the file as the reference's literal serial loops and
- * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz and sc6_j2.npz.
+ * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the three
+ * remaining ductile-damage laws and computeStrain are restated at the end of the file as the reference's literal serial loops and
+ * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz and sc6_j2.npz.
  *
  * Layouts are the reference's logical ones, flattened row-major: per-bond a[i*nn+j], per-particle a[i*c+k],
  * DoF vectors v[dim*i+k], Pin[3*i+k]; three-slot state as separate arrays.  Strict IEEE: compile with
@@ -892,6 +892,102 @@ int oracle_damage_local_bondwise(int N, int nn, double thr, double Ac, const int
             const long e = (long)i * nn + j;
             if (fabs(broken[e]) < EPS || nb[i] == 0 || nb[neighbors[e]] == 0)
                 dD0[e] = 1.0;
+            w[e] = 1.0 - dD0[e];
+        }
+    return k;
+}
+
+/* updateDuctileDamagePwiseLocal, constitutive.c:1529-1579 (a law the reference's dispatcher keeps commented out,
+ * :155): local accumulation per particle; a particle that passes the threshold is set to 1 and loses all its bonds in
+ * both directions (logged as a single index); then damage_D = MAX of the two end values.  `list` receives the
+ * particles, returns their number. */
+int oracle_damage_local_particlewise(int N, int nn, double thr, double Ac, const int *neighbors, const int *nbi, const double *triax,
+                                     const double *dlambda, double *dloc0, double *broken, double *dD0, double *w, int *list, int max_list)
+{
+    int k = 0;
+    for (int i = 0; i < N; i++) {
+        const double f = (1.0 + Ac * triax[i]);
+        if (f > 0.0 && dloc0[i] <= thr)
+            dloc0[i] += f * dlambda[i];
+        if (dloc0[i] > thr && fabs(dloc0[i] - 1.0) > EPS) {
+            dloc0[i] = 1.0;
+            for (int j = 0; j < nbi[i]; j++) {
+                const int nj = neighbors[(long)i * nn + j];
+                broken[(long)i * nn + j] = 0.0;
+                for (int jj = 0; jj < nn; jj++)
+                    if (neighbors[(long)nj * nn + jj] == i)
+                        broken[(long)nj * nn + jj] = 0.0;
+            }
+            if (k < max_list)
+                list[k] = i;
+            k++;
+        }
+    }
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const double a = dloc0[i], b = dloc0[neighbors[e]];
+            dD0[e] = a < b ? b : a; /* MAX(x,y) ((x) < (y) ? (y) : (x)), lpm.h:46 */
+            w[e] = 1.0 - dD0[e];
+        }
+    return k;
+}
+
+/* updateDuctileDamageBwiseNonlocal, constitutive.c:1698-1753 (also commented out in the dispatcher, :156): the
+ * nonlocal average runs over the particle's own bond list with DAM_PHI(distance_initial) (lpm.h:51), the particle
+ * itself enters with weight particle_volume (no phi); a bond breaks when the mean of its two end values passes the
+ * threshold; every direction of a bond is visited, counted and logged on its own. */
+int oracle_damage_nonlocal_bondwise(int N, int nn, double L, double thr, double Ac, double V, const int *neighbors, const int *nbi,
+                                    const double *L0, const double *dlambda, const double *triax, double *Dn, double *broken, double *dD0,
+                                    double *w, int *pairs, int max_pairs)
+{
+    for (int i = 0; i < N; i++) {
+        if (Dn[i] > thr) {
+            if (Dn[i] > 1.0)
+                Dn[i] = 1.0;
+            continue;
+        }
+        double DdotLocal = 0;
+        double f = (1.0 + Ac * triax[i]);
+        if (f > 0.0)
+            DdotLocal = dlambda[i] * (1.0 + Ac * triax[i]);
+        double Ddot = DdotLocal * V;
+        double A = V;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e];
+            DdotLocal = 0;
+            f = (1.0 + Ac * triax[nj]);
+            if (f > 0.0)
+                DdotLocal = dlambda[nj] * (1.0 + Ac * triax[nj]);
+            const double x = L0[e];
+            const double phi = 1.0 / L / sqrt(2 * PI) * exp(-0.5 * x * x / L / L);
+            Ddot += DdotLocal * phi * V;
+            A += phi * V;
+        }
+        if (Ddot > 0.0)
+            Dn[i] += 1.0 / A * Ddot;
+    }
+    int k = 0;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            if (0.5 * (Dn[i] + Dn[neighbors[e]]) > thr)
+                if (fabs(broken[e]) > EPS) {
+                    broken[e] = 0.0;
+                    dD0[e] = 1.0;
+                    if (k < max_pairs) {
+                        pairs[2 * k] = i;
+                        pairs[2 * k + 1] = neighbors[e];
+                    }
+                    k++;
+                }
+        }
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            if (fabs(broken[e]) > EPS)
+                dD0[e] = 0.5 * (Dn[i] + Dn[neighbors[e]]);
             w[e] = 1.0 - dD0[e];
         }
     return k;

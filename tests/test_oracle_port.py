@@ -194,6 +194,57 @@ def test_port_local_bondwise_damage_bit_exact(step):
     assert_same(nb, g[f"{out}.nb"], "nb")
 
 
+@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
+def test_port_particlewise_local_damage_bit_exact(step):
+    """updateDuctileDamagePwiseLocal (constitutive.c:1529-1579) restated, against tests/golden/sc6_damage_variants.npz"""
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_damage_variants.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    pre, out = f"pwl.{step}.pre", f"pwl.{step}.post"
+    f8, i4 = np.float64, np.int32
+    dloc0 = _c(g[f"{pre}.damage_local"][:, 0], f8)
+    broken, w, dD0 = _c(g[f"{pre}.damage_broken"], f8), _c(g[f"{pre}.damage_w"], f8), _c(g[f"{pre}.damage_D"][..., 0], f8)
+    lst = np.full(64, -1, i4)
+    k = lib.oracle_damage_local_particlewise(C.c_int(N), C.c_int(nn), C.c_double(par["damage_threshold"]), C.c_double(par["damagec_A"]),
+                                             _ptr(_c(g["setup.neighbors"], i4)), _ptr(_c(g["setup.nb_initial"], i4)),
+                                             _ptr(_c(g[f"{pre}.J2_triaxiality"], f8)), _ptr(_c(g[f"{pre}.J2_dlambda"], f8)), _ptr(dloc0),
+                                             _ptr(broken), _ptr(dD0), _ptr(w), _ptr(lst), C.c_int(64))
+    assert k == int(g[f"pwl.{step}.broken"][0])
+    assert_same(dloc0, g[f"{out}.damage_local"][:, 0], "damage_local")
+    assert_same(broken, g[f"{out}.damage_broken"], "damage_broken")
+    assert_same(dD0, g[f"{out}.damage_D"][..., 0], "damage_D")
+    assert_same(w, g[f"{out}.damage_w"], "damage_w")
+    assert np.array_equal(lst[:k], np.flatnonzero((g[f"{out}.damage_local"][:, 0] == 1.0) & (g[f"{pre}.damage_local"][:, 0] != 1.0)))
+
+
+@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
+def test_port_bondwise_nonlocal_damage_bit_exact(step):
+    """updateDuctileDamageBwiseNonlocal (constitutive.c:1698-1753) restated, against tests/golden/sc6_damage_variants.npz"""
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_damage_variants.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    pre, out = f"bwn.{step}.pre", f"bwn.{step}.post"
+    f8, i4 = np.float64, np.int32
+    Dn = _c(g[f"{pre}.damage_nonlocal"][:, 0], f8)
+    broken, w, dD0 = _c(g[f"{pre}.damage_broken"], f8), _c(g[f"{pre}.damage_w"], f8), _c(g[f"{pre}.damage_D"][..., 0], f8)
+    pairs = np.full((512, 2), -1, i4)
+    k = lib.oracle_damage_nonlocal_bondwise(C.c_int(N), C.c_int(nn), C.c_double(par["damage_L"]), C.c_double(par["damage_threshold"]),
+                                            C.c_double(par["damagec_A"]), C.c_double(par["particle_volume"]),
+                                            _ptr(_c(g["setup.neighbors"], i4)), _ptr(_c(g["setup.nb_initial"], i4)),
+                                            _ptr(_c(g["setup.distance_initial"], f8)), _ptr(_c(g[f"{pre}.J2_dlambda"], f8)),
+                                            _ptr(_c(g[f"{pre}.J2_triaxiality"], f8)), _ptr(Dn), _ptr(broken), _ptr(dD0), _ptr(w), _ptr(pairs),
+                                            C.c_int(512))
+    assert k == int(g[f"bwn.{step}.broken"][0])
+    assert_same(Dn, g[f"{out}.damage_nonlocal"][:, 0], "damage_nonlocal")
+    assert_same(broken, g[f"{out}.damage_broken"], "damage_broken")
+    assert_same(dD0, g[f"{out}.damage_D"][..., 0], "damage_D")
+    assert_same(w, g[f"{out}.damage_w"], "damage_w")
+
+
 @pytest.mark.parametrize("step", ["s1", "s2"])
 def test_port_compute_strain_bit_exact(golden, step):
     lib, C = _lib()

@@ -121,6 +121,28 @@ def test_j2_iso_golden_matches_reference_build(tmp_path):
     assert int(old["s2.dam.broken"][0]) == 18
 
 
+def test_damage_variants_golden_matches_reference_build(tmp_path):
+    """tests/golden/sc6_damage_variants.npz (the two ductile-damage laws the dispatcher keeps commented out, SURVEY row
+    a16) regenerates bit-identically; the recorded calls really break particles / bonds and freeze damaged particles"""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    import os, subprocess, sys
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    out = tmp_path / "dv.npz"
+    subprocess.run([sys.executable, str(gold / "make_golden_damage_variants.py")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, LPMB_GOLDEN_OUT=str(out)))
+    new, old = np.load(out), np.load(gold / "sc6_damage_variants.npz")
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert np.array_equal(new[k], old[k]), k
+    assert [int(old[f"pwl.s{s}.broken"][0]) for s in (1, 2, 3)] == [0, 9, 16]
+    assert [int(old[f"bwn.s{s}.broken"][0]) for s in (1, 2, 3)] == [0, 6, 264]
+    thr = 0.02
+    assert (old["bwn.s3.pre.damage_nonlocal"][:, 0] > thr).any()        # frozen branch (constitutive.c:1712-1717) taken
+
+
 def test_golden_internal_consistency(golden):
     g = golden
     assert g["setup.xyz"].shape == (216, 3)
