@@ -7,7 +7,7 @@ Everything here is + - * / sqrt in fp64, compiled -fmad=false, and the reference
 import numpy as np
 import pytest
 
-from helpers import (assert_same, get_slots, make_ctx, params_from_golden, put_slots, put_state, rel_err)
+from helpers import (assert_same, get_slots, make_ctx, put_slots, put_state, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -255,61 +255,4 @@ def test_local_bondwise_damage_bit_exact(lpm, step):
     assert_same(get_slots(c, "damage_local", 2), g[f"{step}.dam.damage_local"], "damage_local")
     if step == "s2":
         assert broken == 18 and len(pairs) == 18 and all(i < j for i, j in pairs)
-    c.close()
-
-
-def _dv_ctx(lpm, g, pre):
-    """context for tests/golden/sc6_damage_variants.npz: topology + the damage state recorded before a call"""
-    N, nn = g["setup.neighbors"].shape
-    c = lpm.Context(N, 3, 2, nn, g["setup.conn"].shape[1])
-    c.set_params(**params_from_golden(g))
-    c.set_field("xyz", g["setup.xyz"])
-    c.set_field("xyz_initial", g["setup.xyz"])
-    c.set_neighbors(g["setup.neighbors"], g["setup.nsign"])   # derives nb_initial, mirror slots, distance_initial
-    for n in ("J2_dlambda", "J2_triaxiality", "damage_broken", "damage_w"):
-        c.set_field(n, g[f"{pre}.{n}"])
-    put_slots(c, "damage_D", g[f"{pre}.damage_D"])
-    put_slots(c, "damage_local", g[f"{pre}.damage_local"])
-    put_slots(c, "damage_nonlocal", g[f"{pre}.damage_nonlocal"])
-    return c
-
-
-@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
-def test_particlewise_local_damage_bit_exact(lpm, step):
-    """updateDuctileDamagePwiseLocal (constitutive.c:1529-1579; commented out in the reference's dispatcher, SURVEY row
-    a16): calls 2 and 3 detach 9 and 16 particles, each losing all its bonds in both directions"""
-    from pathlib import Path
-    g = np.load(Path(__file__).parent / "golden" / "sc6_damage_variants.npz")
-    pre, post = f"pwl.{step}.pre", f"pwl.{step}.post"
-    c = _dv_ctx(lpm, g, pre)
-    assert_same(c.get_field("distance_initial"), g["setup.distance_initial"], "distance_initial")
-    broken, pairs = c.update_damage(lpm.capi.DAMAGE_PWISE_LOCAL)
-    assert broken == int(g[f"pwl.{step}.broken"][0])
-    for n in ("damage_broken", "damage_w"):
-        assert_same(c.get_field(n), g[f"{post}.{n}"], n)
-    assert_same(get_slots(c, "damage_D", 2), g[f"{post}.damage_D"], "damage_D")
-    assert_same(get_slots(c, "damage_local", 2), g[f"{post}.damage_local"], "damage_local")
-    detached = np.flatnonzero((g[f"{post}.damage_local"][:, 0] == 1.0) & (g[f"{pre}.damage_local"][:, 0] != 1.0))
-    assert np.array_equal(pairs[:, 0], detached) and (pairs[:, 1] == -1).all()
-    c.close()
-
-
-@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
-def test_bondwise_nonlocal_damage(lpm, step):
-    """updateDuctileDamageBwiseNonlocal (constitutive.c:1698-1753; commented out in the dispatcher): Gaussian average
-    over the bond list (exp() on the device vs glibc: 1e-12 on damage values, bit-exact on which bonds break)"""
-    from pathlib import Path
-    g = np.load(Path(__file__).parent / "golden" / "sc6_damage_variants.npz")
-    pre, post = f"bwn.{step}.pre", f"bwn.{step}.post"
-    c = _dv_ctx(lpm, g, pre)
-    broken, pairs = c.update_damage(lpm.capi.DAMAGE_BWISE_NONLOCAL)
-    assert broken == int(g[f"bwn.{step}.broken"][0])
-    assert_same(c.get_field("damage_broken"), g[f"{post}.damage_broken"], "damage_broken")
-    tol = 1e-12   # fp64 exp(): device libm vs glibc
-    assert rel_err(get_slots(c, "damage_nonlocal", 2), g[f"{post}.damage_nonlocal"]) <= tol
-    assert rel_err(get_slots(c, "damage_D", 2), g[f"{post}.damage_D"]) <= tol
-    assert rel_err(c.get_field("damage_w"), g[f"{post}.damage_w"]) <= tol
-    newly = (g[f"{pre}.damage_broken"] != 0) & (g[f"{post}.damage_broken"] == 0)
-    ii, jj = np.nonzero(newly)
-    assert np.array_equal(pairs, np.stack([ii, g["setup.neighbors"][ii, jj]], axis=1))   # i ascending, then slot ascending
     c.close()

@@ -186,20 +186,3 @@ def test_dropin_replays_j2_iso_golden_case(tmp_path):
         for k in ("F", "Pin", "dL", "stress_tensor"):
             assert _rel(new[f"{t}.bf.{k}"], old[f"{t}.bf.{k}"]) <= 1e-6, (t, k)
     assert int(new["s1.dam.broken"][0]) == 0
-
-
-def test_dropin_replays_damage_variant_golden_case(tmp_path):
-    """tests/golden/sc6_damage_variants.npz: updateDuctileDamagePwiseLocal / updateDuctileDamageBwiseNonlocal (reference
-    names, constitutive.h:24,26) through liblpmc_dropin.so, all three calls of each law.  The generator pokes the
-    multiplier / triaxiality fields into host memory between calls and announces it with
-    lpmc_dropin_invalidate_state() (include/lpmc_dropin.h)."""
-    new = _regen("make_golden_damage_variants.py", tmp_path, "dv.npz")
-    old = np.load(GOLD / "sc6_damage_variants.npz")
-    for s in ("s1", "s2", "s3"):
-        assert int(new[f"pwl.{s}.broken"][0]) == int(old[f"pwl.{s}.broken"][0])
-        assert int(new[f"bwn.{s}.broken"][0]) == int(old[f"bwn.{s}.broken"][0])
-        for n in ("damage_local", "damage_broken", "damage_w", "damage_D"):
-            assert np.array_equal(new[f"pwl.{s}.post.{n}"], old[f"pwl.{s}.post.{n}"]), (s, n)
-        assert np.array_equal(new[f"bwn.{s}.post.damage_broken"], old[f"bwn.{s}.post.damage_broken"])
-        for n in ("damage_nonlocal", "damage_w", "damage_D"):
-            assert _rel(new[f"bwn.{s}.post.{n}"], old[f"bwn.{s}.post.{n}"]) <= 1e-12, (s, n)

@@ -1,0 +1,109 @@
+"""GPU parity for the parts of the reference's API surface that no shipped driver exercises (SURVEY section 8, rows a8 /
+a16 "unused variants"; constitutive.h:24,26): the two ductile-damage laws updateDamageGeneral's dispatcher keeps
+commented out, through the C ABI and through the reference-named drop-in entry points.  Fixture:
+tests/golden/sc6_damage_variants.npz (made by tests/golden/make_golden_damage_variants.py from oracle/_ref)."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, get_slots, params_from_golden, put_slots, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+REFDIR = ROOT / "oracle" / "_ref"
+GOLD = ROOT / "tests" / "golden"
+
+
+def _regen(script, tmp_path, out_name):
+    """run a golden generator with the reference's HOST code + GPU drop-in library instead of the all-CPU build"""
+    import sys
+    host = REFDIR / "liblpmc_b200host.so"
+    if not host.exists():
+        pytest.skip("oracle/_ref/liblpmc_b200host.so not built")
+    out = tmp_path / out_name
+    env = dict(os.environ, LPMB_REF_SO=str(host), LPMB_GOLDEN_OUT=str(out))
+    r = subprocess.run([sys.executable, str(GOLD / script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return np.load(out)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def _dv_ctx(lpm, g, pre):
+    """context for tests/golden/sc6_damage_variants.npz: topology + the damage state recorded before a call"""
+    N, nn = g["setup.neighbors"].shape
+    c = lpm.Context(N, 3, 2, nn, g["setup.conn"].shape[1])
+    c.set_params(**params_from_golden(g))
+    c.set_field("xyz", g["setup.xyz"])
+    c.set_field("xyz_initial", g["setup.xyz"])
+    c.set_neighbors(g["setup.neighbors"], g["setup.nsign"])   # derives nb_initial, mirror slots, distance_initial
+    for n in ("J2_dlambda", "J2_triaxiality", "damage_broken", "damage_w"):
+        c.set_field(n, g[f"{pre}.{n}"])
+    put_slots(c, "damage_D", g[f"{pre}.damage_D"])
+    put_slots(c, "damage_local", g[f"{pre}.damage_local"])
+    put_slots(c, "damage_nonlocal", g[f"{pre}.damage_nonlocal"])
+    return c
+
+
+@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
+def test_particlewise_local_damage_bit_exact(lpm, step):
+    """updateDuctileDamagePwiseLocal (constitutive.c:1529-1579; commented out in the reference's dispatcher, SURVEY row
+    a16): calls 2 and 3 detach 9 and 16 particles, each losing all its bonds in both directions"""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "sc6_damage_variants.npz")
+    pre, post = f"pwl.{step}.pre", f"pwl.{step}.post"
+    c = _dv_ctx(lpm, g, pre)
+    assert_same(c.get_field("distance_initial"), g["setup.distance_initial"], "distance_initial")
+    broken, pairs = c.update_damage(lpm.capi.DAMAGE_PWISE_LOCAL)
+    assert broken == int(g[f"pwl.{step}.broken"][0])
+    for n in ("damage_broken", "damage_w"):
+        assert_same(c.get_field(n), g[f"{post}.{n}"], n)
+    assert_same(get_slots(c, "damage_D", 2), g[f"{post}.damage_D"], "damage_D")
+    assert_same(get_slots(c, "damage_local", 2), g[f"{post}.damage_local"], "damage_local")
+    detached = np.flatnonzero((g[f"{post}.damage_local"][:, 0] == 1.0) & (g[f"{pre}.damage_local"][:, 0] != 1.0))
+    assert np.array_equal(pairs[:, 0], detached) and (pairs[:, 1] == -1).all()
+    c.close()
+
+
+@pytest.mark.parametrize("step", ["s1", "s2", "s3"])
+def test_bondwise_nonlocal_damage(lpm, step):
+    """updateDuctileDamageBwiseNonlocal (constitutive.c:1698-1753; commented out in the dispatcher): Gaussian average
+    over the bond list (exp() on the device vs glibc: 1e-12 on damage values, bit-exact on which bonds break)"""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "sc6_damage_variants.npz")
+    pre, post = f"bwn.{step}.pre", f"bwn.{step}.post"
+    c = _dv_ctx(lpm, g, pre)
+    broken, pairs = c.update_damage(lpm.capi.DAMAGE_BWISE_NONLOCAL)
+    assert broken == int(g[f"bwn.{step}.broken"][0])
+    assert_same(c.get_field("damage_broken"), g[f"{post}.damage_broken"], "damage_broken")
+    tol = 1e-12   # fp64 exp(): device libm vs glibc
+    assert rel_err(get_slots(c, "damage_nonlocal", 2), g[f"{post}.damage_nonlocal"]) <= tol
+    assert rel_err(get_slots(c, "damage_D", 2), g[f"{post}.damage_D"]) <= tol
+    assert rel_err(c.get_field("damage_w"), g[f"{post}.damage_w"]) <= tol
+    newly = (g[f"{pre}.damage_broken"] != 0) & (g[f"{post}.damage_broken"] == 0)
+    ii, jj = np.nonzero(newly)
+    assert np.array_equal(pairs, np.stack([ii, g["setup.neighbors"][ii, jj]], axis=1))   # i ascending, then slot ascending
+    c.close()
+
+
+def test_dropin_replays_damage_variant_golden_case(tmp_path):
+    """tests/golden/sc6_damage_variants.npz: updateDuctileDamagePwiseLocal / updateDuctileDamageBwiseNonlocal (reference
+    names, constitutive.h:24,26) through liblpmc_dropin.so, all three calls of each law.  The generator pokes the
+    multiplier / triaxiality fields into host memory between calls and announces it with
+    lpmc_dropin_invalidate_state() (include/lpmc_dropin.h)."""
+    new = _regen("make_golden_damage_variants.py", tmp_path, "dv.npz")
+    old = np.load(GOLD / "sc6_damage_variants.npz")
+    for s in ("s1", "s2", "s3"):
+        assert int(new[f"pwl.{s}.broken"][0]) == int(old[f"pwl.{s}.broken"][0])
+        assert int(new[f"bwn.{s}.broken"][0]) == int(old[f"bwn.{s}.broken"][0])
+        for n in ("damage_local", "damage_broken", "damage_w", "damage_D"):
+            assert np.array_equal(new[f"pwl.{s}.post.{n}"], old[f"pwl.{s}.post.{n}"]), (s, n)
+        assert np.array_equal(new[f"bwn.{s}.post.damage_broken"], old[f"bwn.{s}.post.damage_broken"])
+        for n in ("damage_nonlocal", "damage_w", "damage_D"):
+            assert _rel(new[f"bwn.{s}.post.{n}"], old[f"bwn.{s}.post.{n}"]) <= 1e-12, (s, n)
