@@ -164,6 +164,13 @@ int lpmb_solve_cg_device(lpmb_ctx *ctx, double rel, double abs_tol, int maxit, i
 int lpmb_calc_kntv(lpmb_ctx *ctx, const double *Ce, int ntype);
 int lpmb_compute_dl(lpmb_ctx *ctx);
 int lpmb_bond_force(lpmb_ctx *ctx, int plmode, int load_indicator);
+/* The reference's per-particle law entry points (constitutive.h:15,17,20): computeBondForceElastic(ii) for plmode 6
+ * (src/constitutive.c:228-283), computeBondForceIncrementalUpdating(ii) for plmode 4 (:167-225),
+ * computeBondForceJ2mixedLinear3D(ii) for plmode 0 (:466-686).  Same side effects as the reference: geometry (and
+ * return-map) outputs of ii AND of its neighbours across intact bonds, F / Pin (and slot-[2] state, J2_dlambda,
+ * dL_ave, stress_tensor := 0) of ii only; no computeStress, no switchStateV(2).  O(N) per call (API completeness;
+ * the assembly and the whole-lattice laws never go through it).  Other plmodes: LPMB_ERR_UNSUPPORTED. */
+int lpmb_bond_force_particle(lpmb_ctx *ctx, int plmode, int particle, int load_indicator);
 int lpmb_switch_state(lpmb_ctx *ctx, int flag);
 /* residual = dispBC_index*(Pex-Pin); returns ||residual||_2 and ||reaction||_2 (either may be NULL) */
 int lpmb_update_rr(lpmb_ctx *ctx, double *norm_residual, double *norm_reaction);

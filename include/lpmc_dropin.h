@@ -27,9 +27,12 @@
  *   constitutive.h:24,26       int updateDuctileDamagePwiseLocal / updateDuctileDamageBwiseNonlocal(const char *, int)
  *                              (commented out in the reference's dispatcher, constitutive.c:155-156)
  *                                                                  lpmb_update_damage (LPMB_DAMAGE_PWISE_LOCAL / _BWISE_NONLOCAL)
- *   constitutive.h:15-20       the per-particle computeBondForce*(int): symbols kept, fail loudly (exit 1) -- nothing
- *                              in the drivers calls them once stiffness.c is replaced; every law (plmode 0, 1, 3, 4,
- *                              5, 6) is reached through computeBondForceGeneral
+ *   constitutive.h:15,17,20    void computeBondForceElastic(int) / computeBondForceJ2mixedLinear3D(int) /
+ *                              computeBondForceIncrementalUpdating(int)                lpmb_bond_force_particle (6 / 0 / 4)
+ *   constitutive.h:16,18,19    computeBondForceJ2nonlinearIso(int), computeBondForceCPMiehe(int),
+ *                              computeBondForceJ2energyReturnMap(int,int): symbols kept, fail loudly (exit 1) -- their
+ *                              per-particle result depends on state only the dispatcher sets up (memo reset, serial
+ *                              in-place order); plmode 1, 3, 5 are reached through computeBondForceGeneral
  *
  * State ownership: the arrays these functions write (plastic state slots, damage_broken / damage_D / damage_w, nb,
  * bond forces ...) are uploaded once, before the first force evaluation -- so initial cracks set by the driver are

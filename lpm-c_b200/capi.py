@@ -71,6 +71,7 @@ lib.lpmb_solve_cg_device.argtypes = [c_vp, C.c_double, C.c_double, C.c_int, C.c_
 lib.lpmb_calc_kntv.argtypes = [c_vp, c_vp, C.c_int]
 lib.lpmb_compute_dl.argtypes = [c_vp]
 lib.lpmb_bond_force.argtypes = [c_vp, C.c_int, C.c_int]
+lib.lpmb_bond_force_particle.argtypes = [c_vp, C.c_int, C.c_int, C.c_int]
 lib.lpmb_switch_state.argtypes = [c_vp, C.c_int]
 lib.lpmb_update_rr.argtypes = [c_vp, c_dp, c_dp]
 lib.lpmb_update_damage.argtypes = [c_vp, C.c_int, c_ip, c_vp, C.c_int]
@@ -284,6 +285,10 @@ class Context:
 
     def bond_force(self, plmode: int, load_indicator: int = 1):
         _check(lib.lpmb_bond_force(self._h, plmode, load_indicator))
+
+    def bond_force_particle(self, plmode: int, particle: int, load_indicator: int = 1):
+        """the reference's per-particle law entry point for plmode 6 / 4 / 0 (computeBondForceElastic(ii), ...)"""
+        _check(lib.lpmb_bond_force_particle(self._h, plmode, int(particle), load_indicator))
 
     def compute_strain(self):
         _check(lib.lpmb_compute_strain(self._h))

@@ -582,11 +582,48 @@ void computeCab()
     CK(lpmb_compute_cab(g_ctx));
     down_d2("cp_Cab", cp_Cab, N, S * S);
 }
-void computeBondForceElastic(int i) { (void)i; not_built("computeBondForceElastic(i): per-particle evaluation is internal to the GPU assembly"); }
-void computeBondForceJ2mixedLinear3D(int ii) { (void)ii; not_built("computeBondForceJ2mixedLinear3D(ii): use computeBondForceGeneral(0, t)"); }
+/* per-particle law entry points (constitutive.h:15,17,20): one particle and its star through lpmb_bond_force_particle */
+static void particle_law(int mode, int ii)
+{
+    ensure_state();
+    const int N = nparticle, nn = nneighbors;
+    up_host_owned();
+    if (mode == 4) {
+        up_d2("xyz_temp", xyz_temp, N, 3);
+        up_d2("F_temp", F_temp, N, nn);
+    }
+    CK(lpmb_bond_force_particle(g_ctx, mode, ii, 1));
+    down_d2("F", F, N, nn);
+    DOWN1D("Pin", Pin, (size_t)NDIM * N);
+    if (mode == 4) {
+        down_d2("ddL", ddL, N, nn);
+        down_d2("ddL_total", ddL_total, N, 2);
+        down_d2("TddL_total", TddL_total, N, 2);
+        return;
+    }
+    down_d2("dL", dL, N, nn);
+    down_d2("csx", csx, N, nn);
+    down_d2("csy", csy, N, nn);
+    down_d2("csz", csz, N, nn);
+    down_d2("dL_total", dL_total, N, 2);
+    down_d2("TdL_total", TdL_total, N, 2);
+    if (mode == 0) {
+        down_d2("dL_ave", dL_ave, N, nn);
+        down_d2("ddLp", ddLp, N, nn);
+        down_d2("stress_tensor", stress_tensor, N, 2 * NDIM);
+        DOWN1D("J2_dlambda", J2_dlambda, N);
+        DOWN1D("pl_flag", pl_flag, N);
+        down_slots(2);
+    }
+}
+void computeBondForceElastic(int i) { particle_law(6, i); }
+void computeBondForceJ2mixedLinear3D(int ii) { particle_law(0, ii); }
+void computeBondForceIncrementalUpdating(int ii) { particle_law(4, ii); }
+/* the remaining per-particle laws keep call-order-dependent state that only the dispatcher defines (plmode 1: the
+ * state_v memo reset by computeBondForceGeneral, constitutive.c:114-117,946-959; plmode 3 and 5: serial in-place
+ * semantics, see lpmb_bond.cu) -> symbols kept, fail loudly */
 void computeBondForceJ2nonlinearIso(int ii) { (void)ii; not_built("computeBondForceJ2nonlinearIso(ii): use computeBondForceGeneral(5, t)"); }
 void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe(ii): use computeBondForceGeneral(1, t)"); }
-void computeBondForceIncrementalUpdating(int ii) { (void)ii; not_built("computeBondForceIncrementalUpdating(ii): use computeBondForceGeneral(4, t)"); }
 void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap(ii, t): use computeBondForceGeneral(3, t)"); }
 int updateDuctileDamageBwiseLocal(const char *d, int t) { return damage(d, t, 5); }
 int updateDuctileDamagePwiseLocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_PWISE_LOCAL); }

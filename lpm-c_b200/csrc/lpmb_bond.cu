@@ -1313,6 +1313,175 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
     return lpmb_switch_state(c, 2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-particle entry points   computeBondForceElastic(ii)             constitutive.c:228-283
+//                             computeBondForceIncrementalUpdating(ii) constitutive.c:167-225
+//                             computeBondForceJ2mixedLinear3D(ii)     constitutive.c:466-686
+// ---------------------------------------------------------------------------------------------
+// The reference evaluates particle ii together with its "star" (ii + the neighbours across intact bonds): the
+// geometry / return-map passes rewrite dL, dL_total, TdL_total, cs* (ddLp, pl_flag) of EVERY star member, the force
+// pass writes F, Pin (and the slot-[2] state, J2_dlambda, dL_ave, stress_tensor := 0) of ii only; nothing else may
+// change.  Every pass is a pure per-particle function of xyz and the slot-[0] state, so the whole-lattice kernels
+// above produce, for the star's rows, exactly the values of the restricted loops: they are run into scratch twins
+// of the output fields (initialised with the current contents) and only the star's / ii's rows are committed.
+// O(N) per call -- this exists for API completeness (nothing in the reference calls these once stiffness.c is
+// replaced by the assembly kernel), not for speed.
+template <typename T>
+__global__ void commit_rows_kernel(T *__restrict__ dst, const T *__restrict__ src, const int *__restrict__ rows, int nrows, int comps, int Np)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrows * comps)
+        return;
+    const size_t e = (size_t)(t / nrows) * Np + rows[t % nrows];
+    dst[e] = src[e];
+}
+
+static int pp_twin(lpmb_ctx *c, const char *name, void **out)
+{
+    Field *f = lpmb_field(c, name);
+    LPMB_REQUIRE(f, LPMB_ERR_STATE, "field %s missing", name);
+    const std::string tn = std::string("pp.") + name;
+    if (!c->fields.count(tn))
+        LPMB_TRY(lpmb_field_alloc(c, tn.c_str(), f->kind, f->type, f->comps));
+    f = lpmb_field(c, name);
+    Field *t = &c->fields[tn];
+    LPMB_CUDA(cudaMemcpyAsync(t->d, f->d, f->count * f->elem(), cudaMemcpyDeviceToDevice, c->stream));
+    *out = t->d;
+    return LPMB_OK;
+}
+
+static int pp_commit(lpmb_ctx *c, const char *name, const int *d_rows, int nrows)
+{
+    Field *f = lpmb_field(c, name);
+    Field *t = &c->fields[std::string("pp.") + name];
+    const int work = nrows * f->comps;
+    if (f->type == FT_F64)
+        commit_rows_kernel<double><<<lpmb_blocks(work, 128), 128, 0, c->stream>>>((double *)f->d, (const double *)t->d, d_rows, nrows, f->comps, c->Np);
+    else if (f->type == FT_I32)
+        commit_rows_kernel<int><<<lpmb_blocks(work, 128), 128, 0, c->stream>>>((int *)f->d, (const int *)t->d, d_rows, nrows, f->comps, c->Np);
+    else
+        commit_rows_kernel<signed char><<<lpmb_blocks(work, 128), 128, 0, c->stream>>>((signed char *)f->d, (const signed char *)t->d, d_rows,
+                                                                                     nrows, f->comps, c->Np);
+    LPMB_LAUNCH_CHECK(c);
+    return LPMB_OK;
+}
+
+extern "C" int lpmb_bond_force_particle(lpmb_ctx *c, int plmode, int ii, int load_indicator)
+{
+    (void)load_indicator;
+    LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    LPMB_REQUIRE(ii >= 0 && ii < c->N, LPMB_ERR_ARG, "particle index %d out of range", ii);
+    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "per-particle laws are single-GPU only");
+    LPMB_REQUIRE(plmode == 6 || plmode == 4 || plmode == 0, LPMB_ERR_UNSUPPORTED,
+                 "per-particle evaluation exists for plmode 6, 4 and 0; the laws of plmode %d keep call-order-dependent state that only "
+                 "computeBondForceGeneral defines (memo / in-place slot [0])", plmode);
+    BondView v;
+    LPMB_TRY(make_view(c, v));
+    const int Np = c->Np, nn = c->nn;
+    double *broken = fptr<double>(c, "damage_broken");
+    LPMB_REQUIRE(broken, LPMB_ERR_STATE, "damage_broken missing");
+    // the star: ii, then the neighbours across intact bonds in slot order, nb[ii] + 1 entries (constitutive.c:231-237)
+    std::vector<int> hn(nn);
+    std::vector<double> hb(nn);
+    int nb_ii = 0;
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    LPMB_CUDA(cudaMemcpy2D(hn.data(), sizeof(int), v.nbr + ii, (size_t)Np * sizeof(int), sizeof(int), nn, cudaMemcpyDeviceToHost));
+    LPMB_CUDA(cudaMemcpy2D(hb.data(), sizeof(double), broken + ii, (size_t)Np * sizeof(double), sizeof(double), nn, cudaMemcpyDeviceToHost));
+    LPMB_CUDA(cudaMemcpy(&nb_ii, v.nb + ii, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> star(1, ii);
+    for (int k = 0; k < nn; k++)
+        if (hb[k] > LPMB_EPS && hn[k] != -1)
+            star.push_back(hn[k]);
+    LPMB_REQUIRE((int)star.size() == nb_ii + 1, LPMB_ERR_STATE, "particle %d: nb = %d but %d intact bonds (the reference would overrun its list)", ii,
+                 nb_ii, (int)star.size() - 1);
+    int *d_rows = nullptr;
+    LPMB_CUDA(cudaMalloc(&d_rows, star.size() * sizeof(int)));
+    LPMB_CUDA(cudaMemcpyAsync(d_rows, star.data(), star.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    const int ns = (int)star.size();
+    const int g = lpmb_blocks(c->N, BT);
+    double *Kn = fptr<double>(c, "Kn"), *Tv = fptr<double>(c, "Tv"), *w = fptr<double>(c, "damage_w"), *L0 = fptr<double>(c, "distance_initial");
+    int rc = LPMB_OK;
+    auto run = [&]() -> int {
+        void *tF, *tPin;
+        LPMB_TRY(pp_twin(c, "F", &tF));
+        LPMB_TRY(pp_twin(c, "Pin", &tPin));
+        if (plmode == 4) {
+            void *tddL, *tddLt, *tTddLt;
+            LPMB_TRY(pp_twin(c, "ddL", &tddL));
+            LPMB_TRY(pp_twin(c, "ddL_total", &tddLt));
+            LPMB_TRY(pp_twin(c, "TddL_total", &tTddLt));
+            predictor_geometry_kernel<<<g, BT, 0, c->stream>>>(v, fptr<double>(c, "xyz_temp"), broken, Tv, (double *)tddL, (double *)tddLt,
+                                                               (double *)tTddLt);
+            LPMB_LAUNCH_CHECK(c);
+            predictor_force_kernel<<<g, BT, 0, c->stream>>>(v, Kn, Tv, broken, fptr<double>(c, "F_temp"), (double *)tddL, (double *)tddLt,
+                                                            (double *)tTddLt, fptr<double>(c, "csx"), fptr<double>(c, "csy"), fptr<double>(c, "csz"),
+                                                            (double *)tF, (double *)tPin);
+            LPMB_LAUNCH_CHECK(c);
+            for (const char *n : {"ddL", "ddL_total", "TddL_total"})
+                LPMB_TRY(pp_commit(c, n, d_rows, ns));
+        } else {
+            void *tdL, *tcx, *tcy, *tcz, *tdLt, *tTdLt, *tave;
+            LPMB_TRY(pp_twin(c, "dL", &tdL));
+            LPMB_TRY(pp_twin(c, "csx", &tcx));
+            LPMB_TRY(pp_twin(c, "csy", &tcy));
+            LPMB_TRY(pp_twin(c, "csz", &tcz));
+            LPMB_TRY(pp_twin(c, "dL_total", &tdLt));
+            LPMB_TRY(pp_twin(c, "TdL_total", &tTdLt));
+            LPMB_TRY(pp_twin(c, "dL_ave", &tave));
+            geometry_kernel<0><<<g, BT, 0, c->stream>>>(v, L0, fptr<double>(c, "dLp0"), broken, Tv, (double *)tdL, (double *)tcx, (double *)tcy,
+                                                        (double *)tcz, (double *)tdLt, (double *)tTdLt, nullptr);
+            LPMB_LAUNCH_CHECK(c);
+            if (plmode == 6) {
+                force_kernel<6><<<g, BT, 0, c->stream>>>(v, Kn, Tv, broken, (double *)tdL, (double *)tdLt, (double *)tTdLt, (double *)tcx,
+                                                         (double *)tcy, (double *)tcz, (double *)tave, (double *)tF, (double *)tPin);
+                LPMB_LAUNCH_CHECK(c);
+            } else {
+                LPMB_REQUIRE(c->params.count("J2_H") && c->params.count("J2_xi") && c->params.count("particle_volume"), LPMB_ERR_STATE,
+                             "J2_H / J2_xi / particle_volume not set");
+                Field *ce = lpmb_field(c, "Ce");
+                LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+                void *tdLp2, *tb2, *ta2, *tddLp, *tdl, *tpf;
+                LPMB_TRY(pp_twin(c, "dLp2", &tdLp2));
+                LPMB_TRY(pp_twin(c, "J2_beta2", &tb2));
+                LPMB_TRY(pp_twin(c, "J2_alpha2", &ta2));
+                LPMB_TRY(pp_twin(c, "ddLp", &tddLp));
+                LPMB_TRY(pp_twin(c, "J2_dlambda", &tdl));
+                LPMB_TRY(pp_twin(c, "pl_flag", &tpf));
+                j2_return_map_kernel<<<g, BT, 0, c->stream>>>(
+                    v, param(c, "particle_volume"), param(c, "J2_H"), param(c, "J2_xi"), (const double *)ce->d, fptr<int>(c, "type"),
+                    fptr<double>(c, "sigmay"), Kn, Tv, w, broken, L0, (double *)tdL, (double *)tdLt, (double *)tTdLt, (double *)tcx, (double *)tcy,
+                    (double *)tcz, fptr<double>(c, "dLp0"), fptr<double>(c, "J2_beta0"), fptr<double>(c, "J2_alpha0"), (double *)tdLp2, (double *)tb2,
+                    (double *)ta2, (double *)tddLp, (double *)tdl, (int *)tpf);
+                LPMB_LAUNCH_CHECK(c);
+                geometry_kernel<0><<<g, BT, 0, c->stream>>>(v, L0, (double *)tdLp2, broken, Tv, (double *)tdL, (double *)tcx, (double *)tcy,
+                                                            (double *)tcz, (double *)tdLt, (double *)tTdLt, nullptr);
+                LPMB_LAUNCH_CHECK(c);
+                force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, (double *)tdL, (double *)tdLt, (double *)tTdLt, (double *)tcx, (double *)tcy,
+                                                         (double *)tcz, (double *)tave, (double *)tF, (double *)tPin);
+                LPMB_LAUNCH_CHECK(c);
+                for (const char *n : {"ddLp", "pl_flag"})
+                    LPMB_TRY(pp_commit(c, n, d_rows, ns));
+                for (const char *n : {"dL_ave", "dLp2", "J2_beta2", "J2_alpha2", "J2_dlambda"})
+                    LPMB_TRY(pp_commit(c, n, d_rows, 1));
+                // memset(stress_tensor[ii], 0, ...)  constitutive.c:647
+                double *st = fptr<double>(c, "stress_tensor");
+                LPMB_REQUIRE(st, LPMB_ERR_STATE, "stress_tensor missing");
+                LPMB_CUDA(cudaMemset2DAsync(st + ii, (size_t)Np * sizeof(double), 0, sizeof(double), 6, c->stream));
+            }
+            for (const char *n : {"dL", "csx", "csy", "csz", "dL_total", "TdL_total"})
+                LPMB_TRY(pp_commit(c, n, d_rows, ns));
+        }
+        LPMB_TRY(pp_commit(c, "F", d_rows, 1));
+        LPMB_TRY(pp_commit(c, "Pin", d_rows, 1));
+        return LPMB_OK;
+    };
+    rc = run();
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_rows);
+    return rc;
+}
+
 extern "C" int lpmb_update_crack(lpmb_ctx *c)
 {
     LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");

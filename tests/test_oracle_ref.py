@@ -143,6 +143,32 @@ def test_damage_variants_golden_matches_reference_build(tmp_path):
     assert (old["bwn.s3.pre.damage_nonlocal"][:, 0] > thr).any()        # frozen branch (constitutive.c:1712-1717) taken
 
 
+def test_per_particle_golden_matches_reference_build(tmp_path):
+    """tests/golden/sc6_particle.npz (the per-particle law entry points called outside the dispatcher) regenerates
+    bit-identically; every call changes rows of the star only"""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    import os, subprocess, sys
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    out = tmp_path / "pp.npz"
+    subprocess.run([sys.executable, str(gold / "make_golden_particle.py")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, LPMB_GOLDEN_OUT=str(out)))
+    new, old = np.load(out), np.load(gold / "sc6_particle.npz")
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert np.array_equal(new[k], old[k]), k
+    nbr, broken = old["setup.neighbors"], old["s2.el.pre.damage_broken"]
+    prev = old["s2.el.pre.dL"]
+    for k, ii in enumerate(old["s2.el.particles"]):
+        cur = old[f"s2.el.c{k}.dL"]
+        star = {int(ii)} | {int(j) for j, b in zip(nbr[ii], broken[ii]) if j >= 0 and b > 1e-6}
+        touched = set(np.flatnonzero((cur != prev).any(axis=1)).tolist())
+        assert touched and touched <= star, (ii, touched - star)
+        prev = cur
+
+
 def test_golden_internal_consistency(golden):
     g = golden
     assert g["setup.xyz"].shape == (216, 3)

@@ -107,3 +107,74 @@ def test_dropin_replays_damage_variant_golden_case(tmp_path):
         assert np.array_equal(new[f"bwn.{s}.post.damage_broken"], old[f"bwn.{s}.post.damage_broken"])
         for n in ("damage_nonlocal", "damage_w", "damage_D"):
             assert _rel(new[f"bwn.{s}.post.{n}"], old[f"bwn.{s}.post.{n}"]) <= 1e-12, (s, n)
+
+
+# ---- per-particle law entry points (constitutive.h:15,17,20) -------------------------------------------------------
+PP_WRITES = {
+    4: ("ddL", "ddL_total", "TddL_total", "F", "Pin"),
+    6: ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin"),
+    0: ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "pl_flag", "dL_ave", "F", "Pin", "stress_tensor", "J2_dlambda", "dLp2",
+        "J2_beta2", "J2_alpha2"),
+}
+PP_STATE = ("dL", "dL_ave", "ddLp", "ddL", "csx", "csy", "csz", "F", "F_temp", "damage_broken", "damage_w", "dL_total", "TdL_total", "ddL_total",
+            "TddL_total", "stress_tensor", "J2_dlambda", "xyz", "xyz_temp", "Pin", "pl_flag", "nb")
+
+
+def _pp_ctx(lpm, g, pre):
+    from helpers import make_ctx
+    c = make_ctx(lpm, g)
+    for n in PP_STATE:
+        c.set_field(n, g[f"{pre}.{n}"])
+    put_slots(c, "dLp", g[f"{pre}.dLp"])
+    put_slots(c, "J2_beta", g[f"{pre}.J2_beta"])
+    put_slots(c, "J2_alpha", g[f"{pre}.J2_alpha"])
+    return c
+
+
+@pytest.mark.parametrize("tag,law", [("s1.pred", 4), ("s1.j2", 0), ("s1.el", 6), ("s2.j2", 0), ("s2.el", 6)])
+def test_per_particle_laws_bit_exact(lpm, tag, law):
+    """computeBondForceIncrementalUpdating(ii) / computeBondForceJ2mixedLinear3D(ii) / computeBondForceElastic(ii) called
+    outside the dispatcher, five particles in sequence (one with a broken bond, its partner, a corner, an interior one,
+    one of the loaded layer): after every call EVERY array the law may write equals the reference's bit for bit -- the
+    star's rows changed, all other rows did not (tests/golden/sc6_particle.npz; step 2 carries plastic history)."""
+    g = np.load(GOLD / "sc6_particle.npz")
+    c = _pp_ctx(lpm, g, f"{tag}.pre")
+    changed = 0
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        c.bond_force_particle(law, int(ii))
+        for n in PP_WRITES[law]:
+            want = g[f"{tag}.c{k}.{n}"]
+            assert_same(c.get_field(n), want, f"{tag} call {k} (particle {ii}): {n}")
+            base = n[:-1] if n.endswith("2") and n[:-1] in ("dLp", "J2_beta", "J2_alpha") else n
+            before = g[f"{tag}.pre.{base}"][..., 2] if base != n else g[f"{tag}.pre.{n}"]
+            changed += int((np.asarray(want) != np.asarray(before)).any())
+    assert changed > 0                                     # the calls really did something
+    if law == 0:
+        assert int(g[f"{tag}.c2.pl_flag"].sum()) > 0       # and the J2 case is plastic
+    c.close()
+
+
+def test_per_particle_law_rejects_other_plmodes(lpm):
+    g = np.load(GOLD / "sc6_particle.npz")
+    c = _pp_ctx(lpm, g, "s1.j2.pre")
+    for plmode in (1, 3, 5):
+        with pytest.raises(lpm.LPMBError):
+            c.bond_force_particle(plmode, 0)
+    with pytest.raises(lpm.LPMBError):
+        c.bond_force_particle(6, 216)
+    c.close()
+
+
+def test_dropin_replays_per_particle_golden_case(tmp_path):
+    """tests/golden/sc6_particle.npz with every call -- including the per-particle ones, by their reference names --
+    going through liblpmc_dropin.so.  Step 1 phases are reached through bit-exact calls only (FD tangent, predictor) or
+    one CG solve (1e-10), so: predictor phase bit-exact, J2 / elastic phases of step 1 to 1e-9."""
+    new = _regen("make_golden_particle.py", tmp_path, "pp.npz")
+    old = np.load(GOLD / "sc6_particle.npz")
+    for k in range(5):
+        for n in PP_WRITES[4]:
+            assert np.array_equal(new[f"s1.pred.c{k}.{n}"], old[f"s1.pred.c{k}.{n}"]), (k, n)
+        for tag, law in (("s1.j2", 0), ("s1.el", 6)):
+            for n in PP_WRITES[law]:
+                assert _rel(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]) <= 1e-9, (tag, k, n)
+    assert np.array_equal(new["s1.j2.c4.pl_flag"], old["s1.j2.c4.pl_flag"])
