@@ -210,6 +210,14 @@ int lpmb_field_copy(lpmb_ctx *ctx, const char *dst, const char *src);
 int lpmb_apply_disp_bc(lpmb_ctx *ctx, int type, char axis, double step);
 int lpmb_apply_force_bc(lpmb_ctx *ctx, int type, double step_x, double step_y, double step_z);
 
+/* ---- binary snapshots (checkpoint / resume) ------------------------ */
+/* The reference only has per-step TEXT dumps (data_handler.c:42-84) and in-memory roll-back state.  save: scalar
+ * parameters + every field, in device layout, to one compact file.  load: into a context created with the same
+ * (nparticle, dim, lattice, nneighbors, nconn_max); restores the state bit for bit, rebuilds the block pattern of K
+ * and the DoF mask; the tangent VALUES are not stored -- call lpmb_fd_stiffness (every load step starts with it). */
+int lpmb_snapshot_save(lpmb_ctx *ctx, const char *path);
+int lpmb_snapshot_load(lpmb_ctx *ctx, const char *path);
+
 /* ---- multi-GPU (one process per GPU; particle slabs = contiguous index ranges) ------------- */
 /* 128-byte NCCL unique id; rank 0 creates it, the harness broadcasts it. */
 int lpmb_dist_unique_id(void *id128);

@@ -72,6 +72,8 @@ lib.lpmb_calc_kntv.argtypes = [c_vp, c_vp, C.c_int]
 lib.lpmb_compute_dl.argtypes = [c_vp]
 lib.lpmb_bond_force.argtypes = [c_vp, C.c_int, C.c_int]
 lib.lpmb_bond_force_particle.argtypes = [c_vp, C.c_int, C.c_int, C.c_int]
+lib.lpmb_snapshot_save.argtypes = [c_vp, C.c_char_p]
+lib.lpmb_snapshot_load.argtypes = [c_vp, C.c_char_p]
 lib.lpmb_switch_state.argtypes = [c_vp, C.c_int]
 lib.lpmb_update_rr.argtypes = [c_vp, c_dp, c_dp]
 lib.lpmb_update_damage.argtypes = [c_vp, C.c_int, c_ip, c_vp, C.c_int]
@@ -309,6 +311,12 @@ class Context:
 
     def update_crack(self):
         _check(lib.lpmb_update_crack(self._h))
+
+    def snapshot_save(self, path):
+        _check(lib.lpmb_snapshot_save(self._h, str(path).encode()))
+
+    def snapshot_load(self, path):
+        _check(lib.lpmb_snapshot_load(self._h, str(path).encode()))
 
     def newton_iteration(self, plmode: int, load_indicator: int = 1, rel=1e-8, abs_tol=1e-12, maxit=None):
         it, nr = C.c_int(), C.c_double()

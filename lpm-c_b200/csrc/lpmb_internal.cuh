@@ -173,6 +173,7 @@ struct CellGrid {
 int lpmb_grid_build(lpmb_ctx *c, const double *d_xyz, double cell_size, CellGrid **out);
 void lpmb_grid_release(lpmb_ctx *c);
 int lpmb_set_connectivity_device(lpmb_ctx *c, const int *d_conn);
+int lpmb_rebuild_connectivity(lpmb_ctx *c);   // conn / block pattern from the device neighbour lists (lpmb_topology.cu)
 int lpmb_derive_topology(lpmb_ctx *c, bool initial_geometry);
 int lpmb_compute_stress(lpmb_ctx *c);
 int lpmb_refresh_mask(lpmb_ctx *c);

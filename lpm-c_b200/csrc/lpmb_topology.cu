@@ -296,6 +296,27 @@ extern "C" int lpmb_build_topology(lpmb_ctx *c, double cutoff1, double cutoff2)
     neighbor_search_kernel<<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, c->Np, c->nn, *g, xyz, 1.01 * cutoff1, 1.01 * cutoff2, nbr, nsign, d_over);
     LPMB_LAUNCH_CHECK(c);
     LPMB_TRY(lpmb_derive_topology(c, true));
+    int over = 0;
+    LPMB_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_over);
+    if (over) {
+        lpmb_set_error("lpmb_build_topology: more than nneighbors entries for some particle (the reference would overrun its arrays)");
+        return LPMB_ERR_ARG;
+    }
+    return lpmb_rebuild_connectivity(c);
+}
+
+// conn / nb_conn / K_pointer (and the block pattern of the stiffness matrix) from the neighbour lists on the device
+// (neighbor.c:49-141); also used after a snapshot was loaded (lpmb_io.cu)
+int lpmb_rebuild_connectivity(lpmb_ctx *c)
+{
+    int *nbr = fptr<int>(c, "neighbors");
+    signed char *nsign = fptr<signed char>(c, "nsign");
+    LPMB_REQUIRE(nbr && nsign, LPMB_ERR_STATE, "neighbour lists missing");
+    int *d_over;
+    LPMB_CUDA(cudaMalloc(&d_over, sizeof(int)));
+    LPMB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(int), c->stream));
     int *d_conn;
     LPMB_CUDA(cudaMalloc(&d_conn, (size_t)c->N * c->nconn * sizeof(int)));
     afem_conn_kernel<<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, c->Np, c->nn, c->nconn, nbr, nsign, d_conn, d_over);
@@ -306,8 +327,7 @@ extern "C" int lpmb_build_topology(lpmb_ctx *c, double cutoff1, double cutoff2)
     cudaFree(d_over);
     if (over) {
         cudaFree(d_conn);
-        lpmb_set_error("lpmb_build_topology: more than %s entries for some particle (the reference would overrun its arrays)",
-                       over == 1 ? "nneighbors" : "nneighbors_AFEM+1");
+        lpmb_set_error("lpmb_build_topology: more than nneighbors_AFEM+1 entries for some particle (the reference would overrun its arrays)");
         return LPMB_ERR_ARG;
     }
     const int rc = lpmb_set_connectivity_device(c, d_conn);

@@ -178,3 +178,37 @@ def test_dropin_replays_per_particle_golden_case(tmp_path):
             for n in PP_WRITES[law]:
                 assert _rel(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]) <= 1e-9, (tag, k, n)
     assert np.array_equal(new["s1.j2.c4.pl_flag"], old["s1.j2.c4.pl_flag"])
+
+
+# ---- binary snapshots (checkpoint / resume) -------------------------------------------
+def test_snapshot_resume_is_bit_identical(lpm, tmp_path):
+    """one plastic load step, lpmb_snapshot_save, a second load step -> A; a FRESH context, lpmb_snapshot_load, the
+    same second load step -> B; A == B bit for bit (state, parameters, topology, BC indices all travel in the file;
+    the block pattern of K and the DoF mask are rebuilt, the tangent is re-assembled by the step itself)"""
+    from helpers import make_ctx
+    g = np.load(GOLD / "sc6_j2.npz")
+    dbp, fbp = [(1, "z", 0.0)], [(2, 0.0, 0.0, -2000.0)]
+    names = ("xyz", "F", "Pin", "stress_tensor", "damage_w", "damage_nonlocal0", "dLp0", "dLp1", "J2_alpha1", "J2_beta1", "dL", "residual", "Pex")
+    c = make_ctx(lpm, g)
+    c.compute_dl()
+    lpm.driver.load_step(c, 0, dbp, fbp)
+    snap = tmp_path / "step1.lpmb"
+    c.snapshot_save(snap)
+    assert snap.stat().st_size > 216 * 18 * 8 * 10
+    log_a = lpm.driver.load_step(c, 0, dbp, fbp)
+    A = {n: c.get_field(n) for n in names}
+    N, nn, nconn = c.N, c.nn, c.nconn
+    c.close()
+    c2 = lpm.Context(N, 3, 2, nn, nconn)
+    c2.snapshot_load(snap)
+    log_b = lpm.driver.load_step(c2, 0, dbp, fbp)
+    assert log_b.newton_iterations == log_a.newton_iterations == int(g["newton_counts"][1])
+    assert log_b.cg_iterations == log_a.cg_iterations
+    for n in names:
+        assert_same(c2.get_field(n), A[n], n)
+    # a context of another shape refuses the file
+    c3 = lpm.Context(N + 32, 3, 2, nn, nconn)
+    with pytest.raises(lpm.LPMBError):
+        c3.snapshot_load(snap)
+    c3.close()
+    c2.close()
