@@ -212,3 +212,29 @@ def test_snapshot_resume_is_bit_identical(lpm, tmp_path):
         c3.snapshot_load(snap)
     c3.close()
     c2.close()
+
+
+# ---- examples/sc_block.c: the default problem device-resident from plain C ----------------------------------------
+def test_c_example_reproduces_default_case_known_answers(tmp_path):
+    """examples/sc_block.c (C host code over the C ABI only, O(N) device set-up) on n = 21 = the default case C1: Newton
+    iterations 2 2 1, CG iterations 80 / 106 in load step 1 and the step-1 mean displacement of the loaded layer
+    (SURVEY section 8(c) known answers; tests/golden/c1_result_disp.txt line 2); binary snapshot written."""
+    import re
+    exe = ROOT / "examples" / "sc_block"
+    if not exe.exists():
+        pytest.skip("examples/sc_block not built (run __graft_entry__.build())")
+    r = subprocess.run([str(exe), "21", "3", "3", str(tmp_path / "c1")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Particle number is 9261, stiffness matrix size is 2203713" in r.stdout
+    steps = re.findall(r"Loading step (\d+) has finished in (\d+) iterations; CG iterations:([ \d]+);", r.stdout)
+    assert [int(s[1]) for s in steps] == [2, 2, 1], r.stdout
+    cg1 = [int(x) for x in steps[0][2].split()]
+    # the lattice here starts at (-0.2, -0.2, -0.2); the reference's createCuboid shifts y and z by its box padding
+    # (initialization.c:240-284): same problem up to a translation, so CG may stop an iteration earlier or later
+    assert abs(cg1[0] - 80) <= 1 and abs(cg1[1] - 106) <= 1, cg1
+    assert (tmp_path / "c1_step0003.lpmb").stat().st_size > 9261 * 18 * 8 * 10
+    r1 = subprocess.run([str(exe), "21", "1"], capture_output=True, text=True, timeout=300)
+    uz = float(re.search(r"mean z-displacement of the loaded layer after 1 steps: (\S+)", r1.stdout).group(1))
+    gold = float((GOLD / "c1_result_disp.txt").read_text().split("\n")[1].split()[1])
+    assert gold == pytest.approx(-1.27857453e-03, rel=1e-8)
+    assert uz == pytest.approx(gold, rel=1e-6)
