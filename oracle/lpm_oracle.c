@@ -6,8 +6,9 @@
  * follows.  It is pinned (tests/test_oracle_port.py) bit-for-bit against the reference's own functions
  * running from oracle/_ref (the unmodified sources) on the committed golden case, and its CG reproduces the
  * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the three
- * remaining ductile-damage laws and computeStrain are restated at the end of the file as the reference's literal serial loops and
- * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz and sc6_j2.npz.
+ * remaining ductile-damage laws, the per-particle law entry points and computeStrain are restated at the end of the file as the reference's literal serial loops and
+ * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz, sc6_particle.npz and
+ * sc6_j2.npz.
  *
  * Layouts are the reference's logical ones, flattened row-major: per-bond a[i*nn+j], per-particle a[i*c+k],
  * DoF vectors v[dim*i+k], Pin[3*i+k]; three-slot state as separate arrays.  Strict IEEE: compile with
@@ -991,6 +992,147 @@ int oracle_damage_nonlocal_bondwise(int N, int nn, double L, double thr, double 
             w[e] = 1.0 - dD0[e];
         }
     return k;
+}
+
+/* ------------------------------------------------------------------ the per-particle law entry points, called
+ * outside the dispatcher: computeBondForceElastic(ii) constitutive.c:228-283 (law 6), computeBondForceIncrementalUpdating(ii)
+ * :167-225 (law 4), computeBondForceJ2mixedLinear3D(ii) :466-686 (law 0).  Literal: temporaries per member of the star
+ * (ii + neighbours across intact bonds), geometry / return map for every member, force pass and state for ii only. */
+void oracle_particle_law(int law, int ii, int N, int nn, double V, double J2_H, double J2_xi, const double *Ce, const int *type,
+                         const double *sigmay, const double *xyz, const double *xyz_temp, const int *neighbors, const int *nsign, const int *nbi,
+                         const int *nb, const double *L0, const double *cx0, const double *cy0, const double *cz0, const double *Kn,
+                         const double *Tv, const double *broken, const double *w, const double *F_temp, const double *dLp0, const double *beta0,
+                         const double *alpha0, double *dL, double *dLt, double *TdLt, double *csx, double *csy, double *csz, double *ddL,
+                         double *ddLt, double *TddLt, double *ddLp, int *pl_flag, double *dL_ave, double *F, double *Pin, double *stress,
+                         double *dlambda, double *dLp2, double *beta2, double *alpha2)
+{
+    int *star = (int *)malloc(sizeof(int) * (nn + 1));
+    const int ns = star_list(ii, nn, neighbors, broken, nb, star);
+    if (law == 4) {
+        for (int k = 0; k < ns; k++) {
+            const int i = star[k];
+            ddLt[2 * i] = ddLt[2 * i + 1] = TddLt[2 * i] = TddLt[2 * i + 1] = 0;
+            for (int j = 0; j < nbi[i]; j++) {
+                const long e = (long)i * nn + j;
+                const int nj = neighbors[e];
+                const double ax = xyz_temp[3 * i] - xyz_temp[3 * nj], ay = xyz_temp[3 * i + 1] - xyz_temp[3 * nj + 1],
+                             az = xyz_temp[3 * i + 2] - xyz_temp[3 * nj + 2];
+                const double dis0 = sqrt(ax * ax + ay * ay + az * az);
+                const double bx = xyz[3 * i] - xyz[3 * nj], by = xyz[3 * i + 1] - xyz[3 * nj + 1], bz = xyz[3 * i + 2] - xyz[3 * nj + 2];
+                const double dis1 = sqrt(bx * bx + by * by + bz * bz);
+                ddL[e] = broken[e] * (dis1 - dis0);
+                ddLt[2 * i + nsign[e]] += ddL[e];
+                TddLt[2 * i + nsign[e]] += Tv[e] * ddL[e];
+            }
+        }
+        const int i = ii;
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e], sg = nsign[e];
+            F[e] = F_temp[e] + 2.0 * Kn[e] * ddL[e] + 0.5 * (TddLt[2 * i + sg] + TddLt[2 * nj + sg]) + 0.5 * Tv[e] * (ddLt[2 * i + sg] + ddLt[2 * nj + sg]);
+            F[e] *= broken[e];
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+        free(star);
+        return;
+    }
+    /* plastic stretch the geometry passes subtract: slot [0] of every member, advanced by the return map (law 0) */
+    double *xdLp = (double *)malloc(sizeof(double) * ns * nn), *xbeta = (double *)malloc(sizeof(double) * ns * 6);
+    double *xalpha = (double *)malloc(sizeof(double) * ns), *xdl = (double *)calloc(ns, sizeof(double));
+    for (int k = 0; k < ns; k++) {
+        const int i = star[k];
+        for (int j = 0; j < nn; j++)
+            xdLp[k * nn + j] = dLp0[(long)i * nn + j];
+        for (int q = 0; q < 6; q++)
+            xbeta[k * 6 + q] = beta0[6 * i + q];
+        xalpha[k] = alpha0[i];
+    }
+    for (int k = 0; k < ns; k++)
+        geom_row(star[k], nn, xyz, neighbors, nsign, nbi, L0, xdLp + k * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+    if (law == 0) {
+        for (int k = 0; k < ns; k++) {
+            const int i = star[k];
+            double st[6] = {0}, dpl[6] = {0};
+            for (int j = 0; j < nbi[i]; j++) {
+                const long e = (long)i * nn + j;
+                double Fij = 2.0 * Kn[e] * dL[e] + TdLt[2 * i + nsign[e]] + Tv[e] * dLt[2 * i + nsign[e]];
+                Fij *= w[e];
+                const double of = opp_flag(i, j, nn, nn, nb, nbi, cx0, cy0, cz0, broken);
+                st[0] += of / V * L0[e] * Fij * csx[e] * csx[e];
+                st[1] += of / V * L0[e] * Fij * csy[e] * csy[e];
+                st[2] += of / V * L0[e] * Fij * csz[e] * csz[e];
+                st[3] += of / V * L0[e] * Fij * csy[e] * csz[e];
+                st[4] += of / V * L0[e] * Fij * csx[e] * csz[e];
+                st[5] += of / V * L0[e] * Fij * csx[e] * csy[e];
+            }
+            const double temp = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+            for (int q = 0; q < 3; q++)
+                st[q] -= temp;
+            for (int q = 0; q < 6; q++)
+                st[q] -= xbeta[k * 6 + q];
+            double seq = 0.0;
+            for (int q = 0; q < 6; q++)
+                seq += (q < 3 ? 1.0 : 2.0) * st[q] * st[q];
+            seq = sqrt(3.0 / 2.0 * seq);
+            const double yf = seq - (sigmay[i] + (1.0 - J2_xi) * J2_H * xalpha[k]);
+            if (yf > 0.0) {
+                pl_flag[i] = 1;
+                xdl[k] = yf / (3 * Ce[3 * type[i] + 2] + J2_H);
+            }
+            xalpha[k] += xdl[k];
+            for (int q = 0; q < 6; q++)
+                if (fabs(seq) > EPS) {
+                    dpl[q] = xdl[k] * 1.5 * st[q] / seq;
+                    xbeta[k * 6 + q] += 2. / 3. * J2_xi * J2_H * dpl[q];
+                }
+            for (int j = 0; j < nbi[i]; j++) {
+                const long e = (long)i * nn + j;
+                ddLp[e] = L0[e] * (dpl[0] * csx[e] * csx[e] + dpl[1] * csy[e] * csy[e] + dpl[2] * csz[e] * csz[e] + 2 * dpl[3] * csy[e] * csz[e] +
+                                   2 * dpl[4] * csx[e] * csz[e] + 2 * dpl[5] * csx[e] * csy[e]);
+                ddLp[e] *= broken[e];
+                xdLp[k * nn + j] += ddLp[e];
+            }
+        }
+        for (int k = 0; k < ns; k++)
+            geom_row(star[k], nn, xyz, neighbors, nsign, nbi, L0, xdLp + k * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+    }
+    const int i = ii;
+    if (law == 0)
+        for (int q = 0; q < 6; q++)
+            stress[6 * i + q] = 0.0;
+    Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+    for (int j = 0; j < nbi[i]; j++) {
+        const long e = (long)i * nn + j;
+        const int nj = neighbors[e], sg = nsign[e];
+        double stretch = dL[e];
+        if (law == 0) {
+            for (int jj = 0; jj < nn; jj++)
+                if (neighbors[(long)nj * nn + jj] == i)
+                    dL_ave[e] = 0.5 * (dL[e] + dL[(long)nj * nn + jj]);
+            stretch = dL_ave[e];
+        }
+        F[e] = 2.0 * Kn[e] * stretch + 0.5 * (TdLt[2 * i + sg] + TdLt[2 * nj + sg]) + 0.5 * Tv[e] * (dLt[2 * i + sg] + dLt[2 * nj + sg]);
+        F[e] *= law == 0 ? w[e] : broken[e];
+        Pin[3 * i] += csx[e] * F[e];
+        Pin[3 * i + 1] += csy[e] * F[e];
+        Pin[3 * i + 2] += csz[e] * F[e];
+    }
+    if (law == 0) {
+        for (int j = 0; j < nn; j++)
+            dLp2[(long)i * nn + j] = broken[(long)i * nn + j] * xdLp[j];
+        for (int q = 0; q < 6; q++)
+            beta2[6 * i + q] = xbeta[q];
+        alpha2[i] = xalpha[0];
+        dlambda[i] = xdl[0];
+    }
+    free(star);
+    free(xdLp);
+    free(xbeta);
+    free(xalpha);
+    free(xdl);
 }
 
 /* computeStrain, lpm_basic.c:127-249, with the LU of oracle/shim's LAPACKE_dgesv (row-major, first maximal pivot;

@@ -46,3 +46,17 @@ def test_dropin_exports_every_reference_entry_point():
     # and it needs the reference's globals from the driver it is linked into
     undef = subprocess.run(["nm", "-D", "--undefined-only", str(so)], capture_output=True, text=True, check=True).stdout
     assert " xyz" in undef and " K_global" in undef
+
+
+def test_c_example_fails_loudly_without_device(lpm):
+    """examples/sc_block (plain C over the C ABI) has no CPU path either"""
+    import subprocess
+    from pathlib import Path
+    import pytest
+    exe = Path(__file__).resolve().parents[1] / "examples" / "sc_block"
+    if not exe.exists():
+        pytest.skip("examples/sc_block not built")
+    if lpm.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([str(exe), "8", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr

@@ -245,6 +245,46 @@ def test_port_bondwise_nonlocal_damage_bit_exact(step):
     assert_same(w, g[f"{out}.damage_w"], "damage_w")
 
 
+@pytest.mark.parametrize("tag,law", [("s1.pred", 4), ("s1.j2", 0), ("s1.el", 6), ("s2.j2", 0), ("s2.el", 6)])
+def test_port_per_particle_laws_bit_exact(tag, law):
+    """oracle_particle_law = the reference's per-particle entry points (constitutive.c:167-283, 466-686) restated, against
+    tests/golden/sc6_particle.npz: five calls in sequence per phase, every written array after every call"""
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_particle.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    f8, i4 = np.float64, np.int32
+    pre = f"{tag}.pre"
+    a = {k: _c(g[f"{pre}.{k}"], f8).copy() for k in ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddL", "ddL_total", "TddL_total", "ddLp",
+                                                     "dL_ave", "F", "Pin", "stress_tensor", "J2_dlambda")}
+    a["pl_flag"] = _c(g[f"{pre}.pl_flag"], i4).copy()
+    a["dLp2"] = _c(g[f"{pre}.dLp"][..., 2], f8).copy()
+    a["J2_beta2"] = _c(g[f"{pre}.J2_beta"][..., 2], f8).copy()
+    a["J2_alpha2"] = _c(g[f"{pre}.J2_alpha"][:, 2], f8).copy()
+    ro = {k: _c(g[f"{pre}.{k}"], f8) for k in ("xyz", "xyz_temp", "damage_broken", "damage_w", "F_temp")}
+    dLp0, beta0, alpha0 = _c(g[f"{pre}.dLp"][..., 0], f8), _c(g[f"{pre}.J2_beta"][..., 0], f8), _c(g[f"{pre}.J2_alpha"][:, 0], f8)
+    nb = _c(g[f"{pre}.nb"], i4)
+    st = {k: _c(g[f"setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial", "type")}
+    sf = {k: _c(g[f"setup.{k}"], f8) for k in ("Ce", "sigmay", "distance_initial", "csx_initial", "csy_initial", "csz_initial", "Kn", "Tv")}
+    writes = {4: ("ddL", "ddL_total", "TddL_total", "F", "Pin"),
+              6: ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin"),
+              0: ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "pl_flag", "dL_ave", "F", "Pin", "stress_tensor", "J2_dlambda", "dLp2",
+                  "J2_beta2", "J2_alpha2")}[law]
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        lib.oracle_particle_law(C.c_int(law), C.c_int(int(ii)), C.c_int(N), C.c_int(nn), C.c_double(par["particle_volume"]), C.c_double(par["J2_H"]),
+                                C.c_double(par["J2_xi"]), _ptr(sf["Ce"]), _ptr(st["type"]), _ptr(sf["sigmay"]), _ptr(ro["xyz"]), _ptr(ro["xyz_temp"]),
+                                _ptr(st["neighbors"]), _ptr(st["nsign"]), _ptr(st["nb_initial"]), _ptr(nb), _ptr(sf["distance_initial"]),
+                                _ptr(sf["csx_initial"]), _ptr(sf["csy_initial"]), _ptr(sf["csz_initial"]), _ptr(sf["Kn"]), _ptr(sf["Tv"]),
+                                _ptr(ro["damage_broken"]), _ptr(ro["damage_w"]), _ptr(ro["F_temp"]), _ptr(dLp0), _ptr(beta0), _ptr(alpha0),
+                                _ptr(a["dL"]), _ptr(a["dL_total"]), _ptr(a["TdL_total"]), _ptr(a["csx"]), _ptr(a["csy"]), _ptr(a["csz"]),
+                                _ptr(a["ddL"]), _ptr(a["ddL_total"]), _ptr(a["TddL_total"]), _ptr(a["ddLp"]), _ptr(a["pl_flag"]), _ptr(a["dL_ave"]),
+                                _ptr(a["F"]), _ptr(a["Pin"]), _ptr(a["stress_tensor"]), _ptr(a["J2_dlambda"]), _ptr(a["dLp2"]), _ptr(a["J2_beta2"]),
+                                _ptr(a["J2_alpha2"]))
+        for n in writes:
+            assert_same(a[n].reshape(g[f"{tag}.c{k}.{n}"].shape), g[f"{tag}.c{k}.{n}"], f"{tag} call {k} (particle {ii}): {n}")
+
+
 @pytest.mark.parametrize("step", ["s1", "s2"])
 def test_port_compute_strain_bit_exact(golden, step):
     lib, C = _lib()
