@@ -47,12 +47,19 @@ struct BrickMatrix {
     int *perm = nullptr;             // [P] permuted row -> original particle (-1 = padding)
     int *inv = nullptr;              // [Np] original particle -> permuted row
     int *ic = nullptr;               // [3][Np] integer lattice coordinates
-    double *bval = nullptr;          // [nbricks][ncls][9][BR]
+    double *bval = nullptr;          // [nbricks][ncls][8 z-layers][9][64]
     double *stage = nullptr;         // [nbricks][3][NSLOT]
     double *ypart = nullptr;         // [3][P]
     double *r = nullptr, *p = nullptr, *ap = nullptr, *x = nullptr, *b = nullptr, *mask = nullptr;  // CG vectors [3][P]
     int cls_d[MAXCLS][3];            // displacement of each class (class 0 = diagonal)
     int key2cls[125];
+    // rows a class tile really needs, per (brick layer, class): local z-layers [zr[..][0], zr[..][1]) of the 8.  A row is
+    // needed when it exists and it, or its partner i+d, is OWNED: the top rows of a partial brick layer are empty, the
+    // upper CG-halo rows of a slab own no pair that touches an owned row (pairs are owned by their lower end), the lower
+    // halo rows only through classes that reach up into the slab.  Only that part of a tile is streamed from HBM.
+    unsigned char *zr = nullptr;     // [nbz][ncls][2]
+    std::vector<unsigned char> h_zr;
+    int nz = 0, own_z0 = 0, own_z1 = 0;
 };
 
 static std::map<lpmb_ctx *, BrickMatrix> g_bricks;
@@ -67,7 +74,7 @@ void lpmb_brick_release(lpmb_ctx *c)
         return;
     BrickMatrix &B = it->second;
     lpmb_peer_halo_release(c);
-    cudaFree(B.perm); cudaFree(B.inv); cudaFree(B.ic); cudaFree(B.bval); cudaFree(B.stage); cudaFree(B.ypart);
+    cudaFree(B.perm); cudaFree(B.inv); cudaFree(B.ic); cudaFree(B.bval); cudaFree(B.stage); cudaFree(B.ypart); cudaFree(B.zr);
     cudaFree(B.r); cudaFree(B.p); cudaFree(B.ap); cudaFree(B.x); cudaFree(B.b); cudaFree(B.mask);
     g_bricks.erase(it);
 }
@@ -176,7 +183,7 @@ __global__ void brick_fill_kernel(int N, int Np, const int *__restrict__ ic, con
             continue;  // negative half space: owned by the other end point
 #pragma unroll
         for (int e = 0; e < 9; e++)
-            bval[((b * ncls + u) * 9 + e) * BR + r] = val[((kbase + k) * 9 + e) * 32 + lane];
+            bval[(((b * ncls + u) * BE + (r >> 6)) * 9 + e) * 64 + (r & 63)] = val[((kbase + k) * 9 + e) * 32 + lane];
     }
 }
 
@@ -230,7 +237,7 @@ __global__ void brick_range_kernel(int i0, int count, int Np, long long P, const
 #define TILE_BYTES (TILE_DOUBLES * 8)
 
 struct BrickSmem {
-    double tile[NST][9][BR];
+    double tile[NST][BE][9][64];   // z-layer major: the needed z-range of a tile is one contiguous run
     double acc[3][NSLOT];
     double xs[3][NSLOT];
     unsigned long long full[NST];
@@ -265,8 +272,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 
 __global__ void __launch_bounds__(BR, 1)
-brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P, const double *__restrict__ bval, const double *__restrict__ x,
-                  double *__restrict__ ypart, double *__restrict__ stage, const double *__restrict__ scal, PeerWait halo_wait)
+brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P, const double *__restrict__ bval,
+                  const unsigned char *__restrict__ zr, const double *__restrict__ x, double *__restrict__ ypart, double *__restrict__ stage,
+                  const double *__restrict__ scal, PeerWait halo_wait)
 {
     extern __shared__ __align__(128) unsigned char brick_smem_raw[];
     BrickSmem &S = *reinterpret_cast<BrickSmem *>(brick_smem_raw);
@@ -288,8 +296,14 @@ brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P,
         const int s = (int)(t % NST);
         const long long brick = blockIdx.x + (t / ncls) * (long long)gridDim.x;
         const int u = (int)(t % ncls);
-        mbar_expect_tx(&S.full[s], TILE_BYTES);
-        bulk_g2s(&S.tile[s][0][0], bval + (brick * ncls + u) * (long long)TILE_DOUBLES, TILE_BYTES, &S.full[s]);
+        const int bzl = (int)(brick / ((long long)nbx * nby));
+        const int z0 = zr[(bzl * ncls + u) * 2], z1 = zr[(bzl * ncls + u) * 2 + 1];
+        const double *src = bval + (brick * ncls + u) * (long long)TILE_DOUBLES;
+        // only the z-layers [z0, z1) (nothing at all if empty): one bulk copy of 4 608 bytes per layer
+        const unsigned n = z1 > z0 ? (unsigned)((z1 - z0) * 9 * 64 * 8) : 0u;
+        mbar_expect_tx(&S.full[s], n);
+        if (n)
+            bulk_g2s(&S.tile[s][z0][0][0], src + z0 * 9 * 64, n, &S.full[s]);
     };
     if (r == 0)
         for (long long t = 0; t < NST && t < ntiles; t++)
@@ -316,22 +330,25 @@ brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P,
         __syncthreads();
         const double xi0 = S.xs[0][myslot], xi1 = S.xs[1][myslot], xi2 = S.xs[2][myslot];
         double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+        const unsigned char *zrb = zr + (size_t)bz * ncls * 2;
         for (int u = 0; u < ncls; u++, t++) {
             const int st = (int)(t % NST);
             mbar_wait(&S.full[st], (unsigned)((t / NST) & 1));
-            double a[9];
+            if (lz >= zrb[2 * u] && lz < zrb[2 * u + 1]) {  // rows outside the streamed z-range: not needed, tile part stale
+                double a[9];
 #pragma unroll
-            for (int e = 0; e < 9; e++)
-                a[e] = S.tile[st][e][r];
-            const int slot = myslot + c_cls_off[u];
-            const double xj0 = S.xs[0][slot], xj1 = S.xs[1][slot], xj2 = S.xs[2][slot];
-            o0 = fma(a[0], xj0, fma(a[1], xj1, fma(a[2], xj2, o0)));
-            o1 = fma(a[3], xj0, fma(a[4], xj1, fma(a[5], xj2, o1)));
-            o2 = fma(a[6], xj0, fma(a[7], xj1, fma(a[8], xj2, o2)));
-            if (u > 0) {  // class 0 is the diagonal block: no transposed partner
-                S.acc[0][slot] += fma(a[0], xi0, fma(a[3], xi1, a[6] * xi2));
-                S.acc[1][slot] += fma(a[1], xi0, fma(a[4], xi1, a[7] * xi2));
-                S.acc[2][slot] += fma(a[2], xi0, fma(a[5], xi1, a[8] * xi2));
+                for (int e = 0; e < 9; e++)
+                    a[e] = S.tile[st][lz][e][r & 63];
+                const int slot = myslot + c_cls_off[u];
+                const double xj0 = S.xs[0][slot], xj1 = S.xs[1][slot], xj2 = S.xs[2][slot];
+                o0 = fma(a[0], xj0, fma(a[1], xj1, fma(a[2], xj2, o0)));
+                o1 = fma(a[3], xj0, fma(a[4], xj1, fma(a[5], xj2, o1)));
+                o2 = fma(a[6], xj0, fma(a[7], xj1, fma(a[8], xj2, o2)));
+                if (u > 0) {  // class 0 is the diagonal block: no transposed partner
+                    S.acc[0][slot] += fma(a[0], xi0, fma(a[3], xi1, a[6] * xi2));
+                    S.acc[1][slot] += fma(a[1], xi0, fma(a[4], xi1, a[7] * xi2));
+                    S.acc[2][slot] += fma(a[2], xi0, fma(a[5], xi1, a[8] * xi2));
+                }
             }
             __syncthreads();  // tile consumed by everybody; the next class may hit the same slots
             if (r == 0 && t + NST < ntiles)
@@ -469,6 +486,14 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
         lo[2] = zl - B.q * std::floor((zl - lo[2]) / B.q + 1e-6);
         hi[2] = zh + B.q * std::floor((hi[2] - zh) / B.q + 1e-6);
     }
+    double own_zl = lo[2], own_zh = hi[2];  // z of the first / last OWNED lattice layer (single GPU: all of them)
+    if (c->world > 1) {
+        own_zl = 1e300, own_zh = -1e300;
+        for (int i = lpmb_own0(c); i < lpmb_own1(c); i++) {
+            own_zl = std::min(own_zl, hx[(size_t)2 * Np + i]);
+            own_zh = std::max(own_zh, hx[(size_t)2 * Np + i]);
+        }
+    }
     hx.clear();
     hx.shrink_to_fit();
     B.ox = lo[0];
@@ -478,6 +503,15 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
     B.nbx = (nx + BE - 1) / BE;
     B.nby = (ny + BE - 1) / BE;
     B.nbz = (nz + BE - 1) / BE;
+    B.nz = nz;
+    B.own_z0 = (int)llround((own_zl - lo[2]) / B.q);
+    B.own_z1 = (int)llround((own_zh - lo[2]) / B.q) + 1;
+    // test hook: emulate a slab on one GPU (rows outside [brick_own_z0, brick_own_z1) are then "halo": their products are
+    // not formed, exactly as in a slab run -- tests/test_solver_gpu.py compares the owned rows with the full format)
+    if (c->world == 1 && c->params.count("brick_own_z0") && c->params.count("brick_own_z1")) {
+        B.own_z0 = std::max(0, (int)param(c, "brick_own_z0"));
+        B.own_z1 = std::min(nz, (int)param(c, "brick_own_z1"));
+    }
     B.nbricks = B.nbx * B.nby * B.nbz;
     B.P = (long long)B.nbricks * BR;
     LPMB_REQUIRE(B.P < (1LL << 31), LPMB_ERR_UNSUPPORTED, "brick SpMV: %lld padded rows exceed 32-bit indices", B.P);
@@ -557,6 +591,18 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
                 }
             }
     LPMB_TRY(brick_upload_tables(B));
+    // needed z-range of every (brick layer, class) tile: rows z with z < nz and (z owned or z + dz owned), dz >= 0
+    B.h_zr.assign((size_t)B.nbz * B.ncls * 2, 0);
+    const bool trim = param(c, "brick_trim", 1.0) != 0.0;
+    for (int bz = 0; bz < B.nbz; bz++)
+        for (int u = 0; u < B.ncls; u++) {
+            const int need0 = trim ? std::max(0, B.own_z0 - B.cls_d[u][2]) : 0, need1 = trim ? std::min(B.nz, B.own_z1) : BE * B.nbz;
+            const int z0 = std::min(BE, std::max(0, need0 - BE * bz)), z1 = std::min(BE, std::max(0, need1 - BE * bz));
+            B.h_zr[((size_t)bz * B.ncls + u) * 2] = (unsigned char)(z1 > z0 ? z0 : 0);
+            B.h_zr[((size_t)bz * B.ncls + u) * 2 + 1] = (unsigned char)(z1 > z0 ? z1 : 0);
+        }
+    LPMB_CUDA(cudaMalloc(&B.zr, B.h_zr.size()));
+    LPMB_CUDA(cudaMemcpy(B.zr, B.h_zr.data(), B.h_zr.size(), cudaMemcpyHostToDevice));
     const size_t nent = (size_t)B.nbricks * B.ncls * BR;
     LPMB_CUDA(cudaMalloc(&B.bval, nent * 9 * sizeof(double)));
     LPMB_CUDA(cudaMalloc(&B.stage, (size_t)B.nbricks * 3 * NSLOT * sizeof(double)));
@@ -632,7 +678,10 @@ long long lpmb_brick_bytes(lpmb_ctx *c)
     if (it == g_bricks.end())
         return 0;
     const BrickMatrix &B = it->second;
-    const long long nent = (long long)B.nbricks * B.ncls * BR;
+    long long nent = 0;  // matrix entries actually streamed: the needed z-layers of every tile
+    for (int bz = 0; bz < B.nbz; bz++)
+        for (int u = 0; u < B.ncls; u++)
+            nent += (long long)B.nbx * B.nby * 64 * (B.h_zr[((size_t)bz * B.ncls + u) * 2 + 1] - B.h_zr[((size_t)bz * B.ncls + u) * 2]);
     const long long halo = (long long)B.nbricks * (NSLOT - BR) * 3 * 8;
     return nent * 72 + 2 * halo + 3 * B.P * 8 * 4;  // matrix + staging (w+r) + x, ypart (w+r), y
 }
@@ -708,7 +757,7 @@ int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const dou
 {
     BrickMatrix &B = g_bricks[c];
     const int grid = B.nbricks < c->sm_count ? B.nbricks : c->sm_count;
-    brick_spmv_kernel<<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, x, B.ypart, B.stage,
+    brick_spmv_kernel<<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, B.zr, x, B.ypart, B.stage,
                                                                   dot ? scal : nullptr, halo_wait);
     LPMB_LAUNCH_CHECK(c);
     if (dot)

@@ -1,0 +1,100 @@
+"""Multi-GPU correctness without torch: the slab-decomposed Newton iteration (halo exchange + all-reduces inside
+liblpmb200.so, brick SpMV streaming only the needed rows of every tile) reproduces the single-GPU full-format one.
+
+    python tests/dist_check_lite.py [n=24] [world=2]
+
+Spawns `world` processes itself (one per GPU); the NCCL unique id travels through a file.  Same checks as
+tests/dist_check.py (which rendezvouses through torch.distributed), a fraction of its start-up time."""
+import importlib
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+KEYS = ("xyz", "F", "stress_tensor", "dLp0", "damage_nonlocal0", "damage_w", "damage_broken", "Pin")
+
+
+def run_steps(c):
+    its, nrs = [], []
+    for _ in range(2):          # two consecutive Newton iterations (no snapshot restore): state really evolves
+        it, nr = c.newton_iteration(0, 1)
+        its.append(it)
+        nrs.append(nr)
+    broken, _ = c.update_damage(0)
+    c.update_crack()
+    c.switch_state(1)
+    return its, nrs, broken
+
+
+def child(rank, world, n, d):
+    import bench
+    lpm = importlib.import_module("lpm-c_b200")
+    partition = importlib.import_module("lpm-c_b200.partition")
+    uid_file = Path(d) / "uid.bin"
+    if rank == 0:
+        uid = lpm.Context.dist_unique_id()
+        (Path(d) / "uid.tmp").write_bytes(uid)
+        os.replace(Path(d) / "uid.tmp", uid_file)
+    else:
+        t0 = time.time()
+        while not uid_file.exists():
+            if time.time() - t0 > 30:
+                raise SystemExit("no unique id from rank 0")
+            time.sleep(0.05)
+        uid = uid_file.read_bytes()
+    slab = partition.make_slab(n, n * n, rank, world)
+    c, info = bench.build_workload(lpm, n, rank, slab=slab, unique_id=uid)
+    its, nrs, broken = run_steps(c)
+    own = slice(slab.own0, slab.own1)
+    out = {k: np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own]) for k in KEYS}
+    np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken]), mode=np.array([c.dist_mode()]),
+             norm0=np.array([info["norm_residual0"]]), spmv_bytes=np.array([c.spmv_bytes_bricks()]), **out)
+    c.close()
+
+
+def main():
+    if "--rank" in sys.argv:
+        a = sys.argv
+        child(int(a[a.index("--rank") + 1]), int(a[a.index("--world") + 1]), int(a[a.index("--n") + 1]), a[a.index("--dir") + 1])
+        return
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    world = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    with tempfile.TemporaryDirectory() as d:
+        procs = [subprocess.Popen([sys.executable, __file__, "--rank", str(r), "--world", str(world), "--n", str(n), "--dir", d])
+                 for r in range(world)]
+        rcs = [p.wait(timeout=240) for p in procs]
+        assert rcs == [0] * world, rcs
+        parts = [np.load(Path(d) / f"rank{r}.npz") for r in range(world)]
+        import bench
+        lpm = importlib.import_module("lpm-c_b200")
+        c1, info1 = bench.build_workload(lpm, n, 0, bricks=False)   # full-format SELL kernel as the cross-check
+        its1, nrs1, broken1 = run_steps(c1)
+        its, nrs, broken = list(parts[0]["its"]), list(parts[0]["nrs"]), int(parts[0]["broken"][0])
+        print(f"world={world} n={n}: CG iterations dist {its} single {its1}; residual norms dist {nrs} single {nrs1}; "
+              f"broken bonds dist {broken} single {broken1}; comm mode {[int(p['mode'][0]) for p in parts]}; "
+              f"brick SpMV bytes per rank {[int(p['spmv_bytes'][0]) for p in parts]}")
+        ok = its == its1 and broken == broken1
+        ok &= all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(nrs, nrs1))
+        ok &= abs(float(parts[0]["norm0"][0]) - info1["norm_residual0"]) <= 1e-12 * info1["norm_residual0"]
+        x0 = c1.get_field("xyz_initial")
+        for k in KEYS:
+            a = np.concatenate([p[k] for p in parts])
+            b = c1.get_field(k).reshape(n ** 3, -1)
+            if k == "xyz":
+                a, b = a - x0, b - x0
+            err = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+            print(f"  {k}: rel.err {err:.2e}")
+            ok &= err <= 1e-9
+        c1.close()
+        print("DIST_CHECK", "OK" if ok else "FAILED")
+        sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

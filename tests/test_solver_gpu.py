@@ -178,6 +178,50 @@ def test_brick_spmv_matches_full_format(lpm, dims):
     c.close()
 
 
+@pytest.mark.parametrize("dims,own", [((16, 12, 31), (2, 29)), ((9, 17, 14), (0, 12)), ((12, 8, 14), (2, 14)), ((8, 8, 21), (0, 21))])
+def test_brick_tiles_stream_only_needed_rows(lpm, dims, own):
+    """Only the z-layers of a class tile whose rows are needed are streamed (lpmb_brick.cu, `zr` table): empty rows of a
+    partial brick layer, the upper CG-halo rows of a slab (they own no pair touching an owned row) and, per class, the
+    lower-halo rows that do not reach into the slab.  A slab is emulated on one GPU with the test hook
+    brick_own_z0 / brick_own_z1: x is arbitrary on the 'halo' layers (as after a halo push), the products of the OWNED
+    rows must equal the full-format kernel's, and the masked CG must behave the same.  (2, 29) of 31 layers is the
+    216^3 / 8-GPU slab shape; (0, 12) / (2, 14) of 14 are the two slabs of tests/dist_check.py."""
+    lat = lpm.lattice.sc_block(*dims, h=0.5, origin=(0.3, -1.7, 2.0))
+    N = lat["xyz"].shape[0]
+    nx, ny, nz = dims
+    z = np.arange(N) // (nx * ny)
+    owned = (z >= own[0]) & (z < own[1])
+    c = lpm.Context(N, 3, 2, 18, 61)
+    c.set_params(radius=0.25, brick_own_z0=own[0], brick_own_z1=own[1])
+    c.set_field("xyz_initial", lat["xyz"])
+    c.set_connectivity(lat["conn"])
+    c.fill_test_pattern()
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(3 * N)
+    b = rng.standard_normal(3 * N)
+    y0 = c.spmv(x).reshape(N, 3)
+    bc = np.repeat(owned.astype(np.int32), 3)                # "ghost" DoFs are masked like lpmb_refresh_mask does in slab runs
+    bc[rng.integers(0, 3 * N, size=N // 10)] = 0
+    c.set_dof_mask(bc, np.ones(3 * N, dtype=np.int32))
+    d0, it0, ok0 = c.solve_cg(b * bc, use_mask=True)
+    full_bytes = None
+    for trim in (0.0, 1.0):
+        c.set_params(brick_trim=trim)
+        c.enable_bricks(True)
+        y1 = c.spmv(x).reshape(N, 3)
+        assert np.abs(y0[owned] - y1[owned]).max() <= 1e-13 * np.abs(y0).max(), trim
+        d1, it1, ok1 = c.solve_cg(b * bc, use_mask=True)
+        assert ok0 and ok1 and abs(it0 - it1) <= 1
+        assert np.linalg.norm(d0 - d1) <= 1e-9 * np.linalg.norm(d0)
+        nbytes = c.spmv_bytes_bricks()
+        if trim == 0.0:
+            full_bytes = nbytes
+        else:
+            assert nbytes < full_bytes                         # every case here has rows to skip
+        c.enable_bricks(False)
+    c.close()
+
+
 def test_brick_cg_on_reference_tangent(lpm, golden):
     """FD tangent of the golden 6^3 case through the brick kernel: reference iteration count and disp"""
     from helpers import make_ctx
