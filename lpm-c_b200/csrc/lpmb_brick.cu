@@ -10,8 +10,8 @@
 // lattice sites = 512 rows = one CTA of 512 threads, thread r <-> row r = local lattice position.  A pair {i,j}
 // is owned by the end point from which the displacement j-i lies in the positive half space (dz>0, or dz=0 &
 // dy>0, or dz=dy=0 & dx>0), so ownership does not depend on any numbering.  Displacements are grouped in classes
-// (30 positive ones + the diagonal for the simple-cubic 2-hop stencil); the brick stores, class-major and
-// coalesced over r, only the 3x3 blocks K_{i,i+d} -- no column indices: the neighbour of row r in class u sits
+// (30 positive ones + the diagonal for the simple-cubic 2-hop stencil); the brick stores, class-major, then z-layer-major and
+// coalesced over the 64 sites of a layer, only the 3x3 blocks K_{i,i+d} -- no column indices: the neighbour of row r in class u sits
 // at a fixed offset in the brick's 12 x 12 x 10 extended box, absent blocks are zeros.  For each class, thread r
 // takes its block from the shared-memory tile TMA delivered and forms
 //        own[r]      += K   x_j        (registers; x of the extended box is staged in shared memory)
@@ -227,7 +227,8 @@ __global__ void brick_range_kernel(int i0, int count, int Np, long long P, const
 }
 
 // ---- the SpMV ------------------------------------------------------------------------------------
-// One persistent CTA per SM walks over bricks.  The 36 KB class tiles ([9][512] doubles, contiguous in HBM) are
+// One persistent CTA per SM walks over bricks.  The 36 KB class tiles ([8 z-layers][9][64] doubles, contiguous in HBM;
+// only the z-layers whose rows are needed -- `zr` table -- are copied: one contiguous run) are
 // streamed into a 4-deep shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier transaction counts),
 // issued by one thread and running ahead across brick boundaries, so ~147 KB per SM are in flight regardless of
 // the per-class barrier.  x of the brick's extended box lives in shared memory too: x_j and the transposed
