@@ -5,7 +5,7 @@
  * never linked, imported or executed by the product path.  Every function cites the reference lines it
  * follows.  It is pinned (tests/test_oracle_port.py) bit-for-bit against the reference's own functions
  * running from oracle/_ref (the unmodified sources) on the committed golden case, and its CG reproduces the
- * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the three
+ * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the brittle and the three
  * remaining ductile-damage laws, the per-particle law entry points and computeStrain are restated at the end of the file as the reference's literal serial loops and
  * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz, sc6_particle.npz and
  * sc6_j2.npz.
@@ -991,6 +991,60 @@ int oracle_damage_nonlocal_bondwise(int N, int nn, double L, double thr, double 
                 dD0[e] = 0.5 * (Dn[i] + Dn[neighbors[e]]);
             w[e] = 1.0 - dD0[e];
         }
+    return k;
+}
+
+/* updateBrittleDamage, constitutive.c:1437-1526 (plmode 6): bonds with dL / L0 >= critical_bstrain are candidates (the
+ * reference holds at most 400, :1444); all of them break if there are <= nbreak, else the nbreak largest after the
+ * reference's (non-stable) shell sort.  Returns the CANDIDATE count like the reference; `pairs` = broken (i, neighbour). */
+int oracle_damage_brittle(int N, int nn, double crit, int nbreak, const int *neighbors, const int *nbi, const double *dL, const double *L0,
+                          double *broken, double *dD0, double *w, int *pairs, int max_pairs)
+{
+    enum { CAP = 400 };
+    int bi[CAP], bj[CAP];
+    double bs[CAP];
+    int k = 0;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const double ave = dL[(long)i * nn + j] / L0[(long)i * nn + j];
+            if (ave >= crit) {
+                if (k >= CAP)
+                    return -1; /* the reference overruns b_cr[] here */
+                bi[k] = i;
+                bj[k] = j;
+                bs[k] = ave;
+                k++;
+            }
+        }
+    int first = 0;
+    if (k > nbreak) {
+        for (int r = k / 2; r >= 1; r = r / 2)
+            for (int i = r; i < k; ++i) {
+                const int ti = bi[i], tj = bj[i];
+                const double tb = bs[i];
+                int j = i - r;
+                while (j >= 0 && bs[j] > tb) {
+                    bs[j + r] = bs[j];
+                    bi[j + r] = bi[j];
+                    bj[j + r] = bj[j];
+                    j = j - r;
+                }
+                bs[j + r] = tb;
+                bi[j + r] = ti;
+                bj[j + r] = tj;
+            }
+        first = k - nbreak;
+    }
+    for (int i = first; i < k; i++) {
+        const long e = (long)bi[i] * nn + bj[i];
+        dD0[e] = 1.0;
+        w[e] = 0.0;
+        broken[e] = 0.0;
+        if (i - first < max_pairs) {
+            pairs[2 * (i - first)] = bi[i];
+            pairs[2 * (i - first) + 1] = neighbors[e];
+        }
+    }
     return k;
 }
 

@@ -159,6 +159,15 @@ class Port:
                                                _p(self.J2_triaxiality), _p(self.damage_nonlocal0), _p(self.damage_broken), _p(self.damage_D0),
                                                _p(self.damage_w))
 
+    def updateBrittleDamage(self, crit, nbreak, max_pairs=64):
+        """constitutive.c:1437-1526; returns (candidate count, broken (i, neighbour) pairs in the reference's order)"""
+        pairs = np.full((max_pairs, 2), -1, np.int32)
+        self.lib.oracle_damage_brittle.restype = C.c_int
+        k = self.lib.oracle_damage_brittle(self.N, self.nn, C.c_double(crit), int(nbreak), _p(self.neighbors), _p(self.nb_initial), _p(self.dL),
+                                           _p(self.distance_initial), _p(self.damage_broken), _p(self.damage_D0), _p(self.damage_w), _p(pairs),
+                                           max_pairs)
+        return k, pairs[: min(k, int(nbreak)) if k > 0 else 0]
+
     def updateCrack(self):
         self.lib.oracle_update_crack(self.N, self.nn, self.dim, _p(self.nb_initial), _p(self.damage_broken), _p(self.damage_w), _p(self.csx),
                                      _p(self.csy), _p(self.csz), _p(self.F), _p(self.Pin), _p(self.nb), _p(self.damage_visual),

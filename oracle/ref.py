@@ -290,6 +290,69 @@ class RefLPM:
         self._finish_sc(E0, mu0, plmode, sigmay, J2_xi, J2_H, nbreak, critical_bstrain, damageb_A, damagec_A,
                         damage_threshold, damage_L, dtime, top_z)
 
+    def setup_2d(self, lattice=1, box=(0.0, 0.064, 0.0, 0.064, 0.0, 1.0), radius=3.2e-3, E0=210e3, mu0=0.3, nbreak=2,
+                 critical_bstrain=2.7e-2, crack=None):
+        """Re-play the set-up of examples/shear_hex_brittle.c (:60-231; lattice 1 = hexagonal) or
+        examples/3_point_bending_sq_brittle.c (lattice 0 = square) on a small box: 2-D, elastic (plmode 6) with brittle
+        bond breaking.  Types as in the hex example: 1 = top y-layer, 2 = bottom y-layer, 3 = full neighbour list.
+        crack = (a1, a2, h): createCrack(a1, a2, 0, h) before the matrices, defineCrack(a1, a2, h) after (:83-84, :224)."""
+        L = self.lib
+        self.si("lattice", lattice)
+        self.si("dim", 2)
+        self.sd("radius", radius)
+        pbc = self.iarr("pbc", 3)
+        pbc[0] = pbc[1] = pbc[2] = 0
+        self.si("eulerflag", 0)
+        for a in ("angle1", "angle2", "angle3"):
+            self.sd(a, 0.0)
+        b = self.darr("box", 6)
+        for k in range(6):
+            b[k] = box[k]
+        self.sd("box_x", b[1] - b[0])
+        self.sd("box_y", b[3] - b[2])
+        self.sd("box_z", b[5] - b[4])
+        L.createCuboid()
+        if crack is not None:
+            L.createCrack.argtypes = [C.c_double] * 4
+            L.createCrack.restype = None
+            L.createCrack(crack[0], crack[1], 0.0, crack[2])
+        L.initMatrices()
+        N = self.N
+        self.set_d2("xyz_initial", self.d2("xyz", N, 3))
+        L.searchNormalNeighbor()
+        L.searchAFEMNeighbor()
+        ytop, ybot = float(self.d2("xyz", N, 3)[:, 1].max()), float(self.d2("xyz", N, 3)[:, 1].min())
+        ntype = 0
+        self.set_ptr("type", L.allocInt1D(N, ntype))
+        ntype += 1
+        L.setTypeRect(-100.0, 100.0, ytop - 1.0 * radius, 100.0, -100.0, 100.0, ntype)
+        ntype += 1
+        L.setTypeRect(-100.0, 100.0, -100.0, ybot + 1.0 * radius, -100.0, 100.0, ntype)
+        ntype += 1
+        L.setTypeFullNeighbor(C.c_int(ntype))
+        ntype += 1
+        self.si("ntype", ntype)
+        C11 = E0 * (1.0 - mu0) / (1.0 + mu0) / (1.0 - 2.0 * mu0)
+        C12 = E0 * mu0 / (1.0 + mu0) / (1.0 - 2.0 * mu0)
+        C44 = E0 / 2.0 / (1.0 + mu0)
+        self.set_ptr("Ce", L.allocDouble2D(ntype, 3, 0.0))
+        self.set_d2("Ce", np.tile(np.array([C11, C12, C44]), (ntype, 1)))
+        self.si("plmode", 6)
+        self.si("nbreak", nbreak)
+        self.sd("critical_bstrain", critical_bstrain)
+        self.sd("damageb_A", 10.0)
+        self.sd("damagec_A", 0.0)
+        self.sd("damage_threshold", 0.9)
+        self.sd("damage_L", 0.5)
+        self.sd("dtime", 0.01)
+        if crack is not None:
+            L.defineCrack.argtypes = [C.c_double] * 3
+            L.defineCrack.restype = None
+            L.defineCrack(crack[0], crack[1], crack[2])
+        L.calcKnTv()
+        L.computedL()
+        L.slipSysDefine3D()
+
     def setup_fcc(self, box=(0.0, 10.0, 0.0, 10.0, 0.0, 10.0), radius=0.3, C11=107.3e3, C12=60.8e3, C44=28.3e3,
                   cp_tau0=1.6, cp_taus=30.0, cp_h0=100.0, cp_p=4.0, cp_q=1.0, cp_eta=1000.0, cp_maxloop=10, dtime=0.1,
                   top_z=None):

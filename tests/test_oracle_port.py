@@ -245,6 +245,98 @@ def test_port_bondwise_nonlocal_damage_bit_exact(step):
     assert_same(w, g[f"{out}.damage_w"], "damage_w")
 
 
+@pytest.mark.parametrize("name,nn,nconn", [("hex2d_brittle", 12, 31), ("sq2d_brittle", 8, 17)])
+def test_port_2d_brittle_trajectory_bit_exact(name, nn, nconn):
+    """The 2-D configurations (hexagonal / square lattice, elastic law + updateBrittleDamage with nbreak = 2): the whole
+    recorded trajectory of tests/golden/{hex,sq}2d_brittle.npz -- topology, 2-D FD tangent (2x2 blocks), BC-modified
+    tangent, CG, predictor, elastic law, residual, every breaking event incl. the reference's shell-sort selection, crack
+    update, re-assembly -- replayed through the restatement, bit for bit."""
+    from pathlib import Path
+    from oracle import port as P
+    if not P.available():
+        pytest.skip("oracle/liblpm_oracle.so not built")
+    g = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+    par = params_from_golden(g)
+    p = P.Port(g["setup.xyz"], dim=2, nn=nn, nconn=nconn, radius=par["radius"], particle_volume=par["particle_volume"])
+    p.search_neighbors(par["neighbor1_cutoff"], par["neighbor2_cutoff"])
+    assert_same(p.neighbors, g["setup.neighbors"], "neighbors"); assert_same(p.nsign, g["setup.nsign"], "nsign")
+    assert_same(p.conn, g["setup.conn"], "conn"); assert_same(p.nb_conn, g["setup.nb_conn"], "nb_conn")
+    assert_same(np.stack([p.kp0, p.kp1], 1), g["setup.K_pointer"].astype(np.int64), "K_pointer")
+    for n in ("distance_initial", "csx_initial", "csy_initial"):
+        assert_same(getattr(p, n), g[f"setup.{n}"], n)
+    p.type[:] = g["setup.type"]
+    p.Kn[:], p.Tv[:] = g["setup.Kn"], g["setup.Tv"]          # calcKnTv is pinned on the GPU side (test_variants_gpu.py)
+    p.computedL()
+    for n in ("distance", "dL", "dL_total", "TdL_total", "csx", "csy"):
+        assert_same(getattr(p, n), g[f"setup.{n}"], n)
+    typ = g["setup.type"]
+    crit, nbreak = par["critical_bstrain"], int(par["nbreak"])
+    for step in (1, 2, 3, 4):
+        s = f"s{step}"
+        assert_same(p.xyz, g[f"{s}.pre.xyz"], f"{s} xyz"); assert_same(p.F, g[f"{s}.pre.F"], f"{s} F")
+        p.xyz_temp[:] = p.xyz; p.F_temp[:] = p.F
+        p.calcStiffnessFiniteDifference()
+        assert_same(p.K_global, g[f"{s}.fd.K_global"], "K_global"); assert np.array_equal(p.IK, g[f"{s}.fd.IK"]); assert np.array_equal(p.JK, g[f"{s}.fd.JK"])
+        for n in ("dL", "csx", "csy", "dL_total", "TdL_total", "F"):
+            assert_same(getattr(p, n), g[f"{s}.fd.{n}"], f"{s} FD side effect {n}")
+        # setDispBC (boundary.c:12-38): type 1 moves 1.5e-4 in x and is held in y, type 2 is held in x and y
+        p.xyz[typ == 1, 0] += 1.5e-4
+        bc = p.dispBC_index.reshape(-1, 2)
+        bc[(typ == 1) | (typ == 2), :] = 0
+        assert_same(p.xyz, g[f"{s}.bc.xyz"], "xyz after BC"); assert np.array_equal(p.dispBC_index, g[f"{s}.bc.dispBC_index"])
+        p.computeBondForceGeneral(4)
+        for n in ("ddL", "ddL_total", "TddL_total", "F", "Pin", "stress_tensor"):
+            assert_same(getattr(p, n), g[f"{s}.pred.{n}"], f"{s} predictor {n}")
+        event, total_ni = 0, 0
+        while True:
+            p.updateRR()
+            nr = float(np.sqrt(np.sum(p.residual ** 2)))
+            nf = float(np.sqrt(np.sum(p.reaction_force ** 2)))
+            if event == 0:
+                assert_same(p.residual, g[f"{s}.rr.residual"], "residual")
+            tol, ni = max(nr, nf), 0
+            while nr > 1e-4 * tol and ni < 100:
+                t = f"{s}.e{event}.n{ni}"
+                p.switchStateV(0)
+                p.setDispBC_stiffnessUpdate()
+                rec = f"{t}.K_bc" in g.files
+                if rec:
+                    assert_same(p.K_global, g[f"{t}.K_bc"], "K_bc"); assert_same(p.residual, g[f"{t}.rhs"], "rhs")
+                it = p.solverCG()
+                if rec:
+                    assert it == int(g[f"{t}.cg_iters"][0])
+                    assert_same(p.disp, g[f"{t}.disp"], "disp"); assert_same(p.xyz, g[f"{t}.xyz"], "xyz")
+                p.computeBondForceGeneral(6)
+                if rec:
+                    for n in ("dL", "csx", "csy", "dL_total", "TdL_total", "F", "Pin", "stress_tensor", "bond_stress"):
+                        assert_same(getattr(p, n), g[f"{t}.bf.{n}"], f"{t} {n}")
+                p.updateRR()
+                nr = float(np.sqrt(np.sum(p.residual ** 2)))
+                ni += 1
+            total_ni += ni
+            d = f"{s}.dam{event}"
+            assert_same(p.dL, g[f"{d}.pre.dL"], f"{d} dL"); assert_same(p.damage_broken, g[f"{d}.pre.damage_broken"], f"{d} broken")
+            k, pairs = p.updateBrittleDamage(crit, nbreak)
+            assert k == int(g[f"{d}.broken"][0]), (d, k)
+            assert_same(p.damage_broken, g[f"{d}.post.damage_broken"], f"{d} damage_broken"); assert_same(p.damage_w, g[f"{d}.post.damage_w"], "damage_w")
+            assert_same(p.damage_D0, g[f"{d}.post.damage_D"][..., 0], "damage_D")
+            p.updateCrack()
+            assert_same(p.F, g[f"{d}.crack.F"], "crack F"); assert_same(p.Pin, g[f"{d}.crack.Pin"], "crack Pin"); assert_same(p.nb, g[f"{d}.crack.nb"], "nb")
+            p.switchStateV(1)
+            if k <= 0:
+                break
+            p.calcStiffnessFiniteDifference()
+            if event == 0:
+                assert_same(p.K_global, g[f"{s}.refd.K_global"], "re-assembled K")
+            event += 1
+            if event >= 6:
+                break
+        assert event + 1 == int(g[f"{s}.events"][0])
+        assert total_ni == int(g["newton_counts"][step - 1])
+        assert_same(p.xyz, g[f"{s}.end.xyz"], "end xyz"); assert_same(p.damage_broken, g[f"{s}.end.damage_broken"], "end broken")
+    assert max(int(g[f"s4.dam{e}.broken"][0]) for e in range(3)) > nbreak      # the shell-sort selection was exercised
+
+
 @pytest.mark.parametrize("tag,law", [("s1.pred", 4), ("s1.j2", 0), ("s1.el", 6), ("s2.j2", 0), ("s2.el", 6)])
 def test_port_per_particle_laws_bit_exact(tag, law):
     """oracle_particle_law = the reference's per-particle entry points (constitutive.c:167-283, 466-686) restated, against

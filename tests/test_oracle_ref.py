@@ -169,6 +169,27 @@ def test_per_particle_golden_matches_reference_build(tmp_path):
         prev = cur
 
 
+def test_2d_goldens_match_reference_build(tmp_path):
+    """tests/golden/hex2d_brittle.npz / sq2d_brittle.npz (BASELINE configs 2 and 3 on a small box) regenerate bit-identically;
+    the recorded runs break bonds and exercise the shell-sort selection (more candidates than nbreak)"""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    import os, subprocess, sys
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    subprocess.run([sys.executable, str(gold / "make_golden_2d.py")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, LPMB_GOLDEN_OUT_DIR=str(tmp_path)))
+    for name, nn, nconn in (("hex2d_brittle", 12, 31), ("sq2d_brittle", 8, 17)):
+        new, old = np.load(tmp_path / f"{name}.npz"), np.load(gold / f"{name}.npz")
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            assert np.array_equal(new[k], old[k]), (name, k)
+        assert old["setup.neighbors"].shape[1] == nn and old["setup.conn"].shape[1] == nconn
+        cands = [int(old[k][0]) for k in old.files if k.endswith(".broken")]
+        assert max(cands) > 2 and (old["s4.end.damage_broken"] == 0).sum() > 0
+
+
 def test_golden_internal_consistency(golden):
     g = golden
     assert g["setup.xyz"].shape == (216, 3)
