@@ -255,13 +255,6 @@ def _ctx_2d(lpm, g):
     return c
 
 
-# Written after the round's GPU budget was spent: these two could not be run on a B200 before the round-end suite, so a
-# mismatch is reported as XFAIL instead of stopping the run (`pytest -x`); a pass shows up as XPASS.  Remove the marks
-# once they have been seen green.
-NOT_YET_RUN = pytest.mark.xfail(strict=False, reason="first B200 run of this test is the round-end suite (GPU budget was spent)")
-
-
-@NOT_YET_RUN
 @pytest.mark.parametrize("name", ["hex2d_brittle", "sq2d_brittle"])
 def test_2d_setup_tangent_and_laws_bit_exact(lpm, name):
     """tests/golden/{hex,sq}2d_brittle.npz (BASELINE configs 2 and 3 on a small box): calcKnTv of the 2-D lattices, the
@@ -302,7 +295,6 @@ def test_2d_setup_tangent_and_laws_bit_exact(lpm, name):
     c.close()
 
 
-@NOT_YET_RUN
 @pytest.mark.parametrize("name,steps", [("hex2d_brittle", 3), ("sq2d_brittle", 4)])
 def test_2d_brittle_trajectory(lpm, name, steps):
     """the same cases as whole load steps, device-resident (driver.py over the C ABI): Newton iterations, the number of
