@@ -57,7 +57,7 @@ def run(args, lpm, dist, rank, world, local, bench):
     spmv_avg_ms = spmv_ms / max(1, spmv_calls)
     # per-rank SpMV bytes: only the slices holding owned rows are streamed
     own_frac = (slab.own1 - slab.own0) / slab.n_local
-    # (brick kernel: every brick of owned +- 2 layers is streamed, lpmb_spmv_bytes_bricks counts exactly that)
+    # (brick kernel: the needed z-layers of every class tile of owned +- 2 layers are streamed; lpmb_spmv_bytes_bricks counts exactly that)
     alg_bytes_rank = c.spmv_bytes_bricks() if info["bricks"] else int(c.spmv_bytes() * own_frac)
     kernel = ("brick_spmv_kernel + brick_gather_kernel<true> (symmetric CG SpMV + fused mask and p.Ap)" if info["bricks"]
               else "spmv_sell_kernel<3,true> (CG SpMV + fused p.Ap)")
