@@ -355,13 +355,13 @@ class RefLPM:
 
     def setup_fcc(self, box=(0.0, 10.0, 0.0, 10.0, 0.0, 10.0), radius=0.3, C11=107.3e3, C12=60.8e3, C44=28.3e3,
                   cp_tau0=1.6, cp_taus=30.0, cp_h0=100.0, cp_p=4.0, cp_q=1.0, cp_eta=1000.0, cp_maxloop=10, dtime=0.1,
-                  top_z=None):
+                  top_z=None, lattice=3):
         """Re-play the set-up of examples/FCC_Al_R0.3_001_tension.c (:62-229, :339-345 of the default driver for the
         call order): FCC lattice, Al elastic constants, crystal plasticity (plmode 1, 24 slip systems).  That example
         does not compile against the reference's current src/ (SURVEY section 2), its library functions do.
         Types: 1 top layer, 2 x-line, 3 y-line, 4 top fix point, 5 lower layer (:160-164)."""
         L = self.lib
-        self.si("lattice", 3)
+        self.si("lattice", lattice)   # 3 = FCC; 4 = BCC (same call order, initialization.c:391-560,636-815)
         self.si("dim", 3)
         self.sd("radius", radius)
         pbc = self.iarr("pbc", 3)

@@ -25,10 +25,20 @@ def state(r, prefix, g):
         g[f"{prefix}.{n}"] = r.get_cp(n)
 
 
+# BCC variant (LPMB_CP_LATTICE=4 -> tests/golden/bcc_cp.npz): 8 + 6 neighbours, 41 conn, 24 slip systems; the x- / y-line
+# types of the FCC example are empty on this lattice, so both end layers are clamped in x and y instead
+DBP_BCC = [(1, "x", 0.0), (1, "y", 0.0), (1, "z", 0.0), (5, "x", 0.0), (5, "y", 0.0), (5, "z", -2.0e-3)]
+
+
 def main():
+    import os
+    global DBP
+    lattice = int(os.environ.get("LPMB_CP_LATTICE", 3))
+    if lattice == 4:
+        DBP = DBP_BCC
     r = RefLPM.instance()
     r.threads(1)
-    r.setup_fcc(box=(0, 3.5, 0, 3.5, 0, 3.5))
+    r.setup_fcc(box=(0, 3.5, 0, 3.5, 0, 3.5), lattice=lattice)
     L = r.lib
     g = {}
     for n in ("xyz", "neighbors", "nsign", "nb_initial", "conn", "nb_conn", "K_pointer", "type", "distance_initial", "csx_initial",
@@ -67,8 +77,10 @@ def main():
         L.switchStateV(1)
         state(r, f"{s}.end", g)
     g["newton_counts"] = np.array(counts)
-    import os
-    out = Path(os.environ.get("LPMB_GOLDEN_OUT", Path(__file__).resolve().parent / "fcc_cp.npz"))
+    g["dbp_type"] = np.array([t for (t, _, _) in DBP])
+    g["dbp_axis"] = np.array([a for (_, a, _) in DBP])
+    g["dbp_step"] = np.array([v for (_, _, v) in DBP])
+    out = Path(os.environ.get("LPMB_GOLDEN_OUT", Path(__file__).resolve().parent / ("bcc_cp.npz" if lattice == 4 else "fcc_cp.npz")))
     np.savez_compressed(out, **g)
     print("wrote", out, round(out.stat().st_size / 1e6, 2), "MB; newton iterations per step:", counts)
 

@@ -190,6 +190,29 @@ def test_2d_goldens_match_reference_build(tmp_path):
         assert max(cands) > 2 and (old["s4.end.damage_broken"] == 0).sum() > 0
 
 
+def test_bcc_cp_golden_matches_reference_build(tmp_path):
+    """tests/golden/bcc_cp.npz (crystal plasticity on the BCC lattice: 14 neighbours, 41 conn, 24 slip systems) regenerates
+    bit-identically; slip systems are active in both load steps"""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    import os, subprocess, sys
+    from pathlib import Path
+    gold = Path(__file__).parent / "golden"
+    out = tmp_path / "bcc.npz"
+    subprocess.run([sys.executable, str(gold / "make_golden_cp.py")], check=True, stdout=subprocess.DEVNULL,
+                   env=dict(os.environ, LPMB_GOLDEN_OUT=str(out), LPMB_CP_LATTICE="4"))
+    new, old = np.load(out), np.load(gold / "bcc_cp.npz")
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        # (the reference's law leaves NaN in cp_dA_single / cp_A_single of one intermediate Newton iteration of step 2 --
+        # rolled back by switchStateV(0); the converged states are clean)
+        assert np.array_equal(new[k], old[k], equal_nan=old[k].dtype.kind == "f"), k
+    assert not np.isnan(old["s2.end.cp_A_single"]).any() and not np.isnan(old["s2.end.F"]).any()
+    assert old["setup.neighbors"].shape[1] == 14 and old["setup.conn"].shape[1] == 41
+    assert int(old["s1.end.cp_Jact"].sum()) > 0 and int(old["s2.end.cp_Jact"].sum()) > 0
+
+
 def test_golden_internal_consistency(golden):
     g = golden
     assert g["setup.xyz"].shape == (216, 3)

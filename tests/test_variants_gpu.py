@@ -316,3 +316,45 @@ def test_2d_brittle_trajectory(lpm, name, steps):
         assert rel_err(c.get_field("F"), g[f"{s}.end.F"]) <= 1e-9
     assert (g[f"s{steps}.end.damage_broken"] == 0).sum() > 0
     c.close()
+
+
+# ---- BCC lattice (8 + 6 neighbours, 41 conn, 24 slip systems): crystal plasticity on the reference's fifth lattice --------
+NOT_YET_RUN = pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first B200 run is the round-end suite")
+
+
+@NOT_YET_RUN
+def test_bcc_crystal_plasticity(lpm):
+    """tests/golden/bcc_cp.npz (tests/golden/make_golden_cp.py with LPMB_CP_LATTICE=4): topology from the O(N) device
+    builder, calcKnTv of the BCC lattice (stiffness.c:236-266), computeCab bit-exact; two load steps of the Miehe law
+    device-resident: Newton iteration counts and active slip systems identical, displacements 1e-9"""
+    g = np.load(GOLD / "bcc_cp.npz")
+    par = {str(k): float(v) for k, v in zip(g["param_names"], g["params"])}
+    N, nn = g["setup.neighbors"].shape
+    assert (nn, g["setup.conn"].shape[1], int(par["nslipSys"])) == (14, 41, 24)
+    c = lpm.Context(N, 3, 4, nn, g["setup.conn"].shape[1])
+    c.set_params(**{k: v for k, v in par.items() if k != "nslipSys"})
+    c.set_field("xyz", g["setup.xyz"])
+    c.set_field("xyz_initial", g["setup.xyz"])
+    c.build_topology(par["neighbor1_cutoff"], par["neighbor2_cutoff"])
+    c.set_field("type", g["setup.type"])
+    c.calc_kntv(g["setup.Ce"])
+    c.compute_dl()
+    c.set_schmid_tensor(g["setup.schmid_tensor"])
+    put_slots(c, "cp_gy", g["setup.cp_gy"])
+    assert_same(c.get_field("neighbors"), g["setup.neighbors"], "neighbors")
+    assert_same(c.get_field("nsign"), g["setup.nsign"], "nsign")
+    assert np.array_equal(c.k_pointer(), g["setup.K_pointer"])
+    assert_same(c.get_field("Kn"), g["setup.Kn"], "Kn")
+    assert_same(c.get_field("Tv"), g["setup.Tv"], "Tv")
+    c.compute_cab()
+    assert_same(c.get_field("cp_Cab"), g["setup.cp_Cab"], "cp_Cab")
+    dbp = [(int(t), str(a), float(v)) for t, a, v in zip(g["dbp_type"], g["dbp_axis"], g["dbp_step"])]
+    for step in (1, 2):
+        log = lpm.driver.load_step(c, 1, dbp, [])
+        assert log.newton_iterations == int(g["newton_counts"][step - 1])
+        s = f"s{step}.end"
+        u, u_ref = c.get_field("xyz") - g["setup.xyz"], g[f"{s}.xyz"] - g["setup.xyz"]
+        assert rel_err(u, u_ref) <= 1e-9
+        assert rel_err(c.get_field("F"), g[f"{s}.F"]) <= 1e-8
+        assert np.array_equal(c.get_field("cp_Jact"), g[f"{s}.cp_Jact"])
+    c.close()
