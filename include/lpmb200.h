@@ -24,8 +24,16 @@
  *                              updateDuctileDamageBwiseLocal (:1607-1695), updateDuctileDamagePwiseLocal (:1529-1579),
  *                              updateDuctileDamageBwiseNonlocal (:1698-1753)
  *   lpmb_update_crack          updateCrack(), src/constitutive.c:1399-1434
- *   lpmb_apply_disp_bc_mask    the effect of setDispBC_stiffnessUpdate{2,3}D, src/boundary.c:72-281,
+ *   lpmb_set_dof_mask          the effect of setDispBC_stiffnessUpdate{2,3}D, src/boundary.c:72-281,
  *                              as a DoF mask applied inside the solve (K is never edited)
+ *   lpmb_apply_disp_bc / _force_bc   setDispBC / setForceBC, src/boundary.c:12-70, on the resident arrays
+ *   lpmb_bond_force_particle   computeBondForceElastic / IncrementalUpdating / J2mixedLinear3D(ii),
+ *                              src/constitutive.c:167-283, 466-686
+ *   lpmb_compute_strain        computeStrain(), src/lpm_basic.c:127-249
+ *   lpmb_compute_cab, lpmb_set_schmid_tensor   computeCab(), src/constitutive.c:1864-1917; plmode 1 of
+ *                              lpmb_bond_force = computeBondForceCPMiehe, :866-1396
+ *   lpmb_newton_iteration      one pass of the driver's Newton loop, src/lpmc_project.c:426-464
+ *   lpmb_snapshot_save / _load no counterpart (the reference has text dumps only, data_handler.c:42-84)
  *
  * The reference-named drop-in entry points (void solverCG(void) ... on the reference's process
  * globals) live in liblpmc_dropin (lpm-c_b200/csrc/dropin.c) and are thin wrappers over this ABI;
