@@ -994,6 +994,50 @@ int oracle_damage_nonlocal_bondwise(int N, int nn, double L, double thr, double 
     return k;
 }
 
+/* calcKnTv, stiffness.c:11-268: KnTve[type] = alpha * M_lattice * (C11, C12, C44)^T (alpha = radius for the 3-D lattices,
+ * 1 in 2-D; the dgemm of oracle/shim: s = sum_p a[p] b[p], then alpha * s), then per bond by shell; the simple-cubic
+ * lattice averages the two end particles' types (:194-200), the others use type[i] only.  lattice: 0 square, 1 hexagon,
+ * 2 SC, 3 FCC, 4 BCC.  KnTve is [ntype][3] here (the hexagon uses 2 of the 3). */
+void oracle_calc_kntv(int lattice, int N, int nn, int ntype, double radius, const double *Ce, const int *type, const int *neighbors,
+                      const int *nsign, const int *nbi, double *KnTve, double *Kn, double *Tv)
+{
+    const double s2 = sqrt(2.0), s3 = sqrt(3.0);
+    const double M0[9] = {1 / 2.0, -1 / 2.0, 0.0, 0.0, 0.0, 1 / 2.0, 0.0, 1.0 / 12.0, -1.0 / 12.0};
+    const double M1[4] = {s3 / 12.0, -s3 / 12.0, -s3 / 144.0, s3 / 48.0};
+    const double M2[9] = {1, -1, -1, 0, 0, 1, 0, 1.0 / 18.0, -1.0 / 18.0};
+    const double M3[9] = {0, 0, s2, s2 / 4.0, -s2 / 4.0, -s2 / 4.0, 0, s2 / 24.0, -s2 / 24.0};
+    const double M4[9] = {0., 0., s3, 1. / s3, -1. / s3, 0., 0., s3 / 14.0, s3 / 14.0};
+    const double *M = lattice == 0 ? M0 : lattice == 1 ? M1 : lattice == 2 ? M2 : lattice == 3 ? M3 : M4;
+    const int d = lattice == 1 ? 2 : 3;
+    const double alpha = lattice >= 2 ? radius : 1.0;
+    for (int k = 0; k < ntype; k++)
+        for (int i = 0; i < d; i++) {
+            double s = 0.0;
+            for (int p = 0; p < d; p++)
+                s += M[i * d + p] * Ce[3 * k + p];
+            KnTve[3 * k + i] = alpha * s;
+        }
+    const int tv = lattice == 1 ? 1 : 2; /* column of KnTve that holds Tv */
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int sh = nsign[e], ti = type[i];
+            if (lattice == 1) {
+                Kn[e] = KnTve[3 * ti];
+                Tv[e] = KnTve[3 * ti + 1];
+            } else if (sh == 0 || sh == 1) {
+                if (lattice == 2) {
+                    const int tj = type[neighbors[e]];
+                    Kn[e] = 0.5 * (KnTve[3 * ti + sh] + KnTve[3 * tj + sh]);
+                    Tv[e] = 0.5 * (KnTve[3 * ti + tv] + KnTve[3 * tj + tv]);
+                } else {
+                    Kn[e] = KnTve[3 * ti + sh];
+                    Tv[e] = KnTve[3 * ti + tv];
+                }
+            }
+        }
+}
+
 /* updateBrittleDamage, constitutive.c:1437-1526 (plmode 6): bonds with dL / L0 >= critical_bstrain are candidates (the
  * reference holds at most 400, :1444); all of them break if there are <= nbreak, else the nbreak largest after the
  * reference's (non-stable) shell sort.  Returns the CANDIDATE count like the reference; `pairs` = broken (i, neighbour). */

@@ -245,6 +245,30 @@ def test_port_bondwise_nonlocal_damage_bit_exact(step):
     assert_same(w, g[f"{out}.damage_w"], "damage_w")
 
 
+@pytest.mark.parametrize("name,lattice", [("sq2d_brittle", 0), ("hex2d_brittle", 1), ("sc6_j2", 2), ("fcc_cp", 3), ("bcc_cp", 4)])
+def test_port_calc_kntv_all_lattices_bit_exact(name, lattice):
+    """calcKnTv (stiffness.c:11-268) restated for the five lattices, against the Kn / Tv the reference computed for the
+    committed fixtures (square, hexagon, simple cubic with type averaging, FCC, BCC)"""
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    f8, i4 = np.float64, np.int32
+    Ce = _c(g["setup.Ce"], f8)
+    ntype = Ce.shape[0]
+    KnTve, Kn, Tv = np.zeros((ntype, 3)), np.zeros((N, nn)), np.zeros((N, nn))
+    lib.oracle_calc_kntv(C.c_int(lattice), C.c_int(N), C.c_int(nn), C.c_int(ntype), C.c_double(par["radius"]), _ptr(Ce),
+                         _ptr(_c(g["setup.type"], i4)), _ptr(_c(g["setup.neighbors"], i4)), _ptr(_c(g["setup.nsign"], i4)),
+                         _ptr(_c(g["setup.nb_initial"], i4)), _ptr(KnTve), _ptr(Kn), _ptr(Tv))
+    assert_same(Kn, g["setup.Kn"], "Kn")
+    assert_same(Tv, g["setup.Tv"], "Tv")
+    if "setup.KnTve" in g.files:
+        ref = g["setup.KnTve"]
+        assert_same(KnTve[:, : ref.shape[1]], ref, "KnTve")
+    assert np.abs(Kn).max() > 0 and np.abs(Tv).max() > 0
+
+
 @pytest.mark.parametrize("name,nn,nconn", [("hex2d_brittle", 12, 31), ("sq2d_brittle", 8, 17)])
 def test_port_2d_brittle_trajectory_bit_exact(name, nn, nconn):
     """The 2-D configurations (hexagonal / square lattice, elastic law + updateBrittleDamage with nbreak = 2): the whole
