@@ -5,10 +5,10 @@
  * never linked, imported or executed by the product path.  Every function cites the reference lines it
  * follows.  It is pinned (tests/test_oracle_port.py) bit-for-bit against the reference's own functions
  * running from oracle/_ref (the unmodified sources) on the committed golden case, and its CG reproduces the
- * reference's iteration counts (80 / 106 on the default case).  The alternative J2 laws (plmode 3 and 5), the brittle and the three
- * remaining ductile-damage laws, the per-particle law entry points and computeStrain are restated at the end of the file as the reference's literal serial loops and
- * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz, sc6_particle.npz and
- * sc6_j2.npz.
+ * reference's iteration counts (80 / 106 on the default case).  calcKnTv for the five lattices, crystal plasticity (plmode 1), the alternative
+ * J2 laws (plmode 3 and 5), the brittle and the three remaining ductile-damage laws, the per-particle law entry points and computeStrain are restated at the end of the file as the reference's literal serial loops and
+ * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz, sc6_particle.npz,
+ * fcc_cp.npz, bcc_cp.npz, hex2d_brittle.npz, sq2d_brittle.npz and sc6_j2.npz.
  *
  * Layouts are the reference's logical ones, flattened row-major: per-bond a[i*nn+j], per-particle a[i*c+k],
  * DoF vectors v[dim*i+k], Pin[3*i+k]; three-slot state as separate arrays.  Strict IEEE: compile with
@@ -1036,6 +1036,280 @@ void oracle_calc_kntv(int lattice, int N, int nn, int ntype, double radius, cons
                 }
             }
         }
+}
+
+/* ------------------------------------------------------------------ crystal plasticity (plmode 1)
+ * computeCab, constitutive.c:1864-1917: Cab[i][a][b] = -d(RSS_a)/d(gamma_b) of the lattice stress, per particle. */
+void oracle_cp_cab(int N, int nn, int S, double V, const int *nsign, const int *nb, const int *nbi, const double *Kn, const double *Tv,
+                   const double *dist, const double *csx, const double *csy, const double *csz, const double *cx0, const double *cy0,
+                   const double *cz0, const double *broken, const double *sch /* [S][6] */, double *Cab /* [N][S*S] */)
+{
+#define PROJ(e, q) (csx[e] * csx[e] * sch[6 * (q)] + csy[e] * csy[e] * sch[6 * (q) + 1] + csz[e] * csz[e] * sch[6 * (q) + 2] + \
+                    csy[e] * csz[e] * sch[6 * (q) + 3] + csx[e] * csz[e] * sch[6 * (q) + 4] + csx[e] * csy[e] * sch[6 * (q) + 5])
+    for (int i = 0; i < N; i++)
+        for (int m = 0; m < S; m++)
+            for (int n = 0; n < S; n++) {
+                double LSum[2] = {0, 0};
+                for (int j = 0; j < nbi[i]; j++) {
+                    const long e = (long)i * nn + j;
+                    LSum[nsign[e]] += Tv[e] * dist[e] * PROJ(e, n);
+                }
+                double acc = 0.;
+                for (int j = 0; j < nbi[i]; j++) {
+                    const long e = (long)i * nn + j;
+                    const double dF = -2.0 * Kn[e] * dist[e] * PROJ(e, n) - 2.0 * LSum[nsign[e]];
+                    const double of = opp_flag(i, j, nn, nn, nb, nbi, cx0, cy0, cz0, broken);
+                    acc += -of / V * dist[e] * dF * PROJ(e, m);
+                }
+                Cab[(long)i * S * S + m * S + n] = acc;
+            }
+#undef PROJ
+}
+
+/* row-major LU with partial pivoting exactly as oracle/shim's LAPACKE_dgesv (first maximal pivot); returns info */
+static int lu_solve_shim(int n, double *a, double *b)
+{
+    int info = 0;
+    for (int k = 0; k < n; k++) {
+        int p = k;
+        double amax = fabs(a[k * n + k]);
+        for (int i = k + 1; i < n; i++) {
+            const double v = fabs(a[i * n + k]);
+            if (v > amax) {
+                amax = v;
+                p = i;
+            }
+        }
+        if (a[p * n + k] == 0.0) {
+            if (info == 0)
+                info = k + 1;
+            continue;
+        }
+        if (p != k) {
+            for (int j = 0; j < n; j++) {
+                const double t = a[k * n + j];
+                a[k * n + j] = a[p * n + j];
+                a[p * n + j] = t;
+            }
+            const double t = b[k];
+            b[k] = b[p];
+            b[p] = t;
+        }
+        const double piv = a[k * n + k];
+        for (int i = k + 1; i < n; i++) {
+            const double l = a[i * n + k] / piv;
+            a[i * n + k] = l;
+            if (l != 0.0) {
+                for (int j = k + 1; j < n; j++)
+                    a[i * n + j] -= l * a[k * n + j];
+                b[i] -= l * b[k];
+            }
+        }
+    }
+    if (info != 0)
+        return info;
+    for (int i = n - 1; i >= 0; i--) {
+        double t = b[i];
+        for (int c = i + 1; c < n; c++)
+            t -= a[i * n + c] * b[c];
+        b[i] = t / a[i * n + i];
+    }
+    return 0;
+}
+
+/* computeBondForceCPMiehe, constitutive.c:866-1396, the part that is evaluated ONCE per particle (the reference memoises
+ * it in state_v[] and lets every star that contains the particle reuse it, :946-959): trial resolved shear stresses on the
+ * S slip systems, active-set outer loop (<= cp_maxloop), inner Newton on D dgamma = r (<= 20 iterations, tol 1e-4) with
+ * tanh/cosh hardening and power-law viscosity.  dL, dLt, TdLt, cs* hold the TRIAL geometry (slot-[0] plastic stretch).
+ * Writes the increments (ddLp, cp_dA, cp_dgy, cp_dA_single), cp_Jact, cp_RSS, pl_flag and the slot-[2] state.
+ * Returns 0, or i + 1 if the slip Jacobian of particle i is singular (the reference exits there, :1216-1221). */
+int oracle_cp_return_map(int N, int nn, int S, double V, double h0, double taus, double tau0, double q, double eta, double pp, double maxloop,
+                         double dtime, const int *nsign, const int *nb, const int *nbi, const double *Kn, const double *Tv, const double *w,
+                         const double *broken, const double *L0, const double *cx0, const double *cy0, const double *cz0, const double *dL,
+                         const double *dLt, const double *TdLt, const double *csx, const double *csy, const double *csz, const double *sch,
+                         const double *Cab, const double *dLp0, const double *gy0 /* [N][S] */, const double *A0 /* [N] */,
+                         const double *As0 /* [N][S] */, double *ddLp, double *dA, double *dgy, double *dAs, int *Jact, double *RSS,
+                         int *pl_flag, double *dLp2, double *gy2, double *A2, double *As2)
+{
+    double *gam = (double *)malloc(sizeof(double) * S), *r = (double *)malloc(sizeof(double) * S), *rhs = (double *)malloc(sizeof(double) * S);
+    double *D = (double *)malloc(sizeof(double) * S * S), *xgy = (double *)malloc(sizeof(double) * S), *yf = (double *)malloc(sizeof(double) * S);
+    double *xdL = (double *)malloc(sizeof(double) * nn);
+    int bad = 0;
+    for (int i = 0; i < N && !bad; i++) {
+        const long b0 = (long)i * nn;
+        double st[6] = {0}, xt[2] = {dLt[2 * i], dLt[2 * i + 1]}, xT[2] = {TdLt[2 * i], TdLt[2 * i + 1]};
+        for (int j = 0; j < nbi[i]; j++)
+            xdL[j] = dL[b0 + j];
+#define STRESS()                                                                                                      \
+    do {                                                                                                              \
+        memset(st, 0, sizeof st);                                                                                     \
+        for (int j = 0; j < nbi[i]; j++) {                                                                            \
+            const long e = b0 + j;                                                                                    \
+            double Fij = 2.0 * Kn[e] * xdL[j] + xT[nsign[e]] + Tv[e] * xt[nsign[e]];                                   \
+            Fij *= w[e];                                                                                              \
+            const double of = opp_flag(i, j, nn, nn, nb, nbi, cx0, cy0, cz0, broken);                                  \
+            st[0] += of / V * L0[e] * Fij * csx[e] * csx[e];                                                          \
+            st[1] += of / V * L0[e] * Fij * csy[e] * csy[e];                                                          \
+            st[2] += of / V * L0[e] * Fij * csz[e] * csz[e];                                                          \
+            st[3] += of / V * L0[e] * Fij * csy[e] * csz[e];                                                          \
+            st[4] += of / V * L0[e] * Fij * csx[e] * csz[e];                                                          \
+            st[5] += of / V * L0[e] * Fij * csx[e] * csy[e];                                                          \
+        }                                                                                                             \
+    } while (0)
+#define RSS_OF(m) (st[0] * sch[6 * (m)] + st[1] * sch[6 * (m) + 1] + st[2] * sch[6 * (m) + 2] + st[3] * sch[6 * (m) + 3] + \
+                   st[4] * sch[6 * (m) + 4] + st[5] * sch[6 * (m) + 5])
+        STRESS();
+        double tmax = 0.0;
+        for (int m = 0; m < S; m++) {
+            RSS[(long)i * S + m] = RSS_OF(m);
+            yf[m] = RSS[(long)i * S + m] - gy0[(long)i * S + m];
+            if (yf[m] > tmax)
+                tmax = yf[m];
+            xgy[m] = gy0[(long)i * S + m];
+        }
+        double xA = A0[i];
+        for (int m = 0; m < S; m++)
+            gam[m] = 0.0;
+        if (tmax <= EPS) {
+            for (int j = 0; j < nbi[i]; j++)
+                ddLp[b0 + j] = 0.0;
+            dA[i] = 0.0;
+            for (int m = 0; m < S; m++) {
+                Jact[(long)i * S + m] = 0;
+                dgy[(long)i * S + m] = 0.0;
+                dAs[(long)i * S + m] = 0.0;
+            }
+        } else {
+            int *J = Jact + (long)i * S;
+            int outer = 0;
+            pl_flag[i] = 1;
+            memset(J, 0, sizeof(int) * S);
+            for (;;) {
+                outer++;
+                double norm_r = 1.0;
+                memset(gam, 0, sizeof(double) * S);
+                memset(r, 0, sizeof(double) * S);
+                memset(rhs, 0, sizeof(double) * S);
+                memset(D, 0, sizeof(double) * S * S);
+                int inner = 0;
+                do {
+                    inner++;
+                    double dpl[6] = {0};
+                    for (int s2 = 0; s2 < S; s2++)
+                        for (int c = 0; c < 6; c++)
+                            dpl[c] += J[s2] * gam[s2] * sch[6 * s2 + c];
+                    xt[0] = xt[1] = xT[0] = xT[1] = 0;
+                    for (int j = 0; j < nbi[i]; j++) {
+                        const long e = b0 + j;
+                        ddLp[e] = L0[e] * (dpl[0] * csx[e] * csx[e] + dpl[1] * csy[e] * csy[e] + dpl[2] * csz[e] * csz[e] + dpl[3] * csy[e] * csz[e] +
+                                           dpl[4] * csx[e] * csz[e] + dpl[5] * csx[e] * csy[e]);
+                        ddLp[e] *= broken[e];
+                        xdL[j] = dL[e] - ddLp[e];
+                        xt[nsign[e]] += xdL[j];
+                        xT[nsign[e]] += Tv[e] * xdL[j];
+                    }
+                    STRESS();
+                    dA[i] = 0.0;
+                    for (int s2 = 0; s2 < S; s2++)
+                        dA[i] += gam[s2];
+                    xA = A0[i] + dA[i];
+                    const double h_hat = h0 / pow(cosh(h0 * xA / (taus - tau0)), 2.0);
+                    const double h_hatp = -2.0 * h0 * h0 / (taus - tau0) * tanh(h0 * xA / (taus - tau0)) * h_hat;
+                    for (int a = 0; a < S; a++) {
+                        double t1 = 0.0;
+                        for (int b = 0; b < S; b++) {
+                            const double hab = a == b ? h_hat : q * h_hat;
+                            t1 += J[b] * hab * gam[b];
+                        }
+                        dgy[(long)i * S + a] = J[a] * t1;
+                        xgy[a] = gy0[(long)i * S + a] + dgy[(long)i * S + a];
+                    }
+                    for (int m = 0; m < S; m++) {
+                        const double t1 = pow(1. + gam[m] * eta / dtime, 1. / pp);
+                        RSS[(long)i * S + m] = RSS_OF(m);
+                        r[m] = J[m] * (RSS[(long)i * S + m] - xgy[m] * t1);
+                        rhs[m] = r[m];
+                    }
+                    for (int m = 0; m < S; m++)
+                        for (int n = 0; n < S; n++) {
+                            if (J[m] == 1 && J[n] == 1) {
+                                double h_star = 0.0;
+                                for (int d = 0; d < S; d++) {
+                                    double hd = 0.0;
+                                    if (m == d && n == d)
+                                        hd = h_hat + h_hatp * gam[d];
+                                    else if (m == d && n != d)
+                                        hd = h_hatp * gam[d];
+                                    else if (m != d && n == d)
+                                        hd = q * (h_hat + h_hatp * gam[d]);
+                                    else
+                                        hd = q * h_hatp * gam[d];
+                                    h_star += J[d] * hd;
+                                }
+                                const double t1 = xgy[m] * (eta / pp / dtime * pow(1. + eta * gam[m] / dtime, (1. - pp) / pp));
+                                const double t2 = h_star * pow(1. + eta * gam[m] / dtime, (1. / pp));
+                                D[m * S + n] = m == n ? Cab[(long)i * S * S + m * S + n] + t1 + t2 : Cab[(long)i * S * S + m * S + n] + t2;
+                            } else if (m == n)
+                                D[m * S + n] = 1.0;
+                        }
+                    if (lu_solve_shim(S, D, rhs) > 0) {
+                        bad = i + 1;
+                        break;
+                    }
+                    for (int m = 0; m < S; m++)
+                        gam[m] += J[m] * rhs[m];
+                    double nr2 = 0.0;
+                    for (int m = 0; m < S; m++)
+                        nr2 += r[m] * r[m];
+                    norm_r = sqrt(nr2);
+                } while (norm_r > 1e-4 && inner < 20);
+                if (bad)
+                    break;
+                int minI = -1, maxI = -1;
+                double minY = 0.0, maxY = 0.0;
+                for (int m = 0; m < S; m++) {
+                    yf[m] = RSS[(long)i * S + m] - xgy[m];
+                    if (J[m] == 1 && gam[m] <= 0.0 && yf[m] < minY) {
+                        minY = yf[m];
+                        minI = m;
+                    }
+                }
+                if (minI != -1) {
+                    J[minI] = 0;
+                    continue;
+                }
+                for (int m = 0; m < S; m++)
+                    if (J[m] == 0 && yf[m] > 0.0 && yf[m] > maxY) {
+                        maxY = yf[m];
+                        maxI = m;
+                    }
+                if (maxI != -1) {
+                    J[maxI] = 1;
+                    if (outer < maxloop)
+                        continue;
+                }
+                break;
+            }
+            for (int m = 0; m < S; m++)
+                dAs[(long)i * S + m] = J[m] * gam[m];
+        }
+        /* slot [2]: what the star owner stores for itself (:1371-1379) */
+        for (int j = 0; j < nn; j++) {
+            double xd = dLp0[b0 + j];
+            if (j < nbi[i])
+                xd += ddLp[b0 + j];
+            dLp2[b0 + j] = broken[b0 + j] * xd;
+        }
+        for (int m = 0; m < S; m++) {
+            gy2[(long)i * S + m] = xgy[m];
+            As2[(long)i * S + m] = As0[(long)i * S + m] + dAs[(long)i * S + m];
+        }
+        A2[i] = xA;
+#undef STRESS
+#undef RSS_OF
+    }
+    free(gam); free(r); free(rhs); free(D); free(xgy); free(yf); free(xdL);
+    return bad;
 }
 
 /* updateBrittleDamage, constitutive.c:1437-1526 (plmode 6): bonds with dL / L0 >= critical_bstrain are candidates (the
