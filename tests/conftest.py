@@ -43,10 +43,12 @@ def ref():
     return r
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture
 def ref_c1(ref):
     """default driver configuration C1 (21^3 SC) set up by the reference's own code, after the first
-    FD assembly + BCs + predictor + updateRR of load step 1"""
+    FD assembly + BCs + predictor + updateRR of load step 1.  Function-scoped on purpose: the reference is one set of
+    process globals that the tests advance (solves, load steps), so every user gets a fresh set-up (~3 s) and the
+    known answers (80 then 106 CG iterations) do not depend on which tests ran before."""
     ref.setup_sc()
     nr, nf = ref.begin_step([(1, "z", 0.0)], [(2, 0.0, 0.0, -2000.0)])
     return {"ref": ref, "norm_residual": nr, "norm_reaction": nf}
