@@ -379,7 +379,7 @@ def _cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: i
     t_full = t_cg * scale_n * (n_full / m) + (t_step - t_cg) * scale_n
     return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": (f"reference's own switchStateV/setDispBC_stiffnessUpdate3D/solverCG/computeBondForceGeneral(0)/updateRR "
-                       f"(unmodified sources + open MKL stand-in, not Intel MKL) on an SC {m}^3 block ({N} particles): "
+                       f"(unmodified sources + open MKL stand-in with a threaded symmetric SpMV, not Intel MKL) on an SC {m}^3 block ({N} particles): "
                        f"{t_step:.3f} s per Newton iteration ({it_s} CG its, solverCG {t_cg:.3f} s), {steps} timed; "
                        f"extrapolated to {n_full}^3 as t_cg*(N/Ns)*(n/m) + t_rest*(N/Ns) (CG iterations grow ~ n)"),
             "sample_newton_it_per_s": 1.0 / t_step, "sample_particles": N, "sample_cg_iterations": it_s,

@@ -21,6 +21,7 @@
 static int g_threads = 1;
 static long g_spmv_calls = 0;
 static double g_spmv_seconds = 0.0;
+static double g_setup_seconds = 0.0; /* threaded baseline: one-off work per matrix handle, part of g_spmv_seconds */
 static int g_last_itercount = -1;
 int lpmb_shim_last_itercount(void) { return g_last_itercount; }
 
@@ -28,10 +29,12 @@ void lpmb_shim_set_threads(int threads) { g_threads = threads < 1 ? 1 : threads;
 int lpmb_shim_get_threads(void) { return g_threads; }
 long lpmb_shim_spmv_calls(void) { return g_spmv_calls; }
 double lpmb_shim_spmv_seconds(void) { return g_spmv_seconds; }
+double lpmb_shim_setup_seconds(void) { return g_setup_seconds; }
 void lpmb_shim_reset_counters(void)
 {
     g_spmv_calls = 0;
     g_spmv_seconds = 0.0;
+    g_setup_seconds = 0.0;
 }
 
 /* ------------------------------------------------------------------ CBLAS */
@@ -206,10 +209,11 @@ struct lpmb_shim_sparse_matrix {
     int base, rows, cols;
     int *rs, *re, *col;
     double *val;
-    /* lazily expanded full CSR for the threaded variant */
-    long *frp;
-    int *fcol;
-    double *fval;
+    /* threaded variant (timed CPU baseline only): row chunks of equal non-zero count, one per thread, and per-chunk
+     * overflow buffers for the transposed contributions that land behind the chunk (at most `band` rows behind it) */
+    int nchunk, band;
+    int *chunk;   /* [nchunk+1] first row of every chunk */
+    double *ovf;  /* [nchunk][band] */
 };
 
 sparse_status_t mkl_sparse_d_create_csr(sparse_matrix_t *A, const sparse_index_base_t indexing, const MKL_INT rows,
@@ -231,52 +235,44 @@ sparse_status_t mkl_sparse_d_create_csr(sparse_matrix_t *A, const sparse_index_b
 sparse_status_t mkl_sparse_destroy(sparse_matrix_t A)
 {
     if (A) {
-        free(A->frp);
-        free(A->fcol);
-        free(A->fval);
+        free(A->chunk);
+        free(A->ovf);
         free(A);
     }
     return SPARSE_STATUS_SUCCESS;
 }
 
-/* Expand the stored upper triangle into a full row-sorted CSR (threaded baseline only). */
-static void expand_full(struct lpmb_shim_sparse_matrix *m)
+/* Threaded symmetric SpMV works on the stored triangle directly (half the bytes of an expanded matrix, nothing to build
+ * per handle but two small tables -- solver.c:206 creates a new handle for every solve).  Rows are cut into one chunk
+ * per thread with equal non-zero counts.  A thread owns y on its chunk; the transposed products v*x_i that fall behind
+ * its chunk (columns j >= chunk end; the lattice matrix is banded, j - i <= band) go into its private overflow buffer,
+ * and after a barrier every thread adds the overflow parts that target its own rows, in chunk order. */
+static void plan_threaded(struct lpmb_shim_sparse_matrix *m, int nt)
 {
     const int n = m->rows, base = m->base;
-    long *cnt = (long *)calloc((size_t)n + 1, sizeof(long));
+    int band = 0;
+#pragma omp parallel for reduction(max : band) num_threads(nt) schedule(static)
     for (int i = 0; i < n; i++)
-        for (int k = m->rs[i] - base; k < m->re[i] - base; k++) {
-            int j = m->col[k] - base;
-            cnt[i + 1]++;
-            if (j != i)
-                cnt[j + 1]++;
+        if (m->re[i] > m->rs[i]) {
+            /* columns of a row are not assumed sorted */
+            for (int k = m->rs[i] - base; k < m->re[i] - base; k++)
+                if (m->col[k] - base - i > band)
+                    band = m->col[k] - base - i;
         }
-    for (int i = 0; i < n; i++)
-        cnt[i + 1] += cnt[i];
-    const long nnz = cnt[n];
-    m->frp = (long *)malloc(((size_t)n + 1) * sizeof(long));
-    memcpy(m->frp, cnt, ((size_t)n + 1) * sizeof(long));
-    m->fcol = (int *)malloc((size_t)nnz * sizeof(int));
-    m->fval = (double *)malloc((size_t)nnz * sizeof(double));
-    /* Lower-triangle entries of row j come from rows i<j, visited in ascending i, so filling
-     * them first keeps each full row sorted by column. */
-    long *pos = (long *)malloc((size_t)n * sizeof(long));
-    memcpy(pos, cnt, (size_t)n * sizeof(long));
-    for (int i = 0; i < n; i++)
-        for (int k = m->rs[i] - base; k < m->re[i] - base; k++) {
-            int j = m->col[k] - base;
-            if (j != i) {
-                m->fcol[pos[j]] = i;
-                m->fval[pos[j]++] = m->val[k];
-            }
-        }
-    for (int i = 0; i < n; i++)
-        for (int k = m->rs[i] - base; k < m->re[i] - base; k++) {
-            m->fcol[pos[i]] = m->col[k] - base;
-            m->fval[pos[i]++] = m->val[k];
-        }
-    free(pos);
-    free(cnt);
+    m->band = band;
+    m->nchunk = nt;
+    m->chunk = (int *)malloc(((size_t)nt + 1) * sizeof(int));
+    const long first = m->rs[0] - base, total = (long)(m->re[n - 1] - base) - first;
+    m->chunk[0] = 0;
+    int row = 0;
+    for (int t = 1; t < nt; t++) {
+        const long want = first + total * t / nt;
+        while (row < n && m->rs[row] - base < want)
+            row++;
+        m->chunk[t] = row;
+    }
+    m->chunk[nt] = n;
+    m->ovf = (double *)malloc((size_t)nt * (size_t)(band > 0 ? band : 1) * sizeof(double));
 }
 
 /* y = alpha*A*x + beta*y for SYMMETRIC/UPPER/NON_UNIT (solver.c:198-200,243). */
@@ -291,17 +287,53 @@ sparse_status_t mkl_sparse_d_mv(const sparse_operation_t operation, const double
     const double t0 = omp_get_wtime();
     struct lpmb_shim_sparse_matrix *m = A;
     const int n = m->rows, base = m->base;
-    if (g_threads > 1) {
-        if (!m->frp)
-            expand_full(m);
-        /* the matrix values may have been edited in place since the expansion was made
-         * only if a new handle was created (solver.c:206 creates one per solve). */
-#pragma omp parallel for num_threads(g_threads) schedule(static)
-        for (int i = 0; i < n; i++) {
-            double s = 0.0;
-            for (long k = m->frp[i]; k < m->frp[i + 1]; k++)
-                s += m->fval[k] * x[m->fcol[k]];
-            y[i] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[i];
+    if (g_threads > 1 && n > 0) {
+        if (!m->chunk || m->nchunk != g_threads) {
+            free(m->chunk);
+            free(m->ovf);
+            plan_threaded(m, g_threads);
+            g_setup_seconds += omp_get_wtime() - t0;
+        }
+        const int nt = m->nchunk, band = m->band;
+#pragma omp parallel num_threads(nt)
+        {
+            /* one chunk per thread; loops over chunks so that a smaller team than requested still covers all of them */
+            const int me = omp_get_thread_num(), team = omp_get_num_threads();
+            for (int t = me; t < nt; t += team) {
+                const int r0 = m->chunk[t], r1 = m->chunk[t + 1];
+                double *ov = m->ovf + (size_t)t * (band > 0 ? band : 1);
+                for (int j = 0; j < band; j++)
+                    ov[j] = 0.0;
+                for (int i = r0; i < r1; i++)
+                    y[i] = (beta == 0.0) ? 0.0 : beta * y[i];
+                for (int i = r0; i < r1; i++) {
+                    double s = 0.0;
+                    const double axi = alpha * x[i];
+                    for (int k = m->rs[i] - base; k < m->re[i] - base; k++) {
+                        const int j = m->col[k] - base;
+                        const double v = m->val[k];
+                        s += v * x[j];
+                        if (j != i) {
+                            if (j < r1)
+                                y[j] += v * axi; /* j > i inside the own chunk (upper triangle) */
+                            else
+                                ov[j - r1] += v * axi;
+                        }
+                    }
+                    y[i] += alpha * s;
+                }
+            }
+#pragma omp barrier
+            for (int t = me; t < nt; t += team) {
+                const int r0 = m->chunk[t], r1 = m->chunk[t + 1];
+                for (int s = 0; s < t; s++) { /* earlier chunks spill forward only */
+                    const int e = m->chunk[s + 1];
+                    const double *ov = m->ovf + (size_t)s * (band > 0 ? band : 1);
+                    const int lo = r0 > e ? r0 : e, hi = r1 < e + band ? r1 : e + band;
+                    for (int i = lo; i < hi; i++)
+                        y[i] += ov[i - e];
+                }
+            }
         }
     } else {
         if (beta == 0.0)

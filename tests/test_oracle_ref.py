@@ -50,6 +50,38 @@ def test_default_case_cg_iteration_counts(ref_c1):
     assert np.isfinite(xyz).all()
 
 
+def test_threaded_cpu_baseline_solves_like_the_serial_reference(ref_c1):
+    """bench.py times the reference with all host threads; the shim then runs a threaded symmetric SpMV on the stored
+    triangle (chunked rows + overflow buffers).  Same matrix, same rhs: the threaded solve must agree with the serial one
+    up to summation order -- same iteration count +-1, disp to 1e-9 -- also when the chunks are shorter than the band
+    (12 threads on 27 783 rows with a band of ~2 700) and with fewer rows than threads' worth of work at the edges."""
+    import scipy.sparse as sp
+    r = ref_c1["ref"]
+    L = r.lib
+    L.switchStateV(0)
+    L.setDispBC_stiffnessUpdate3D()
+    xyz0, rhs = r.get("xyz"), r.get("residual")
+    K, IK, JK = r.get("K_global"), r.get("IK"), r.get("JK")
+    n = 3 * r.N
+    U = sp.csr_matrix((K, JK - 1, IK - 1), shape=(n, n))
+    A = U + sp.triu(U, 1).T
+    L.solverCG()
+    it1, d1 = L.lpmb_shim_last_itercount(), r.get("disp")
+    assert it1 == 80
+    assert np.linalg.norm(A @ d1 - rhs) <= 2e-4 * np.linalg.norm(rhs)
+    try:
+        for nt in (3, 12, 64):
+            r.put("xyz", xyz0)
+            r.put("residual", rhs)
+            r.threads(nt)
+            L.solverCG()
+            it, d = L.lpmb_shim_last_itercount(), r.get("disp")
+            assert abs(it - it1) <= 1, (nt, it, it1)
+            assert np.linalg.norm(d - d1) <= 1e-9 * np.linalg.norm(d1), nt
+    finally:
+        r.threads(1)
+
+
 def test_golden_matches_reference_build(golden):
     """the committed fixture is bit-identical to what the oracle build produces today"""
     from oracle import ref as oref
