@@ -125,3 +125,53 @@ def test_distributed_cg_emulation_with_gloo():
         p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
     assert 0 < it < 200 and res <= 1.01e-4 and narrow_ok
+
+
+def test_ragged_slabs_for_carved_specimens():
+    """SURVEY 8(e): irregular specimens are cut at layer boundaries, balanced on the layer weights (sum of nb_conn);
+    the counts handed to lpmb_dist_set_slab must agree pairwise between neighbouring ranks"""
+    part = importlib.import_module("lpm-c_b200.partition")
+    # uniform layers that divide evenly: identical to make_slab
+    for nz, world in [(216, 8), (32, 4), (20, 2), (9, 1)]:
+        for r in range(world):
+            a, b = part.make_slab(nz, 7, r, world), part.make_ragged_slab([7] * nz, r, world)
+            assert a.set_slab_args() == b.set_slab_args() and a.n_local == b.n_local and a.first_global == b.first_global
+    # a notched plate: thin layers in the middle, weights != counts
+    rng = np.random.default_rng(20240607)
+    counts = [int(c) for c in np.r_[np.full(20, 400), np.full(9, 150), np.full(25, 400)] + rng.integers(0, 30, 54)]
+    weights = [c * (61 if 2 <= z < 52 else 40) for z, c in enumerate(counts)]
+    for world in (2, 3, 4, 8):
+        slabs = [part.make_ragged_slab(counts, r, world, weights) for r in range(world)]
+        assert slabs[0].z0 == 0 and slabs[-1].z1 == len(counts) and slabs[0].first_global == 0
+        assert sum(s.own1 - s.own0 for s in slabs) == sum(counts)
+        for s in slabs:
+            assert s.z1 - s.z0 >= 4
+            assert s.n_local == sum(counts[s.z0 - s.g_lo:s.z1 + s.g_hi]) and s.first_global == sum(counts[:s.z0 - s.g_lo])
+            assert s.own1 - s.own0 == sum(counts[s.z0:s.z1])
+        for a, b in zip(slabs[:-1], slabs[1:]):
+            assert a.z1 == b.z0
+            assert a.narrow_recv_hi == b.narrow_send_lo and b.narrow_recv_lo == a.narrow_send_hi
+            assert a.n_local - a.own1 == b.wide_send_lo and b.own0 == a.wide_send_hi
+            # global index ranges line up: my upper ghosts are the first particles my upper neighbour owns
+            assert a.first_global + a.own1 == b.first_global + b.own0
+        # optimal bottleneck: no contiguous partition with >= 4 layers per rank does better (brute force for small worlds)
+        if world <= 3:
+            import itertools
+            nz, best = len(counts), float("inf")
+            for cuts in itertools.combinations(range(4, nz - 3), world - 1):
+                c = (0,) + cuts + (nz,)
+                if min(b - a for a, b in zip(c[:-1], c[1:])) >= 4:
+                    best = min(best, max(sum(weights[a:b]) for a, b in zip(c[:-1], c[1:])))
+            assert max(s.weight for s in slabs) == best
+        # better than the equal-layer split whenever the layers differ
+        equal = [part.owned_layers(len(counts), r, world) for r in range(world)]
+        assert max(s.weight for s in slabs) <= max(sum(weights[a:b]) for a, b in equal)
+    with pytest.raises(ValueError):
+        part.make_ragged_slab([5] * 7, 0, 2)          # fewer than 4 layers per rank
+    # layer detection from z-slowest coordinates
+    z = np.repeat(0.5 * np.arange(6), [4, 4, 2, 2, 4, 4]) - 1.25
+    assert part.layer_counts(z, 0.5) == [4, 4, 2, 2, 4, 4]
+    with pytest.raises(ValueError):
+        part.layer_counts(z[::-1], 0.5)               # not z-slowest
+    with pytest.raises(ValueError):
+        part.layer_counts(np.r_[z[:8], z[12:]], 0.5)  # a missing layer
