@@ -27,8 +27,8 @@
  *   lpmb_set_dof_mask          the effect of setDispBC_stiffnessUpdate{2,3}D, src/boundary.c:72-281,
  *                              as a DoF mask applied inside the solve (K is never edited)
  *   lpmb_apply_disp_bc / _force_bc   setDispBC / setForceBC, src/boundary.c:12-70, on the resident arrays
- *   lpmb_bond_force_particle   computeBondForceElastic / IncrementalUpdating / J2mixedLinear3D(ii),
- *                              src/constitutive.c:167-283, 466-686
+ *   lpmb_bond_force_particle   computeBondForceElastic / IncrementalUpdating / J2mixedLinear3D / J2energyReturnMap /
+ *                              J2nonlinearIso(ii), src/constitutive.c:167-283, 286-463, 466-686, 689-863
  *   lpmb_compute_strain        computeStrain(), src/lpm_basic.c:127-249
  *   lpmb_compute_cab, lpmb_set_schmid_tensor   computeCab(), src/constitutive.c:1864-1917; plmode 1 of
  *                              lpmb_bond_force = computeBondForceCPMiehe, :866-1396
@@ -139,8 +139,8 @@ int lpmb_spmv_bench(lpmb_ctx *ctx, int reps, int variant, double *ms_per_spmv);
 /* Brick-blocked symmetric SpMV (lpmb_brick.cu): K is symmetric (stiffness.c:441-481 keeps one triangle), so
  * every block is streamed from HBM once and used for both of its contributions inside one CTA; about half the
  * bytes of the full format per CG iteration.  Needs radius, xyz_initial and the connectivity; applies to
- * axis-aligned simple-cubic 3-D lattices on a single GPU and returns LPMB_ERR_UNSUPPORTED (nothing enabled)
- * otherwise.  Once on, lpmb_solve_cg* / lpmb_newton_iteration / lpmb_spmv_host use it; on = 0 releases it.
+ * axis-aligned simple-cubic 3-D lattices -- one GPU, or z-slabs of whole layers (then a collective call: either every
+ * rank gets its bricks or none does) -- and returns LPMB_ERR_UNSUPPORTED (nothing enabled) otherwise.  Once on, lpmb_solve_cg* / lpmb_newton_iteration / lpmb_spmv_host use it; on = 0 releases it.
  * Particle numbering at the ABI is unchanged (the brick order is internal to the solve). */
 int lpmb_matrix_enable_bricks(lpmb_ctx *ctx, int on);
 /* bytes one brick SpMV moves (matrix + staging + vectors); 0 when bricks are off */
@@ -172,12 +172,15 @@ int lpmb_solve_cg_device(lpmb_ctx *ctx, double rel, double abs_tol, int maxit, i
 int lpmb_calc_kntv(lpmb_ctx *ctx, const double *Ce, int ntype);
 int lpmb_compute_dl(lpmb_ctx *ctx);
 int lpmb_bond_force(lpmb_ctx *ctx, int plmode, int load_indicator);
-/* The reference's per-particle law entry points (constitutive.h:15,17,20): computeBondForceElastic(ii) for plmode 6
+/* The reference's per-particle law entry points (constitutive.h:15,17,18,20,21): computeBondForceElastic(ii) for plmode 6
  * (src/constitutive.c:228-283), computeBondForceIncrementalUpdating(ii) for plmode 4 (:167-225),
- * computeBondForceJ2mixedLinear3D(ii) for plmode 0 (:466-686).  Same side effects as the reference: geometry (and
- * return-map) outputs of ii AND of its neighbours across intact bonds, F / Pin (and slot-[2] state, J2_dlambda,
- * dL_ave, stress_tensor := 0) of ii only; no computeStress, no switchStateV(2).  O(N) per call (API completeness;
- * the assembly and the whole-lattice laws never go through it).  Other plmodes: LPMB_ERR_UNSUPPORTED. */
+ * computeBondForceJ2mixedLinear3D(ii) for plmode 0 (:466-686), computeBondForceJ2energyReturnMap(ii, load_indicator) for
+ * plmode 3 (:286-463), computeBondForceJ2nonlinearIso(ii) for plmode 5 (:689-863).  Same side effects as the reference:
+ * geometry (and return-map) outputs of ii AND of its neighbours across intact bonds, F / Pin (and slot-[2] state,
+ * J2_dlambda, dL_ave; plmode 0 / 5: stress_tensor[ii] := 0) of ii only; plmode 5 advances the slot-[0] plastic state of the
+ * whole star in place and leaves the star members' trial forces in F; no computeStress, no switchStateV(2).  O(N) per
+ * call (API completeness; the assembly and the whole-lattice laws never go through it).  plmode 1 (its memo state_v is
+ * only defined inside computeBondForceGeneral) and anything else: LPMB_ERR_UNSUPPORTED. */
 int lpmb_bond_force_particle(lpmb_ctx *ctx, int plmode, int particle, int load_indicator);
 int lpmb_switch_state(lpmb_ctx *ctx, int flag);
 /* residual = dispBC_index*(Pex-Pin); returns ||residual||_2 and ||reaction||_2 (either may be NULL) */

@@ -29,10 +29,12 @@
  *                                                                  lpmb_update_damage (LPMB_DAMAGE_PWISE_LOCAL / _BWISE_NONLOCAL)
  *   constitutive.h:15,17,20    void computeBondForceElastic(int) / computeBondForceJ2mixedLinear3D(int) /
  *                              computeBondForceIncrementalUpdating(int)                lpmb_bond_force_particle (6 / 0 / 4)
- *   constitutive.h:16,18,19    computeBondForceJ2nonlinearIso(int), computeBondForceCPMiehe(int),
- *                              computeBondForceJ2energyReturnMap(int,int): symbols kept, fail loudly (exit 1) -- their
- *                              per-particle result depends on state only the dispatcher sets up (memo reset, serial
- *                              in-place order); plmode 1, 3, 5 are reached through computeBondForceGeneral
+ *   constitutive.h:18,21       void computeBondForceJ2nonlinearIso(int) / computeBondForceJ2energyReturnMap(int, int)
+ *                                                                  lpmb_bond_force_particle (5 / 3): one call of the
+ *                              reference's serial loop -- plmode 5 advances slot [0] of ii's whole star in place
+ *   constitutive.h:19          computeBondForceCPMiehe(int): symbol kept, fails loudly (exit 1) -- called on its own it
+ *                              reuses whatever the state_v memo still flags (only computeBondForceGeneral resets it,
+ *                              constitutive.c:114-117,946-959); plmode 1 is reached through computeBondForceGeneral
  *
  * State ownership: the arrays these functions write (plastic state slots, damage_broken / damage_D / damage_w, nb,
  * bond forces ...) are uploaded once, before the first force evaluation -- so initial cracks set by the driver are

@@ -512,6 +512,8 @@ static int damage(const char *dataName, int tstep, int mode)
             int logged = broken;
             if (mode == 6 && broken > nbreak)
                 logged = nbreak;
+            if (logged > cap) /* the ABI reports the count exactly but lists at most `cap` pairs */
+                fprintf(stderr, "lpmc_dropin: %d bonds broke in one update; only the first %d are listed in %s\n", logged, cap, dataName);
             for (int k = 0; k < logged && k < cap; k++) {
                 if (mode == LPMB_DAMAGE_PWISE_LOCAL)
                     fprintf(fpt, "%d \n", pairs[2 * k]); /* detached particles, one index per line */
@@ -583,7 +585,7 @@ void computeCab()
     down_d2("cp_Cab", cp_Cab, N, S * S);
 }
 /* per-particle law entry points (constitutive.h:15,17,20): one particle and its star through lpmb_bond_force_particle */
-static void particle_law(int mode, int ii)
+static void particle_law(int mode, int ii, int t)
 {
     ensure_state();
     const int N = nparticle, nn = nneighbors;
@@ -592,7 +594,7 @@ static void particle_law(int mode, int ii)
         up_d2("xyz_temp", xyz_temp, N, 3);
         up_d2("F_temp", F_temp, N, nn);
     }
-    CK(lpmb_bond_force_particle(g_ctx, mode, ii, 1));
+    CK(lpmb_bond_force_particle(g_ctx, mode, ii, t));
     down_d2("F", F, N, nn);
     DOWN1D("Pin", Pin, (size_t)NDIM * N);
     if (mode == 4) {
@@ -607,24 +609,29 @@ static void particle_law(int mode, int ii)
     down_d2("csz", csz, N, nn);
     down_d2("dL_total", dL_total, N, 2);
     down_d2("TdL_total", TdL_total, N, 2);
-    if (mode == 0) {
+    if (mode == 0 || mode == 3 || mode == 5) {
         down_d2("dL_ave", dL_ave, N, nn);
         down_d2("ddLp", ddLp, N, nn);
-        down_d2("stress_tensor", stress_tensor, N, 2 * NDIM);
         DOWN1D("J2_dlambda", J2_dlambda, N);
+    }
+    if (mode == 0 || mode == 5)
+        down_d2("stress_tensor", stress_tensor, N, 2 * NDIM); /* row ii zeroed, constitutive.c:647,834 */
+    if (mode == 0 || mode == 3) {
         DOWN1D("pl_flag", pl_flag, N);
         down_slots(2);
     }
+    if (mode == 5)
+        down_slots(0); /* the law advances slot [0] of the whole star in place (constitutive.c:793,799,811) */
 }
-void computeBondForceElastic(int i) { particle_law(6, i); }
-void computeBondForceJ2mixedLinear3D(int ii) { particle_law(0, ii); }
-void computeBondForceIncrementalUpdating(int ii) { particle_law(4, ii); }
-/* the remaining per-particle laws keep call-order-dependent state that only the dispatcher defines (plmode 1: the
- * state_v memo reset by computeBondForceGeneral, constitutive.c:114-117,946-959; plmode 3 and 5: serial in-place
- * semantics, see lpmb_bond.cu) -> symbols kept, fail loudly */
-void computeBondForceJ2nonlinearIso(int ii) { (void)ii; not_built("computeBondForceJ2nonlinearIso(ii): use computeBondForceGeneral(5, t)"); }
+void computeBondForceElastic(int i) { particle_law(6, i, 1); }
+void computeBondForceJ2mixedLinear3D(int ii) { particle_law(0, ii, 1); }
+void computeBondForceIncrementalUpdating(int ii) { particle_law(4, ii, 1); }
+void computeBondForceJ2energyReturnMap(int ii, int t) { particle_law(3, ii, t); }
+void computeBondForceJ2nonlinearIso(int ii) { particle_law(5, ii, 1); }
+/* plmode 1 on its own depends on the state_v memo that only computeBondForceGeneral resets (constitutive.c:114-117,
+ * 946-959): the reference function called directly REUSES whatever increments an earlier dispatcher pass left for every
+ * star member whose flag is still set -> symbol kept, fails loudly */
 void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe(ii): use computeBondForceGeneral(1, t)"); }
-void computeBondForceJ2energyReturnMap(int ii, int t) { (void)ii; (void)t; not_built("computeBondForceJ2energyReturnMap(ii, t): use computeBondForceGeneral(3, t)"); }
 int updateDuctileDamageBwiseLocal(const char *d, int t) { return damage(d, t, 5); }
 int updateDuctileDamagePwiseLocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_PWISE_LOCAL); }
 int updateDuctileDamageBwiseNonlocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_BWISE_NONLOCAL); }
@@ -638,6 +645,7 @@ void lpmc_dropin_shutdown(void)
     if (g_ctx)
         lpmb_destroy(g_ctx);
     g_ctx = NULL;
+    g_state_uploaded = g_cp_ready = 0; /* a later call sets everything up again from the host arrays */
     free(g_buf);
     g_buf = NULL;
     g_buf_bytes = 0;

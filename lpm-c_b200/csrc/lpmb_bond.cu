@@ -560,7 +560,8 @@ j2iso_trajectory_kernel(BondView v, double V, double J2_C, const double *__restr
                         double *__restrict__ dlambda_out, double *__restrict__ ddLp, double *__restrict__ dL, double *__restrict__ dLt,
                         double *__restrict__ TdLt, double *__restrict__ csx, double *__restrict__ csy, double *__restrict__ csz,
                         double *__restrict__ F, double *__restrict__ snap_dL /* [nn][Np] */, double *__restrict__ snap_t /* [nn][4][Np] */,
-                        double *__restrict__ self_dL /* [nn][Np] */, double *__restrict__ self_t /* [4][Np] */, int *__restrict__ self_last)
+                        double *__restrict__ self_dL /* [nn][Np] */, double *__restrict__ self_t /* [4][Np] */, int *__restrict__ self_last,
+                        int only_caller /* -1: the whole serial loop; ii: just call ii (computeBondForceJ2nonlinearIso(ii) on its own) */)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
     if (i >= v.N)
@@ -607,7 +608,7 @@ j2iso_trajectory_kernel(BondView v, double V, double J2_C, const double *__restr
         }
     };
     // callers in ascending particle index: neighbour slots are ascending (neighbor.c:29,40), i itself slots in between
-    bool self_done = false;
+    bool self_done = false, ran = false;
     for (int s = 0; s <= n; s++) {
         int caller_slot;  // -1 = i itself
         if (!self_done && (s == n || v.nbr[(size_t)s * Np + i] > i)) {
@@ -621,6 +622,9 @@ j2iso_trajectory_kernel(BondView v, double V, double J2_C, const double *__restr
             if (!(broken[(size_t)s * Np + i] > LPMB_EPS))
                 continue;  // not in that particle's list (constitutive.c:694-699)
         }
+        if (only_caller >= 0 && (caller_slot < 0 ? i : v.nbr[(size_t)caller_slot * Np + i]) != only_caller)
+            continue;
+        ran = true;
         // (A) elastic stretches with the current plastic stretch   :703-721
         geometry();
         // (B) trial force / stress, return map   :729-809
@@ -706,6 +710,8 @@ j2iso_trajectory_kernel(BondView v, double V, double J2_C, const double *__restr
             last_is_self = 0;
         }
     }
+    if (only_caller >= 0 && !ran)
+        return;  // not in the star of the one call that is made: the reference does not touch this particle
     // what the serial loop leaves behind
     for (int j = 0; j < n; j++) {
         const size_t e = (size_t)j * Np + i;
@@ -734,10 +740,12 @@ j2iso_force_kernel(BondView v, const double *__restrict__ Kn, const double *__re
                    const double *__restrict__ self_dL, const double *__restrict__ self_t, const int *__restrict__ self_last,
                    const double *__restrict__ dL_prev, const double *__restrict__ dLt_prev, const double *__restrict__ TdLt_prev,
                    const double *__restrict__ csx, const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ dL_ave,
-                   double *__restrict__ F, double *__restrict__ Pin)
+                   double *__restrict__ F, double *__restrict__ Pin,
+                   int only_row /* -1: every particle; ii: the force pass of the single call ii (partners across broken bonds are then
+                                   read as they are in memory = the `prev` arrays, which the caller points at the live fields) */)
 {
     const int i = blockIdx.x * BT + threadIdx.x;
-    if (i >= v.N)
+    if (i >= v.N || (only_row >= 0 && i != only_row))
         return;
     const size_t Np = v.Np;
     const double ti[4] = {self_t[i], self_t[Np + i], self_t[2 * Np + i], self_t[3 * Np + i]};
@@ -759,9 +767,9 @@ j2iso_force_kernel(BondView v, const double *__restrict__ Kn, const double *__re
         } else {
             // broken bond: nj holds what its latest caller below i left, or the values from before the whole call
             int best = -2, best_slot = -1;  // -2: none yet; slot -1 = nj itself
-            if (nj < i)
+            if (only_row < 0 && nj < i)
                 best = nj;
-            for (int m = 0; m < v.nn; m++) {
+            for (int m = 0; only_row < 0 && m < v.nn; m++) {
                 const size_t em = (size_t)m * Np + nj;
                 const int q = v.nbr[em];
                 if (q != -1 && broken[em] > LPMB_EPS && q < i && q > best) {
@@ -1205,6 +1213,24 @@ int lpmb_compute_stress(lpmb_ctx *c)
 }
 
 // computeBondForceGeneral(plmode, t)   constitutive.c:88-146
+// scratch of the plmode-5 law: per-caller snapshots, the particle's own snapshot, the fields as they were before the call
+static int iso_scratch(lpmb_ctx *c)
+{
+    if (!c->fields.count("iso_snap_dL")) {
+        LPMB_TRY(lpmb_field_alloc(c, "iso_snap_dL", FK_BOND, FT_F64, c->nn));
+        LPMB_TRY(lpmb_field_alloc(c, "iso_snap_t", FK_PART, FT_F64, 4 * c->nn));
+        LPMB_TRY(lpmb_field_alloc(c, "iso_self_dL", FK_BOND, FT_F64, c->nn));
+        LPMB_TRY(lpmb_field_alloc(c, "iso_self_t", FK_PART, FT_F64, 4));
+        LPMB_TRY(lpmb_field_alloc(c, "iso_self_last", FK_PART, FT_I32, 1));
+        LPMB_TRY(lpmb_field_alloc(c, "dL_prev", FK_BOND, FT_F64, c->nn));
+    }
+    if (!c->fields.count("dL_total_prev")) {
+        LPMB_TRY(lpmb_field_alloc(c, "dL_total_prev", FK_PART, FT_F64, 2));
+        LPMB_TRY(lpmb_field_alloc(c, "TdL_total_prev", FK_PART, FT_F64, 2));
+    }
+    return LPMB_OK;
+}
+
 extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
 {
     LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
@@ -1272,18 +1298,7 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         LPMB_REQUIRE(c->dim == 3, LPMB_ERR_UNSUPPORTED, "plmode 5 is a 3-D law (constitutive.c:706-708)");
         Field *ce = lpmb_field(c, "Ce");
         LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
-        if (!c->fields.count("iso_snap_dL")) {
-            LPMB_TRY(lpmb_field_alloc(c, "iso_snap_dL", FK_BOND, FT_F64, c->nn));
-            LPMB_TRY(lpmb_field_alloc(c, "iso_snap_t", FK_PART, FT_F64, 4 * c->nn));
-            LPMB_TRY(lpmb_field_alloc(c, "iso_self_dL", FK_BOND, FT_F64, c->nn));
-            LPMB_TRY(lpmb_field_alloc(c, "iso_self_t", FK_PART, FT_F64, 4));
-            LPMB_TRY(lpmb_field_alloc(c, "iso_self_last", FK_PART, FT_I32, 1));
-            LPMB_TRY(lpmb_field_alloc(c, "dL_prev", FK_BOND, FT_F64, c->nn));
-        }
-        if (!c->fields.count("dL_total_prev")) {
-            LPMB_TRY(lpmb_field_alloc(c, "dL_total_prev", FK_PART, FT_F64, 2));
-            LPMB_TRY(lpmb_field_alloc(c, "TdL_total_prev", FK_PART, FT_F64, 2));
-        }
+        LPMB_TRY(iso_scratch(c));
         LPMB_TRY(copy_field(c, "dL_total_prev", "dL_total"));
         LPMB_TRY(copy_field(c, "TdL_total_prev", "TdL_total"));
         LPMB_TRY(copy_field(c, "dL_prev", "dL"));
@@ -1291,12 +1306,12 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
             v, param(c, "particle_volume"), param(c, "J2_C"), (const double *)ce->d, fptr<int>(c, "type"), Kn, Tv, broken,
             fptr<double>(c, "distance_initial"), fptr<double>(c, "dLp0"), fptr<double>(c, "J2_alpha0"), fptr<double>(c, "J2_beta0"),
             fptr<double>(c, "J2_dlambda"), fptr<double>(c, "ddLp"), dL, dLt, TdLt, csx, csy, csz, F, fptr<double>(c, "iso_snap_dL"),
-            fptr<double>(c, "iso_snap_t"), fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"), fptr<int>(c, "iso_self_last"));
+            fptr<double>(c, "iso_snap_t"), fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"), fptr<int>(c, "iso_self_last"), -1);
         LPMB_LAUNCH_CHECK(c);
         j2iso_force_kernel<<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, broken, fptr<double>(c, "iso_snap_dL"), fptr<double>(c, "iso_snap_t"),
                                                      fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"), fptr<int>(c, "iso_self_last"),
                                                      fptr<double>(c, "dL_prev"), fptr<double>(c, "dL_total_prev"), fptr<double>(c, "TdL_total_prev"),
-                                                     csx, csy, csz, dL_ave, F, Pin);
+                                                     csx, csy, csz, dL_ave, F, Pin, -1);
         LPMB_LAUNCH_CHECK(c);
     } else if (plmode == 1) {
         // crystal plasticity (constitutive.c:866-1396): geometry -> Miehe return map -> geometry -> averaged force
@@ -1317,6 +1332,8 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
 // per-particle entry points   computeBondForceElastic(ii)             constitutive.c:228-283
 //                             computeBondForceIncrementalUpdating(ii) constitutive.c:167-225
 //                             computeBondForceJ2mixedLinear3D(ii)     constitutive.c:466-686
+//                             computeBondForceJ2energyReturnMap(ii,t) constitutive.c:286-463
+//                             computeBondForceJ2nonlinearIso(ii)      constitutive.c:689-863
 // ---------------------------------------------------------------------------------------------
 // The reference evaluates particle ii together with its "star" (ii + the neighbours across intact bonds): the
 // geometry / return-map passes rewrite dL, dL_total, TdL_total, cs* (ddLp, pl_flag) of EVERY star member, the force
@@ -1326,6 +1343,11 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
 // of the output fields (initialised with the current contents) and only the star's / ii's rows are committed.
 // O(N) per call -- this exists for API completeness (nothing in the reference calls these once stiffness.c is
 // replaced by the assembly kernel), not for speed.
+// plmode 3: same scheme, but the star's geometry rows are committed BEFORE the force pass of ii, which then reads the
+// live fields: across a broken bond the partner is not a star member and the reference reads its rows as they are.
+// plmode 5: the law advances slot [0] of the whole star in place; the trajectory kernel restricted to the single
+// caller ii does exactly that on the live fields (threads outside the star return untouched), the force kernel
+// restricted to row ii reads the star's snapshots for caller ii and, across broken bonds, the live rows.
 template <typename T>
 __global__ void commit_rows_kernel(T *__restrict__ dst, const T *__restrict__ src, const int *__restrict__ rows, int nrows, int comps, int Np)
 {
@@ -1368,14 +1390,13 @@ static int pp_commit(lpmb_ctx *c, const char *name, const int *d_rows, int nrows
 
 extern "C" int lpmb_bond_force_particle(lpmb_ctx *c, int plmode, int ii, int load_indicator)
 {
-    (void)load_indicator;
     LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(ii >= 0 && ii < c->N, LPMB_ERR_ARG, "particle index %d out of range", ii);
     LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "per-particle laws are single-GPU only");
-    LPMB_REQUIRE(plmode == 6 || plmode == 4 || plmode == 0, LPMB_ERR_UNSUPPORTED,
-                 "per-particle evaluation exists for plmode 6, 4 and 0; the laws of plmode %d keep call-order-dependent state that only "
-                 "computeBondForceGeneral defines (memo / in-place slot [0])", plmode);
+    LPMB_REQUIRE(plmode == 6 || plmode == 4 || plmode == 0 || plmode == 3 || plmode == 5, LPMB_ERR_UNSUPPORTED,
+                 "per-particle evaluation exists for plmode 6, 4, 0, 3 and 5; plmode %d is not a law of the reference or (plmode 1) keeps a "
+                 "memo that only computeBondForceGeneral resets (state_v, constitutive.c:114-117,946-959)", plmode);
     BondView v;
     LPMB_TRY(make_view(c, v));
     const int Np = c->Np, nn = c->nn;
@@ -1403,10 +1424,78 @@ extern "C" int lpmb_bond_force_particle(lpmb_ctx *c, int plmode, int ii, int loa
     double *Kn = fptr<double>(c, "Kn"), *Tv = fptr<double>(c, "Tv"), *w = fptr<double>(c, "damage_w"), *L0 = fptr<double>(c, "distance_initial");
     int rc = LPMB_OK;
     auto run = [&]() -> int {
+        if (plmode == 5) {
+            LPMB_REQUIRE(c->params.count("J2_C") && c->params.count("particle_volume"), LPMB_ERR_STATE, "J2_C / particle_volume not set");
+            LPMB_REQUIRE(c->nn <= ISO_MAXNN, LPMB_ERR_UNSUPPORTED, "plmode 5: more than %d neighbours per particle", ISO_MAXNN);
+            LPMB_REQUIRE(c->dim == 3, LPMB_ERR_UNSUPPORTED, "plmode 5 is a 3-D law (constitutive.c:706-708)");
+            Field *ce = lpmb_field(c, "Ce");
+            LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+            LPMB_TRY(iso_scratch(c));
+            double *dL = fptr<double>(c, "dL"), *dLt = fptr<double>(c, "dL_total"), *TdLt = fptr<double>(c, "TdL_total");
+            double *csx = fptr<double>(c, "csx"), *csy = fptr<double>(c, "csy"), *csz = fptr<double>(c, "csz");
+            j2iso_trajectory_kernel<<<g, BT, 0, c->stream>>>(
+                v, param(c, "particle_volume"), param(c, "J2_C"), (const double *)ce->d, fptr<int>(c, "type"), Kn, Tv, broken, L0,
+                fptr<double>(c, "dLp0"), fptr<double>(c, "J2_alpha0"), fptr<double>(c, "J2_beta0"), fptr<double>(c, "J2_dlambda"),
+                fptr<double>(c, "ddLp"), dL, dLt, TdLt, csx, csy, csz, fptr<double>(c, "F"), fptr<double>(c, "iso_snap_dL"),
+                fptr<double>(c, "iso_snap_t"), fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"), fptr<int>(c, "iso_self_last"), ii);
+            LPMB_LAUNCH_CHECK(c);
+            // memset(stress_tensor[ii], 0, ...)  constitutive.c:834
+            double *st = fptr<double>(c, "stress_tensor");
+            LPMB_REQUIRE(st, LPMB_ERR_STATE, "stress_tensor missing");
+            LPMB_CUDA(cudaMemset2DAsync(st + ii, (size_t)Np * sizeof(double), 0, sizeof(double), 6, c->stream));
+            j2iso_force_kernel<<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, broken, fptr<double>(c, "iso_snap_dL"), fptr<double>(c, "iso_snap_t"),
+                                                         fptr<double>(c, "iso_self_dL"), fptr<double>(c, "iso_self_t"),
+                                                         fptr<int>(c, "iso_self_last"), dL, dLt, TdLt, csx, csy, csz, fptr<double>(c, "dL_ave"),
+                                                         fptr<double>(c, "F"), fptr<double>(c, "Pin"), ii);
+            LPMB_LAUNCH_CHECK(c);
+            return LPMB_OK;
+        }
         void *tF, *tPin;
         LPMB_TRY(pp_twin(c, "F", &tF));
         LPMB_TRY(pp_twin(c, "Pin", &tPin));
-        if (plmode == 4) {
+        if (plmode == 3) {
+            LPMB_REQUIRE(c->params.count("J2_H") && c->params.count("J2_xi") && c->params.count("radius") && c->params.count("particle_volume"),
+                         LPMB_ERR_STATE, "J2_H / J2_xi / radius / particle_volume not set");
+            Field *ce = lpmb_field(c, "Ce");
+            LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+            void *tdL, *tcx, *tcy, *tcz, *tdLt, *tTdLt, *tave, *tdLp2, *tb2, *ta2, *tddLp, *tdl, *tpf;
+            LPMB_TRY(pp_twin(c, "dL", &tdL));
+            LPMB_TRY(pp_twin(c, "csx", &tcx));
+            LPMB_TRY(pp_twin(c, "csy", &tcy));
+            LPMB_TRY(pp_twin(c, "csz", &tcz));
+            LPMB_TRY(pp_twin(c, "dL_total", &tdLt));
+            LPMB_TRY(pp_twin(c, "TdL_total", &tTdLt));
+            LPMB_TRY(pp_twin(c, "dL_ave", &tave));
+            LPMB_TRY(pp_twin(c, "dLp2", &tdLp2));
+            LPMB_TRY(pp_twin(c, "J2_beta_eq2", &tb2));
+            LPMB_TRY(pp_twin(c, "J2_alpha2", &ta2));
+            LPMB_TRY(pp_twin(c, "ddLp", &tddLp));
+            LPMB_TRY(pp_twin(c, "J2_dlambda", &tdl));
+            LPMB_TRY(pp_twin(c, "pl_flag", &tpf));
+            geometry_kernel<0><<<g, BT, 0, c->stream>>>(v, L0, fptr<double>(c, "dLp0"), broken, Tv, (double *)tdL, (double *)tcx, (double *)tcy,
+                                                        (double *)tcz, (double *)tdLt, (double *)tTdLt, nullptr);
+            LPMB_LAUNCH_CHECK(c);
+            j2_energy_return_map_kernel<<<g, BT, 0, c->stream>>>(
+                v, param(c, "particle_volume"), param(c, "J2_H"), param(c, "J2_xi"), param(c, "radius"), load_indicator, (const double *)ce->d,
+                fptr<int>(c, "type"), fptr<double>(c, "sigmay"), Kn, broken, (double *)tdL, (double *)tdLt, fptr<double>(c, "dLp0"),
+                fptr<double>(c, "J2_beta_eq0"), fptr<double>(c, "J2_alpha0"), (double *)tdLp2, (double *)tb2, (double *)ta2, (double *)tddLp,
+                (double *)tdl, (int *)tpf);
+            LPMB_LAUNCH_CHECK(c);
+            geometry_kernel<0><<<g, BT, 0, c->stream>>>(v, L0, (double *)tdLp2, broken, Tv, (double *)tdL, (double *)tcx, (double *)tcy,
+                                                        (double *)tcz, (double *)tdLt, (double *)tTdLt, nullptr);
+            LPMB_LAUNCH_CHECK(c);
+            // the star's rows become visible first ...
+            for (const char *n : {"dL", "csx", "csy", "csz", "dL_total", "TdL_total", "ddLp", "pl_flag"})
+                LPMB_TRY(pp_commit(c, n, d_rows, ns));
+            // ... then the force pass of ii over the LIVE fields (`prev` = the same arrays: either branch reads memory as it is)
+            double *dL = fptr<double>(c, "dL"), *dLt = fptr<double>(c, "dL_total"), *TdLt = fptr<double>(c, "TdL_total");
+            force_kernel<3><<<g, BT, 0, c->stream>>>(v, Kn, Tv, fptr<double>(c, "damage_D0"), dL, dLt, TdLt, fptr<double>(c, "csx"),
+                                                     fptr<double>(c, "csy"), fptr<double>(c, "csz"), (double *)tave, (double *)tF, (double *)tPin,
+                                                     broken, dLt, TdLt);
+            LPMB_LAUNCH_CHECK(c);
+            for (const char *n : {"dL_ave", "dLp2", "J2_beta_eq2", "J2_alpha2", "J2_dlambda"})
+                LPMB_TRY(pp_commit(c, n, d_rows, 1));
+        } else if (plmode == 4) {
             void *tddL, *tddLt, *tTddLt;
             LPMB_TRY(pp_twin(c, "ddL", &tddL));
             LPMB_TRY(pp_twin(c, "ddL_total", &tddLt));

@@ -662,17 +662,19 @@ static int star_list(int ii, int nn, const int *neighbors, const double *broken,
 }
 
 /* computeBondForceJ2energyReturnMap for all particles in order, constitutive.c:286-463 (plmode 3) */
-void oracle_j2_energy_force(int N, int nn, double V, double radius, double J2_H, double J2_xi, int load_indicator, const double *Ce,
-                            const int *type, const double *sigmay, const double *xyz, const int *neighbors, const int *nsign, const int *nbi,
-                            const int *nb, const double *L0, const double *Kn, const double *Tv, const double *broken, const double *dD0,
-                            const double *dLp0, const double *beq0, const double *alpha0, double *dLp2, double *beq2, double *alpha2,
-                            double *dlambda_out, int *pl_flag, double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt,
-                            double *csx, double *csy, double *csz, double *F, double *Pin)
+/* calls ii = ii0 .. ii1-1 of the serial loop; (0, N) = the dispatcher's loop, (ii, ii+1) = the entry point called on its own */
+void oracle_j2_energy_force_range(int ii0, int ii1, int N, int nn, double V, double radius, double J2_H, double J2_xi, int load_indicator,
+                                  const double *Ce, const int *type, const double *sigmay, const double *xyz, const int *neighbors,
+                                  const int *nsign, const int *nbi, const int *nb, const double *L0, const double *Kn, const double *Tv,
+                                  const double *broken, const double *dD0, const double *dLp0, const double *beq0, const double *alpha0,
+                                  double *dLp2, double *beq2, double *alpha2, double *dlambda_out, int *pl_flag, double *ddLp, double *dL,
+                                  double *dL_ave, double *dLt, double *TdLt, double *csx, double *csy, double *csz, double *F, double *Pin)
 {
+    (void)N;
     int *tmp = (int *)malloc(sizeof(int) * (nn + 1));
     double *xdLp = (double *)malloc(sizeof(double) * (nn + 1) * nn), *xa = (double *)malloc(sizeof(double) * (nn + 1));
     double *xb = (double *)malloc(sizeof(double) * (nn + 1)), *xl = (double *)malloc(sizeof(double) * (nn + 1));
-    for (int ii = 0; ii < N; ii++) {
+    for (int ii = ii0; ii < ii1; ii++) {
         const int cnt = star_list(ii, nn, neighbors, broken, nb, tmp);
         for (int k = 0; k < cnt; k++) {
             const int i = tmp[k];
@@ -766,16 +768,29 @@ void oracle_j2_energy_force(int N, int nn, double V, double radius, double J2_H,
     free(xl);
 }
 
+void oracle_j2_energy_force(int N, int nn, double V, double radius, double J2_H, double J2_xi, int load_indicator, const double *Ce,
+                            const int *type, const double *sigmay, const double *xyz, const int *neighbors, const int *nsign, const int *nbi,
+                            const int *nb, const double *L0, const double *Kn, const double *Tv, const double *broken, const double *dD0,
+                            const double *dLp0, const double *beq0, const double *alpha0, double *dLp2, double *beq2, double *alpha2,
+                            double *dlambda_out, int *pl_flag, double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt,
+                            double *csx, double *csy, double *csz, double *F, double *Pin)
+{
+    oracle_j2_energy_force_range(0, N, N, nn, V, radius, J2_H, J2_xi, load_indicator, Ce, type, sigmay, xyz, neighbors, nsign, nbi, nb, L0, Kn, Tv,
+                                 broken, dD0, dLp0, beq0, alpha0, dLp2, beq2, alpha2, dlambda_out, pl_flag, ddLp, dL, dL_ave, dLt, TdLt, csx, csy,
+                                 csz, F, Pin);
+}
+
 /* computeBondForceJ2nonlinearIso for all particles in order, constitutive.c:689-863 (plmode 5); state slot [0] in place.
  * SY(x) is the macro of lpm.h:50, whose argument is not parenthesised: SY(a + dl) = 620 + 3300 (1 - exp(-0.4 a + dl)). */
-void oracle_j2_iso_force(int N, int nn, double V, double J2_C, const double *Ce, const int *type, const double *xyz, const int *neighbors,
-                         const int *nsign, const int *nbi, const int *nb, const double *L0, const double *Kn, const double *Tv,
-                         const double *broken, const double *w, double *dLp0, double *beta0 /* [N][6] */, double *alpha0, double *dlambda,
-                         double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt, double *csx, double *csy, double *csz, double *F,
-                         double *Pin)
+void oracle_j2_iso_force_range(int ii0, int ii1, int N, int nn, double V, double J2_C, const double *Ce, const int *type, const double *xyz,
+                               const int *neighbors, const int *nsign, const int *nbi, const int *nb, const double *L0, const double *Kn,
+                               const double *Tv, const double *broken, const double *w, double *dLp0, double *beta0 /* [N][6] */,
+                               double *alpha0, double *dlambda, double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt, double *csx,
+                               double *csy, double *csz, double *F, double *Pin)
 {
+    (void)N;
     int *tmp = (int *)malloc(sizeof(int) * (nn + 1));
-    for (int ii = 0; ii < N; ii++) {
+    for (int ii = ii0; ii < ii1; ii++) {
         const int cnt = star_list(ii, nn, neighbors, broken, nb, tmp);
         for (int k = 0; k < cnt; k++)
             geom_row(tmp[k], nn, xyz, neighbors, nsign, nbi, L0, dLp0 + (long)tmp[k] * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
@@ -850,6 +865,16 @@ void oracle_j2_iso_force(int N, int nn, double V, double J2_C, const double *Ce,
         }
     }
     free(tmp);
+}
+
+void oracle_j2_iso_force(int N, int nn, double V, double J2_C, const double *Ce, const int *type, const double *xyz, const int *neighbors,
+                         const int *nsign, const int *nbi, const int *nb, const double *L0, const double *Kn, const double *Tv,
+                         const double *broken, const double *w, double *dLp0, double *beta0 /* [N][6] */, double *alpha0, double *dlambda,
+                         double *ddLp, double *dL, double *dL_ave, double *dLt, double *TdLt, double *csx, double *csy, double *csz, double *F,
+                         double *Pin)
+{
+    oracle_j2_iso_force_range(0, N, N, nn, V, J2_C, Ce, type, xyz, neighbors, nsign, nbi, nb, L0, Kn, Tv, broken, w, dLp0, beta0, alpha0, dlambda,
+                              ddLp, dL, dL_ave, dLt, TdLt, csx, csy, csz, F, Pin);
 }
 
 /* updateDuctileDamageBwiseLocal, constitutive.c:1607-1695; pairs = newly broken (i, neighbour) in logging order */

@@ -169,6 +169,86 @@ def test_port_j2_iso_law_bit_exact(tag):
     assert np.abs(dLp0).max() > 1e-4      # plastic stretch accumulated in place (the reference wipes it afterwards)
 
 
+def _params2(g, pre):
+    return {str(k): float(v) for k, v in zip(g[f"{pre}.param_names"], g[f"{pre}.params"])}
+
+
+@pytest.mark.parametrize("tag", ["e.s1", "e.s2"])
+def test_port_j2_energy_law_called_per_particle_bit_exact(tag):
+    """computeBondForceJ2energyReturnMap(ii, t) called on its own (constitutive.h:21), five particles in sequence, against
+    tests/golden/sc6_particle2.npz: every array the call may write, after every call (the star's rows change, the others
+    do not; across a broken bond the force pass reads the partner's stale rows)"""
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_particle2.npz")
+    par = _params2(g, "e")
+    N, nn = g["e.setup.neighbors"].shape
+    pre = f"{tag}.pre"
+    t = int(g[f"{tag}.t"][0])
+    f8, i4 = np.float64, np.int32
+    a = {k: _c(g[f"{pre}.{k}"], f8) for k in ("xyz", "damage_broken", "ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin",
+                                              "J2_dlambda")}
+    dLp, alpha, beq, dD = g[f"{pre}.dLp"], g[f"{pre}.J2_alpha"], g[f"{pre}.J2_beta_eq"], g[f"{pre}.damage_D"]
+    dLp0, dLp2 = _c(dLp[..., 0], f8), _c(dLp[..., 2], f8)
+    a0, a2, b0, b2 = _c(alpha[:, 0], f8), _c(alpha[:, 2], f8), _c(beq[:, 0], f8), _c(beq[:, 2], f8)
+    plf, nb = _c(g[f"{pre}.pl_flag"], i4), _c(g[f"{pre}.nb"], i4)
+    cst = {k: _c(g[f"e.setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial", "type")}
+    cf = {k: _c(g[f"e.setup.{k}"], f8) for k in ("Ce", "sigmay", "distance_initial", "Kn", "Tv")}
+    dD0 = _c(dD[..., 0], f8)
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        ii = int(ii)
+        lib.oracle_j2_energy_force_range(C.c_int(ii), C.c_int(ii + 1), C.c_int(N), C.c_int(nn), C.c_double(par["particle_volume"]),
+                                         C.c_double(par["radius"]), C.c_double(par["J2_H"]), C.c_double(par["J2_xi"]), C.c_int(t), _ptr(cf["Ce"]),
+                                         _ptr(cst["type"]), _ptr(cf["sigmay"]), _ptr(a["xyz"]), _ptr(cst["neighbors"]), _ptr(cst["nsign"]),
+                                         _ptr(cst["nb_initial"]), _ptr(nb), _ptr(cf["distance_initial"]), _ptr(cf["Kn"]), _ptr(cf["Tv"]),
+                                         _ptr(a["damage_broken"]), _ptr(dD0), _ptr(dLp0), _ptr(b0), _ptr(a0), _ptr(dLp2), _ptr(b2), _ptr(a2),
+                                         _ptr(a["J2_dlambda"]), _ptr(plf), _ptr(a["ddLp"]), _ptr(a["dL"]), _ptr(a["dL_ave"]), _ptr(a["dL_total"]),
+                                         _ptr(a["TdL_total"]), _ptr(a["csx"]), _ptr(a["csy"]), _ptr(a["csz"]), _ptr(a["F"]), _ptr(a["Pin"]))
+        for n in ("ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin", "J2_dlambda"):
+            assert_same(a[n], g[f"{tag}.c{k}.{n}"], f"call {k} (particle {ii}): {n}")
+        assert_same(plf, g[f"{tag}.c{k}.pl_flag"], "pl_flag")
+        assert_same(dLp2, g[f"{tag}.c{k}.dLp2"], "dLp[2]")
+        assert_same(a2, g[f"{tag}.c{k}.J2_alpha2"], "J2_alpha[2]")
+        assert_same(b2, g[f"{tag}.c{k}.J2_beta_eq2"], "J2_beta_eq[2]")
+    assert (a["dL"] != g[f"{pre}.dL"]).any()
+
+
+@pytest.mark.parametrize("tag", ["i.s1", "i.s2"])
+def test_port_j2_iso_law_called_per_particle_bit_exact(tag):
+    """computeBondForceJ2nonlinearIso(ii) called on its own (constitutive.h:18): the star's plastic state advances in
+    place (slot [0]), star members keep their trial forces in F, ii gets its final F / Pin and a zeroed stress row"""
+    from pathlib import Path
+    lib, C = _lib()
+    g = np.load(Path(__file__).parent / "golden" / "sc6_particle2.npz")
+    par = _params2(g, "i")
+    N, nn = g["i.setup.neighbors"].shape
+    pre = f"{tag}.pre"
+    f8, i4 = np.float64, np.int32
+    a = {k: _c(g[f"{pre}.{k}"], f8) for k in ("xyz", "damage_broken", "damage_w", "ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz",
+                                              "F", "Pin", "J2_dlambda", "stress_tensor")}
+    dLp0 = _c(g[f"{pre}.dLp"][..., 0], f8)
+    beta0 = _c(g[f"{pre}.J2_beta"][..., 0], f8)
+    alpha0 = _c(g[f"{pre}.J2_alpha"][:, 0], f8)
+    nb = _c(g[f"{pre}.nb"], i4)
+    cst = {k: _c(g[f"i.setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial", "type")}
+    cf = {k: _c(g[f"i.setup.{k}"], f8) for k in ("Ce", "distance_initial", "Kn", "Tv")}
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        ii = int(ii)
+        lib.oracle_j2_iso_force_range(C.c_int(ii), C.c_int(ii + 1), C.c_int(N), C.c_int(nn), C.c_double(par["particle_volume"]),
+                                      C.c_double(par["J2_C"]), _ptr(cf["Ce"]), _ptr(cst["type"]), _ptr(a["xyz"]), _ptr(cst["neighbors"]),
+                                      _ptr(cst["nsign"]), _ptr(cst["nb_initial"]), _ptr(nb), _ptr(cf["distance_initial"]), _ptr(cf["Kn"]),
+                                      _ptr(cf["Tv"]), _ptr(a["damage_broken"]), _ptr(a["damage_w"]), _ptr(dLp0), _ptr(beta0), _ptr(alpha0),
+                                      _ptr(a["J2_dlambda"]), _ptr(a["ddLp"]), _ptr(a["dL"]), _ptr(a["dL_ave"]), _ptr(a["dL_total"]),
+                                      _ptr(a["TdL_total"]), _ptr(a["csx"]), _ptr(a["csy"]), _ptr(a["csz"]), _ptr(a["F"]), _ptr(a["Pin"]))
+        a["stress_tensor"][ii] = 0.0      # memset(stress_tensor[ii], 0, ...), constitutive.c:834 (the dispatcher recomputes the stress)
+        for n in ("ddLp", "dL", "dL_ave", "dL_total", "TdL_total", "csx", "csy", "csz", "F", "Pin", "J2_dlambda", "stress_tensor"):
+            assert_same(a[n], g[f"{tag}.c{k}.{n}"], f"call {k} (particle {ii}): {n}")
+        assert_same(dLp0, g[f"{tag}.c{k}.dLp0"], "dLp[0]")
+        assert_same(alpha0, g[f"{tag}.c{k}.J2_alpha0"], "J2_alpha[0]")
+        assert_same(beta0, g[f"{tag}.c{k}.J2_beta0"], "J2_beta[0]")
+    assert (dLp0 != g[f"{pre}.dLp"][..., 0]).any()
+
+
 @pytest.mark.parametrize("step", ["s1", "s2", "s3"])
 def test_port_local_bondwise_damage_bit_exact(step):
     from pathlib import Path

@@ -1,0 +1,100 @@
+"""GPU: the two remaining J2 per-particle law entry points, computeBondForceJ2energyReturnMap(ii, t) (plmode 3) and
+computeBondForceJ2nonlinearIso(ii) (plmode 5), against tests/golden/sc6_particle2.npz (made from the unmodified reference by
+tests/golden/make_golden_particle2.py; the oracle restatement of the same calls is pinned bit-exact on it in the CPU suite,
+tests/test_oracle_port.py::test_port_*_called_per_particle_bit_exact).
+
+Written after the round's GPU budget was spent, hence non-strict xfail and a file name that sorts LAST: nothing that has
+been seen green on a B200 runs after these in the same process."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, make_ctx, put_slots
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+GOLD = ROOT / "tests" / "golden"
+REFDIR = ROOT / "oracle" / "_ref"
+
+
+def _regen(script, tmp_path, out_name):
+    """run a golden generator with the reference's HOST code + GPU drop-in library instead of the all-CPU build"""
+    import sys
+    host = REFDIR / "liblpmc_b200host.so"
+    if not host.exists():
+        pytest.skip("oracle/_ref/liblpmc_b200host.so not built")
+    out = tmp_path / out_name
+    env = dict(os.environ, LPMB_REF_SO=str(host), LPMB_GOLDEN_OUT=str(out))
+    r = subprocess.run([sys.executable, str(GOLD / script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return np.load(out)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+class _Sub:
+    """view of one case ("e" / "i") of sc6_particle2.npz with the keys make_ctx expects"""
+
+    def __init__(self, g, pre):
+        self.g, self.pre = g, pre
+        self.files = [k[len(pre) + 1:] for k in g.files if k.startswith(pre + ".")]
+
+    def __getitem__(self, k):
+        return self.g[f"{self.pre}.{k}"]
+
+
+PP2_WRITES = {
+    3: ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "pl_flag", "dL_ave", "F", "Pin", "J2_dlambda", "dLp2", "J2_beta_eq2",
+        "J2_alpha2"),
+    5: ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "dL_ave", "F", "Pin", "stress_tensor", "J2_dlambda", "dLp0", "J2_beta0",
+        "J2_alpha0"),
+}
+PP2_STATE = ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "damage_broken", "damage_w", "dL_total", "TdL_total", "stress_tensor", "J2_dlambda",
+             "xyz", "Pin", "pl_flag", "nb")
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first B200 run is the round-end suite "
+                                        "(the oracle restatement of the same calls is pinned bit-exact on the fixture in the CPU suite)")
+@pytest.mark.parametrize("tag,law", [("e.s1", 3), ("e.s2", 3), ("i.s1", 5), ("i.s2", 5)])
+def test_per_particle_j2_energy_and_iso_laws_bit_exact(lpm, tag, law):
+    """computeBondForceJ2energyReturnMap(ii, t) / computeBondForceJ2nonlinearIso(ii) called outside the dispatcher
+    (constitutive.h:21,18), five particles in sequence (owners of broken bonds, the partner across one, a corner, an
+    interior particle): after every call EVERY array the law may write equals the reference's bit for bit
+    (tests/golden/sc6_particle2.npz; step 2 carries plastic history, broken bonds, and for plmode 3 t = -1)."""
+    g = np.load(GOLD / "sc6_particle2.npz")
+    case = tag.split(".")[0]
+    c = make_ctx(lpm, _Sub(g, case))
+    pre = f"{tag}.pre"
+    for n in PP2_STATE:
+        c.set_field(n, g[f"{pre}.{n}"])
+    for n in ("dLp", "J2_beta", "J2_alpha", "J2_beta_eq", "damage_D"):
+        put_slots(c, n, g[f"{pre}.{n}"])
+    t = int(g[f"{tag}.t"][0])
+    changed = 0
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        c.bond_force_particle(law, int(ii), t)
+        for n in PP2_WRITES[law]:
+            want = g[f"{tag}.c{k}.{n}"]
+            assert_same(c.get_field(n), want, f"{tag} call {k} (particle {ii}): {n}")
+        changed += int((np.asarray(g[f"{tag}.c{k}.dL"]) != np.asarray(g[f"{pre}.dL"])).any())
+    assert changed > 0
+    c.close()
+
+
+@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (see the test above)")
+def test_dropin_replays_per_particle_j2_energy_and_iso_case(tmp_path):
+    """tests/golden/sc6_particle2.npz regenerated with every call -- the per-particle ones by their reference names --
+    going through liblpmc_dropin.so: phases of step 1 follow one CG solve (1e-10), so 1e-9; plastic flags identical"""
+    new = _regen("make_golden_particle2.py", tmp_path, "pp2.npz")
+    old = np.load(GOLD / "sc6_particle2.npz")
+    for tag, law in (("e.s1", 3), ("i.s1", 5)):
+        for k in range(5):
+            for n in PP2_WRITES[law]:
+                assert _rel(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]) <= 1e-9, (tag, k, n)
+    assert np.array_equal(new["e.s1.c4.pl_flag"], old["e.s1.c4.pl_flag"])
