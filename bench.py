@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None = None, bricks: bool = True):
+def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None = None, bricks: bool = True, brick_trim: bool = True):
     """set up the n^3 block (or this rank's slab of it: owned layers + ghosts, see lpm-c_b200/partition.py) on the
     device: lattice -> O(N) topology -> material -> first FD tangent -> BCs -> predictor -> residual; snapshot"""
     t0 = time.time()
@@ -150,6 +150,8 @@ def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None 
     c.copy_field("xyz_save", "xyz")
     c.copy_field("residual_save", "residual")
     if bricks:
+        if not brick_trim:      # A/B switch: stream every row of every class tile (slab runs; a single GPU has no partial tiles at 216)
+            c.set_params(brick_trim=0.0)
         c.enable_bricks(True)   # brick-blocked symmetric SpMV for the CG (lpmb_brick.cu); SC lattice: eligible
     c.synchronize()
     info = {"N": N, "n": n, "setup_s": round(t1 - t0, 2), "fd_assembly_s": round(t2 - t1, 3), "norm_residual0": nr,
@@ -181,7 +183,7 @@ def gpu_arm(args):
         return import_module("lpm-c_b200.dist_bench").run(args, lpm, dist, rank, world, local, sys.modules[__name__])
 
     n = args.n
-    c, info = build_workload(lpm, n, local, bricks=args.spmv == "bricks")
+    c, info = build_workload(lpm, n, local, bricks=args.spmv == "bricks", brick_trim=not args.no_brick_trim)
     N = info["N"]
     hbm_peak, peak_src = peaks()
 
@@ -419,6 +421,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv", default="bricks", choices=["bricks", "full"],
                     help="CG SpMV kernel: brick-blocked symmetric (default) or the full-format SELL kernel")
+    ap.add_argument("--no-brick-trim", action="store_true", help="A/B: stream whole class tiles instead of only the needed z-layers")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

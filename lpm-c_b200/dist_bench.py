@@ -20,7 +20,8 @@ def run(args, lpm, dist, rank, world, local, bench):
     # rank 0 creates the NCCL id; torch.distributed ships it
     uid = [lpm.Context.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0], bricks=args.spmv == "bricks")
+    c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0], bricks=args.spmv == "bricks",
+                                    brick_trim=not getattr(args, "no_brick_trim", False))
     hbm_peak, peak_src = bench.peaks()
     comm_mode = c.dist_mode()
 
