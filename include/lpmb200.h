@@ -28,7 +28,7 @@
  *                              as a DoF mask applied inside the solve (K is never edited)
  *   lpmb_apply_disp_bc / _force_bc   setDispBC / setForceBC, src/boundary.c:12-70, on the resident arrays
  *   lpmb_bond_force_particle   computeBondForceElastic / IncrementalUpdating / J2mixedLinear3D / J2energyReturnMap /
- *                              J2nonlinearIso(ii), src/constitutive.c:167-283, 286-463, 466-686, 689-863
+ *                              J2nonlinearIso / CPMiehe(ii), src/constitutive.c:167-283, 286-463, 466-686, 689-863, 866-1396
  *   lpmb_compute_strain        computeStrain(), src/lpm_basic.c:127-249
  *   lpmb_compute_cab, lpmb_set_schmid_tensor   computeCab(), src/constitutive.c:1864-1917; plmode 1 of
  *                              lpmb_bond_force = computeBondForceCPMiehe, :866-1396
@@ -179,8 +179,11 @@ int lpmb_bond_force(lpmb_ctx *ctx, int plmode, int load_indicator);
  * geometry (and return-map) outputs of ii AND of its neighbours across intact bonds, F / Pin (and slot-[2] state,
  * J2_dlambda, dL_ave; plmode 0 / 5: stress_tensor[ii] := 0) of ii only; plmode 5 advances the slot-[0] plastic state of the
  * whole star in place and leaves the star members' trial forces in F; no computeStress, no switchStateV(2).  O(N) per
- * call (API completeness; the assembly and the whole-lattice laws never go through it).  plmode 1 (its memo state_v is
- * only defined inside computeBondForceGeneral) and anything else: LPMB_ERR_UNSUPPORTED. */
+ * call (API completeness; the assembly and the whole-lattice laws never go through it).  plmode 1 =
+ * computeBondForceCPMiehe(ii) (:866-1396) with its memo, the int field "state_v" (:946-959): star members flagged 1 REUSE
+ * the increments ddLp / cp_dgy / cp_dA / cp_dA_single an earlier call left, the others are return-mapped and flagged;
+ * lpmb_bond_force(1, .) leaves the memo all 1 like the reference's serial loop, the host zeroes it with lpmb_field_set.
+ * Anything else: LPMB_ERR_UNSUPPORTED. */
 int lpmb_bond_force_particle(lpmb_ctx *ctx, int plmode, int particle, int load_indicator);
 int lpmb_switch_state(lpmb_ctx *ctx, int flag);
 /* residual = dispBC_index*(Pex-Pin); returns ||residual||_2 and ||reaction||_2 (either may be NULL) */

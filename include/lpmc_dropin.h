@@ -32,9 +32,10 @@
  *   constitutive.h:18,21       void computeBondForceJ2nonlinearIso(int) / computeBondForceJ2energyReturnMap(int, int)
  *                                                                  lpmb_bond_force_particle (5 / 3): one call of the
  *                              reference's serial loop -- plmode 5 advances slot [0] of ii's whole star in place
- *   constitutive.h:19          computeBondForceCPMiehe(int): symbol kept, fails loudly (exit 1) -- called on its own it
- *                              reuses whatever the state_v memo still flags (only computeBondForceGeneral resets it,
- *                              constitutive.c:114-117,946-959); plmode 1 is reached through computeBondForceGeneral
+ *   constitutive.h:19          void computeBondForceCPMiehe(int)   lpmb_bond_force_particle (1): honours the host-visible memo
+ *                              state_v like the reference (constitutive.c:946-959: flagged star members REUSE the increments an
+ *                              earlier call left, the others are return-mapped and flagged); computeBondForceGeneral(1, .)
+ *                              leaves state_v all 1, as the reference's serial loop does
  *
  * State ownership: the arrays these functions write (plastic state slots, damage_broken / damage_D / damage_w, nb,
  * bond forces ...) are uploaded once, before the first force evaluation -- so initial cracks set by the driver are

@@ -25,7 +25,7 @@
 /* ---- the reference's globals this layer touches (include/lpm.h:55-81); defined by the driver ---- */
 #define NDIM 3
 extern int ntype, nparticle, nneighbors, dim, lattice, nneighbors_AFEM, plmode, nslipSys, nbreak;
-extern int *IK, *JK, *type, *dispBC_index, *fix_index, *pl_flag, *nb, *nb_initial, *nb_conn;
+extern int *IK, *JK, *type, *dispBC_index, *fix_index, *pl_flag, *nb, *nb_initial, *nb_conn, *state_v;
 extern int **neighbors, **K_pointer, **conn, **nsign;
 extern double radius, particle_volume, J2_H, J2_xi, J2_C, damage_L, damage_threshold, damageb_A, damagec_A, critical_bstrain, dtime;
 extern double *K_global, *residual, *Pin, *Pex, *disp, *sigmay, *reaction_force, *damage_visual;
@@ -490,6 +490,9 @@ void computeBondForceGeneral(int mode, int temp)
         }
         down_slots(2);
         down_cp_slots(2);
+        if (state_v) /* the memo as the reference's serial loop leaves it (constitutive.c:114-117,957) */
+            for (int i = 0; i < N; i++)
+                state_v[i] = 1;
     }
     down_slots(0); /* switchStateV(2) ran inside (constitutive.c:145) */
     down_cp_slots(0);
@@ -559,12 +562,6 @@ void updateCrack()
     DOWN1D("fix_index", fix_index, (size_t)dim * N);
 }
 
-/* ---- entry points whose laws are not built: keep the symbols, fail loudly ---- */
-static void not_built(const char *what)
-{
-    fprintf(stderr, "lpmc_dropin: %s is not available in the B200 build (no CPU fallback)\n", what);
-    exit(1);
-}
 void computeCab()
 {
     ensure_state(); /* Kn, Tv, cs*, damage_broken, nb (calcKnTv and computedL have run: lpmc_project.c:339-345) */
@@ -594,6 +591,11 @@ static void particle_law(int mode, int ii, int t)
         up_d2("xyz_temp", xyz_temp, N, 3);
         up_d2("F_temp", F_temp, N, nn);
     }
+    if (mode == 1) {
+        ensure_cp();
+        if (state_v) /* host-visible memo: a driver may have reset it (the reference's dispatcher does, constitutive.c:116) */
+            UP1D("state_v", state_v, N);
+    }
     CK(lpmb_bond_force_particle(g_ctx, mode, ii, t));
     down_d2("F", F, N, nn);
     DOWN1D("Pin", Pin, (size_t)NDIM * N);
@@ -622,16 +624,33 @@ static void particle_law(int mode, int ii, int t)
     }
     if (mode == 5)
         down_slots(0); /* the law advances slot [0] of the whole star in place (constitutive.c:793,799,811) */
+    if (mode == 1) {
+        const int S = nslipSys;
+        down_d2("dL_ave", dL_ave, N, nn);
+        down_d2("ddLp", ddLp, N, nn);
+        DOWN1D("pl_flag", pl_flag, N);
+        down_d2("cp_RSS", cp_RSS, N, S);
+        down_d2("cp_dgy", cp_dgy, N, S);
+        down_d2("cp_dA_single", cp_dA_single, N, S);
+        DOWN1D("cp_dA", cp_dA, N);
+        int *b = (int *)buf((size_t)N * S * sizeof(int));
+        CK(lpmb_field_get(g_ctx, "cp_Jact", b, (size_t)N * S));
+        for (int i = 0; i < N; i++)
+            memcpy(cp_Jact[i], b + (size_t)i * S, sizeof(int) * S);
+        down_slot("dLp", dLp, N, nn, 2);
+        down_cp_slots(2);
+        if (state_v)
+            DOWN1D("state_v", state_v, N);
+    }
 }
 void computeBondForceElastic(int i) { particle_law(6, i, 1); }
 void computeBondForceJ2mixedLinear3D(int ii) { particle_law(0, ii, 1); }
 void computeBondForceIncrementalUpdating(int ii) { particle_law(4, ii, 1); }
 void computeBondForceJ2energyReturnMap(int ii, int t) { particle_law(3, ii, t); }
 void computeBondForceJ2nonlinearIso(int ii) { particle_law(5, ii, 1); }
-/* plmode 1 on its own depends on the state_v memo that only computeBondForceGeneral resets (constitutive.c:114-117,
- * 946-959): the reference function called directly REUSES whatever increments an earlier dispatcher pass left for every
- * star member whose flag is still set -> symbol kept, fails loudly */
-void computeBondForceCPMiehe(int ii) { (void)ii; not_built("computeBondForceCPMiehe(ii): use computeBondForceGeneral(1, t)"); }
+/* plmode 1 on its own honours the state_v memo exactly like the reference (constitutive.c:946-959): star members still
+ * flagged REUSE the increments an earlier call left, the others are return-mapped and flagged */
+void computeBondForceCPMiehe(int ii) { particle_law(1, ii, 1); }
 int updateDuctileDamageBwiseLocal(const char *d, int t) { return damage(d, t, 5); }
 int updateDuctileDamagePwiseLocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_PWISE_LOCAL); }
 int updateDuctileDamageBwiseNonlocal(const char *d, int t) { return damage(d, t, LPMB_DAMAGE_BWISE_NONLOCAL); }

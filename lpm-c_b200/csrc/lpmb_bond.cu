@@ -37,6 +37,8 @@ struct BondView {
     const double *xyz;          // [3][Np]
 };
 
+__global__ void fill_int_kernel(int *__restrict__ p, int n, int v);
+
 static int make_view(lpmb_ctx *c, BondView &v)
 {
     v.N = c->N;
@@ -1317,6 +1319,9 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         // crystal plasticity (constitutive.c:866-1396): geometry -> Miehe return map -> geometry -> averaged force
         LPMB_TRY(run_geometry(c, v, "dLp0"));
         LPMB_TRY(lpmb_cp_return_map(c));
+        // the memo the serial loop leaves behind: every particle's increments of this pass exist (constitutive.c:114-117,957)
+        fill_int_kernel<<<g, BT, 0, c->stream>>>(fptr<int>(c, "state_v"), c->N, 1);
+        LPMB_LAUNCH_CHECK(c);
         LPMB_TRY(run_geometry(c, v, "dLp2"));
         force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, dL, dLt, TdLt, csx, csy, csz, dL_ave, F, Pin);
         LPMB_LAUNCH_CHECK(c);
@@ -1348,6 +1353,50 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
 // plmode 5: the law advances slot [0] of the whole star in place; the trajectory kernel restricted to the single
 // caller ii does exactly that on the live fields (threads outside the star return untouched), the force kernel
 // restricted to row ii reads the star's snapshots for caller ii and, across broken bonds, the live rows.
+__global__ void fill_int_kernel(int *__restrict__ p, int n, int v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = v;
+}
+
+// xdLp = dLp[.][.][0] + ddLp over the initial bond list (constitutive.c:950-951 / 1308-1309)
+__global__ void __launch_bounds__(BT)
+cp_xdlp_kernel(BondView v, const double *__restrict__ dLp0, const double *__restrict__ ddLp, double *__restrict__ out)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const int n = v.nbi[i];
+    for (int j = 0; j < v.nn; j++) {
+        const size_t e = (size_t)j * v.Np + i;
+        double x = dLp0[e];
+        if (j < n)
+            x += ddLp[e];
+        out[e] = x;
+    }
+}
+
+// slot [2] of particle ii when its increments are REUSED from the memo (constitutive.c:946-956, 1371-1379)
+__global__ void cp_slot2_reuse_kernel(int ii, int Np, int nn, int S, const double *__restrict__ broken, const double *__restrict__ xdLp,
+                                      const double *__restrict__ gy0, const double *__restrict__ dgy, const double *__restrict__ As0,
+                                      const double *__restrict__ dAs, const double *__restrict__ A0, const double *__restrict__ dA,
+                                      double *__restrict__ dLp2, double *__restrict__ gy2, double *__restrict__ As2, double *__restrict__ A2)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nn) {
+        const size_t e = (size_t)t * Np + ii;
+        dLp2[e] = broken[e] * xdLp[e];
+    }
+    if (t < S) {
+        const size_t e = (size_t)t * Np + ii;
+        gy2[e] = gy0[e] + dgy[e];
+        As2[e] = As0[e] + dAs[e];
+    }
+    if (t == 0)
+        A2[ii] = A0[ii] + dA[ii];
+}
+
 template <typename T>
 __global__ void commit_rows_kernel(T *__restrict__ dst, const T *__restrict__ src, const int *__restrict__ rows, int nrows, int comps, int Np)
 {
@@ -1394,9 +1443,8 @@ extern "C" int lpmb_bond_force_particle(lpmb_ctx *c, int plmode, int ii, int loa
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(ii >= 0 && ii < c->N, LPMB_ERR_ARG, "particle index %d out of range", ii);
     LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "per-particle laws are single-GPU only");
-    LPMB_REQUIRE(plmode == 6 || plmode == 4 || plmode == 0 || plmode == 3 || plmode == 5, LPMB_ERR_UNSUPPORTED,
-                 "per-particle evaluation exists for plmode 6, 4, 0, 3 and 5; plmode %d is not a law of the reference or (plmode 1) keeps a "
-                 "memo that only computeBondForceGeneral resets (state_v, constitutive.c:114-117,946-959)", plmode);
+    LPMB_REQUIRE(plmode == 6 || plmode == 4 || plmode == 0 || plmode == 1 || plmode == 3 || plmode == 5, LPMB_ERR_UNSUPPORTED,
+                 "per-particle evaluation: plmode %d is not a law of the reference (0, 1, 3, 4, 5, 6 are)", plmode);
     BondView v;
     LPMB_TRY(make_view(c, v));
     const int Np = c->Np, nn = c->nn;
@@ -1453,7 +1501,93 @@ extern "C" int lpmb_bond_force_particle(lpmb_ctx *c, int plmode, int ii, int loa
         void *tF, *tPin;
         LPMB_TRY(pp_twin(c, "F", &tF));
         LPMB_TRY(pp_twin(c, "Pin", &tPin));
-        if (plmode == 3) {
+        if (plmode == 1) {
+            // computeBondForceCPMiehe(ii), constitutive.c:866-1396.  Star members whose memo flag state_v is still 0 are
+            // return-mapped (increments, cp_RSS, cp_Jact, pl_flag written, flag set); the others REUSE the increments an
+            // earlier call left (:946-956).  Then the star's geometry with dLp[0] + ddLp, the force pass of ii over the live
+            // fields, slot [2] of ii.
+            const int S = (int)param(c, "nslipSys", 0.0);
+            LPMB_REQUIRE(S > 0, LPMB_ERR_STATE, "plmode 1 needs the slip systems (lpmb_set_schmid_tensor)");
+            int *state_v = fptr<int>(c, "state_v");
+            LPMB_REQUIRE(state_v, LPMB_ERR_STATE, "state_v missing");
+            std::vector<int> hsv(c->N), rows0;
+            LPMB_CUDA(cudaMemcpyAsync(hsv.data(), state_v, (size_t)c->N * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LPMB_CUDA(cudaStreamSynchronize(c->stream));
+            for (int q : star)
+                if (hsv[q] == 0) {
+                    rows0.push_back(q);
+                    hsv[q] = 1;  // a particle listed twice would be reused the second time, as in the reference
+                }
+            const bool ii_fresh = !rows0.empty() && rows0[0] == ii;
+            void *tdL, *tcx, *tcy, *tcz, *tdLt, *tTdLt, *tave;
+            LPMB_TRY(pp_twin(c, "dL", &tdL));
+            LPMB_TRY(pp_twin(c, "csx", &tcx));
+            LPMB_TRY(pp_twin(c, "csy", &tcy));
+            LPMB_TRY(pp_twin(c, "csz", &tcz));
+            LPMB_TRY(pp_twin(c, "dL_total", &tdLt));
+            LPMB_TRY(pp_twin(c, "TdL_total", &tTdLt));
+            LPMB_TRY(pp_twin(c, "dL_ave", &tave));
+            geometry_kernel<0><<<g, BT, 0, c->stream>>>(v, L0, fptr<double>(c, "dLp0"), broken, Tv, (double *)tdL, (double *)tcx, (double *)tcy,
+                                                        (double *)tcz, (double *)tdLt, (double *)tTdLt, nullptr);
+            LPMB_LAUNCH_CHECK(c);
+            if (!rows0.empty()) {
+                CPIO io;
+                void *q[11];
+                const char *names[11] = {"dLp2", "cp_gy2", "cp_A2", "cp_A_single2", "ddLp", "cp_RSS", "cp_Jact", "cp_dgy", "cp_dA", "cp_dA_single",
+                                         "pl_flag"};
+                for (int k = 0; k < 11; k++)
+                    LPMB_TRY(pp_twin(c, names[k], &q[k]));
+                io.dL = (double *)tdL, io.dLt = (double *)tdLt, io.TdLt = (double *)tTdLt;
+                io.csx = (double *)tcx, io.csy = (double *)tcy, io.csz = (double *)tcz;
+                io.dLp2 = (double *)q[0], io.gy2 = (double *)q[1], io.A2 = (double *)q[2], io.As2 = (double *)q[3], io.ddLp = (double *)q[4];
+                io.RSS = (double *)q[5], io.Jact = (int *)q[6], io.dgy = (double *)q[7], io.dA = (double *)q[8], io.dAs = (double *)q[9];
+                io.pl_flag = (int *)q[10];
+                int err = 0;
+                LPMB_TRY(lpmb_cp_return_map_io(c, &io, &err));
+                for (int r0 : rows0)
+                    LPMB_REQUIRE(err - 1 != r0, LPMB_ERR_STATE,
+                                 "crystal plasticity: singular slip Jacobian at particle %d (the reference exits here, constitutive.c:1216-1221)", r0);
+                int *d_rows0 = nullptr;
+                LPMB_CUDA(cudaMalloc(&d_rows0, rows0.size() * sizeof(int)));
+                LPMB_CUDA(cudaMemcpyAsync(d_rows0, rows0.data(), rows0.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                int rc2 = LPMB_OK;
+                for (const char *n : {"ddLp", "cp_RSS", "cp_Jact", "cp_dgy", "cp_dA", "cp_dA_single", "pl_flag"})
+                    if (rc2 == LPMB_OK)
+                        rc2 = pp_commit(c, n, d_rows0, (int)rows0.size());
+                cudaStreamSynchronize(c->stream);
+                cudaFree(d_rows0);
+                LPMB_TRY(rc2);
+                LPMB_CUDA(cudaMemcpyAsync(state_v, hsv.data(), (size_t)c->N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                LPMB_CUDA(cudaStreamSynchronize(c->stream));  // hsv is pageable host memory
+            }
+            // plastic stretch the geometry pass uses: previous + the (new or reused) increment, live arrays
+            if (!c->fields.count("pp.xdLp"))
+                LPMB_TRY(lpmb_field_alloc(c, "pp.xdLp", FK_BOND, FT_F64, c->nn));
+            double *xdLp = fptr<double>(c, "pp.xdLp");
+            cp_xdlp_kernel<<<g, BT, 0, c->stream>>>(v, fptr<double>(c, "dLp0"), fptr<double>(c, "ddLp"), xdLp);
+            LPMB_LAUNCH_CHECK(c);
+            geometry_kernel<0><<<g, BT, 0, c->stream>>>(v, L0, xdLp, broken, Tv, (double *)tdL, (double *)tcx, (double *)tcy, (double *)tcz,
+                                                        (double *)tdLt, (double *)tTdLt, nullptr);
+            LPMB_LAUNCH_CHECK(c);
+            for (const char *n : {"dL", "csx", "csy", "csz", "dL_total", "TdL_total"})
+                LPMB_TRY(pp_commit(c, n, d_rows, ns));
+            force_kernel<0><<<g, BT, 0, c->stream>>>(v, Kn, Tv, w, fptr<double>(c, "dL"), fptr<double>(c, "dL_total"), fptr<double>(c, "TdL_total"),
+                                                     fptr<double>(c, "csx"), fptr<double>(c, "csy"), fptr<double>(c, "csz"), (double *)tave,
+                                                     (double *)tF, (double *)tPin);
+            LPMB_LAUNCH_CHECK(c);
+            LPMB_TRY(pp_commit(c, "dL_ave", d_rows, 1));
+            if (ii_fresh) {
+                for (const char *n : {"dLp2", "cp_gy2", "cp_A2", "cp_A_single2"})
+                    LPMB_TRY(pp_commit(c, n, d_rows, 1));
+            } else {
+                const int T = c->nn > S ? c->nn : S;
+                cp_slot2_reuse_kernel<<<lpmb_blocks(T, 64), 64, 0, c->stream>>>(
+                    ii, Np, c->nn, S, broken, xdLp, fptr<double>(c, "cp_gy0"), fptr<double>(c, "cp_dgy"), fptr<double>(c, "cp_A_single0"),
+                    fptr<double>(c, "cp_dA_single"), fptr<double>(c, "cp_A0"), fptr<double>(c, "cp_dA"), fptr<double>(c, "dLp2"),
+                    fptr<double>(c, "cp_gy2"), fptr<double>(c, "cp_A_single2"), fptr<double>(c, "cp_A2"));
+                LPMB_LAUNCH_CHECK(c);
+            }
+        } else if (plmode == 3) {
             LPMB_REQUIRE(c->params.count("J2_H") && c->params.count("J2_xi") && c->params.count("radius") && c->params.count("particle_volume"),
                          LPMB_ERR_STATE, "J2_H / J2_xi / radius / particle_volume not set");
             Field *ce = lpmb_field(c, "Ce");

@@ -390,6 +390,31 @@ int lpmb_cp_return_map(lpmb_ctx *c)
 {
     int S = 0;
     LPMB_TRY(cp_need(c, &S));
+    CPIO io;
+    io.dL = fptr<double>(c, "dL");
+    io.dLt = fptr<double>(c, "dL_total");
+    io.TdLt = fptr<double>(c, "TdL_total");
+    io.csx = fptr<double>(c, "csx");
+    io.csy = fptr<double>(c, "csy");
+    io.csz = fptr<double>(c, "csz");
+    io.dLp2 = fptr<double>(c, "dLp2");
+    io.gy2 = fptr<double>(c, "cp_gy2");
+    io.A2 = fptr<double>(c, "cp_A2");
+    io.As2 = fptr<double>(c, "cp_A_single2");
+    io.ddLp = fptr<double>(c, "ddLp");
+    io.RSS = fptr<double>(c, "cp_RSS");
+    io.Jact = fptr<int>(c, "cp_Jact");
+    io.dgy = fptr<double>(c, "cp_dgy");
+    io.dA = fptr<double>(c, "cp_dA");
+    io.dAs = fptr<double>(c, "cp_dA_single");
+    io.pl_flag = fptr<int>(c, "pl_flag");
+    return lpmb_cp_return_map_io(c, &io, nullptr);
+}
+
+int lpmb_cp_return_map_io(lpmb_ctx *c, const CPIO *io, int *err_particle)
+{
+    int S = 0;
+    LPMB_TRY(cp_need(c, &S));
     for (const char *p : {"cp_h0", "cp_taus0", "cp_tau00", "cp_q", "cp_eta", "cp_p", "cp_maxloop", "dtime", "particle_volume"})
         LPMB_REQUIRE(c->params.count(p), LPMB_ERR_STATE, "parameter %s not set", p);
     CPParams P;
@@ -412,11 +437,9 @@ int lpmb_cp_return_map(lpmb_ctx *c)
 #define CP_ARGS                                                                                                                                   \
     c->N, c->Np, c->nn, P, fptr<int>(c, "nb_initial"), fptr<int>(c, "nb"), fptr<signed char>(c, "nsign"), fptr<signed char>(c, "oppslot"),       \
         (const double *)c->fields["schmid_tensor"].d, fptr<double>(c, "Kn"), fptr<double>(c, "Tv"), fptr<double>(c, "damage_w"),                  \
-        fptr<double>(c, "damage_broken"), fptr<double>(c, "distance_initial"), fptr<double>(c, "dL"), fptr<double>(c, "dL_total"),                \
-        fptr<double>(c, "TdL_total"), fptr<double>(c, "csx"), fptr<double>(c, "csy"), fptr<double>(c, "csz"), fptr<double>(c, "dLp0"),            \
-        fptr<double>(c, "cp_gy0"), fptr<double>(c, "cp_A0"), fptr<double>(c, "cp_A_single0"), fptr<double>(c, "cp_Cab"), fptr<double>(c, "dLp2"), \
-        fptr<double>(c, "cp_gy2"), fptr<double>(c, "cp_A2"), fptr<double>(c, "cp_A_single2"), fptr<double>(c, "ddLp"), fptr<double>(c, "cp_RSS"), \
-        fptr<int>(c, "cp_Jact"), fptr<double>(c, "cp_dgy"), fptr<double>(c, "cp_dA"), fptr<double>(c, "cp_dA_single"), fptr<int>(c, "pl_flag"), d_err
+        fptr<double>(c, "damage_broken"), fptr<double>(c, "distance_initial"), io->dL, io->dLt, io->TdLt, io->csx, io->csy, io->csz,              \
+        fptr<double>(c, "dLp0"), fptr<double>(c, "cp_gy0"), fptr<double>(c, "cp_A0"), fptr<double>(c, "cp_A_single0"), fptr<double>(c, "cp_Cab"), \
+        io->dLp2, io->gy2, io->A2, io->As2, io->ddLp, io->RSS, io->Jact, io->dgy, io->dA, io->dAs, io->pl_flag, d_err
     if (S <= 24)
         cp_miehe_kernel<24><<<lpmb_blocks(c->N, CPT), CPT, 0, c->stream>>>(CP_ARGS);
     else
@@ -426,6 +449,10 @@ int lpmb_cp_return_map(lpmb_ctx *c)
     int err = 0;
     LPMB_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    if (err_particle) {
+        *err_particle = err;
+        return LPMB_OK;
+    }
     LPMB_REQUIRE(err == 0, LPMB_ERR_STATE, "crystal plasticity: singular slip Jacobian at particle %d (the reference exits here, constitutive.c:1216-1221)",
                  err - 1);
     return LPMB_OK;

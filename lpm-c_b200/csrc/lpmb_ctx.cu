@@ -69,6 +69,8 @@ static const FieldSpec kSpecs[] = {
     // per-particle integer
     {"type", FK_PART, FT_I32, 1, 0}, {"pl_flag", FK_PART, FT_I32, 1, 0}, {"nb", FK_PART, FT_I32, 1, 0},
     {"nb_initial", FK_PART, FT_I32, 1, 0},
+    // memo of the crystal-plasticity law: 1 = this particle's increments of the current pass exist (constitutive.c:946-959)
+    {"state_v", FK_PART, FT_I32, 1, 0},
     // DoF vectors
     {"residual", FK_DOF, FT_F64, -1, 0}, {"Pex", FK_DOF, FT_F64, -1, 0}, {"Pex_temp", FK_DOF, FT_F64, -1, 0},
     {"disp", FK_DOF, FT_F64, -1, 0},

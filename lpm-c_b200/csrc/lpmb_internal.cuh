@@ -178,6 +178,16 @@ int lpmb_derive_topology(lpmb_ctx *c, bool initial_geometry);
 int lpmb_compute_stress(lpmb_ctx *c);
 int lpmb_refresh_mask(lpmb_ctx *c);
 int lpmb_cp_return_map(lpmb_ctx *c);
+// the same kernel on explicit input / output arrays (per-particle entry point: scratch twins); err_particle != nullptr:
+// a singular slip Jacobian is reported there (particle index + 1, 0 = none) instead of failing the call
+struct CPIO {
+    const double *dL, *dLt, *TdLt, *csx, *csy, *csz;
+    double *dLp2, *gy2, *A2, *As2, *ddLp, *RSS;
+    int *Jact;
+    double *dgy, *dA, *dAs;
+    int *pl_flag;
+};
+int lpmb_cp_return_map_io(lpmb_ctx *c, const CPIO *io, int *err_particle);
 
 // multi-GPU helpers (lpmb_dist.cu); all are no-ops when world == 1
 static inline int lpmb_own0(const lpmb_ctx *c) { return c->own0; }

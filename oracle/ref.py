@@ -178,7 +178,7 @@ class RefLPM:
     PART_D1 = ("J2_dlambda", "J2_stresseq", "J2_stressm", "J2_triaxiality", "sigmay", "damage_visual")
     DOF_D1 = ("residual", "Pex", "Pex_temp", "disp")
     BOND_I2 = ("neighbors", "nsign")
-    PART_I1 = ("nb", "nb_initial", "nb_conn", "type", "pl_flag")
+    PART_I1 = ("nb", "nb_initial", "nb_conn", "type", "pl_flag", "state_v")
 
     def get(self, name: str) -> np.ndarray:
         N, nn, dim = self.N, self.nn, self.dim

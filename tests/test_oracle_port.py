@@ -403,6 +403,98 @@ def test_port_crystal_plasticity_bit_exact(name):
     assert checked > 0                                          # slip systems were active in the recorded calls
 
 
+@pytest.mark.parametrize("tag", ["fresh", "memo"])
+def test_port_cp_law_called_per_particle_bit_exact(tag):
+    """computeBondForceCPMiehe(ii) called on its own (constitutive.h:19, constitutive.c:866-1396) with its memo state_v
+    (:946-959), against tests/golden/fcc_cp_particle.npz.  Restated exactly the way the CUDA entry point is organised
+    (lpmb_bond_force_particle, plmode 1): whole-lattice geometry and return map into scratch copies, the rows of the star
+    members whose flag was 0 committed and flagged, geometry of the star with dLp[0] + ddLp (new or REUSED increments),
+    force pass of ii over the live arrays, slot [2] of ii -- every array after every call, bit for bit."""
+    from pathlib import Path
+    lib, C = _lib()
+    lib.oracle_cp_return_map.restype = C.c_int
+    g = np.load(Path(__file__).parent / "golden" / "fcc_cp_particle.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    S = int(par["nslipSys"])
+    f8, i4 = np.float64, np.int32
+    st = {k: _c(g[f"setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial")}
+    sf = {k: _c(g[f"setup.{k}"], f8) for k in ("distance_initial", "csx_initial", "csy_initial", "csz_initial", "Kn", "Tv", "schmid_tensor", "cp_Cab")}
+    V = C.c_double(par["particle_volume"])
+    pre = f"{tag}.pre"
+    live = {k: _c(g[f"{pre}.{k}"], f8).copy() for k in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "dL_total", "TdL_total", "Pin", "cp_RSS",
+                                                        "cp_dgy", "cp_dA", "cp_dA_single")}
+    live["pl_flag"], live["cp_Jact"], live["state_v"] = (_c(g[f"{pre}.{k}"], i4).copy() for k in ("pl_flag", "cp_Jact", "state_v"))
+    live["dLp2"] = _c(g[f"{pre}.dLp"][..., 2], f8).copy()
+    live["cp_gy2"], live["cp_A_single2"] = _c(g[f"{pre}.cp_gy"][..., 2], f8).copy(), _c(g[f"{pre}.cp_A_single"][..., 2], f8).copy()
+    live["cp_A2"] = _c(g[f"{pre}.cp_A"][:, 2], f8).copy()
+    xyz, broken, w, nb = _c(g[f"{pre}.xyz"], f8), _c(g[f"{pre}.damage_broken"], f8), _c(g[f"{pre}.damage_w"], f8), _c(g[f"{pre}.nb"], i4)
+    dLp0 = _c(g[f"{pre}.dLp"][..., 0], f8)
+    gy0, As0, A0 = _c(g[f"{pre}.cp_gy"][..., 0], f8), _c(g[f"{pre}.cp_A_single"][..., 0], f8), _c(g[f"{pre}.cp_A"][:, 0], f8)
+    nbr, nbi = st["neighbors"], st["nb_initial"]
+
+    def geometry(dLp, t):
+        lib.oracle_geometry(C.c_int(N), C.c_int(nn), _ptr(xyz), _ptr(nbr), _ptr(st["nsign"]), _ptr(nbi), _ptr(sf["distance_initial"]), _ptr(dLp),
+                            _ptr(broken), _ptr(sf["Tv"]), C.c_int(1), _ptr(t["dL"]), _ptr(t["csx"]), _ptr(t["csy"]), _ptr(t["csz"]),
+                            _ptr(t["dL_total"]), _ptr(t["TdL_total"]), None)
+
+    fresh_calls = 0
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        ii = int(ii)
+        star = [ii] + [int(nbr[ii, j]) for j in range(nn) if broken[ii, j] > 1e-6 and nbr[ii, j] != -1]
+        assert len(star) == nb[ii] + 1
+        rows0 = []
+        for q in star:
+            if live["state_v"][q] == 0:
+                rows0.append(q)
+                live["state_v"][q] = 1
+        t = {n: live[n].copy() for n in live}
+        geometry(dLp0, t)
+        if rows0:
+            rc = lib.oracle_cp_return_map(C.c_int(N), C.c_int(nn), C.c_int(S), V, C.c_double(par["cp_h0"]), C.c_double(par["cp_taus0"]),
+                                          C.c_double(par["cp_tau00"]), C.c_double(par["cp_q"]), C.c_double(par["cp_eta"]), C.c_double(par["cp_p"]),
+                                          C.c_double(par["cp_maxloop"]), C.c_double(par["dtime"]), _ptr(st["nsign"]), _ptr(nb), _ptr(nbi),
+                                          _ptr(sf["Kn"]), _ptr(sf["Tv"]), _ptr(w), _ptr(broken), _ptr(sf["distance_initial"]), _ptr(sf["csx_initial"]),
+                                          _ptr(sf["csy_initial"]), _ptr(sf["csz_initial"]), _ptr(t["dL"]), _ptr(t["dL_total"]), _ptr(t["TdL_total"]),
+                                          _ptr(t["csx"]), _ptr(t["csy"]), _ptr(t["csz"]), _ptr(sf["schmid_tensor"]), _ptr(sf["cp_Cab"]), _ptr(dLp0),
+                                          _ptr(gy0), _ptr(A0), _ptr(As0), _ptr(t["ddLp"]), _ptr(t["cp_dA"]), _ptr(t["cp_dgy"]), _ptr(t["cp_dA_single"]),
+                                          _ptr(t["cp_Jact"]), _ptr(t["cp_RSS"]), _ptr(t["pl_flag"]), _ptr(t["dLp2"]), _ptr(t["cp_gy2"]),
+                                          _ptr(t["cp_A2"]), _ptr(t["cp_A_single2"]))
+            assert rc == 0
+            for n in ("ddLp", "cp_RSS", "cp_Jact", "cp_dgy", "cp_dA", "cp_dA_single", "pl_flag"):
+                live[n][rows0] = t[n][rows0]
+        xdLp = dLp0.copy()
+        for i in range(N):
+            xdLp[i, :nbi[i]] += live["ddLp"][i, :nbi[i]]
+        geometry(xdLp, t)
+        for n in ("dL", "csx", "csy", "csz", "dL_total", "TdL_total"):
+            live[n][star] = t[n][star]
+        lib.oracle_force(C.c_int(N), C.c_int(nn), C.c_int(0), _ptr(nbr), _ptr(st["nsign"]), _ptr(nbi), _ptr(sf["Kn"]), _ptr(sf["Tv"]), _ptr(w),
+                         _ptr(live["dL"]), _ptr(live["dL_total"]), _ptr(live["TdL_total"]), _ptr(live["csx"]), _ptr(live["csy"]), _ptr(live["csz"]),
+                         _ptr(t["dL_ave"]), _ptr(t["F"]), _ptr(t["Pin"]))
+        for n in ("dL_ave", "F"):
+            live[n][ii] = t[n][ii]
+        live["Pin"][3 * ii:3 * ii + 3] = t["Pin"][3 * ii:3 * ii + 3]
+        if rows0 and rows0[0] == ii:
+            fresh_calls += 1
+            for n in ("dLp2", "cp_gy2", "cp_A2", "cp_A_single2"):
+                live[n][ii] = t[n][ii]
+        else:
+            live["dLp2"][ii] = broken[ii] * xdLp[ii]
+            live["cp_gy2"][ii] = gy0[ii] + live["cp_dgy"][ii]
+            live["cp_A_single2"][ii] = As0[ii] + live["cp_dA_single"][ii]
+            live["cp_A2"][ii] = A0[ii] + live["cp_dA"][ii]
+        for n in ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "pl_flag", "dL_ave", "F", "Pin", "state_v", "cp_RSS", "cp_Jact",
+                  "cp_dgy", "cp_dA", "cp_dA_single", "dLp2", "cp_gy2", "cp_A_single2", "cp_A2"):
+            want = np.asarray(g[f"{tag}.c{k}.{n}"])
+            got = live[n]
+            ok = ~np.isnan(want) if want.dtype.kind == "f" else np.ones(want.shape, bool)
+            assert_same(np.where(ok, got, 0), np.where(ok, want, 0), f"{tag} call {k} (particle {ii}): {n}")
+    # "fresh": the second particle sits in the first one's star (already flagged) and the fifth repeats the first -> 3 of 5
+    # calls return-map their own particle; all "memo" calls reuse everything
+    assert fresh_calls == (3 if tag == "fresh" else 0)
+
+
 @pytest.mark.parametrize("name,lattice", [("sq2d_brittle", 0), ("hex2d_brittle", 1), ("sc6_j2", 2), ("fcc_cp", 3), ("bcc_cp", 4)])
 def test_port_calc_kntv_all_lattices_bit_exact(name, lattice):
     """calcKnTv (stiffness.c:11-268) restated for the five lattices, against the Kn / Tv the reference computed for the

@@ -157,7 +157,7 @@ def test_per_particle_laws_bit_exact(lpm, tag, law):
 def test_per_particle_law_rejects_other_plmodes(lpm):
     g = np.load(GOLD / "sc6_particle.npz")
     c = _pp_ctx(lpm, g, "s1.j2.pre")
-    for plmode in (1, 2, 7):
+    for plmode in (2, 7):
         with pytest.raises(lpm.LPMBError):
             c.bond_force_particle(plmode, 0)
     with pytest.raises(lpm.LPMBError):

@@ -98,3 +98,50 @@ def test_dropin_replays_per_particle_j2_energy_and_iso_case(tmp_path):
             for n in PP2_WRITES[law]:
                 assert _rel(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]) <= 1e-9, (tag, k, n)
     assert np.array_equal(new["e.s1.c4.pl_flag"], old["e.s1.c4.pl_flag"])
+
+
+# ---- computeBondForceCPMiehe(ii) with its memo (constitutive.h:19, constitutive.c:866-1396, 946-959) ---------------
+CP_WRITES = ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "dL_ave", "F", "cp_RSS", "cp_dgy", "cp_dA", "cp_dA_single", "dLp2",
+             "cp_gy2", "cp_A_single2", "cp_A2")
+CP_EXACT = ("pl_flag", "state_v", "cp_Jact")
+
+
+@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite; the scheme itself (scratch copies, commit of the rows "
+                                        "whose memo flag was 0, reuse formula) is pinned bit-exact on the fixture in the CPU suite")
+@pytest.mark.parametrize("tag", ["fresh", "memo"])
+def test_per_particle_crystal_plasticity_law(lpm, tag):
+    """five / three calls in sequence on the FCC case (tests/golden/fcc_cp_particle.npz): memo flags and active sets exactly,
+    every other array the call may write to 1e-9 (pow / cosh / tanh differ from glibc by 1-2 ulp, as for the dispatcher)"""
+    from test_cp_gpu import make_cp_ctx
+    from helpers import rel_err
+    g = np.load(GOLD / "fcc_cp_particle.npz")
+    c, _ = make_cp_ctx(lpm, g)
+    c.set_field("cp_Cab", g["setup.cp_Cab"])
+    pre = f"{tag}.pre"
+    for n in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "damage_broken", "damage_w", "dL_total", "TdL_total", "stress_tensor", "xyz", "Pin",
+              "pl_flag", "nb", "state_v", "cp_RSS", "cp_Jact", "cp_dgy", "cp_dA", "cp_dA_single"):
+        c.set_field(n, g[f"{pre}.{n}"])
+    for n in ("dLp", "cp_gy", "cp_A_single", "cp_A"):
+        put_slots(c, n, g[f"{pre}.{n}"])
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        c.bond_force_particle(1, int(ii))
+        for n in CP_EXACT:
+            assert np.array_equal(c.get_field(n), g[f"{tag}.c{k}.{n}"]), (tag, k, n)
+        for n in CP_WRITES:
+            want = np.nan_to_num(np.asarray(g[f"{tag}.c{k}.{n}"]))
+            assert rel_err(np.nan_to_num(c.get_field(n)), want) <= 1e-9, (tag, k, n)
+        assert rel_err(c.get_field("Pin"), g[f"{tag}.c{k}.Pin"]) <= 1e-7, (tag, k)     # sums of cancelling bond forces
+    c.close()
+
+
+@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (see the test above)")
+def test_dropin_replays_per_particle_crystal_plasticity_case(tmp_path):
+    """the fixture regenerated with computeBondForceCPMiehe(ii) and everything around it going through liblpmc_dropin.so"""
+    new = _regen("make_golden_cp_particle.py", tmp_path, "cpp.npz")
+    old = np.load(GOLD / "fcc_cp_particle.npz")
+    for tag, ncall in (("fresh", 5), ("memo", 3)):
+        for k in range(ncall):
+            for n in CP_EXACT:
+                assert np.array_equal(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]), (tag, k, n)
+            for n in ("F", "dL", "ddLp", "cp_dgy", "dLp2", "cp_gy2"):
+                assert _rel(np.nan_to_num(new[f"{tag}.c{k}.{n}"]), np.nan_to_num(old[f"{tag}.c{k}.{n}"])) <= 1e-7, (tag, k, n)
