@@ -120,7 +120,7 @@ def _i32(a):
 
 # host dtype of the integer fields (everything else is float64)
 _INT_FIELDS = {"cp_Jact", "neighbors", "nsign", "mirror", "oppslot", "type", "pl_flag", "nb", "nb_initial", "dispBC_index",
-               "fix_index"}
+               "fix_index", "state_v"}
 
 NOTCONVERGED = 4
 # lpmb_update_damage codes of the two laws updateDamageGeneral's dispatcher keeps commented out (include/lpmb200.h)
@@ -289,7 +289,8 @@ class Context:
         _check(lib.lpmb_bond_force(self._h, plmode, load_indicator))
 
     def bond_force_particle(self, plmode: int, particle: int, load_indicator: int = 1):
-        """the reference's per-particle law entry point for plmode 6 / 4 / 0 (computeBondForceElastic(ii), ...)"""
+        """the reference's per-particle law entry points: plmode 6 / 4 / 0 / 3 / 5 / 1 = computeBondForceElastic(ii),
+        ...IncrementalUpdating(ii), ...J2mixedLinear3D(ii), ...J2energyReturnMap(ii, t), ...J2nonlinearIso(ii), ...CPMiehe(ii)"""
         _check(lib.lpmb_bond_force_particle(self._h, plmode, int(particle), load_indicator))
 
     def compute_strain(self):
