@@ -82,6 +82,49 @@ def test_threaded_cpu_baseline_solves_like_the_serial_reference(ref_c1):
         r.threads(1)
 
 
+def test_point_preconditioners_do_not_pay_on_the_lattice_tangent(ref_c1):
+    """north_star speaks of a preconditioned CG; the reference's solverCG is unpreconditioned (solver.c:219-220, ipar[10] = 0)
+    and the GPU solver replays it iteration for iteration.  This measures what the cheap (HBM-neutral) preconditioners would
+    buy on the reference's own tangent: the diagonal blocks of a uniform lattice are all alike, so Jacobi / 3x3 block-Jacobi
+    change the iteration count by a few percent only (80 -> 77 / 76 on the default case) while costing a vector pass per
+    iteration and the iteration-count parity -- DESIGN.md section 3."""
+    import scipy.sparse as sp
+    r = ref_c1["ref"]
+    L = r.lib
+    L.switchStateV(0)
+    L.setDispBC_stiffnessUpdate3D()
+    K, IK, JK, rhs = r.get("K_global"), r.get("IK"), r.get("JK"), r.get("residual")
+    n = 3 * r.N
+    U = sp.csr_matrix((K, JK - 1, IK - 1), shape=(n, n))
+    A = (U + sp.triu(U, 1).T).tocsr()
+
+    def cg(M):
+        x, res = np.zeros(n), rhs.copy()
+        z = M(res)
+        p, rz = z.copy(), res @ z
+        thr = 1e-8 * (res @ res) + 1e-12
+        for it in range(1, 1000):
+            Ap = A @ p
+            a = rz / (p @ Ap)
+            x += a * p
+            res -= a * Ap
+            if res @ res <= thr:
+                return it
+            z = M(res)
+            rz, rz_old = res @ z, rz
+            p = z + (rz / rz_old) * p
+        return 1000
+
+    d = A.diagonal()
+    blocks = np.stack([A[3 * i:3 * i + 3, 3 * i:3 * i + 3].toarray() for i in range(0, r.N, 1)])
+    binv = np.linalg.inv(blocks)
+    plain = cg(lambda v: v)
+    jacobi = cg(lambda v: v / d)
+    bjacobi = cg(lambda v: np.einsum("nij,nj->ni", binv, v.reshape(-1, 3)).ravel())
+    assert plain == 80
+    assert 0.9 * plain <= jacobi <= plain and 0.9 * plain <= bjacobi <= plain, (plain, jacobi, bjacobi)
+
+
 def test_golden_matches_reference_build(golden):
     """the committed fixture is bit-identical to what the oracle build produces today"""
     from oracle import ref as oref
