@@ -152,6 +152,10 @@ def build_workload(lpm, n: int, device: int, slab=None, unique_id: bytes | None 
     if bricks:
         if not brick_trim:      # A/B switch: stream every row of every class tile (slab runs; a single GPU has no partial tiles at 216)
             c.set_params(brick_trim=0.0)
+        if os.environ.get("LPMB_BRICK_LAZY_WAIT", "0") not in ("", "0"):
+            # experimental (slab runs with the peer-memory halo push): wait for the neighbours' pushes brick by brick, interior
+            # brick layers first (brick_spmv_kernel<true>); not measured yet, off by default
+            c.set_params(brick_lazy_wait=1.0)
         c.enable_bricks(True)   # brick-blocked symmetric SpMV for the CG (lpmb_brick.cu); SC lattice: eligible
     c.synchronize()
     info = {"N": N, "n": n, "setup_s": round(t1 - t0, 2), "fd_assembly_s": round(t2 - t1, 3), "norm_residual0": nr,

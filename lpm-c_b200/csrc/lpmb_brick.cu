@@ -272,16 +272,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 
+// LAZY (slab runs with the peer-memory halo push, param brick_lazy_wait; experimental, off by default): a CTA does not wait
+// for the neighbours' pushes up front but only before the first brick whose extended box really holds halo rows of x
+// -- the lower ghost layers sit in brick layer 0, the upper ones are reached from the top brick layer(s) -- and the
+// bricks are walked in an order rotated by `rot` (one brick layer), so that layer 0 comes last: the pushes land while the
+// interior layers are being processed.  LAZY = false is the kernel as measured in round 1 (wait up front, natural order).
+template <bool LAZY>
 __global__ void __launch_bounds__(BR, 1)
 brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P, const double *__restrict__ bval,
                   const unsigned char *__restrict__ zr, const double *__restrict__ x, double *__restrict__ ypart, double *__restrict__ stage,
-                  const double *__restrict__ scal, PeerWait halo_wait)
+                  const double *__restrict__ scal, PeerWait halo_wait, int rot, int own_z0, int own_z1)
 {
     extern __shared__ __align__(128) unsigned char brick_smem_raw[];
     BrickSmem &S = *reinterpret_cast<BrickSmem *>(brick_smem_raw);
     if (scal && scal[7] != 0.0)  // S_DONE
         return;
-    lpmb_peer_wait(halo_wait);  // slab runs: the neighbours' pushes of the halo rows of x have landed (lpmb_peer.cu)
+    if (!LAZY)
+        lpmb_peer_wait(halo_wait);  // slab runs: the neighbours' pushes of the halo rows of x have landed (lpmb_peer.cu)
+    bool waited_lo = !LAZY || halo_wait.n == 0, waited_hi = waited_lo;
+    // logical position in this CTA's walk -> brick
+    auto phys = [&](long long k) -> long long {
+        if (!LAZY)
+            return k;
+        const long long b = k + rot;
+        return b >= nbricks ? b - nbricks : b;
+    };
     const int r = threadIdx.x;
     const int lx = r & 7, ly = (r >> 3) & 7, lz = r >> 6;
     const int myslot = (lx + 2) + EXX * ((ly + 2) + EXY * lz);
@@ -295,7 +310,7 @@ brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P,
     __syncthreads();
     auto issue = [&](long long t) {
         const int s = (int)(t % NST);
-        const long long brick = blockIdx.x + (t / ncls) * (long long)gridDim.x;
+        const long long brick = phys(blockIdx.x + (t / ncls) * (long long)gridDim.x);
         const int u = (int)(t % ncls);
         const int bzl = (int)(brick / ((long long)nbx * nby));
         const int z0 = zr[(bzl * ncls + u) * 2], z1 = zr[(bzl * ncls + u) * 2 + 1];
@@ -311,8 +326,25 @@ brick_spmv_kernel(int nbricks, int ncls, int nbx, int nby, int nbz, long long P,
             issue(t);
     long long t = 0;
     for (int lb = 0; lb < nloc; lb++) {
-        const long long brick = blockIdx.x + (long long)lb * gridDim.x;
+        const long long brick = phys(blockIdx.x + (long long)lb * gridDim.x);
         const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((long long)nbx * nby));
+        if (LAZY) {
+            // uniform over the CTA (depends on bz only): flag 0 is raised by rank-1 (lower ghosts), flag 1 by rank+1
+            const bool need_lo = !waited_lo && bz * BE < own_z0, need_hi = !waited_hi && bz * BE + EXZ > own_z1;
+            if (need_lo || need_hi) {
+                if (r == 0) {
+                    if (need_lo)
+                        while (lpmb_ld_acquire_sys(halo_wait.seqs + 0) < halo_wait.seq) {
+                        }
+                    if (need_hi)
+                        while (lpmb_ld_acquire_sys(halo_wait.seqs + 1) < halo_wait.seq) {
+                        }
+                }
+                __syncthreads();
+                waited_lo |= need_lo;
+                waited_hi |= need_hi;
+            }
+        }
         // x over the extended box (zero outside the lattice), accumulators to zero
         for (int s = r; s < NSLOT; s += BR) {
             const int gx = bx * BE + (s % EXX) - 2, gy = by * BE + ((s / EXX) % EXY) - 2, gz = bz * BE + s / (EXX * EXY);
@@ -614,7 +646,8 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
     }
     B.ic = ic;
     // 216.6 KB of dynamic shared memory per CTA: opt in on this context's device
-    LPMB_CUDA(cudaFuncSetAttribute(brick_spmv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
+    LPMB_CUDA(cudaFuncSetAttribute(brick_spmv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
+    LPMB_CUDA(cudaFuncSetAttribute(brick_spmv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BrickSmem)));
     B.pattern_ready = true;
     return LPMB_OK;
 }
@@ -758,8 +791,15 @@ int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const dou
 {
     BrickMatrix &B = g_bricks[c];
     const int grid = B.nbricks < c->sm_count ? B.nbricks : c->sm_count;
-    brick_spmv_kernel<<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, B.zr, x, B.ypart, B.stage,
-                                                                  dot ? scal : nullptr, halo_wait);
+    // experimental: wait for the halo pushes brick by brick (see the kernel); only meaningful when there is something to wait for
+    const bool lazy = halo_wait.n == 2 && B.nbz > 1 && param(c, "brick_lazy_wait", 0.0) != 0.0;
+    if (lazy)
+        brick_spmv_kernel<true><<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, B.zr, x, B.ypart,
+                                                                            B.stage, dot ? scal : nullptr, halo_wait, B.nbx * B.nby, B.own_z0,
+                                                                            B.own_z1);
+    else
+        brick_spmv_kernel<false><<<grid, BR, sizeof(BrickSmem), c->stream>>>(B.nbricks, B.ncls, B.nbx, B.nby, B.nbz, B.P, B.bval, B.zr, x, B.ypart,
+                                                                             B.stage, dot ? scal : nullptr, halo_wait, 0, 0, 0);
     LPMB_LAUNCH_CHECK(c);
     if (dot)
         brick_gather_kernel<true><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, partials, scal);

@@ -28,7 +28,14 @@ for w in 2 4 8; do
   timeout 900 $py -m torch.distributed.run --nnodes=1 --nproc-per-node "$w" --master-addr 127.0.0.1 --master-port "$port" \
     bench.py --gpus "$w" --steps 3 --warmup 3 --no-brick-trim > "$out/${tag}_bench_notrim_n${w}.log" 2>&1
 done
-grep -h '"metric"' "$out"/${tag}_bench_n*.log | $py -c '
+# experimental: halo wait brick by brick (interior layers first); correctness, then the scaling lines
+w=$maxn
+LPMB_BRICK_LAZY_WAIT=1 timeout 600 $py tests/dist_check_lite.py 40 2 > "$out/${tag}_dist_lite_lazy_w2.log" 2>&1
+echo "rc=$?" >> "$out/${tag}_dist_lite_lazy_w2.log"
+port=$((port + 1))
+LPMB_BRICK_LAZY_WAIT=1 timeout 900 $py -m torch.distributed.run --nnodes=1 --nproc-per-node "$w" --master-addr 127.0.0.1 --master-port "$port" \
+  bench.py --gpus "$w" --steps 3 --warmup 3 > "$out/${tag}_bench_lazy_n${w}.log" 2>&1
+grep -h '"metric"' "$out"/${tag}_bench_n*.log "$out"/${tag}_bench_lazy_n*.log "$out"/${tag}_bench_notrim_n*.log | $py -c '
 import sys, json
 for ln in sys.stdin:
     d = json.loads(ln)
