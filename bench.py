@@ -280,6 +280,7 @@ def gpu_arm(args):
         "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {n}^3 lattice, "
                                f"{N} particles, {nd} DoF; Newton iteration 0 of load step 1 replayed from a snapshot",
                    "lattice_n": n, "particles": N, "dof": nd, "cg_iterations_per_step": iters,
+                   "cg_iterations_per_s": float(sum(iters)) / (ms_total * 1e-3),   # secondary metric of SURVEY 8(d)
                    "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
                    "l2": "inputs larger than L2 (matrix %.1f GB)" % (c.spmv_bytes_stored() / 1e9),
                    "setup_s": info["setup_s"], "fd_assembly_s": info["fd_assembly_s"], "parallelism": "1 GPU",

@@ -119,6 +119,7 @@ def run(args, lpm, dist, rank, world, local, bench):
             "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {n}^3 lattice, {Ng} particles, "
                                    f"{3 * Ng} DoF; Newton iteration 0 of load step 1 replayed from a snapshot",
                        "lattice_n": n, "particles": Ng, "dof": 3 * Ng, "cg_iterations_per_step": iters,
+                       "cg_iterations_per_s": float(sum(iters)) / (ms_total * 1e-3),
                        "spmv_kernel": "brick-blocked symmetric" if info["bricks"] else "full-format SELL-32",
                        "cg": "unpreconditioned, rel 1e-8 / abs 1e-12 on squared norms (solver.c:217-222)",
                        "l2": "inputs larger than L2 (per-rank matrix %.1f GB)" % (c.spmv_bytes_stored() * own_frac / 1e9),
