@@ -30,7 +30,7 @@ def test_slabs_tile_the_lattice():
         part.make_slab(12, 7, 0, 8)     # fewer than 4 owned layers per rank
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, ragged=False):
     import torch.distributed as dist
     import scipy.sparse as sp
     sys.path.insert(0, str(ROOT))
@@ -47,31 +47,44 @@ def _worker(rank, world, port, q):
     cols = conn.ravel()[conn.ravel() >= 0]
     vals = np.where(rows == cols, 70.0, -1.0 - ((rows + cols) % 5) / 5.0)
     A = sp.csr_matrix((vals, (rows, cols)), shape=(N, N))
+    if ragged:
+        # carve a notch out of layers 3..5 (order preserved, as the reference's carving helpers do): layers of 100 / 60 particles
+        x = lat["xyz"]
+        keep = ~((x[:, 2] > 1.4) & (x[:, 2] < 2.6) & (x[:, 0] > 2.9))
+        A = A[keep][:, keep].tocsr()
+        N = int(keep.sum())
+        counts = part.layer_counts(x[keep, 2], lat["h"])
+        weights = np.bincount(np.rint(x[keep, 2] / lat["h"]).astype(int), weights=np.diff(A.indptr)).tolist()   # sum of nb_conn per layer
+        s = part.make_ragged_slab(counts, rank, world, weights)
+        n_lo_r, n_hi_r, n_lo_s, n_hi_s = s.narrow_recv_lo, s.narrow_recv_hi, s.narrow_send_lo, s.narrow_send_hi
+    else:
+        s = part.make_slab(n, n * n, rank, world)
+        L = s.layer_size
+        n_lo_r, n_hi_r, n_lo_s, n_hi_s = s.narrow_lo * L, s.narrow_hi * L, s.send_narrow_lo * L, s.send_narrow_hi * L
     b = np.sin(1e-2 * np.arange(N))
-    s = part.make_slab(n, n * n, rank, world)
     g0 = s.first_global
     loc = slice(g0, g0 + s.n_local)
     Al = A[loc, loc].tocsr()                       # local operator incl. ghost columns
     own = np.zeros(s.n_local, dtype=bool)
     own[s.own0:s.own1] = True
-    L = s.layer_size
 
-    def exchange(v, lo_recv, hi_recv, lo_send, hi_send):
+    def exchange(v):
+        # particle counts, exactly what lpmb_dist_set_slab / lpmb_dist_exchange use (csrc/lpmb_dist.cu)
         reqs = []
         if rank > 0:
-            reqs.append(dist.isend(torch.from_numpy(v[s.own0:s.own0 + lo_send * L].copy()), rank - 1))
-            rl = torch.empty(lo_recv * L, dtype=torch.float64)
+            reqs.append(dist.isend(torch.from_numpy(v[s.own0:s.own0 + n_lo_s].copy()), rank - 1))
+            rl = torch.empty(n_lo_r, dtype=torch.float64)
             reqs.append(dist.irecv(rl, rank - 1))
         if rank < world - 1:
-            reqs.append(dist.isend(torch.from_numpy(v[s.own1 - hi_send * L:s.own1].copy()), rank + 1))
-            rh = torch.empty(hi_recv * L, dtype=torch.float64)
+            reqs.append(dist.isend(torch.from_numpy(v[s.own1 - n_hi_s:s.own1].copy()), rank + 1))
+            rh = torch.empty(n_hi_r, dtype=torch.float64)
             reqs.append(dist.irecv(rh, rank + 1))
         for r in reqs:
             r.wait()
         if rank > 0:
-            v[s.own0 - lo_recv * L:s.own0] = rl.numpy()
+            v[s.own0 - n_lo_r:s.own0] = rl.numpy()
         if rank < world - 1:
-            v[s.own1:s.own1 + hi_recv * L] = rh.numpy()
+            v[s.own1:s.own1 + n_hi_r] = rh.numpy()
 
     def allsum(x):
         t = torch.tensor([x], dtype=torch.float64)
@@ -86,7 +99,7 @@ def _worker(rank, world, port, q):
     thresh = 1e-8 * rr + 1e-12
     it = 0
     while rr > thresh and it < 500:
-        exchange(p, s.narrow_lo, s.narrow_hi, s.send_narrow_lo, s.send_narrow_hi)
+        exchange(p)
         ap = (Al @ p) * own
         alpha = rr / allsum(p @ ap)
         x += alpha * p
@@ -105,19 +118,20 @@ def _worker(rank, world, port, q):
     res = np.linalg.norm(b - A @ t.numpy()) / np.linalg.norm(b)
     narrow_ok = True
     if rank > 0:
-        lo = slice(s.own0 - s.narrow_lo * L, s.own0)
+        lo = slice(s.own0 - n_lo_r, s.own0)
         narrow_ok &= np.array_equal(x[lo], t.numpy()[g0 + lo.start:g0 + lo.stop])
     if rank == 0:
         q.put((it, res, narrow_ok))
     dist.destroy_process_group()
 
 
-def test_distributed_cg_emulation_with_gloo():
+@pytest.mark.parametrize("ragged", [False, True], ids=["full_layers", "carved"])
+def test_distributed_cg_emulation_with_gloo(ragged):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29400 + (os.getpid() % 500)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29400 + (os.getpid() % 500) + (500 if ragged else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, ragged)) for r in range(2)]
     for p in procs:
         p.start()
     it, res, narrow_ok = q.get(timeout=300)
