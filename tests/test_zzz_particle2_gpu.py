@@ -3,8 +3,9 @@ computeBondForceJ2nonlinearIso(ii) (plmode 5), against tests/golden/sc6_particle
 tests/golden/make_golden_particle2.py; the oracle restatement of the same calls is pinned bit-exact on it in the CPU suite,
 tests/test_oracle_port.py::test_port_*_called_per_particle_bit_exact).
 
-Written after the round's GPU budget was spent, hence non-strict xfail and a file name that sorts LAST: nothing that has
-been seen green on a B200 runs after these in the same process."""
+The C-ABI tests ran green on a B200 with the round's last GPU seconds (profiles/r01i_per_particle_and_regression_gpu_tests.log:
+plmode 3 / 5 bit-exact, plmode 1 within 1e-9 with identical memo flags and active sets); the two drop-in replays (which run
+the reference's host code for ~10 s each) did not fit and stay non-strict xfail.  The file name sorts last."""
 import os
 import subprocess
 from pathlib import Path
@@ -59,8 +60,6 @@ PP2_STATE = ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "damage_broken", 
              "xyz", "Pin", "pl_flag", "nb")
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first B200 run is the round-end suite "
-                                        "(the oracle restatement of the same calls is pinned bit-exact on the fixture in the CPU suite)")
 @pytest.mark.parametrize("tag,law", [("e.s1", 3), ("e.s2", 3), ("i.s1", 5), ("i.s2", 5)])
 def test_per_particle_j2_energy_and_iso_laws_bit_exact(lpm, tag, law):
     """computeBondForceJ2energyReturnMap(ii, t) / computeBondForceJ2nonlinearIso(ii) called outside the dispatcher
@@ -87,7 +86,7 @@ def test_per_particle_j2_energy_and_iso_laws_bit_exact(lpm, tag, law):
     c.close()
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (see the test above)")
+@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (the C-ABI tests above ran green)")
 def test_dropin_replays_per_particle_j2_energy_and_iso_case(tmp_path):
     """tests/golden/sc6_particle2.npz regenerated with every call -- the per-particle ones by their reference names --
     going through liblpmc_dropin.so: phases of step 1 follow one CG solve (1e-10), so 1e-9; plastic flags identical"""
@@ -106,8 +105,6 @@ CP_WRITES = ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "dL_ave
 CP_EXACT = ("pl_flag", "state_v", "cp_Jact")
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite; the scheme itself (scratch copies, commit of the rows "
-                                        "whose memo flag was 0, reuse formula) is pinned bit-exact on the fixture in the CPU suite")
 @pytest.mark.parametrize("tag", ["fresh", "memo"])
 def test_per_particle_crystal_plasticity_law(lpm, tag):
     """five / three calls in sequence on the FCC case (tests/golden/fcc_cp_particle.npz): memo flags and active sets exactly,
@@ -134,7 +131,7 @@ def test_per_particle_crystal_plasticity_law(lpm, tag):
     c.close()
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (see the test above)")
+@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (the C-ABI tests above ran green)")
 def test_dropin_replays_per_particle_crystal_plasticity_case(tmp_path):
     """the fixture regenerated with computeBondForceCPMiehe(ii) and everything around it going through liblpmc_dropin.so"""
     new = _regen("make_golden_cp_particle.py", tmp_path, "cpp.npz")
