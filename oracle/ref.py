@@ -291,7 +291,7 @@ class RefLPM:
                         damage_threshold, damage_L, dtime, top_z)
 
     def setup_2d(self, lattice=1, box=(0.0, 0.064, 0.0, 0.064, 0.0, 1.0), radius=3.2e-3, E0=210e3, mu0=0.3, nbreak=2,
-                 critical_bstrain=2.7e-2, crack=None):
+                 critical_bstrain=2.7e-2, crack=None, crack_w=0.0):
         """Re-play the set-up of examples/shear_hex_brittle.c (:60-231; lattice 1 = hexagonal) or
         examples/3_point_bending_sq_brittle.c (lattice 0 = square) on a small box: 2-D, elastic (plmode 6) with brittle
         bond breaking.  Types as in the hex example: 1 = top y-layer, 2 = bottom y-layer, 3 = full neighbour list.
@@ -315,7 +315,7 @@ class RefLPM:
         if crack is not None:
             L.createCrack.argtypes = [C.c_double] * 4
             L.createCrack.restype = None
-            L.createCrack(crack[0], crack[1], 0.0, crack[2])
+            L.createCrack(crack[0], crack[1], crack_w, crack[2])   # crack_w > 0 removes a notch of that half-width (bending example :121-122)
         L.initMatrices()
         N = self.N
         self.set_d2("xyz_initial", self.d2("xyz", N, 3))

@@ -125,6 +125,40 @@ def test_point_preconditioners_do_not_pay_on_the_lattice_tangent(ref_c1):
     assert 0.9 * plain <= jacobi <= plain and 0.9 * plain <= bjacobi <= plain, (plain, jacobi, bjacobi)
 
 
+@pytest.mark.parametrize("tag", ["C2", "C3", "C4"])
+def test_topology_known_answers_at_the_real_config_sizes(ref, tag):
+    """particle count, sum of bonds, sum of conn blocks and nnz_upper of BASELINE configs 2-4
+    at their REAL sizes (the committed fixtures of these lattices are small blocks), produced by the reference's own set-up
+    code -- and the oracle port's restatement of neighbor.c:9-141 reproduces the lists bit for bit at that size."""
+    from oracle import port as P
+    r = ref
+    if tag == "C2":     # examples/shear_hex_brittle.c:61,70,97-99,121-122
+        r.setup_2d(lattice=1, box=(0.0, 1.0, 0.0, 1.0, 0.0, 1.0), radius=3.2e-3, crack=(-0.5, 0.5, 0.5))
+        want, dim, nn, nconn = (28170, 334370, 858256, 1744682), 2, 12, 31
+    elif tag == "C3":   # examples/3_point_bending_sq_brittle.c:61,70,97-99,121-122 (notch of half-width 1.2 r)
+        r.setup_2d(lattice=0, box=(0.0, 0.2, 0.0, 1.0, 0.0, 1.0), radius=2e-3, crack=(-0.5, 0.08, 0.5002), crack_w=1.2 * 2e-3,
+                   critical_bstrain=2.7e-4)
+        want, dim, nn, nconn = (12460, 97768, 206096, 424652), 2, 8, 17
+    else:               # examples/FCC_Al_R0.3_001_tension.c geometry through the default driver (lattice 3, r = 0.3, box 0..10)
+        r.setup_fcc()
+        want, dim, nn, nconn = (6912, 114192, 365016, 1652940), 3, 18, 61
+    N = r.N
+    nbr, nsign, conn = r.get("neighbors"), r.get("nsign"), r.get("conn")
+    kp = r.get("K_pointer")
+    got = (N, int(r.get("nb_initial").sum()), int(r.get("nb_conn").sum()), int(kp[N, 1]))
+    assert got == want, got
+    assert nbr.shape[1] == nn and conn.shape[1] == nconn
+    if not P.available():
+        pytest.skip("oracle/liblpm_oracle.so not built")
+    p = P.Port(r.get("xyz_initial"), dim=dim, nn=nn, nconn=nconn, radius=r.gd("radius"), particle_volume=r.gd("particle_volume"))
+    p.search_neighbors(r.gd("neighbor1_cutoff"), r.gd("neighbor2_cutoff"))
+    assert np.array_equal(p.neighbors, nbr) and np.array_equal(p.nsign, nsign), "neighbour lists differ"
+    assert np.array_equal(p.nb_initial, r.get("nb_initial"))
+    assert np.array_equal(p.conn, conn) and np.array_equal(p.nb_conn, r.get("nb_conn")), "conn differs"
+    assert np.array_equal(p.kp0[:N], kp[:N, 0]) and np.array_equal(p.kp1, kp[:, 1]), "K_pointer differs"
+    assert np.array_equal(p.distance_initial, r.get("distance_initial"))
+
+
 def test_golden_matches_reference_build(golden):
     """the committed fixture is bit-identical to what the oracle build produces today"""
     from oracle import ref as oref

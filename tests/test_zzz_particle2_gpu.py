@@ -142,3 +142,38 @@ def test_dropin_replays_per_particle_crystal_plasticity_case(tmp_path):
                 assert np.array_equal(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]), (tag, k, n)
             for n in ("F", "dL", "ddLp", "cp_dgy", "dLp2", "cp_gy2"):
                 assert _rel(np.nan_to_num(new[f"{tag}.c{k}.{n}"]), np.nan_to_num(old[f"{tag}.c{k}.{n}"])) <= 1e-7, (tag, k, n)
+
+
+# ---- O(N) device topology builder at the REAL sizes of BASELINE configs 2-4 ------------------------------------------
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; the reference side of the comparison (sizes of "
+                                        "SURVEY's config table, oracle port bit-exact) is in the CPU suite")
+@pytest.mark.parametrize("tag", ["C2", "C3", "C4"])
+def test_build_topology_at_the_real_config_sizes(lpm, ref, tag):
+    """lpmb_build_topology (cell grid, O(N)) against the reference's own O(N^2) searchNormalNeighbor / searchAFEMNeighbor
+    (neighbor.c:9-141) on the hexagonal 28 170-particle plate of shear_hex_brittle.c, the notched square 12 460-particle
+    beam of 3_point_bending_sq_brittle.c and the 6 912-particle FCC block: lists, shells, K_pointer, initial geometry
+    bit for bit.  The last test of the suite on purpose."""
+    r = ref
+    if tag == "C2":
+        r.setup_2d(lattice=1, box=(0.0, 1.0, 0.0, 1.0, 0.0, 1.0), radius=3.2e-3, crack=(-0.5, 0.5, 0.5))
+        dim, lattice, nn, nconn = 2, 1, 12, 31
+    elif tag == "C3":
+        r.setup_2d(lattice=0, box=(0.0, 0.2, 0.0, 1.0, 0.0, 1.0), radius=2e-3, crack=(-0.5, 0.08, 0.5002), crack_w=1.2 * 2e-3,
+                   critical_bstrain=2.7e-4)
+        dim, lattice, nn, nconn = 2, 0, 8, 17
+    else:
+        r.setup_fcc()
+        dim, lattice, nn, nconn = 3, 3, 18, 61
+    N = r.N
+    c = lpm.Context(N, dim, lattice, nn, nconn)
+    c.set_params(radius=r.gd("radius"))
+    c.set_field("xyz", r.get("xyz_initial"))
+    c.build_topology(r.gd("neighbor1_cutoff"), r.gd("neighbor2_cutoff"))
+    assert_same(c.get_field("neighbors"), r.get("neighbors"), "neighbors")
+    assert_same(c.get_field("nsign"), r.get("nsign"), "nsign")
+    assert_same(c.get_field("nb_initial"), r.get("nb_initial"), "nb_initial")
+    assert_same(c.get_field("distance_initial"), r.get("distance_initial"), "distance_initial")
+    assert np.array_equal(c.k_pointer(), r.get("K_pointer"))
+    nnz, nblk = c.csr_sizes()
+    assert nnz == int(r.get("K_pointer")[N, 1]) and nblk == int(r.get("nb_conn").sum())
+    c.close()
