@@ -290,6 +290,44 @@ class RefLPM:
         self._finish_sc(E0, mu0, plmode, sigmay, J2_xi, J2_H, nbreak, critical_bstrain, damageb_A, damagec_A,
                         damage_threshold, damage_L, dtime, top_z)
 
+    def setup_ct_geometry(self):
+        """Geometry and topology of examples/CT_sc_ductile_nonlocal.c (:60-160; BASELINE config 5 as shipped): simple-cubic
+        plate 50 x 48 x 10, radius 0.33, two stacked pre-cracks and the two loading holes -> 75 030 particles; then
+        initMatrices + searchNormalNeighbor + searchAFEMNeighbor (O(N^2): ~25 s single-threaded).  No material set-up."""
+        L = self.lib
+        self.si("lattice", 2)
+        self.si("dim", 3)
+        radius = 0.33
+        self.sd("radius", radius)
+        pbc = self.iarr("pbc", 3)
+        pbc[0] = pbc[1] = pbc[2] = 0
+        self.si("eulerflag", 0)
+        for a in ("angle1", "angle2", "angle3"):
+            self.sd(a, 0.0)
+        b = self.darr("box", 6)
+        for k, v in enumerate((0.0, 50.0, 0.0, 48.0, 0.0, 10.0)):
+            b[k] = v
+        self.sd("box_x", b[1] - b[0])
+        self.sd("box_y", b[3] - b[2])
+        self.sd("box_z", b[5] - b[4])
+        L.createCuboid()
+        mv = (C.c_double * 3)(-0.0, -0.0, -0.0)
+        L.moveParticle(mv)
+        L.createCrack.argtypes = [C.c_double] * 4
+        L.createCrack.restype = None
+        ca1, ca2, w, ch = -10.0, 18.0, 1.0, 24.021
+        L.createCrack(ca1, ca2, w, ch)
+        L.createCrack(ca1, ca2 + 3 * radius, 0.5 * w, ch)
+        L.removeCircle.argtypes = [C.POINTER(C.c_double), C.c_double, C.c_char]
+        L.removeCircle.restype = None
+        L.removeCircle((C.c_double * 3)(9.9, 13.13, 0.0), 5.0, b"z")
+        L.removeCircle((C.c_double * 3)(9.9, 34.91, 0.0), 5.0, b"z")
+        L.initMatrices()
+        N = self.N
+        self.set_d2("xyz_initial", self.d2("xyz", N, 3))
+        L.searchNormalNeighbor()
+        L.searchAFEMNeighbor()
+
     def setup_2d(self, lattice=1, box=(0.0, 0.064, 0.0, 0.064, 0.0, 1.0), radius=3.2e-3, E0=210e3, mu0=0.3, nbreak=2,
                  critical_bstrain=2.7e-2, crack=None, crack_w=0.0):
         """Re-play the set-up of examples/shear_hex_brittle.c (:60-231; lattice 1 = hexagonal) or

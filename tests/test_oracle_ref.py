@@ -125,7 +125,7 @@ def test_point_preconditioners_do_not_pay_on_the_lattice_tangent(ref_c1):
     assert 0.9 * plain <= jacobi <= plain and 0.9 * plain <= bjacobi <= plain, (plain, jacobi, bjacobi)
 
 
-@pytest.mark.parametrize("tag", ["C2", "C3", "C4"])
+@pytest.mark.parametrize("tag", ["C2", "C3", "C4", "C5src"])
 def test_topology_known_answers_at_the_real_config_sizes(ref, tag):
     """particle count, sum of bonds, sum of conn blocks and nnz_upper of BASELINE configs 2-4
     at their REAL sizes (the committed fixtures of these lattices are small blocks), produced by the reference's own set-up
@@ -139,6 +139,13 @@ def test_topology_known_answers_at_the_real_config_sizes(ref, tag):
         r.setup_2d(lattice=0, box=(0.0, 0.2, 0.0, 1.0, 0.0, 1.0), radius=2e-3, crack=(-0.5, 0.08, 0.5002), crack_w=1.2 * 2e-3,
                    critical_bstrain=2.7e-4)
         want, dim, nn, nconn = (12460, 97768, 206096, 424652), 2, 8, 17
+    elif tag == "C5src":  # examples/CT_sc_ductile_nonlocal.c as shipped: carved, pre-cracked compact-tension specimen
+        r.threads(8)      # its searches are OpenMP loops over disjoint rows (neighbor.c:13,48); the lists do not depend on it
+        try:
+            r.setup_ct_geometry()
+        finally:
+            r.threads(1)
+        want, dim, nn, nconn = (75030, 1267032, 4072398, 18438336), 3, 18, 61
     else:               # examples/FCC_Al_R0.3_001_tension.c geometry through the default driver (lattice 3, r = 0.3, box 0..10)
         r.setup_fcc()
         want, dim, nn, nconn = (6912, 114192, 365016, 1652940), 3, 18, 61
