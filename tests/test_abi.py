@@ -60,3 +60,35 @@ def test_c_example_fails_loudly_without_device(lpm):
         pytest.skip("a CUDA device is present")
     r = subprocess.run([str(exe), "8", "1"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_every_entry_point_rejects_null_arguments_without_crashing():
+    """error behaviour at the boundary: every function include/lpmb200.h declares, called with all-zero arguments (NULL
+    context, NULL pointers), returns -- an error code for the calls that need a context, 0 for the pure getters -- instead of
+    dereferencing NULL.  One child process walks all of them and prints each name before the call, so a crash names itself."""
+    import re
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    hdr = re.sub(r"/\*.*?\*/", "", (root / "include" / "lpmb200.h").read_text(), flags=re.S)
+    decls = re.findall(r"\b(lpmb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(decls) >= 50
+    calls = [(n, 0 if a.strip() in ("", "void") else len(a.split(","))) for n, a in decls]
+    code = (
+        "import ctypes as C, sys\n"
+        f"lib = C.CDLL({str(root / 'lpm-c_b200' / 'liblpmb200.so')!r})\n"
+        f"for name, n in {calls!r}:\n"
+        "    print('CALL', name, flush=True)\n"
+        "    f = getattr(lib, name)\n"
+        "    f.restype = C.c_longlong\n"
+        "    rc = f(*([C.c_void_p(0)] * n))\n"
+        "    print('RC', name, rc, flush=True)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    last = [ln for ln in r.stdout.splitlines() if ln.startswith("CALL")][-1]
+    assert r.returncode == 0, f"crashed in {last}: {r.stderr[-500:]}"
+    rcs = {ln.split()[1]: int(ln.split()[2]) for ln in r.stdout.splitlines() if ln.startswith("RC")}
+    getters = {"lpmb_last_error", "lpmb_version", "lpmb_device_count", "lpmb_destroy", "lpmb_launch_count", "lpmb_stream",
+               "lpmb_spmv_bytes_bricks", "lpmb_spmv_bytes", "lpmb_spmv_bytes_stored", "lpmb_dist_mode"}
+    accepted_null = {n for n, rc in rcs.items() if rc == 0} - getters
+    assert not accepted_null, f"accepted a NULL context: {sorted(accepted_null)}"
