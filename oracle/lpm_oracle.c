@@ -8,7 +8,10 @@
  * reference's iteration counts (80 / 106 on the default case).  calcKnTv for the five lattices, crystal plasticity (plmode 1), the alternative
  * J2 laws (plmode 3 and 5), the brittle and the three remaining ductile-damage laws, the per-particle law entry points and computeStrain are restated at the end of the file as the reference's literal serial loops and
  * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz, sc6_particle.npz,
- * fcc_cp.npz, bcc_cp.npz, hex2d_brittle.npz, sq2d_brittle.npz and sc6_j2.npz.
+ * sc6_particle2.npz (plmode 3 / 5 called per particle: the *_range entry points), fcc_cp.npz, fcc_cp_particle.npz
+ * (plmode 1 called per particle with its memo), bcc_cp.npz, hex2d_brittle.npz, sq2d_brittle.npz and sc6_j2.npz; the
+ * topology restatement also against the reference's lists at the real sizes of BASELINE configs 2-5
+ * (tests/test_oracle_ref.py::test_topology_known_answers_at_the_real_config_sizes).
  *
  * Layouts are the reference's logical ones, flattened row-major: per-bond a[i*nn+j], per-particle a[i*c+k],
  * DoF vectors v[dim*i+k], Pin[3*i+k]; three-slot state as separate arrays.  Strict IEEE: compile with
