@@ -29,7 +29,7 @@ def _regen(script, tmp_path, out_name):
         pytest.skip("oracle/_ref/liblpmc_b200host.so not built")
     out = tmp_path / out_name
     env = dict(os.environ, LPMB_REF_SO=str(host), LPMB_GOLDEN_OUT=str(out))
-    r = subprocess.run([sys.executable, str(GOLD / script)], env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, str(GOLD / script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return np.load(out)
 
