@@ -15,7 +15,12 @@ for w in 2 4; do
   timeout 600 $py tests/dist_check_lite.py 40 "$w" > "$out/${tag}_dist_lite_w${w}.log" 2>&1
   echo "rc=$?" >> "$out/${tag}_dist_lite_w${w}.log"
 done
-timeout 900 $py -m pytest tests/test_dist_gpu.py -m gpu -x -q > "$out/${tag}_dist_tests.log" 2>&1
+timeout 900 $py -m pytest tests/test_dist_gpu.py -m gpu -q -rxX > "$out/${tag}_dist_tests.log" 2>&1
+# plain-C multi-GPU driver (never run in round 1): default case on 2 ranks, then the 10M-particle case on all of them
+timeout 300 examples/sc_block_mgpu 2 21 3 > "$out/${tag}_sc_block_mgpu_21.log" 2>&1
+echo "rc=$?" >> "$out/${tag}_sc_block_mgpu_21.log"
+timeout 600 examples/sc_block_mgpu "$maxn" 216 1 > "$out/${tag}_sc_block_mgpu_216.log" 2>&1
+echo "rc=$?" >> "$out/${tag}_sc_block_mgpu_216.log"
 # scaling: the bench exactly as the driver launches it
 timeout 600 $py bench.py --no-cpu-baseline > "$out/${tag}_bench_n1.log" 2>&1
 for w in 2 4 8; do

@@ -92,3 +92,20 @@ def test_every_entry_point_rejects_null_arguments_without_crashing():
                "lpmb_spmv_bytes_bricks", "lpmb_spmv_bytes", "lpmb_spmv_bytes_stored", "lpmb_dist_mode"}
     accepted_null = {n for n, rc in rcs.items() if rc == 0} - getters
     assert not accepted_null, f"accepted a NULL context: {sorted(accepted_null)}"
+
+
+def test_c_multi_gpu_example_usage_and_loud_failure(lpm):
+    """examples/sc_block_mgpu (one process per GPU from plain C): bad arguments -> usage, exit 2; without devices every rank
+    says so and the parent reports the failure (no hang, no CPU path)"""
+    import subprocess
+    from pathlib import Path
+    import pytest
+    exe = Path(__file__).resolve().parents[1] / "examples" / "sc_block_mgpu"
+    if not exe.exists():
+        pytest.skip("examples/sc_block_mgpu not built")
+    r = subprocess.run([str(exe), "3", "8"], capture_output=True, text=True, timeout=60)      # 8 layers cannot feed 3 ranks
+    assert r.returncode == 2 and "usage" in r.stderr
+    if lpm.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([str(exe), "2", "8", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and "rank 0 failed" in r.stderr

@@ -25,3 +25,24 @@ def test_two_gpu_slabs_match_single_gpu_without_torch(lpm):
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "dist_check_lite.py"), "24", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.xfail(strict=False, reason="examples/sc_block_mgpu.c was written after round 1's GPU budget was spent: not run on a multi-GPU box yet")
+def test_c_multi_gpu_example_reproduces_default_case_known_answers(lpm):
+    """examples/sc_block_mgpu: the default case C1 (21^3) on 2 GPUs from plain C over the C ABI (fork + exec per rank, NCCL id
+    through a file): Newton iterations 2 2 1 and -- up to the summation order of the all-reduced dot products -- the CG
+    iteration counts 80 / 106 of the single-GPU run"""
+    import re
+    if lpm.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = ROOT / "examples" / "sc_block_mgpu"
+    if not exe.exists():
+        pytest.skip("examples/sc_block_mgpu not built")
+    r = subprocess.run([str(exe), "2", "21", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    steps = re.findall(r"Loading step (\d+) has finished in (\d+) iterations; CG iterations:([ \d]+);", r.stdout)
+    assert [int(s[1]) for s in steps] == [2, 2, 1], r.stdout
+    cg1 = [int(x) for x in steps[0][2].split()]
+    assert abs(cg1[0] - 80) <= 1 and abs(cg1[1] - 106) <= 1, cg1
+    m = re.search(r"mean z-displacement of the loaded layer after 3 steps: (\S+)", r.stdout)
+    assert m and abs(float(m.group(1)) / (3 * -1.27857453e-03) - 1.0) < 0.05      # ~linear in the elastic range
