@@ -189,3 +189,40 @@ def test_ragged_slabs_for_carved_specimens():
         part.layer_counts(z[::-1], 0.5)               # not z-slowest
     with pytest.raises(ValueError):
         part.layer_counts(np.r_[z[:8], z[12:]], 0.5)  # a missing layer
+
+
+def test_ragged_slab_invariants_on_random_specimens():
+    """property test (hypothesis): for any layer counts / weights and any world that fits, the slabs tile the lattice, every
+    rank owns >= 4 layers, neighbouring ranks agree on every exchanged count, and the bottleneck is never worse than the
+    equal-layer split"""
+    from hypothesis import given, settings, strategies as st
+    part = importlib.import_module("lpm-c_b200.partition")
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.integers(1, 6).flatmap(lambda world: st.tuples(
+        st.just(world),
+        st.lists(st.tuples(st.integers(1, 500), st.integers(1, 70)), min_size=4 * world if world > 1 else 1, max_size=4 * world + 30))))
+    def check(arg):
+        world, layers = arg
+        counts = [c for c, _ in layers]
+        weights = [c * w for c, w in layers]
+        nz = len(counts)
+        slabs = [part.make_ragged_slab(counts, r, world, weights) for r in range(world)]
+        assert slabs[0].z0 == 0 and slabs[-1].z1 == nz and slabs[0].own0 == 0 and slabs[-1].n_local == slabs[-1].own1
+        assert sum(s.own1 - s.own0 for s in slabs) == sum(counts)
+        for s in slabs:
+            assert world == 1 or s.z1 - s.z0 >= 4
+            a = s.set_slab_args()
+            assert 0 <= a[0] < a[1] <= s.n_local                      # what lpmb_dist_set_slab checks (csrc/lpmb_dist.cu)
+            assert a[2] <= a[0] and a[3] <= s.n_local - a[1]
+            assert max(a[4:]) <= a[1] - a[0]
+        for lo, hi in zip(slabs[:-1], slabs[1:]):
+            assert lo.z1 == hi.z0
+            assert lo.narrow_recv_hi == hi.narrow_send_lo and hi.narrow_recv_lo == lo.narrow_send_hi
+            assert lo.n_local - lo.own1 == hi.wide_send_lo and hi.own0 == lo.wide_send_hi
+            assert lo.first_global + lo.own1 == hi.first_global + hi.own0
+        if world > 1:
+            equal = [part.owned_layers(nz, r, world) for r in range(world)]
+            assert max(s.weight for s in slabs) <= max(sum(weights[a:b]) for a, b in equal) + 1e-9
+
+    check()
