@@ -72,3 +72,17 @@ def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     n = np.linalg.norm(b.ravel())
     return float(np.linalg.norm((a - b).ravel()) / (n if n else 1.0))
+
+
+def run_isolated(test_file, node, timeout=900):
+    """Run ONE test body -- a function named impl_* of `test_file`, `node` = its name incl. any [param] -- in a child pytest
+    process.  For GPU tests that have never been run: a crash of the library or a sticky CUDA error then stays in the child
+    instead of taking the rest of the suite (or the pytest process itself) down."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "-o", "python_functions=impl_*", "-m", "gpu",
+                        f"{test_file}::{node}"], capture_output=True, text=True, timeout=timeout, cwd=root)
+    assert r.returncode == 0, f"isolated run of {node} failed (rc {r.returncode}):\n{r.stdout[-3000:]}\n{r.stderr[-1500:]}"
+    return r.stdout

@@ -323,7 +323,13 @@ NOT_YET_RUN = pytest.mark.xfail(strict=False, reason="written after the round's 
 
 
 @NOT_YET_RUN
-def test_bcc_crystal_plasticity(lpm):
+def test_bcc_crystal_plasticity():
+    """runs impl_bcc_crystal_plasticity in a child process (never run on a B200 yet: keep a failure of the library there)"""
+    from helpers import run_isolated
+    print(run_isolated(__file__, "impl_bcc_crystal_plasticity")[-300:])
+
+
+def impl_bcc_crystal_plasticity(lpm):
     """tests/golden/bcc_cp.npz (tests/golden/make_golden_cp.py with LPMB_CP_LATTICE=4): topology from the O(N) device
     builder, calcKnTv of the BCC lattice (stiffness.c:236-266), computeCab bit-exact; two load steps of the Miehe law
     device-resident: Newton iteration counts and active slip systems identical, displacements 1e-9"""

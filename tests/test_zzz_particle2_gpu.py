@@ -154,7 +154,14 @@ def test_dropin_replays_per_particle_crystal_plasticity_case(tmp_path):
 @pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; the reference side of the comparison (sizes of "
                                         "SURVEY's config table, oracle port bit-exact) is in the CPU suite")
 @pytest.mark.parametrize("tag", ["C2", "C3", "C4", "C5src"])
-def test_build_topology_at_the_real_config_sizes(lpm, ref, tag):
+def test_build_topology_at_the_real_config_sizes(tag):
+    """runs impl_build_topology_at_the_real_config_sizes[tag] in a child process (never run on a B200 yet)"""
+    from helpers import run_isolated
+    print(run_isolated(__file__, f"impl_build_topology_at_the_real_config_sizes[{tag}]")[-300:])
+
+
+@pytest.mark.parametrize("tag", ["C2", "C3", "C4", "C5src"])
+def impl_build_topology_at_the_real_config_sizes(lpm, ref, tag):
     """lpmb_build_topology (cell grid, O(N)) against the reference's own O(N^2) searchNormalNeighbor / searchAFEMNeighbor
     (neighbor.c:9-141) on the hexagonal 28 170-particle plate of shear_hex_brittle.c, the notched square 12 460-particle
     beam of 3_point_bending_sq_brittle.c, the 6 912-particle FCC block and the 75 030-particle compact-tension specimen:
