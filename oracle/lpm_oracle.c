@@ -9,7 +9,7 @@
  * J2 laws (plmode 3 and 5), the brittle and the three remaining ductile-damage laws, the per-particle law entry points and computeStrain are restated at the end of the file as the reference's literal serial loops and
  * pinned bit-for-bit against tests/golden/sc6_j2energy.npz, sc6_j2iso.npz, sc6_damage_variants.npz, sc6_particle.npz,
  * sc6_particle2.npz (plmode 3 / 5 called per particle: the *_range entry points), fcc_cp.npz, fcc_cp_particle.npz
- * (plmode 1 called per particle with its memo), bcc_cp.npz, hex2d_brittle.npz, sq2d_brittle.npz and sc6_j2.npz; the
+ * (plmode 1 called per particle with its memo: oracle_cp_particle), bcc_cp.npz, hex2d_brittle.npz, sq2d_brittle.npz and sc6_j2.npz; the
  * topology restatement also against the reference's lists at the real sizes of BASELINE configs 2-5
  * (tests/test_oracle_ref.py::test_topology_known_answers_at_the_real_config_sizes).
  *
@@ -1151,19 +1151,23 @@ static int lu_solve_shim(int n, double *a, double *b)
  * tanh/cosh hardening and power-law viscosity.  dL, dLt, TdLt, cs* hold the TRIAL geometry (slot-[0] plastic stretch).
  * Writes the increments (ddLp, cp_dA, cp_dgy, cp_dA_single), cp_Jact, cp_RSS, pl_flag and the slot-[2] state.
  * Returns 0, or i + 1 if the slip Jacobian of particle i is singular (the reference exits there, :1216-1221). */
-int oracle_cp_return_map(int N, int nn, int S, double V, double h0, double taus, double tau0, double q, double eta, double pp, double maxloop,
-                         double dtime, const int *nsign, const int *nb, const int *nbi, const double *Kn, const double *Tv, const double *w,
-                         const double *broken, const double *L0, const double *cx0, const double *cy0, const double *cz0, const double *dL,
-                         const double *dLt, const double *TdLt, const double *csx, const double *csy, const double *csz, const double *sch,
-                         const double *Cab, const double *dLp0, const double *gy0 /* [N][S] */, const double *A0 /* [N] */,
-                         const double *As0 /* [N][S] */, double *ddLp, double *dA, double *dgy, double *dAs, int *Jact, double *RSS,
-                         int *pl_flag, double *dLp2, double *gy2, double *A2, double *As2)
+/* the return map of the particles rows[0..nrows) (rows == NULL: all N particles) */
+static int cp_return_map_rows(int nrows, const int *rows, int N, int nn, int S, double V, double h0, double taus, double tau0, double q,
+                              double eta, double pp, double maxloop, double dtime, const int *nsign, const int *nb, const int *nbi,
+                              const double *Kn, const double *Tv, const double *w, const double *broken, const double *L0, const double *cx0,
+                              const double *cy0, const double *cz0, const double *dL, const double *dLt, const double *TdLt, const double *csx,
+                              const double *csy, const double *csz, const double *sch, const double *Cab, const double *dLp0,
+                              const double *gy0 /* [N][S] */, const double *A0 /* [N] */, const double *As0 /* [N][S] */, double *ddLp,
+                              double *dA, double *dgy, double *dAs, int *Jact, double *RSS, int *pl_flag, double *dLp2, double *gy2, double *A2,
+                              double *As2)
 {
     double *gam = (double *)malloc(sizeof(double) * S), *r = (double *)malloc(sizeof(double) * S), *rhs = (double *)malloc(sizeof(double) * S);
     double *D = (double *)malloc(sizeof(double) * S * S), *xgy = (double *)malloc(sizeof(double) * S), *yf = (double *)malloc(sizeof(double) * S);
     double *xdL = (double *)malloc(sizeof(double) * nn);
     int bad = 0;
-    for (int i = 0; i < N && !bad; i++) {
+    const int count = rows ? nrows : N;
+    for (int qq = 0; qq < count && !bad; qq++) {
+        const int i = rows ? rows[qq] : qq;
         const long b0 = (long)i * nn;
         double st[6] = {0}, xt[2] = {dLt[2 * i], dLt[2 * i + 1]}, xT[2] = {TdLt[2 * i], TdLt[2 * i + 1]};
         for (int j = 0; j < nbi[i]; j++)
@@ -1337,6 +1341,92 @@ int oracle_cp_return_map(int N, int nn, int S, double V, double h0, double taus,
 #undef RSS_OF
     }
     free(gam); free(r); free(rhs); free(D); free(xgy); free(yf); free(xdL);
+    return bad;
+}
+
+int oracle_cp_return_map(int N, int nn, int S, double V, double h0, double taus, double tau0, double q, double eta, double pp, double maxloop,
+                         double dtime, const int *nsign, const int *nb, const int *nbi, const double *Kn, const double *Tv, const double *w,
+                         const double *broken, const double *L0, const double *cx0, const double *cy0, const double *cz0, const double *dL,
+                         const double *dLt, const double *TdLt, const double *csx, const double *csy, const double *csz, const double *sch,
+                         const double *Cab, const double *dLp0, const double *gy0 /* [N][S] */, const double *A0 /* [N] */,
+                         const double *As0 /* [N][S] */, double *ddLp, double *dA, double *dgy, double *dAs, int *Jact, double *RSS,
+                         int *pl_flag, double *dLp2, double *gy2, double *A2, double *As2)
+{
+    return cp_return_map_rows(0, NULL, N, nn, S, V, h0, taus, tau0, q, eta, pp, maxloop, dtime, nsign, nb, nbi, Kn, Tv, w, broken, L0, cx0, cy0, cz0,
+                              dL, dLt, TdLt, csx, csy, csz, sch, Cab, dLp0, gy0, A0, As0, ddLp, dA, dgy, dAs, Jact, RSS, pl_flag, dLp2, gy2, A2, As2);
+}
+
+/* computeBondForceCPMiehe(ii) called on its own, constitutive.c:866-1396, with the memo state_v (:946-959): the geometry of
+ * ii's star with the slot-[0] plastic stretch (:912-935); star members still flagged REUSE the increments an earlier call
+ * left, the others are return-mapped and flagged (:938-1317); the star's geometry with dLp[0] + ddLp (:1320-1341); the force
+ * pass of ii over the arrays as they are (:1343-1361); slot [2] of ii (:1371-1379).  Returns the reference's exit condition
+ * (singular slip Jacobian) as a non-zero value. */
+int oracle_cp_particle(int ii, int N, int nn, int S, double V, double h0, double taus, double tau0, double q, double eta, double pp,
+                       double maxloop, double dtime, const double *xyz, const int *neighbors, const int *nsign, const int *nb, const int *nbi,
+                       const double *Kn, const double *Tv, const double *w, const double *broken, const double *L0, const double *cx0,
+                       const double *cy0, const double *cz0, const double *sch, const double *Cab, const double *dLp0, const double *gy0,
+                       const double *A0, const double *As0, int *state_v, double *dL, double *dLt, double *TdLt, double *csx, double *csy,
+                       double *csz, double *ddLp, double *dA, double *dgy, double *dAs, int *Jact, double *RSS, int *pl_flag, double *dL_ave,
+                       double *F, double *Pin, double *dLp2, double *gy2, double *A2, double *As2)
+{
+    int *star = (int *)malloc(sizeof(int) * (nn + 1)), *rows0 = (int *)malloc(sizeof(int) * (nn + 1));
+    const int cnt = star_list(ii, nn, neighbors, broken, nb, star);
+    for (int k = 0; k < cnt; k++)
+        geom_row(star[k], nn, xyz, neighbors, nsign, nbi, L0, dLp0 + (long)star[k] * nn, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+    int n0 = 0;
+    for (int k = 0; k < cnt; k++)
+        if (state_v[star[k]] == 0) {
+            state_v[star[k]] = 1;
+            rows0[n0++] = star[k];
+        }
+    const int ii_fresh = n0 > 0 && rows0[0] == ii;
+    /* slot [2] is only stored for ii (:1371-1379): the other star members' go to scratch */
+    double *t_dLp2 = (double *)malloc(sizeof(double) * (size_t)N * nn), *t_gy2 = (double *)malloc(sizeof(double) * (size_t)N * S);
+    double *t_A2 = (double *)malloc(sizeof(double) * N), *t_As2 = (double *)malloc(sizeof(double) * (size_t)N * S);
+    int bad = 0;
+    if (n0 > 0)
+        bad = cp_return_map_rows(n0, rows0, N, nn, S, V, h0, taus, tau0, q, eta, pp, maxloop, dtime, nsign, nb, nbi, Kn, Tv, w, broken, L0, cx0,
+                                 cy0, cz0, dL, dLt, TdLt, csx, csy, csz, sch, Cab, dLp0, gy0, A0, As0, ddLp, dA, dgy, dAs, Jact, RSS, pl_flag,
+                                 t_dLp2, t_gy2, t_A2, t_As2);
+    double *xd = (double *)malloc(sizeof(double) * nn);
+    for (int k = 0; k < cnt; k++) {
+        const int i = star[k];
+        for (int j = 0; j < nn; j++)
+            xd[j] = dLp0[(long)i * nn + j] + (j < nbi[i] ? ddLp[(long)i * nn + j] : 0.0);
+        geom_row(i, nn, xyz, neighbors, nsign, nbi, L0, xd, broken, Tv, dL, dLt, TdLt, csx, csy, csz);
+        if (i == ii && !ii_fresh)
+            for (int j = 0; j < nn; j++)
+                dLp2[(long)i * nn + j] = broken[(long)i * nn + j] * xd[j];
+    }
+    {
+        const int i = ii;
+        Pin[3 * i] = Pin[3 * i + 1] = Pin[3 * i + 2] = 0.0;
+        for (int j = 0; j < nbi[i]; j++) {
+            const long e = (long)i * nn + j;
+            const int nj = neighbors[e], s = nsign[e];
+            for (int jj = 0; jj < nn; jj++)
+                if (neighbors[(long)nj * nn + jj] == i)
+                    dL_ave[e] = 0.5 * (dL[e] + dL[(long)nj * nn + jj]);
+            F[e] = 2.0 * Kn[e] * dL_ave[e] + 0.5 * (TdLt[2 * i + s] + TdLt[2 * nj + s]) + 0.5 * Tv[e] * (dLt[2 * i + s] + dLt[2 * nj + s]);
+            F[e] *= w[e];
+            Pin[3 * i] += csx[e] * F[e];
+            Pin[3 * i + 1] += csy[e] * F[e];
+            Pin[3 * i + 2] += csz[e] * F[e];
+        }
+        if (ii_fresh) {
+            memcpy(dLp2 + (long)i * nn, t_dLp2 + (long)i * nn, sizeof(double) * nn);
+            memcpy(gy2 + (long)i * S, t_gy2 + (long)i * S, sizeof(double) * S);
+            memcpy(As2 + (long)i * S, t_As2 + (long)i * S, sizeof(double) * S);
+            A2[i] = t_A2[i];
+        } else {
+            for (int m = 0; m < S; m++) {
+                gy2[(long)i * S + m] = gy0[(long)i * S + m] + dgy[(long)i * S + m];
+                As2[(long)i * S + m] = As0[(long)i * S + m] + dAs[(long)i * S + m];
+            }
+            A2[i] = A0[i] + dA[i];
+        }
+    }
+    free(star); free(rows0); free(t_dLp2); free(t_gy2); free(t_A2); free(t_As2); free(xd);
     return bad;
 }
 

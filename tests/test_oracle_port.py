@@ -495,6 +495,50 @@ def test_port_cp_law_called_per_particle_bit_exact(tag):
     assert fresh_calls == (3 if tag == "fresh" else 0)
 
 
+@pytest.mark.parametrize("tag", ["fresh", "memo"])
+def test_port_cp_particle_restatement_bit_exact(tag):
+    """oracle_cp_particle = computeBondForceCPMiehe(ii) restated literally (geometry of the star, memo, return map of the
+    unflagged members, geometry with the new / reused increments, force pass of ii, slot [2] of ii), against
+    tests/golden/fcc_cp_particle.npz: every array after every call, bit for bit"""
+    from pathlib import Path
+    lib, C = _lib()
+    lib.oracle_cp_particle.restype = C.c_int
+    g = np.load(Path(__file__).parent / "golden" / "fcc_cp_particle.npz")
+    par = params_from_golden(g)
+    N, nn = g["setup.neighbors"].shape
+    S = int(par["nslipSys"])
+    f8, i4 = np.float64, np.int32
+    st = {k: _c(g[f"setup.{k}"], i4) for k in ("neighbors", "nsign", "nb_initial")}
+    sf = {k: _c(g[f"setup.{k}"], f8) for k in ("distance_initial", "csx_initial", "csy_initial", "csz_initial", "Kn", "Tv", "schmid_tensor", "cp_Cab")}
+    pre = f"{tag}.pre"
+    a = {k: _c(g[f"{pre}.{k}"], f8).copy() for k in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "dL_total", "TdL_total", "Pin", "cp_RSS",
+                                                     "cp_dgy", "cp_dA", "cp_dA_single")}
+    a["pl_flag"], a["cp_Jact"], a["state_v"] = (_c(g[f"{pre}.{k}"], i4).copy() for k in ("pl_flag", "cp_Jact", "state_v"))
+    a["dLp2"] = _c(g[f"{pre}.dLp"][..., 2], f8).copy()
+    a["cp_gy2"], a["cp_A_single2"] = _c(g[f"{pre}.cp_gy"][..., 2], f8).copy(), _c(g[f"{pre}.cp_A_single"][..., 2], f8).copy()
+    a["cp_A2"] = _c(g[f"{pre}.cp_A"][:, 2], f8).copy()
+    xyz, broken, w, nb = _c(g[f"{pre}.xyz"], f8), _c(g[f"{pre}.damage_broken"], f8), _c(g[f"{pre}.damage_w"], f8), _c(g[f"{pre}.nb"], i4)
+    dLp0 = _c(g[f"{pre}.dLp"][..., 0], f8)
+    gy0, As0, A0 = _c(g[f"{pre}.cp_gy"][..., 0], f8), _c(g[f"{pre}.cp_A_single"][..., 0], f8), _c(g[f"{pre}.cp_A"][:, 0], f8)
+    d = C.c_double
+    for k, ii in enumerate(g[f"{tag}.particles"]):
+        rc = lib.oracle_cp_particle(C.c_int(int(ii)), C.c_int(N), C.c_int(nn), C.c_int(S), d(par["particle_volume"]), d(par["cp_h0"]),
+                                    d(par["cp_taus0"]), d(par["cp_tau00"]), d(par["cp_q"]), d(par["cp_eta"]), d(par["cp_p"]), d(par["cp_maxloop"]),
+                                    d(par["dtime"]), _ptr(xyz), _ptr(st["neighbors"]), _ptr(st["nsign"]), _ptr(nb), _ptr(st["nb_initial"]),
+                                    _ptr(sf["Kn"]), _ptr(sf["Tv"]), _ptr(w), _ptr(broken), _ptr(sf["distance_initial"]), _ptr(sf["csx_initial"]),
+                                    _ptr(sf["csy_initial"]), _ptr(sf["csz_initial"]), _ptr(sf["schmid_tensor"]), _ptr(sf["cp_Cab"]), _ptr(dLp0),
+                                    _ptr(gy0), _ptr(A0), _ptr(As0), _ptr(a["state_v"]), _ptr(a["dL"]), _ptr(a["dL_total"]), _ptr(a["TdL_total"]),
+                                    _ptr(a["csx"]), _ptr(a["csy"]), _ptr(a["csz"]), _ptr(a["ddLp"]), _ptr(a["cp_dA"]), _ptr(a["cp_dgy"]),
+                                    _ptr(a["cp_dA_single"]), _ptr(a["cp_Jact"]), _ptr(a["cp_RSS"]), _ptr(a["pl_flag"]), _ptr(a["dL_ave"]),
+                                    _ptr(a["F"]), _ptr(a["Pin"]), _ptr(a["dLp2"]), _ptr(a["cp_gy2"]), _ptr(a["cp_A2"]), _ptr(a["cp_A_single2"]))
+        assert rc == 0
+        for n in ("dL", "dL_total", "TdL_total", "csx", "csy", "csz", "ddLp", "pl_flag", "dL_ave", "F", "Pin", "state_v", "cp_RSS", "cp_Jact",
+                  "cp_dgy", "cp_dA", "cp_dA_single", "dLp2", "cp_gy2", "cp_A_single2", "cp_A2"):
+            want = np.asarray(g[f"{tag}.c{k}.{n}"])
+            ok = ~np.isnan(want) if want.dtype.kind == "f" else np.ones(want.shape, bool)
+            assert_same(np.where(ok, a[n], 0), np.where(ok, want, 0), f"{tag} call {k} (particle {ii}): {n}")
+
+
 @pytest.mark.parametrize("name,lattice", [("sq2d_brittle", 0), ("hex2d_brittle", 1), ("sc6_j2", 2), ("fcc_cp", 3), ("bcc_cp", 4)])
 def test_port_calc_kntv_all_lattices_bit_exact(name, lattice):
     """calcKnTv (stiffness.c:11-268) restated for the five lattices, against the Kn / Tv the reference computed for the
