@@ -341,7 +341,11 @@ def _cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: i
     if not oref.available():
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     m = args.cpu_sample_n
-    cores = args.cpu_threads or (os.cpu_count() or 1)
+    try:
+        usable = len(os.sched_getaffinity(0))   # the cores this process may run on (os.cpu_count() ignores an affinity mask)
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    cores = args.cpu_threads or usable
     steps = steps or args.cpu_steps
     r = oref.RefLPM.instance()
     r.threads(cores)
