@@ -109,3 +109,13 @@ def test_c_multi_gpu_example_usage_and_loud_failure(lpm):
         pytest.skip("a CUDA device is present")
     r = subprocess.run([str(exe), "2", "8", "1"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr and "rank 0 failed" in r.stderr
+
+
+def test_python_binding_declares_argument_types_for_every_entry_point(lpm):
+    """ctypes would otherwise pass 64-bit handles / sizes as C ints: every declared function that takes arguments has
+    its argtypes set in lpm-c_b200/capi.py"""
+    from importlib import import_module
+    capi = import_module("lpm-c_b200.capi")
+    no_args = {"lpmb_device_count", "lpmb_last_error", "lpmb_version"}
+    missing = [n for n in capi.declared_symbols() if n not in no_args and getattr(capi.lib, n).argtypes is None]
+    assert not missing, missing
