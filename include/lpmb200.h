@@ -133,8 +133,8 @@ int lpmb_matrix_fill_test_pattern(lpmb_ctx *ctx);
 /* y = K x on host DoF vectors (interleaved); for tests and the SpMV micro-benchmark */
 int lpmb_spmv_host(lpmb_ctx *ctx, const double *x, double *y);
 /* repeat y = K x `reps` times on device-resident vectors, returns mean milliseconds per SpMV
- * measured with CUDA events on the context stream.  variant: 0 = full-format SELL kernel, 1 = experimental
- * L2-mediated symmetric storage, 2 = brick-blocked symmetric kernel (needs lpmb_matrix_enable_bricks) */
+ * measured with CUDA events on the context stream.  variant: 0 = full-format SELL kernel, 2 = brick-blocked
+ * symmetric kernel (needs lpmb_matrix_enable_bricks); 1 was an L2-mediated symmetric variant, removed (0.85x) */
 int lpmb_spmv_bench(lpmb_ctx *ctx, int reps, int variant, double *ms_per_spmv);
 /* Brick-blocked symmetric SpMV (lpmb_brick.cu): K is symmetric (stiffness.c:441-481 keeps one triangle), so
  * every block is streamed from HBM once and used for both of its contributions inside one CTA; about half the

@@ -44,6 +44,11 @@
  * (xyz, xyz_temp, F_temp, Pex, dispBC_index, fix_index, residual, K_global, type, Ce, parameters) are uploaded on
  * entry of the call that reads them.
  *
+ * solverPARDISO() (solver.c:3-92; selected by no shipped driver): no sparse direct factorisation on the GPU path.  The
+ * call runs the same CG to ||r|| <= 1e-12 ||r0|| (at most dim*N iterations), prints one notice on stderr the first time,
+ * and exits with status 3 if that residual is not reached -- the reference's PARDISO path also exits on failure
+ * (solver.c:50-84) rather than applying an unconverged displacement.
+ *
  * Declarations use empty parameter lists exactly like the reference's headers (the default driver
  * even calls updateRR(ni++), lpmc_project.c:462 -- harmless under the SysV x86-64 ABI).
  *

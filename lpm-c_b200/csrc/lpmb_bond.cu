@@ -1455,9 +1455,9 @@ extern "C" int lpmb_bond_force_particle(lpmb_ctx *c, int plmode, int ii, int loa
     std::vector<double> hb(nn);
     int nb_ii = 0;
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
-    LPMB_CUDA(cudaMemcpy2D(hn.data(), sizeof(int), v.nbr + ii, (size_t)Np * sizeof(int), sizeof(int), nn, cudaMemcpyDeviceToHost));
-    LPMB_CUDA(cudaMemcpy2D(hb.data(), sizeof(double), broken + ii, (size_t)Np * sizeof(double), sizeof(double), nn, cudaMemcpyDeviceToHost));
-    LPMB_CUDA(cudaMemcpy(&nb_ii, v.nb + ii, sizeof(int), cudaMemcpyDeviceToHost));
+    LPMB_CUDA(cudaMemcpy2DAsync(hn.data(), sizeof(int), v.nbr + ii, (size_t)Np * sizeof(int), sizeof(int), nn, cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaMemcpy2DAsync(hb.data(), sizeof(double), broken + ii, (size_t)Np * sizeof(double), sizeof(double), nn, cudaMemcpyDeviceToHost, c->stream));
+    LPMB_D2H(c, &nb_ii, v.nb + ii, sizeof(int));
     std::vector<int> star(1, ii);
     for (int k = 0; k < nn; k++)
         if (hb[k] > LPMB_EPS && hn[k] != -1)

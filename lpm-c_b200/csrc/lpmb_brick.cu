@@ -3,8 +3,8 @@
 //
 // Why.  K is symmetric (stiffness.c:441-481 keeps one triangle); the default SELL kernel streams both triangles
 // (61 blocks * 76 B per interior SC particle) and already runs at the HBM roofline, so the only way to make a CG
-// iteration faster is to move fewer bytes.  Re-using a block through L2 does not work on this chip (measured,
-// lpmb_symspmv.cu); re-using it inside one CTA does.
+// iteration faster is to move fewer bytes.  Re-using a block through L2 does not work on this chip (measured in
+// round 1: 0.85x of the full-format kernel at 216^3); re-using it inside one CTA does.
 //
 // How.  Particles are regrouped (internally only; the ABI keeps the reference's numbering) into bricks of 8x8x8
 // lattice sites = 512 rows = one CTA of 512 threads, thread r <-> row r = local lattice position.  A pair {i,j}
@@ -498,7 +498,7 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
     // lattice origin = component-wise minimum.  Slab runs (world > 1): rows exist only for the owned z-layers plus the
     // CG halo (2 layers); the outer, position-only ghost layers are left out.
     std::vector<double> hx((size_t)3 * Np);
-    LPMB_CUDA(cudaMemcpy(hx.data(), x0, hx.size() * 8, cudaMemcpyDeviceToHost));
+    LPMB_D2H(c, hx.data(), x0, hx.size() * 8);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int k = 0; k < 3; k++)
         for (int i = 0; i < N; i++) {
@@ -552,7 +552,7 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
     double *d_dev;
     LPMB_CUDA(cudaMalloc(&ic, (size_t)3 * Np * sizeof(int)));
     LPMB_CUDA(cudaMalloc(&d_dev, sizeof(double)));
-    LPMB_CUDA(cudaMemset(d_dev, 0, sizeof(double)));
+    LPMB_MEMSET(c, d_dev, 0, sizeof(double));
     brick_quantize_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, x0, B.ox, B.oy, B.oz, B.q, nz, ic, d_dev);
     LPMB_LAUNCH_CHECK(c);
     double dev = 0.0;
@@ -565,11 +565,11 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
         return LPMB_ERR_UNSUPPORTED;
     }
     LPMB_CUDA(cudaMalloc(&B.perm, (size_t)B.P * sizeof(int)));
-    LPMB_CUDA(cudaMemset(B.perm, 0xff, (size_t)B.P * sizeof(int)));
+    LPMB_MEMSET(c, B.perm, 0xff, (size_t)B.P * sizeof(int));
     LPMB_CUDA(cudaMalloc(&B.inv, (size_t)Np * sizeof(int)));
     int *d_flags;
     LPMB_CUDA(cudaMalloc(&d_flags, 128 * sizeof(int)));
-    LPMB_CUDA(cudaMemset(d_flags, 0, 128 * sizeof(int)));
+    LPMB_MEMSET(c, d_flags, 0, 128 * sizeof(int));
     brick_place_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, ic, B.nbx, B.nby, B.perm, B.inv, d_flags + 126);
     LPMB_LAUNCH_CHECK(c);
     brick_keys_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, ic, c->K.sptr, c->K.col, c->K.nbc, d_flags);
@@ -635,14 +635,14 @@ static int brick_build_pattern(lpmb_ctx *c, BrickMatrix &B)
             B.h_zr[((size_t)bz * B.ncls + u) * 2 + 1] = (unsigned char)(z1 > z0 ? z1 : 0);
         }
     LPMB_CUDA(cudaMalloc(&B.zr, B.h_zr.size()));
-    LPMB_CUDA(cudaMemcpy(B.zr, B.h_zr.data(), B.h_zr.size(), cudaMemcpyHostToDevice));
+    LPMB_H2D(c, B.zr, B.h_zr.data(), B.h_zr.size());
     const size_t nent = (size_t)B.nbricks * B.ncls * BR;
     LPMB_CUDA(cudaMalloc(&B.bval, nent * 9 * sizeof(double)));
     LPMB_CUDA(cudaMalloc(&B.stage, (size_t)B.nbricks * 3 * NSLOT * sizeof(double)));
-    LPMB_CUDA(cudaMemset(B.stage, 0, (size_t)B.nbricks * 3 * NSLOT * sizeof(double)));
+    LPMB_MEMSET(c, B.stage, 0, (size_t)B.nbricks * 3 * NSLOT * sizeof(double));
     for (double **v : {&B.ypart, &B.r, &B.p, &B.ap, &B.x, &B.b, &B.mask}) {
         LPMB_CUDA(cudaMalloc(v, (size_t)3 * B.P * sizeof(double)));
-        LPMB_CUDA(cudaMemset(*v, 0, (size_t)3 * B.P * sizeof(double)));
+        LPMB_MEMSET(c, *v, 0, (size_t)3 * B.P * sizeof(double));
     }
     B.ic = ic;
     // 216.6 KB of dynamic shared memory per CTA: opt in on this context's device

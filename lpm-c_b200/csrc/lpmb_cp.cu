@@ -364,7 +364,7 @@ extern "C" int lpmb_set_schmid_tensor(lpmb_ctx *c, const double *schmid, int nsl
     f.comps = 6;
     f.count = (size_t)nslipSys * 6;
     LPMB_CUDA(cudaMalloc(&f.d, f.count * 8));
-    LPMB_CUDA(cudaMemcpy(f.d, schmid, f.count * 8, cudaMemcpyHostToDevice));
+    LPMB_H2D(c, f.d, schmid, f.count * 8);
     c->fields["schmid_tensor"] = f;
     return LPMB_OK;
 }

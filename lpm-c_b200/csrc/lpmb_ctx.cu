@@ -389,7 +389,6 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaStreamSynchronize(c->stream);
     lpmb_grid_release(c);
     lpmb_dist_release(c);
-    lpmb_sym_release(c);
     lpmb_brick_release(c);
     for (auto &e : c->prof_events)
         cudaEventDestroy(e);

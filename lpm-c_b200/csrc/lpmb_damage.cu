@@ -406,8 +406,8 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
             // reference logging order: i ascending, then slot j ascending (constitutive.c:1829-1845)
             std::vector<signed char> hn((size_t)nn * Np);
             std::vector<int> hnbr((size_t)nn * Np);
-            LPMB_CUDA(cudaMemcpy(hn.data(), newly, hn.size(), cudaMemcpyDeviceToHost));
-            LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            LPMB_D2H(c, hn.data(), newly, hn.size());
+            LPMB_D2H(c, hnbr.data(), nbr, hnbr.size() * sizeof(int));
             int t = 0;
             for (int i = 0; i < N && t < max_pairs; i++)
                 for (int j = 0; j < nn && t < max_pairs; j++)
@@ -443,8 +443,8 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
         if (k > 0) {
             std::vector<int> hk(k);
             std::vector<double> hs(k);
-            LPMB_CUDA(cudaMemcpy(hk.data(), keys, k * sizeof(int), cudaMemcpyDeviceToHost));
-            LPMB_CUDA(cudaMemcpy(hs.data(), strain, k * sizeof(double), cudaMemcpyDeviceToHost));
+            LPMB_D2H(c, hk.data(), keys, k * sizeof(int));
+            LPMB_D2H(c, hs.data(), strain, k * sizeof(double));
             // restore the reference's scan order (i, then j ascending == key ascending)
             std::vector<int> ord(k);
             for (int t = 0; t < k; t++)
@@ -484,12 +484,12 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
                 first = k - nbreak;
             }
             const int nb = k - first;
-            LPMB_CUDA(cudaMemcpy(keys, bi.data() + first, nb * sizeof(int), cudaMemcpyHostToDevice));
+            LPMB_H2D(c, keys, bi.data() + first, nb * sizeof(int));
             brittle_apply_kernel<<<lpmb_blocks(nb, 128), 128, 0, c->stream>>>(nb, nn, Np, keys, broken, dD0, w);
             c->launches++;
             if (pairs && max_pairs > 0) {
                 std::vector<int> hnbr((size_t)nn * Np);
-                LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                LPMB_D2H(c, hnbr.data(), nbr, hnbr.size() * sizeof(int));
                 for (int t = 0; t < nb && t < max_pairs; t++) {
                     const int i = bi[first + t] / nn, j = bi[first + t] % nn;
                     pairs[2 * t] = i;
@@ -525,8 +525,8 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
             // reference logging order: i ascending, then slot j ascending (constitutive.c:1644-1676)
             std::vector<signed char> hn((size_t)nn * Np);
             std::vector<int> hnbr((size_t)nn * Np);
-            LPMB_CUDA(cudaMemcpy(hn.data(), newly, hn.size(), cudaMemcpyDeviceToHost));
-            LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            LPMB_D2H(c, hn.data(), newly, hn.size());
+            LPMB_D2H(c, hnbr.data(), nbr, hnbr.size() * sizeof(int));
             int t = 0;
             for (int i = 0; i < N && t < max_pairs; i++)
                 for (int j = 0; j < nn && t < max_pairs; j++)
@@ -577,7 +577,7 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
             // reference logging order: particle (or i, then slot j) ascending; the particle-wise law logs a single
             // index per entry (constitutive.c:1562) -> second column -1
             std::vector<signed char> hn(nflag);
-            LPMB_CUDA(cudaMemcpy(hn.data(), newly, hn.size(), cudaMemcpyDeviceToHost));
+            LPMB_D2H(c, hn.data(), newly, hn.size());
             int t = 0;
             if (pw) {
                 for (int i = 0; i < N && t < max_pairs; i++)
@@ -588,7 +588,7 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
                     }
             } else {
                 std::vector<int> hnbr((size_t)nn * Np);
-                LPMB_CUDA(cudaMemcpy(hnbr.data(), nbr, hnbr.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                LPMB_D2H(c, hnbr.data(), nbr, hnbr.size() * sizeof(int));
                 for (int i = 0; i < N && t < max_pairs; i++)
                     for (int j = 0; j < nn && t < max_pairs; j++)
                         if (hn[(size_t)j * Np + i]) {

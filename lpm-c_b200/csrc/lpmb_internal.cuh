@@ -26,6 +26,22 @@ void lpmb_set_error(const char *fmt, ...);
         }                                                                                            \
     } while (0)
 
+// Every device operation of a context is ordered on c->stream, which is created cudaStreamNonBlocking: the legacy
+// NULL stream does NOT synchronise with it, so memsets and copies must be issued on c->stream as well (a cudaMemset /
+// cudaMemcpy on the NULL stream may run before or after kernels queued on c->stream).  The copies wait for completion
+// because their host side is pageable and reused right away.
+#define LPMB_MEMSET(c, p, v, n) LPMB_CUDA(cudaMemsetAsync((p), (v), (n), (c)->stream))
+#define LPMB_D2H(c, dst, src, n)                                                                     \
+    do {                                                                                             \
+        LPMB_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, (c)->stream));          \
+        LPMB_CUDA(cudaStreamSynchronize((c)->stream));                                               \
+    } while (0)
+#define LPMB_H2D(c, dst, src, n)                                                                     \
+    do {                                                                                             \
+        LPMB_CUDA(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, (c)->stream));          \
+        LPMB_CUDA(cudaStreamSynchronize((c)->stream));                                               \
+    } while (0)
+
 #define LPMB_TRY(call)              \
     do {                            \
         int r__ = (call);           \
@@ -76,20 +92,6 @@ struct SellMatrix {
     bool values_ready = false;
 };
 
-// Symmetric acceleration structure for the SpMV (lpmb_symspmv.cu): only blocks with column >= row are
-// streamed from HBM; the transposed (lower) contributions are gathered from the partner rows' upper blocks,
-// which a strip-ordered slice schedule keeps L2-resident.
-struct SymMatrix {
-    bool ready = false;
-    long long ukunits = 0, lkunits = 0;
-    long long *usptr = nullptr, *lsptr = nullptr;  // [nslices+1]
-    int *ucol = nullptr;                            // [ukunits+1][32]
-    double *uval = nullptr;                         // [ukunits+1][D*D][32] (last unit = zeros, padding target)
-    int *lcol = nullptr, *lpos = nullptr;           // [lkunits][32]: partner row j, position of block (j,i) in uval
-    int *order = nullptr;                           // slice processing order
-    int norder = 0;
-};
-
 struct CGWork {
     double *r = nullptr, *p = nullptr, *ap = nullptr, *x = nullptr;  // [D][Np] each
     double *partials = nullptr;                                       // [2][max_blocks]
@@ -123,7 +125,6 @@ struct lpmb_ctx {
     int narrow_recv_lo = 0, narrow_recv_hi = 0, narrow_send_lo = 0, narrow_send_hi = 0;
     int wide_send_lo = 0, wide_send_hi = 0;
     // optional live profiling of the dominant kernel (CUDA events around every CG SpMV launch)
-    SymMatrix sym;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;
     double prof_spmv_ms = 0.0;
@@ -244,11 +245,6 @@ __device__ __forceinline__ void lpmb_peer_wait(const PeerWait &w)
     }
 }
 
-// symmetric SpMV (lpmb_symspmv.cu)
-int lpmb_sym_build(lpmb_ctx *c);
-void lpmb_sym_release(lpmb_ctx *c);
-int lpmb_sym_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int grid);
-long long lpmb_sym_bytes(lpmb_ctx *c);
 
 // brick-blocked symmetric SpMV (lpmb_brick.cu): optional, single GPU, simple-cubic 3-D
 void lpmb_brick_release(lpmb_ctx *c);

@@ -125,10 +125,10 @@ int lpmb_peer_init(lpmb_ctx *c)
         return LPMB_OK;
     PeerComm &pc = g_peers[c];
     LPMB_CUDA(cudaMalloc(&pc.buf, PEER_BUF_BYTES));
-    LPMB_CUDA(cudaMemset(pc.buf, 0, PEER_BUF_BYTES));
+    LPMB_MEMSET(c, pc.buf, 0, PEER_BUF_BYTES);
     {   // neighbours that do not exist never raise a flag: pre-raise it for good
         unsigned long long halo[2] = {c->rank > 0 ? 0ull : ~0ull, c->rank < c->world - 1 ? 0ull : ~0ull};
-        LPMB_CUDA(cudaMemcpy(pc.buf + OFF_HALO, halo, sizeof(halo), cudaMemcpyHostToDevice));
+        LPMB_H2D(c, pc.buf + OFF_HALO, halo, sizeof(halo));
     }
     void *opened[LPMB_PEER_MAXW] = {nullptr};
     bool ok = false;

@@ -153,8 +153,8 @@ extern "C" int lpmb_get_k_pointer(lpmb_ctx *c, int *k_pointer)
     const int N = c->N;
     std::vector<long long> kp((size_t)N + 1);
     std::vector<int> k0(N);
-    LPMB_CUDA(cudaMemcpy(kp.data(), c->K.kp, ((size_t)N + 1) * sizeof(long long), cudaMemcpyDeviceToHost));
-    LPMB_CUDA(cudaMemcpy(k0.data(), c->K.k0, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+    LPMB_D2H(c, kp.data(), c->K.kp, ((size_t)N + 1) * sizeof(long long));
+    LPMB_D2H(c, k0.data(), c->K.k0, (size_t)N * sizeof(int));
     for (int i = 0; i <= N; i++) {
         k_pointer[2 * i] = i < N ? k0[i] : 0;
         k_pointer[2 * i + 1] = (int)kp[i];
@@ -174,8 +174,6 @@ extern "C" long long lpmb_spmv_bytes_stored(lpmb_ctx *c)
 {
     if (!c || !c->K.pattern_ready)
         return 0;
-    if (param(c, "spmv_symmetric", 0.0) != 0.0 && c->sym.usptr)
-        return lpmb_sym_bytes(c);
     const long long d = c->dim;
     return c->K.kunits * 32 * (8 * d * d + 4) + 8LL * (c->K.nslices + 1) + 16LL * d * c->Np;
 }
@@ -326,7 +324,6 @@ extern "C" int lpmb_matrix_from_upper_csr(lpmb_ctx *c, const double *K_global, l
     LPMB_LAUNCH_CHECK(c);
     LPMB_CUDA(cudaStreamSynchronize(c->stream));
     K.values_ready = true;
-    c->sym.ready = false;  // the symmetric acceleration structures mirror these values
     lpmb_brick_touch(c);
     return LPMB_OK;
 }
@@ -377,7 +374,6 @@ extern "C" int lpmb_matrix_fill_test_pattern(lpmb_ctx *c)
         fill_test_pattern_kernel<2><<<blocks, 128, 0, c->stream>>>(K.nbc, K.sptr, K.col, K.val, c->N, K.nslices);
     LPMB_LAUNCH_CHECK(c);
     K.values_ready = true;
-    c->sym.ready = false;  // the symmetric acceleration structures mirror these values
     lpmb_brick_touch(c);
     return LPMB_OK;
 }
@@ -540,12 +536,6 @@ static int launch_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, bool u
     const int grid = spmv_grid(c);
     const int sb = slice_begin(c), se = slice_end(c);
     const double *m = use_mask ? c->mask : nullptr;
-    if (param(c, "spmv_symmetric", 0.0) != 0.0) {
-        // upper-triangle streaming variant (lpmb_symspmv.cu); the structure mirrors K.val and is rebuilt lazily
-        if (!c->sym.ready)
-            LPMB_TRY(lpmb_sym_build(c));
-        return lpmb_sym_spmv(c, x, y, dot, m, c->cg.partials, dot ? c->cg.scal : nullptr, grid);
-    }
     if (c->dim == 3) {
         if (dot)
             spmv_sell_kernel<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
@@ -989,7 +979,7 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
     LPMB_REQUIRE(c && reps > 0 && ms_per_spmv, LPMB_ERR_ARG, "lpmb_spmv_bench: bad argument");
     LPMB_CUDA(cudaSetDevice(c->device));
     LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
-    LPMB_REQUIRE(variant >= 0 && variant <= 2, LPMB_ERR_ARG, "unknown SpMV variant %d (0 = full SELL, 1 = symmetric upper, 2 = bricks)", variant);
+    LPMB_REQUIRE(variant == 0 || variant == 2, LPMB_ERR_ARG, "unknown SpMV variant %d (0 = full SELL, 2 = bricks)", variant);
     if (variant == 2) {
         LPMB_REQUIRE(lpmb_brick_active(c), LPMB_ERR_STATE, "brick SpMV not enabled (lpmb_matrix_enable_bricks)");
         LPMB_TRY(lpmb_cg_alloc(c));
@@ -1018,8 +1008,6 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
         *ms_per_spmv = (double)ms / reps;
         return LPMB_OK;
     }
-    const double saved_variant = param(c, "spmv_symmetric", 0.0);
-    c->params["spmv_symmetric"] = (double)variant;
     LPMB_TRY(lpmb_cg_alloc(c));
     fill_sin_kernel<<<vec_grid(c, (size_t)c->dim * c->Np), VEC_THREADS, 0, c->stream>>>(c->cg.p, c->dim, c->N, c->Np);
     LPMB_LAUNCH_CHECK(c);
@@ -1038,6 +1026,5 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_per_spmv = (double)ms / reps;
-    c->params["spmv_symmetric"] = saved_variant;
     return LPMB_OK;
 }

@@ -595,7 +595,6 @@ extern "C" int lpmb_fd_stiffness(lpmb_ctx *c, int emulate_side_effects)
         LPMB_LAUNCH_CHECK(c);
     }
     K.values_ready = true;
-    c->sym.ready = false;  // the symmetric acceleration structures mirror these values
     lpmb_brick_touch(c);
     if (emulate_side_effects) {
         double *dL = fptr<double>(c, "dL"), *csx = fptr<double>(c, "csx"), *csy = fptr<double>(c, "csy"), *csz = fptr<double>(c, "csz");

@@ -63,6 +63,8 @@ def main():
                 w[i, j] = w[k, jj] = 0.0
             r.put("damage_broken", br)
             r.put("damage_w", w)
+            if hasattr(L, "lpmc_dropin_invalidate_state"):   # drop-in replay: announce the HOST edit (include/lpmc_dropin.h)
+                L.lpmc_dropin_invalidate_state()
             L.updateCrack()
         r.set_d2("xyz_temp", r.d2("xyz", N, 3))
         r.set_d2("F_temp", r.d2("F", N, nn))

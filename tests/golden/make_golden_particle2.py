@@ -79,6 +79,8 @@ def break_bonds(r):
         partners.append(k)
     r.put("damage_broken", br)
     r.put("damage_w", w)
+    if hasattr(r.lib, "lpmc_dropin_invalidate_state"):   # drop-in replay: a HOST edit of device-authoritative state must be announced
+        r.lib.lpmc_dropin_invalidate_state()             # (include/lpmc_dropin.h, "State ownership"); without it the device keeps nb = 18
     r.lib.updateCrack()
     return partners
 

@@ -27,7 +27,6 @@ def test_two_gpu_slabs_match_single_gpu_without_torch(lpm):
     assert r.returncode == 0 and "DIST_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.xfail(strict=False, reason="examples/sc_block_mgpu.c was written after round 1's GPU budget was spent: not run on a multi-GPU box yet")
 def test_c_multi_gpu_example_reproduces_default_case_known_answers(lpm):
     """examples/sc_block_mgpu: the default case C1 (21^3) on 2 GPUs from plain C over the C ABI (fork + exec per rank, NCCL id
     through a file): Newton iterations 2 2 1 and -- up to the summation order of the all-reduced dot products -- the CG
@@ -48,7 +47,6 @@ def test_c_multi_gpu_example_reproduces_default_case_known_answers(lpm):
     assert m and abs(float(m.group(1)) / (3 * -1.27857453e-03) - 1.0) < 0.05      # ~linear in the elastic range
 
 
-@pytest.mark.xfail(strict=False, reason="brick_spmv_kernel<true> (lazy halo wait) was written after round 1's GPU budget was spent: never run")
 def test_two_gpu_slabs_with_lazy_halo_wait(lpm):
     """the experimental brick-by-brick halo wait (param brick_lazy_wait, LPMB_BRICK_LAZY_WAIT=1): same 2-GPU-vs-1-GPU check"""
     import os

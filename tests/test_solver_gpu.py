@@ -126,25 +126,6 @@ def test_large_lattice_properties(lpm):
     c.close()
 
 
-def test_symmetric_storage_variant_agrees(lpm, golden):
-    """experimental upper-triangle SpMV (lpmb_symspmv.cu): same product and same CG as the full format"""
-    from helpers import make_ctx
-    c = make_ctx(lpm, golden)
-    c.fd_stiffness(False)
-    rng = np.random.default_rng(20240607)
-    x = rng.standard_normal(648)
-    y0 = c.spmv(x)
-    c.set_dof_mask(golden["s1.bc.dispBC_index"], golden["s1.bc.fix_index"])
-    d0, it0, ok0 = c.solve_cg(golden["s1.rr.residual"], use_mask=True)
-    c.set_param("spmv_symmetric", 1)
-    y1 = c.spmv(x)
-    d1, it1, ok1 = c.solve_cg(golden["s1.rr.residual"], use_mask=True)
-    assert np.abs(y0 - y1).max() <= 1e-13 * np.abs(y0).max()
-    assert ok0 and ok1 and it0 == it1 == int(golden["s1.n0.cg_iters"][0])
-    assert np.linalg.norm(d0 - d1) <= 1e-11 * np.linalg.norm(d0)
-    c.close()
-
-
 @pytest.mark.parametrize("dims", [(8, 8, 8), (20, 13, 9), (17, 24, 33)])
 def test_brick_spmv_matches_full_format(lpm, dims):
     """brick-blocked symmetric kernel (lpmb_brick.cu) == full-format SELL kernel, including partial bricks,

@@ -319,12 +319,8 @@ def test_2d_brittle_trajectory(lpm, name, steps):
 
 
 # ---- BCC lattice (8 + 6 neighbours, 41 conn, 24 slip systems): crystal plasticity on the reference's fifth lattice --------
-NOT_YET_RUN = pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first B200 run is the round-end suite")
-
-
-@NOT_YET_RUN
 def test_bcc_crystal_plasticity():
-    """runs impl_bcc_crystal_plasticity in a child process (never run on a B200 yet: keep a failure of the library there)"""
+    """runs impl_bcc_crystal_plasticity in a child process (child process: keeps a failure of the library there)"""
     from helpers import run_isolated
     print(run_isolated(__file__, "impl_bcc_crystal_plasticity")[-300:])
 

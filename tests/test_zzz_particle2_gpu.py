@@ -8,10 +8,10 @@ runs after them in the same process.
    bit-exact on them in the CPU suite.  These ran green on a B200 with the round's last GPU seconds
    (profiles/r01i_per_particle_and_regression_gpu_tests.log: plmode 3 / 5 bit-exact, plmode 1 within 1e-9 with identical
    memo flags and active sets).
-2. Drop-in replays of the two fixtures (the reference's host code drives liblpmc_dropin.so; ~10 s each): did not fit the
-   remaining budget -> non-strict xfail.
+2. Drop-in replays of the two fixtures (the reference's host code drives liblpmc_dropin.so; ~10 s each).
 3. The O(N) device topology builder at the REAL sizes of BASELINE configs 2-5 against the reference's own O(N^2) search
-   (oracle/_ref at run time): not run yet -> non-strict xfail."""
+   (oracle/_ref at run time).
+No test of the suite is hedged with xfail."""
 import os
 import subprocess
 from pathlib import Path
@@ -92,10 +92,15 @@ def test_per_particle_j2_energy_and_iso_laws_bit_exact(lpm, tag, law):
     c.close()
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (the C-ABI tests above ran green)")
 def test_dropin_replays_per_particle_j2_energy_and_iso_case(tmp_path):
-    """tests/golden/sc6_particle2.npz regenerated with every call -- the per-particle ones by their reference names --
-    going through liblpmc_dropin.so: phases of step 1 follow one CG solve (1e-10), so 1e-9; plastic flags identical"""
+    """tests/golden/sc6_particle2.npz regenerated with every call -- the per-particle ones by their reference names
+    (constitutive.h:18,21) -- going through liblpmc_dropin.so.  Step 1 phases follow one GPU CG solve (disp within 1e-10 of
+    the reference's): 1e-9, plastic flags identical.  Step 2 (three bonds broken on the HOST -- announced with
+    lpmc_dropin_invalidate_state() as include/lpmc_dropin.h asks --, updateCrack, committed plastic history, t = -1 for
+    plmode 3) follows four more solves and bisection-quantised multipliers (2^-14, constitutive.c:369-387,773-790): the same
+    bounds as the whole-lattice replays in tests/test_dropin_gpu.py (1e-7 / 1e-6, one bisection step on J2_dlambda).
+    Round-1 failure of this test: the generator broke the bonds on the host WITHOUT the announcement, the device kept
+    nb = 18 and lpmb_bond_force_particle refused the inconsistent star ("nb = 18 but 17 intact bonds") -- a harness bug."""
     new = _regen("make_golden_particle2.py", tmp_path, "pp2.npz")
     old = np.load(GOLD / "sc6_particle2.npz")
     for tag, law in (("e.s1", 3), ("i.s1", 5)):
@@ -103,6 +108,14 @@ def test_dropin_replays_per_particle_j2_energy_and_iso_case(tmp_path):
             for n in PP2_WRITES[law]:
                 assert _rel(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]) <= 1e-9, (tag, k, n)
     assert np.array_equal(new["e.s1.c4.pl_flag"], old["e.s1.c4.pl_flag"])
+    for tag, law, tol in (("e.s2", 3, 1e-7), ("i.s2", 5, 1e-6)):
+        assert np.array_equal(new[f"{tag}.pre.nb"], old[f"{tag}.pre.nb"]) and int(old[f"{tag}.pre.nb"].min()) < 18
+        assert np.array_equal(new[f"{tag}.pre.damage_broken"], old[f"{tag}.pre.damage_broken"])
+        for k in range(5):
+            assert np.abs(new[f"{tag}.c{k}.J2_dlambda"] - old[f"{tag}.c{k}.J2_dlambda"]).max() <= 2.0 ** -13, (tag, k)
+            for n in PP2_WRITES[law]:
+                if n != "J2_dlambda":
+                    assert _rel(new[f"{tag}.c{k}.{n}"], old[f"{tag}.c{k}.{n}"]) <= tol, (tag, k, n)
 
 
 # ---- computeBondForceCPMiehe(ii) with its memo (constitutive.h:19, constitutive.c:866-1396, 946-959) ---------------
@@ -137,7 +150,6 @@ def test_per_particle_crystal_plasticity_law(lpm, tag):
     c.close()
 
 
-@pytest.mark.xfail(strict=False, reason="first B200 run is the round-end suite (the C-ABI tests above ran green)")
 def test_dropin_replays_per_particle_crystal_plasticity_case(tmp_path):
     """the fixture regenerated with computeBondForceCPMiehe(ii) and everything around it going through liblpmc_dropin.so"""
     new = _regen("make_golden_cp_particle.py", tmp_path, "cpp.npz")
@@ -151,8 +163,6 @@ def test_dropin_replays_per_particle_crystal_plasticity_case(tmp_path):
 
 
 # ---- O(N) device topology builder at the REAL sizes of BASELINE configs 2-4 ------------------------------------------
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; the reference side of the comparison (sizes of "
-                                        "SURVEY's config table, oracle port bit-exact) is in the CPU suite")
 @pytest.mark.parametrize("tag", ["C2", "C3", "C4", "C5src"])
 def test_build_topology_at_the_real_config_sizes(tag):
     """runs impl_build_topology_at_the_real_config_sizes[tag] in a child process (never run on a B200 yet)"""
