@@ -298,9 +298,9 @@ def gpu_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference_sample(args, n_full=n)
     c.close()
+    if not args.no_cpu_baseline:
+        out.update(cpu_reference_sample(args, n_full=n, with_gpu_dropin=True, device=local))
     print(json.dumps(out), flush=True)
 
 
@@ -328,43 +328,52 @@ class _QuietStdout:
         return False
 
 
-def cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: int = 1) -> dict:
-    with _QuietStdout():
-        return _cpu_reference_sample(args, n_full, steps, warmup)
+# CG iterations of Newton iteration 0 of load step 1 of this workload, by lattice size n (n^3 particles).  MEASURED: 116 at
+# 48^3 and 226 at 100^3 by the reference's own solverCG() and by the GPU arm alike (parity_at_sample / reference arm print
+# them), 458 at 216^3 by the GPU arm (every BENCH / SCALE line, config.cg_iterations_per_step) -- the reference cannot
+# set 216^3 up at all (32-bit K_pointer, neighbor.c:114-134).  Used to carry a measured CPU time to the 216^3 config.
+CG_ITERS_MEASURED = {48: 116, 100: 226, 216: 458}
 
 
-def _cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: int = 1) -> dict:
-    """The reference's OWN functions (oracle/_ref = its unmodified sources + open MKL stand-in, NOT Intel MKL)
-    timed on the host cores on a bounded sample of the workload: the same physics / BCs / Newton iteration on an
-    m^3 block, extrapolated to n_full^3 with the per-particle cost and the measured CG-iterations ~ n law."""
-    from oracle import ref as oref
-    if not oref.available():
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-    m = args.cpu_sample_n
+def usable_cores() -> int:
     try:
-        usable = len(os.sched_getaffinity(0))   # the cores this process may run on (os.cpu_count() ignores an affinity mask)
+        return len(os.sched_getaffinity(0))   # the cores this process may run on (os.cpu_count() ignores an affinity mask)
     except AttributeError:
-        usable = os.cpu_count() or 1
-    cores = args.cpu_threads or usable
-    steps = steps or args.cpu_steps
+        return os.cpu_count() or 1
+
+
+def reference_newton_sample(m: int, steps: int, warmup: int, cores: int, keep_outputs: bool = False) -> dict:
+    """One load-step start + `warmup + steps` replays of Newton iteration 0 on an SC m^3 block of the bench physics, through
+    the reference-named entry points of whatever oracle.ref.REF_SO is loaded in THIS process: oracle/_ref/liblpmc_ref.so (the
+    unmodified reference, CPU) or oracle/_ref/liblpmc_b200host.so (the reference's host code + the GPU drop-in library).
+    Topology by oracle.ref.inject_sc_topology (O(N), bit-identical to the reference's O(N^2) search).  The reference's FD
+    assembly races under OpenMP when threads work on nearby layers (measured here: 8 threads on 32 layers
+    -> K wrong by 2e-4, 494 instead of 79 CG iterations), so it runs on m // 12 threads (>= 12 layers per static chunk;
+    48^3: 1 vs 4 threads agree to 2e-16 in K, 5e-16 in disp)."""
+    from oracle import ref as oref
     r = oref.RefLPM.instance()
     r.threads(cores)
     hi = 0.5 * (m - 1)
+    t_setup = time.perf_counter()
     for extra in (0.0, 0.25, -0.2):
         box = (-0.2, hi + extra, -0.2, hi + extra, -0.2, hi + extra)
         r.setup_sc(box=box, radius=PHYS["radius"], E0=PHYS["E0"], mu0=PHYS["mu0"],
                    plmode=0, sigmay=PHYS["sigmay"], J2_xi=PHYS["J2_xi"], J2_H=PHYS["J2_H"], nbreak=PHYS["nbreak"],
                    critical_bstrain=PHYS["critical_bstrain"], damageb_A=PHYS["damageb_A"], damagec_A=PHYS["damagec_A"],
-                   damage_threshold=PHYS["damage_threshold"], damage_L=PHYS["damage_L"], top_z="auto")
+                   damage_threshold=PHYS["damage_threshold"], damage_L=PHYS["damage_L"], top_z="auto", neighbor_search="lattice")
         if r.N == m ** 3:
             break
-    N = r.N
-    L = r.lib
-    height = float(r.get("xyz")[:, 2].max() - r.get("xyz")[:, 2].min())
-    # reference types from setup_sc: 1 = top layer, 2 = bottom layer; same BCs as the GPU arm
-    L.omp_set_num_threads(3)   # the author's nt_force for the racy FD assembly (lpmc_project.c:57,391)
+    assert r.N == m ** 3, (r.N, m)
+    t_setup = time.perf_counter() - t_setup
+    N, L = r.N, r.lib
+    z = r.get("xyz")[:, 2]
+    height = float(z.max() - z.min())
+    dropin = hasattr(L, "lpmc_dropin_last_cg_iterations")
+    fd_threads = max(1, min(cores, m // 12))
+    L.omp_set_num_threads(fd_threads)
     t0 = time.perf_counter()
-    r.begin_step([(2, "z", 0.0), (1, "z", STRAIN_STEP * height)], [])
+    # reference types from setup_sc: 1 = top layer, 2 = bottom layer; same BCs as the GPU arm
+    nr0, nf0 = r.begin_step([(2, "z", 0.0), (1, "z", STRAIN_STEP * height)], [])
     t_fd = time.perf_counter() - t0
     L.omp_set_num_threads(cores)
     xyz_s, res_s = r.get("xyz"), r.get("residual")
@@ -374,46 +383,167 @@ def _cpu_reference_sample(args, n_full: int, steps: int | None = None, warmup: i
         a = time.perf_counter()
         L.solverCG()
         t_solve.append(time.perf_counter() - a)
-        its.append(L.lpmb_shim_last_itercount())
+        its.append(int(L.lpmc_dropin_last_cg_iterations() if dropin else L.lpmb_shim_last_itercount()))
 
     for k in range(warmup + steps):
         r.put("xyz", xyz_s)
         r.put("residual", res_s)
         a = time.perf_counter()
-        r.newton_iteration(hooks={"solve": timed_solve})
+        nr = r.newton_iteration(hooks={"solve": timed_solve})
         if k >= warmup:
             times.append(time.perf_counter() - a)
-    t_step = float(np.mean(times))
-    t_cg = float(np.mean(t_solve[warmup:]))
-    it_s = int(its[-1])
-    scale_n = (n_full ** 3) / N
-    t_full = t_cg * scale_n * (n_full / m) + (t_step - t_cg) * scale_n
-    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": (f"reference's own switchStateV/setDispBC_stiffnessUpdate3D/solverCG/computeBondForceGeneral(0)/updateRR "
-                       f"(unmodified sources + open MKL stand-in with a threaded symmetric SpMV, not Intel MKL) on an SC {m}^3 block ({N} particles): "
-                       f"{t_step:.3f} s per Newton iteration ({it_s} CG its, solverCG {t_cg:.3f} s), {steps} timed; "
-                       f"extrapolated to {n_full}^3 as t_cg*(N/Ns)*(n/m) + t_rest*(N/Ns) (CG iterations grow ~ n)"),
-            "sample_newton_it_per_s": 1.0 / t_step, "sample_particles": N, "sample_cg_iterations": it_s,
-            "sample_fd_assembly_s_3threads": t_fd}
+    out = {"m": m, "particles": N, "cores": cores, "fd_threads": fd_threads, "setup_s": t_setup, "begin_step_s": t_fd,
+           "t_step": float(np.mean(times)), "t_cg": float(np.mean(t_solve[warmup:])), "cg_iterations": int(its[-1]), "steps": steps,
+           "norm_residual0": float(nr0), "norm_residual1": float(nr), "impl": "dropin" if dropin else "cpu"}
+    if keep_outputs:
+        out["arrays"] = {"disp": r.get("disp"), "F": r.get("F"), "Pin": r.get("Pin"), "xyz0": xyz_s, "xyz": r.get("xyz")}
+    return out
+
+
+def extrapolate_to(n_full: int, smp: dict) -> float:
+    """seconds per Newton iteration at n_full^3 from a measured m^3 sample: per-particle cost, CG time additionally scaled
+    with the MEASURED iteration counts (CG_ITERS_MEASURED), the rest of the iteration linearly"""
+    m = smp["m"]
+    scale_n = (n_full ** 3) / smp["particles"]
+    it_ratio = CG_ITERS_MEASURED[n_full] / smp["cg_iterations"] if n_full in CG_ITERS_MEASURED else n_full / m
+    return smp["t_cg"] * scale_n * it_ratio + (smp["t_step"] - smp["t_cg"]) * scale_n
+
+
+def dropin_sample_child(args):
+    """child process of the GPU arm (LPMB_REF_SO = oracle/_ref/liblpmc_b200host.so): the same sample through the reference's
+    host code + reference-named GPU drop-in entry points; results to args.sample_child (npz)"""
+    with _QuietStdout():
+        smp = reference_newton_sample(args.cpu_sample_n, args.cpu_steps, 1, args.cpu_threads or usable_cores(), keep_outputs=True)
+    arrays = smp.pop("arrays")
+    np.savez(args.sample_child, meta=np.array([json.dumps(smp)]), **arrays)
+
+
+def run_dropin_sample(args, m: int, steps: int, device: int = 0, device_bc: bool = False):
+    """GPU drop-in run of the sample in a child process (its own CUDA context; the reference keeps its state in process
+    globals, so the CPU and the drop-in build cannot share a process)"""
+    import tempfile
+    host_so = ROOT / "oracle" / "_ref" / "liblpmc_b200host.so"
+    if not host_so.exists():
+        return None, None
+    with tempfile.TemporaryDirectory() as d:
+        out = Path(d) / "dropin.npz"
+        env = dict(os.environ, LPMB_REF_SO=str(host_so), LPMB_DEVICE=str(device))
+        if device_bc:
+            env["LPMB_DROPIN_DEVICE_BC"] = "1"
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--sample-child", str(out), "--cpu-sample-n", str(m), "--cpu-steps", str(steps),
+               "--cpu-threads", str(args.cpu_threads or 0)]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        if r.returncode != 0 or not out.exists():
+            return {"error": (r.stderr or r.stdout)[-500:]}, None
+        z = np.load(out)
+        return json.loads(str(z["meta"][0])), {k: z[k] for k in z.files if k != "meta"}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float).ravel(), np.asarray(b, float).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def cpu_reference_sample(args, n_full: int, with_gpu_dropin: bool = False, device: int = 0) -> dict:
+    """cpu_baseline leg of the GPU arm: the reference's OWN functions (oracle/_ref = its unmodified sources + open MKL
+    stand-in, NOT Intel MKL) on all host cores on the m^3 sample (default 48^3), carried to n_full^3 with the measured
+    CG iteration counts.  with_gpu_dropin: the same sample once more through liblpmc_dropin.so (child process) ->
+    parity_at_sample (CG iterations equal, disp / F / Pin to 1e-9) and same_config_sample (one measured GPU/CPU pair on
+    identical inputs through the reference's own API)."""
+    from oracle import ref as oref
+    if not oref.available():
+        return {"cpu_baseline": {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}}
+    m, cores = args.cpu_sample_n, args.cpu_threads or usable_cores()
+    with _QuietStdout():
+        smp = reference_newton_sample(m, args.cpu_steps, 1, cores, keep_outputs=with_gpu_dropin)
+    cpu_arrays = smp.pop("arrays", None)
+    t_full = extrapolate_to(n_full, smp)
+    res = {"cpu_baseline": {
+        "value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "reference",
+        "sample": (f"reference's own switchStateV / setDispBC_stiffnessUpdate3D / solverCG / computeBondForceGeneral(0) / updateRR "
+                   f"(unmodified sources + open MKL stand-in with a threaded symmetric SpMV, not Intel MKL) on an SC {m}^3 block "
+                   f"({smp['particles']} particles): {smp['t_step']:.3f} s per Newton iteration ({smp['cg_iterations']} CG its, solverCG "
+                   f"{smp['t_cg']:.3f} s), {smp['steps']} timed; carried to {n_full}^3 as t_cg*(N/Ns)*({CG_ITERS_MEASURED.get(n_full)}/"
+                   f"{smp['cg_iterations']} measured CG iterations) + t_rest*(N/Ns); the --impl reference arm measures 100^3"),
+        "sample_newton_it_per_s": 1.0 / smp["t_step"], "sample_particles": smp["particles"], "sample_cg_iterations": smp["cg_iterations"],
+        "sample_fd_assembly_s": smp["begin_step_s"], "sample_fd_threads": smp["fd_threads"]}}
+    if not with_gpu_dropin:
+        return res
+    g, g_arrays = run_dropin_sample(args, m, args.cpu_steps, device)
+    if g is None or "error" in g:
+        res["parity_at_sample"] = {"ok": False, "error": "drop-in sample did not run: " + str(g)}
+        return res
+    x0 = cpu_arrays["xyz0"]
+    par = {"particles": smp["particles"], "through": "reference host code + liblpmc_dropin.so (strict mode: K_global re-imported per solve)",
+           "cg_iterations_reference": smp["cg_iterations"], "cg_iterations_gpu": g["cg_iterations"],
+           "cg_iterations_equal": smp["cg_iterations"] == g["cg_iterations"],
+           "rel_err_disp": _rel(g_arrays["disp"], cpu_arrays["disp"]), "rel_err_F": _rel(g_arrays["F"], cpu_arrays["F"]),
+           "rel_err_Pin": _rel(g_arrays["Pin"], cpu_arrays["Pin"]),
+           "rel_err_xyz_moved": _rel(g_arrays["xyz"] - x0, cpu_arrays["xyz"] - x0), "tolerance": 1e-9}
+    par["ok"] = bool(par["cg_iterations_equal"] and max(par["rel_err_disp"], par["rel_err_F"], par["rel_err_Pin"]) <= 1e-9)
+    res["parity_at_sample"] = par
+    same = {"particles": smp["particles"], "cpu_it_per_s": 1.0 / smp["t_step"], "cpu_cores": cores,
+            "gpu_it_per_s": 1.0 / g["t_step"], "gpu_through": "liblpmc_dropin.so, host arrays in / out on every call",
+            "gpu_begin_step_s": g["begin_step_s"], "cpu_begin_step_s": smp["begin_step_s"], "cpu_fd_threads": smp["fd_threads"]}
+    g2, _ = run_dropin_sample(args, m, args.cpu_steps, device, device_bc=True)
+    if g2 and "error" not in g2:
+        same["gpu_it_per_s_device_bc"] = 1.0 / g2["t_step"]   # LPMB_DROPIN_DEVICE_BC=1: tangent stays on the device (DoF mask)
+    if args.dropin_s1 > 0:
+        g3, _ = run_dropin_sample(args, args.dropin_s1, 2, device)
+        if g3 and "error" not in g3:
+            same["s1"] = {"particles": g3["particles"], "gpu_it_per_s": 1.0 / g3["t_step"], "cg_iterations_gpu": g3["cg_iterations"],
+                          "gpu_begin_step_s": g3["begin_step_s"], "cpu_it_per_s": "see the --impl reference line (s1_measured)"}
+    res["same_config_sample"] = same
+    return res
 
 
 def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = unmodified sources + open MKL
+    stand-in) on all host threads.  The 216^3 config cannot be set up by the reference at all (32-bit CSR offsets), so:
+      * the K timed `steps` (after W warm-ups) are Newton iteration 0 on the 48^3 sample -- `ms_per_step` is their MEASURED
+        wall time, the same sample the GPU arm's same_config_sample / parity_at_sample use;
+      * S1 = 100^3 is set up with the injected O(N) topology and timed for --ref-s1-steps Newton
+        iterations; `value` carries THAT measurement to 216^3 with the measured CG iteration counts (226 -> 458)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    base = cpu_reference_sample(args, n_full=args.n, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
-    if base["value"] is None:
-        print(json.dumps({"impl": "reference", "unavailable": base["sample"]}), flush=True)
+    from oracle import ref as oref
+    if not oref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}), flush=True)
         return
-    N = args.n ** 3
-    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {args.n}^3 lattice, {N} particles; "
-                                  "Newton iteration 0 of load step 1", "lattice_n": args.n, "particles": N,
-                      "parallelism": f"{base['cores']} host threads (OpenMP)"},
+    cores = args.cpu_threads or usable_cores()
+    n = args.n
+    with _QuietStdout():
+        small = reference_newton_sample(args.cpu_sample_n, args.steps, max(1, args.warmup), cores)
+        s1 = reference_newton_sample(args.ref_s1_n, args.ref_s1_steps, 1, cores) if args.ref_s1_n > 0 else None
+    anchor = s1 or small
+    t_full = extrapolate_to(n, anchor)
+    value = 1.0 / t_full
+    N = n ** 3
+    describe = lambda s: {"particles": s["particles"], "newton_it_per_s": 1.0 / s["t_step"], "s_per_newton_iteration": s["t_step"],
+                          "solverCG_s": s["t_cg"], "cg_iterations": s["cg_iterations"], "steps_timed": s["steps"],
+                          "fd_assembly_s": s["begin_step_s"], "fd_threads": s["fd_threads"], "setup_s": s["setup_s"],
+                          "extrapolated_to_config_it_per_s": 1.0 / extrapolate_to(n, s)}
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": (f"unmodified reference sources + open MKL stand-in (not Intel MKL), {cores} OpenMP threads; measured: SC "
+                       f"{anchor['m']}^3 ({anchor['particles']} particles) {anchor['t_step']:.3f} s per Newton iteration "
+                       f"({anchor['cg_iterations']} CG its, solverCG {anchor['t_cg']:.3f} s); carried to {n}^3 as t_cg*(N/Ns)*"
+                       f"({CG_ITERS_MEASURED.get(n)}/{anchor['cg_iterations']} measured CG iterations) + t_rest*(N/Ns)")}
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1000.0 * small["t_step"],
+           "ms_per_step_is": f"MEASURED wall time of one timed step = Newton iteration 0 on the {args.cpu_sample_n}^3 sample; "
+                             f"`value` is the {n}^3 config (ms_per_step_config below), carried over from the measured {anchor['m']}^3 run",
+           "ms_per_step_config": 1000.0 * t_full,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"C5 physics (J2 plasticity + nonlocal damage) on a synthetic SC {n}^3 lattice, {N} particles; "
+                                  "Newton iteration 0 of load step 1", "lattice_n": n, "particles": N,
+                      "parallelism": f"{cores} host threads (OpenMP)"},
            "cpu_baseline": base,
-           "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "same_config_sample": {"particles": small["particles"], "cpu_it_per_s": 1.0 / small["t_step"], "cpu_cores": cores,
+                                  "gpu_it_per_s": "see the b200 arm's same_config_sample"},
+           "sample_measured": describe(small), "s1_measured": describe(s1) if s1 else None,
+           "cg_iterations_measured": CG_ITERS_MEASURED,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
@@ -425,14 +555,21 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lattice-n", dest="n", type=int, default=int(os.environ.get("LPMB_BENCH_N", 216)), help="lattice points per side")
     ap.add_argument("--cpu-sample-n", type=int, default=48)   # 110 592 particles: ~1 s per reference Newton iteration
-    ap.add_argument("--cpu-steps", type=int, default=10)      # => ~10-15 s of timed CPU work
+    ap.add_argument("--cpu-steps", type=int, default=4)       # FD assembly ~20 s + 5 Newton iterations: ~25-30 s of CPU work
+    ap.add_argument("--ref-s1-n", type=int, default=100, help="--impl reference: lattice size of the measured S1 anchor (0 = skip)")
+    ap.add_argument("--ref-s1-steps", type=int, default=1)
+    ap.add_argument("--dropin-s1", type=int, default=100, help="b200 arm: also run the drop-in sample at this lattice size (0 = skip)")
+    ap.add_argument("--dist-parity-n", type=int, default=40, help="N>1: lattice size of the slabs-vs-single-GPU check run before the timed region (0 = skip)")
+    ap.add_argument("--sample-child", default="", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv", default="bricks", choices=["bricks", "full"],
                     help="CG SpMV kernel: brick-blocked symmetric (default) or the full-format SELL kernel")
     ap.add_argument("--no-brick-trim", action="store_true", help="A/B: stream whole class tiles instead of only the needed z-layers")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sample_child:
+        dropin_sample_child(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)

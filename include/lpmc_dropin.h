@@ -99,6 +99,9 @@ void updateCrack();
  * force evaluation); test generators that poke state between calls use it. */
 void lpmc_dropin_invalidate_state(void);
 
+/* CG iterations of the last solverCG() / solverPARDISO() call (the reference only prints them, solver.c:254) */
+int lpmc_dropin_last_cg_iterations(void);
+
 /* release the device context (optional; the process exit does it too) */
 void lpmc_dropin_shutdown(void);
 

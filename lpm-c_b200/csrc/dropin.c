@@ -381,6 +381,10 @@ void calcStiffness2DFiniteDifference(int mode) { fd_stiffness(mode); }
 void calcStiffness3DFiniteDifference(int mode) { fd_stiffness(mode); }
 
 /* ---------------------------------------------------------------------------------------- solver.h */
+static int g_last_cg_iterations = 0;
+/* CG iterations of the last solverCG() / solverPARDISO() (the reference only printf()s them, solver.c:254) */
+int lpmc_dropin_last_cg_iterations(void) { return g_last_cg_iterations; }
+
 static void solve(double rel, double abs_tol, const char *who, int direct)
 {
     ensure_state();
@@ -393,6 +397,7 @@ static void solve(double rel, double abs_tol, const char *who, int direct)
         CK(lpmb_matrix_from_upper_csr(g_ctx, K_global, (long long)K_pointer[N][1]));
         rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 0, &iters);
     }
+    g_last_cg_iterations = iters;
     if (rc == LPMB_OK)
         printf("The system has been solved after %d iterations\n", iters); /* solver.c:254 */
     else if (rc == LPMB_ERR_NOTCONVERGED && direct) {

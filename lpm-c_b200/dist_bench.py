@@ -11,11 +11,85 @@ import json
 import numpy as np
 
 
+PARITY_KEYS = ("xyz", "F", "Pin", "stress_tensor", "dLp0", "damage_nonlocal0", "damage_w", "damage_broken")
+
+
+def _parity_steps(c):
+    """two consecutive Newton iterations (state really evolves), then the nonlocal damage update, updateCrack and the commit"""
+    its, nrs = [], []
+    for _ in range(2):
+        it, nr = c.newton_iteration(0, 1)
+        its.append(int(it))
+        nrs.append(float(nr))
+    broken, _ = c.update_damage(0)
+    c.update_crack()
+    c.switch_state(1)
+    return its, nrs, int(broken)
+
+
+def dist_parity(args, lpm, dist, rank, world, local, bench, n):
+    """Before the timed region: the slab-decomposed path (this world size, the comm mode and SpMV kernel of the timed run)
+    against ONE GPU running the full-format kernel on the same n^3 block of the bench workload -- CG iteration counts and
+    broken-bond counts equal, residual norms and xyz / F / Pin / stress / plastic stretch / damage fields of every owned
+    particle within 1e-9 (tests/dist_check_lite.py, made driver-visible).  Returns the report (rank 0) and ok (all ranks)."""
+    import numpy as np
+    import torch
+    from . import partition
+    slab = partition.make_slab(n, n * n, rank, world)
+    uid = [lpm.Context.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c, info = bench.build_workload(lpm, n, local, slab=slab, unique_id=uid[0], bricks=args.spmv == "bricks",
+                                    brick_trim=not getattr(args, "no_brick_trim", False))
+    its, nrs, broken = _parity_steps(c)
+    own = slice(slab.own0, slab.own1)
+    mine = {k: np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own]) for k in PARITY_KEYS}
+    mine["_meta"] = (its, nrs, broken, int(c.dist_mode()), float(info["norm_residual0"]))
+    c.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    report = None
+    if rank == 0:
+        c1, info1 = bench.build_workload(lpm, n, local, bricks=False)
+        its1, nrs1, broken1 = _parity_steps(c1)
+        x0 = c1.get_field("xyz_initial")
+        errs = {}
+        for k in PARITY_KEYS:
+            a = np.concatenate([q[k] for q in parts])
+            b = c1.get_field(k).reshape(n ** 3, -1)
+            if k == "xyz":
+                a, b = a - x0, b - x0
+            errs[k] = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+        c1.close()
+        same_meta = all(q["_meta"][0] == its and q["_meta"][2] == broken for q in parts)
+        ok = (same_meta and its == its1 and broken == broken1 and max(errs.values()) <= 1e-9
+              and all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(nrs, nrs1))
+              and abs(info["norm_residual0"] - info1["norm_residual0"]) <= 1e-12 * info1["norm_residual0"])
+        report = {"ok": bool(ok), "lattice_n": n, "particles": n ** 3, "world": world, "comm_mode": [q["_meta"][3] for q in parts],
+                  "cg_iterations_slabs": its, "cg_iterations_single_gpu": its1, "cg_iterations_equal": its == its1,
+                  "broken_bonds_slabs": broken, "broken_bonds_single_gpu": broken1,
+                  "rel_err": errs, "rel_err_residual_norms": [abs(a - b) / abs(b) for a, b in zip(nrs, nrs1)], "tolerance": 1e-9,
+                  "checked": "2 Newton iterations + update_damage(0) + update_crack + switch_state(1); slabs on the timed run's SpMV kernel "
+                             "and comm mode vs one GPU on the full-format kernel"}
+    flag = torch.tensor([1 if (report and report["ok"]) else 0], device=f"cuda:{local}")
+    dist.broadcast(flag, src=0)
+    return report, bool(flag.item())
+
+
 def run(args, lpm, dist, rank, world, local, bench):
     import torch
     from . import partition
 
     n = args.n
+    parity_report, parity_ok = (None, True)
+    if getattr(args, "dist_parity_n", 0) > 0:
+        parity_report, parity_ok = dist_parity(args, lpm, dist, rank, world, local, bench, args.dist_parity_n)
+        if not parity_ok:
+            if rank == 0:
+                print(json.dumps({"metric": bench.METRIC, "value": None, "n_gpus": world, "dist_parity": parity_report,
+                                  "error": "slab-decomposed path does not reproduce the single-GPU path; no timing reported"}), flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            raise SystemExit(3)
     slab = partition.make_slab(n, n * n, rank, world)
     # rank 0 creates the NCCL id; torch.distributed ships it
     uid = [lpm.Context.dist_unique_id() if rank == 0 else None]
@@ -79,16 +153,15 @@ def run(args, lpm, dist, rank, world, local, bench):
     h_bc[:] = c.get_field("dispBC_index")
     h_fix[:] = c.get_field("fix_index")
 
-    def e2e_step():
-        c.set_field("xyz", h_xyz)
-        c.set_field("residual", h_res)
-        c.set_field("dispBC_index", h_bc)
-        c.set_field("fix_index", h_fix)
+    import importlib
+    capi = importlib.import_module("lpm-c_b200.capi")
+
+    def e2e_step():   # straight between the pinned buffers and the device, exactly like the single-GPU arm (bench.py)
+        for nm, a in (("xyz", h_xyz), ("residual", h_res), ("dispBC_index", h_bc), ("fix_index", h_fix)):
+            capi._check(capi.lib.lpmb_field_set(c._h, nm.encode(), a.ctypes.data, a.size))
         r = c.newton_iteration(0, 1)
-        o_xyz[:] = c.get_field("xyz")
-        o_disp[:] = c.get_field("disp")
-        o_pin[:] = c.get_field("Pin")
-        o_res[:] = c.get_field("residual")
+        for nm, a in (("xyz", o_xyz), ("disp", o_disp), ("Pin", o_pin), ("residual", o_res)):
+            capi._check(capi.lib.lpmb_field_get(c._h, nm.encode(), a.ctypes.data, a.size))
         return r
 
     import time
@@ -135,6 +208,7 @@ def run(args, lpm, dist, rank, world, local, bench):
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps},
             "gpu_launches": int(sum(d["launches"] for d in per_rank)),
             "clocks": clocks,
+            "dist_parity": parity_report,
         }
         print(json.dumps(out), flush=True)
     c.close()

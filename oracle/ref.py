@@ -282,13 +282,109 @@ class RefLPM:
         L.initMatrices()
         N = self.N
         self.set_d2("xyz_initial", self.d2("xyz", N, 3))
-        if neighbor_search:
+        if neighbor_search == "lattice":
+            self.inject_sc_topology()   # O(N), bit-identical to the two O(N^2) calls below (tests/test_oracle_ref.py)
+        elif neighbor_search:
             L.searchNormalNeighbor()
             L.searchAFEMNeighbor()
         else:
             return  # caller fills the topology globals, then calls finish_setup_sc()
         self._finish_sc(E0, mu0, plmode, sigmay, J2_xi, J2_H, nbreak, critical_bstrain, damageb_A, damagec_A,
                         damage_threshold, damage_L, dtime, top_z)
+
+    def inject_sc_topology(self):
+        """What searchNormalNeighbor() + searchAFEMNeighbor() (neighbor.c:9-141) leave in the reference's globals, computed
+        in O(N) with numpy for a FULL simple-cubic block (createCuboid, lattice 2, no carving) and written into the arrays
+        initMatrices() allocated; K_global / IK / JK are allocated with the reference's own allocators (neighbor.c:132-134).
+        The reference's O(N^2) search needs ~18 min at 10^6 particles; this makes S1 = 100^3 reachable for the CPU arm of
+        bench.py.  Lists are in ascending-j order with the shells interleaved (neighbor.c:29,40), distances and unit
+        vectors use the same expressions (sqrt(dx^2+dy^2+dz^2), (x_i - x_j)/dis), conn = sorted unique union (:56-112)."""
+        L = self.lib
+        N, nn = self.N, self.nn
+        assert self.gi("lattice") == 2 and self.gi("dim") == 3 and nn == 18
+        xyz = self.d2("xyz", N, 3)
+        h = 2.0 * self.gd("radius")
+        ijk = np.rint((xyz - xyz.min(axis=0)) / h).astype(np.int64)
+        nx, ny, nz = (int(v) + 1 for v in ijk.max(axis=0))
+        assert nx * ny * nz == N, "inject_sc_topology: not a full simple-cubic block"
+        grid = np.full((nx + 4, ny + 4, nz + 4), -1, dtype=np.int64)      # 2-cell apron of -1 around the block
+        grid[ijk[:, 0] + 2, ijk[:, 1] + 2, ijk[:, 2] + 2] = np.arange(N)
+        assert np.abs(xyz - (xyz.min(axis=0) + h * ijk)).max() < 1e-6 * h
+        o1 = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+        o2 = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1) if abs(a) + abs(b) + abs(c) == 2]
+        look = lambda o: grid[ijk[:, 0] + 2 + o[0], ijk[:, 1] + 2 + o[1], ijk[:, 2] + 2 + o[2]]
+        big = np.iinfo(np.int64).max
+        cand = np.stack([look(o) for o in o1 + o2], axis=1)
+        shell = np.array([0] * 6 + [1] * 12, dtype=np.int32)
+        key = np.where(cand >= 0, cand, big)
+        order = np.argsort(key, axis=1, kind="stable")
+        nbr = np.take_along_axis(cand, order, axis=1)
+        sgn = np.where(nbr >= 0, shell[order], 0).astype(np.int32)        # unused slots: initMatrices' fill value of nsign is kept below
+        cnt = (nbr >= 0).sum(axis=1).astype(np.int32)
+        # distances / unit vectors with the reference's expressions (neighbor.c:18,23-26)
+        j = np.where(nbr >= 0, nbr, 0)
+        d = xyz[j] - xyz[:, None, :]
+        dis = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2])
+        c1, c2 = 1.01 * self.gd("neighbor1_cutoff"), 1.01 * self.gd("neighbor2_cutoff")
+        valid = nbr >= 0
+        assert np.all((dis[valid & (sgn == 0)] < c1)) and np.all((dis[valid & (sgn == 1)] > c1) & (dis[valid & (sgn == 1)] < c2))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cs = (xyz[:, None, :] - xyz[j]) / dis[..., None]
+        old = {n: self.d2(n, N, nn) for n in ("csx_initial", "csy_initial", "csz_initial", "distance_initial")}
+        old_sgn, old_nbr = self.i2("nsign", N, nn), self.i2("neighbors", N, nn)
+        for k, n in enumerate(("csx_initial", "csy_initial", "csz_initial")):
+            self.set_d2(n, np.where(valid, cs[..., k], old[n]))
+        self.set_d2("distance_initial", np.where(valid, dis, old["distance_initial"]))
+        self.set_i2("nsign", np.where(valid, sgn, old_sgn))
+        self.set_i2("neighbors", np.where(valid, nbr, old_nbr).astype(np.int32))
+        for name, sh, width in (("neighbors1", 0, self.gi("nneighbors1")), ("neighbors2", 1, self.gi("nneighbors2"))):
+            sel = valid & (sgn == sh)
+            k2 = np.where(sel, nbr, big)
+            part = np.sort(k2, axis=1)[:, :width]
+            prev = self.i2(name, N, width)
+            self.set_i2(name, np.where(part != big, part, prev).astype(np.int32))
+        self.set_i1("nb", cnt)
+        self.set_i1("nb_initial", cnt)
+        del cand, key, order, d, dis, cs, old
+        # conn: direct neighbours, 1st-of-1st, 2nd-of-2nd (reached through an EXISTING intermediate), self included
+        nA = self.gi("nneighbors_AFEM") + 1
+        offs = {}
+        for group in (o1, o2):
+            for a in group:
+                for b in group:
+                    offs.setdefault((a[0] + b[0], a[1] + b[1], a[2] + b[2]), []).append(a)
+        cols = []
+        for o, vias in sorted(offs.items()):
+            tgt = look(o) if max(abs(v) for v in o) <= 2 else None
+            ok = np.zeros(N, dtype=bool)
+            for a in vias:
+                ok |= look(a) >= 0
+            cols.append(np.where(ok, tgt, -1))
+        for o in o1 + o2:
+            if o not in offs:
+                cols.append(look(o))
+        cm = np.stack(cols, axis=1)
+        cm = np.sort(np.where(cm >= 0, cm, big), axis=1)
+        assert cm.shape[1] <= nA or np.all(cm[:, nA:] == big)
+        cm = cm[:, :nA]
+        nbc = (cm != big).sum(axis=1).astype(np.int32)
+        prev = self.i2("conn", N, nA)
+        self.set_i2("conn", np.where(cm != big, cm, prev).astype(np.int32))
+        self.set_i1("nb_conn", nbc)
+        k0 = ((cm != big) & (cm >= np.arange(N)[:, None])).sum(axis=1).astype(np.int64)
+        kp = np.zeros((N + 1, 2), dtype=np.int64)
+        kp[:N, 0] = k0
+        kp[1:, 1] = np.cumsum(9 * k0 - 3)
+        assert kp[N, 1] < 2 ** 31, "nnz_upper exceeds the reference's 32-bit K_pointer"
+        prevkp = self.i2("K_pointer", N + 1, 2)
+        kp[N, 0] = prevkp[N, 0]
+        self.set_i2("K_pointer", kp.astype(np.int32))
+        nnz = int(kp[N, 1])
+        L.allocInt1D.restype, L.allocDouble1D.restype = c_ip, c_dp
+        self.set_ptr("JK", L.allocInt1D(nnz, -1))
+        self.set_ptr("IK", L.allocInt1D(3 * N + 1, -1))
+        self.set_ptr("K_global", L.allocDouble1D(nnz, -1.0))
+        return nnz
 
     def setup_ct_geometry(self):
         """Geometry and topology of examples/CT_sc_ductile_nonlocal.c (:60-160; BASELINE config 5 as shipped): simple-cubic

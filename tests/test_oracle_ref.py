@@ -376,3 +376,23 @@ def test_reference_rounding_noise_floor(tmp_path):
     assert rel("x1") < 1e-12 and rel("F1") < 1e-10 and rel("F2") < 1e-9
     assert rel("x3") < 1e-9
     assert 1e-9 < rel("F3") < 1e-7          # the reference's own bond forces are not reproducible to 1e-9 here
+
+
+@pytest.mark.parametrize("box", [(-0.2, 10.2, -0.2, 10.2, -0.2, 10.2), (-0.2, 3.2, -0.2, 5.7, -0.2, 2.2)])
+def test_injected_lattice_topology_equals_the_reference_search(ref, box):
+    """oracle/ref.py::inject_sc_topology (O(N) lattice stencils in numpy; what lets bench.py's reference arm reach S1 = 100^3)
+    leaves exactly what searchNormalNeighbor() + searchAFEMNeighbor() (neighbor.c:9-141, O(N^2)) leave in the reference's
+    globals: neighbour lists in ascending-j order with interleaved shells, shell signs, counts, initial distances and unit
+    vectors bit for bit, conn / nb_conn / K_pointer and the CSR size -- on the default 21^3 block and a ragged 7 x 12 x 5 one"""
+    r = ref
+    names = ["neighbors", "nsign", "nb", "nb_initial", "conn", "nb_conn", "K_pointer", "distance_initial", "csx_initial", "csy_initial",
+             "csz_initial"]
+    r.setup_sc(box=box)
+    a = {n: r.get(n) for n in names}
+    a["neighbors1"], a["neighbors2"] = r.i2("neighbors1", r.N, 6), r.i2("neighbors2", r.N, 12)
+    r.setup_sc(box=box, neighbor_search="lattice")
+    b = {n: r.get(n) for n in names}
+    b["neighbors1"], b["neighbors2"] = r.i2("neighbors1", r.N, 6), r.i2("neighbors2", r.N, 12)
+    for n in a:
+        assert np.array_equal(a[n], b[n]), n
+    assert int(b["K_pointer"][r.N, 1]) == int(a["K_pointer"][r.N, 1]) > 0
