@@ -3,7 +3,16 @@
  * plain C over the C ABI only: one process per GPU, each holding a z-slab of the lattice (contiguous particle index
  * range + 4 ghost layers towards each neighbour), exactly the decomposition bench.py uses (lpm-c_b200/partition.py).
  *
- *   sc_block_mgpu <world> [n=48] [steps=1]
+ *   sc_block_mgpu <world> [n=48] [steps=1] [physics=c1|c5] [strain_step=0.005]
+ *
+ * physics c1 (default): the default driver's problem (src/lpmc_project.c: E = 146e3, nu = 0.3, sigma_y = 200, force-controlled
+ * -2000 per step on the bottom layer).  physics c5: BASELINE config 5 -- the material and damage law of
+ * examples/CT_sc_ductile_nonlocal.c (:171,195-202,230-235: E = 115e3, nu = 0.28, sigma_y = 955, H = 2401.8, damagec_A = 400,
+ * damage_L = 0.6, threshold 0.85) on the synthetic block, displacement-controlled like that example: bottom z-layer held,
+ * top z-layer moved by strain_step * height every load step (yield strain 0.83 %: plastic from step 2 at the default
+ * 0.5 %); every load step runs the reference's loop body (lpmc_project.c:382-546): FD tangent, BCs, predictor, Newton
+ * iterations, updateDamageGeneral (nonlocal Gaussian gather over 3 * damage_L, constitutive.c:1757-1862, with its halo
+ * exchange), updateCrack, switchStateV(1), re-assembly while bonds break.  The time of the damage update is printed.
  *
  * The parent starts `world` copies of itself (fork + exec, so no process inherits an initialised CUDA runtime); rank 0
  * creates the 128-byte NCCL id with lpmb_dist_unique_id and hands it to the others through a file in a private temporary
@@ -12,8 +21,8 @@
  * damage fields happen inside the same entry points once lpmb_dist_init + lpmb_dist_set_slab have been called.
  * Requirements: every rank owns at least 4 lattice layers (n >= 4 * world).  Exit code 0 = all ranks finished.
  *
- * NOT RUN YET on a multi-GPU box (written after round 1's GPU budget was spent); tests/test_dist_gpu.py runs it when two
- * devices are visible and compares the iteration counts with the single-GPU known answers.
+ * tests/test_dist_gpu.py runs it when two devices are visible and compares the iteration counts with the single-GPU
+ * known answers.
  */
 #define _GNU_SOURCE
 #include <math.h>
@@ -70,7 +79,7 @@ static void ghosts(int nz, int r, int world, int *lo, int *hi)
     *hi = r < world - 1 ? imin(GHOST, nz - b) : 0;
 }
 
-static int run_rank(int rank, int world, int n, int steps, const char *dir)
+static int run_rank(int rank, int world, int n, int steps, const char *dir, int c5, double strain_step)
 {
     g_rank = rank;
     if (lpmb_device_count() < world) {
@@ -120,8 +129,8 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir)
     const long long N = (z1 - z0 + g_lo + g_hi) * L, first = (long long)(z0 - g_lo) * L;
     const int own0 = (int)(g_lo * L), own1 = (int)((g_lo + z1 - z0) * L);
 
-    const double radius = 0.2499999944120646, h = 2.0 * radius;
-    const double E0 = 146e3, mu0 = 0.3, sigmay0 = 200.0, J2_H = 38.714e3, J2_xi = 0.0;
+    const double radius = c5 ? 0.25 : 0.2499999944120646, h = 2.0 * radius;
+    const double E0 = c5 ? 115e3 : 146e3, mu0 = c5 ? 0.28 : 0.3, sigmay0 = c5 ? 955.0 : 200.0, J2_H = c5 ? 2401.8 : 38.714e3, J2_xi = 0.0;
     const double C11 = E0 * (1.0 - mu0) / (1.0 + mu0) / (1.0 - 2.0 * mu0), C12 = E0 * mu0 / (1.0 + mu0) / (1.0 - 2.0 * mu0),
                  C44 = E0 / 2.0 / (1.0 + mu0);
     const int nn = 18, nconn = 61, dim = 3, plmode = 0, ntype = 4;
@@ -136,9 +145,9 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir)
     CK(lpmb_set_param(ctx, "particle_volume", pow(2.0 * radius, 3)));
     CK(lpmb_set_param(ctx, "J2_H", J2_H));
     CK(lpmb_set_param(ctx, "J2_xi", J2_xi));
-    CK(lpmb_set_param(ctx, "damage_L", 0.5));
-    CK(lpmb_set_param(ctx, "damage_threshold", 0.9));
-    CK(lpmb_set_param(ctx, "damagec_A", 0.0));
+    CK(lpmb_set_param(ctx, "damage_L", c5 ? 0.6 : 0.5));
+    CK(lpmb_set_param(ctx, "damage_threshold", c5 ? 0.85 : 0.9));
+    CK(lpmb_set_param(ctx, "damagec_A", c5 ? 400.0 : 0.0));
     double *xyz = (double *)malloc(sizeof(double) * 3 * N);
     int *type = (int *)malloc(sizeof(int) * N);
     double *sig = (double *)malloc(sizeof(double) * N);
@@ -167,8 +176,8 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir)
         fprintf(stderr, "sc_block_mgpu[rank %d]: brick SpMV not used (%s)\n", rank, lpmb_last_error());
     CK(lpmb_synchronize(ctx));
     if (rank == 0)
-        printf("%d ranks, lattice %d^3 = %lld particles, %d..%d owned layers per rank, communication mode %d, set-up %.2f s\n", world, n,
-               (long long)n * n * n, n / world, (n + world - 1) / world, lpmb_dist_mode(ctx), now() - t0);
+        printf("%d ranks, lattice %d^3 = %lld particles, %d..%d owned layers per rank, communication mode %d, physics %s, set-up %.2f s\n", world,
+               n, (long long)n * n * n, n / world, (n + world - 1) / world, lpmb_dist_mode(ctx), c5 ? "c5" : "c1", now() - t0);
 
     for (int step = 1; step <= steps; step++) {
         const double ts = now();
@@ -176,9 +185,17 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir)
         CK(lpmb_field_copy(ctx, "F_temp", "F"));
         CK(lpmb_field_copy(ctx, "Pex_temp", "Pex"));
         int newton = 0, ncg = 0, broken_total = 0, cg[MAXITER];
+        double t_fd = 0, t_dam = 0, tq = now();
         CK(lpmb_fd_stiffness(ctx, 1));
-        CK(lpmb_apply_disp_bc(ctx, 1, 'z', 0.0));
-        CK(lpmb_apply_force_bc(ctx, 2, 0.0, 0.0, -2000.0));      /* shared by the loaded layer of the WHOLE lattice */
+        CK(lpmb_synchronize(ctx));
+        t_fd += now() - tq;
+        if (c5) {   /* displacement control (CT_sc_ductile_nonlocal.c:263-275): type 2 = bottom layer held, type 1 = top layer moved */
+            CK(lpmb_apply_disp_bc(ctx, 2, 'z', 0.0));
+            CK(lpmb_apply_disp_bc(ctx, 1, 'z', strain_step * h * (n - 1)));
+        } else {
+            CK(lpmb_apply_disp_bc(ctx, 1, 'z', 0.0));
+            CK(lpmb_apply_force_bc(ctx, 2, 0.0, 0.0, -2000.0));  /* shared by the loaded layer of the WHOLE lattice */
+        }
         CK(lpmb_bond_force(ctx, 4, 1));
         for (;;) {
             double nr = 0, nf = 0;
@@ -194,22 +211,46 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir)
             }
             newton += ni;
             int broken = 0;
+            CK(lpmb_synchronize(ctx));
+            tq = now();
             CK(lpmb_update_damage(ctx, plmode, &broken, NULL, 0));   /* global count */
+            CK(lpmb_synchronize(ctx));
+            t_dam += now() - tq;
             CK(lpmb_update_crack(ctx));
             CK(lpmb_switch_state(ctx, 1));
             broken_total += broken;
             if (broken <= 0)
                 break;
+            tq = now();
             CK(lpmb_fd_stiffness(ctx, 1));
+            CK(lpmb_synchronize(ctx));
+            t_fd += now() - tq;
         }
         CK(lpmb_synchronize(ctx));
         if (rank == 0) {
             printf("Loading step %d has finished in %d iterations; CG iterations:", step, newton);
             for (int k = 0; k < ncg; k++)
                 printf(" %d", cg[k]);
-            printf("; broken bonds %d; %.3f s\n", broken_total, now() - ts);
+            printf("; broken bonds %d; %.3f s (FD assembly %.3f s, damage update %.3f s)\n", broken_total, now() - ts, t_fd, t_dam);
             fflush(stdout);
         }
+    }
+    if (c5) {   /* how far the damage law got: maximum of damage_nonlocal (slot 0) over this rank's owned particles */
+        double *dn = (double *)malloc(sizeof(double) * N), *al = (double *)malloc(sizeof(double) * N);
+        CK(lpmb_field_get(ctx, "damage_nonlocal0", dn, N));
+        CK(lpmb_field_get(ctx, "J2_alpha0", al, N));
+        double dmax = 0, amax = 0;
+        long long nyield = 0;
+        for (long long k = own0; k < own1; k++) {
+            dmax = dn[k] > dmax ? dn[k] : dmax;
+            amax = al[k] > amax ? al[k] : amax;
+            nyield += al[k] > 0.0;
+        }
+        printf("rank %d: yielded particles %lld of %d owned, max equivalent plastic strain %.4e, max nonlocal damage %.4e\n", rank, nyield,
+               own1 - own0, amax, dmax);
+        fflush(stdout);
+        free(dn);
+        free(al);
     }
     /* the rank that owns the loaded (bottom) layer reports its mean z-displacement */
     if (rank == 0) {
@@ -235,13 +276,15 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir)
 
 int main(int argc, char **argv)
 {
-    if (argc >= 7 && strcmp(argv[1], "--rank") == 0)   /* child: --rank r world n steps dir */
-        return run_rank(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6]);
+    if (argc >= 9 && strcmp(argv[1], "--rank") == 0)   /* child: --rank r world n steps dir c5 strain_step */
+        return run_rank(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6], atoi(argv[7]), atof(argv[8]));
     const int world = argc > 1 ? atoi(argv[1]) : 0;
     const int n = argc > 2 ? atoi(argv[2]) : 48;
     const int steps = argc > 3 ? atoi(argv[3]) : 1;
-    if (world < 1 || world > 16 || steps < 1 || n < 4 * world) {
-        fprintf(stderr, "usage: sc_block_mgpu <world 1..16> [n >= 4*world] [steps >= 1]\n");
+    const int c5 = argc > 4 && strcmp(argv[4], "c5") == 0;
+    const double strain_step = argc > 5 ? atof(argv[5]) : 0.005;
+    if (world < 1 || world > 16 || steps < 1 || n < 4 * world || (argc > 4 && !c5 && strcmp(argv[4], "c1") != 0)) {
+        fprintf(stderr, "usage: sc_block_mgpu <world 1..16> [n >= 4*world] [steps >= 1] [c1|c5] [strain_step]\n");
         return 2;
     }
     char dir[] = "/tmp/lpmb_mgpu_XXXXXX";
@@ -250,7 +293,9 @@ int main(int argc, char **argv)
         return 1;
     }
     pid_t pid[16];
-    char a_rank[16], a_world[16], a_n[16], a_steps[16];
+    char a_rank[16], a_world[16], a_n[16], a_steps[16], a_c5[4], a_strain[40];
+    snprintf(a_c5, sizeof a_c5, "%d", c5);
+    snprintf(a_strain, sizeof a_strain, "%.17g", strain_step);
     snprintf(a_world, sizeof a_world, "%d", world);
     snprintf(a_n, sizeof a_n, "%d", n);
     snprintf(a_steps, sizeof a_steps, "%d", steps);
@@ -262,7 +307,7 @@ int main(int argc, char **argv)
         }
         if (pid[r] == 0) {
             snprintf(a_rank, sizeof a_rank, "%d", r);
-            char *args[] = {argv[0], "--rank", a_rank, a_world, a_n, a_steps, dir, NULL};
+            char *args[] = {argv[0], "--rank", a_rank, a_world, a_n, a_steps, dir, a_c5, a_strain, NULL};
             execv("/proc/self/exe", args);
             perror("execv");
             _exit(127);

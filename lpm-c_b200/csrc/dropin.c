@@ -57,6 +57,55 @@ static int g_cp_ready = 0;
         }                                                                                      \
     } while (0)
 
+/* LPMB_DROPIN_PROFILE=1: wall time per reference-named entry point, printed on stderr at exit */
+#include <time.h>
+enum { P_KNTV, P_RR, P_FD, P_FD_DOWN, P_SOLVE_IMPORT, P_SOLVE_CG, P_SOLVE_XYZ, P_SWITCH, P_BF_UP, P_BF, P_BF_DOWN, P_DAMAGE, P_CRACK, P_STATE, P_COUNT };
+static const char *g_prof_name[P_COUNT] = {"calcKnTv", "updateRR", "calcStiffness: assembly + K_global export", "calcStiffness: side-effect downloads",
+                                           "solverCG: K_global import", "solverCG: CG", "solverCG: disp download + xyz update", "switchStateV",
+                                           "computeBondForceGeneral: uploads", "computeBondForceGeneral: kernels",
+                                           "computeBondForceGeneral: downloads", "updateDamage*", "updateCrack", "first state upload"};
+static double g_prof_s[P_COUNT];
+static long g_prof_n[P_COUNT];
+static int g_prof_on = -1;
+static double prof_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static void prof_report(void)
+{
+    double tot = 0;
+    for (int k = 0; k < P_COUNT; k++)
+        tot += g_prof_s[k];
+    fprintf(stderr, "lpmc_dropin profile (wall seconds inside the drop-in entry points, total %.3f):\n", tot);
+    for (int k = 0; k < P_COUNT; k++)
+        if (g_prof_n[k])
+            fprintf(stderr, "  %-48s %8ld calls %9.3f s %7.3f ms/call\n", g_prof_name[k], g_prof_n[k], g_prof_s[k], 1e3 * g_prof_s[k] / g_prof_n[k]);
+}
+static double prof_begin(void)
+{
+    if (g_prof_on < 0) {
+        const char *e = getenv("LPMB_DROPIN_PROFILE");
+        g_prof_on = e && atoi(e) != 0;
+        if (g_prof_on)
+            atexit(prof_report);
+    }
+    return g_prof_on ? prof_now() : 0.0;
+}
+/* closes the interval opened at *t0 under `id` and opens the next one */
+static void prof_lap(int id, double *t0)
+{
+    if (g_prof_on > 0) {
+        if (g_ctx)
+            lpmb_synchronize(g_ctx);
+        const double t = prof_now();
+        g_prof_s[id] += t - *t0;
+        g_prof_n[id]++;
+        *t0 = t;
+    }
+}
+
 static void *buf(size_t bytes)
 {
     if (bytes > g_buf_bytes) {
@@ -262,6 +311,7 @@ static void ensure_state(void)
     if (g_state_uploaded)
         return;
     g_state_uploaded = 1;
+    double pt = prof_begin();
     const int N = nparticle, nn = nneighbors;
     UP1D("nb", nb, N);
     UP1D("type", type, N);
@@ -304,6 +354,7 @@ static void ensure_state(void)
         up_d2("Kn", Kn, N, nn);
         up_d2("Tv", Tv, N, nn);
     }
+    prof_lap(P_STATE, &pt);
 }
 
 static void down_slots(int s)
@@ -342,6 +393,7 @@ void calcKnTv()
 void updateRR()
 {
     ensure_state();
+    double pt = prof_begin();
     const int N = nparticle;
     UP1D("dispBC_index", dispBC_index, (size_t)dim * N);
     UP1D("Pex", Pex, (size_t)dim * N);
@@ -353,6 +405,7 @@ void updateRR()
         for (int k = 0; k < dim; k++)
             if (dispBC_index[dim * i + k] == 0)
                 reaction_force[ii++] = Pin[NDIM * i + k];
+    prof_lap(P_RR, &pt);
 }
 
 static void fd_stiffness(int mode)
@@ -362,11 +415,13 @@ static void fd_stiffness(int mode)
         exit(1);
     }
     ensure_state();
+    double pt = prof_begin();
     const int N = nparticle, nn = nneighbors;
     set_params();
     up_d2("xyz", xyz, N, 3);
     CK(lpmb_fd_stiffness(g_ctx, 1));
     CK(lpmb_matrix_to_upper_csr(g_ctx, K_global, IK, JK));
+    prof_lap(P_FD, &pt);
     /* what the reference's assembly leaves behind */
     down_d2("dL", dL, N, nn);
     down_d2("csx", csx, N, nn);
@@ -376,6 +431,7 @@ static void fd_stiffness(int mode)
     down_d2("TdL_total", TdL_total, N, 2);
     down_d2("F", F, N, nn);
     DOWN1D("Pin", Pin, (size_t)NDIM * N);
+    prof_lap(P_FD_DOWN, &pt);
 }
 void calcStiffness2DFiniteDifference(int mode) { fd_stiffness(mode); }
 void calcStiffness3DFiniteDifference(int mode) { fd_stiffness(mode); }
@@ -388,15 +444,19 @@ int lpmc_dropin_last_cg_iterations(void) { return g_last_cg_iterations; }
 static void solve(double rel, double abs_tol, const char *who, int direct)
 {
     ensure_state();
+    double pt = prof_begin();
     const int N = nparticle, n = dim * nparticle;
     int iters = 0, rc;
     if (g_device_bc) {
         CK(lpmb_set_dof_mask(g_ctx, dispBC_index, fix_index));
+        prof_lap(P_SOLVE_IMPORT, &pt);
         rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 1, &iters);
     } else {
         CK(lpmb_matrix_from_upper_csr(g_ctx, K_global, (long long)K_pointer[N][1]));
+        prof_lap(P_SOLVE_IMPORT, &pt);
         rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 0, &iters);
     }
+    prof_lap(P_SOLVE_CG, &pt);
     g_last_cg_iterations = iters;
     if (rc == LPMB_OK)
         printf("The system has been solved after %d iterations\n", iters); /* solver.c:254 */
@@ -413,6 +473,7 @@ static void solve(double rel, double abs_tol, const char *who, int direct)
     for (int i = 0; i < N; i++) /* solver.c:263-267 */
         for (int j = 0; j < dim; j++)
             xyz[i][j] += disp[dim * i + j];
+    prof_lap(P_SOLVE_XYZ, &pt);
 }
 void solverCG() { solve(1e-8, 1e-12, "solverCG", 0); }
 void solverPARDISO()
@@ -433,6 +494,7 @@ void switchStateV(int conv_flag)
 {
     ensure_state();
     ensure_cp();
+    double pt = prof_begin();
     CK(lpmb_switch_state(g_ctx, conv_flag));
     const int N = nparticle, nn = nneighbors;
     const int dst = conv_flag == 1 ? 1 : 0;
@@ -444,11 +506,13 @@ void switchStateV(int conv_flag)
         down_pslot("damage_local", damage_local, N, dst);
         down_pslot("damage_nonlocal", damage_nonlocal, N, dst);
     }
+    prof_lap(P_SWITCH, &pt);
 }
 
 void computeBondForceGeneral(int mode, int temp)
 {
     ensure_state();
+    double pt = prof_begin();
     const int N = nparticle, nn = nneighbors;
     up_host_owned();
     if (mode == 4) {
@@ -457,7 +521,9 @@ void computeBondForceGeneral(int mode, int temp)
     }
     if (mode == 1)
         ensure_cp();
+    prof_lap(P_BF_UP, &pt);
     CK(lpmb_bond_force(g_ctx, mode, temp));
+    prof_lap(P_BF, &pt);
     down_d2("F", F, N, nn);
     DOWN1D("Pin", Pin, (size_t)NDIM * N);
     down_d2("stress_tensor", stress_tensor, N, 2 * NDIM);
@@ -512,11 +578,13 @@ void computeBondForceGeneral(int mode, int temp)
     }
     down_slots(0); /* switchStateV(2) ran inside (constitutive.c:145) */
     down_cp_slots(0);
+    prof_lap(P_BF_DOWN, &pt);
 }
 
 static int damage(const char *dataName, int tstep, int mode)
 {
     ensure_state();
+    double pt = prof_begin();
     set_params();
     const int N = nparticle, nn = nneighbors;
     int broken = 0;
@@ -552,6 +620,7 @@ static int damage(const char *dataName, int tstep, int mode)
             DOWN1D("nb", nb, N);
     }
     free(pairs);
+    prof_lap(P_DAMAGE, &pt);
     return broken;
 }
 int updateDamageGeneral(const char *dataName, int tstep, int mode) { return damage(dataName, tstep, mode); }
@@ -568,6 +637,7 @@ int updateBrittleDamage(const char *dataName, int tstep, int nbreak_arg)
 void updateCrack()
 {
     ensure_state();
+    double pt = prof_begin();
     const int N = nparticle, nn = nneighbors;
     UP1D("fix_index", fix_index, (size_t)dim * N);
     CK(lpmb_update_crack(g_ctx));
@@ -576,6 +646,7 @@ void updateCrack()
     DOWN1D("Pin", Pin, (size_t)NDIM * N);
     DOWN1D("damage_visual", damage_visual, N);
     DOWN1D("fix_index", fix_index, (size_t)dim * N);
+    prof_lap(P_CRACK, &pt);
 }
 
 void computeCab()

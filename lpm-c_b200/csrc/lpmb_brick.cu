@@ -411,7 +411,7 @@ template <bool DOT>
 __global__ void __launch_bounds__(256)
 brick_gather_kernel(long long P, int nbx, int nby, int nbz, const double *__restrict__ ypart, const double *__restrict__ stage,
                     const double *__restrict__ mask, const double *__restrict__ x, double *__restrict__ y, double *__restrict__ partials,
-                    const double *__restrict__ scal)
+                    const double *__restrict__ scal, PeerPublish pub)
 {
     __shared__ double red[8];
     if (DOT && scal && scal[7] != 0.0)
@@ -473,6 +473,9 @@ brick_gather_kernel(long long P, int nbx, int nby, int nbz, const double *__rest
                 tsum += red[k];
             partials[blockIdx.x] = tsum;
         }
+        // slab runs on the peer-memory path: the last block folds the partials and publishes this rank's p.Ap (lpmb_peer.cu)
+        if (pub.world > 0 && lpmb_last_block(pub.counter))
+            lpmb_peer_publish_block(partials, gridDim.x, pub, red);
     }
 }
 
@@ -787,7 +790,7 @@ int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec)
 
 // y = [mask .*] K x in the permuted space (+ p.Ap partials into `partials`, one per block of the gather grid)
 int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid,
-                    const PeerWait &halo_wait)
+                    const PeerWait &halo_wait, const PeerPublish &pub)
 {
     BrickMatrix &B = g_bricks[c];
     const int grid = B.nbricks < c->sm_count ? B.nbricks : c->sm_count;
@@ -802,9 +805,10 @@ int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const dou
                                                                              B.stage, dot ? scal : nullptr, halo_wait, 0, 0, 0);
     LPMB_LAUNCH_CHECK(c);
     if (dot)
-        brick_gather_kernel<true><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, partials, scal);
+        brick_gather_kernel<true><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, partials, scal, pub);
     else
-        brick_gather_kernel<false><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, nullptr, nullptr);
+        brick_gather_kernel<false><<<gather_grid, 256, 0, c->stream>>>(B.P, B.nbx, B.nby, B.nbz, B.ypart, B.stage, mask, x, y, nullptr, nullptr,
+                                                                       PeerPublish());
     LPMB_LAUNCH_CHECK(c);
     return LPMB_OK;
 }

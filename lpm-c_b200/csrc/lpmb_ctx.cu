@@ -406,6 +406,7 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaFree(c->cg.x);
     cudaFree(c->cg.partials);
     cudaFree(c->cg.scal);
+    cudaFree(c->cg.counters);
     if (c->cg.h_scal)
         cudaFreeHost(c->cg.h_scal);
     cudaFree(c->mask);

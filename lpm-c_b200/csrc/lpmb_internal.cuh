@@ -97,6 +97,7 @@ struct CGWork {
     double *partials = nullptr;                                       // [2][max_blocks]
     double *scal = nullptr;                                           // device scalars (see lpmb_solver.cu)
     double *h_scal = nullptr;                                         // pinned mirror
+    unsigned int *counters = nullptr;                                 // [4] last-block tickets (gather, update, direction)
     int max_blocks = 0;
 };
 
@@ -218,6 +219,16 @@ bool lpmb_peer_ready(lpmb_ctx *c);
 // reduce `nparts` per-block partials to this rank's scalar, publish it to all ranks; *vals (world doubles, local
 // memory) and *wait describe what the consumer kernel has to do.  Skipped on the device when scal[S_DONE] != 0.
 int lpmb_peer_allreduce_publish(lpmb_ctx *c, const double *partials, int nparts, const double *scal, const double **vals, PeerWait *wait);
+// The same without the extra launch: the PRODUCER kernel of the partials gets `pub` by value and its last block to
+// finish folds the partials (same fixed order) and publishes (lpmb_last_block / lpmb_peer_publish_block below).
+struct PeerPublish {
+    double *vals[LPMB_PEER_MAXW];
+    unsigned long long *seqs[LPMB_PEER_MAXW];
+    unsigned long long seq = 0;
+    unsigned int *counter = nullptr;  // last-block detection, self-resetting
+    int world = 0, rank = 0, set = 0; // world == 0: nothing to publish
+};
+int lpmb_peer_allreduce_prepare(lpmb_ctx *c, unsigned int *counter, PeerPublish *pub, const double **vals, PeerWait *wait);
 int lpmb_peer_halo_setup(lpmb_ctx *c, double *perm_vec, long long P, const int *inv);
 bool lpmb_peer_halo_ready(lpmb_ctx *c);
 int lpmb_peer_halo_push(lpmb_ctx *c, const double *scal, PeerWait *wait);
@@ -232,6 +243,55 @@ __device__ __forceinline__ unsigned long long lpmb_ld_acquire_sys(const unsigned
 __device__ __forceinline__ void lpmb_st_release_sys(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// True in every thread of the LAST block of the grid to arrive here; every write the other blocks made before their own
+// call is then visible to it (threadfence + atomic ticket).  The counter resets itself for the next launch.  All threads
+// of all blocks must call it.
+__device__ __forceinline__ bool lpmb_last_block(unsigned int *counter)
+{
+    __shared__ int lpmb_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        lpmb_is_last = ticket == gridDim.x - 1;
+        if (lpmb_is_last)
+            *counter = 0;
+    }
+    __syncthreads();
+    const bool last = lpmb_is_last != 0;
+    if (last)
+        __threadfence();
+    return last;
+}
+// One block of 256 threads: fold `nparts` per-block partials in the fixed order of peer_publish_kernel (lpmb_peer.cu) and
+// store {value, sequence} into slot [set][rank] of every rank's buffer.  Partials are read with ld.cg (written by other
+// blocks of the same launch).
+__device__ __forceinline__ void lpmb_peer_publish_block(const double *partials, int nparts, const PeerPublish &pb, double *red /* [8] */)
+{
+    __shared__ double lpmb_pub_total;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 256)
+        s += __ldcg(partials + i);
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+        red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; k++)
+            t += red[k];
+        lpmb_pub_total = t;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pb.world) {
+        const int r = threadIdx.x;
+        *(volatile double *)(pb.vals[r] + pb.set * LPMB_PEER_MAXW + pb.rank) = lpmb_pub_total;
+        __threadfence_system();
+        lpmb_st_release_sys(pb.seqs[r] + pb.set * LPMB_PEER_MAXW + pb.rank, pb.seq);
+    }
 }
 // thread 0 of the block waits for the peers, then the block proceeds
 __device__ __forceinline__ void lpmb_peer_wait(const PeerWait &w)
@@ -256,7 +316,7 @@ int lpmb_brick_to_perm(lpmb_ctx *c, const double *src, double *dst);
 int lpmb_brick_from_perm(lpmb_ctx *c, const double *src, double *dst);
 struct PeerWait;
 int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const double *mask, double *partials, const double *scal, int gather_grid,
-                    const PeerWait &halo_wait);
+                    const PeerWait &halo_wait, const PeerPublish &pub);
 long long lpmb_brick_bytes(lpmb_ctx *c);
 int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec);
 

@@ -233,6 +233,28 @@ int lpmb_peer_allreduce_publish(lpmb_ctx *c, const double *partials, int nparts,
     return LPMB_OK;
 }
 
+// the same bookkeeping without a launch: the caller hands `pub` to the kernel that produces the partials
+int lpmb_peer_allreduce_prepare(lpmb_ctx *c, unsigned int *counter, PeerPublish *pub, const double **vals, PeerWait *wait)
+{
+    PeerComm &pc = g_peers[c];
+    pc.seq++;
+    const int set = (int)(pc.seq & 1);
+    for (int r = 0; r < c->world; r++) {
+        pub->vals[r] = reinterpret_cast<double *>(pc.peer_buf[r] + OFF_VALS);
+        pub->seqs[r] = reinterpret_cast<unsigned long long *>(pc.peer_buf[r] + OFF_SEQS);
+    }
+    pub->seq = pc.seq;
+    pub->counter = counter;
+    pub->world = c->world;
+    pub->rank = c->rank;
+    pub->set = set;
+    *vals = reinterpret_cast<const double *>(pc.buf + OFF_VALS) + set * LPMB_PEER_MAXW;
+    wait->seqs = reinterpret_cast<const unsigned long long *>(pc.buf + OFF_SEQS) + set * LPMB_PEER_MAXW;
+    wait->seq = pc.seq;
+    wait->n = c->world;
+    return LPMB_OK;
+}
+
 // ---- halo push --------------------------------------------------------------------------------------
 // my rows src[t] -> the neighbour's rows dst[t], three components; blockIdx.y = side (0: to rank-1, 1: to rank+1)
 __global__ void __launch_bounds__(256)
@@ -247,8 +269,8 @@ peer_push_kernel(const double *__restrict__ mine, long long P, const int *__rest
     const int cnt = side ? cnt1 : cnt0;
     double *nbr = side ? nbr1 : nbr0;
     const long long PN = side ? P1 : P0;
-    if (cnt == 0)
-        return;
+    if ((side ? flag1 : flag0) == nullptr)
+        return;  // no neighbour on this side; with a neighbour but nothing to send the flag is still raised (it waits for it)
     for (int t = blockIdx.x * 256 + threadIdx.x; t < cnt; t += gridDim.x * 256) {
         const long long s = src[t], d = dst[t];
         nbr[d] = mine[s];

@@ -599,7 +599,7 @@ cg_init_scalars_kernel(const double *__restrict__ partials, int nparts, double r
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_update_kernel(const double *__restrict__ p, const double *__restrict__ ap, double *__restrict__ x, double *__restrict__ r, size_t n,
                  const double *__restrict__ partials_pap, int nparts_pap, double *__restrict__ partials_rr, double *__restrict__ scal,
-                 int parity, PeerWait pw)
+                 int parity, PeerWait pw, PeerPublish pub)
 {
     __shared__ double red[VEC_THREADS / 32];
     if (scal[S_DONE] != 0.0)
@@ -622,13 +622,17 @@ cg_update_kernel(const double *__restrict__ p, const double *__restrict__ ap, do
             scal[S_ALPHA] = alpha;
         }
     }
+    // slab runs on the peer-memory path: the last block folds the r.r partials and publishes this rank's scalar
+    if (pub.world > 0 && lpmb_last_block(pub.counter))
+        lpmb_peer_publish_block(partials_rr, gridDim.x, pub, red);
 }
 
 // rr' = sum partials ; iter++ ; stop test rr' <= threshold (solver.c:218,221-222) or iter >= maxit ;
 // beta = rr'/rr ; p = r + beta p
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_direction_kernel(const double *__restrict__ r, double *__restrict__ p, size_t n, const double *__restrict__ partials_rr, int nparts,
-                    double *__restrict__ scal, int parity, int maxit, PeerWait pw, const double *__restrict__ skip_mask)
+                    double *__restrict__ scal, int parity, int maxit, PeerWait pw, const double *__restrict__ skip_mask,
+                    unsigned int *__restrict__ counter)
 {
     __shared__ double red[VEC_THREADS / 32];
     if (scal[S_DONE] != 0.0)
@@ -639,10 +643,9 @@ cg_direction_kernel(const double *__restrict__ r, double *__restrict__ p, size_t
     const double iter = scal[S_ITER] + 1.0;
     const bool conv = rr_new <= scal[S_THRESH];
     const bool stop = conv || iter >= (double)maxit;
-    // all blocks have read the scalars they need before block 0 may overwrite them
-    // (S_RR0+parity / S_ITER / S_DONE are only written below, after every read above in this
-    // block; other blocks read S_ITER/S_DONE possibly after this write -> write into the
-    // *other* parity slot and keep S_ITER/S_DONE updates for a trailing single-block kernel)
+    // Other blocks may still be reading S_RR0+parity / S_ITER / S_THRESH / S_DONE when this one is done: the new r.r goes
+    // into the *other* parity slot, and the iteration counter, beta and the stop flag are written by the LAST block to
+    // finish (every block has read its scalars by then) -- the bookkeeping needs no kernel of its own.
     if (!stop) {
         const double beta = rr_new / rr_old;
         // skip_mask (peer halo push only): masked rows keep p -- constrained DoFs stay 0 either way, and the ghost rows
@@ -651,23 +654,15 @@ cg_direction_kernel(const double *__restrict__ r, double *__restrict__ p, size_t
             if (!skip_mask || skip_mask[i] != 0.0)
                 p[i] = fma(beta, p[i], r[i]);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (lpmb_last_block(counter) && threadIdx.x == 0) {
         scal[S_RR0 + (parity ^ 1)] = rr_new;
-}
-
-// single-thread bookkeeping after the direction kernel: iteration counter, stop flag, beta
-__global__ void cg_bookkeep_kernel(double *__restrict__ scal, int parity, int maxit)
-{
-    if (scal[S_DONE] != 0.0)
-        return;
-    const double rr_new = scal[S_RR0 + (parity ^ 1)], rr_old = scal[S_RR0 + parity];
-    const double iter = scal[S_ITER] + 1.0;
-    scal[S_ITER] = iter;
-    scal[S_BETA] = rr_new / rr_old;
-    if (rr_new <= scal[S_THRESH])
-        scal[S_DONE] = 1.0;
-    else if (iter >= (double)maxit)
-        scal[S_DONE] = 2.0;
+        scal[S_ITER] = iter;
+        scal[S_BETA] = rr_new / rr_old;
+        if (conv)
+            scal[S_DONE] = 1.0;
+        else if (iter >= (double)maxit)
+            scal[S_DONE] = 2.0;
+    }
 }
 
 __global__ void __launch_bounds__(VEC_THREADS)
@@ -697,6 +692,8 @@ int lpmb_cg_alloc(lpmb_ctx *c)
     LPMB_CUDA(cudaMalloc(&w.scal, S_COUNT * 8));
     LPMB_CUDA(cudaMemsetAsync(w.scal, 0, S_COUNT * 8, c->stream));
     LPMB_CUDA(cudaMallocHost(&w.h_scal, S_COUNT * 8));
+    LPMB_CUDA(cudaMalloc(&w.counters, 4 * sizeof(unsigned int)));
+    LPMB_CUDA(cudaMemsetAsync(w.counters, 0, 4 * sizeof(unsigned int), c->stream));
     return LPMB_OK;
 }
 
@@ -789,40 +786,45 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
                 LPMB_TRY(brick ? lpmb_brick_exchange(c, vp) : lpmb_dist_exchange(c, vp, c->dim, false));
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b], c->stream));
+            // peer-memory path: the scalar publishes ride in the last block of the kernels that produce the partials
+            PeerPublish pub_a, pub_b;
+            PeerWait pw_a, pw_b;
+            const double *vals_a = nullptr, *vals_b = nullptr;
+            const bool fold_a = peer && brick;   // the SELL kernel keeps the separate publish launch
+            if (fold_a)
+                LPMB_TRY(lpmb_peer_allreduce_prepare(c, w.counters + 0, &pub_a, &vals_a, &pw_a));
             if (brick)
-                LPMB_TRY(lpmb_brick_spmv(c, vp, vap, true, m, part_a, w.scal, sg, hw));
+                LPMB_TRY(lpmb_brick_spmv(c, vp, vap, true, m, part_a, w.scal, sg, hw, pub_a));
             else
                 LPMB_TRY(launch_spmv(c, vp, vap, true, use_mask));  // partials -> part_a (w.partials)
             if (c->profile)
                 LPMB_CUDA(cudaEventRecord(c->prof_events[2 * b + 1], c->stream));
             if (peer) {
-                const double *vals;
-                PeerWait pw;
-                LPMB_TRY(lpmb_peer_allreduce_publish(c, part_a, sg, w.scal, &vals, &pw));
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, vals, c->world, part_b, w.scal, parity, pw);
+                if (!fold_a)
+                    LPMB_TRY(lpmb_peer_allreduce_publish(c, part_a, sg, w.scal, &vals_a, &pw_a));
+                LPMB_TRY(lpmb_peer_allreduce_prepare(c, w.counters + 1, &pub_b, &vals_b, &pw_b));
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, vals_a, c->world, part_b, w.scal, parity, pw_a, pub_b);
                 LPMB_LAUNCH_CHECK(c);
-                LPMB_TRY(lpmb_peer_allreduce_publish(c, part_b, vg, w.scal, &vals, &pw));
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, vals, c->world, w.scal, parity, maxit, pw, peer_halo ? m : nullptr);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, vals_b, c->world, w.scal, parity, maxit, pw_b, peer_halo ? m : nullptr,
+                                                                       w.counters + 2);
                 LPMB_LAUNCH_CHECK(c);
             } else if (dist) {
                 reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, sg, red_a, w.scal);
                 LPMB_LAUNCH_CHECK(c);
                 LPMB_TRY(lpmb_dist_allreduce_sum(c, red_a, 1));
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, red_a, 1, part_b, w.scal, parity, nowait);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, red_a, 1, part_b, w.scal, parity, nowait, PeerPublish());
                 LPMB_LAUNCH_CHECK(c);
                 reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_b, vg, red_b, w.scal);
                 LPMB_LAUNCH_CHECK(c);
                 LPMB_TRY(lpmb_dist_allreduce_sum(c, red_b, 1));
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, red_b, 1, w.scal, parity, maxit, nowait, nullptr);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, red_b, 1, w.scal, parity, maxit, nowait, nullptr, w.counters + 2);
                 LPMB_LAUNCH_CHECK(c);
             } else {
-                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, part_a, sg, part_b, w.scal, parity, nowait);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, part_a, sg, part_b, w.scal, parity, nowait, PeerPublish());
                 LPMB_LAUNCH_CHECK(c);
-                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, part_b, vg, w.scal, parity, maxit, nowait, nullptr);
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, part_b, vg, w.scal, parity, maxit, nowait, nullptr, w.counters + 2);
                 LPMB_LAUNCH_CHECK(c);
             }
-            cg_bookkeep_kernel<<<1, 1, 0, c->stream>>>(w.scal, parity, maxit);
-            LPMB_LAUNCH_CHECK(c);
             parity ^= 1;
         }
         LPMB_CUDA(cudaMemcpyAsync(w.h_scal, w.scal, S_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -956,7 +958,7 @@ extern "C" int lpmb_spmv_host(lpmb_ctx *c, const double *x, double *y)
         LPMB_TRY(lpmb_brick_prepare(c));
         lpmb_brick_vectors(c, &vr, &vp, &vap, &vx, &vb, &vm, &P);
         LPMB_TRY(lpmb_brick_to_perm(c, c->cg.p, vp));
-        LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, vec_grid(c, (size_t)3 * P), PeerWait()));
+        LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, vec_grid(c, (size_t)3 * P), PeerWait(), PeerPublish()));
         LPMB_TRY(lpmb_brick_from_perm(c, vap, c->cg.ap));
     } else
         LPMB_TRY(launch_spmv(c, c->cg.p, c->cg.ap, false, false));
@@ -995,10 +997,10 @@ extern "C" int lpmb_spmv_bench(lpmb_ctx *c, int reps, int variant, double *ms_pe
         LPMB_CUDA(cudaEventCreate(&e0));
         LPMB_CUDA(cudaEventCreate(&e1));
         for (int i = 0; i < 3; i++)
-            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg, PeerWait()));
+            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg, PeerWait(), PeerPublish()));
         LPMB_CUDA(cudaEventRecord(e0, c->stream));
         for (int i = 0; i < reps; i++)
-            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg, PeerWait()));
+            LPMB_TRY(lpmb_brick_spmv(c, vp, vap, false, nullptr, nullptr, nullptr, gg, PeerWait(), PeerPublish()));
         LPMB_CUDA(cudaEventRecord(e1, c->stream));
         LPMB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
