@@ -396,6 +396,16 @@ def reference_newton_sample(m: int, steps: int, warmup: int, cores: int, keep_ou
            "t_step": float(np.mean(times)), "t_cg": float(np.mean(t_solve[warmup:])), "cg_iterations": int(its[-1]), "steps": steps,
            "norm_residual0": float(nr0), "norm_residual1": float(nr), "impl": "dropin" if dropin else "cpu"}
     if keep_outputs:
+        # one more, UNTIMED replay whose outputs are compared (parity_at_sample): the reference's threaded force loop writes
+        # its neighbours' dL / dL_total rows from several threads -- usually benign, but one bench run
+        # on the 16-core box came back with F off by 4.6e-4 while disp agreed to 8e-15; single-threaded it is deterministic
+        def law_on_one_thread():
+            L.omp_set_num_threads(1)
+            L.computeBondForceGeneral(r.gi("plmode"), 1)
+            L.omp_set_num_threads(cores)
+        r.put("xyz", xyz_s)
+        r.put("residual", res_s)
+        r.newton_iteration(hooks={"solve": timed_solve, "bondforce": law_on_one_thread})
         out["arrays"] = {"disp": r.get("disp"), "F": r.get("F"), "Pin": r.get("Pin"), "xyz0": xyz_s, "xyz": r.get("xyz")}
     return out
 

@@ -44,6 +44,10 @@
  * (xyz, xyz_temp, F_temp, Pex, dispBC_index, fix_index, residual, K_global, type, Ce, parameters) are uploaded on
  * entry of the call that reads them.
  *
+ * A second set-up in the same process (initMatrices() + the neighbour searches run again: the reference allocates new
+ * arrays) is recognised by the addresses of neighbors / xyz_initial / conn / dLp and the sizes; the device context is then
+ * rebuilt from the new host arrays on the next call.
+ *
  * solverPARDISO() (solver.c:3-92; selected by no shipped driver): no sparse direct factorisation on the GPU path.  The
  * call runs the same CG to ||r|| <= 1e-12 ||r0|| (at most dim*N iterations), prints one notice on stderr the first time,
  * and exits with status 3 if that residual is not reached -- the reference's PARDISO path also exits on failure

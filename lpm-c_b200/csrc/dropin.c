@@ -253,10 +253,23 @@ static void up_host_owned(void)
 
 /* first call: create the context from the reference's set-up (createCuboid / searchNormalNeighbor /
  * searchAFEMNeighbor / initMatrices have run) and upload every array these functions read */
+void lpmc_dropin_shutdown(void);
+/* identity of the set-up the device context was built from: initMatrices() / searchNormalNeighbor() allocate these arrays
+ * anew (the reference never frees them), so a driver -- or a Python test -- that sets a second problem up in the same
+ * process is recognised and gets a fresh context instead of the first problem's device state */
+static const void *g_sig[4];
+static int g_sig_n[4];
+
 static void ensure_ctx(void)
 {
-    if (g_ctx)
-        return;
+    if (g_ctx) {
+        if (g_sig[0] == (const void *)neighbors && g_sig[1] == (const void *)xyz_initial && g_sig[2] == (const void *)conn &&
+            g_sig[3] == (const void *)dLp && g_sig_n[0] == nparticle && g_sig_n[1] == dim && g_sig_n[2] == lattice && g_sig_n[3] == nneighbors)
+            return;
+        lpmc_dropin_shutdown();
+    }
+    g_sig[0] = neighbors, g_sig[1] = xyz_initial, g_sig[2] = conn, g_sig[3] = dLp;
+    g_sig_n[0] = nparticle, g_sig_n[1] = dim, g_sig_n[2] = lattice, g_sig_n[3] = nneighbors;
     const char *dev = getenv("LPMB_DEVICE");
     const char *dbc = getenv("LPMB_DROPIN_DEVICE_BC");
     g_device_bc = dbc && atoi(dbc) != 0;

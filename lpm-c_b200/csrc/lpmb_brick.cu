@@ -79,8 +79,9 @@ void lpmb_brick_release(lpmb_ctx *c)
     g_bricks.erase(it);
 }
 
-void lpmb_brick_touch(lpmb_ctx *c)
+void lpmb_brick_touch(lpmb_ctx *c)   // K.val changed: every mirror of it is stale
 {
+    c->K.rows_ready = false;
     auto it = g_bricks.find(c);
     if (it != g_bricks.end())
         it->second.values_ready = false;

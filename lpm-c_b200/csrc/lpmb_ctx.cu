@@ -404,6 +404,9 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaFree(c->cg.p);
     cudaFree(c->cg.ap);
     cudaFree(c->cg.x);
+    cudaFree(c->K.rptr);
+    cudaFree(c->K.rcol);
+    cudaFree(c->K.rval);
     cudaFree(c->cg.partials);
     cudaFree(c->cg.scal);
     cudaFree(c->cg.counters);

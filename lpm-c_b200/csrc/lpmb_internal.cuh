@@ -90,6 +90,13 @@ struct SellMatrix {
     long long *kp = nullptr;   // [N+1] K_pointer[i][1] (64-bit)
     bool pattern_ready = false;
     bool values_ready = false;
+    // Row-packed mirror for SMALL lattices (lpmb_solver.cu, spmv_rows_kernel): block row i = nb_conn[i] consecutive
+    // D x D blocks, so one warp owns a row and its lanes stride over the blocks -- ~60x more parallelism per row than the
+    // SELL kernel's one-lane-per-row walk, which is latency-bound when the whole lattice is a few hundred warps.
+    long long *rptr = nullptr; // [N+1] block offsets
+    int *rcol = nullptr;       // [nblocks]
+    double *rval = nullptr;    // [nblocks][D*D]
+    bool rows_ready = false;   // mirrors val (reset whenever val changes)
 };
 
 struct CGWork {

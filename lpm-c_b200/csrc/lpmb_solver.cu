@@ -517,12 +517,131 @@ spmv_sell_kernel(int s_begin, int s_end, const long long *__restrict__ sptr, con
     }
 }
 
+// ---- small lattices: row-packed mirror, one warp per block row ------------------------------------------------
+// BASELINE configs 1-4 (9 k - 75 k particles, matrix 8 - 313 MB) are a few hundred warps in the SELL kernel, each
+// walking its 61 blocks one after the other: latency-bound (measured: 83 us per CG iteration in the default case).
+// Here the 32 lanes of a warp stride over the blocks of ONE row (contiguous 72-byte blocks: coalesced), the D partial
+// sums are folded by a fixed shuffle tree: deterministic, no atomics.
+#define ROWS_THREADS 256
+template <int D>
+__global__ void sell_to_rows_kernel(int N, const long long *__restrict__ sptr, const int *__restrict__ col, const double *__restrict__ val,
+                                    const int *__restrict__ nbc, const long long *__restrict__ rptr, int *__restrict__ rcol,
+                                    double *__restrict__ rval)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N)
+        return;
+    const long long ka = sptr[row >> 5], b0 = rptr[row];
+    const int lane = row & 31, n = nbc[row];
+    for (int k = 0; k < n; k++) {
+        rcol[b0 + k] = col[(ka + k) * 32 + lane];
+#pragma unroll
+        for (int e = 0; e < D * D; e++)
+            rval[(b0 + k) * (D * D) + e] = val[((ka + k) * (D * D) + e) * 32 + lane];
+    }
+}
+
+template <int D, bool DOT>
+__global__ void __launch_bounds__(ROWS_THREADS)
+spmv_rows_kernel(int N, const long long *__restrict__ rptr, const int *__restrict__ rcol, const double *__restrict__ rval,
+                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ mask, int Np,
+                 double *__restrict__ partials, const double *__restrict__ scal)
+{
+    __shared__ double red[ROWS_THREADS / 32];
+    if (DOT && scal && scal[S_DONE] != 0.0)
+        return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * ROWS_THREADS + threadIdx.x) >> 5, nwarps = (gridDim.x * ROWS_THREADS) >> 5;
+    double dot = 0.0;
+    for (int row = warp; row < N; row += nwarps) {
+        const long long b0 = rptr[row], b1 = rptr[row + 1];
+        double acc[D];
+#pragma unroll
+        for (int r = 0; r < D; r++)
+            acc[r] = 0.0;
+        for (long long k = b0 + lane; k < b1; k += 32) {
+            const int cidx = rcol[k];
+            const double *a = rval + k * (D * D);
+            double xv[D];
+#pragma unroll
+            for (int q = 0; q < D; q++)
+                xv[q] = x[(size_t)q * Np + cidx];
+#pragma unroll
+            for (int r = 0; r < D; r++)
+#pragma unroll
+                for (int q = 0; q < D; q++)
+                    acc[r] = fma(a[r * D + q], xv[q], acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < D; r++)
+            acc[r] = warp_sum(acc[r]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < D; r++) {
+                double v = acc[r];
+                if (mask)
+                    v *= mask[(size_t)r * Np + row];
+                y[(size_t)r * Np + row] = v;
+                if (DOT)
+                    dot = fma(v, x[(size_t)r * Np + row], dot);
+            }
+        }
+    }
+    if (DOT) {
+        const double t = block_sum<ROWS_THREADS>(dot, red);
+        if (threadIdx.x == 0)
+            partials[blockIdx.x] = t;
+    }
+}
+
+static bool rows_active(lpmb_ctx *c)
+{
+    return c->world == 1 && c->N <= (int)param(c, "spmv_rows_max", 262144.0) && param(c, "spmv_rows", 1.0) != 0.0;
+}
+
+static int rows_grid(lpmb_ctx *c)
+{
+    const int want = (c->N + ROWS_THREADS / 32 - 1) / (ROWS_THREADS / 32);
+    const int cap = c->sm_count * 8;
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+// (re)build the row-packed mirror from K.val
+static int rows_prepare(lpmb_ctx *c)
+{
+    SellMatrix &K = c->K;
+    if (K.rows_ready)
+        return LPMB_OK;
+    const int N = c->N;
+    if (!K.rptr) {
+        std::vector<int> nbc(N);
+        LPMB_D2H(c, nbc.data(), K.nbc, (size_t)N * sizeof(int));
+        std::vector<long long> rp((size_t)N + 1, 0);
+        for (int i = 0; i < N; i++)
+            rp[i + 1] = rp[i] + nbc[i];
+        const size_t nb = (size_t)rp[N] + 1;
+        LPMB_CUDA(cudaMalloc(&K.rptr, ((size_t)N + 1) * sizeof(long long)));
+        LPMB_CUDA(cudaMalloc(&K.rcol, nb * sizeof(int)));
+        LPMB_CUDA(cudaMalloc(&K.rval, nb * K.D * K.D * sizeof(double)));
+        LPMB_H2D(c, K.rptr, rp.data(), ((size_t)N + 1) * sizeof(long long));
+    }
+    if (c->dim == 3)
+        sell_to_rows_kernel<3><<<lpmb_blocks(N, 128), 128, 0, c->stream>>>(N, K.sptr, K.col, K.val, K.nbc, K.rptr, K.rcol, K.rval);
+    else
+        sell_to_rows_kernel<2><<<lpmb_blocks(N, 128), 128, 0, c->stream>>>(N, K.sptr, K.col, K.val, K.nbc, K.rptr, K.rcol, K.rval);
+    LPMB_LAUNCH_CHECK(c);
+    K.rows_ready = true;
+    return LPMB_OK;
+}
+
 // slices that contain owned rows (all of them on a single GPU)
 static inline int slice_begin(lpmb_ctx *c) { return lpmb_own0(c) / 32; }
 static inline int slice_end(lpmb_ctx *c) { return (lpmb_own1(c) + 31) / 32; }
 
 static int spmv_grid(lpmb_ctx *c)
 {
+    if (rows_active(c))
+        return rows_grid(c);
     // persistent-ish: at most 16 CTAs of 4 warps per SM, never more CTAs than slices/4
     const int ns = slice_end(c) - slice_begin(c);
     const int want = (ns + (SPMV_THREADS / 32) - 1) / (SPMV_THREADS / 32);
@@ -536,6 +655,24 @@ static int launch_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, bool u
     const int grid = spmv_grid(c);
     const int sb = slice_begin(c), se = slice_end(c);
     const double *m = use_mask ? c->mask : nullptr;
+    if (rows_active(c)) {
+        LPMB_TRY(rows_prepare(c));
+        double *part = dot ? c->cg.partials : nullptr;
+        const double *sc = dot ? c->cg.scal : nullptr;
+        if (c->dim == 3) {
+            if (dot)
+                spmv_rows_kernel<3, true><<<grid, ROWS_THREADS, 0, c->stream>>>(c->N, K.rptr, K.rcol, K.rval, x, y, m, c->Np, part, sc);
+            else
+                spmv_rows_kernel<3, false><<<grid, ROWS_THREADS, 0, c->stream>>>(c->N, K.rptr, K.rcol, K.rval, x, y, m, c->Np, part, sc);
+        } else {
+            if (dot)
+                spmv_rows_kernel<2, true><<<grid, ROWS_THREADS, 0, c->stream>>>(c->N, K.rptr, K.rcol, K.rval, x, y, m, c->Np, part, sc);
+            else
+                spmv_rows_kernel<2, false><<<grid, ROWS_THREADS, 0, c->stream>>>(c->N, K.rptr, K.rcol, K.rval, x, y, m, c->Np, part, sc);
+        }
+        LPMB_LAUNCH_CHECK(c);
+        return LPMB_OK;
+    }
     if (c->dim == 3) {
         if (dot)
             spmv_sell_kernel<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(sb, se, K.sptr, K.col, K.val, x, y, m, c->Np, c->cg.partials, c->cg.scal);
