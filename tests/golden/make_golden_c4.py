@@ -40,7 +40,7 @@ def main():
     g = {"setup.xyz": r.get("xyz"), "setup.type": r.get("type"), "setup.nb_initial": r.get("nb_initial"),
          "sizes": np.array([r.N, int(r.get("nb_initial").sum()), int(r.get("nb_conn").sum()), int(r.get("K_pointer")[r.N, 1])])}
     print("set-up", round(time.time() - t0, 1), "s; N, bonds, conn blocks, nnz_upper =", g["sizes"].tolist(), flush=True)
-    newton, cg_all, wall = [], [], []
+    newton, cg_all, wall, law = [], [], [], []
     for step in range(1, steps + 1):
         ts = time.time()
         nr, nf = r.begin_step(DBP, [])
@@ -65,6 +65,7 @@ def main():
         newton.append(ni)
         cg_all.append(cg)
         wall.append(time.time() - ts)
+        law.append(t_law)
         g[f"s{step}.xyz"] = r.get("xyz")
         g[f"s{step}.stress_tensor"] = r.get("stress_tensor")
         g[f"s{step}.cp_A"] = r.get_cp("cp_A")[:, 0]
@@ -80,6 +81,7 @@ def main():
               f"{int(jact.sum())}, max cp_A {g[f's{step}.cp_A'].max():.3e}", flush=True)
     g["newton_counts"] = np.array(newton)
     g["wall_s"] = np.array(wall)
+    g["law_s"] = np.array(law)        # computeBondForceGeneral(1) per load step (serial in the reference, constitutive.c:114-117)
     out = Path(os.environ.get("LPMB_GOLDEN_OUT", Path(__file__).resolve().parent / "c4_fcc_real.npz"))
     np.savez_compressed(out, **g)
     print("wrote", out, round(out.stat().st_size / 1e6, 2), "MB")

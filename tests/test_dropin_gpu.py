@@ -199,3 +199,30 @@ def test_dropin_solver_pardiso():
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "scripts" / "dropin_pardiso_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PARDISO_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "solverPARDISO() is served by the GPU CG" in r.stderr
+
+
+def test_dropin_runs_config4_at_its_real_size(tmp_path):
+    """BASELINE config 4 at its REAL size (FCC, radius 0.3, box 0..10: 6 912 particles, 114 192 bonds, nnz_upper 1 652 940; crystal
+    plasticity with 24 slip systems, the nine displacement BCs and -2e-3 per step of examples/FCC_Al_R0.3_001_tension.c), three
+    load steps (11 / 10 / 8 Newton iterations, ~124 CG iterations per solve, every particle plastic) through the reference's
+    host code + liblpmc_dropin.so against the serial all-CPU run of the same generator (tests/golden/c4_fcc_real.npz,
+    tests/golden/make_golden_c4.py -- which also says why the example's own TU cannot be compiled)."""
+    new = _regen("make_golden_c4.py", tmp_path, "c4.npz")
+    old = np.load(GOLD / "c4_fcc_real.npz")
+    assert list(new["sizes"]) == list(old["sizes"]) == [6912, 114192, 365016, 1652940]       # SURVEY section 8, config C4
+    assert list(new["newton_counts"]) == list(old["newton_counts"])
+    x0 = old["setup.xyz"]
+    for step in (1, 2, 3):
+        a, b = new[f"s{step}.cg_iterations"], old[f"s{step}.cg_iterations"]
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1, (step, a, b)
+        assert _rel(new[f"s{step}.xyz"] - x0, old[f"s{step}.xyz"] - x0) <= 1e-8, step
+        assert _rel(new[f"s{step}.stress_tensor"], old[f"s{step}.stress_tensor"]) <= 1e-7, step
+        assert _rel(new[f"s{step}.cp_A"], old[f"s{step}.cp_A"]) <= 1e-7, step
+        assert abs(int(new[f"s{step}.active_systems"][0]) - int(old[f"s{step}.active_systems"][0])) <= 6, step
+        assert abs(float(new[f"s{step}.reaction_norm"][0]) / float(old[f"s{step}.reaction_norm"][0]) - 1.0) <= 1e-8, step
+    for n in ("F", "cp_gy", "dLp"):
+        assert _rel(new[f"s3.{n}"], old[f"s3.{n}"]) <= 1e-7, n
+    mism = int((new["s3.cp_Jact_last"] != old["s3.cp_Jact_last"]).sum())
+    assert mism <= 6, mism                                   # borderline systems of the last active-set search
+    print(f"config 4 through the drop-in: wall per load step {new['wall_s'].round(2).tolist()} s (serial CPU reference {old['wall_s'].round(1).tolist()} s), "
+          f"crystal-plasticity law per step {new['law_s'].round(3).tolist()} s (CPU {old['law_s'].round(1).tolist()} s), Jact mismatches {mism}")
