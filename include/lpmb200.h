@@ -99,6 +99,11 @@ int lpmb_get_param(lpmb_ctx *ctx, const char *name, double *value);
  * "damage_nonlocal0/1", "damage_local0/1". */
 int lpmb_field_set(lpmb_ctx *ctx, const char *name, const void *host, size_t count);
 int lpmb_field_get(lpmb_ctx *ctx, const char *name, void *host, size_t count);
+/* n <= 64 fields with ONE device->host copy and ONE synchronisation: staged[k] points at the host-layout image of
+ * names[k] inside the context's pinned staging buffer (valid until the next call that stages data), counts[k] (optional)
+ * receives its element count.  What liblpmc_dropin.so uses to refresh the reference's host arrays after a call: it
+ * scatters straight from the pinned images into the jagged arrays. */
+int lpmb_fields_get_staged(lpmb_ctx *ctx, int n, const char *const *names, const void **staged, size_t *counts);
 /* raw device pointer + element count of a field (device layout; for zero-copy harnesses) */
 int lpmb_field_device(lpmb_ctx *ctx, const char *name, void **dptr, size_t *count);
 

@@ -54,6 +54,7 @@ lib.lpmb_get_param.argtypes = [c_vp, C.c_char_p, c_dp]
 lib.lpmb_field_set.argtypes = [c_vp, C.c_char_p, c_vp, C.c_size_t]
 lib.lpmb_field_get.argtypes = [c_vp, C.c_char_p, c_vp, C.c_size_t]
 lib.lpmb_field_device.argtypes = [c_vp, C.c_char_p, C.POINTER(c_vp), C.POINTER(C.c_size_t)]
+lib.lpmb_fields_get_staged.argtypes = [c_vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_vp), C.POINTER(C.c_size_t)]
 lib.lpmb_set_neighbors.argtypes = [c_vp, c_vp, c_vp]
 lib.lpmb_set_connectivity.argtypes = [c_vp, c_vp]
 lib.lpmb_build_topology.argtypes = [c_vp, C.c_double, C.c_double]
@@ -183,6 +184,19 @@ class Context:
     def get_field(self, name: str) -> np.ndarray:
         out = np.empty(self._shape(name), dtype=np.int32 if name in _INT_FIELDS else np.float64)
         _check(lib.lpmb_field_get(self._h, name.encode(), out.ctypes.data, out.size))
+        return out
+
+    def get_fields(self, names) -> dict:
+        """several fields with one device->host copy and one synchronisation (lpmb_fields_get_staged)"""
+        n = len(names)
+        arr = (C.c_char_p * n)(*[nm.encode() for nm in names])
+        ptrs, cnts = (c_vp * n)(), (C.c_size_t * n)()
+        _check(lib.lpmb_fields_get_staged(self._h, n, arr, ptrs, cnts))
+        out = {}
+        for k, nm in enumerate(names):
+            dt = np.int32 if nm in _INT_FIELDS else np.float64
+            buf = (C.c_char * (cnts[k] * np.dtype(dt).itemsize)).from_address(ptrs[k])
+            out[nm] = np.frombuffer(buf, dtype=dt).reshape(self._shape(nm)).copy()
         return out
 
     # -- topology

@@ -334,6 +334,56 @@ extern "C" int lpmb_field_get(lpmb_ctx *c, const char *name, void *host, size_t 
     return LPMB_OK;
 }
 
+// Several fields with ONE device->host copy and ONE synchronisation: the host-layout images are laid out back to back
+// in the context's pinned staging buffer; staged[k] points at the image of names[k] (valid until the next call that
+// uses the staging buffers).  The caller copies / scatters from there (the drop-in layer scatters into the reference's
+// jagged arrays directly, with no intermediate flat copy).
+extern "C" int lpmb_fields_get_staged(lpmb_ctx *c, int n, const char *const *names, const void **staged, size_t *counts)
+{
+    LPMB_REQUIRE(c && names && staged && n > 0 && n <= 64, LPMB_ERR_ARG, "lpmb_fields_get_staged: bad argument");
+    LPMB_CUDA(cudaSetDevice(c->device));
+    size_t off[65];
+    Field *fs[64];
+    off[0] = 0;
+    for (int k = 0; k < n; k++) {
+        fs[k] = lpmb_field(c, names[k]);
+        if (!fs[k])
+            return LPMB_ERR_ARG;
+        const size_t cnt = fs[k]->kind == FK_RAW ? fs[k]->count : (size_t)c->N * fs[k]->comps;
+        const size_t bytes = cnt * (fs[k]->kind == FK_RAW ? fs[k]->elem() : host_elem(*fs[k]));
+        if (counts)
+            counts[k] = cnt;
+        off[k + 1] = off[k] + ((bytes + 255) & ~(size_t)255);
+    }
+    LPMB_TRY(lpmb_ensure_staging(c, off[n]));
+    LPMB_TRY(lpmb_ensure_h_staging(c, off[n]));
+    for (int k = 0; k < n; k++) {
+        Field *f = fs[k];
+        char *dst = (char *)c->staging + off[k];
+        if (f->kind == FK_RAW) {
+            LPMB_CUDA(cudaMemcpyAsync(dst, f->d, f->count * f->elem(), cudaMemcpyDeviceToDevice, c->stream));
+            continue;
+        }
+        const int blocks = c->Np / 32;
+        const size_t smem = (size_t)32 * f->comps * host_elem(*f);
+        if (smem > 40 * 1024) {
+            LPMB_REQUIRE(f->type == FT_F64, LPMB_ERR_UNSUPPORTED, "wide integer field %s", names[k]);
+            wide_to_host<<<4 * c->sm_count, 256, 0, c->stream>>>((const double *)f->d, (double *)dst, c->N, c->Np, f->comps);
+        } else if (f->type == FT_F64)
+            to_host_layout<double, double><<<blocks, 256, smem, c->stream>>>((const double *)f->d, (double *)dst, c->N, c->Np, f->comps);
+        else if (f->type == FT_I32)
+            to_host_layout<int, int><<<blocks, 256, smem, c->stream>>>((const int *)f->d, (int *)dst, c->N, c->Np, f->comps);
+        else
+            to_host_layout<int, signed char><<<blocks, 256, smem, c->stream>>>((const signed char *)f->d, (int *)dst, c->N, c->Np, f->comps);
+        LPMB_LAUNCH_CHECK(c);
+    }
+    LPMB_CUDA(cudaMemcpyAsync(c->h_staging, c->staging, off[n], cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n; k++)
+        staged[k] = (const char *)c->h_staging + off[k];
+    return LPMB_OK;
+}
+
 extern "C" int lpmb_field_device(lpmb_ctx *c, const char *name, void **dptr, size_t *count)
 {
     LPMB_REQUIRE(c && name, LPMB_ERR_ARG, "lpmb_field_device: null argument");
