@@ -273,6 +273,36 @@ def gpu_arm(args):
     d2h = o_xyz.nbytes + o_disp.nbytes + o_pin.nbytes + o_res.nbytes
     assert np.isfinite(o_xyz).all() and np.isfinite(nr_e)
 
+    # ---- opt-in fast mode: CG preconditioned with the matrix-free multigrid V-cycle (lpmb_mg.cu).  Reported BESIDE the
+    # parity-mode headline above, never instead of it: another Krylov sequence, same stop rule on the true residual.
+    fast = None
+    if not args.no_fast_mode:
+        try:
+            c.set_params(cg_precond=1.0)
+            for _ in range(2):
+                one_step(c)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            f_iters, f_nr = [], []
+            for _ in range(args.steps):
+                itf, nrf = one_step(c)
+                f_iters.append(itf)
+                f_nr.append(nrf)
+            f1.record(stream)
+            barrier()
+            f_ms = f0.elapsed_time(f1) / args.steps
+            fast = {"newton_it_per_s": 1000.0 / f_ms, "ms_per_step": f_ms, "pcg_iterations_per_step": f_iters,
+                    "speedup_vs_parity_mode": ms_per_step / f_ms, "norm_residual_after_the_iteration": f_nr[-1],
+                    "norm_residual_after_the_iteration_parity_mode": nr,
+                    "preconditioner": "matrix-free geometric multigrid V-cycle (2+2 damped block-Jacobi sweeps, trilinear transfer, "
+                                      "one 61-point stencil of the assembled tangent for all levels), param cg_precond = 1",
+                    "note": "not the parity path: the reference's CG is unpreconditioned (solver.c:219-220); same stop rule on the true residual"}
+        except Exception as e:   # the fast mode is optional; the parity-mode line stands on its own
+            fast = {"error": str(e)[:300]}
+        finally:
+            c.set_params(cg_precond=0.0)
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -297,6 +327,7 @@ def gpu_arm(args):
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "fast_mode": fast,
     }
     c.close()
     if not args.no_cpu_baseline:
@@ -575,6 +606,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spmv", default="bricks", choices=["bricks", "full"],
                     help="CG SpMV kernel: brick-blocked symmetric (default) or the full-format SELL kernel")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the opt-in preconditioned (multigrid) fast-mode line")
     ap.add_argument("--no-brick-trim", action="store_true", help="A/B: stream whole class tiles instead of only the needed z-layers")
     args = ap.parse_args()
     if args.sample_child:

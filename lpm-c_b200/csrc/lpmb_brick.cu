@@ -82,6 +82,7 @@ void lpmb_brick_release(lpmb_ctx *c)
 void lpmb_brick_touch(lpmb_ctx *c)   // K.val changed: every mirror of it is stale
 {
     c->K.rows_ready = false;
+    lpmb_mg_touch(c);
     auto it = g_bricks.find(c);
     if (it != g_bricks.end())
         it->second.values_ready = false;

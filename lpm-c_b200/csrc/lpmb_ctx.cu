@@ -454,6 +454,8 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaFree(c->cg.p);
     cudaFree(c->cg.ap);
     cudaFree(c->cg.x);
+    lpmb_mg_release(c);
+    cudaFree(c->cg.z);
     cudaFree(c->K.rptr);
     cudaFree(c->K.rcol);
     cudaFree(c->K.rval);

@@ -105,6 +105,7 @@ struct CGWork {
     double *scal = nullptr;                                           // device scalars (see lpmb_solver.cu)
     double *h_scal = nullptr;                                         // pinned mirror
     unsigned int *counters = nullptr;                                 // [4] last-block tickets (gather, update, direction)
+    double *z = nullptr;                                              // [D][Np] preconditioned residual (fast mode only)
     int max_blocks = 0;
 };
 
@@ -326,6 +327,13 @@ int lpmb_brick_spmv(lpmb_ctx *c, const double *x, double *y, bool dot, const dou
                     const PeerWait &halo_wait, const PeerPublish &pub);
 long long lpmb_brick_bytes(lpmb_ctx *c);
 int lpmb_brick_exchange(lpmb_ctx *c, double *perm_vec);
+
+// matrix-free multigrid preconditioner of the opt-in fast mode (lpmb_mg.cu)
+int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0);
+int lpmb_mg_apply(lpmb_ctx *c, const double *r, double *z, const double *done);
+void lpmb_mg_touch(lpmb_ctx *c);
+void lpmb_mg_release(lpmb_ctx *c);
+int lpmb_mg_levels(lpmb_ctx *c);
 
 // solver-side entry points used across TUs
 int lpmb_cg_alloc(lpmb_ctx *c);

@@ -1,0 +1,504 @@
+// lpmb_mg.cu -- matrix-free geometric multigrid V-cycle: the preconditioner of the OPT-IN fast mode of the solve
+// (param "cg_precond" = 1; lpmb_solver.cu::pcg_run).  The parity mode -- the reference's unpreconditioned CG,
+// solver.c:188-270 with ipar[10] = 0 -- is untouched by anything in this file.
+//
+// Why.  north_star asks for a preconditioned CG.  On the lattice tangent point preconditioners do not pay (Jacobi /
+// block-Jacobi save 4-5 % of the iterations, tests/test_oracle_ref.py); the iteration count grows like n^(1/3) (116 at
+// 48^3, 226 at 100^3, 458 at 216^3), i.e. it is a multilevel problem.  What makes a multilevel preconditioner nearly
+// free here: the reference assembles K as the ELASTIC tangent only (stiffness.c:394,420: plmode 6), so on an undamaged
+// simple-cubic block every interior block row of K is the same 61-point stencil of 3x3 blocks up to the O(strain)
+// geometric change -- the hierarchy needs NO matrices, one stencil in constant memory serves all levels:
+//
+//   level l = the simple-cubic lattice coarsened l times (vertex-centred: coarse site I sits on fine site 2I),
+//   A_l u (i)  =  sum over stencil offsets o with i+o inside the box of  2^l S_o (u(i+o) - u(i))
+//                 -- S_o = the off-diagonal blocks of one interior row of the assembled K; the diagonal block is minus
+//                 the sum of the off-diagonal blocks that are present, which is what translation invariance of the real
+//                 tangent gives (free surfaces handled); the factor 2^l is the rediscretised operator on spacing 2^l h
+//                 (bond stiffness ~ radius, stiffness.c:179-185), equal to the Galerkin operator on smooth fields,
+//   smoother   =  damped block-Jacobi (3x3 diagonal blocks inverted per boundary class on the host), nu sweeps before and
+//                 after the coarse correction, R = P^T with trilinear P: a symmetric positive definite V-cycle,
+//   constraints: the DoF mask of the solve on level 0; a coarse DoF is constrained when any fine DoF in its
+//                 interpolation support is (Dirichlet faces stay Dirichlet faces).
+//
+// numpy prototype on the reference's own tangent (C5 material, 1 % stretch, bottom layer held): stencil operator vs real K
+// 0.4-0.6 % apart; PCG iterations to the reference's stop rule 11 at 24^3 (plain CG 64), 13 at 48^3 (plain CG 116).
+//
+// Cost per V-cycle at 216^3: 5 fine-level stencil passes over 30 M unknowns with no matrix traffic (x is read through
+// L1/L2, 61 x 18 flop per site) + 1/7 of that for the coarse levels -- against 24 GB of matrix per real SpMV.
+//
+// Scope: one GPU, 3-D simple-cubic FULL blocks numbered x-fastest (initialization.c:266-284) with >= 5 sites per edge;
+// anything else -> LPMB_ERR_UNSUPPORTED (the caller fails loudly; there is no silent fallback to another solver).
+#include <algorithm>
+#include <cmath>
+
+#include "lpmb_internal.cuh"
+
+#define MG_MAXOFF 64
+#define MG_MAXLEV 12
+
+__constant__ int c_mg_off[MG_MAXOFF][3];
+__constant__ double c_mg_S[MG_MAXOFF][9];
+__constant__ int c_mg_noff;
+
+struct MGLevel {
+    int nx = 0, ny = 0, nz = 0;
+    long long n = 0, stride = 0;   // sites; distance between the components of a vector
+    double scale = 1.0;
+    double *dinv = nullptr;        // [729][9] inverse diagonal block per boundary class
+    double *mask = nullptr;        // [3][stride] (level 0: the solve's mask, not owned)
+    double *u = nullptr, *u2 = nullptr, *f = nullptr, *res = nullptr;   // [3][stride] (level 0: u = caller's z, f = caller's r)
+};
+
+struct MGState {
+    bool ready = false;
+    int nlev = 0;
+    MGLevel lev[MG_MAXLEV];
+    double S[MG_MAXOFF][9];
+    int off[MG_MAXOFF][3];
+    int noff = 0;
+    int nu = 2, nu_coarse = 40;
+    double omega = 0.6;
+};
+
+static std::map<lpmb_ctx *, MGState> g_mg;
+
+void lpmb_mg_release(lpmb_ctx *c)
+{
+    auto it = g_mg.find(c);
+    if (it == g_mg.end())
+        return;
+    MGState &M = it->second;
+    for (int l = 0; l < M.nlev; l++) {
+        MGLevel &L = M.lev[l];
+        cudaFree(L.dinv);
+        cudaFree(L.u2);
+        cudaFree(L.res);
+        if (l > 0) {
+            cudaFree(L.mask);
+            cudaFree(L.u);
+            cudaFree(L.f);
+        }
+    }
+    g_mg.erase(it);
+}
+
+void lpmb_mg_touch(lpmb_ctx *c)   // K.val changed: the stencil is re-read at the next solve
+{
+    auto it = g_mg.find(c);
+    if (it != g_mg.end())
+        it->second.ready = false;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int mg_axis_class(int i, int n) { return min(i, 2) + 3 * min(n - 1 - i, 2); }
+
+// MODE 0: out = u + omega * mask .* Dinv (f - A u)      (one damped block-Jacobi sweep, out != u)
+// MODE 1: out = mask .* (f - A u)                       (residual)
+// MODE 2: out = omega * mask .* Dinv f                  (first sweep from u = 0: no stencil pass)
+template <int MODE>
+__global__ void __launch_bounds__(128)
+mg_stencil_kernel(int nx, int ny, int nz, long long stride, double scale, const double *__restrict__ dinv, const double *__restrict__ mask,
+                  const double *__restrict__ u, const double *__restrict__ f, double *__restrict__ out, double omega, const double *__restrict__ done)
+{
+    if (done && done[0] != 0.0)
+        return;
+    const long long n = (long long)nx * ny * nz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int ix = (int)(i % nx), iy = (int)((i / nx) % ny), iz = (int)(i / ((long long)nx * ny));
+    double r0 = f[i], r1 = f[stride + i], r2 = f[2 * stride + i];
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    if (MODE != 2) {
+        u0 = u[i], u1 = u[stride + i], u2 = u[2 * stride + i];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const int noff = c_mg_noff;
+        for (int k = 0; k < noff; k++) {
+            const int jx = ix + c_mg_off[k][0], jy = iy + c_mg_off[k][1], jz = iz + c_mg_off[k][2];
+            if (jx < 0 || jx >= nx || jy < 0 || jy >= ny || jz < 0 || jz >= nz)
+                continue;
+            const long long j = jx + (long long)nx * (jy + (long long)ny * jz);
+            const double d0 = __ldg(u + j) - u0, d1 = __ldg(u + stride + j) - u1, d2 = __ldg(u + 2 * stride + j) - u2;
+            a0 = fma(c_mg_S[k][0], d0, fma(c_mg_S[k][1], d1, fma(c_mg_S[k][2], d2, a0)));
+            a1 = fma(c_mg_S[k][3], d0, fma(c_mg_S[k][4], d1, fma(c_mg_S[k][5], d2, a1)));
+            a2 = fma(c_mg_S[k][6], d0, fma(c_mg_S[k][7], d1, fma(c_mg_S[k][8], d2, a2)));
+        }
+        r0 -= scale * a0;
+        r1 -= scale * a1;
+        r2 -= scale * a2;
+    }
+    const double m0 = mask ? mask[i] : 1.0, m1 = mask ? mask[stride + i] : 1.0, m2 = mask ? mask[2 * stride + i] : 1.0;
+    if (MODE == 1) {
+        out[i] = m0 * r0;
+        out[stride + i] = m1 * r1;
+        out[2 * stride + i] = m2 * r2;
+        return;
+    }
+    // constrained DoFs carry no residual: the block solve must not leak their (unmasked) residual into the free ones
+    r0 *= m0, r1 *= m1, r2 *= m2;
+    const double *D = dinv + 9 * (mg_axis_class(ix, nx) + 9 * (mg_axis_class(iy, ny) + 9 * mg_axis_class(iz, nz)));
+    out[i] = u0 + omega * m0 * (D[0] * r0 + D[1] * r1 + D[2] * r2);
+    out[stride + i] = u1 + omega * m1 * (D[3] * r0 + D[4] * r1 + D[5] * r2);
+    out[2 * stride + i] = u2 + omega * m2 * (D[6] * r0 + D[7] * r1 + D[8] * r2);
+}
+
+// 1-D interpolation weight of fine site f from coarse site X (coarse X sits on fine 2X; nc coarse sites)
+__device__ __forceinline__ double mg_w1(int f, int X, int nc)
+{
+    const int d = f - 2 * X;
+    if (d == 0)
+        return 1.0;
+    if (d == 1)
+        return X + 1 < nc ? 0.5 : 1.0;   // the upper coarse neighbour does not exist: constant extrapolation
+    if (d == -1)
+        return 0.5;
+    return 0.0;
+}
+
+// fc = mask_c .* P^T rf     (full weighting = transpose of the trilinear interpolation)
+__global__ void __launch_bounds__(128)
+mg_restrict_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, const double *__restrict__ rf,
+                   const double *__restrict__ mask_c, double *__restrict__ fc, const double *__restrict__ done)
+{
+    if (done && done[0] != 0.0)
+        return;
+    const long long nc = (long long)ncx * ncy * ncz;
+    const long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc)
+        return;
+    const int X = (int)(I % ncx), Y = (int)((I / ncx) % ncy), Z = (int)(I / ((long long)ncx * ncy));
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int dz = -1; dz <= 1; dz++) {
+        const int fz = 2 * Z + dz;
+        if (fz < 0 || fz >= nfz)
+            continue;
+        const double wz = mg_w1(fz, Z, ncz);
+        for (int dy = -1; dy <= 1; dy++) {
+            const int fy = 2 * Y + dy;
+            if (fy < 0 || fy >= nfy)
+                continue;
+            const double wy = wz * mg_w1(fy, Y, ncy);
+            for (int dx = -1; dx <= 1; dx++) {
+                const int fx = 2 * X + dx;
+                if (fx < 0 || fx >= nfx)
+                    continue;
+                const double w = wy * mg_w1(fx, X, ncx);
+                const long long j = fx + (long long)nfx * (fy + (long long)nfy * fz);
+                s0 = fma(w, rf[j], s0);
+                s1 = fma(w, rf[sf + j], s1);
+                s2 = fma(w, rf[2 * sf + j], s2);
+            }
+        }
+    }
+    fc[I] = mask_c[I] * s0;
+    fc[sc + I] = mask_c[sc + I] * s1;
+    fc[2 * sc + I] = mask_c[2 * sc + I] * s2;
+}
+
+// uf += mask_f .* P uc
+__global__ void __launch_bounds__(128)
+mg_prolong_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, const double *__restrict__ uc,
+                  const double *__restrict__ mask_f, double *__restrict__ uf, const double *__restrict__ done)
+{
+    if (done && done[0] != 0.0)
+        return;
+    const long long nf = (long long)nfx * nfy * nfz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf)
+        return;
+    const int fx = (int)(i % nfx), fy = (int)((i / nfx) % nfy), fz = (int)(i / ((long long)nfx * nfy));
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    const int X0 = fx >> 1, Y0 = fy >> 1, Z0 = fz >> 1;
+    for (int az = 0; az <= (fz & 1); az++) {
+        const int Z = Z0 + az;
+        if (Z >= ncz)
+            continue;
+        const double wz = mg_w1(fz, Z, ncz);
+        for (int ay = 0; ay <= (fy & 1); ay++) {
+            const int Y = Y0 + ay;
+            if (Y >= ncy)
+                continue;
+            const double wy = wz * mg_w1(fy, Y, ncy);
+            for (int ax = 0; ax <= (fx & 1); ax++) {
+                const int X = X0 + ax;
+                if (X >= ncx)
+                    continue;
+                const double w = wy * mg_w1(fx, X, ncx);
+                const long long J = X + (long long)ncx * (Y + (long long)ncy * Z);
+                s0 = fma(w, uc[J], s0);
+                s1 = fma(w, uc[sc + J], s1);
+                s2 = fma(w, uc[2 * sc + J], s2);
+            }
+        }
+    }
+    const double m0 = mask_f ? mask_f[i] : 1.0, m1 = mask_f ? mask_f[sf + i] : 1.0, m2 = mask_f ? mask_f[2 * sf + i] : 1.0;
+    uf[i] += m0 * s0;
+    uf[sf + i] += m1 * s1;
+    uf[2 * sf + i] += m2 * s2;
+}
+
+// coarse DoF free only if every fine DoF in its interpolation support is free
+__global__ void mg_coarse_mask_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, const double *__restrict__ mf,
+                                      double *__restrict__ mc)
+{
+    const long long nc = (long long)ncx * ncy * ncz;
+    const long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= nc)
+        return;
+    const int X = (int)(I % ncx), Y = (int)((I / ncx) % ncy), Z = (int)(I / ((long long)ncx * ncy));
+    double m[3] = {1.0, 1.0, 1.0};
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const int fx = 2 * X + dx, fy = 2 * Y + dy, fz = 2 * Z + dz;
+                if (fx < 0 || fx >= nfx || fy < 0 || fy >= nfy || fz < 0 || fz >= nfz)
+                    continue;
+                if (mg_w1(fx, X, ncx) * mg_w1(fy, Y, ncy) * mg_w1(fz, Z, ncz) == 0.0)
+                    continue;
+                const long long j = fx + (long long)nfx * (fy + (long long)nfy * fz);
+                for (int k = 0; k < 3; k++)
+                    m[k] = fmin(m[k], mf ? mf[k * sf + j] : 1.0);
+            }
+    for (int k = 0; k < 3; k++)
+        mc[k * sc + I] = m[k];
+}
+
+// particle i must sit on lattice site (i % nx, (i / nx) % ny, i / (nx ny)) of an axis-aligned lattice of spacing q
+__global__ void mg_check_order_kernel(int N, int Np, const double *__restrict__ x0, double ox, double oy, double oz, double q, int nx, int ny,
+                                      int *__restrict__ bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const double fx = (x0[i] - ox) / q, fy = (x0[(size_t)Np + i] - oy) / q, fz = (x0[(size_t)2 * Np + i] - oz) / q;
+    const int ix = i % nx, iy = (i / nx) % ny, iz = i / (nx * ny);
+    if (fabs(fx - ix) > 1e-6 || fabs(fy - iy) > 1e-6 || fabs(fz - iz) > 1e-6)
+        atomicExch(bad, 1);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+static bool invert3(const double *a, double *inv)
+{
+    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    if (!(std::fabs(det) > 0.0))
+        return false;
+    const double id = 1.0 / det;
+    inv[0] = (a[4] * a[8] - a[5] * a[7]) * id;
+    inv[1] = (a[2] * a[7] - a[1] * a[8]) * id;
+    inv[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    inv[3] = (a[5] * a[6] - a[3] * a[8]) * id;
+    inv[4] = (a[0] * a[8] - a[2] * a[6]) * id;
+    inv[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    inv[6] = (a[3] * a[7] - a[4] * a[6]) * id;
+    inv[7] = (a[1] * a[6] - a[0] * a[7]) * id;
+    inv[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+    return true;
+}
+
+// lattice dimensions + ordering check (once), level storage
+static int mg_build_levels(lpmb_ctx *c, MGState &M)
+{
+    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "cg_precond: the multigrid preconditioner runs on one GPU only");
+    LPMB_REQUIRE(c->dim == 3 && c->lattice == LPMB_LATTICE_SC, LPMB_ERR_UNSUPPORTED, "cg_precond: 3-D simple-cubic lattices only");
+    LPMB_REQUIRE(c->params.count("radius") && c->fields.count("xyz_initial"), LPMB_ERR_STATE, "cg_precond needs radius and xyz_initial");
+    const int N = c->N, Np = c->Np;
+    const double q = 2.0 * param(c, "radius");
+    const double *x0 = fptr<double>(c, "xyz_initial");
+    std::vector<double> hx((size_t)3 * Np);
+    LPMB_D2H(c, hx.data(), x0, hx.size() * 8);
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; k++) {
+        lo[k] = 1e300, hi[k] = -1e300;
+        for (int i = 0; i < N; i++) {
+            lo[k] = std::min(lo[k], hx[(size_t)k * Np + i]);
+            hi[k] = std::max(hi[k], hx[(size_t)k * Np + i]);
+        }
+    }
+    const int nx = (int)llround((hi[0] - lo[0]) / q) + 1, ny = (int)llround((hi[1] - lo[1]) / q) + 1, nz = (int)llround((hi[2] - lo[2]) / q) + 1;
+    LPMB_REQUIRE((long long)nx * ny * nz == N, LPMB_ERR_UNSUPPORTED, "cg_precond: %d particles are not a full %d x %d x %d simple-cubic block", N, nx, ny,
+                 nz);
+    LPMB_REQUIRE(nx >= 5 && ny >= 5 && nz >= 5, LPMB_ERR_UNSUPPORTED, "cg_precond: the block needs at least 5 sites per edge");
+    int *d_bad;
+    LPMB_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    LPMB_MEMSET(c, d_bad, 0, sizeof(int));
+    mg_check_order_kernel<<<lpmb_blocks(N, 256), 256, 0, c->stream>>>(N, Np, x0, lo[0], lo[1], lo[2], q, nx, ny, d_bad);
+    LPMB_LAUNCH_CHECK(c);
+    int bad = 0;
+    LPMB_D2H(c, &bad, d_bad, sizeof(int));
+    cudaFree(d_bad);
+    LPMB_REQUIRE(!bad, LPMB_ERR_UNSUPPORTED, "cg_precond: particles are not numbered x-fastest on an axis-aligned lattice of spacing %g", q);
+    M.nlev = 0;
+    int ax = nx, ay = ny, az = nz;
+    double scale = 1.0;
+    for (;;) {
+        LPMB_REQUIRE(M.nlev < MG_MAXLEV, LPMB_ERR_UNSUPPORTED, "cg_precond: too many levels");
+        MGLevel &L = M.lev[M.nlev];
+        L.nx = ax, L.ny = ay, L.nz = az;
+        L.n = (long long)ax * ay * az;
+        L.stride = M.nlev == 0 ? Np : L.n;
+        L.scale = scale;
+        LPMB_CUDA(cudaMalloc(&L.dinv, 729 * 9 * sizeof(double)));
+        LPMB_CUDA(cudaMalloc(&L.u2, (size_t)3 * L.stride * 8));
+        LPMB_CUDA(cudaMalloc(&L.res, (size_t)3 * L.stride * 8));
+        LPMB_MEMSET(c, L.u2, 0, (size_t)3 * L.stride * 8);
+        LPMB_MEMSET(c, L.res, 0, (size_t)3 * L.stride * 8);
+        if (M.nlev > 0) {
+            LPMB_CUDA(cudaMalloc(&L.mask, (size_t)3 * L.stride * 8));
+            LPMB_CUDA(cudaMalloc(&L.u, (size_t)3 * L.stride * 8));
+            LPMB_CUDA(cudaMalloc(&L.f, (size_t)3 * L.stride * 8));
+        }
+        M.nlev++;
+        if (std::min(ax, std::min(ay, az)) <= 4)
+            break;
+        ax = (ax + 1) / 2, ay = (ay + 1) / 2, az = (az + 1) / 2;
+        scale *= 2.0;
+    }
+    return LPMB_OK;
+}
+
+// stencil = the off-diagonal blocks of the block row of the centre particle (re-read after every assembly)
+static int mg_read_stencil(lpmb_ctx *c, MGState &M)
+{
+    SellMatrix &K = c->K;
+    const MGLevel &L0 = M.lev[0];
+    const int ic = (L0.nx / 2) + L0.nx * ((L0.ny / 2) + L0.ny * (L0.nz / 2));
+    int nbc = 0;
+    long long ka = 0;
+    LPMB_D2H(c, &nbc, K.nbc + ic, sizeof(int));
+    LPMB_D2H(c, &ka, K.sptr + (ic >> 5), sizeof(long long));
+    LPMB_REQUIRE(nbc > 1 && nbc <= MG_MAXOFF, LPMB_ERR_UNSUPPORTED, "cg_precond: centre particle has %d conn entries", nbc);
+    std::vector<int> col(nbc);
+    std::vector<double> val((size_t)nbc * 9);
+    const int lane = ic & 31;
+    LPMB_CUDA(cudaMemcpy2DAsync(col.data(), sizeof(int), K.col + ka * 32 + lane, 32 * sizeof(int), sizeof(int), nbc, cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaMemcpy2DAsync(val.data(), sizeof(double), K.val + ka * 9 * 32 + lane, 32 * sizeof(double), sizeof(double), (size_t)nbc * 9,
+                                cudaMemcpyDeviceToHost, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+    M.noff = 0;
+    const int cx = L0.nx / 2, cy = L0.ny / 2, cz = L0.nz / 2;
+    for (int k = 0; k < nbc; k++) {
+        const int j = col[k];
+        if (j == ic)
+            continue;
+        const int jx = j % L0.nx, jy = (j / L0.nx) % L0.ny, jz = j / (L0.nx * L0.ny);
+        M.off[M.noff][0] = jx - cx, M.off[M.noff][1] = jy - cy, M.off[M.noff][2] = jz - cz;
+        for (int e = 0; e < 9; e++)
+            M.S[M.noff][e] = val[(size_t)k * 9 + e];
+        M.noff++;
+    }
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_off, M.off, sizeof(M.off), 0, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_noff, &M.noff, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+    // inverse diagonal blocks per boundary class and level: D = -scale * sum of the present off-diagonal blocks
+    std::vector<double> tab((size_t)729 * 9);
+    for (int l = 0; l < M.nlev; l++) {
+        MGLevel &L = M.lev[l];
+        for (int cls = 0; cls < 729; cls++) {
+            const int cxs = cls % 9, cys = (cls / 9) % 9, czs = cls / 81;
+            const int lo3[3] = {cxs % 3, cys % 3, czs % 3}, hi3[3] = {cxs / 3, cys / 3, czs / 3};
+            double D[9] = {0};
+            for (int k = 0; k < M.noff; k++) {
+                bool present = true;
+                for (int a = 0; a < 3; a++)
+                    present = present && M.off[k][a] >= -lo3[a] && M.off[k][a] <= hi3[a];
+                if (present)
+                    for (int e = 0; e < 9; e++)
+                        D[e] -= L.scale * M.S[k][e];
+            }
+            double inv[9] = {0};
+            if (!invert3(D, inv))
+                for (int e = 0; e < 9; e++)
+                    inv[e] = 0.0;   // a class that cannot occur on this level (isolated site)
+            for (int e = 0; e < 9; e++)
+                tab[(size_t)cls * 9 + e] = inv[e];
+        }
+        LPMB_H2D(c, L.dinv, tab.data(), tab.size() * sizeof(double));
+    }
+    M.nu = std::max(1, (int)param(c, "mg_nu", 2.0));
+    M.nu_coarse = std::max(1, (int)param(c, "mg_nu_coarse", 40.0));
+    M.omega = param(c, "mg_omega", 0.6);
+    M.ready = true;
+    return LPMB_OK;
+}
+
+// hierarchy + stencil ready; coarse masks follow the solve's current DoF mask
+int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
+{
+    MGState &M = g_mg[c];
+    if (M.nlev == 0) {
+        const int rc = mg_build_levels(c, M);
+        if (rc != LPMB_OK) {
+            lpmb_mg_release(c);
+            return rc;
+        }
+    }
+    LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
+    if (!M.ready)
+        LPMB_TRY(mg_read_stencil(c, M));
+    M.lev[0].mask = const_cast<double *>(mask0);
+    for (int l = 1; l < M.nlev; l++) {
+        const MGLevel &F = M.lev[l - 1];
+        MGLevel &C = M.lev[l];
+        mg_coarse_mask_kernel<<<lpmb_blocks(C.n, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, F.stride, C.nx, C.ny, C.nz, C.stride, F.mask, C.mask);
+        LPMB_LAUNCH_CHECK(c);
+    }
+    return LPMB_OK;
+}
+
+// nu damped-Jacobi sweeps on level l starting from u = 0 (first = true) or from L.u; result in L.u
+static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const double *done)
+{
+    MGLevel &L = M.lev[l];
+    const int grid = lpmb_blocks(L.n, 128);
+    for (int s = 0; s < nu; s++) {
+        if (first && s == 0)
+            mg_stencil_kernel<2><<<grid, 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, L.scale, L.dinv, L.mask, nullptr, L.f, L.u2, M.omega, done);
+        else
+            mg_stencil_kernel<0><<<grid, 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, L.scale, L.dinv, L.mask, L.u, L.f, L.u2, M.omega, done);
+        LPMB_LAUNCH_CHECK(c);
+        std::swap(L.u, L.u2);
+    }
+    return LPMB_OK;
+}
+
+static int mg_vcycle(lpmb_ctx *c, MGState &M, int l, const double *done)
+{
+    MGLevel &L = M.lev[l];
+    if (l == M.nlev - 1)
+        return mg_smooth(c, M, l, M.nu_coarse, true, done);
+    LPMB_TRY(mg_smooth(c, M, l, M.nu, true, done));
+    mg_stencil_kernel<1><<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, L.scale, L.dinv, L.mask, L.u, L.f, L.res, 0.0, done);
+    LPMB_LAUNCH_CHECK(c);
+    MGLevel &C = M.lev[l + 1];
+    mg_restrict_kernel<<<lpmb_blocks(C.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, L.res, C.mask, C.f, done);
+    LPMB_LAUNCH_CHECK(c);
+    LPMB_TRY(mg_vcycle(c, M, l + 1, done));
+    mg_prolong_kernel<<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, C.u, L.mask, L.u, done);
+    LPMB_LAUNCH_CHECK(c);
+    return mg_smooth(c, M, l, M.nu, false, done);
+}
+
+// z = V-cycle(r) on the context's original-order vectors ([3][Np]); r is not modified.  `done` (device, may be null):
+// every kernel returns at once when *done != 0 (the PCG loop issues iterations in batches).
+int lpmb_mg_apply(lpmb_ctx *c, const double *r, double *z, const double *done)
+{
+    MGState &M = g_mg[c];
+    LPMB_REQUIRE(M.ready && M.nlev > 0, LPMB_ERR_STATE, "multigrid hierarchy not prepared");
+    MGLevel &L0 = M.lev[0];
+    // level 0 smooths between z and its scratch twin; an even total number of swaps leaves the result in z
+    L0.f = const_cast<double *>(r);
+    L0.u = z;
+    LPMB_TRY(mg_vcycle(c, M, 0, done));
+    if (L0.u != z) {   // odd number of sweeps in total: the result sits in the scratch buffer
+        LPMB_CUDA(cudaMemcpyAsync(z, L0.u, (size_t)3 * L0.stride * 8, cudaMemcpyDeviceToDevice, c->stream));
+        L0.u2 = L0.u;
+    }
+    L0.u = nullptr;
+    return LPMB_OK;
+}
+
+int lpmb_mg_levels(lpmb_ctx *c)
+{
+    auto it = g_mg.find(c);
+    return it == g_mg.end() ? 0 : it->second.nlev;
+}
