@@ -279,7 +279,9 @@ def test_preconditioned_fast_mode(lpm, bricks):
     n = 24
     c, info = bench.build_workload(lpm, n, 0, bricks=bricks)
     N = n ** 3
-    mask = ((c.get_field("dispBC_index") != 0) & (c.get_field("fix_index") != 0)).astype(float)
+    bc, fix = c.get_field("dispBC_index"), c.get_field("fix_index")
+    c.set_dof_mask(bc, fix)
+    mask = ((bc != 0) & (fix != 0)).astype(float)
     b = c.get_field("residual") * mask
 
     def solve(rel):
