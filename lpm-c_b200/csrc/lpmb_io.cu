@@ -11,7 +11,7 @@
 // File layout (little endian):
 //   char[8]  "LPMBSNP1"
 //   int32    N, Np, dim, lattice, nn, nconn, nparams, nfields
-//   nparams  x { uint16 len; char name[len]; double value }
+//   nparams  x { uint16 len; char name[len]; double value }     (slab runs add "__world", "__rank", "__own0", "__own1")
 //   nfields  x { uint16 len; char name[len]; int32 kind, type, comps; uint64 count; byte data[count * elem] }
 #include <cstdio>
 
@@ -56,9 +56,17 @@ extern "C" int lpmb_snapshot_save(lpmb_ctx *c, const char *path)
     for (auto &kv : c->fields)
         if (!snap_skip(kv.first))
             nfields++;
-    const int head[8] = {c->N, c->Np, c->dim, c->lattice, c->nn, c->nconn, (int)c->params.size(), nfields};
+    // slab runs: the file is this rank's slab; its place in the decomposition travels as four pseudo-parameters
+    std::map<std::string, double> params = c->params;
+    if (c->world > 1) {
+        params["__world"] = c->world;
+        params["__rank"] = c->rank;
+        params["__own0"] = lpmb_own0(c);
+        params["__own1"] = lpmb_own1(c);
+    }
+    const int head[8] = {c->N, c->Np, c->dim, c->lattice, c->nn, c->nconn, (int)params.size(), nfields};
     SNAP_IO(fwrite(SNAP_MAGIC, 1, 8, fc.f) == 8 && fwrite(head, sizeof(int), 8, fc.f) == 8, "write header");
-    for (auto &kv : c->params) {
+    for (auto &kv : params) {
         const unsigned short len = (unsigned short)kv.first.size();
         SNAP_IO(fwrite(&len, 2, 1, fc.f) == 1 && fwrite(kv.first.data(), 1, len, fc.f) == len && fwrite(&kv.second, 8, 1, fc.f) == 1, "write parameter");
     }
@@ -89,7 +97,8 @@ extern "C" int lpmb_snapshot_load(lpmb_ctx *c, const char *path)
 {
     LPMB_REQUIRE(c && path, LPMB_ERR_ARG, "lpmb_snapshot_load: null argument");
     LPMB_CUDA(cudaSetDevice(c->device));
-    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "snapshots of slab runs are per rank: load before lpmb_dist_set_slab");
+    // slab runs: one file per rank, loaded AFTER lpmb_dist_init + lpmb_dist_set_slab into a context with the same
+    // decomposition (checked below against the "__world/__rank/__own0/__own1" entries the save wrote)
     FileCloser fc{fopen(path, "rb")};
     SNAP_IO(fc.f, "open for reading");
     char magic[8];
@@ -100,13 +109,30 @@ extern "C" int lpmb_snapshot_load(lpmb_ctx *c, const char *path)
                  LPMB_ERR_ARG, "snapshot %s is for N=%d dim=%d lattice=%d nn=%d nconn=%d, the context has N=%d dim=%d lattice=%d nn=%d nconn=%d", path,
                  head[0], head[2], head[3], head[4], head[5], c->N, c->dim, c->lattice, c->nn, c->nconn);
     char name[256];
+    int s_world = 1, s_rank = 0, s_own0 = 0, s_own1 = c->N;
     for (int k = 0; k < head[6]; k++) {
         unsigned short len = 0;
         double v = 0;
         SNAP_IO(fread(&len, 2, 1, fc.f) == 1 && len < sizeof(name) && fread(name, 1, len, fc.f) == len && fread(&v, 8, 1, fc.f) == 1, "read parameter");
         name[len] = 0;
+        if (name[0] == '_' && name[1] == '_') {
+            const std::string key(name);
+            if (key == "__world")
+                s_world = (int)v;
+            else if (key == "__rank")
+                s_rank = (int)v;
+            else if (key == "__own0")
+                s_own0 = (int)v;
+            else if (key == "__own1")
+                s_own1 = (int)v;
+            continue;
+        }
         c->params[name] = v;
     }
+    LPMB_REQUIRE(s_world == c->world && s_rank == c->rank && (c->world == 1 || (s_own0 == lpmb_own0(c) && s_own1 == lpmb_own1(c))), LPMB_ERR_ARG,
+                 "snapshot %s was written by rank %d of %d (owned particles [%d, %d)); this context is rank %d of %d (owned [%d, %d)) -- slab "
+                 "snapshots are per rank and need the same decomposition (lpmb_dist_init + lpmb_dist_set_slab before the load)",
+                 path, s_rank, s_world, s_own0, s_own1, c->rank, c->world, lpmb_own0(c), lpmb_own1(c));
     LPMB_TRY(lpmb_ensure_h_staging(c, SNAP_CHUNK));
     for (int k = 0; k < head[7]; k++) {
         unsigned short len = 0;

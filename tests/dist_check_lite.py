@@ -53,6 +53,24 @@ def child(rank, world, n, d):
     its, nrs, broken = run_steps(c)
     own = slice(slab.own0, slab.own1)
     out = {k: np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own]) for k in KEYS}
+    # per-rank snapshot / resume of a slab run (lpmb_io.cu): save, run on, wipe, load, run on again -> identical
+    snap = Path(d) / f"rank{rank}.snap"
+    c.snapshot_save(snap)
+
+    def next_step():
+        c.copy_field("xyz_temp", "xyz")
+        c.copy_field("F_temp", "F")
+        c.fd_stiffness(False)
+        c.bond_force(4)
+        c.update_rr()
+        return c.newton_iteration(0, 1)
+
+    a = next_step()
+    xa = c.get_field("xyz")
+    c.set_field("xyz", np.zeros_like(xa))
+    c.snapshot_load(snap)
+    b = next_step()
+    assert a == b and np.array_equal(xa, c.get_field("xyz")), ("slab snapshot resume differs", a, b)
     np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken]), mode=np.array([c.dist_mode()]),
              norm0=np.array([info["norm_residual0"]]), spmv_bytes=np.array([c.spmv_bytes_bricks()]), **out)
     c.close()
