@@ -3,7 +3,10 @@
  * plain C over the C ABI only: one process per GPU, each holding a z-slab of the lattice (contiguous particle index
  * range + 4 ghost layers towards each neighbour), exactly the decomposition bench.py uses (lpm-c_b200/partition.py).
  *
- *   sc_block_mgpu <world> [n=48] [steps=1] [physics=c1|c5] [strain_step=0.005]
+ *   sc_block_mgpu <world> [n=48] [steps=1] [physics=c1|c5] [strain_step=0.005] [solver=parity|fast]
+ *
+ * solver fast (world = 1 only): the opt-in preconditioned mode of the solve (param cg_precond = 1: CG preconditioned with
+ * the matrix-free multigrid V-cycle, lpmb_mg.cu) -- NOT the parity path; the iteration counts printed are then PCG iterations.
  *
  * physics c1 (default): the default driver's problem (src/lpmc_project.c: E = 146e3, nu = 0.3, sigma_y = 200, force-controlled
  * -2000 per step on the bottom layer).  physics c5: BASELINE config 5 -- the material and damage law of
@@ -79,7 +82,7 @@ static void ghosts(int nz, int r, int world, int *lo, int *hi)
     *hi = r < world - 1 ? imin(GHOST, nz - b) : 0;
 }
 
-static int run_rank(int rank, int world, int n, int steps, const char *dir, int c5, double strain_step)
+static int run_rank(int rank, int world, int n, int steps, const char *dir, int c5, double strain_step, int fast)
 {
     g_rank = rank;
     if (lpmb_device_count() < world) {
@@ -145,6 +148,8 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir, int 
     CK(lpmb_set_param(ctx, "particle_volume", pow(2.0 * radius, 3)));
     CK(lpmb_set_param(ctx, "J2_H", J2_H));
     CK(lpmb_set_param(ctx, "J2_xi", J2_xi));
+    if (fast)
+        CK(lpmb_set_param(ctx, "cg_precond", 1.0));
     CK(lpmb_set_param(ctx, "damage_L", c5 ? 0.6 : 0.5));
     CK(lpmb_set_param(ctx, "damage_threshold", c5 ? 0.85 : 0.9));
     CK(lpmb_set_param(ctx, "damagec_A", c5 ? 400.0 : 0.0));
@@ -177,7 +182,7 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir, int 
     CK(lpmb_synchronize(ctx));
     if (rank == 0)
         printf("%d ranks, lattice %d^3 = %lld particles, %d..%d owned layers per rank, communication mode %d, physics %s, set-up %.2f s\n", world,
-               n, (long long)n * n * n, n / world, (n + world - 1) / world, lpmb_dist_mode(ctx), c5 ? "c5" : "c1", now() - t0);
+               n, (long long)n * n * n, n / world, (n + world - 1) / world, lpmb_dist_mode(ctx), c5 ? (fast ? "c5, fast mode (multigrid PCG)" : "c5") : (fast ? "c1, fast mode (multigrid PCG)" : "c1"), now() - t0);
 
     for (int step = 1; step <= steps; step++) {
         const double ts = now();
@@ -276,15 +281,16 @@ static int run_rank(int rank, int world, int n, int steps, const char *dir, int 
 
 int main(int argc, char **argv)
 {
-    if (argc >= 9 && strcmp(argv[1], "--rank") == 0)   /* child: --rank r world n steps dir c5 strain_step */
-        return run_rank(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6], atoi(argv[7]), atof(argv[8]));
+    if (argc >= 10 && strcmp(argv[1], "--rank") == 0)   /* child: --rank r world n steps dir c5 strain_step fast */
+        return run_rank(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), argv[6], atoi(argv[7]), atof(argv[8]), atoi(argv[9]));
     const int world = argc > 1 ? atoi(argv[1]) : 0;
     const int n = argc > 2 ? atoi(argv[2]) : 48;
     const int steps = argc > 3 ? atoi(argv[3]) : 1;
     const int c5 = argc > 4 && strcmp(argv[4], "c5") == 0;
     const double strain_step = argc > 5 ? atof(argv[5]) : 0.005;
-    if (world < 1 || world > 16 || steps < 1 || n < 4 * world || (argc > 4 && !c5 && strcmp(argv[4], "c1") != 0)) {
-        fprintf(stderr, "usage: sc_block_mgpu <world 1..16> [n >= 4*world] [steps >= 1] [c1|c5] [strain_step]\n");
+    const int fast = argc > 6 && strcmp(argv[6], "fast") == 0;
+    if (world < 1 || world > 16 || steps < 1 || n < 4 * world || (argc > 4 && !c5 && strcmp(argv[4], "c1") != 0) || (fast && world != 1)) {
+        fprintf(stderr, "usage: sc_block_mgpu <world 1..16> [n >= 4*world] [steps >= 1] [c1|c5] [strain_step] [parity|fast (world 1 only)]\n");
         return 2;
     }
     char dir[] = "/tmp/lpmb_mgpu_XXXXXX";
@@ -293,7 +299,8 @@ int main(int argc, char **argv)
         return 1;
     }
     pid_t pid[16];
-    char a_rank[16], a_world[16], a_n[16], a_steps[16], a_c5[4], a_strain[40];
+    char a_rank[16], a_world[16], a_n[16], a_steps[16], a_c5[4], a_strain[40], a_fast[4];
+    snprintf(a_fast, sizeof a_fast, "%d", fast);
     snprintf(a_c5, sizeof a_c5, "%d", c5);
     snprintf(a_strain, sizeof a_strain, "%.17g", strain_step);
     snprintf(a_world, sizeof a_world, "%d", world);
@@ -307,7 +314,7 @@ int main(int argc, char **argv)
         }
         if (pid[r] == 0) {
             snprintf(a_rank, sizeof a_rank, "%d", r);
-            char *args[] = {argv[0], "--rank", a_rank, a_world, a_n, a_steps, dir, a_c5, a_strain, NULL};
+            char *args[] = {argv[0], "--rank", a_rank, a_world, a_n, a_steps, dir, a_c5, a_strain, a_fast, NULL};
             execv("/proc/self/exe", args);
             perror("execv");
             _exit(127);

@@ -60,6 +60,11 @@
  *   LPMB_DEVICE=<n>            CUDA device (default 0)
  *   LPMB_DROPIN_BRICKS=1|0     force the brick-blocked symmetric CG SpMV on / off (default: on from 2^18 particles
  *                              on axis-aligned simple-cubic 3-D lattices; see lpmb_matrix_enable_bricks)
+ *   LPMB_DROPIN_FAST=1         opt-in fast mode of solverCG(): CG preconditioned with the matrix-free multigrid V-cycle
+ *                              (param cg_precond).  NOT the parity path (another Krylov sequence, same
+ *                              stop rule); works on the re-imported K_global as well;
+ *                              full simple-cubic blocks only, any other lattice makes solverCG() exit with the library's message
+ *   LPMB_DROPIN_PROFILE=1      wall time per entry point on stderr at exit
  *   LPMB_DROPIN_DEVICE_BC=1    solverCG() keeps the tangent on the device and applies the displacement
  *                              BCs as a DoF mask instead of re-uploading the host-edited K_global
  *                              (identical iterates, see tests/test_solver_gpu.py; default off = strict)

@@ -45,6 +45,7 @@ static lpmb_ctx *g_ctx = NULL;
 static double *g_buf = NULL; /* flat staging for one array */
 static size_t g_buf_bytes = 0;
 static int g_device_bc = 0;
+static int g_fast = 0; /* LPMB_DROPIN_FAST: multigrid-preconditioned solve (the constrained DoFs are then masked out) */
 static int g_state_uploaded = 0;
 static int g_cp_ready = 0;
 
@@ -383,6 +384,13 @@ static void ensure_ctx(void)
     CK(lpmb_create(&g_ctx, dev ? atoi(dev) : 0, nparticle, dim, lattice, nneighbors, nneighbors_AFEM + 1));
     const int N = nparticle, nn = nneighbors;
     set_params();
+    {   /* LPMB_DROPIN_FAST=1: the opt-in preconditioned mode of the solve (multigrid PCG, lpmb_mg.cu) -- NOT the parity path;
+         * full simple-cubic blocks only, solverCG() exits with the library's message on any other lattice */
+        const char *fm = getenv("LPMB_DROPIN_FAST");
+        g_fast = fm && atoi(fm) != 0;
+        if (g_fast)
+            CK(lpmb_set_param(g_ctx, "cg_precond", 1.0));
+    }
     up_d2("xyz", xyz, N, 3);
     up_d2("xyz_initial", xyz_initial, N, 3);
     up_d2("distance_initial", distance_initial, N, nn);
@@ -583,8 +591,10 @@ static void solve(double rel, double abs_tol, const char *who, int direct)
         rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 1, &iters);
     } else {
         CK(lpmb_matrix_from_upper_csr(g_ctx, K_global, (long long)K_pointer[N][1]));
+        if (g_fast) /* the preconditioner must not see the constrained DoFs: mask them (same iterates as the edited rows give) */
+            CK(lpmb_set_dof_mask(g_ctx, dispBC_index, fix_index));
         prof_lap(P_SOLVE_IMPORT, &pt);
-        rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, 0, &iters);
+        rc = lpmb_solve_cg(g_ctx, residual, disp, rel, abs_tol, n, g_fast, &iters);
     }
     prof_lap(P_SOLVE_CG, &pt);
     g_last_cg_iterations = iters;
