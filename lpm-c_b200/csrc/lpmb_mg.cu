@@ -218,7 +218,7 @@ mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, 
 template <int MODE>
 static int mg_launch_stencil(lpmb_ctx *c, const MGLevel &L, const double *u, const double *f, double *out, double omega, const double *done)
 {
-    const bool tiled = MODE != 2 && L.n >= 32768 && param(c, "mg_tiled", 1.0) != 0.0;
+    const bool tiled = MODE != 2 && (double)L.n >= param(c, "mg_tiled_min", 32768.0) && param(c, "mg_tiled", 1.0) != 0.0;
     if (tiled) {
         const size_t smem = (size_t)3 * MG_TILE_SITES * sizeof(double);
         // > 48 KB of dynamic shared memory: opt in (per device; cheap enough to repeat)
