@@ -39,6 +39,7 @@
 __constant__ int c_mg_off[MG_MAXOFF][3];
 __constant__ double c_mg_S[MG_MAXOFF][9];
 __constant__ int c_mg_noff;
+__constant__ int c_mg_nz[MG_MAXOFF];   // bit e set <=> S[k][e] != 0 (the lattice stencil is mostly rank-1 blocks with zero entries: skipped warp-uniformly)
 
 struct MGLevel {
     int nx = 0, ny = 0, nz = 0;
@@ -90,6 +91,21 @@ void lpmb_mg_touch(lpmb_ctx *c)   // K.val changed: the stencil is re-read at th
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------
+// a += S_k d with the zero entries of S_k skipped (the mask is the same for every thread: uniform branches)
+#define MG_ACC(k, d0, d1, d2, a0, a1, a2)                       \
+    do {                                                        \
+        const int nz__ = c_mg_nz[k];                            \
+        if (nz__ & 1) a0 = fma(c_mg_S[k][0], d0, a0);           \
+        if (nz__ & 2) a0 = fma(c_mg_S[k][1], d1, a0);           \
+        if (nz__ & 4) a0 = fma(c_mg_S[k][2], d2, a0);           \
+        if (nz__ & 8) a1 = fma(c_mg_S[k][3], d0, a1);           \
+        if (nz__ & 16) a1 = fma(c_mg_S[k][4], d1, a1);          \
+        if (nz__ & 32) a1 = fma(c_mg_S[k][5], d2, a1);          \
+        if (nz__ & 64) a2 = fma(c_mg_S[k][6], d0, a2);          \
+        if (nz__ & 128) a2 = fma(c_mg_S[k][7], d1, a2);         \
+        if (nz__ & 256) a2 = fma(c_mg_S[k][8], d2, a2);         \
+    } while (0)
+
 __device__ __forceinline__ int mg_axis_class(int i, int n) { return min(i, 2) + 3 * min(n - 1 - i, 2); }
 
 // MODE 0: out = u + omega * mask .* Dinv (f - A u)      (one damped block-Jacobi sweep, out != u)
@@ -119,9 +135,7 @@ mg_stencil_kernel(int nx, int ny, int nz, long long stride, double scale, const 
                 continue;
             const long long j = jx + (long long)nx * (jy + (long long)ny * jz);
             const double d0 = __ldg(u + j) - u0, d1 = __ldg(u + stride + j) - u1, d2 = __ldg(u + 2 * stride + j) - u2;
-            a0 = fma(c_mg_S[k][0], d0, fma(c_mg_S[k][1], d1, fma(c_mg_S[k][2], d2, a0)));
-            a1 = fma(c_mg_S[k][3], d0, fma(c_mg_S[k][4], d1, fma(c_mg_S[k][5], d2, a1)));
-            a2 = fma(c_mg_S[k][6], d0, fma(c_mg_S[k][7], d1, fma(c_mg_S[k][8], d2, a2)));
+            MG_ACC(k, d0, d1, d2, a0, a1, a2);
         }
         r0 -= scale * a0;
         r1 -= scale * a1;
@@ -196,9 +210,7 @@ mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, 
         }
         const int sl = me + ox + MG_SX * (oy + MG_SY * oz);
         const double d0 = mg_us[sl] - u0, d1 = mg_us[MG_TILE_SITES + sl] - u1, d2 = mg_us[2 * MG_TILE_SITES + sl] - u2;
-        a0 = fma(c_mg_S[k][0], d0, fma(c_mg_S[k][1], d1, fma(c_mg_S[k][2], d2, a0)));
-        a1 = fma(c_mg_S[k][3], d0, fma(c_mg_S[k][4], d1, fma(c_mg_S[k][5], d2, a1)));
-        a2 = fma(c_mg_S[k][6], d0, fma(c_mg_S[k][7], d1, fma(c_mg_S[k][8], d2, a2)));
+        MG_ACC(k, d0, d1, d2, a0, a1, a2);
     }
     double r0 = f[i] - scale * a0, r1 = f[stride + i] - scale * a1, r2 = f[2 * stride + i] - scale * a2;
     const double m0 = mask ? mask[i] : 1.0, m1 = mask ? mask[stride + i] : 1.0, m2 = mask ? mask[2 * stride + i] : 1.0;
@@ -218,7 +230,7 @@ mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, 
 template <int MODE>
 static int mg_launch_stencil(lpmb_ctx *c, const MGLevel &L, const double *u, const double *f, double *out, double omega, const double *done)
 {
-    const bool tiled = MODE != 2 && (double)L.n >= param(c, "mg_tiled_min", 32768.0) && param(c, "mg_tiled", 1.0) != 0.0;
+    const bool tiled = MODE != 2 && (double)L.n >= param(c, "mg_tiled_min", 1024.0) && param(c, "mg_tiled", 1.0) != 0.0;
     if (tiled) {
         const size_t smem = (size_t)3 * MG_TILE_SITES * sizeof(double);
         // > 48 KB of dynamic shared memory: opt in (per device; cheap enough to repeat)
@@ -230,6 +242,56 @@ static int mg_launch_stencil(lpmb_ctx *c, const MGLevel &L, const double *u, con
     }
     LPMB_LAUNCH_CHECK(c);
     return LPMB_OK;
+}
+
+// Coarsest level (<= MG_COARSE_MAX sites): all nu damped-Jacobi sweeps from u = 0 in ONE block, u ping-ponging in shared
+// memory -- the same arithmetic as nu launches of the plain kernel (MODE 2, then MODE 0), without 40 launch latencies.
+#define MG_COARSE_MAX 512
+__global__ void __launch_bounds__(256)
+mg_coarse_solve_kernel(int nx, int ny, int nz, long long stride, double scale, const double *__restrict__ dinv, const double *__restrict__ mask,
+                       const double *__restrict__ f, double *__restrict__ out, double omega, int nu, const double *__restrict__ done)
+{
+    __shared__ double us[2][3][MG_COARSE_MAX];
+    if (done && done[0] != 0.0)
+        return;
+    const int n = nx * ny * nz;
+    for (int sweep = 0; sweep < nu; sweep++) {
+        const int src = (sweep & 1) ^ 1, dst = sweep & 1;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int ix = i % nx, iy = (i / nx) % ny, iz = i / (nx * ny);
+            double r0 = f[i], r1 = f[stride + i], r2 = f[2 * stride + i];
+            double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+            if (sweep > 0) {
+                u0 = us[src][0][i], u1 = us[src][1][i], u2 = us[src][2][i];
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                const int noff = c_mg_noff;
+                for (int k = 0; k < noff; k++) {
+                    const int jx = ix + c_mg_off[k][0], jy = iy + c_mg_off[k][1], jz = iz + c_mg_off[k][2];
+                    if (jx < 0 || jx >= nx || jy < 0 || jy >= ny || jz < 0 || jz >= nz)
+                        continue;
+                    const int j = jx + nx * (jy + ny * jz);
+                    const double d0 = us[src][0][j] - u0, d1 = us[src][1][j] - u1, d2 = us[src][2][j] - u2;
+                    MG_ACC(k, d0, d1, d2, a0, a1, a2);
+                }
+                r0 -= scale * a0;
+                r1 -= scale * a1;
+                r2 -= scale * a2;
+            }
+            const double m0 = mask[i], m1 = mask[stride + i], m2 = mask[2 * stride + i];
+            r0 *= m0, r1 *= m1, r2 *= m2;
+            const double *D = dinv + 9 * (mg_axis_class(ix, nx) + 9 * (mg_axis_class(iy, ny) + 9 * mg_axis_class(iz, nz)));
+            us[dst][0][i] = u0 + omega * m0 * (D[0] * r0 + D[1] * r1 + D[2] * r2);
+            us[dst][1][i] = u1 + omega * m1 * (D[3] * r0 + D[4] * r1 + D[5] * r2);
+            us[dst][2][i] = u2 + omega * m2 * (D[6] * r0 + D[7] * r1 + D[8] * r2);
+        }
+        __syncthreads();
+    }
+    const int last = (nu - 1) & 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        out[i] = us[last][0][i];
+        out[stride + i] = us[last][1][i];
+        out[2 * stride + i] = us[last][2][i];
+    }
 }
 
 // 1-D interpolation weight of fine site f from coarse site X (coarse X sits on fine 2X; nc coarse sites)
@@ -479,6 +541,23 @@ static int mg_read_stencil(lpmb_ctx *c, MGState &M)
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_off, M.off, sizeof(M.off), 0, cudaMemcpyHostToDevice, c->stream));
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_noff, &M.noff, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+    {   // entries that are exactly zero (or rounding dust of the FD assembly relative to the block's largest entry) are skipped
+        static int nzmask[MG_MAXOFF];
+        for (int k = 0; k < MG_MAXOFF; k++)
+            nzmask[k] = 0;
+        for (int k = 0; k < M.noff; k++) {
+            double big = 0.0;
+            for (int e = 0; e < 9; e++)
+                big = std::max(big, std::fabs(M.S[k][e]));
+            for (int e = 0; e < 9; e++)
+                if (std::fabs(M.S[k][e]) > 1e-9 * big)
+                    nzmask[k] |= 1 << e;
+                else
+                    M.S[k][e] = 0.0;   // keep the host copy (diagonal blocks) consistent with what the kernels apply
+        }
+        LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_nz, nzmask, sizeof(nzmask), 0, cudaMemcpyHostToDevice, c->stream));
+        LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
+    }
     // inverse diagonal blocks per boundary class and level: D = -scale * sum of the present off-diagonal blocks
     std::vector<double> tab((size_t)729 * 9);
     for (int l = 0; l < M.nlev; l++) {
@@ -552,8 +631,14 @@ static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const d
 static int mg_vcycle(lpmb_ctx *c, MGState &M, int l, const double *done)
 {
     MGLevel &L = M.lev[l];
-    if (l == M.nlev - 1)
+    if (l == M.nlev - 1) {
+        if (L.n <= MG_COARSE_MAX && param(c, "mg_coarse_fused", 1.0) != 0.0) {
+            mg_coarse_solve_kernel<<<1, 256, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, L.scale, L.dinv, L.mask, L.f, L.u, M.omega, M.nu_coarse, done);
+            LPMB_LAUNCH_CHECK(c);
+            return LPMB_OK;
+        }
         return mg_smooth(c, M, l, M.nu_coarse, true, done);
+    }
     LPMB_TRY(mg_smooth(c, M, l, M.nu, true, done));
     LPMB_TRY(mg_launch_stencil<1>(c, L, L.u, L.f, L.res, 0.0, done));
     MGLevel &C = M.lev[l + 1];

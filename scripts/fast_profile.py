@@ -1,0 +1,29 @@
+"""one fast-mode solve (multigrid PCG) between cudaProfilerStart/Stop: run under
+   ncu --profile-from-start off --metrics gpu__time_duration.sum --csv ... python scripts/fast_profile.py [n=216]"""
+import ctypes, importlib, sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import bench
+lpm = importlib.import_module("lpm-c_b200")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 216
+c, info = bench.build_workload(lpm, n, 0, bricks=n >= 64)
+c.set_dof_mask(c.get_field("dispBC_index"), c.get_field("fix_index"))
+c.set_params(cg_precond=1.0)
+rt = None
+for name in ("libcudart.so", "libcudart.so.12"):
+    try:
+        rt = ctypes.CDLL(name); break
+    except OSError:
+        pass
+def solve():
+    c.copy_field("residual", "residual_save")
+    return c.solve_cg_device(update_xyz=False)
+solve()
+c.synchronize()
+if rt: rt.cudaProfilerStart()
+it, ok = solve()
+c.synchronize()
+if rt: rt.cudaProfilerStop()
+print("fast-mode solve:", it, "PCG iterations", ok)
+c.close()
