@@ -39,7 +39,6 @@
 __constant__ int c_mg_off[MG_MAXOFF][3];
 __constant__ double c_mg_S[MG_MAXOFF][9];
 __constant__ int c_mg_noff;
-__constant__ int c_mg_nz[MG_MAXOFF];   // bit e set <=> S[k][e] != 0 (the lattice stencil is mostly rank-1 blocks with zero entries: skipped warp-uniformly)
 
 struct MGLevel {
     int nx = 0, ny = 0, nz = 0;
@@ -91,19 +90,14 @@ void lpmb_mg_touch(lpmb_ctx *c)   // K.val changed: the stencil is re-read at th
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------
-// a += S_k d with the zero entries of S_k skipped (the mask is the same for every thread: uniform branches)
-#define MG_ACC(k, d0, d1, d2, a0, a1, a2)                       \
-    do {                                                        \
-        const int nz__ = c_mg_nz[k];                            \
-        if (nz__ & 1) a0 = fma(c_mg_S[k][0], d0, a0);           \
-        if (nz__ & 2) a0 = fma(c_mg_S[k][1], d1, a0);           \
-        if (nz__ & 4) a0 = fma(c_mg_S[k][2], d2, a0);           \
-        if (nz__ & 8) a1 = fma(c_mg_S[k][3], d0, a1);           \
-        if (nz__ & 16) a1 = fma(c_mg_S[k][4], d1, a1);          \
-        if (nz__ & 32) a1 = fma(c_mg_S[k][5], d2, a1);          \
-        if (nz__ & 64) a2 = fma(c_mg_S[k][6], d0, a2);          \
-        if (nz__ & 128) a2 = fma(c_mg_S[k][7], d1, a2);         \
-        if (nz__ & 256) a2 = fma(c_mg_S[k][8], d2, a2);         \
+// a += S_k d.  (Skipping the zero entries of the mostly rank-1 stencil blocks with warp-uniform branches was measured and
+// is SLOWER -- 415 instead of 335 us per tiled pass on average, profiles/r02l_fast_launches.csv: the dense form keeps the
+// constant-bank operands fused into nine back-to-back DFMAs.)
+#define MG_ACC(k, d0, d1, d2, a0, a1, a2)                                                        \
+    do {                                                                                         \
+        a0 = fma(c_mg_S[k][0], d0, fma(c_mg_S[k][1], d1, fma(c_mg_S[k][2], d2, a0)));            \
+        a1 = fma(c_mg_S[k][3], d0, fma(c_mg_S[k][4], d1, fma(c_mg_S[k][5], d2, a1)));            \
+        a2 = fma(c_mg_S[k][6], d0, fma(c_mg_S[k][7], d1, fma(c_mg_S[k][8], d2, a2)));            \
     } while (0)
 
 __device__ __forceinline__ int mg_axis_class(int i, int n) { return min(i, 2) + 3 * min(n - 1 - i, 2); }
@@ -541,23 +535,6 @@ static int mg_read_stencil(lpmb_ctx *c, MGState &M)
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_off, M.off, sizeof(M.off), 0, cudaMemcpyHostToDevice, c->stream));
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_noff, &M.noff, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
-    {   // entries that are exactly zero (or rounding dust of the FD assembly relative to the block's largest entry) are skipped
-        static int nzmask[MG_MAXOFF];
-        for (int k = 0; k < MG_MAXOFF; k++)
-            nzmask[k] = 0;
-        for (int k = 0; k < M.noff; k++) {
-            double big = 0.0;
-            for (int e = 0; e < 9; e++)
-                big = std::max(big, std::fabs(M.S[k][e]));
-            for (int e = 0; e < 9; e++)
-                if (std::fabs(M.S[k][e]) > 1e-9 * big)
-                    nzmask[k] |= 1 << e;
-                else
-                    M.S[k][e] = 0.0;   // keep the host copy (diagonal blocks) consistent with what the kernels apply
-        }
-        LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_nz, nzmask, sizeof(nzmask), 0, cudaMemcpyHostToDevice, c->stream));
-        LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
-    }
     // inverse diagonal blocks per boundary class and level: D = -scale * sum of the present off-diagonal blocks
     std::vector<double> tab((size_t)729 * 9);
     for (int l = 0; l < M.nlev; l++) {

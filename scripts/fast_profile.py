@@ -19,11 +19,17 @@ for name in ("libcudart.so", "libcudart.so.12"):
 def solve():
     c.copy_field("residual", "residual_save")
     return c.solve_cg_device(update_xyz=False)
+whole_step = len(sys.argv) > 2 and sys.argv[2] == "step"   # profile a whole Newton iteration (bench.one_step) instead of the solve alone
 solve()
+bench.one_step(c)
 c.synchronize()
 if rt: rt.cudaProfilerStart()
-it, ok = solve()
+if whole_step:
+    it, nr = bench.one_step(c)
+    ok = True
+else:
+    it, ok = solve()
 c.synchronize()
 if rt: rt.cudaProfilerStop()
-print("fast-mode solve:", it, "PCG iterations", ok)
+print("fast-mode", "Newton iteration:" if whole_step else "solve:", it, "PCG iterations", ok)
 c.close()
