@@ -39,6 +39,7 @@
 __constant__ int c_mg_off[MG_MAXOFF][3];
 __constant__ double c_mg_S[MG_MAXOFF][9];
 __constant__ int c_mg_noff;
+__constant__ int c_mg_delta[MG_MAXOFF];   // shared-memory slot offset of each stencil offset inside the 36 x 8 x 8 tile
 
 struct MGLevel {
     int nx = 0, ny = 0, nz = 0;
@@ -161,6 +162,7 @@ mg_stencil_kernel(int nx, int ny, int nz, long long stride, double scale, const 
 #define MG_SY (MG_TY + 4)
 #define MG_SZ (MG_TZ + 4)
 #define MG_TILE_SITES (MG_SX * MG_SY * MG_SZ)
+#define MG_SC_NOFF 60   // off-diagonal blocks of an interior simple-cubic block row (61 conn entries minus the particle itself)
 template <int MODE>
 __global__ void __launch_bounds__(MG_TX * MG_TY * MG_TZ)
 mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, const double *__restrict__ dinv, const double *__restrict__ mask,
@@ -195,16 +197,27 @@ mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, 
     const bool interior = x0 >= 2 && x0 + MG_TX + 2 <= nx && y0 >= 2 && y0 + MG_TY + 2 <= ny && z0 >= 2 && z0 + MG_TZ + 2 <= nz;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     const int noff = c_mg_noff;
-    for (int k = 0; k < noff; k++) {
-        const int ox = c_mg_off[k][0], oy = c_mg_off[k][1], oz = c_mg_off[k][2];
-        if (!interior) {
-            const int jx = ix + ox, jy = iy + oy, jz = iz + oz;
-            if (jx < 0 || jx >= nx || jy < 0 || jy >= ny || jz < 0 || jz >= nz)
-                continue;
+    if (interior && noff == MG_SC_NOFF) {
+        // the common case (simple-cubic 2-hop stencil, tile away from the faces): fully unrolled, slot offsets and stencil
+        // entries are constant-bank operands of the instructions -- no index arithmetic, no bounds tests
+#pragma unroll
+        for (int k = 0; k < MG_SC_NOFF; k++) {
+            const int sl = me + c_mg_delta[k];
+            const double d0 = mg_us[sl] - u0, d1 = mg_us[MG_TILE_SITES + sl] - u1, d2 = mg_us[2 * MG_TILE_SITES + sl] - u2;
+            MG_ACC(k, d0, d1, d2, a0, a1, a2);
         }
-        const int sl = me + ox + MG_SX * (oy + MG_SY * oz);
-        const double d0 = mg_us[sl] - u0, d1 = mg_us[MG_TILE_SITES + sl] - u1, d2 = mg_us[2 * MG_TILE_SITES + sl] - u2;
-        MG_ACC(k, d0, d1, d2, a0, a1, a2);
+    } else {
+        for (int k = 0; k < noff; k++) {
+            const int ox = c_mg_off[k][0], oy = c_mg_off[k][1], oz = c_mg_off[k][2];
+            if (!interior) {
+                const int jx = ix + ox, jy = iy + oy, jz = iz + oz;
+                if (jx < 0 || jx >= nx || jy < 0 || jy >= ny || jz < 0 || jz >= nz)
+                    continue;
+            }
+            const int sl = me + ox + MG_SX * (oy + MG_SY * oz);
+            const double d0 = mg_us[sl] - u0, d1 = mg_us[MG_TILE_SITES + sl] - u1, d2 = mg_us[2 * MG_TILE_SITES + sl] - u2;
+            MG_ACC(k, d0, d1, d2, a0, a1, a2);
+        }
     }
     double r0 = f[i] - scale * a0, r1 = f[stride + i] - scale * a1, r2 = f[2 * stride + i] - scale * a2;
     const double m0 = mask ? mask[i] : 1.0, m1 = mask ? mask[stride + i] : 1.0, m2 = mask ? mask[2 * stride + i] : 1.0;
@@ -535,6 +548,12 @@ static int mg_read_stencil(lpmb_ctx *c, MGState &M)
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_off, M.off, sizeof(M.off), 0, cudaMemcpyHostToDevice, c->stream));
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
     LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_noff, &M.noff, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+    {
+        static int delta[MG_MAXOFF];
+        for (int k = 0; k < MG_MAXOFF; k++)
+            delta[k] = k < M.noff ? M.off[k][0] + MG_SX * (M.off[k][1] + MG_SY * M.off[k][2]) : 0;
+        LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_delta, delta, sizeof(delta), 0, cudaMemcpyHostToDevice, c->stream));
+    }
     // inverse diagonal blocks per boundary class and level: D = -scale * sum of the present off-diagonal blocks
     std::vector<double> tab((size_t)729 * 9);
     for (int l = 0; l < M.nlev; l++) {

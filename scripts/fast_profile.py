@@ -32,4 +32,19 @@ else:
 c.synchronize()
 if rt: rt.cudaProfilerStop()
 print("fast-mode", "Newton iteration:" if whole_step else "solve:", it, "PCG iterations", ok)
+if len(sys.argv) > 3 and sys.argv[3] == "breakdown":
+    import time
+    def timed(label, fn, reps=3):
+        c.synchronize(); t0 = time.perf_counter()
+        for _ in range(reps): fn()
+        c.synchronize(); print(f"  {label:42s} {(time.perf_counter()-t0)/reps*1e3:9.3f} ms")
+    for mode in (1.0, 0.0):
+        c.set_params(cg_precond=mode)
+        print("cg_precond =", mode)
+        timed("one_step (restore + newton_iteration)", lambda: bench.one_step(c))
+        timed("copy_field xyz + residual", lambda: (c.copy_field("xyz", "xyz_save"), c.copy_field("residual", "residual_save")))
+        timed("switch_state(0)", lambda: c.switch_state(0))
+        timed("solve_cg_device(update_xyz=True)", lambda: (c.copy_field("residual", "residual_save"), c.solve_cg_device(update_xyz=True)), reps=2)
+        timed("bond_force(0)", lambda: c.bond_force(0))
+        timed("update_rr", lambda: c.update_rr())
 c.close()
