@@ -55,3 +55,20 @@ def test_two_gpu_slabs_with_lazy_halo_wait(lpm):
     env = dict(os.environ, LPMB_BRICK_LAZY_WAIT="1")
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "dist_check_lite.py"), "40", "2"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "DIST_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ct_specimen_on_slabs_matches_serial_reference(lpm, world):
+    """BASELINE config 5 AS SHIPPED (examples/CT_sc_ductile_nonlocal.c: carved, pre-cracked compact-tension specimen, 75 030
+    particles = 15 z-layers of 5 002) on 2 and 3 z-slabs over the C ABI (tests/dist_ct_check.py): Newton iteration counts, the
+    CG iteration count of every solve and the printed residual / reaction norms of three load steps equal the SERIAL all-CPU
+    run of the unchanged example (tests/golden/c5src_log.txt); the device-built neighbour lists of every slab equal the
+    reference's.  Geometry / types / initial crack come from the reference's host code (oracle/_ref) in the parent."""
+    from oracle import ref as oref
+    if lpm.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if not oref.available():
+        pytest.skip("oracle/_ref/liblpmc_ref.so not built")
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "dist_ct_check.py"), str(world), "3"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "DIST_CT_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    print(r.stdout[-600:])
