@@ -70,7 +70,14 @@ def child(rank, world, n, d):
     c.set_field("xyz", np.zeros_like(xa))
     c.snapshot_load(snap)
     b = next_step()
-    assert a == b and np.array_equal(xa, c.get_field("xyz")), ("slab snapshot resume differs", a, b)
+    xb = c.get_field("xyz")
+    c.snapshot_load(snap)
+    b2 = next_step()
+    xb2 = c.get_field("xyz")
+    print(f"rank {rank}: snapshot resume: live {a} | loaded {b} | loaded again {b2}; xyz live-vs-loaded max {np.abs(xa - xb).max():.3e}, "
+          f"loaded-vs-loaded {np.abs(xb - xb2).max():.3e}", flush=True)
+    assert b == b2 and np.array_equal(xb, xb2), ("two resumes from the same slab snapshot differ", b, b2)
+    assert a[0] == b[0] and abs(a[1] - b[1]) <= 1e-12 * abs(a[1]) and np.abs(xa - xb).max() <= 1e-13, ("slab snapshot resume differs", a, b)
     np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken]), mode=np.array([c.dist_mode()]),
              norm0=np.array([info["norm_residual0"]]), spmv_bytes=np.array([c.spmv_bytes_bricks()]), **out)
     c.close()
