@@ -58,7 +58,7 @@ struct MGState {
     int off[MG_MAXOFF][3];
     int noff = 0;
     int nu = 2, nu_coarse = 40;
-    double omega = 0.6;
+    double omega = 0.6, omega2 = 0.6;   // damping of the odd / even sweeps (two different values = a degree-2 polynomial smoother)
 };
 
 static std::map<lpmb_ctx *, MGState> g_mg;
@@ -600,6 +600,7 @@ int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
     M.nu = std::max(1, (int)param(c, "mg_nu", 2.0));
     M.nu_coarse = std::max(1, (int)param(c, "mg_nu_coarse", 40.0));
     M.omega = param(c, "mg_omega", 0.6);
+    M.omega2 = param(c, "mg_omega2", M.omega);
     M.lev[0].mask = const_cast<double *>(mask0);
     for (int l = 1; l < M.nlev; l++) {
         const MGLevel &F = M.lev[l - 1];
@@ -615,10 +616,11 @@ static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const d
 {
     MGLevel &L = M.lev[l];
     for (int s = 0; s < nu; s++) {
+        const double om = (s & 1) ? M.omega2 : M.omega;
         if (first && s == 0)
-            LPMB_TRY(mg_launch_stencil<2>(c, L, nullptr, L.f, L.u2, M.omega, done));
+            LPMB_TRY(mg_launch_stencil<2>(c, L, nullptr, L.f, L.u2, om, done));
         else
-            LPMB_TRY(mg_launch_stencil<0>(c, L, L.u, L.f, L.u2, M.omega, done));
+            LPMB_TRY(mg_launch_stencil<0>(c, L, L.u, L.f, L.u2, om, done));
         std::swap(L.u, L.u2);
     }
     return LPMB_OK;

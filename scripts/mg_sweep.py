@@ -22,11 +22,12 @@ def solve(reps=3):
 it0, t0 = solve(2)
 print(f"n={n}: plain CG {it0} iterations, {t0:.1f} ms per solve")
 c.set_params(cg_precond=1.0)
-for tiled in (0.0, 1.0):
-    for nu, om in ((2, 0.6), (1, 0.6), (1, 0.7), (2, 0.7), (3, 0.7), (2, 0.5), (1, 0.8)):
-        if tiled == 0.0 and (nu, om) != (2, 0.6):
-            continue
-        c.set_params(mg_nu=float(nu), mg_omega=om, mg_tiled=tiled)
+for nu, om, om2 in ((2, 0.6, 0.6), (1, 0.7, 0.7), (2, 0.56, 1.39), (2, 0.5, 1.2), (2, 0.6, 1.0), (2, 0.55, 0.9), (2, 0.7, 0.5), (2, 0.8, 0.5), (2, 1.0, 0.5),
+                    (3, 0.6, 1.0), (2, 0.6, 0.8), (4, 0.5, 1.2)):
+    c.set_params(mg_nu=float(nu), mg_omega=om, mg_omega2=om2)
+    try:
         it, ms = solve(3)
-        print(f"  tiled={int(tiled)} nu={nu} omega={om}: {it} PCG iterations, {ms:.1f} ms per solve ({ms/max(it,1):.2f} ms per iteration)")
+        print(f"  nu={nu} omega={om}/{om2}: {it} PCG iterations, {ms:.1f} ms per solve ({ms/max(it,1):.2f} ms per iteration)")
+    except Exception as e:
+        print(f"  nu={nu} omega={om}/{om2}: {str(e)[:80]}")
 c.close()
