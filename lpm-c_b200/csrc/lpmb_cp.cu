@@ -219,7 +219,14 @@ cp_miehe_kernel(int N, int Np, int nn, CPParams P, const int *__restrict__ nbi_g
                     r[m] = jact[m] * (rss - xgy[m] * term1);
                     rrhs[m] = r[m];
                 }
-                for (int m = 0; m < S; m++)
+                for (int m = 0; m < S; m++) {
+                    // the two powers of the viscous term depend on the row only: once per active row instead of once per
+                    // active PAIR (same arguments -> the same bits; pow is ~half of this kernel's instructions otherwise)
+                    double pw_a = 0.0, pw_b = 0.0;
+                    if (jact[m] == 1) {
+                        pw_a = pow(1. + P.eta * gamma[m] / P.dtime, (1. - P.p) / P.p);
+                        pw_b = pow(1. + P.eta * gamma[m] / P.dtime, (1. / P.p));
+                    }
                     for (int nn2 = 0; nn2 < S; nn2++) {
                         double v = (m == nn2) ? 1.0 : 0.0;
                         if (jact[m] == 1 && jact[nn2] == 1) {
@@ -236,13 +243,14 @@ cp_miehe_kernel(int N, int Np, int nn, CPParams P, const int *__restrict__ nbi_g
                                     hd = P.q * h_hatp * gamma[d];
                                 h_star += jact[d] * hd;
                             }
-                            const double term1 = xgy[m] * (P.eta / P.p / P.dtime * pow(1. + P.eta * gamma[m] / P.dtime, (1. - P.p) / P.p));
-                            const double term2 = h_star * pow(1. + P.eta * gamma[m] / P.dtime, (1. / P.p));
+                            const double term1 = xgy[m] * (P.eta / P.p / P.dtime * pw_a);
+                            const double term2 = h_star * pw_b;
                             const double cab = Cab[(size_t)(m * S + nn2) * Npz + i];
                             v = (m == nn2) ? cab + term1 + term2 : cab + term2;
                         }
                         D[m * SMAX + nn2] = v;
                     }
+                }
                 if (dgesv_rowmajor<SMAX>(S, D, rrhs) != 0) {
                     atomicExch(err, i + 1);  // the reference prints and exit(1)s (constitutive.c:1216-1221)
                     return;
