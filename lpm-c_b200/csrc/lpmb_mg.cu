@@ -15,8 +15,9 @@
 //                 the sum of the off-diagonal blocks that are present, which is what translation invariance of the real
 //                 tangent gives (free surfaces handled); the factor 2^l is the rediscretised operator on spacing 2^l h
 //                 (bond stiffness ~ radius, stiffness.c:179-185), equal to the Galerkin operator on smooth fields,
-//   smoother   =  damped block-Jacobi (3x3 diagonal blocks inverted per boundary class on the host), nu sweeps before and
-//                 after the coarse correction, R = P^T with trilinear P: a symmetric positive definite V-cycle,
+//   smoother   =  damped block-Jacobi (3x3 diagonal blocks inverted per boundary class on the host), nu = 2 sweeps before
+//                 and after the coarse correction with the two damping factors of the degree-2 Chebyshev polynomial
+//                 (0.56, 1.39), R = P^T with trilinear P: a symmetric positive definite V-cycle,
 //   constraints: the DoF mask of the solve on level 0; a coarse DoF is constrained when any fine DoF in its
 //                 interpolation support is (Dirichlet faces stay Dirichlet faces).
 //
@@ -58,7 +59,7 @@ struct MGState {
     int off[MG_MAXOFF][3];
     int noff = 0;
     int nu = 2, nu_coarse = 40;
-    double omega = 0.6, omega2 = 0.6;   // damping of the odd / even sweeps (two different values = a degree-2 polynomial smoother)
+    double omega = 0.56, omega2 = 1.39;   // damping of the odd / even sweeps (two different values = a degree-2 polynomial smoother)
 };
 
 static std::map<lpmb_ctx *, MGState> g_mg;
@@ -599,8 +600,11 @@ int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
         LPMB_TRY(mg_read_stencil(c, M));
     M.nu = std::max(1, (int)param(c, "mg_nu", 2.0));
     M.nu_coarse = std::max(1, (int)param(c, "mg_nu_coarse", 40.0));
-    M.omega = param(c, "mg_omega", 0.6);
-    M.omega2 = param(c, "mg_omega2", M.omega);
+    // two damping factors = the degree-2 Chebyshev smoother for D^-1 A on [lambda_max / 4, lambda_max], lambda_max = 2
+    // (roots 1.25 -+ 0.75 cos(pi/4)): 9 instead of 11 PCG iterations at 216^3 against omega = 0.6 twice
+    // (profiles/r02r_mg_sweep_n216.log); mg_omega2 defaults to mg_omega when only that one is set
+    M.omega = param(c, "mg_omega", 0.56);
+    M.omega2 = param(c, "mg_omega2", c->params.count("mg_omega") ? M.omega : 1.39);
     M.lev[0].mask = const_cast<double *>(mask0);
     for (int l = 1; l < M.nlev; l++) {
         const MGLevel &F = M.lev[l - 1];
