@@ -58,11 +58,13 @@ struct MGState {
     double S[MG_MAXOFF][9];
     int off[MG_MAXOFF][3];
     int noff = 0;
+    int delta[MG_MAXOFF];
     int nu = 2, nu_coarse = 40;
     double omega = 0.56, omega2 = 1.39;   // damping of the odd / even sweeps (two different values = a degree-2 polynomial smoother)
 };
 
 static std::map<lpmb_ctx *, MGState> g_mg;
+static lpmb_ctx *g_mg_const_owner[64] = {nullptr};   // per device: the context whose stencil sits in __constant__ memory
 
 void lpmb_mg_release(lpmb_ctx *c)
 {
@@ -70,6 +72,8 @@ void lpmb_mg_release(lpmb_ctx *c)
     if (it == g_mg.end())
         return;
     MGState &M = it->second;
+    if (c->device >= 0 && c->device < 64 && g_mg_const_owner[c->device] == c)
+        g_mg_const_owner[c->device] = nullptr;
     for (int l = 0; l < M.nlev; l++) {
         MGLevel &L = M.lev[l];
         cudaFree(L.dinv);
@@ -516,6 +520,23 @@ static int mg_build_levels(lpmb_ctx *c, MGState &M)
     return LPMB_OK;
 }
 
+// The stencil lives in __constant__ memory, i.e. ONCE per device: the context that uploaded last is remembered, and a
+// solve of any other context (a second lattice in the same process) uploads its own copy first.
+
+static int mg_upload_constants(lpmb_ctx *c, MGState &M)
+{
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_off, M.off, sizeof(M.off), 0, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_noff, &M.noff, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < MG_MAXOFF; k++)
+        M.delta[k] = k < M.noff ? M.off[k][0] + MG_SX * (M.off[k][1] + MG_SY * M.off[k][2]) : 0;
+    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_delta, M.delta, sizeof(M.delta), 0, cudaMemcpyHostToDevice, c->stream));
+    LPMB_CUDA(cudaStreamSynchronize(c->stream));   // the host copies may change before an asynchronous upload has read them
+    if (c->device >= 0 && c->device < 64)
+        g_mg_const_owner[c->device] = c;
+    return LPMB_OK;
+}
+
 // stencil = the off-diagonal blocks of the block row of the centre particle (re-read after every assembly)
 static int mg_read_stencil(lpmb_ctx *c, MGState &M)
 {
@@ -546,15 +567,7 @@ static int mg_read_stencil(lpmb_ctx *c, MGState &M)
             M.S[M.noff][e] = val[(size_t)k * 9 + e];
         M.noff++;
     }
-    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_off, M.off, sizeof(M.off), 0, cudaMemcpyHostToDevice, c->stream));
-    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_S, M.S, sizeof(M.S), 0, cudaMemcpyHostToDevice, c->stream));
-    LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_noff, &M.noff, sizeof(int), 0, cudaMemcpyHostToDevice, c->stream));
-    {
-        static int delta[MG_MAXOFF];
-        for (int k = 0; k < MG_MAXOFF; k++)
-            delta[k] = k < M.noff ? M.off[k][0] + MG_SX * (M.off[k][1] + MG_SY * M.off[k][2]) : 0;
-        LPMB_CUDA(cudaMemcpyToSymbolAsync(c_mg_delta, delta, sizeof(delta), 0, cudaMemcpyHostToDevice, c->stream));
-    }
+    LPMB_TRY(mg_upload_constants(c, M));
     // inverse diagonal blocks per boundary class and level: D = -scale * sum of the present off-diagonal blocks
     std::vector<double> tab((size_t)729 * 9);
     for (int l = 0; l < M.nlev; l++) {
@@ -598,6 +611,8 @@ int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
     LPMB_REQUIRE(c->K.values_ready, LPMB_ERR_STATE, "stiffness matrix not available");
     if (!M.ready)
         LPMB_TRY(mg_read_stencil(c, M));
+    else if (c->device < 0 || c->device >= 64 || g_mg_const_owner[c->device] != c)
+        LPMB_TRY(mg_upload_constants(c, M));   // another context used the constant bank since
     M.nu = std::max(1, (int)param(c, "mg_nu", 2.0));
     M.nu_coarse = std::max(1, (int)param(c, "mg_nu_coarse", 40.0));
     // two damping factors = the degree-2 Chebyshev smoother for D^-1 A on [lambda_max / 4, lambda_max], lambda_max = 2

@@ -331,6 +331,41 @@ def test_fast_mode_tiled_stencil_kernel_equals_plain_kernel(lpm):
     c.close()
 
 
+def test_fast_mode_two_contexts_interleaved(lpm):
+    """the multigrid stencil sits in __constant__ memory, i.e. once per device: two lattices with DIFFERENT tangents solved
+    alternately in one process must each see their own stencil (the context that uploaded last is tracked and the other one
+    re-uploads): the second solve of context A equals its first bit for bit although context B solved in between"""
+    import bench
+    a, _ = bench.build_workload(lpm, 24, 0, bricks=False)
+    saved = dict(bench.PHYS)
+    try:
+        bench.PHYS.update(E0=210e3, mu0=0.2)            # another material -> another 61-point stencil
+        b, _ = bench.build_workload(lpm, 20, 0, bricks=False)
+    finally:
+        bench.PHYS.clear()
+        bench.PHYS.update(saved)
+    out = []
+    for c in (a, b):
+        c.set_dof_mask(c.get_field("dispBC_index"), c.get_field("fix_index"))
+        c.set_params(cg_precond=1.0)
+
+    def solve(c):
+        c.copy_field("residual", "residual_save")
+        it, ok = c.solve_cg_device(update_xyz=False)
+        assert ok
+        return it, c.get_field("disp")
+
+    ia1, da1 = solve(a)
+    ib1, db1 = solve(b)
+    ia2, da2 = solve(a)
+    ib2, db2 = solve(b)
+    assert ia1 == ia2 and np.array_equal(da1, da2), (ia1, ia2)
+    assert ib1 == ib2 and np.array_equal(db1, db2), (ib1, ib2)
+    assert ia1 <= 15 and ib1 <= 15, (ia1, ib1)
+    a.close()
+    b.close()
+
+
 def test_fast_mode_fails_loudly_when_not_eligible(lpm, golden):
     """cg_precond = 1 on a lattice the multigrid hierarchy does not cover (here: a block only 4 sites thick, so no interior
     61-point stencil row exists) must return an error that names the parameter -- no silent fall back to another solver"""
