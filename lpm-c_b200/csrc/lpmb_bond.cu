@@ -458,6 +458,227 @@ j2_return_map_kernel(BondView v, double V, double J2_H, double J2_xi, const doub
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused passes of the plmode-0 dispatcher (computeBondForceGeneral(0, t), constitutive.c:88-146 + 466-686 + lpm_basic.c:53-125).
+// The five separate kernels re-read the per-bond arrays 3.7 times (78 GB of DRAM traffic for 21 GB of algorithmic bytes at
+// 10 M particles, profiles/README.md).  Every pass is a pure per-particle function, so two kernels suffice:
+//   j2_fused_kernel          = geometry(dLp[0]) -> return map -> geometry(dLp[2]): the first geometry stays in registers /
+//                              local memory (its global outputs would be overwritten by the second one anyway),
+//   j2_force_stress_kernel   = averaged bond force + Pin + computeStress (needs the neighbours' new dL / shell sums, hence
+//                              the kernel boundary).
+// Same expressions in the same order as the separate kernels (compiled with -fmad=false): bit-identical outputs, which the
+// golden tests of the dispatcher check.  The separate kernels remain for plmode 1 / 3 / 6 and the per-particle entry points.
+// ---------------------------------------------------------------------------------------------
+#define J2F_MAXNN 18
+__global__ void __launch_bounds__(BT)
+j2_fused_kernel(BondView v, double V, double J2_H, double J2_xi, const double *__restrict__ Ce, const int *__restrict__ type,
+                const double *__restrict__ sigmay, const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ w,
+                const double *__restrict__ broken, const double *__restrict__ L0, const double *__restrict__ dLp0,
+                const double *__restrict__ beta0, const double *__restrict__ alpha0, double *__restrict__ dLp2, double *__restrict__ beta2,
+                double *__restrict__ alpha2, double *__restrict__ ddLp, double *__restrict__ dlambda, int *__restrict__ pl_flag,
+                double *__restrict__ dL, double *__restrict__ csx, double *__restrict__ csy, double *__restrict__ csz, double *__restrict__ dLt,
+                double *__restrict__ TdLt)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const int n = v.nbi[i], nb_i = v.nb[i];
+    const double xi = v.xyz[i], yi = v.xyz[Np + i], zi = v.xyz[2 * Np + i];
+    double dis_[J2F_MAXNN], d_[J2F_MAXNN], cx_[J2F_MAXNN], cy_[J2F_MAXNN], cz_[J2F_MAXNN];
+    // ---- geometry with the slot-[0] plastic stretch (geometry_kernel<0>)
+    double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const double dx = xi - v.xyz[nj], dy = yi - v.xyz[Np + nj], dz = zi - v.xyz[2 * Np + nj];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        double d = dis - L0[e];
+        d -= dLp0[e];
+        d *= broken[e];
+        const double td = Tv[e] * d;
+        if (v.nsign[e] == 0) {
+            t0 += d;
+            T0 += td;
+        } else {
+            t1 += d;
+            T1 += td;
+        }
+        dis_[j] = dis;
+        d_[j] = d;
+        cx_[j] = dx / dis;
+        cy_[j] = dy / dis;
+        cz_[j] = dz / dis;
+    }
+    // ---- return map (j2_return_map_kernel)
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int s = v.nsign[e];
+        double Fij = 2.0 * Kn[e] * d_[j] + (s ? T1 : T0) + Tv[e] * (s ? t1 : t0);
+        Fij *= w[e];
+        const double of = opp_flag(nb_i, v.nn, v.opp[e], broken, Np, i);
+        const double cx = cx_[j], cy = cy_[j], cz = cz_[j];
+        const double pre = of / V * L0[e] * Fij;
+        st[0] += pre * cx * cx;
+        st[1] += pre * cy * cy;
+        st[2] += pre * cz * cz;
+        st[3] += pre * cy * cz;
+        st[4] += pre * cx * cz;
+        st[5] += pre * cx * cy;
+    }
+    const double temp = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+    st[0] -= temp;
+    st[1] -= temp;
+    st[2] -= temp;
+    double beta[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        beta[q] = beta0[(size_t)q * Np + i];
+        st[q] -= beta[q];
+    }
+    double seq = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        if (q < 3)
+            seq += st[q] * st[q];
+        else
+            seq += 2.0 * st[q] * st[q];
+    }
+    seq = sqrt(3.0 / 2.0 * seq);
+    double alpha = alpha0[i];
+    double dl = 0.0;
+    const double yield_func = seq - (sigmay[i] + (1.0 - J2_xi) * J2_H * alpha);
+    if (yield_func > 0.0) {
+        pl_flag[i] = 1;
+        dl = yield_func / (3 * Ce[3 * type[i] + 2] + J2_H);
+    }
+    alpha += dl;
+    double dpl[6] = {0, 0, 0, 0, 0, 0};
+    if (fabs(seq) > LPMB_EPS) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            dpl[q] = dl * 1.5 * st[q] / seq;
+            beta[q] += 2. / 3. * J2_xi * J2_H * dpl[q];
+        }
+    }
+    // ---- new plastic stretch, then geometry with it (geometry_kernel<0> on slot [2]); unit vectors and distances are the same
+    t0 = t1 = T0 = T1 = 0;
+    for (int j = 0; j < v.nn; j++) {
+        const size_t e = (size_t)j * Np + i;
+        double xd = dLp0[e];
+        const double b = broken[e];
+        if (j < n) {
+            const double cx = cx_[j], cy = cy_[j], cz = cz_[j];
+            double dd = L0[e] * (dpl[0] * cx * cx + dpl[1] * cy * cy + dpl[2] * cz * cz + 2 * dpl[3] * cy * cz + 2 * dpl[4] * cx * cz +
+                                 2 * dpl[5] * cx * cy);
+            dd *= b;
+            ddLp[e] = dd;
+            xd += dd;
+        }
+        const double p2 = b * xd;  // constitutive.c:670-671
+        dLp2[e] = p2;
+        if (j < n) {
+            double d = dis_[j] - L0[e];
+            d -= p2;
+            d *= b;
+            dL[e] = d;
+            const double td = Tv[e] * d;
+            if (v.nsign[e] == 0) {
+                t0 += d;
+                T0 += td;
+            } else {
+                t1 += d;
+                T1 += td;
+            }
+            csx[e] = cx_[j];
+            csy[e] = cy_[j];
+            csz[e] = cz_[j];
+        }
+    }
+    dLt[i] = t0;
+    dLt[Np + i] = t1;
+    TdLt[i] = T0;
+    TdLt[Np + i] = T1;
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        beta2[(size_t)q * Np + i] = beta[q];
+    alpha2[i] = alpha;
+    dlambda[i] = dl;
+}
+
+// force_kernel<0> + stress_kernel in one pass over the bonds of i
+__global__ void __launch_bounds__(BT)
+j2_force_stress_kernel(BondView v, double V, const double *__restrict__ Kn, const double *__restrict__ Tv, const double *__restrict__ w,
+                       const double *__restrict__ broken, const double *__restrict__ L0, const double *__restrict__ dL,
+                       const double *__restrict__ dLt, const double *__restrict__ TdLt, const double *__restrict__ csx,
+                       const double *__restrict__ csy, const double *__restrict__ csz, double *__restrict__ dL_ave, double *__restrict__ F,
+                       double *__restrict__ Pin, double *__restrict__ stress, double *__restrict__ seq_out, double *__restrict__ sm_out,
+                       double *__restrict__ triax, double *__restrict__ bond_stress)
+{
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i >= v.N)
+        return;
+    const size_t Np = v.Np;
+    const double dLt_i0 = dLt[i], dLt_i1 = dLt[Np + i], TdLt_i0 = TdLt[i], TdLt_i1 = TdLt[Np + i];
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    double st[6] = {0, 0, 0, 0, 0, 0};
+    const int n = v.nbi[i], nb_i = v.nb[i];
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const int nj = v.nbr[e];
+        const int s = v.nsign[e];
+        const double dLt_i = s ? dLt_i1 : dLt_i0, TdLt_i = s ? TdLt_i1 : TdLt_i0;
+        const double dLt_j = dLt[(size_t)s * Np + nj], TdLt_j = TdLt[(size_t)s * Np + nj];
+        double stretch;
+        const int mj = v.mirror[e];
+        if (mj >= 0) {
+            stretch = 0.5 * (dL[e] + dL[(size_t)mj * Np + nj]);
+            dL_ave[e] = stretch;
+        } else {
+            stretch = dL_ave[e];
+        }
+        double f = 2.0 * Kn[e] * stretch + 0.5 * (TdLt_i + TdLt_j) + 0.5 * Tv[e] * (dLt_i + dLt_j);
+        f *= w[e];
+        F[e] = f;
+        const double cx = csx[e], cy = csy[e], cz = csz[e];
+        p0 += cx * f;
+        p1 += cy * f;
+        p2 += cz * f;
+        const double of = opp_flag(nb_i, v.nn, v.opp[e], broken, Np, i);
+        const double pre = of / V * L0[e] * f;
+        st[0] += pre * cx * cx;
+        st[1] += pre * cy * cy;
+        st[2] += pre * cz * cz;
+        st[3] += pre * cy * cz;
+        st[4] += pre * cx * cz;
+        st[5] += pre * cx * cy;
+    }
+    Pin[i] = p0;
+    Pin[Np + i] = p1;
+    Pin[2 * Np + i] = p2;
+    double seq = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        stress[(size_t)q * Np + i] = st[q];
+        if (q < 3)
+            seq += st[q] * st[q];
+        else
+            seq += 2.0 * st[q] * st[q];
+    }
+    seq = sqrt(3.0 / 2.0 * seq);
+    const double sm = 1.0 / 3.0 * (st[0] + st[1] + st[2]);
+    seq_out[i] = seq;
+    sm_out[i] = sm;
+    if (seq > LPMB_EPS)
+        triax[i] = sm / seq;  // keeps the previous value otherwise (lpm_basic.c:111-112)
+    for (int j = 0; j < n; j++) {
+        const size_t e = (size_t)j * Np + i;
+        const double cx = csx[e], cy = csy[e], cz = csz[e];
+        bond_stress[e] = (st[0] * cx * cx + st[1] * cy * cy + st[2] * cz * cz + 2 * st[3] * cy * cz + 2 * st[4] * cx * cz + 2 * st[5] * cx * cy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // J2 with the distortional-energy return map (plmode 3), per particle   constitutive.c:336-411
 // Scalar equivalent back stress / plastic strain, plastic multiplier by bisection on (0,1) to TOLITER = 1e-4
 // (14 halvings).  Quirks kept: the bond loops run over the first nb[i] slots (the CURRENT intact count, not
@@ -1259,6 +1480,22 @@ extern "C" int lpmb_bond_force(lpmb_ctx *c, int plmode, int load_indicator)
         LPMB_REQUIRE(c->params.count("J2_H") && c->params.count("J2_xi"), LPMB_ERR_STATE, "J2_H / J2_xi not set");
         Field *ce = lpmb_field(c, "Ce");
         LPMB_REQUIRE(ce, LPMB_ERR_STATE, "Ce not uploaded (lpmb_calc_kntv)");
+        if (c->nn <= J2F_MAXNN && param(c, "j2_fused", 1.0) != 0.0) {
+            // two fused passes instead of five (same arithmetic, bit-identical outputs; see j2_fused_kernel)
+            j2_fused_kernel<<<g, BT, 0, c->stream>>>(
+                v, param(c, "particle_volume"), param(c, "J2_H"), param(c, "J2_xi"), (const double *)ce->d, fptr<int>(c, "type"),
+                fptr<double>(c, "sigmay"), Kn, Tv, w, broken, fptr<double>(c, "distance_initial"), fptr<double>(c, "dLp0"),
+                fptr<double>(c, "J2_beta0"), fptr<double>(c, "J2_alpha0"), fptr<double>(c, "dLp2"), fptr<double>(c, "J2_beta2"),
+                fptr<double>(c, "J2_alpha2"), fptr<double>(c, "ddLp"), fptr<double>(c, "J2_dlambda"), fptr<int>(c, "pl_flag"), dL, csx, csy, csz,
+                dLt, TdLt);
+            LPMB_LAUNCH_CHECK(c);
+            j2_force_stress_kernel<<<g, BT, 0, c->stream>>>(
+                v, param(c, "particle_volume"), Kn, Tv, w, broken, fptr<double>(c, "distance_initial"), dL, dLt, TdLt, csx, csy, csz, dL_ave, F,
+                Pin, fptr<double>(c, "stress_tensor"), fptr<double>(c, "J2_stresseq"), fptr<double>(c, "J2_stressm"),
+                fptr<double>(c, "J2_triaxiality"), fptr<double>(c, "bond_stress"));
+            LPMB_LAUNCH_CHECK(c);
+            return lpmb_switch_state(c, 2);
+        }
         LPMB_TRY(run_geometry(c, v, "dLp0"));
         j2_return_map_kernel<<<g, BT, 0, c->stream>>>(
             v, param(c, "particle_volume"), param(c, "J2_H"), param(c, "J2_xi"), (const double *)ce->d, fptr<int>(c, "type"),
