@@ -427,6 +427,473 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
     }
 }
 
+// =====================================================================================================================
+// Round-2 assembly for 3-D lattices: slice-cooperative, two kernels (param `fd_variant`, default 1; 0 = the kernel above).
+//
+// The CTA-per-particle kernel above spends 37 k warp instructions per particle: every owner re-derives the perturbed
+// shell sums of its 18 neighbours (each neighbour's table is rebuilt by ~18 owners), stages 342 scattered bond records
+// and writes K 8 bytes at a time into 256-byte lines.  The perturbed shell sums of a particle do not depend on who
+// asks, so they are tabulated ONCE per particle, and the rows are then formed by CTAs that own a whole SELL slice
+// (32 consecutive block rows, lane = row):
+//
+//  fd_shell_table_kernel  particle a -> planes of `tab` ([plane][Np], lane = particle: coalesced both ways)
+//      0..3                       unperturbed dL_total[a][0..1], TdL_total[a][0..1]
+//      4 + (mm*3 + r)*2 + {0,1}   shell sums (dL, TdL) of shell nsign[a][mm] when neighbour slot mm moves by +h in r
+//      4 + NN*6 + r*4 + 2*s+{0,1} shell sums of shell s when a itself moves by +h in r
+//    each sum is accumulated in the reference's order with exactly its expressions (constitutive.c:241-260); stretches
+//    of bonds the perturbation does not touch are bit-identical to the unperturbed ones and are re-added from a cache.
+//  fd_rows_kernel         one CTA per slice, warp w takes the conn positions q = w, w+8, ...; a THREAD owns the three
+//      perturbations (conn[i][q], r = 0..2) of its row: a bond whose inputs the perturbation does not touch contributes
+//      its cached unperturbed product cs*F (bit-identical: same inputs, same operations), the others are re-evaluated
+//      with sums looked up in `tab`.  On a regular lattice the 32 rows of a slice share one topology pattern, so the
+//      "is bond m touched by conn member q" branches are warp-uniform, and every store of K is a full 256-byte line.
+//
+// ~2 k warp instructions per particle instead of 37 k; the arithmetic per stored value is unchanged, so K_global / IK /
+// JK stay bit-identical to stiffness.c:384-516 (tests/test_constitutive_gpu.py, test_variants_gpu.py and the
+// old-vs-new comparison on perturbed, damaged lattices in tests/test_fd_variants_gpu.py).
+// =====================================================================================================================
+
+#define FD_TAB_PLANES(NN) (4 + (NN) * 6 + 12)
+
+template <int NN>
+__global__ void __launch_bounds__(32 * (NN + 1))
+fd_shell_table_kernel(int N, int Np, double h, const int *__restrict__ nbr, const signed char *__restrict__ nsign, const int *__restrict__ nbi_g,
+                      const double *__restrict__ xyz, const double *__restrict__ L0g, const double *__restrict__ dLp0g,
+                      const double *__restrict__ brkg, const double *__restrict__ Tvg, double *__restrict__ tab)
+{
+    __shared__ double bd[NN][32], tv[NN][32], ds[3][NN][32];
+    __shared__ signed char sgs[NN][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int a = blockIdx.x * 32 + lane;
+    const size_t Npz = Np;
+    const bool valid = a < N;
+    const int n = valid ? nbi_g[a] : 0;
+    const bool have = w < NN && w < n;
+    double dn[3] = {0.0, 0.0, 0.0};
+    int smm = 0;
+    if (have) {
+        const size_t g = (size_t)w * Npz + a;
+        const int nj = nbr[g];
+        const double pa[3] = {xyz[a], xyz[Npz + a], xyz[2 * Npz + a]};
+        const double pn[3] = {xyz[nj], xyz[Npz + nj], xyz[2 * Npz + nj]};
+        const double l0 = L0g[g], dlp = dLp0g[g], bk = brkg[g];
+        smm = nsign[g];
+        {
+            const double dx = pa[0] - pn[0], dy = pa[1] - pn[1], dz = pa[2] - pn[2];
+            const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            double d = dis - l0;
+            d -= dlp;
+            d *= bk;
+            bd[w][lane] = d;
+        }
+        tv[w][lane] = Tvg[g];
+        sgs[w][lane] = (signed char)smm;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            // the neighbour moves (constitutive.c:248-250 with xyz[neighbors[a][w]][r] + h)
+            double q[3] = {pn[0], pn[1], pn[2]};
+            q[r] = q[r] + h;
+            double dx = pa[0] - q[0], dy = pa[1] - q[1], dz = pa[2] - q[2];
+            double dis = sqrt(dx * dx + dy * dy + dz * dz);
+            double d = dis - l0;
+            d -= dlp;
+            d *= bk;
+            dn[r] = d;
+            // a itself moves
+            double o[3] = {pa[0], pa[1], pa[2]};
+            o[r] = o[r] + h;
+            dx = o[0] - pn[0], dy = o[1] - pn[1], dz = o[2] - pn[2];
+            dis = sqrt(dx * dx + dy * dy + dz * dz);
+            d = dis - l0;
+            d -= dlp;
+            d *= bk;
+            ds[r][w][lane] = d;
+        }
+    }
+    __syncthreads();
+    if (w < NN) {
+        if (!have)
+            return;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            double t = 0.0, T = 0.0;
+            for (int m2 = 0; m2 < n; m2++) {
+                if (sgs[m2][lane] != smm)
+                    continue;
+                const double d = m2 == w ? dn[r] : bd[m2][lane];
+                t += d;
+                T += tv[m2][lane] * d;
+            }
+            tab[(size_t)(4 + (w * 3 + r) * 2) * Npz + a] = t;
+            tab[(size_t)(4 + (w * 3 + r) * 2 + 1) * Npz + a] = T;
+        }
+        return;
+    }
+    if (!valid)
+        return;
+    {
+        double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+        for (int m2 = 0; m2 < n; m2++) {
+            const double d = bd[m2][lane];
+            const double td = tv[m2][lane] * d;
+            if (sgs[m2][lane] == 0) {
+                t0 += d;
+                T0 += td;
+            } else {
+                t1 += d;
+                T1 += td;
+            }
+        }
+        tab[a] = t0;
+        tab[Npz + a] = t1;
+        tab[2 * Npz + a] = T0;
+        tab[3 * Npz + a] = T1;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        double t0 = 0, t1 = 0, T0 = 0, T1 = 0;
+        for (int m2 = 0; m2 < n; m2++) {
+            const double d = ds[r][m2][lane];
+            const double td = tv[m2][lane] * d;
+            if (sgs[m2][lane] == 0) {
+                t0 += d;
+                T0 += td;
+            } else {
+                t1 += d;
+                T1 += td;
+            }
+        }
+        double *o = tab + (size_t)(4 + NN * 6 + r * 4) * Npz + a;
+        o[0] = t0;
+        o[Npz] = T0;
+        o[2 * Npz] = t1;
+        o[3 * Npz] = T1;
+    }
+}
+
+template <int NN>
+struct FdRowsSmem {
+    int conn[64][32];                       // sorted conn list of every row of the slice
+    int na[NN][32];                         // neighbour ids
+    double bd[NN][32], cx[NN][32], cy[NN][32], cz[NN][32], Kn[NN][32], Tv[NN][32], brk[NN][32], fb[NN][32];
+    double btj[NN][32], bTj[NN][32];        // unperturbed sums of neighbour m in the shell of bond m
+    double bti[2][32], bTi[2][32];          // unperturbed sums of the row's own particle
+    double bpin[3][32];
+    unsigned long long amask[NN][32];       // bit q: conn member q changes neighbour m's sums in the shell of bond m
+    unsigned long long ownmask[32];         // bit q: conn member q is one of the row's own neighbours
+    unsigned char slotof[NN][NN + 1][32];   // rank of q inside amask -> slot in the neighbour's list (NN = the neighbour itself)
+    unsigned char sg[NN][32];
+    unsigned char ownq[NN][32];             // conn position of own neighbour m (255: none)
+    unsigned char selfq[32];
+};
+
+// first position k in the sorted column `conn[.][lane]` (n entries) with conn[k] >= target
+__device__ __forceinline__ int fd_lower_bound(const int (*conn)[32], int lane, int n, int target)
+{
+    int lo = 0, len = n;
+    while (len > 0) {
+        const int half = len >> 1;
+        if (conn[lo + half][lane] < target) {
+            lo += half + 1;
+            len -= half + 1;
+        } else
+            len = half;
+    }
+    return lo;
+}
+
+template <int NN>
+__global__ void __launch_bounds__(256, 2)
+fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__restrict__ nbr, const signed char *__restrict__ nsign,
+               const int *__restrict__ nbi_g, const double *__restrict__ xyz, const double *__restrict__ L0g,
+               const double *__restrict__ dLp0g, const double *__restrict__ brkg, const double *__restrict__ Tvg,
+               const double *__restrict__ Kng, const long long *__restrict__ sptr, const int *__restrict__ col,
+               const int *__restrict__ nbc_g, const double *__restrict__ tab, double *__restrict__ val, double *__restrict__ F_side,
+               double *__restrict__ Pin_side)
+{
+    extern __shared__ unsigned char smem_raw[];
+    FdRowsSmem<NN> &S = *reinterpret_cast<FdRowsSmem<NN> *>(smem_raw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const bool valid = i < N;
+    const size_t Npz = Np;
+    const long long krow = sptr[blockIdx.x];
+    const int width = (int)(sptr[blockIdx.x + 1] - krow);
+    const int n0 = valid ? nbi_g[i] : 0;
+    const int nbc = valid ? nbc_g[i] : 0;
+    const double *tabN = tab + 4 * Npz, *tabS = tab + (size_t)(4 + NN * 6) * Npz;
+
+    for (int k = w; k < width; k += 8)
+        S.conn[k][lane] = col[(krow + k) * 32 + lane];
+    if (w == 0)
+        S.ownmask[lane] = 0ull;
+    __syncthreads();
+
+    // ---- the row's own bonds: unperturbed stretch and direction cosines, neighbour sums, conn positions ----
+    double pi0 = 0.0, pi1 = 0.0, pi2 = 0.0;
+    if (valid) {
+        pi0 = xyz[i];
+        pi1 = xyz[Npz + i];
+        pi2 = xyz[2 * Npz + i];
+    }
+    for (int m = w; m < NN; m += 8) {
+        if (m >= n0)
+            continue;
+        const size_t g = (size_t)m * Npz + i;
+        const int a = nbr[g];
+        const double dx = pi0 - xyz[a], dy = pi1 - xyz[Npz + a], dz = pi2 - xyz[2 * Npz + a];
+        const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        const double bk = brkg[g];
+        double d = dis - L0g[g];
+        d -= dLp0g[g];
+        d *= bk;
+        const int s = nsign[g];
+        S.na[m][lane] = a;
+        S.bd[m][lane] = d;
+        S.cx[m][lane] = dx / dis;
+        S.cy[m][lane] = dy / dis;
+        S.cz[m][lane] = dz / dis;
+        S.Kn[m][lane] = Kng[g];
+        S.Tv[m][lane] = Tvg[g];
+        S.brk[m][lane] = bk;
+        S.sg[m][lane] = (unsigned char)s;
+        S.btj[m][lane] = tab[(size_t)s * Npz + a];
+        S.bTj[m][lane] = tab[(size_t)(2 + s) * Npz + a];
+        const int pos = fd_lower_bound(S.conn, lane, nbc, a);
+        const bool found = pos < nbc && S.conn[pos][lane] == a;
+        S.ownq[m][lane] = found ? (unsigned char)pos : (unsigned char)255;
+        if (found)
+            atomicOr(&S.ownmask[lane], 1ull << pos);
+    }
+    if (w == 7) {
+        unsigned char sq = 255;
+        if (valid) {
+            const int pos = fd_lower_bound(S.conn, lane, nbc, i);
+            if (pos < nbc && S.conn[pos][lane] == i)
+                sq = (unsigned char)pos;
+            S.bti[0][lane] = tab[i];
+            S.bti[1][lane] = tab[Npz + i];
+            S.bTi[0][lane] = tab[2 * Npz + i];
+            S.bTi[1][lane] = tab[3 * Npz + i];
+        }
+        S.selfq[lane] = sq;
+    }
+    __syncthreads();
+
+    // ---- unperturbed bond forces (constitutive.c:269-270) and the "who touches whom" masks ----
+    for (int m = w; m < NN; m += 8) {
+        if (m >= n0)
+            continue;
+        const int s = S.sg[m][lane];
+        double f = 2.0 * S.Kn[m][lane] * S.bd[m][lane] + 0.5 * (S.bTi[s][lane] + S.bTj[m][lane]) +
+                   0.5 * S.Tv[m][lane] * (S.bti[s][lane] + S.btj[m][lane]);
+        f *= S.brk[m][lane];
+        S.fb[m][lane] = f;
+        const int a = S.na[m][lane];
+        const int nan_ = nbi_g[a];
+        unsigned long long mask = 0ull;
+        unsigned char qs[NN];
+#pragma unroll
+        for (int mm = 0; mm < NN; mm++) {
+            qs[mm] = 255;
+            if (mm < nan_) {
+                const size_t gg = (size_t)mm * Npz + a;
+                if (nsign[gg] == s) {
+                    const int c = nbr[gg];
+                    const int pos = fd_lower_bound(S.conn, lane, nbc, c);
+                    if (pos < nbc && S.conn[pos][lane] == c) {
+                        mask |= 1ull << pos;
+                        qs[mm] = (unsigned char)pos;
+                    }
+                }
+            }
+        }
+        const int oq = S.ownq[m][lane];
+        if (oq != 255)
+            mask |= 1ull << oq;
+        S.amask[m][lane] = mask;
+#pragma unroll
+        for (int mm = 0; mm < NN; mm++)
+            if (qs[mm] != 255)
+                S.slotof[m][__popcll(mask & ((1ull << qs[mm]) - 1ull))][lane] = (unsigned char)mm;
+        if (oq != 255)
+            S.slotof[m][__popcll(mask & ((1ull << oq) - 1ull))][lane] = (unsigned char)NN;
+    }
+    __syncthreads();
+
+    // ---- unperturbed internal force of every row (constitutive.c:275-277) ----
+    if (w == 0 && valid) {
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+        for (int m = 0; m < n0; m++) {
+            const double f = S.fb[m][lane];
+            q0 += S.cx[m][lane] * f;
+            q1 += S.cy[m][lane] * f;
+            q2 += S.cz[m][lane] * f;
+        }
+        S.bpin[0][lane] = q0;
+        S.bpin[1][lane] = q1;
+        S.bpin[2][lane] = q2;
+    }
+    __syncthreads();
+
+    // ---- one conn member per thread: the three perturbed evaluations of the row's internal force ----
+    for (int q = w; q < width; q += 8) {
+        if (q >= nbc)
+            continue;
+        const unsigned long long bitq = 1ull << q, below = bitq - 1ull;
+        const bool own_all = S.selfq[lane] == q;
+        int mstar = -1, sstar = -1;
+        if (!own_all && (S.ownmask[lane] & bitq)) {
+            for (int m = 0; m < n0; m++)
+                if (S.ownq[m][lane] == q)
+                    mstar = m;
+            sstar = S.sg[mstar][lane];
+        }
+        // the row's own shell sums under the three perturbations: [r][shell]
+        double ot[3][2], oT[3][2];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            ot[r][0] = S.bti[0][lane];
+            ot[r][1] = S.bti[1][lane];
+            oT[r][0] = S.bTi[0][lane];
+            oT[r][1] = S.bTi[1][lane];
+        }
+        if (own_all) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const double *o = tabS + (size_t)(r * 4) * Npz + i;
+                ot[r][0] = o[0];
+                oT[r][0] = o[Npz];
+                ot[r][1] = o[2 * Npz];
+                oT[r][1] = o[3 * Npz];
+            }
+        } else if (mstar >= 0) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const double t = tabN[(size_t)((mstar * 3 + r) * 2) * Npz + i], T = tabN[(size_t)((mstar * 3 + r) * 2 + 1) * Npz + i];
+                if (sstar == 0) {
+                    ot[r][0] = t;
+                    oT[r][0] = T;
+                } else {
+                    ot[r][1] = t;
+                    oT[r][1] = T;
+                }
+            }
+        }
+        const bool last = (q == nbc - 1) && (F_side != nullptr);
+        double p[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            p[r][0] = p[r][1] = p[r][2] = 0.0;
+
+        for (int m = 0; m < n0; m++) {
+            const int s = S.sg[m][lane];
+            const unsigned long long am = S.amask[m][lane];
+            const bool affn = (am & bitq) != 0ull;
+            const bool own_d = own_all || m == mstar;
+            const bool own_s = own_all || s == sstar;
+            if (!(affn || own_d || own_s)) {
+                const double f = S.fb[m][lane];
+                const double ax = S.cx[m][lane] * f, ay = S.cy[m][lane] * f, az = S.cz[m][lane] * f;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    p[r][0] += ax;
+                    p[r][1] += ay;
+                    p[r][2] += az;
+                }
+                if (last)
+                    F_side[(size_t)m * Npz + i] = f;
+                continue;
+            }
+            // neighbour's sums in the shell of bond m
+            double tj[3], Tj[3];
+            if (affn) {
+                const int slot = S.slotof[m][__popcll(am & below)][lane];
+                const int a = S.na[m][lane];
+                if (slot == NN) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        tj[r] = tabS[(size_t)(r * 4 + 2 * s) * Npz + a];
+                        Tj[r] = tabS[(size_t)(r * 4 + 2 * s + 1) * Npz + a];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        tj[r] = tabN[(size_t)((slot * 3 + r) * 2) * Npz + a];
+                        Tj[r] = tabN[(size_t)((slot * 3 + r) * 2 + 1) * Npz + a];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    tj[r] = S.btj[m][lane];
+                    Tj[r] = S.bTj[m][lane];
+                }
+            }
+            // the bond itself
+            double d[3], ux[3], uy[3], uz[3];
+            const double bk = S.brk[m][lane];
+            if (own_d) {
+                const size_t g = (size_t)m * Npz + i;
+                const int a = S.na[m][lane];
+                const double pa0 = xyz[a], pa1 = xyz[Npz + a], pa2 = xyz[2 * Npz + a];
+                const double l0 = L0g[g], dlp = dLp0g[g];
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    double o[3] = {pi0, pi1, pi2}, e[3] = {pa0, pa1, pa2};
+                    if (own_all)
+                        o[r] = o[r] + h;
+                    else
+                        e[r] = e[r] + h;
+                    const double dx = o[0] - e[0], dy = o[1] - e[1], dz = o[2] - e[2];
+                    const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+                    double dd = dis - l0;
+                    dd -= dlp;
+                    dd *= bk;
+                    d[r] = dd;
+                    ux[r] = dx / dis;
+                    uy[r] = dy / dis;
+                    uz[r] = dz / dis;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    d[r] = S.bd[m][lane];
+                    ux[r] = S.cx[m][lane];
+                    uy[r] = S.cy[m][lane];
+                    uz[r] = S.cz[m][lane];
+                }
+            }
+            const double kn = S.Kn[m][lane], tvm = S.Tv[m][lane];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const double ti = s ? ot[r][1] : ot[r][0], Ti = s ? oT[r][1] : oT[r][0];
+                double f = 2.0 * kn * d[r] + 0.5 * (Ti + Tj[r]) + 0.5 * tvm * (ti + tj[r]);
+                f *= bk;
+                p[r][0] += ux[r] * f;
+                p[r][1] += uy[r] * f;
+                p[r][2] += uz[r] * f;
+                if (last && r == 2)
+                    F_side[(size_t)m * Npz + i] = f;
+            }
+        }
+        if (last) {
+            Pin_side[i] = p[2][0];
+            Pin_side[Npz + i] = p[2][1];
+            Pin_side[2 * Npz + i] = p[2][2];
+        }
+        // A_i[c][s][r] = (Pin_pert[s] - Pin_base[s]) / EPS / radius -> element (row s, col r) of block (i, c)
+        const long long k = krow + q;
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            const double b = S.bpin[s][lane];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                val[(k * 9 + s * 3 + r) * 32 + lane] = (p[r][s] - b) / eps / radius;
+        }
+    }
+}
+
 // position of block column `target` in (sorted) block row `row`, or -1
 __device__ __forceinline__ int find_col(const int *__restrict__ col, const long long *__restrict__ sptr, const int *__restrict__ nbc, int row,
                                         int target)
@@ -577,11 +1044,33 @@ extern "C" int lpmb_fd_stiffness(lpmb_ctx *c, int emulate_side_effects)
     double *Fs = emulate_side_effects ? F : nullptr, *Ps = emulate_side_effects ? Pin : nullptr;
     if (c->dim == 3) {
         LPMB_REQUIRE(c->nn <= 18 && c->nconn <= 64, LPMB_ERR_UNSUPPORTED, "fd_stiffness<3>: nn=%d nconn=%d", c->nn, c->nconn);
-        const size_t smem = sizeof(StarSmem<3, 18>);
-        auto kern = fd_stiffness_kernel<3, 18, 192>;
-        LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<c->N, 192, smem, c->stream>>>(c->N, c->Np, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, K.val, Fs, Ps);
-        LPMB_LAUNCH_CHECK(c);
+        // slice-cooperative assembly (default); its per-particle table of perturbed shell sums is scratch of this call.
+        // fd_variant = 0, or no memory for the table, selects the CTA-per-particle kernel (same bits).
+        double *tab = nullptr;
+        if ((int)param(c, "fd_variant", 1.0) != 0) {
+            const size_t tab_bytes = (size_t)FD_TAB_PLANES(18) * c->Np * sizeof(double);
+            if (cudaMalloc(&tab, tab_bytes) != cudaSuccess) {
+                (void)cudaGetLastError();
+                tab = nullptr;
+            }
+        }
+        if (tab) {
+            fd_shell_table_kernel<18><<<c->Np / 32, 32 * 19, 0, c->stream>>>(c->N, c->Np, h, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, tab);
+            LPMB_LAUNCH_CHECK(c);
+            const size_t smem = sizeof(FdRowsSmem<18>);
+            auto kern = fd_rows_kernel<18>;
+            LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<K.nslices, 256, smem, c->stream>>>(c->N, c->Np, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, tab, K.val, Fs, Ps);
+            LPMB_LAUNCH_CHECK(c);
+            LPMB_CUDA(cudaStreamSynchronize(c->stream));
+            LPMB_CUDA(cudaFree(tab));
+        } else {
+            const size_t smem = sizeof(StarSmem<3, 18>);
+            auto kern = fd_stiffness_kernel<3, 18, 192>;
+            LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<c->N, 192, smem, c->stream>>>(c->N, c->Np, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, K.val, Fs, Ps);
+            LPMB_LAUNCH_CHECK(c);
+        }
         symmetrize_kernel<3><<<lpmb_blocks(c->N, 128), 128, 0, c->stream>>>(c->N, K.sptr, K.col, K.nbc, K.val);
         LPMB_LAUNCH_CHECK(c);
     } else {
