@@ -465,6 +465,7 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     if (c->cg.h_scal)
         cudaFreeHost(c->cg.h_scal);
     cudaFree(c->mask);
+    cudaFree(c->fd_tab);
     cudaFree(c->staging);
     if (c->h_staging)
         cudaFreeHost(c->h_staging);

@@ -120,6 +120,8 @@ struct lpmb_ctx {
     SellMatrix K;
     CGWork cg;
     double *mask = nullptr;      // [dim][Np] 1.0 free / 0.0 constrained (nullptr = all free)
+    double *fd_tab = nullptr;    // FD assembly scratch: perturbed shell sums of a window of particles (lpmb_stiffness.cu)
+    size_t fd_tab_bytes = 0;
     void *staging = nullptr;     // device staging for host<->device re-layout
     size_t staging_bytes = 0;
     void *h_staging = nullptr;   // pinned host staging

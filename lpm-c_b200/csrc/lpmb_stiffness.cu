@@ -457,18 +457,19 @@ fd_stiffness_kernel(int N, int Np, double h, double eps, double radius, const in
 
 template <int NN>
 __global__ void __launch_bounds__(32 * (NN + 1))
-fd_shell_table_kernel(int N, int Np, double h, const int *__restrict__ nbr, const signed char *__restrict__ nsign, const int *__restrict__ nbi_g,
+fd_shell_table_kernel(int N, int Np, int a0, int tabNp, double h, const int *__restrict__ nbr, const signed char *__restrict__ nsign, const int *__restrict__ nbi_g,
                       const double *__restrict__ xyz, const double *__restrict__ L0g, const double *__restrict__ dLp0g,
                       const double *__restrict__ brkg, const double *__restrict__ Tvg, double *__restrict__ tab)
 {
     __shared__ double bd[NN][32], tv[NN][32], ds[3][NN][32];
     __shared__ signed char sgs[NN][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int a = blockIdx.x * 32 + lane;
-    const size_t Npz = Np;
+    const int a = a0 + blockIdx.x * 32 + lane;   // the table covers particles [a0, a0 + tabNp): window of the current chunk
+    const size_t Npz = Np, Tz = tabNp;
     const bool valid = a < N;
     const int n = valid ? nbi_g[a] : 0;
     const bool have = w < NN && w < n;
+    tab -= a0;
     double dn[3] = {0.0, 0.0, 0.0};
     int smm = 0;
     if (have) {
@@ -524,8 +525,8 @@ fd_shell_table_kernel(int N, int Np, double h, const int *__restrict__ nbr, cons
                 t += d;
                 T += tv[m2][lane] * d;
             }
-            tab[(size_t)(4 + (w * 3 + r) * 2) * Npz + a] = t;
-            tab[(size_t)(4 + (w * 3 + r) * 2 + 1) * Npz + a] = T;
+            tab[(size_t)(4 + (w * 3 + r) * 2) * Tz + a] = t;
+            tab[(size_t)(4 + (w * 3 + r) * 2 + 1) * Tz + a] = T;
         }
         return;
     }
@@ -545,9 +546,9 @@ fd_shell_table_kernel(int N, int Np, double h, const int *__restrict__ nbr, cons
             }
         }
         tab[a] = t0;
-        tab[Npz + a] = t1;
-        tab[2 * Npz + a] = T0;
-        tab[3 * Npz + a] = T1;
+        tab[Tz + a] = t1;
+        tab[2 * Tz + a] = T0;
+        tab[3 * Tz + a] = T1;
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) {
@@ -563,11 +564,11 @@ fd_shell_table_kernel(int N, int Np, double h, const int *__restrict__ nbr, cons
                 T1 += td;
             }
         }
-        double *o = tab + (size_t)(4 + NN * 6 + r * 4) * Npz + a;
+        double *o = tab + (size_t)(4 + NN * 6 + r * 4) * Tz + a;
         o[0] = t0;
-        o[Npz] = T0;
-        o[2 * Npz] = t1;
-        o[3 * Npz] = T1;
+        o[Tz] = T0;
+        o[2 * Tz] = t1;
+        o[3 * Tz] = T1;
     }
 }
 
@@ -604,7 +605,7 @@ __device__ __forceinline__ int fd_lower_bound(const int (*conn)[32], int lane, i
 
 template <int NN>
 __global__ void __launch_bounds__(256, 2)
-fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__restrict__ nbr, const signed char *__restrict__ nsign,
+fd_rows_kernel(int N, int Np, int slice0, int a0, int tabNp, double h, double eps, double radius, const int *__restrict__ nbr, const signed char *__restrict__ nsign,
                const int *__restrict__ nbi_g, const double *__restrict__ xyz, const double *__restrict__ L0g,
                const double *__restrict__ dLp0g, const double *__restrict__ brkg, const double *__restrict__ Tvg,
                const double *__restrict__ Kng, const long long *__restrict__ sptr, const int *__restrict__ col,
@@ -614,14 +615,16 @@ fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__
     extern __shared__ unsigned char smem_raw[];
     FdRowsSmem<NN> &S = *reinterpret_cast<FdRowsSmem<NN> *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + lane;
+    const int slice = slice0 + blockIdx.x;
+    const int i = slice * 32 + lane;
     const bool valid = i < N;
-    const size_t Npz = Np;
-    const long long krow = sptr[blockIdx.x];
-    const int width = (int)(sptr[blockIdx.x + 1] - krow);
+    const size_t Npz = Np, Tz = tabNp;
+    const long long krow = sptr[slice];
+    const int width = (int)(sptr[slice + 1] - krow);
     const int n0 = valid ? nbi_g[i] : 0;
     const int nbc = valid ? nbc_g[i] : 0;
-    const double *tabN = tab + 4 * Npz, *tabS = tab + (size_t)(4 + NN * 6) * Npz;
+    tab -= a0;   // indexed by particle id; the window [a0, a0 + tabNp) covers the rows of this launch and their neighbours
+    const double *tabN = tab + 4 * Tz, *tabS = tab + (size_t)(4 + NN * 6) * Tz;
 
     for (int k = w; k < width; k += 8)
         S.conn[k][lane] = col[(krow + k) * 32 + lane];
@@ -657,8 +660,8 @@ fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__
         S.Tv[m][lane] = Tvg[g];
         S.brk[m][lane] = bk;
         S.sg[m][lane] = (unsigned char)s;
-        S.btj[m][lane] = tab[(size_t)s * Npz + a];
-        S.bTj[m][lane] = tab[(size_t)(2 + s) * Npz + a];
+        S.btj[m][lane] = tab[(size_t)s * Tz + a];
+        S.bTj[m][lane] = tab[(size_t)(2 + s) * Tz + a];
         const int pos = fd_lower_bound(S.conn, lane, nbc, a);
         const bool found = pos < nbc && S.conn[pos][lane] == a;
         S.ownq[m][lane] = found ? (unsigned char)pos : (unsigned char)255;
@@ -672,9 +675,9 @@ fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__
             if (pos < nbc && S.conn[pos][lane] == i)
                 sq = (unsigned char)pos;
             S.bti[0][lane] = tab[i];
-            S.bti[1][lane] = tab[Npz + i];
-            S.bTi[0][lane] = tab[2 * Npz + i];
-            S.bTi[1][lane] = tab[3 * Npz + i];
+            S.bti[1][lane] = tab[Tz + i];
+            S.bTi[0][lane] = tab[2 * Tz + i];
+            S.bTi[1][lane] = tab[3 * Tz + i];
         }
         S.selfq[lane] = sq;
     }
@@ -761,16 +764,16 @@ fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__
         if (own_all) {
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                const double *o = tabS + (size_t)(r * 4) * Npz + i;
+                const double *o = tabS + (size_t)(r * 4) * Tz + i;
                 ot[r][0] = o[0];
-                oT[r][0] = o[Npz];
-                ot[r][1] = o[2 * Npz];
-                oT[r][1] = o[3 * Npz];
+                oT[r][0] = o[Tz];
+                ot[r][1] = o[2 * Tz];
+                oT[r][1] = o[3 * Tz];
             }
         } else if (mstar >= 0) {
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                const double t = tabN[(size_t)((mstar * 3 + r) * 2) * Npz + i], T = tabN[(size_t)((mstar * 3 + r) * 2 + 1) * Npz + i];
+                const double t = tabN[(size_t)((mstar * 3 + r) * 2) * Tz + i], T = tabN[(size_t)((mstar * 3 + r) * 2 + 1) * Tz + i];
                 if (sstar == 0) {
                     ot[r][0] = t;
                     oT[r][0] = T;
@@ -813,14 +816,14 @@ fd_rows_kernel(int N, int Np, double h, double eps, double radius, const int *__
                 if (slot == NN) {
 #pragma unroll
                     for (int r = 0; r < 3; r++) {
-                        tj[r] = tabS[(size_t)(r * 4 + 2 * s) * Npz + a];
-                        Tj[r] = tabS[(size_t)(r * 4 + 2 * s + 1) * Npz + a];
+                        tj[r] = tabS[(size_t)(r * 4 + 2 * s) * Tz + a];
+                        Tj[r] = tabS[(size_t)(r * 4 + 2 * s + 1) * Tz + a];
                     }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 3; r++) {
-                        tj[r] = tabN[(size_t)((slot * 3 + r) * 2) * Npz + a];
-                        Tj[r] = tabN[(size_t)((slot * 3 + r) * 2 + 1) * Npz + a];
+                        tj[r] = tabN[(size_t)((slot * 3 + r) * 2) * Tz + a];
+                        Tj[r] = tabN[(size_t)((slot * 3 + r) * 2 + 1) * Tz + a];
                     }
                 }
             } else {
@@ -1023,6 +1026,35 @@ fd_side_effects_kernel(int N, int Np, double h, const int *__restrict__ nbr, con
     TdLt[Npz + p] = T1;
 }
 
+// max |neighbour id - own id| over all bonds (one int back to the host; 0.2 ms at 10 M particles)
+__global__ void fd_bandwidth_kernel(int N, int Np, int nn, const int *__restrict__ nbr, const int *__restrict__ nbi, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = 0;
+    if (i < N) {
+        const int n = nbi[i];
+        for (int m = 0; m < n && m < nn; m++) {
+            const int d = nbr[(size_t)m * Np + i] - i;
+            b = max(b, d < 0 ? -d : d);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b > 0)
+        atomicMax(out, b);
+}
+
+static int fd_bandwidth(lpmb_ctx *c, const int *nbr, const int *nbi, int *band)
+{
+    LPMB_TRY(lpmb_ensure_staging(c, 64));
+    int *d = (int *)c->staging;
+    LPMB_MEMSET(c, d, 0, sizeof(int));
+    fd_bandwidth_kernel<<<lpmb_blocks(c->N, 256), 256, 0, c->stream>>>(c->N, c->Np, c->nn, nbr, nbi, d);
+    LPMB_LAUNCH_CHECK(c);
+    LPMB_D2H(c, band, d, sizeof(int));
+    return LPMB_OK;
+}
+
 extern "C" int lpmb_fd_stiffness(lpmb_ctx *c, int emulate_side_effects)
 {
     LPMB_REQUIRE(c, LPMB_ERR_ARG, "null context");
@@ -1044,27 +1076,53 @@ extern "C" int lpmb_fd_stiffness(lpmb_ctx *c, int emulate_side_effects)
     double *Fs = emulate_side_effects ? F : nullptr, *Ps = emulate_side_effects ? Pin : nullptr;
     if (c->dim == 3) {
         LPMB_REQUIRE(c->nn <= 18 && c->nconn <= 64, LPMB_ERR_UNSUPPORTED, "fd_stiffness<3>: nn=%d nconn=%d", c->nn, c->nconn);
-        // slice-cooperative assembly (default); its per-particle table of perturbed shell sums is scratch of this call.
-        // fd_variant = 0, or no memory for the table, selects the CTA-per-particle kernel (same bits).
-        double *tab = nullptr;
+        // slice-cooperative assembly (default).  Its table of perturbed shell sums is persistent scratch of bounded size
+        // (param fd_tab_mb, default 2048): the rows are processed in chunks of consecutive SELL slices and the table
+        // covers the chunk's rows plus `band` = max |neighbour id - own id| particles either side (x-fastest lattices:
+        // one or two lattice layers).  fd_variant = 0 -- or a numbering so scattered that no chunk fits the budget --
+        // selects the CTA-per-particle kernel (same bits).
+        bool done = false;
         if ((int)param(c, "fd_variant", 1.0) != 0) {
-            const size_t tab_bytes = (size_t)FD_TAB_PLANES(18) * c->Np * sizeof(double);
-            if (cudaMalloc(&tab, tab_bytes) != cudaSuccess) {
-                (void)cudaGetLastError();
-                tab = nullptr;
+            int band = 0;
+            LPMB_TRY(fd_bandwidth(c, nbr, nbi, &band));
+            const size_t per_particle = (size_t)FD_TAB_PLANES(18) * sizeof(double);
+            const size_t budget = (size_t)(param(c, "fd_tab_mb", 2048.0) * 1048576.0);
+            long long W = (long long)(budget / per_particle) & ~31ll;   // particles the table may hold
+            if (W > c->Np)
+                W = c->Np;
+            const long long band32 = ((long long)band + 31) & ~31ll;
+            long long rows = W >= c->Np ? c->Np : ((W - 2 * band32) & ~31ll);  // rows per chunk
+            if (rows >= 256 || rows >= c->Np) {
+                if (c->fd_tab_bytes < (size_t)W * per_particle) {
+                    LPMB_CUDA(cudaStreamSynchronize(c->stream));
+                    cudaFree(c->fd_tab);
+                    c->fd_tab = nullptr;
+                    c->fd_tab_bytes = 0;
+                    if (cudaMalloc(&c->fd_tab, (size_t)W * per_particle) == cudaSuccess)
+                        c->fd_tab_bytes = (size_t)W * per_particle;
+                    else
+                        (void)cudaGetLastError();
+                }
+                if (c->fd_tab) {
+                    const size_t smem = sizeof(FdRowsSmem<18>);
+                    auto kern = fd_rows_kernel<18>;
+                    LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    for (long long p0 = 0; p0 < c->Np; p0 += rows) {
+                        const long long p1 = p0 + rows < c->Np ? p0 + rows : c->Np;
+                        long long a0 = p0 - band32, a1 = p1 + band32;
+                        a0 = a0 < 0 ? 0 : a0;
+                        a1 = a1 > c->Np ? c->Np : a1;
+                        const int tabNp = (int)(a1 - a0);
+                        fd_shell_table_kernel<18><<<tabNp / 32, 32 * 19, 0, c->stream>>>(c->N, c->Np, (int)a0, tabNp, h, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, c->fd_tab);
+                        LPMB_LAUNCH_CHECK(c);
+                        kern<<<(int)((p1 - p0) / 32), 256, smem, c->stream>>>(c->N, c->Np, (int)(p0 / 32), (int)a0, tabNp, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, c->fd_tab, K.val, Fs, Ps);
+                        LPMB_LAUNCH_CHECK(c);
+                    }
+                    done = true;
+                }
             }
         }
-        if (tab) {
-            fd_shell_table_kernel<18><<<c->Np / 32, 32 * 19, 0, c->stream>>>(c->N, c->Np, h, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, tab);
-            LPMB_LAUNCH_CHECK(c);
-            const size_t smem = sizeof(FdRowsSmem<18>);
-            auto kern = fd_rows_kernel<18>;
-            LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<K.nslices, 256, smem, c->stream>>>(c->N, c->Np, h, eps, radius, nbr, nsign, nbi, xyz, L0, dLp0, brk, Tv, Kn, K.sptr, K.col, K.nbc, tab, K.val, Fs, Ps);
-            LPMB_LAUNCH_CHECK(c);
-            LPMB_CUDA(cudaStreamSynchronize(c->stream));
-            LPMB_CUDA(cudaFree(tab));
-        } else {
+        if (!done) {
             const size_t smem = sizeof(StarSmem<3, 18>);
             auto kern = fd_stiffness_kernel<3, 18, 192>;
             LPMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -100,3 +100,21 @@ def test_assembly_is_repeatable_and_default_is_the_new_variant(lpm):
     assert_same(Kd, K1, "default == variant 1")
     assert_same(K1, K0, "variant 1 == variant 0")
     c.close()
+
+
+def test_chunked_table_window(lpm):
+    """the table of perturbed shell sums is bounded scratch (param fd_tab_mb): with a budget far below the lattice the rows
+    are assembled chunk by chunk against a sliding window of the table -- same bits"""
+    c = _block(lpm, 2, 37, 5, 6, seed=11)      # band = 37 * 5 + 37 + 1 = 223 particles
+    K0, _, _, s0 = _assemble(c, 0)
+    c.fill_test_pattern()
+    c.set_params(fd_tab_mb=0.7)                # 736 particles in the table -> 288 rows per chunk, 4 chunks
+    K1, _, _, s1 = _assemble(c, 1)
+    assert_same(K1, K0, "K_global, chunked")
+    for n in s0:
+        assert_same(s1[n], s0[n], f"side effect {n}, chunked")
+    c.set_params(fd_tab_mb=2048.0)
+    c.fill_test_pattern()
+    K2 = _assemble(c, 1)[0]
+    assert_same(K2, K0, "K_global, one chunk after the table grew")
+    c.close()
