@@ -1,5 +1,5 @@
 """crystal-plasticity law (plmode 1, cp_miehe_kernel) timing on FCC blocks of BASELINE config 4's material:
-   python scripts/cp_profile.py [cells=12 -> 6 912 particles] [reps=3]        (63 cells -> 1 000 188 particles)"""
+   python scripts/cp_profile.py [cells=12 -> 6 912 particles] [reps=3] [cp_warp=1]        (63 cells -> 1 000 188 particles)"""
 import importlib, sys, time
 from pathlib import Path
 import numpy as np
@@ -38,6 +38,8 @@ c.synchronize(); t2 = time.perf_counter()
 nb = c.get_field("nb_initial") if False else None
 x1 = xyz.copy(); x1[:, 2] *= 1.0 + 4e-4; x1[:, 0] *= 1.0 - 1.2e-4; x1[:, 1] *= 1.0 - 1.2e-4   # uniaxial stretch beyond yield
 c.set_field("xyz", x1)
+if len(sys.argv) > 3:
+    c.set_params(cp_warp=float(sys.argv[3]))     # 1 = warp-per-particle kernel (default), 0 = thread-per-particle kernel
 ts = []
 for _ in range(reps):
     c.switch_state(0)

@@ -23,6 +23,8 @@ for what in ("force", "disp"):
     rel = [abs(a[k][1] - b[k][1]) / max(abs(b[k][1]), 1e-30) for k in range(n)]
     bad = [k for k in range(n) if rel[k] > 2e-8]
     print(what, "records", len(a), len(b), "first differing record", bad[:5], "values", [(a[k], b[k]) for k in bad[:3]], "max rel", max(rel))
+    big = [k for k in range(n) if rel[k] > 1e-7]
+    print(what, "records above 1e-7:", [(k, a[k], b[k], f"{rel[k]:.2e}") for k in big[:40]])
 ba = [l.strip() for l in (d / "result_brokenbonds.txt").read_text().split("\n") if l.strip()]
 bb = [l.strip() for l in (G / f"{gold}_result_brokenbonds.txt").read_text().split("\n") if l.strip()]
 k = 0
@@ -31,4 +33,6 @@ while k < min(len(ba), len(bb)) and ba[k] == bb[k]:
 print("broken-bond logs: lines", len(ba), len(bb), "first differing line", k, ba[max(0,k-3):k+4], "|", bb[max(0,k-3):k+4])
 log = (d / "run.log").read_text()
 import re
+gn = [int(x) for x in re.findall(r"has finished in (\d+) iterations", log)]
+print("GPU newton iterations per finished step:", " ".join(map(str, gn)))
 print("GPU newton passes", len(re.findall(r"has finished in", log)), "golden summary:", (G / f"{gold}_log_summary.txt").read_text()[:200])

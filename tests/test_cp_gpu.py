@@ -80,6 +80,35 @@ def test_cp_bond_force(lpm, gcp, tag, prev):
     c.close()
 
 
+@pytest.mark.parametrize("tag,prev", [("s1.n0", "s1.pred"), ("s1.n2", "s1.n1.bf")])
+def test_warp_kernel_equals_thread_kernel(lpm, gcp, tag, prev):
+    """cp_miehe_warp_kernel (one warp per particle, lane = slip system, LU across the lanes; the default for <= 24 slip
+    systems) against cp_miehe_kernel (one thread per particle; param cp_warp = 0): every sum is accumulated in the same
+    order and the LU applies the same operations to every element, so all outputs must agree BIT FOR BIT"""
+    from helpers import assert_same
+    g = gcp
+    out = {}
+    for warp in (0, 1):
+        c, _ = make_cp_ctx(lpm, g)
+        c.set_params(cp_warp=float(warp))
+        c.set_field("cp_Cab", g["setup.cp_Cab"])
+        for n in ("dL", "dL_ave", "ddLp", "csx", "csy", "csz", "F", "damage_broken", "damage_w", "J2_triaxiality", "pl_flag"):
+            c.set_field(n, g[f"{prev}.{n}"])
+        put_slots(c, "dLp", g[f"{prev}.dLp"])
+        put_slots(c, "cp_gy", g[f"{prev}.cp_gy"])
+        put_slots(c, "cp_A_single", g[f"{prev}.cp_A_single"])
+        put_slots(c, "cp_A", g[f"{prev}.cp_A"])
+        c.switch_state(0)
+        c.set_field("xyz", g[f"{tag}.xyz"])
+        c.bond_force(1)
+        out[warp] = {n: c.get_field(n) for n in ("F", "Pin", "dL", "ddLp", "stress_tensor", "cp_RSS", "cp_dgy", "cp_dA", "cp_dA_single",
+                                                  "cp_Jact", "pl_flag", "dLp2", "cp_gy2", "cp_A2", "cp_A_single2")}
+        c.close()
+    assert int(out[0]["cp_Jact"].sum()) > 0
+    for n in out[0]:
+        assert_same(out[1][n], out[0][n], f"{n} (warp kernel vs thread kernel)")
+
+
 def test_cp_two_load_steps(lpm, gcp):
     """whole load steps, device resident (driver.load_step with plmode 1) vs the reference's run"""
     g = gcp

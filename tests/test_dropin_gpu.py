@@ -57,9 +57,10 @@ def _compare_tables(a, b, rtol, what):
     return n, worst
 
 
-def _compare_tables_to_peak(a, b, rtol, what):
+def _compare_tables_to_peak(a, b, rtol, what, relaxed=(), rtol_relaxed=0.0):
     """every record within rtol of the PEAK magnitude of the golden column set (records after the specimen failed are ~1e-4
-    of the peak load: a per-record relative bound would compare rounding noise with rounding noise there)"""
+    of the peak load: a per-record relative bound would compare rounding noise with rounding noise there); the records
+    of the load steps listed in `relaxed` are held to rtol_relaxed of their own magnitude instead"""
     n = min(len(a), len(b))
     assert n > 0, what
     peak = max(float(np.abs(np.array(r[1:])).max()) for r in b[:n])
@@ -67,6 +68,10 @@ def _compare_tables_to_peak(a, b, rtol, what):
     for k in range(n):
         ra, rb = np.array(a[k]), np.array(b[k])
         assert ra.shape == rb.shape and ra[0] == rb[0], (what, k)
+        if int(ra[0]) in relaxed:     # first column = load step
+            own = float(np.abs(ra[1:] - rb[1:]).max() / max(np.abs(rb[1:]).max(), 1e-30))
+            assert own <= rtol_relaxed, f"{what}: record {k} (Newton pass count differs from the golden run) off by {own:.2e}"
+            continue
         worst = max(worst, float(np.abs(ra[1:] - rb[1:]).max() / peak))
     assert worst <= rtol, f"{what}: worst line difference {worst:.2e} of the peak {peak:.6g} over {n} records"
     return n, worst
@@ -113,7 +118,14 @@ def test_brittle_example_matches_serial_reference(tmp_path, name, gold):
     iteration counts the two runs still differ by the rounding of the dot products (pairwise in the shim, tree-reduced on
     the device), which that loose stop amplifies -- measured 2.8e-8 of the peak at worst (record 24: 17685.6898 vs
     17685.6903), constant in absolute size along the run, and the reference moves its own bond forces by 9e-9 when only
-    its summation order changes (test_oracle_ref.py::test_reference_rounding_noise_floor)."""
+    its summation order changes (test_oracle_ref.py::test_reference_rounding_noise_floor).
+    The Newton loop stops at ||residual|| <= TOLITER = 1e-4 of the reaction norm (include/lpm.h:41); a pass that ends within
+    a hair of that bound can be the last one in one run and not in the other (the reference does that between thread
+    counts; the 91-step default case allows the same).  Measured on the beam: ONE of 215 passes (load step 44: residual
+    ratio at the bound after the first iteration) -- the golden run iterates once more, so that record differs by
+    1.3e-4 = the accepted Newton error, the next one by 2e-7, and the trajectories are back within 1e-7 after that.  The test
+    therefore compares the Newton iteration count of every pass, allows <= 3 passes to differ by one, and holds the record of
+    such a pass and the following one to 3 x TOLITER of their own magnitude."""
     gpu = REFDIR / f"{name}_b200"
     if not gpu.exists() or not (GOLD / f"{gold}_result_force.txt").exists():
         pytest.skip("example binary or golden records missing")
@@ -123,7 +135,15 @@ def test_brittle_example_matches_serial_reference(tmp_path, name, gold):
     f, d = _table(tmp_path / "result_force.txt"), _table(tmp_path / "result_disp.txt")
     n = min(len(f), len(d), len(gf)) - 1          # the GPU run was cut by the time budget: drop its last record
     assert n >= 30, n
-    nf, wf = _compare_tables_to_peak(f[:n], gf[:n], 1e-7, "force")
+    log = (tmp_path / "run.log").read_text()
+    steps_passes = [(int(a), int(b)) for a, b in re.findall(r"Loading step (\d+) has finished in (\d+) iterations", log)]
+    passes = [b for _, b in steps_passes]
+    gold_passes = [int(x) for x in re.search(r"newton_passes ([\d ]+)", (GOLD / f"{gold}_log_summary.txt").read_text()).group(1).split()]
+    m = min(len(passes), len(gold_passes), n)
+    differ = [k for k in range(m) if passes[k] != gold_passes[k]]
+    assert len(differ) <= 3 and all(abs(passes[k] - gold_passes[k]) == 1 for k in differ), (differ, passes[:m], gold_passes[:m])
+    relaxed = {steps_passes[k][0] for k in differ} | {steps_passes[k][0] + 1 for k in differ}   # load steps of those passes + the next
+    nf, wf = _compare_tables_to_peak(f[:n], gf[:n], 1e-7, "force", relaxed, 3e-4)
     nd, wd = _compare_tables_to_peak(d[:n], gd[:n], 2e-8, "disp")
     last_step = int(gf[n - 1][0])
     def blocks(path):
@@ -138,7 +158,7 @@ def test_brittle_example_matches_serial_reference(tmp_path, name, gold):
     assert bg == bc, "broken-bond logs diverge"
     broken = sum(1 for ln in bc if not ln.startswith("TIMESTEP"))
     assert broken >= 2, "the compared prefix contains no breaking event"
-    print(f"{name}: {nf} force records agree to {wf:.1e}, {nd} disp records to {wd:.1e} (serial reference), load steps < {last_step}: "
+    print(f"{name}: {nf} force records agree to {wf:.1e} of the peak ({len(differ)} passes with another Newton count), {nd} disp records to {wd:.1e} (serial reference), load steps < {last_step}: "
           f"{broken} broken bonds logged identically")
 
 
