@@ -13,6 +13,8 @@
 // O(N^2) all-pairs loop; here the candidates come from the uniform cell grid (lpmb_topology.cu) built
 // over xyz_initial with cell size 3*damage_L, i.e. 27 cells per particle.  The Gaussian uses exp(), so
 // this kernel is compared at 1e-12 relative, not bit for bit.
+#include <algorithm>
+
 #include "lpmb_internal.cuh"
 
 #define DT 128
@@ -313,10 +315,10 @@ bwise_nonlocal_break_kernel(int N, int Np, const int *__restrict__ nbi, const in
 // brittle: candidates with dL/L0 >= critical_bstrain, appended to a device list (order restored on the host)
 __global__ void __launch_bounds__(DT)
 brittle_candidates_kernel(int N, int Np, int nn, const int *__restrict__ nbi, const double *__restrict__ dL, const double *__restrict__ L0,
-                          double crit, int cap, int *__restrict__ count, int *__restrict__ keys, double *__restrict__ strain)
+                          double crit, int cap, int *__restrict__ count, int *__restrict__ keys, double *__restrict__ strain, int own0, int own1)
 {
     const int i = blockIdx.x * DT + threadIdx.x;
-    if (i >= N)
+    if (i >= N || i < own0 || i >= own1)   // slab runs: every bond is a candidate on the rank that owns its particle
         return;
     const int n = nbi[i];
     for (int j = 0; j < n; j++) {
@@ -419,7 +421,11 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
         }
         cudaFree(newly);
     } else if (plmode == 6) {
-        LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "brittle damage (global selection of the nbreak largest strains) is single-GPU only");
+        // Slab runs (SURVEY 8(e) / constitutive.c:1489-1520): the nbreak largest strains are selected GLOBALLY.  Every rank lists
+        // the candidates among the bonds of its owned particles, the lists travel to all ranks (two all-gathers: sizes, then
+        // keys + strains padded to the longest list), and every rank runs the reference's selection on the same global list --
+        // rank order = ascending global particle index, so the list is in the reference's scan order -- and applies the winners
+        // that fall on its owned particles or on its ghosts with complete stars.
         LPMB_REQUIRE(c->params.count("critical_bstrain") && c->params.count("nbreak"), LPMB_ERR_STATE, "critical_bstrain / nbreak not set");
         const int cap = 1 << 16;
         int *keys;
@@ -427,73 +433,141 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
         LPMB_CUDA(cudaMalloc(&keys, cap * sizeof(int)));
         LPMB_CUDA(cudaMalloc(&strain, cap * sizeof(double)));
         brittle_candidates_kernel<<<g, DT, 0, c->stream>>>(N, Np, nn, nbi, fptr<double>(c, "dL"), fptr<double>(c, "distance_initial"),
-                                                           param(c, "critical_bstrain"), cap, d_count, keys, strain);
+                                                           param(c, "critical_bstrain"), cap, d_count, keys, strain, lpmb_own0(c), lpmb_own1(c));
         LPMB_LAUNCH_CHECK(c);
         int k = 0;
         LPMB_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         LPMB_CUDA(cudaStreamSynchronize(c->stream));
-        if (k > cap) {
-            cudaFree(keys);
-            cudaFree(strain);
-            cudaFree(d_count);
-            lpmb_set_error("updateBrittleDamage: %d candidate bonds (the reference's b_cr[] holds 400, constitutive.c:1444)", k);
-            return LPMB_ERR_UNSUPPORTED;
-        }
-        *broken_out = k;  // the reference returns the candidate count even when it breaks only nbreak of them
-        if (k > 0) {
+        // this rank's candidates in scan order (i, then j ascending == key ascending)
+        std::vector<long long> bi;
+        std::vector<double> bs;
+        bool overflow = k > cap;
+        if (!overflow && k > 0) {
             std::vector<int> hk(k);
             std::vector<double> hs(k);
             LPMB_D2H(c, hk.data(), keys, k * sizeof(int));
             LPMB_D2H(c, hs.data(), strain, k * sizeof(double));
-            // restore the reference's scan order (i, then j ascending == key ascending)
             std::vector<int> ord(k);
             for (int t = 0; t < k; t++)
                 ord[t] = t;
-            for (int a = 1; a < k; a++) {  // insertion sort by key (k is tiny)
-                const int v = ord[a];
-                int b = a - 1;
-                while (b >= 0 && hk[ord[b]] > hk[v]) {
-                    ord[b + 1] = ord[b];
-                    b--;
-                }
-                ord[b + 1] = v;
-            }
-            std::vector<int> bi(k);
-            std::vector<double> bs(k);
+            std::sort(ord.begin(), ord.end(), [&](int a, int b2) { return hk[a] < hk[b2]; });   // keys are unique
+            bi.resize(k);
+            bs.resize(k);
             for (int t = 0; t < k; t++) {
                 bi[t] = hk[ord[t]];
                 bs[t] = hs[ord[t]];
             }
+        }
+        long long gshift = 0;   // global index of a local particle = local index + gshift
+        if (c->world > 1) {
+            // sizes: {owned particles, candidates (-1: overflow)} of every rank
+            LPMB_TRY(lpmb_ensure_staging(c, (size_t)(c->world + 1) * 2 * sizeof(long long)));
+            long long mine[2] = {(long long)(lpmb_own1(c) - lpmb_own0(c)), overflow ? -1ll : (long long)k};
+            long long *d_mine = (long long *)c->staging, *d_all = d_mine + 2;
+            LPMB_H2D(c, d_mine, mine, sizeof(mine));
+            LPMB_TRY(lpmb_dist_allgather_bytes(c, d_mine, d_all, sizeof(mine)));
+            std::vector<long long> all((size_t)c->world * 2);
+            LPMB_D2H(c, all.data(), d_all, all.size() * sizeof(long long));
+            long long g0 = 0, kmax = 0, ktot = 0;
+            for (int r = 0; r < c->world; r++) {
+                if (r < c->rank)
+                    g0 += all[2 * r];
+                overflow = overflow || all[2 * r + 1] < 0;
+                kmax = std::max(kmax, all[2 * r + 1]);
+                ktot += std::max(0ll, all[2 * r + 1]);
+            }
+            overflow = overflow || ktot > cap;
+            gshift = g0 - lpmb_own0(c);
+            if (!overflow && ktot > 0) {
+                // keys (global, 64-bit) and strains, padded to the longest list
+                const size_t per = (size_t)kmax * 16;
+                void *d_send = nullptr, *d_recv = nullptr;
+                LPMB_CUDA(cudaMalloc(&d_send, per));
+                LPMB_CUDA(cudaMalloc(&d_recv, per * c->world));
+                std::vector<long long> sk(kmax, 0);
+                std::vector<double> ss(kmax, 0.0);
+                for (int t = 0; t < k; t++) {
+                    sk[t] = (bi[t] / nn + gshift) * nn + bi[t] % nn;
+                    ss[t] = bs[t];
+                }
+                LPMB_H2D(c, d_send, sk.data(), (size_t)kmax * 8);
+                LPMB_H2D(c, (char *)d_send + (size_t)kmax * 8, ss.data(), (size_t)kmax * 8);
+                int rc2 = lpmb_dist_allgather_bytes(c, d_send, d_recv, per);
+                std::vector<char> h(per * c->world);
+                if (rc2 == LPMB_OK)
+                    LPMB_D2H(c, h.data(), d_recv, h.size());
+                cudaFree(d_send);
+                cudaFree(d_recv);
+                if (rc2 != LPMB_OK) {
+                    cudaFree(keys);
+                    cudaFree(strain);
+                    cudaFree(d_count);
+                    return rc2;
+                }
+                bi.clear();
+                bs.clear();
+                for (int r = 0; r < c->world; r++) {
+                    const long long *rk = (const long long *)(h.data() + per * r);
+                    const double *rs = (const double *)(h.data() + per * r + (size_t)kmax * 8);
+                    for (long long t = 0; t < all[2 * r + 1]; t++) {
+                        bi.push_back(rk[t]);
+                        bs.push_back(rs[t]);
+                    }
+                }
+            }
+            k = (int)ktot;
+        }
+        if (overflow) {
+            cudaFree(keys);
+            cudaFree(strain);
+            cudaFree(d_count);
+            lpmb_set_error("updateBrittleDamage: more than %d candidate bonds (the reference's b_cr[] holds 400, constitutive.c:1444)", cap);
+            return LPMB_ERR_UNSUPPORTED;
+        }
+        *broken_out = k;  // the reference returns the candidate count even when it breaks only nbreak of them
+        if (k > 0) {
             const int nbreak = (int)param(c, "nbreak");
             int first = 0;
             if (k > nbreak) {
                 // the reference's shell sort, verbatim in behaviour (not stable: ties resolved exactly as there)
                 for (int r = k / 2; r >= 1; r = r / 2)
-                    for (int a = r; a < k; ++a) {
-                        const int ti = bi[a];
-                        const double tb = bs[a];
-                        int b = a - r;
-                        while (b >= 0 && bs[b] > tb) {
-                            bs[b + r] = bs[b];
-                            bi[b + r] = bi[b];
-                            b = b - r;
+                    for (int a2 = r; a2 < k; ++a2) {
+                        const long long ti = bi[a2];
+                        const double tb = bs[a2];
+                        int b2 = a2 - r;
+                        while (b2 >= 0 && bs[b2] > tb) {
+                            bs[b2 + r] = bs[b2];
+                            bi[b2 + r] = bi[b2];
+                            b2 = b2 - r;
                         }
-                        bs[b + r] = tb;
-                        bi[b + r] = ti;
+                        bs[b2 + r] = tb;
+                        bi[b2 + r] = ti;
                     }
                 first = k - nbreak;
             }
             const int nb = k - first;
-            LPMB_H2D(c, keys, bi.data() + first, nb * sizeof(int));
-            brittle_apply_kernel<<<lpmb_blocks(nb, 128), 128, 0, c->stream>>>(nb, nn, Np, keys, broken, dD0, w);
-            c->launches++;
+            // winners on this rank: owned particles and the ghosts whose stars are complete (same slot order as on their owner)
+            const int lo = c->world > 1 ? lpmb_own0(c) - c->narrow_recv_lo : 0, hi = c->world > 1 ? lpmb_own1(c) + c->narrow_recv_hi : N;
+            std::vector<int> mine;
+            for (int t = 0; t < nb; t++) {
+                const long long li = bi[first + t] / nn - gshift;
+                if (li >= lo && li < hi)
+                    mine.push_back((int)li * nn + (int)(bi[first + t] % nn));
+            }
+            if (!mine.empty()) {
+                LPMB_H2D(c, keys, mine.data(), mine.size() * sizeof(int));
+                brittle_apply_kernel<<<lpmb_blocks((int)mine.size(), 128), 128, 0, c->stream>>>((int)mine.size(), nn, Np, keys, broken, dD0, w);
+                c->launches++;
+            }
             if (pairs && max_pairs > 0) {
+                // (particle, neighbour) of every broken bond in GLOBAL indices; the neighbour is -1 where this rank does not hold the particle
                 std::vector<int> hnbr((size_t)nn * Np);
                 LPMB_D2H(c, hnbr.data(), nbr, hnbr.size() * sizeof(int));
                 for (int t = 0; t < nb && t < max_pairs; t++) {
-                    const int i = bi[first + t] / nn, j = bi[first + t] % nn;
-                    pairs[2 * t] = i;
-                    pairs[2 * t + 1] = hnbr[(size_t)j * Np + i];
+                    const long long gi = bi[first + t] / nn, li = gi - gshift;
+                    const int j = (int)(bi[first + t] % nn);
+                    pairs[2 * t] = (int)gi;
+                    pairs[2 * t + 1] = (li >= 0 && li < N) ? (int)(hnbr[(size_t)j * Np + li] + gshift) : -1;
                 }
             }
         }
