@@ -178,9 +178,13 @@ extern "C" int lpmb_snapshot_load(lpmb_ctx *c, const char *path)
     // derived structures: block pattern of K from the neighbour lists (values are re-assembled by the caller),
     // DoF mask from the BC index fields
     c->K.values_ready = false;
+    const bool had_bricks = lpmb_brick_active(c);
     lpmb_brick_touch(c);
-    if (c->fields.count("neighbors") && c->fields.count("nsign"))
-        LPMB_TRY(lpmb_rebuild_connectivity(c));
+    if (c->fields.count("neighbors") && c->fields.count("nsign")) {
+        LPMB_TRY(lpmb_rebuild_connectivity(c));   // releases the brick mirror of the previous pattern
+        if (had_bricks)                           // ... which the resumed run would silently lose (CG on the full-format kernel)
+            LPMB_TRY(lpmb_matrix_enable_bricks(c, 1));
+    }
     if (c->fields.count("dispBC_index") && c->fields.count("fix_index"))
         LPMB_TRY(lpmb_refresh_mask(c));
     return LPMB_OK;

@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT))
 KEYS = ("xyz", "F", "stress_tensor", "dLp0", "damage_nonlocal0", "damage_w", "damage_broken", "Pin")
 
 
-def run_steps(c, first_global=0, n_total=None):
+def run_steps(c):
     its, nrs = [], []
     for _ in range(2):          # two consecutive Newton iterations (no snapshot restore): state really evolves
         it, nr = c.newton_iteration(0, 1)
@@ -29,26 +29,26 @@ def run_steps(c, first_global=0, n_total=None):
     broken, _ = c.update_damage(0)
     c.update_crack()
     c.switch_state(1)
-    # Brittle law on slabs (updateBrittleDamage, constitutive.c:1437-1526: the nbreak largest bond strains are selected
-    # GLOBALLY).  Bond stretches are replaced by a hash of the GLOBAL bond id -- well separated values, so that the selection
-    # cannot hinge on the 1e-15 differences between a slab run and a single-GPU run -- with ~60 candidates above the critical
-    # strain and nbreak = 7 of them to break; then one more assembly + Newton iteration on the damaged lattice (the ghosts'
-    # broken flags enter the owned rows through the neighbours' shell sums).
-    nn = c.nn
-    n_local = c.N
+    return its, nrs, broken
+
+
+def brittle_phase(c, first_global=0, n_total=None):
+    """Brittle law on slabs (updateBrittleDamage, constitutive.c:1437-1526: the nbreak largest bond strains are selected
+    GLOBALLY).  Bond stretches are replaced by a hash of the GLOBAL bond id -- well separated values, so that the selection
+    cannot hinge on the 1e-15 differences between a slab run and a single-GPU run -- with ~60 candidates above the critical
+    strain and nbreak = 7 of them to break; then the elastic law on the damaged lattice (the ghosts' broken flags enter the
+    owned rows through the neighbours' shell sums, so F / Pin of the owned rows check them too)."""
+    nn, n_local = c.nn, c.N
     n_total = n_total or n_local
     L0 = c.get_field("distance_initial")
-    key = (first_global + np.arange(n_local, dtype=np.uint64))[:, None] * np.uint64(nn) + np.arange(nn, dtype=np.uint64)[None, :]
+    key = (np.uint64(first_global) + np.arange(n_local, dtype=np.uint64))[:, None] * np.uint64(nn) + np.arange(nn, dtype=np.uint64)[None, :]
     h = ((key * np.uint64(2654435761)) % np.uint64(1000003)).astype(np.float64) / 1000003.0
     c.set_field("dL", h * 2e-3 * L0)
     c.set_params(critical_bstrain=2e-3 * (1.0 - 60.0 / (n_total * nn)), nbreak=7.0)
     cand, pairs = c.update_damage(6)
     c.update_crack()
-    c.fd_stiffness(False)
-    it, nr = c.newton_iteration(0, 1)
-    its.append(it)
-    nrs.append(nr)
-    return its, nrs, (broken, cand, sorted(int(p) for p in np.asarray(pairs)[:, 0] if p >= 0) if len(pairs) else [])
+    c.bond_force(6)
+    return [cand] + (sorted(int(p) for p in np.asarray(pairs)[:, 0] if p >= 0) if len(pairs) else [])
 
 
 def child(rank, world, n, d):
@@ -69,9 +69,8 @@ def child(rank, world, n, d):
         uid = uid_file.read_bytes()
     slab = partition.make_slab(n, n * n, rank, world)
     c, info = bench.build_workload(lpm, n, rank, slab=slab, unique_id=uid)
-    its, nrs, broken = run_steps(c, slab.first_global, n ** 3)
+    its, nrs, broken = run_steps(c)
     own = slice(slab.own0, slab.own1)
-    out = {k: np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own]) for k in KEYS}
     # per-rank snapshot / resume of a slab run (lpmb_io.cu): save, run on, wipe, load, run on again -> identical
     snap = Path(d) / f"rank{rank}.snap"
     c.snapshot_save(snap)
@@ -97,7 +96,11 @@ def child(rank, world, n, d):
           f"loaded-vs-loaded {np.abs(xb - xb2).max():.3e}", flush=True)
     assert b == b2 and np.array_equal(xb, xb2), ("two resumes from the same slab snapshot differ", b, b2)
     assert a[0] == b[0] and abs(a[1] - b[1]) <= 1e-12 * abs(a[1]) and np.abs(xa - xb).max() <= 1e-13, ("slab snapshot resume differs", a, b)
-    np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken[0], broken[1]] + broken[2]), mode=np.array([c.dist_mode()]),
+    # back to the state after the load step, then the brittle selection across the slabs
+    c.snapshot_load(snap)
+    brittle = brittle_phase(c, slab.first_global, n ** 3)
+    out = {k: np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own]) for k in KEYS}
+    np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken] + brittle), mode=np.array([c.dist_mode()]),
              norm0=np.array([info["norm_residual0"]]), spmv_bytes=np.array([c.spmv_bytes_bricks()]), **out)
     c.close()
 
@@ -119,7 +122,7 @@ def main():
         lpm = importlib.import_module("lpm-c_b200")
         c1, info1 = bench.build_workload(lpm, n, 0, bricks=False)   # full-format SELL kernel as the cross-check
         its1, nrs1, broken1 = run_steps(c1)
-        broken1 = [broken1[0], broken1[1]] + broken1[2]
+        broken1 = [broken1] + brittle_phase(c1)
         its, nrs, broken = list(parts[0]["its"]), list(parts[0]["nrs"]), [int(x) for x in parts[0]["broken"]]
         assert all([int(x) for x in p["broken"]] == broken for p in parts), "ranks disagree on the broken bonds"
         print(f"world={world} n={n}: CG iterations dist {its} single {its1}; residual norms dist {nrs} single {nrs1}; "
