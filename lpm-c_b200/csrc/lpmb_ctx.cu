@@ -462,6 +462,8 @@ extern "C" void lpmb_destroy(lpmb_ctx *c)
     cudaFree(c->cg.partials);
     cudaFree(c->cg.scal);
     cudaFree(c->cg.counters);
+    if (c->cg.graph)
+        cudaGraphExecDestroy(c->cg.graph);
     if (c->cg.h_scal)
         cudaFreeHost(c->cg.h_scal);
     cudaFree(c->mask);

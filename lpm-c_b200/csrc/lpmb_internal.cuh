@@ -107,6 +107,9 @@ struct CGWork {
     unsigned int *counters = nullptr;                                 // [4] last-block tickets (gather, update, direction)
     double *z = nullptr;                                              // [D][Np] preconditioned residual (fast mode only)
     int max_blocks = 0;
+    // small lattices (row-packed SpMV, one GPU): a batch of 16 CG iterations = 48 launches replayed as ONE CUDA graph
+    cudaGraphExec_t graph = nullptr;
+    unsigned long long graph_key[12] = {0};
 };
 
 struct lpmb_ctx {

@@ -908,6 +908,42 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     LPMB_LAUNCH_CHECK(c);
     const int batch = 16;
     int parity = 0, issued = 0;
+    // Small lattices (BASELINE configs 1-4: 7-75 k particles, matrix L2-resident): an iteration is ~12 us of kernels, and three
+    // launches of 2-4 us each are a third of it.  The batch of 16 iterations between two convergence polls is captured ONCE
+    // as a CUDA graph (every argument is a device pointer or a per-solve constant; alpha / beta / the stop flag live on the
+    // device) and replayed -- same kernels, same order, same bits.  Param cg_graph = 0 switches it off.
+    const bool use_graph = !dist && !brick && !c->profile && rows_active(c) && maxit >= batch && param(c, "cg_graph", 1.0) != 0.0;
+    if (use_graph) {
+        LPMB_TRY(rows_prepare(c));
+        const unsigned long long key[12] = {(unsigned long long)vr, (unsigned long long)vp, (unsigned long long)vap, (unsigned long long)vx,
+                                            (unsigned long long)m, (unsigned long long)c->K.rptr, (unsigned long long)c->K.rcol,
+                                            (unsigned long long)c->K.rval, (unsigned long long)n, (unsigned long long)maxit,
+                                            (unsigned long long)vg * 65536ull + (unsigned long long)sg, (unsigned long long)w.partials};
+        if (!w.graph || memcmp(key, w.graph_key, sizeof(key)) != 0) {
+            if (w.graph) {
+                cudaGraphExecDestroy(w.graph);
+                w.graph = nullptr;
+            }
+            cudaGraph_t g = nullptr;
+            LPMB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = LPMB_OK, par = 0;
+            for (int b = 0; b < batch && rc == LPMB_OK; b++, par ^= 1) {
+                rc = launch_spmv(c, vp, vap, true, use_mask);
+                cg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vp, vap, vx, vr, n, part_a, sg, part_b, w.scal, par, nowait, PeerPublish());
+                cg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(vr, vp, n, part_b, vg, w.scal, par, maxit, nowait, nullptr, w.counters + 2);
+            }
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+            if (rc != LPMB_OK || ce != cudaSuccess || cudaGraphInstantiate(&w.graph, g, 0) != cudaSuccess) {
+                (void)cudaGetLastError();
+                w.graph = nullptr;   // fall back to plain launches (same kernels)
+            } else {
+                memcpy(w.graph_key, key, sizeof(key));
+            }
+            if (g)
+                cudaGraphDestroy(g);
+            c->launches -= batch;   // launch_spmv counted the captured launches; they have not run
+        }
+    }
     if (c->profile && c->prof_events.empty()) {
         c->prof_events.resize(2 * batch);
         for (auto &e : c->prof_events)
@@ -915,6 +951,11 @@ static int cg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, in
     }
     for (;;) {
         const int issued0 = issued;
+        if (use_graph && w.graph && maxit - issued >= batch) {
+            LPMB_CUDA(cudaGraphLaunch(w.graph, c->stream));   // 16 iterations: parity returns to 0 after an even batch
+            issued += batch;
+            c->launches += 3 * batch;
+        } else
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
             PeerWait hw;  // what this rank's SpMV has to wait for (peer halo push only)
             if (peer_halo)

@@ -1,5 +1,5 @@
 """small-lattice regime (BASELINE configs 1-4 live here: matrix in L2, everything launch / latency bound): time the
-device-resident CG and the whole Newton iteration on an n^3 block of the bench workload.  python scripts/small_cg_profile.py [n=21] [reps=20]"""
+device-resident CG and the whole Newton iteration on an n^3 block of the bench workload.  python scripts/small_cg_profile.py [n=21] [reps=20] [cg_graph=1]"""
 import importlib, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
@@ -9,6 +9,8 @@ lpm = importlib.import_module("lpm-c_b200")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 21
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 c, info = bench.build_workload(lpm, n, 0, bricks=False)
+if len(sys.argv) > 3:
+    c.set_params(cg_graph=float(sys.argv[3]))    # 1 = batches of 16 iterations replayed as a CUDA graph (default), 0 = plain launches
 for _ in range(3):
     bench.one_step(c)
 c.synchronize()

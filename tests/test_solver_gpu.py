@@ -72,6 +72,30 @@ def test_masked_cg_equals_bc_modified_matrix(ctx6, golden):
     assert np.all(x[golden["s1.bc.dispBC_index"] == 0] == 0.0)
 
 
+def test_graph_replayed_cg_batches_are_bit_identical(ctx6, golden):
+    """small lattices: the 16 iterations between two convergence polls are replayed as one CUDA graph (param cg_graph, default
+    on) -- same kernels, same order: iteration counts and every bit of the solution equal the plain-launch path, also when the
+    graph is re-captured for another mask / maxit and when a solve ends inside a batch"""
+    ctx6.matrix_from_upper_csr(golden["s1.n0.K_bc"])
+    res = {}
+    for graph in (1.0, 0.0, 1.0):
+        ctx6.set_params(cg_graph=graph)
+        res.setdefault(graph, []).append(ctx6.solve_cg(golden["s1.n0.rhs"]))
+        res[graph].append(ctx6.solve_cg(golden["s1.n0.rhs"], maxit=19))   # 23 needed: one graph batch + 3 plain iterations
+    ctx6.matrix_from_upper_csr(golden["s1.fd.K_global"])
+    ctx6.set_dof_mask(golden["s1.bc.dispBC_index"], golden["s1.bc.fix_index"])
+    for graph in (1.0, 0.0):
+        ctx6.set_params(cg_graph=graph)
+        res[graph].append(ctx6.solve_cg(golden["s1.rr.residual"], use_mask=True))
+    assert res[1.0][0][1] == int(golden["s1.n0.cg_iters"][0]) and res[1.0][0][2]
+    assert res[1.0][1][1] == 19 and not res[1.0][1][2]
+    plain = res[0.0]
+    for k, (x, it, ok) in enumerate(res[1.0][:2] + res[1.0][4:5]):
+        assert it == plain[k][1] and ok == plain[k][2] and np.array_equal(x, plain[k][0]), k
+    for k in (2, 3):   # the second pass with the graph (re-used executable)
+        assert np.array_equal(res[1.0][k][0], plain[k - 2][0]) and res[1.0][k][1] == plain[k - 2][1]
+
+
 def test_cg_zero_rhs_and_maxit(ctx6, golden):
     ctx6.matrix_from_upper_csr(golden["s1.n0.K_bc"])
     x, iters, ok = ctx6.solve_cg(np.zeros(648))
