@@ -88,7 +88,9 @@ long long lpmb_launch_count(lpmb_ctx *ctx);
 void *lpmb_stream(lpmb_ctx *ctx);
 
 /* scalar parameters by reference name: radius, particle_volume, J2_H, J2_xi, damage_L,
- * damage_threshold, damagec_A, damageb_A, critical_bstrain, dtime, ... ; ints: nbreak, plmode */
+ * damage_threshold, damagec_A, damageb_A, critical_bstrain, dtime, ... ; ints: nbreak, plmode.
+ * Implementation switches: cg_precond, fd_variant, fd_tab_mb, cp_warp, cg_graph, j2_fused,
+ * spmv_rows, spmv_rows_max, brick_trim, brick_lazy_wait, peer_comm. */
 int lpmb_set_param(lpmb_ctx *ctx, const char *name, double value);
 int lpmb_get_param(lpmb_ctx *ctx, const char *name, double *value);
 
