@@ -196,6 +196,55 @@ int lpmb_dist_allreduce_sum(lpmb_ctx *c, double *d_buf, int count)
     return LPMB_OK;
 }
 
+// contiguous fp64 ranges with rank-1 ("lo") and rank+1 ("hi"): `comps` components `stride` apart, n elements each way
+// (multigrid levels of the fast mode: two lattice layers of a level's vector)
+int lpmb_dist_neighbor_doubles(lpmb_ctx *c, double *base, long long stride, int comps, long long send_lo_off, long long recv_lo_off,
+                               long long send_hi_off, long long recv_hi_off, long long n)
+{
+    if (c->world <= 1 || n <= 0)
+        return LPMB_OK;
+    LPMB_REQUIRE(c->nccl, LPMB_ERR_STATE, "lpmb_dist_init not called");
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->nccl);
+    LPMB_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < comps; k++) {
+        double *b = base + (size_t)k * stride;
+        if (c->rank > 0) {
+            LPMB_NCCL(g_nccl.Send(b + send_lo_off, n, ncclDouble, c->rank - 1, comm, c->stream));
+            LPMB_NCCL(g_nccl.Recv(b + recv_lo_off, n, ncclDouble, c->rank - 1, comm, c->stream));
+        }
+        if (c->rank < c->world - 1) {
+            LPMB_NCCL(g_nccl.Send(b + send_hi_off, n, ncclDouble, c->rank + 1, comm, c->stream));
+            LPMB_NCCL(g_nccl.Recv(b + recv_hi_off, n, ncclDouble, c->rank + 1, comm, c->stream));
+        }
+    }
+    LPMB_NCCL(g_nccl.GroupEnd());
+    return LPMB_OK;
+}
+
+// every rank contributes the range [offs[rank], offs[rank] + counts[rank]) of each component and ends up with all ranges
+// (variable-length all-gather in place; the first replicated multigrid level)
+int lpmb_dist_allgatherv_doubles(lpmb_ctx *c, double *base, long long stride, int comps, const long long *offs, const long long *counts)
+{
+    if (c->world <= 1)
+        return LPMB_OK;
+    LPMB_REQUIRE(c->nccl, LPMB_ERR_STATE, "lpmb_dist_init not called");
+    ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->nccl);
+    LPMB_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < comps; k++) {
+        double *b = base + (size_t)k * stride;
+        for (int r = 0; r < c->world; r++) {
+            if (r == c->rank)
+                continue;
+            if (counts[c->rank] > 0)
+                LPMB_NCCL(g_nccl.Send(b + offs[c->rank], counts[c->rank], ncclDouble, r, comm, c->stream));
+            if (counts[r] > 0)
+                LPMB_NCCL(g_nccl.Recv(b + offs[r], counts[r], ncclDouble, r, comm, c->stream));
+        }
+    }
+    LPMB_NCCL(g_nccl.GroupEnd());
+    return LPMB_OK;
+}
+
 // exchange a named per-particle / DoF fp64 field (harness + damage path)
 extern "C" int lpmb_dist_exchange_field(lpmb_ctx *c, const char *name, int wide)
 {

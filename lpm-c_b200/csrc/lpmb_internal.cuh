@@ -212,6 +212,9 @@ int lpmb_dist_allreduce_sum(lpmb_ctx *c, double *d_buf, int count);     // in-st
 void lpmb_dist_release(lpmb_ctx *c);
 
 int lpmb_dist_allgather_bytes(lpmb_ctx *c, const void *d_send, void *d_recv, size_t bytes_per_rank);
+int lpmb_dist_neighbor_doubles(lpmb_ctx *c, double *base, long long stride, int comps, long long send_lo_off, long long recv_lo_off,
+                               long long send_hi_off, long long recv_hi_off, long long n);
+int lpmb_dist_allgatherv_doubles(lpmb_ctx *c, double *base, long long stride, int comps, const long long *offs, const long long *counts);
 int lpmb_dist_neighbor_ints(lpmb_ctx *c, const int *to_lo, int n_to_lo, const int *to_hi, int n_to_hi, int *from_lo, int n_from_lo, int *from_hi,
                             int n_from_hi);
 

@@ -27,8 +27,20 @@
 // Cost per V-cycle at 216^3: 5 fine-level stencil passes over 30 M unknowns with no matrix traffic (x is read through
 // L1/L2, 61 x 18 flop per site) + 1/7 of that for the coarse levels -- against 24 GB of matrix per real SpMV.
 //
-// Scope: one GPU, 3-D simple-cubic FULL blocks numbered x-fastest (initialization.c:266-284) with >= 5 sites per edge;
-// anything else -> LPMB_ERR_UNSUPPORTED (the caller fails loudly; there is no silent fallback to another solver).
+// Scope: 3-D simple-cubic FULL blocks numbered x-fastest (initialization.c:266-284) with >= 5 sites per edge, on one GPU or
+// on z-slabs (below); anything else -> LPMB_ERR_UNSUPPORTED (the caller fails loudly; no silent fallback to another solver).
+//
+// Slab runs (world > 1, param mg_dist = 1, default): ONE global hierarchy, distributed.  Coarse site I sits on fine site 2I
+// in GLOBAL lattice coordinates, a rank owns the coarse layers whose fine layer it owns, and every distributed level keeps
+// [2 ghost layers | owned layers | 2 ghost layers] (level 0: the context's own 4-layer ghosts).  Before every stencil pass
+// (smoother sweep, residual) the two ghost layers of the iterate are refreshed from the neighbours, the residual's before
+// the restriction, the coarse correction's before the prolongation -- 6 small exchanges per level and V-cycle; boundary
+// classes and interpolation weights use global coordinates, so the operator is the single-GPU one.  From the first level on
+// which some rank would own fewer than 2 layers the level is REPLICATED: the ranks' restricted residuals are all-gathered and
+// every rank runs the remaining (tiny) levels redundantly.  All ranks use the stencil read by the middle rank (a symmetric
+// preconditioner needs one operator).  mg_dist = 0 keeps a hierarchy per slab without any communication: block-Jacobi over
+// the slabs, symmetric positive definite but without coupling across the interfaces (41 instead of 9 iterations on two slabs
+// of the 216^3 block, profiles/r02af_bench_n2.log).
 #include <algorithm>
 #include <cmath>
 
@@ -49,6 +61,11 @@ struct MGLevel {
     double *dinv = nullptr;        // [729][9] inverse diagonal block per boundary class
     double *mask = nullptr;        // [3][stride] (level 0: the solve's mask, not owned)
     double *u = nullptr, *u2 = nullptr, *f = nullptr, *res = nullptr;   // [3][stride] (level 0: u = caller's z, f = caller's r)
+    // slab runs: nz above = layers of the LOCAL block of this level
+    int gz0 = 0;            // global z index of local layer 0
+    int nzg = 0;            // layers of the whole level (== nz on one GPU and on replicated levels)
+    int oz0 = 0, oz1 = 0;   // owned local layers [oz0, oz1)
+    bool dist = false;      // distributed over the ranks (ghost layers refreshed by exchanges)
 };
 
 struct MGState {
@@ -61,6 +78,11 @@ struct MGState {
     int delta[MG_MAXOFF];
     int nu = 2, nu_coarse = 40;
     double omega = 0.56, omega2 = 1.39;   // damping of the odd / even sweeps (two different values = a degree-2 polynomial smoother)
+    // slab runs
+    bool dist = false;                    // distributed hierarchy (mg_dist = 1)
+    double *mask_phys = nullptr;          // [3][Np] level-0 mask of the boundary conditions alone (the solve's mask also zeroes the ghosts)
+    int lrep = -1;                        // first replicated level
+    long long gat_off[LPMB_PEER_MAXW], gat_cnt[LPMB_PEER_MAXW];   // the ranks' owned ranges of level lrep (elements per component)
 };
 
 static std::map<lpmb_ctx *, MGState> g_mg;
@@ -74,6 +96,7 @@ void lpmb_mg_release(lpmb_ctx *c)
     MGState &M = it->second;
     if (c->device >= 0 && c->device < 64 && g_mg_const_owner[c->device] == c)
         g_mg_const_owner[c->device] = nullptr;
+    cudaFree(M.mask_phys);
     for (int l = 0; l < M.nlev; l++) {
         MGLevel &L = M.lev[l];
         cudaFree(L.dinv);
@@ -113,8 +136,9 @@ __device__ __forceinline__ int mg_axis_class(int i, int n) { return min(i, 2) + 
 // MODE 2: out = omega * mask .* Dinv f                  (first sweep from u = 0: no stencil pass)
 template <int MODE>
 __global__ void __launch_bounds__(128)
-mg_stencil_kernel(int nx, int ny, int nz, long long stride, double scale, const double *__restrict__ dinv, const double *__restrict__ mask,
-                  const double *__restrict__ u, const double *__restrict__ f, double *__restrict__ out, double omega, const double *__restrict__ done)
+mg_stencil_kernel(int nx, int ny, int nz, int gz0, int nzg, long long stride, double scale, const double *__restrict__ dinv,
+                  const double *__restrict__ mask, const double *__restrict__ u, const double *__restrict__ f, double *__restrict__ out, double omega,
+                  const double *__restrict__ done)
 {
     if (done && done[0] != 0.0)
         return;
@@ -150,7 +174,7 @@ mg_stencil_kernel(int nx, int ny, int nz, long long stride, double scale, const 
     }
     // constrained DoFs carry no residual: the block solve must not leak their (unmasked) residual into the free ones
     r0 *= m0, r1 *= m1, r2 *= m2;
-    const double *D = dinv + 9 * (mg_axis_class(ix, nx) + 9 * (mg_axis_class(iy, ny) + 9 * mg_axis_class(iz, nz)));
+    const double *D = dinv + 9 * (mg_axis_class(ix, nx) + 9 * (mg_axis_class(iy, ny) + 9 * mg_axis_class(iz + gz0, nzg)));   // the class is a property of the GLOBAL position
     out[i] = u0 + omega * m0 * (D[0] * r0 + D[1] * r1 + D[2] * r2);
     out[stride + i] = u1 + omega * m1 * (D[3] * r0 + D[4] * r1 + D[5] * r2);
     out[2 * stride + i] = u2 + omega * m2 * (D[6] * r0 + D[7] * r1 + D[8] * r2);
@@ -170,9 +194,9 @@ mg_stencil_kernel(int nx, int ny, int nz, long long stride, double scale, const 
 #define MG_SC_NOFF 60   // off-diagonal blocks of an interior simple-cubic block row (61 conn entries minus the particle itself)
 template <int MODE>
 __global__ void __launch_bounds__(MG_TX * MG_TY * MG_TZ)
-mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, const double *__restrict__ dinv, const double *__restrict__ mask,
-                        const double *__restrict__ u, const double *__restrict__ f, double *__restrict__ out, double omega,
-                        const double *__restrict__ done)
+mg_stencil_tiled_kernel(int nx, int ny, int nz, int gz0, int nzg, long long stride, double scale, const double *__restrict__ dinv,
+                        const double *__restrict__ mask, const double *__restrict__ u, const double *__restrict__ f, double *__restrict__ out,
+                        double omega, const double *__restrict__ done)
 {
     extern __shared__ double mg_us[];   // [3][MG_TILE_SITES]
     if (done && done[0] != 0.0)
@@ -233,7 +257,7 @@ mg_stencil_tiled_kernel(int nx, int ny, int nz, long long stride, double scale, 
         return;
     }
     r0 *= m0, r1 *= m1, r2 *= m2;
-    const double *D = dinv + 9 * (mg_axis_class(ix, nx) + 9 * (mg_axis_class(iy, ny) + 9 * mg_axis_class(iz, nz)));
+    const double *D = dinv + 9 * (mg_axis_class(ix, nx) + 9 * (mg_axis_class(iy, ny) + 9 * mg_axis_class(iz + gz0, nzg)));   // the class is a property of the GLOBAL position
     out[i] = u0 + omega * m0 * (D[0] * r0 + D[1] * r1 + D[2] * r2);
     out[stride + i] = u1 + omega * m1 * (D[3] * r0 + D[4] * r1 + D[5] * r2);
     out[2 * stride + i] = u2 + omega * m2 * (D[6] * r0 + D[7] * r1 + D[8] * r2);
@@ -248,9 +272,9 @@ static int mg_launch_stencil(lpmb_ctx *c, const MGLevel &L, const double *u, con
         // > 48 KB of dynamic shared memory: opt in (per device; cheap enough to repeat)
         LPMB_CUDA(cudaFuncSetAttribute(mg_stencil_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const dim3 grid((L.nx + MG_TX - 1) / MG_TX, (L.ny + MG_TY - 1) / MG_TY, (L.nz + MG_TZ - 1) / MG_TZ), block(MG_TX, MG_TY, MG_TZ);
-        mg_stencil_tiled_kernel<MODE><<<grid, block, smem, c->stream>>>(L.nx, L.ny, L.nz, L.stride, L.scale, L.dinv, L.mask, u, f, out, omega, done);
+        mg_stencil_tiled_kernel<MODE><<<grid, block, smem, c->stream>>>(L.nx, L.ny, L.nz, L.gz0, L.nzg, L.stride, L.scale, L.dinv, L.mask, u, f, out, omega, done);
     } else {
-        mg_stencil_kernel<MODE><<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, L.scale, L.dinv, L.mask, u, f, out, omega, done);
+        mg_stencil_kernel<MODE><<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.gz0, L.nzg, L.stride, L.scale, L.dinv, L.mask, u, f, out, omega, done);
     }
     LPMB_LAUNCH_CHECK(c);
     return LPMB_OK;
@@ -321,8 +345,8 @@ __device__ __forceinline__ double mg_w1(int f, int X, int nc)
 
 // fc = mask_c .* P^T rf     (full weighting = transpose of the trilinear interpolation)
 __global__ void __launch_bounds__(128)
-mg_restrict_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, const double *__restrict__ rf,
-                   const double *__restrict__ mask_c, double *__restrict__ fc, const double *__restrict__ done)
+mg_restrict_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, int gzf, int gzc, int nczg,
+                   const double *__restrict__ rf, const double *__restrict__ mask_c, double *__restrict__ fc, const double *__restrict__ done)
 {
     if (done && done[0] != 0.0)
         return;
@@ -332,11 +356,12 @@ mg_restrict_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, in
         return;
     const int X = (int)(I % ncx), Y = (int)((I / ncx) % ncy), Z = (int)(I / ((long long)ncx * ncy));
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    const int Zg = Z + gzc;   // global coarse layer; its fine layer 2 Zg is local fine layer 2 Zg - gzf
     for (int dz = -1; dz <= 1; dz++) {
-        const int fz = 2 * Z + dz;
+        const int fz = 2 * Zg + dz - gzf;
         if (fz < 0 || fz >= nfz)
             continue;
-        const double wz = mg_w1(fz, Z, ncz);
+        const double wz = mg_w1(fz + gzf, Zg, nczg);
         for (int dy = -1; dy <= 1; dy++) {
             const int fy = 2 * Y + dy;
             if (fy < 0 || fy >= nfy)
@@ -361,8 +386,8 @@ mg_restrict_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, in
 
 // uf += mask_f .* P uc
 __global__ void __launch_bounds__(128)
-mg_prolong_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, const double *__restrict__ uc,
-                  const double *__restrict__ mask_f, double *__restrict__ uf, const double *__restrict__ done)
+mg_prolong_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, int gzf, int gzc, int nczg,
+                  const double *__restrict__ uc, const double *__restrict__ mask_f, double *__restrict__ uf, const double *__restrict__ done)
 {
     if (done && done[0] != 0.0)
         return;
@@ -372,12 +397,13 @@ mg_prolong_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int
         return;
     const int fx = (int)(i % nfx), fy = (int)((i / nfx) % nfy), fz = (int)(i / ((long long)nfx * nfy));
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    const int X0 = fx >> 1, Y0 = fy >> 1, Z0 = fz >> 1;
-    for (int az = 0; az <= (fz & 1); az++) {
-        const int Z = Z0 + az;
-        if (Z >= ncz)
+    const int fzg = fz + gzf;   // global fine layer
+    const int X0 = fx >> 1, Y0 = fy >> 1, Z0 = fzg >> 1;
+    for (int az = 0; az <= (fzg & 1); az++) {
+        const int Zg = Z0 + az, Z = Zg - gzc;
+        if (Zg >= nczg || Z < 0 || Z >= ncz)
             continue;
-        const double wz = mg_w1(fz, Z, ncz);
+        const double wz = mg_w1(fzg, Zg, nczg);
         for (int ay = 0; ay <= (fy & 1); ay++) {
             const int Y = Y0 + ay;
             if (Y >= ncy)
@@ -402,8 +428,8 @@ mg_prolong_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int
 }
 
 // coarse DoF free only if every fine DoF in its interpolation support is free
-__global__ void mg_coarse_mask_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, const double *__restrict__ mf,
-                                      double *__restrict__ mc)
+__global__ void mg_coarse_mask_kernel(int nfx, int nfy, int nfz, long long sf, int ncx, int ncy, int ncz, long long sc, int gzf, int gzc, int nczg,
+                                      const double *__restrict__ mf, double *__restrict__ mc)
 {
     const long long nc = (long long)ncx * ncy * ncz;
     const long long I = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,10 +440,10 @@ __global__ void mg_coarse_mask_kernel(int nfx, int nfy, int nfz, long long sf, i
     for (int dz = -1; dz <= 1; dz++)
         for (int dy = -1; dy <= 1; dy++)
             for (int dx = -1; dx <= 1; dx++) {
-                const int fx = 2 * X + dx, fy = 2 * Y + dy, fz = 2 * Z + dz;
+                const int fx = 2 * X + dx, fy = 2 * Y + dy, fz = 2 * (Z + gzc) + dz - gzf;
                 if (fx < 0 || fx >= nfx || fy < 0 || fy >= nfy || fz < 0 || fz >= nfz)
                     continue;
-                if (mg_w1(fx, X, ncx) * mg_w1(fy, Y, ncy) * mg_w1(fz, Z, ncz) == 0.0)
+                if (mg_w1(fx, X, ncx) * mg_w1(fy, Y, ncy) * mg_w1(fz + gzf, Z + gzc, nczg) == 0.0)
                     continue;
                 const long long j = fx + (long long)nfx * (fy + (long long)nfy * fz);
                 for (int k = 0; k < 3; k++)
@@ -462,7 +488,10 @@ static bool invert3(const double *a, double *inv)
 // lattice dimensions + ordering check (once), level storage
 static int mg_build_levels(lpmb_ctx *c, MGState &M)
 {
-    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "cg_precond: the multigrid preconditioner runs on one GPU only");
+    // Slab runs: the hierarchy is built on the rank's LOCAL block [ghost layers | owned layers | ghost layers] -- itself a full
+    // x-fastest simple-cubic block.  The level-0 mask constrains every ghost DoF, so the V-cycle is a multigrid solve of the
+    // slab's own Dirichlet problem and the preconditioner of the whole system is block-Jacobi over the slabs (additive Schwarz
+    // without a coarse space across ranks): symmetric positive definite, no communication inside the V-cycle.
     LPMB_REQUIRE(c->dim == 3 && c->lattice == LPMB_LATTICE_SC, LPMB_ERR_UNSUPPORTED, "cg_precond: 3-D simple-cubic lattices only");
     LPMB_REQUIRE(c->params.count("radius") && c->fields.count("xyz_initial"), LPMB_ERR_STATE, "cg_precond needs radius and xyz_initial");
     const int N = c->N, Np = c->Np;
@@ -491,14 +520,49 @@ static int mg_build_levels(lpmb_ctx *c, MGState &M)
     LPMB_D2H(c, &bad, d_bad, sizeof(int));
     cudaFree(d_bad);
     LPMB_REQUIRE(!bad, LPMB_ERR_UNSUPPORTED, "cg_precond: particles are not numbered x-fastest on an axis-aligned lattice of spacing %g", q);
+    // ---- slab runs: global z-extent of every level and this rank's part of it
+    const long long lay0 = (long long)nx * ny;
+    const int W = c->world;
+    M.dist = W > 1 && param(c, "mg_dist", 1.0) != 0.0;
+    M.lrep = -1;
+    std::vector<long long> ga(W + 1, 0);   // global first owned layer of every rank on the current level (ga[W] = layers of the level)
+    int gz0 = 0;
+    if (M.dist) {
+        LPMB_REQUIRE(W <= LPMB_PEER_MAXW, LPMB_ERR_UNSUPPORTED, "cg_precond on slabs: at most %d ranks", LPMB_PEER_MAXW);
+        const int o0 = lpmb_own0(c), o1 = lpmb_own1(c);
+        LPMB_REQUIRE(o0 % lay0 == 0 && o1 % lay0 == 0, LPMB_ERR_UNSUPPORTED, "cg_precond on slabs: the owned range is not whole lattice layers");
+        LPMB_TRY(lpmb_ensure_staging(c, (size_t)(W + 1) * sizeof(long long)));
+        long long mine = (o1 - o0) / lay0, *d_mine = (long long *)c->staging, *d_all = d_mine + 1;
+        LPMB_H2D(c, d_mine, &mine, sizeof(mine));
+        LPMB_TRY(lpmb_dist_allgather_bytes(c, d_mine, d_all, sizeof(mine)));
+        std::vector<long long> all(W);
+        LPMB_D2H(c, all.data(), d_all, (size_t)W * sizeof(long long));
+        for (int r = 0; r < W; r++)
+            ga[r + 1] = ga[r] + all[r];
+        gz0 = (int)(ga[c->rank] - o0 / lay0);
+    }
     M.nlev = 0;
-    int ax = nx, ay = ny, az = nz;
+    int ax = nx, ay = ny, az = M.dist ? (int)ga[W] : nz;   // az = GLOBAL layers of the level
     double scale = 1.0;
+    bool level_dist = M.dist;
     for (;;) {
         LPMB_REQUIRE(M.nlev < MG_MAXLEV, LPMB_ERR_UNSUPPORTED, "cg_precond: too many levels");
         MGLevel &L = M.lev[M.nlev];
-        L.nx = ax, L.ny = ay, L.nz = az;
-        L.n = (long long)ax * ay * az;
+        L.nx = ax, L.ny = ay, L.nzg = az;
+        L.dist = level_dist;
+        if (M.nlev == 0) {
+            L.nz = nz, L.gz0 = gz0;
+            L.oz0 = M.dist ? (int)(lpmb_own0(c) / lay0) : 0;
+            L.oz1 = M.dist ? (int)(lpmb_own1(c) / lay0) : nz;
+        } else if (level_dist) {
+            const int A = (int)ga[c->rank], B = (int)ga[c->rank + 1];
+            L.gz0 = std::max(0, A - 2);
+            L.nz = std::min(az, B + 2) - L.gz0;
+            L.oz0 = A - L.gz0, L.oz1 = B - L.gz0;
+        } else {
+            L.nz = az, L.gz0 = 0, L.oz0 = 0, L.oz1 = az;
+        }
+        L.n = (long long)ax * ay * L.nz;
         L.stride = M.nlev == 0 ? Np : L.n;
         L.scale = scale;
         LPMB_CUDA(cudaMalloc(&L.dinv, 729 * 9 * sizeof(double)));
@@ -510,12 +574,33 @@ static int mg_build_levels(lpmb_ctx *c, MGState &M)
             LPMB_CUDA(cudaMalloc(&L.mask, (size_t)3 * L.stride * 8));
             LPMB_CUDA(cudaMalloc(&L.u, (size_t)3 * L.stride * 8));
             LPMB_CUDA(cudaMalloc(&L.f, (size_t)3 * L.stride * 8));
+            LPMB_MEMSET(c, L.mask, 0, (size_t)3 * L.stride * 8);
+            LPMB_MEMSET(c, L.u, 0, (size_t)3 * L.stride * 8);
+            LPMB_MEMSET(c, L.f, 0, (size_t)3 * L.stride * 8);
         }
         M.nlev++;
-        if (std::min(ax, std::min(ay, az)) <= 4)
+        if (std::min(ax, std::min(ay, az)) <= 4 && !level_dist)
             break;
+        LPMB_REQUIRE(std::min(ax, std::min(ay, az)) > 2, LPMB_ERR_UNSUPPORTED, "cg_precond on slabs: the block is too thin for %d ranks", W);
         ax = (ax + 1) / 2, ay = (ay + 1) / 2, az = (az + 1) / 2;
         scale *= 2.0;
+        if (level_dist) {
+            // a rank owns the coarse layers whose fine layer (2 Z) it owns; the level stays distributed while every rank
+            // keeps at least 2 layers (the depth of the exchanged ghosts) and the level is worth the latency
+            long long min_own = 1 << 30;
+            for (int r = 0; r <= W; r++)
+                ga[r] = (ga[r] + 1) / 2;
+            for (int r = 0; r < W; r++)
+                min_own = std::min(min_own, ga[r + 1] - ga[r]);
+            if (min_own < 2 || az <= 8) {
+                level_dist = false;
+                M.lrep = M.nlev;
+                for (int r = 0; r < W; r++) {
+                    M.gat_off[r] = ga[r] * (long long)ax * ay;
+                    M.gat_cnt[r] = (ga[r + 1] - ga[r]) * (long long)ax * ay;
+                }
+            }
+        }
     }
     return LPMB_OK;
 }
@@ -567,6 +652,29 @@ static int mg_read_stencil(lpmb_ctx *c, MGState &M)
             M.S[M.noff][e] = val[(size_t)k * 9 + e];
         M.noff++;
     }
+    if (M.dist) {
+        // one operator for all ranks: the stencil the middle rank read (a symmetric preconditioner needs it; the ranks' own
+        // interior rows differ by the local strain)
+        const size_t bytes = sizeof(M.S) + sizeof(M.off) + sizeof(int);
+        std::vector<char> mine(bytes), all(bytes * c->world);
+        memcpy(mine.data(), M.S, sizeof(M.S));
+        memcpy(mine.data() + sizeof(M.S), M.off, sizeof(M.off));
+        memcpy(mine.data() + sizeof(M.S) + sizeof(M.off), &M.noff, sizeof(int));
+        void *d_send = nullptr, *d_recv = nullptr;
+        LPMB_CUDA(cudaMalloc(&d_send, bytes));
+        LPMB_CUDA(cudaMalloc(&d_recv, bytes * c->world));
+        LPMB_H2D(c, d_send, mine.data(), bytes);
+        const int rc = lpmb_dist_allgather_bytes(c, d_send, d_recv, bytes);
+        if (rc == LPMB_OK)
+            LPMB_D2H(c, all.data(), d_recv, all.size());
+        cudaFree(d_send);
+        cudaFree(d_recv);
+        LPMB_TRY(rc);
+        const char *src = all.data() + bytes * (c->world / 2);
+        memcpy(M.S, src, sizeof(M.S));
+        memcpy(M.off, src + sizeof(M.S), sizeof(M.off));
+        memcpy(&M.noff, src + sizeof(M.S) + sizeof(M.off), sizeof(int));
+    }
     LPMB_TRY(mg_upload_constants(c, M));
     // inverse diagonal blocks per boundary class and level: D = -scale * sum of the present off-diagonal blocks
     std::vector<double> tab((size_t)729 * 9);
@@ -598,8 +706,44 @@ static int mg_read_stencil(lpmb_ctx *c, MGState &M)
 }
 
 // hierarchy + stencil ready; coarse masks follow the solve's current DoF mask
+// mask of the boundary conditions alone: 0 on constrained DoFs (boundary.c:182,214,247), 1 elsewhere
+__global__ void mg_phys_mask_kernel(const int *__restrict__ bc, const int *__restrict__ fix, double *__restrict__ mask, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        mask[i] = (bc[i] == 0 || fix[i] == 0) ? 0.0 : 1.0;
+}
+
+// slab runs: refresh the two ghost layers either side of the owned layers of a distributed level's vector
+static int mg_exchange(lpmb_ctx *c, const MGLevel &L, double *v)
+{
+    if (!L.dist)
+        return LPMB_OK;
+    const long long lay = (long long)L.nx * L.ny;
+    return lpmb_dist_neighbor_doubles(c, v, L.stride, 3, L.oz0 * lay, (L.oz0 - 2) * lay, (L.oz1 - 2) * lay, L.oz1 * lay, 2 * lay);
+}
+
+// a vector of level l was just formed from level l - 1 for the sites this rank owns: complete it (ghost layers of a
+// distributed level; the other ranks' layers of the first replicated level)
+static int mg_sync_coarse(lpmb_ctx *c, MGState &M, int l, double *v)
+{
+    if (!M.dist)
+        return LPMB_OK;
+    const MGLevel &C = M.lev[l];
+    if (C.dist)
+        return mg_exchange(c, C, v);
+    if (l == M.lrep)
+        return lpmb_dist_allgatherv_doubles(c, v, C.stride, 3, M.gat_off, M.gat_cnt);
+    return LPMB_OK;
+}
+
 int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
 {
+    {
+        auto it = g_mg.find(c);   // mg_dist switched since the hierarchy was built: build the other one
+        if (it != g_mg.end() && it->second.nlev > 0 && it->second.dist != (c->world > 1 && param(c, "mg_dist", 1.0) != 0.0))
+            lpmb_mg_release(c);
+    }
     MGState &M = g_mg[c];
     if (M.nlev == 0) {
         const int rc = mg_build_levels(c, M);
@@ -621,11 +765,25 @@ int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
     M.omega = param(c, "mg_omega", 0.56);
     M.omega2 = param(c, "mg_omega2", c->params.count("mg_omega") ? M.omega : 1.39);
     M.lev[0].mask = const_cast<double *>(mask0);
+    if (M.dist) {
+        // the solve's mask also zeroes the ghost DoFs; the distributed hierarchy needs the boundary conditions alone (ghost
+        // sites are ordinary sites of the global lattice whose values arrive by exchange)
+        const int *bc = fptr<int>(c, "dispBC_index"), *fix = fptr<int>(c, "fix_index");
+        LPMB_REQUIRE(bc && fix, LPMB_ERR_STATE, "cg_precond on slabs: BC index fields missing (lpmb_set_dof_mask / lpmb_apply_*_bc)");
+        const size_t n3 = (size_t)3 * c->Np;
+        if (!M.mask_phys)
+            LPMB_CUDA(cudaMalloc(&M.mask_phys, n3 * 8));
+        mg_phys_mask_kernel<<<lpmb_blocks((long long)n3, 256), 256, 0, c->stream>>>(bc, fix, M.mask_phys, n3);
+        LPMB_LAUNCH_CHECK(c);
+        M.lev[0].mask = M.mask_phys;
+    }
     for (int l = 1; l < M.nlev; l++) {
         const MGLevel &F = M.lev[l - 1];
         MGLevel &C = M.lev[l];
-        mg_coarse_mask_kernel<<<lpmb_blocks(C.n, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, F.stride, C.nx, C.ny, C.nz, C.stride, F.mask, C.mask);
+        mg_coarse_mask_kernel<<<lpmb_blocks(C.n, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, F.stride, C.nx, C.ny, C.nz, C.stride, F.gz0, C.gz0, C.nzg,
+                                                                            F.mask, C.mask);
         LPMB_LAUNCH_CHECK(c);
+        LPMB_TRY(mg_sync_coarse(c, M, l, C.mask));   // slab runs: ghost layers / the other ranks' parts
     }
     return LPMB_OK;
 }
@@ -636,10 +794,12 @@ static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const d
     MGLevel &L = M.lev[l];
     for (int s = 0; s < nu; s++) {
         const double om = (s & 1) ? M.omega2 : M.omega;
-        if (first && s == 0)
+        if (first && s == 0) {
             LPMB_TRY(mg_launch_stencil<2>(c, L, nullptr, L.f, L.u2, om, done));
-        else
+        } else {
+            LPMB_TRY(mg_exchange(c, L, L.u));   // slab runs: the stencil reaches two layers into the neighbours' sites
             LPMB_TRY(mg_launch_stencil<0>(c, L, L.u, L.f, L.u2, om, done));
+        }
         std::swap(L.u, L.u2);
     }
     return LPMB_OK;
@@ -657,12 +817,19 @@ static int mg_vcycle(lpmb_ctx *c, MGState &M, int l, const double *done)
         return mg_smooth(c, M, l, M.nu_coarse, true, done);
     }
     LPMB_TRY(mg_smooth(c, M, l, M.nu, true, done));
+    LPMB_TRY(mg_exchange(c, L, L.u));
     LPMB_TRY(mg_launch_stencil<1>(c, L, L.u, L.f, L.res, 0.0, done));
     MGLevel &C = M.lev[l + 1];
-    mg_restrict_kernel<<<lpmb_blocks(C.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, L.res, C.mask, C.f, done);
+    LPMB_TRY(mg_exchange(c, L, L.res));   // full weighting reaches one layer into the neighbours' sites
+    mg_restrict_kernel<<<lpmb_blocks(C.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, L.gz0, C.gz0, C.nzg, L.res,
+                                                                     C.mask, C.f, done);
     LPMB_LAUNCH_CHECK(c);
+    if (M.dist && !C.dist && l + 1 == M.lrep)
+        LPMB_TRY(mg_sync_coarse(c, M, l + 1, C.f));   // first replicated level: every rank gets the whole right-hand side
     LPMB_TRY(mg_vcycle(c, M, l + 1, done));
-    mg_prolong_kernel<<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, C.u, L.mask, L.u, done);
+    LPMB_TRY(mg_exchange(c, C, C.u));   // the interpolation reads one coarse layer beyond the owned ones
+    mg_prolong_kernel<<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, L.gz0, C.gz0, C.nzg, C.u,
+                                                                    L.mask, L.u, done);
     LPMB_LAUNCH_CHECK(c);
     return mg_smooth(c, M, l, M.nu, false, done);
 }

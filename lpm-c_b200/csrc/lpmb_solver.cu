@@ -1118,19 +1118,24 @@ pcg_direction_kernel(const double *__restrict__ z, double *__restrict__ p, size_
 }
 
 // y = mask .* (K x) + partials of x.y, on original-order vectors, whatever SpMV kernel is enabled
-static int pcg_apply_K(lpmb_ctx *c, const double *x, double *y, const double *m, int *nparts)
+static int pcg_apply_K(lpmb_ctx *c, const double *x /* ghost rows are overwritten in slab runs */, double *y, const double *m, int *nparts)
 {
     CGWork &w = c->cg;
+    const bool dist = c->world > 1;   // slab runs: the halo rows of x come from the neighbours (NCCL) before every product
     if (lpmb_brick_active(c)) {
         double *vr, *vp, *vap, *vx, *vb, *vm;
         long long P;
         lpmb_brick_vectors(c, &vr, &vp, &vap, &vx, &vb, &vm, &P);
         LPMB_TRY(lpmb_brick_to_perm(c, x, vp));
+        if (dist)
+            LPMB_TRY(lpmb_brick_exchange(c, vp));
         const int gg = vec_grid(c, (size_t)3 * P);
         LPMB_TRY(lpmb_brick_spmv(c, vp, vap, true, m ? vm : nullptr, w.partials, w.scal, gg, PeerWait(), PeerPublish()));
         LPMB_TRY(lpmb_brick_from_perm(c, vap, y));
         *nparts = gg;
     } else {
+        if (dist)
+            LPMB_TRY(lpmb_dist_exchange(c, const_cast<double *>(x), c->dim, false));
         LPMB_TRY(launch_spmv(c, x, y, true, m != nullptr));
         *nparts = spmv_grid(c);
     }
@@ -1140,7 +1145,12 @@ static int pcg_apply_K(lpmb_ctx *c, const double *x, double *y, const double *m,
 static int pcg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, int maxit, bool use_mask, int *iterations)
 {
     CGWork &w = c->cg;
-    LPMB_REQUIRE(c->world == 1, LPMB_ERR_UNSUPPORTED, "cg_precond: the preconditioned fast mode runs on one GPU only");
+    // Slab runs (world > 1): same iteration; p is halo-exchanged before every product, the three dot products are folded to
+    // one scalar per rank and all-reduced (NCCL, in stream), and the V-cycle acts on the rank's own slab (lpmb_mg.cu:
+    // block-Jacobi over the slabs).  Every rank sees the same scalars, hence takes the same decisions.
+    const bool dist = c->world > 1;
+    if (dist)
+        use_mask = true;  // the mask also zeroes the ghost DoFs (lpmb_refresh_mask)
     const size_t n = (size_t)c->dim * c->Np;
     const double *m = use_mask ? c->mask : nullptr;
     LPMB_REQUIRE(!use_mask || m, LPMB_ERR_STATE, "DoF mask not built");
@@ -1158,19 +1168,38 @@ static int pcg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, i
             LPMB_TRY(lpmb_brick_to_perm(c, m, vm));
     }
     double *part_a = w.partials, *part_b = w.partials + w.max_blocks;
+    double *red_a = w.scal + 10, *red_b = w.scal + 11;  // per-rank scalars that get all-reduced
     const int vg = vec_grid(c, n);
     const PeerWait nowait;
+    // partials -> what the consuming kernel reads: the per-block partials themselves, or (slab runs) the all-reduced scalar
+    auto global_sum = [&](const double *parts, int np, double *red, const double *done_flag, const double **out, int *nout) -> int {
+        if (!dist) {
+            *out = parts;
+            *nout = np;
+            return LPMB_OK;
+        }
+        reduce_to_scalar_kernel<<<1, VEC_THREADS, 0, c->stream>>>(parts, np, red, done_flag);
+        LPMB_LAUNCH_CHECK(c);
+        LPMB_TRY(lpmb_dist_allreduce_sum(c, red, 1));
+        *out = red;
+        *nout = 1;
+        return LPMB_OK;
+    };
+    const double *sp = nullptr;
+    int sn = 0;
     cg_init_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(d_b, m, w.r, w.p, w.x, n, part_a);   // r = mask .* b, x = 0 (p overwritten below)
     LPMB_LAUNCH_CHECK(c);
-    cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_a, vg, rel, abs_tol, w.scal, nowait);
+    LPMB_TRY(global_sum(part_a, vg, red_a, nullptr, &sp, &sn));
+    cg_init_scalars_kernel<<<1, VEC_THREADS, 0, c->stream>>>(sp, sn, rel, abs_tol, w.scal, nowait);
     LPMB_LAUNCH_CHECK(c);
     const double *done = w.scal + S_DONE;
     // z = M^-1 r ; rho = r.z ; p = z
     LPMB_TRY(lpmb_mg_apply(c, w.r, w.z, done));
     pcg_dot_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.z, n, part_b, w.scal);
     LPMB_LAUNCH_CHECK(c);
+    LPMB_TRY(global_sum(part_b, vg, red_b, w.scal, &sp, &sn));
     int parity = 0;
-    pcg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.z, w.p, n, part_b, vg, w.scal, parity ^ 1, 1, w.counters + 2);  // stores rho into slot `parity`
+    pcg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.z, w.p, n, sp, sn, w.scal, parity ^ 1, 1, w.counters + 2);  // stores rho into slot `parity`
     LPMB_LAUNCH_CHECK(c);
     const int batch = 4;
     int issued = 0;
@@ -1178,14 +1207,17 @@ static int pcg_run(lpmb_ctx *c, const double *d_b, double rel, double abs_tol, i
         for (int b = 0; b < batch && issued < maxit; b++, issued++) {
             int np = 0;
             LPMB_TRY(pcg_apply_K(c, w.p, w.ap, m, &np));
-            pcg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, part_a, np, part_b, w.scal, parity);
+            LPMB_TRY(global_sum(part_a, np, red_a, w.scal, &sp, &sn));
+            pcg_update_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.p, w.ap, w.x, w.r, n, sp, sn, part_b, w.scal, parity);
             LPMB_LAUNCH_CHECK(c);
-            pcg_check_kernel<<<1, VEC_THREADS, 0, c->stream>>>(part_b, vg, w.scal, maxit);
+            LPMB_TRY(global_sum(part_b, vg, red_b, w.scal, &sp, &sn));
+            pcg_check_kernel<<<1, VEC_THREADS, 0, c->stream>>>(sp, sn, w.scal, maxit);
             LPMB_LAUNCH_CHECK(c);
             LPMB_TRY(lpmb_mg_apply(c, w.r, w.z, done));
             pcg_dot_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.r, w.z, n, part_b, w.scal);
             LPMB_LAUNCH_CHECK(c);
-            pcg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.z, w.p, n, part_b, vg, w.scal, parity, 0, w.counters + 2);
+            LPMB_TRY(global_sum(part_b, vg, red_a, w.scal, &sp, &sn));
+            pcg_direction_kernel<<<vg, VEC_THREADS, 0, c->stream>>>(w.z, w.p, n, sp, sn, w.scal, parity, 0, w.counters + 2);
             LPMB_LAUNCH_CHECK(c);
             parity ^= 1;
         }

@@ -51,6 +51,16 @@ def brittle_phase(c, first_global=0, n_total=None):
     return [cand] + (sorted(int(p) for p in np.asarray(pairs)[:, 0] if p >= 0) if len(pairs) else [])
 
 
+def next_step_of(c):
+    """the first Newton iteration of the next load step (assembly, predictor, residual, solve, constitutive update)"""
+    c.copy_field("xyz_temp", "xyz")
+    c.copy_field("F_temp", "F")
+    c.fd_stiffness(False)
+    c.bond_force(4)
+    c.update_rr()
+    return c.newton_iteration(0, 1)
+
+
 def child(rank, world, n, d):
     import bench
     lpm = importlib.import_module("lpm-c_b200")
@@ -76,12 +86,7 @@ def child(rank, world, n, d):
     c.snapshot_save(snap)
 
     def next_step():
-        c.copy_field("xyz_temp", "xyz")
-        c.copy_field("F_temp", "F")
-        c.fd_stiffness(False)
-        c.bond_force(4)
-        c.update_rr()
-        return c.newton_iteration(0, 1)
+        return next_step_of(c)
 
     a = next_step()
     xa = c.get_field("xyz")
@@ -96,11 +101,27 @@ def child(rank, world, n, d):
           f"loaded-vs-loaded {np.abs(xb - xb2).max():.3e}", flush=True)
     assert b == b2 and np.array_equal(xb, xb2), ("two resumes from the same slab snapshot differ", b, b2)
     assert a[0] == b[0] and abs(a[1] - b[1]) <= 1e-12 * abs(a[1]) and np.abs(xa - xb).max() <= 1e-13, ("slab snapshot resume differs", a, b)
+    # opt-in fast mode on slabs (CG preconditioned with one multigrid V-cycle per slab = block-Jacobi over the ranks,
+    # lpmb_mg.cu / pcg_run): the same step from the same snapshot -- far fewer iterations, the same stop rule on the true
+    # residual, and a Newton residual after the iteration within the accepted solve error of the parity-mode one
+    c.snapshot_load(snap)
+    c.set_params(cg_precond=1.0)
+    f = next_step()
+    c.set_params(cg_precond=0.0)
+    print(f"rank {rank}: fast mode on slabs: {f[0]} PCG iterations (parity mode {b[0]} CG iterations), Newton residual {f[1]:.6e} vs {b[1]:.6e}", flush=True)
+    assert 0 < f[0] <= b[0] // 2 and abs(f[1] - b[1]) <= 1e-3 * abs(b[1]), ("fast mode on slabs", f, b)
+    # ... and the same with one hierarchy per slab and no communication inside the V-cycle (block-Jacobi over the slabs)
+    c.snapshot_load(snap)
+    c.set_params(cg_precond=1.0, mg_dist=0.0)
+    fj = next_step()
+    c.set_params(cg_precond=0.0, mg_dist=1.0)
+    print(f"rank {rank}: fast mode, block-Jacobi over the slabs: {fj[0]} PCG iterations", flush=True)
+    assert 0 < fj[0] < b[0] and abs(fj[1] - b[1]) <= 1e-3 * abs(b[1]), ("block-Jacobi fast mode on slabs", fj, b)
     # back to the state after the load step, then the brittle selection across the slabs
     c.snapshot_load(snap)
     brittle = brittle_phase(c, slab.first_global, n ** 3)
     out = {k: np.ascontiguousarray(c.get_field(k).reshape(slab.n_local, -1)[own]) for k in KEYS}
-    np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken] + brittle), mode=np.array([c.dist_mode()]),
+    np.savez(Path(d) / f"rank{rank}.npz", its=np.array(its), nrs=np.array(nrs), broken=np.array([broken] + brittle), mode=np.array([c.dist_mode()]), fast=np.array([f[0], b[0], fj[0]]), fast_nr=np.array([f[1]]),
              norm0=np.array([info["norm_residual0"]]), spmv_bytes=np.array([c.spmv_bytes_bricks()]), **out)
     c.close()
 
@@ -122,13 +143,24 @@ def main():
         lpm = importlib.import_module("lpm-c_b200")
         c1, info1 = bench.build_workload(lpm, n, 0, bricks=False)   # full-format SELL kernel as the cross-check
         its1, nrs1, broken1 = run_steps(c1)
+        # the distributed multigrid hierarchy is the single-GPU one: same PCG iteration count, same Newton residual
+        snap1 = Path(d) / "single.snap"
+        c1.snapshot_save(snap1)
+        c1.set_params(cg_precond=1.0)
+        f1 = next_step_of(c1)
+        c1.set_params(cg_precond=0.0)
+        c1.snapshot_load(snap1)
+        fd_its, fd_nr = int(parts[0]["fast"][0]), float(parts[0]["fast_nr"][0])
+        print(f"fast mode: slabs {fd_its} PCG iterations, Newton residual {fd_nr:.9e}; one GPU {f1[0]} iterations, {f1[1]:.9e}; "
+              f"block-Jacobi over the slabs {int(parts[0]['fast'][2])} iterations; parity mode {int(parts[0]['fast'][1])} CG iterations")
+        fast_ok = abs(fd_its - f1[0]) <= 1 and abs(fd_nr - f1[1]) <= 1e-5 * abs(f1[1])
         broken1 = [broken1] + brittle_phase(c1)
         its, nrs, broken = list(parts[0]["its"]), list(parts[0]["nrs"]), [int(x) for x in parts[0]["broken"]]
         assert all([int(x) for x in p["broken"]] == broken for p in parts), "ranks disagree on the broken bonds"
         print(f"world={world} n={n}: CG iterations dist {its} single {its1}; residual norms dist {nrs} single {nrs1}; "
-              f"broken bonds [nonlocal law, brittle candidates, particles of the 7 brittle breaks] dist {broken} single {broken1}; comm mode {[int(p['mode'][0]) for p in parts]}; "
+              f"broken bonds [nonlocal law, brittle candidates, particles of the 7 brittle breaks] dist {broken} single {broken1}; comm mode {[int(p['mode'][0]) for p in parts]}; fast mode on slabs {int(parts[0]['fast'][0])} PCG iterations against {int(parts[0]['fast'][1])} CG iterations; "
               f"brick SpMV bytes per rank {[int(p['spmv_bytes'][0]) for p in parts]}")
-        ok = its == its1 and broken == broken1
+        ok = its == its1 and broken == broken1 and fast_ok
         ok &= all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(nrs, nrs1))
         ok &= abs(float(parts[0]["norm0"][0]) - info1["norm_residual0"]) <= 1e-12 * info1["norm_residual0"]
         x0 = c1.get_field("xyz_initial")
