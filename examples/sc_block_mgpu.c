@@ -5,7 +5,7 @@
  *
  *   sc_block_mgpu <world> [n=48] [steps=1] [physics=c1|c5] [strain_step=0.005] [solver=parity|fast]
  *
- * solver fast (world = 1 only): the opt-in preconditioned mode of the solve (param cg_precond = 1: CG preconditioned with
+ * solver fast: the opt-in preconditioned mode of the solve (param cg_precond = 1: CG preconditioned with
  * the matrix-free multigrid V-cycle, lpmb_mg.cu) -- NOT the parity path; the iteration counts printed are then PCG iterations.
  *
  * physics c1 (default): the default driver's problem (src/lpmc_project.c: E = 146e3, nu = 0.3, sigma_y = 200, force-controlled
@@ -289,8 +289,8 @@ int main(int argc, char **argv)
     const int c5 = argc > 4 && strcmp(argv[4], "c5") == 0;
     const double strain_step = argc > 5 ? atof(argv[5]) : 0.005;
     const int fast = argc > 6 && strcmp(argv[6], "fast") == 0;
-    if (world < 1 || world > 16 || steps < 1 || n < 4 * world || (argc > 4 && !c5 && strcmp(argv[4], "c1") != 0) || (fast && world != 1)) {
-        fprintf(stderr, "usage: sc_block_mgpu <world 1..16> [n >= 4*world] [steps >= 1] [c1|c5] [strain_step] [parity|fast (world 1 only)]\n");
+    if (world < 1 || world > 16 || steps < 1 || n < 4 * world || (argc > 4 && !c5 && strcmp(argv[4], "c1") != 0) || 0) {
+        fprintf(stderr, "usage: sc_block_mgpu <world 1..16> [n >= 4*world] [steps >= 1] [c1|c5] [strain_step] [parity|fast]\n");
         return 2;
     }
     char dir[] = "/tmp/lpmb_mgpu_XXXXXX";

@@ -180,8 +180,8 @@ def run(args, lpm, dist, rank, world, local, bench):
     bytes_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
     dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
 
-    # ---- opt-in fast mode on slabs (param cg_precond = 1): CG preconditioned with one multigrid V-cycle per slab = block-Jacobi
-    # over the ranks, no communication inside the V-cycle (lpmb_mg.cu, pcg_run).  Reported BESIDE the parity-mode headline.
+    # ---- opt-in fast mode on slabs (param cg_precond = 1): CG preconditioned with the multigrid V-cycle of the single-GPU fast
+    # mode, its hierarchy distributed over the slabs (lpmb_mg.cu, pcg_run).  Reported BESIDE the parity-mode headline.
     fast = None
     if not getattr(args, "no_fast_mode", False):
         try:
@@ -204,8 +204,9 @@ def run(args, lpm, dist, rank, world, local, bench):
             fast = {"newton_it_per_s": 1000.0 / f_ms, "ms_per_step": f_ms, "pcg_iterations_per_step": f_iters,
                     "speedup_vs_parity_mode": (ms_total / args.steps) / f_ms, "norm_residual_after_the_iteration": f_nr[-1],
                     "norm_residual_after_the_iteration_parity_mode": nr,
-                    "preconditioner": "block-Jacobi over the slabs: one matrix-free geometric multigrid V-cycle per rank on its own "
-                                      "slab (ghost DoFs constrained), no communication inside the V-cycle; param cg_precond = 1",
+                    "preconditioner": "matrix-free geometric multigrid V-cycle, ONE hierarchy distributed over the slabs (global coarse "
+                                      "grids, two ghost layers exchanged before every stencil pass, coarse levels replicated); "
+                                      "param cg_precond = 1",
                     "note": "not the parity path: the reference's CG is unpreconditioned (solver.c:219-220); same stop rule on the true residual"}
         except Exception as e:   # optional; the parity-mode line stands on its own
             fast = {"error": str(e)[:300]}
