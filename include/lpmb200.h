@@ -259,6 +259,14 @@ int lpmb_dist_exchange_field(lpmb_ctx *ctx, const char *name, int wide);
  * variable LPMB_NO_PEER is set or a rank cannot map another (then all ranks stay on NCCL together); param
  * "peer_comm" = 0 switches the fast path off at run time. */
 int lpmb_dist_mode(lpmb_ctx *ctx);
+/* The multigrid levels of the fast mode (param cg_precond) for a full simple-cubic block of nx x ny x sum(owned) sites split
+ * into z-slabs of owned[r] layers: pure host arithmetic, no device.  plan[8 l + k], k = 0: level distributed over the ranks
+ * (else whole on every rank), 1 / 2: nx, ny of the level, 3: layers of THIS rank's block of it, 4: global z of its layer 0,
+ * 5 / 6: its owned layers [oz0, oz1) inside the block, 7: layers of the whole level.  lrep = first replicated level (-1: none),
+ * gat_off / gat_cnt [world] = the ranks' owned ranges of that level (elements per component).  nz_local0 / ghost_lo0: layers of
+ * this rank's level-0 block and how many of them lie below the owned ones (world = 1: sum(owned), 0).  See lpmb_mg.cu. */
+int lpmb_mg_slab_plan(int world, int rank, const long long *owned, int nx, int ny, int nz_local0, int ghost_lo0, int max_levels, int *plan,
+                      long long *gat_off, long long *gat_cnt, int *nlev, int *lrep);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ lib.lpmb_dist_unique_id.argtypes = [c_vp]
 lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
 lib.lpmb_dist_set_slab.argtypes = [c_vp] + [C.c_int] * 8
 lib.lpmb_dist_exchange_field.argtypes = [c_vp, C.c_char_p, C.c_int]
+lib.lpmb_mg_slab_plan.argtypes = [C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
 lib.lpmb_synchronize.argtypes = [c_vp]
 lib.lpmb_set_schmid_tensor.argtypes = [c_vp, c_vp, C.c_int]
 lib.lpmb_compute_cab.argtypes = [c_vp]
@@ -99,6 +100,19 @@ def declared_symbols() -> list[str]:
     text = HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(lpmb_[a-z0-9_]+)\s*\(", text)))
+
+
+def mg_slab_plan(world: int, rank: int, owned, nx: int, ny: int, nz_local0: int, ghost_lo0: int, max_levels: int = 12):
+    """levels of the fast mode's multigrid hierarchy and rank `rank`'s part of each (lpmb_mg_slab_plan: host arithmetic, no GPU)"""
+    owned = np.ascontiguousarray(owned, dtype=np.int64)
+    plan = np.zeros((max_levels, 8), dtype=np.int32)
+    off, cnt = np.zeros(16, dtype=np.int64), np.zeros(16, dtype=np.int64)
+    nlev, lrep = C.c_int(), C.c_int()
+    _check(lib.lpmb_mg_slab_plan(world, rank, owned.ctypes.data, nx, ny, nz_local0, ghost_lo0, max_levels, plan.ctypes.data, off.ctypes.data,
+                                 cnt.ctypes.data, C.addressof(nlev), C.addressof(lrep)))
+    keys = ("dist", "nx", "ny", "nz", "gz0", "oz0", "oz1", "nzg")
+    return {"levels": [dict(zip(keys, (int(v) for v in plan[l]))) for l in range(nlev.value)], "lrep": lrep.value,
+            "gat_off": off[:world].tolist(), "gat_cnt": cnt[:world].tolist()}
 
 
 def device_count() -> int:

@@ -485,6 +485,69 @@ static bool invert3(const double *a, double *inv)
     return true;
 }
 
+// The multigrid levels of a full simple-cubic block -- and, for z-slabs, the part of every level a rank holds.  Pure host
+// arithmetic (no device, no context): tests/test_partition.py checks its invariants for all ranks on CPU.
+//   owned[r]   fine lattice layers rank r owns (world = 1: the whole block); nz_local0 / ghost_lo0: layers of this rank's
+//              level-0 block and how many of them lie below its owned ones
+//   plan[8 l + {0: distributed, 1: nx, 2: ny, 3: nz of the local block, 4: global z of local layer 0, 5 / 6: owned local
+//              layers [oz0, oz1), 7: layers of the whole level}]
+//   Coarse site I sits on fine site 2 I (global), so a rank owns the coarse layers [ceil(a / 2), ceil(b / 2)) of its fine
+//   layers [a, b); a distributed level keeps 2 ghost layers either side (clipped at the block's faces).  The level is
+//   replicated (lrep = its index; gat_off / gat_cnt = the ranks' owned ranges of it in elements per component) as soon as a
+//   rank would own fewer than 2 layers or the level has <= 8 layers; levels end when an edge is <= 4 sites.
+extern "C" int lpmb_mg_slab_plan(int world, int rank, const long long *owned, int nx, int ny, int nz_local0, int ghost_lo0, int max_levels, int *plan,
+                                 long long *gat_off, long long *gat_cnt, int *nlev, int *lrep)
+{
+    LPMB_REQUIRE(world >= 1 && world <= LPMB_PEER_MAXW && rank >= 0 && rank < world && owned && plan && nlev && lrep && nx > 0 && ny > 0 &&
+                     max_levels > 0 && (world == 1 || (gat_off && gat_cnt)),
+                 LPMB_ERR_ARG, "lpmb_mg_slab_plan: bad argument");
+    std::vector<long long> ga(world + 1, 0);
+    for (int r = 0; r < world; r++) {
+        LPMB_REQUIRE(owned[r] > 0, LPMB_ERR_ARG, "lpmb_mg_slab_plan: rank %d owns no layer", r);
+        ga[r + 1] = ga[r] + owned[r];
+    }
+    int ax = nx, ay = ny, az = (int)ga[world], n = 0;
+    bool level_dist = world > 1;
+    *lrep = -1;
+    for (;;) {
+        LPMB_REQUIRE(n < max_levels, LPMB_ERR_UNSUPPORTED, "cg_precond: too many levels");
+        int *P = plan + 8 * n;
+        P[0] = level_dist ? 1 : 0, P[1] = ax, P[2] = ay, P[7] = az;
+        const int A = (int)ga[rank], B = (int)ga[rank + 1];
+        if (n == 0 && world > 1) {
+            P[3] = nz_local0, P[4] = A - ghost_lo0, P[5] = ghost_lo0, P[6] = ghost_lo0 + (B - A);
+        } else if (level_dist) {
+            P[4] = std::max(0, A - 2);
+            P[3] = std::min(az, B + 2) - P[4];
+            P[5] = A - P[4], P[6] = B - P[4];
+        } else {
+            P[3] = az, P[4] = 0, P[5] = world > 1 ? A : 0, P[6] = world > 1 ? B : az;
+        }
+        n++;
+        if (std::min(ax, std::min(ay, az)) <= 4 && !level_dist)
+            break;
+        LPMB_REQUIRE(std::min(ax, std::min(ay, az)) > 2, LPMB_ERR_UNSUPPORTED, "cg_precond on slabs: the block is too thin for %d ranks", world);
+        ax = (ax + 1) / 2, ay = (ay + 1) / 2, az = (az + 1) / 2;
+        for (int r = 0; r <= world; r++)
+            ga[r] = (ga[r] + 1) / 2;
+        if (level_dist) {
+            long long min_own = 1ll << 40;
+            for (int r = 0; r < world; r++)
+                min_own = std::min(min_own, ga[r + 1] - ga[r]);
+            if (min_own < 2 || az <= 8) {
+                level_dist = false;
+                *lrep = n;
+                for (int r = 0; r < world; r++) {
+                    gat_off[r] = ga[r] * (long long)ax * ay;
+                    gat_cnt[r] = (ga[r + 1] - ga[r]) * (long long)ax * ay;
+                }
+            }
+        }
+    }
+    *nlev = n;
+    return LPMB_OK;
+}
+
 // lattice dimensions + ordering check (once), level storage
 static int mg_build_levels(lpmb_ctx *c, MGState &M)
 {
@@ -520,13 +583,12 @@ static int mg_build_levels(lpmb_ctx *c, MGState &M)
     LPMB_D2H(c, &bad, d_bad, sizeof(int));
     cudaFree(d_bad);
     LPMB_REQUIRE(!bad, LPMB_ERR_UNSUPPORTED, "cg_precond: particles are not numbered x-fastest on an axis-aligned lattice of spacing %g", q);
-    // ---- slab runs: global z-extent of every level and this rank's part of it
+    // ---- the levels: dimensions, and in slab runs this rank's part of every level (lpmb_mg_slab_plan below)
     const long long lay0 = (long long)nx * ny;
     const int W = c->world;
     M.dist = W > 1 && param(c, "mg_dist", 1.0) != 0.0;
-    M.lrep = -1;
-    std::vector<long long> ga(W + 1, 0);   // global first owned layer of every rank on the current level (ga[W] = layers of the level)
-    int gz0 = 0;
+    std::vector<long long> owned(1, nz);
+    int ghost_lo = 0;
     if (M.dist) {
         LPMB_REQUIRE(W <= LPMB_PEER_MAXW, LPMB_ERR_UNSUPPORTED, "cg_precond on slabs: at most %d ranks", LPMB_PEER_MAXW);
         const int o0 = lpmb_own0(c), o1 = lpmb_own1(c);
@@ -535,71 +597,34 @@ static int mg_build_levels(lpmb_ctx *c, MGState &M)
         long long mine = (o1 - o0) / lay0, *d_mine = (long long *)c->staging, *d_all = d_mine + 1;
         LPMB_H2D(c, d_mine, &mine, sizeof(mine));
         LPMB_TRY(lpmb_dist_allgather_bytes(c, d_mine, d_all, sizeof(mine)));
-        std::vector<long long> all(W);
-        LPMB_D2H(c, all.data(), d_all, (size_t)W * sizeof(long long));
-        for (int r = 0; r < W; r++)
-            ga[r + 1] = ga[r] + all[r];
-        gz0 = (int)(ga[c->rank] - o0 / lay0);
+        owned.resize(W);
+        LPMB_D2H(c, owned.data(), d_all, (size_t)W * sizeof(long long));
+        ghost_lo = (int)(o0 / lay0);
     }
-    M.nlev = 0;
-    int ax = nx, ay = ny, az = M.dist ? (int)ga[W] : nz;   // az = GLOBAL layers of the level
+    int plan[MG_MAXLEV * 8];
+    LPMB_TRY(lpmb_mg_slab_plan(M.dist ? W : 1, M.dist ? c->rank : 0, owned.data(), nx, ny, nz, ghost_lo, MG_MAXLEV, plan, M.gat_off, M.gat_cnt, &M.nlev,
+                               &M.lrep));
     double scale = 1.0;
-    bool level_dist = M.dist;
-    for (;;) {
-        LPMB_REQUIRE(M.nlev < MG_MAXLEV, LPMB_ERR_UNSUPPORTED, "cg_precond: too many levels");
-        MGLevel &L = M.lev[M.nlev];
-        L.nx = ax, L.ny = ay, L.nzg = az;
-        L.dist = level_dist;
-        if (M.nlev == 0) {
-            L.nz = nz, L.gz0 = gz0;
-            L.oz0 = M.dist ? (int)(lpmb_own0(c) / lay0) : 0;
-            L.oz1 = M.dist ? (int)(lpmb_own1(c) / lay0) : nz;
-        } else if (level_dist) {
-            const int A = (int)ga[c->rank], B = (int)ga[c->rank + 1];
-            L.gz0 = std::max(0, A - 2);
-            L.nz = std::min(az, B + 2) - L.gz0;
-            L.oz0 = A - L.gz0, L.oz1 = B - L.gz0;
-        } else {
-            L.nz = az, L.gz0 = 0, L.oz0 = 0, L.oz1 = az;
-        }
-        L.n = (long long)ax * ay * L.nz;
-        L.stride = M.nlev == 0 ? Np : L.n;
+    for (int l = 0; l < M.nlev; l++, scale *= 2.0) {
+        MGLevel &L = M.lev[l];
+        const int *P = plan + 8 * l;
+        L.dist = P[0] != 0;
+        L.nx = P[1], L.ny = P[2], L.nz = P[3], L.gz0 = P[4], L.oz0 = P[5], L.oz1 = P[6], L.nzg = P[7];
+        L.n = (long long)L.nx * L.ny * L.nz;
+        L.stride = l == 0 ? Np : L.n;
         L.scale = scale;
         LPMB_CUDA(cudaMalloc(&L.dinv, 729 * 9 * sizeof(double)));
         LPMB_CUDA(cudaMalloc(&L.u2, (size_t)3 * L.stride * 8));
         LPMB_CUDA(cudaMalloc(&L.res, (size_t)3 * L.stride * 8));
         LPMB_MEMSET(c, L.u2, 0, (size_t)3 * L.stride * 8);
         LPMB_MEMSET(c, L.res, 0, (size_t)3 * L.stride * 8);
-        if (M.nlev > 0) {
+        if (l > 0) {
             LPMB_CUDA(cudaMalloc(&L.mask, (size_t)3 * L.stride * 8));
             LPMB_CUDA(cudaMalloc(&L.u, (size_t)3 * L.stride * 8));
             LPMB_CUDA(cudaMalloc(&L.f, (size_t)3 * L.stride * 8));
             LPMB_MEMSET(c, L.mask, 0, (size_t)3 * L.stride * 8);
             LPMB_MEMSET(c, L.u, 0, (size_t)3 * L.stride * 8);
             LPMB_MEMSET(c, L.f, 0, (size_t)3 * L.stride * 8);
-        }
-        M.nlev++;
-        if (std::min(ax, std::min(ay, az)) <= 4 && !level_dist)
-            break;
-        LPMB_REQUIRE(std::min(ax, std::min(ay, az)) > 2, LPMB_ERR_UNSUPPORTED, "cg_precond on slabs: the block is too thin for %d ranks", W);
-        ax = (ax + 1) / 2, ay = (ay + 1) / 2, az = (az + 1) / 2;
-        scale *= 2.0;
-        if (level_dist) {
-            // a rank owns the coarse layers whose fine layer (2 Z) it owns; the level stays distributed while every rank
-            // keeps at least 2 layers (the depth of the exchanged ghosts) and the level is worth the latency
-            long long min_own = 1 << 30;
-            for (int r = 0; r <= W; r++)
-                ga[r] = (ga[r] + 1) / 2;
-            for (int r = 0; r < W; r++)
-                min_own = std::min(min_own, ga[r + 1] - ga[r]);
-            if (min_own < 2 || az <= 8) {
-                level_dist = false;
-                M.lrep = M.nlev;
-                for (int r = 0; r < W; r++) {
-                    M.gat_off[r] = ga[r] * (long long)ax * ay;
-                    M.gat_cnt[r] = (ga[r + 1] - ga[r]) * (long long)ax * ay;
-                }
-            }
         }
     }
     return LPMB_OK;

@@ -226,3 +226,63 @@ def test_ragged_slab_invariants_on_random_specimens():
             assert max(s.weight for s in slabs) <= max(sum(weights[a:b]) for a, b in equal) + 1e-9
 
     check()
+
+
+@pytest.mark.parametrize("world,n,ghost", [(2, 24, 4), (8, 216, 4), (4, 216, 4), (3, 100, 4), (8, 64, 4), (5, 47, 4)])
+def test_multigrid_levels_on_slabs(world, n, ghost):
+    """lpmb_mg_slab_plan (the level geometry of the fast mode's DISTRIBUTED multigrid hierarchy, lpmb_mg.cu): for every rank of
+    a z-slab decomposition -- coarse site I sits on fine site 2 I in global coordinates; the ranks' owned layers tile every
+    level; a distributed level gives every rank >= 2 owned layers and 2 ghost layers either side (clipped at the faces), its
+    block holds every fine layer the restriction of its owned coarse layers reads and every coarse layer the prolongation of
+    its owned fine layers reads; all ranks agree on the level count, on which level is the first replicated one and on the
+    owned ranges gathered there; the coarsest level is whole on every rank."""
+    import importlib
+    capi = importlib.import_module("lpm-c_b200.capi")
+    partition = importlib.import_module("lpm-c_b200.partition")
+    slabs = [partition.make_slab(n, n * n, r, world, ghost_layers=ghost) for r in range(world)]
+    owned = [s.z1 - s.z0 for s in slabs]
+    plans = []
+    for r, s in enumerate(slabs):
+        nz_local = s.n_local // (n * n)
+        plans.append(capi.mg_slab_plan(world, r, owned, n, n, nz_local, s.own0 // (n * n)))
+    nlev, lrep = len(plans[0]["levels"]), plans[0]["lrep"]
+    assert all(len(p["levels"]) == nlev and p["lrep"] == lrep and p["gat_off"] == plans[0]["gat_off"] and p["gat_cnt"] == plans[0]["gat_cnt"]
+               for p in plans)
+    assert 1 <= lrep < nlev and not plans[0]["levels"][-1]["dist"]
+    for l in range(nlev):
+        L = [p["levels"][l] for p in plans]
+        nzg = L[0]["nzg"]
+        assert all(x["nzg"] == nzg and x["nx"] == L[0]["nx"] and x["dist"] == L[0]["dist"] for x in L)
+        if l > 0:
+            assert nzg == (plans[0]["levels"][l - 1]["nzg"] + 1) // 2 and L[0]["nx"] == (plans[0]["levels"][l - 1]["nx"] + 1) // 2
+        assert (l < lrep) == bool(L[0]["dist"])
+        if not L[0]["dist"]:
+            assert all(x["gz0"] == 0 and x["nz"] == nzg for x in L)
+        # the owned global ranges tile the level, in rank order
+        og = [(x["gz0"] + x["oz0"], x["gz0"] + x["oz1"]) for x in L] if (L[0]["dist"] or l == lrep) else None
+        if og:
+            assert og[0][0] == 0 and og[-1][1] == nzg and all(og[r][1] == og[r + 1][0] for r in range(world - 1))
+        if l == lrep:
+            lay = L[0]["nx"] * L[0]["ny"]
+            assert plans[0]["gat_off"] == [a * lay for a, _ in og] and plans[0]["gat_cnt"] == [(b - a) * lay for a, b in og]
+        if L[0]["dist"]:
+            for r, x in enumerate(L):
+                a, b = og[r]
+                assert b - a >= 2
+                assert x["gz0"] <= max(0, a - 2) and x["gz0"] + x["nz"] >= min(nzg, b + 2)      # two ghost layers, clipped
+                if l > 0:   # coarse layer Z is owned by the owner of fine layer 2 Z
+                    fa, fb = plans[r]["levels"][l - 1]["gz0"] + plans[r]["levels"][l - 1]["oz0"], plans[r]["levels"][l - 1]["gz0"] + plans[r]["levels"][l - 1]["oz1"]
+                    assert a == (fa + 1) // 2 and b == (fb + 1) // 2
+        if l > 0:
+            nzf = plans[0]["levels"][l - 1]["nzg"]
+            for r in range(world):
+                F, Cc = plans[r]["levels"][l - 1], plans[r]["levels"][l]
+                if not F["dist"]:
+                    continue
+                fa, fb = F["gz0"] + F["oz0"], F["gz0"] + F["oz1"]
+                ca, cb = (fa + 1) // 2, (fb + 1) // 2
+                # restriction of the owned coarse layers reads fine layers 2 Z - 1 .. 2 Z + 1: inside the fine block
+                assert F["gz0"] <= max(0, 2 * ca - 1) and F["gz0"] + F["nz"] >= min(nzf, 2 * (cb - 1) + 2)
+                # prolongation to the owned fine layers reads coarse layers z >> 1 and (z >> 1) + 1: inside the coarse block
+                lo, hi = fa >> 1, min(Cc["nzg"] - 1, ((fb - 1) >> 1) + ((fb - 1) & 1))
+                assert Cc["gz0"] <= lo and Cc["gz0"] + Cc["nz"] > hi
