@@ -34,7 +34,7 @@
 // in GLOBAL lattice coordinates, a rank owns the coarse layers whose fine layer it owns, and every distributed level keeps
 // [2 ghost layers | owned layers | 2 ghost layers] (level 0: the context's own 4-layer ghosts).  Before every stencil pass
 // (smoother sweep, residual) the two ghost layers of the iterate are refreshed from the neighbours, the residual's before
-// the restriction, the coarse correction's before the prolongation -- 6 small exchanges per level and V-cycle; boundary
+// the restriction, the coarse correction's before the prolongation -- 5 small exchanges per level and V-cycle; boundary
 // classes and interpolation weights use global coordinates, so the operator is the single-GPU one.  From the first level on
 // which some rank would own fewer than 2 layers the level is REPLICATED: the ranks' restricted residuals are all-gathered and
 // every rank runs the remaining (tiny) levels redundantly.  All ranks use the stencil read by the middle rank (a symmetric
@@ -814,7 +814,7 @@ int lpmb_mg_prepare(lpmb_ctx *c, const double *mask0)
 }
 
 // nu damped-Jacobi sweeps on level l starting from u = 0 (first = true) or from L.u; result in L.u
-static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const double *done)
+static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const double *done, bool ghosts_valid = false)
 {
     MGLevel &L = M.lev[l];
     for (int s = 0; s < nu; s++) {
@@ -822,7 +822,8 @@ static int mg_smooth(lpmb_ctx *c, MGState &M, int l, int nu, bool first, const d
         if (first && s == 0) {
             LPMB_TRY(mg_launch_stencil<2>(c, L, nullptr, L.f, L.u2, om, done));
         } else {
-            LPMB_TRY(mg_exchange(c, L, L.u));   // slab runs: the stencil reaches two layers into the neighbours' sites
+            if (!(ghosts_valid && s == 0))
+                LPMB_TRY(mg_exchange(c, L, L.u));   // slab runs: the stencil reaches two layers into the neighbours' sites
             LPMB_TRY(mg_launch_stencil<0>(c, L, L.u, L.f, L.u2, om, done));
         }
         std::swap(L.u, L.u2);
@@ -856,7 +857,10 @@ static int mg_vcycle(lpmb_ctx *c, MGState &M, int l, const double *done)
     mg_prolong_kernel<<<lpmb_blocks(L.n, 128), 128, 0, c->stream>>>(L.nx, L.ny, L.nz, L.stride, C.nx, C.ny, C.nz, C.stride, L.gz0, C.gz0, C.nzg, C.u,
                                                                     L.mask, L.u, done);
     LPMB_LAUNCH_CHECK(c);
-    return mg_smooth(c, M, l, M.nu, false, done);
+    // The interpolation ran on every local site: the two ghost layers of u (valid since the exchange before the residual)
+    // received the same correction as on their owner (it read the coarse ghost layers just exchanged, and the hierarchy's
+    // level-0 mask is the boundary-condition mask, the same on both sides) -- the first post-smoothing sweep needs no exchange.
+    return mg_smooth(c, M, l, M.nu, false, done, M.dist && L.dist);
 }
 
 // z = V-cycle(r) on the context's original-order vectors ([3][Np]); r is not modified.  `done` (device, may be null):
