@@ -3,6 +3,8 @@
 The golden vectors were produced by the unmodified reference sources (oracle/_ref); the restatement must
 reproduce them BIT FOR BIT through a whole plastic load step (set-up -> FD tangent -> predictor -> residual ->
 BC-modified tangent -> CG -> J2 bond force -> ... -> damage -> crack update)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -706,3 +708,21 @@ def test_port_compute_strain_bit_exact(golden, step):
                               _ptr(_c(g["setup.nsign"], i4)), _ptr(_c(g["setup.nb_initial"], i4)), _ptr(_c(g["setup.distance_initial"], f8)),
                               _ptr(_c(g[f"{step}.strain.dL"], f8)), _ptr(strain))
     assert_same(strain, g[f"{step}.strain.strain_tensor"], "strain_tensor")
+
+
+def test_reciprocal_quotient_of_the_fd_kernel_is_the_ieee_quotient(tmp_path):
+    """fd_div_by (lpmb_stiffness.cu) forms x / y for a divisor used many times (`/ EPS / radius`, the three direction cosines
+    of one bond) from rcp = RN(1 / y) and two corrections with exact FMA residuals.  The bit-exactness of the FD tangent rests
+    on that being the IEEE quotient: scripts/check_exact_division.c compares it with `/` on random numerators over 600
+    binades for the divisors the kernel uses (1e-6, 0.25, 0.3, ...) and on random divisors -- here 2e6 per divisor + 6e6
+    random pairs; the full 8.6e8-pair run is quoted in DESIGN.md."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    src = Path(__file__).resolve().parents[1] / "scripts" / "check_exact_division.c"
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    exe = tmp_path / "check_exact_division"
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run([gcc, "-O2", "-march=native", "-ffp-contract=off", str(src), "-o", str(exe), "-lm"], check=True, env=env)
+    r = subprocess.run([str(exe), "2000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().startswith("bad 0 of"), r.stdout[-500:]
