@@ -286,3 +286,199 @@ def test_multigrid_levels_on_slabs(world, n, ghost):
                 # prolongation to the owned fine layers reads coarse layers z >> 1 and (z >> 1) + 1: inside the coarse block
                 lo, hi = fa >> 1, min(Cc["nzg"] - 1, ((fb - 1) >> 1) + ((fb - 1) & 1))
                 assert Cc["gz0"] <= lo and Cc["gz0"] + Cc["nz"] > hi
+
+
+def test_distributed_vcycle_schedule_reproduces_the_global_vcycle():
+    """The communication schedule of the distributed multigrid V-cycle (lpmb_mg.cu::mg_vcycle / mg_smooth) on a 1-D column
+    of the lattice, emulated rank by rank in numpy on the level geometry lpmb_mg_slab_plan returns: two ghost layers of the
+    iterate refreshed before every stencil pass EXCEPT the first post-smoothing sweep, the residual's before the restriction,
+    the coarse correction's before the prolongation, the restricted residual all-gathered at the first replicated level,
+    boundary classes and interpolation weights in GLOBAL coordinates.  The owned parts of the result must equal the V-cycle
+    of one rank on the whole column -- for several decompositions, with a Dirichlet end (mask) and free ends.  Ghost and
+    not-owned entries are poisoned before every use that the schedule does not cover, so a missing exchange shows."""
+    import importlib
+    capi = importlib.import_module("lpm-c_b200.capi")
+    partition = importlib.import_module("lpm-c_b200.partition")
+    S = {-2: 0.3, -1: 1.0, 1: 1.0, 2: 0.3}          # 2-hop stencil like the lattice tangent's z-reach
+    NU, OM = 2, (0.56, 1.39)
+
+    def w1(f, X, nc):                                # mg_w1
+        d = f - 2 * X
+        return 1.0 if d == 0 else (0.5 if X + 1 < nc else 1.0) if d == 1 else 0.5 if d == -1 else 0.0
+
+    def apply_level(u, f, mask, gz0, nzg, scale, mode, om):
+        """mg_stencil_kernel on a local block: neighbours outside the BLOCK are skipped, the diagonal is the global class's"""
+        n = len(f)
+        out = np.empty(n)
+        for i in range(n):
+            g = i + gz0
+            a = 0.0
+            if mode != 2:
+                for o, s in S.items():
+                    if 0 <= i + o < n:
+                        a += s * (u[i + o] - u[i])
+            diag = -scale * sum(s for o, s in S.items() if 0 <= g + o < nzg)
+            r = f[i] - scale * a
+            if mode == 1:
+                out[i] = mask[i] * r
+            else:
+                out[i] = (0.0 if mode == 2 else u[i]) + om * mask[i] * (mask[i] * r) / diag
+        return out
+
+    def vcycle(world, owned, nz_local0, ghost_lo0, f0_global, mask0_global):
+        plans = [capi.mg_slab_plan(world, r, owned, 64, 64, nz_local0[r], ghost_lo0[r]) for r in range(world)]
+        nlev, lrep = len(plans[0]["levels"]), plans[0]["lrep"]
+        lev = lambda r, l: plans[r]["levels"][l]
+        POISON = 1e30
+
+        def own(r, l):
+            L = lev(r, l)
+            return L["gz0"] + L["oz0"], L["gz0"] + L["oz1"]
+
+        def exchange(vs, l):                         # mg_exchange: owners' values into the neighbours' two ghost layers
+            if not lev(0, l)["dist"]:
+                return
+            for r in range(world):
+                a, b = own(r, l)
+                for q in (r - 1, r + 1):
+                    if 0 <= q < world:
+                        for g in (range(a, a + 2) if q == r - 1 else range(b - 2, b)):
+                            vs[q][g - lev(q, l)["gz0"]] = vs[r][g - lev(r, l)["gz0"]]
+
+        def poison_unowned(vs, l, keep_ghosts=0, before_gather=False):
+            for r in range(world):
+                # on a replicated level every rank computes every site itself; only what is about to be all-gathered (the
+                # restricted residual and the mask of the first replicated level) is valid on the owned layers alone
+                if world == 1 or not (lev(r, l)["dist"] or (before_gather and l == lrep)):
+                    continue
+                a, b = own(r, l)
+                for i in range(len(vs[r])):
+                    g = i + lev(r, l)["gz0"]
+                    if not (a - keep_ghosts <= g < b + keep_ghosts):
+                        vs[r][i] = POISON
+
+        def sync_coarse(vs, l):                      # mg_sync_coarse
+            if world == 1:
+                return
+            if lev(0, l)["dist"]:
+                exchange(vs, l)
+            elif l == lrep:
+                for r in range(world):
+                    a, b = own(r, l)
+                    for q in range(world):
+                        vs[q][a:b] = vs[r][a:b]
+
+        # masks: level 0 = the boundary conditions on every local site; coarser = min over the interpolation support
+        masks = [[mask0_global[lev(r, 0)["gz0"]:lev(r, 0)["gz0"] + lev(r, 0)["nz"]].copy() for r in range(world)]]
+        for l in range(1, nlev):
+            ms = []
+            for r in range(world):
+                F, Cc = lev(r, l - 1), lev(r, l)
+                m = np.ones(Cc["nz"])
+                for Z in range(Cc["nz"]):
+                    Zg = Z + Cc["gz0"]
+                    for dz in (-1, 0, 1):
+                        fz = 2 * Zg + dz - F["gz0"]
+                        if 0 <= fz < F["nz"] and w1(fz + F["gz0"], Zg, Cc["nzg"]) != 0.0:
+                            m[Z] = min(m[Z], masks[l - 1][r][fz])
+                ms.append(m)
+            poison_unowned(ms, l, before_gather=True)
+            sync_coarse(ms, l)
+            masks.append(ms)
+
+        U = [[None] * world for _ in range(nlev)]
+        Fv = [[None] * world for _ in range(nlev)]
+        # level-0 right-hand side: the PCG residual, ZERO on the ghost rows (the solve's mask)
+        for r in range(world):
+            L = lev(r, 0)
+            f = f0_global[L["gz0"]:L["gz0"] + L["nz"]].copy()
+            a, b = own(r, 0)
+            for i in range(L["nz"]):
+                if world > 1 and not (a <= i + L["gz0"] < b):
+                    f[i] = 0.0
+            Fv[0][r] = f
+
+        def smooth(l, first, ghosts_valid=False):
+            for s in range(NU):
+                if first and s == 0:
+                    for r in range(world):
+                        L = lev(r, l)
+                        U[l][r] = apply_level(None, Fv[l][r], masks[l][r], L["gz0"], L["nzg"], 2.0 ** l, 2, OM[s & 1])
+                else:
+                    if not (ghosts_valid and s == 0):
+                        poison_unowned(U[l], l)
+                        exchange(U[l], l)
+                    else:
+                        poison_unowned(U[l], l, keep_ghosts=2)
+                    for r in range(world):
+                        L = lev(r, l)
+                        U[l][r] = apply_level(U[l][r], Fv[l][r], masks[l][r], L["gz0"], L["nzg"], 2.0 ** l, 0, OM[s & 1])
+
+        def cycle(l):
+            if l == nlev - 1:
+                for r in range(world):
+                    L = lev(r, l)
+                    u = None
+                    for s in range(6):
+                        u = apply_level(u, Fv[l][r], masks[l][r], 0, L["nzg"], 2.0 ** l, 2 if s == 0 else 0, OM[0])
+                    U[l][r] = u
+                return
+            smooth(l, True)
+            poison_unowned(U[l], l)
+            exchange(U[l], l)
+            res = [apply_level(U[l][r], Fv[l][r], masks[l][r], lev(r, l)["gz0"], lev(r, l)["nzg"], 2.0 ** l, 1, 0.0) for r in range(world)]
+            poison_unowned(res, l)
+            exchange(res, l)
+            for r in range(world):
+                F, Cc = lev(r, l), lev(r, l + 1)
+                fc = np.zeros(Cc["nz"])
+                for Z in range(Cc["nz"]):
+                    Zg = Z + Cc["gz0"]
+                    for dz in (-1, 0, 1):
+                        fz = 2 * Zg + dz - F["gz0"]
+                        if 0 <= fz < F["nz"]:
+                            fc[Z] += w1(fz + F["gz0"], Zg, Cc["nzg"]) * res[r][fz]
+                    fc[Z] *= masks[l + 1][r][Z]
+                Fv[l + 1][r] = fc
+            if world > 1 and not lev(0, l + 1)["dist"] and l + 1 == lrep:
+                poison_unowned(Fv[l + 1], l + 1, before_gather=True)
+                sync_coarse(Fv[l + 1], l + 1)
+            cycle(l + 1)
+            poison_unowned(U[l + 1], l + 1)
+            exchange(U[l + 1], l + 1)
+            for r in range(world):
+                F, Cc = lev(r, l), lev(r, l + 1)
+                for fz in range(F["nz"]):
+                    fzg = fz + F["gz0"]
+                    s = 0.0
+                    for az in range((fzg & 1) + 1):
+                        Zg = (fzg >> 1) + az
+                        Z = Zg - Cc["gz0"]
+                        if Zg < Cc["nzg"] and 0 <= Z < Cc["nz"]:
+                            s += w1(fzg, Zg, Cc["nzg"]) * U[l + 1][r][Z]
+                    U[l][r][fz] += masks[l][r][fz] * s
+            smooth(l, False, ghosts_valid=world > 1 and bool(lev(0, l)["dist"]))
+
+        with np.errstate(all="ignore"):
+            cycle(0)
+        out = np.full(len(f0_global), np.nan)
+        for r in range(world):
+            a, b = own(r, 0)
+            out[a:b] = U[0][r][a - lev(r, 0)["gz0"]:b - lev(r, 0)["gz0"]]
+        return out, nlev, lrep
+
+    rng = np.random.default_rng(11)
+    for world, nz in ((2, 64), (4, 64), (8, 64), (3, 50), (5, 47)):
+        f = rng.standard_normal(nz)
+        for dirichlet in (False, True):
+            mask = np.ones(nz)
+            if dirichlet:
+                mask[0] = 0.0
+                f[0] = 0.0
+            ref, nlev1, _ = vcycle(1, [nz], [nz], [0], f, mask)
+            slabs = [partition.make_slab(nz, 64 * 64, r, world) for r in range(world)]
+            owned = [s.z1 - s.z0 for s in slabs]
+            got, nlev, lrep = vcycle(world, owned, [s.n_local // 4096 for s in slabs], [s.own0 // 4096 for s in slabs], f, mask)
+            assert nlev == nlev1 and 1 <= lrep < nlev
+            assert np.isfinite(got).all() and np.abs(got).max() < 1e6, "a poisoned (never exchanged) value reached the result"
+            assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), (world, nz, dirichlet, np.abs(got - ref).max())
