@@ -600,6 +600,9 @@ static int mg_build_levels(lpmb_ctx *c, MGState &M)
         owned.resize(W);
         LPMB_D2H(c, owned.data(), d_all, (size_t)W * sizeof(long long));
         ghost_lo = (int)(o0 / lay0);
+        // the ghost exchange of level 0 writes two layers either side of the owned ones
+        LPMB_REQUIRE((c->rank == 0 || ghost_lo >= 2) && (c->rank == W - 1 || nz - (int)(o1 / lay0) >= 2), LPMB_ERR_UNSUPPORTED,
+                     "cg_precond on slabs: fewer than 2 ghost layers towards a neighbouring rank");
     }
     int plan[MG_MAXLEV * 8];
     LPMB_TRY(lpmb_mg_slab_plan(M.dist ? W : 1, M.dist ? c->rank : 0, owned.data(), nx, ny, nz, ghost_lo, MG_MAXLEV, plan, M.gat_off, M.gat_cnt, &M.nlev,
