@@ -259,6 +259,11 @@ int lpmb_dist_exchange_field(lpmb_ctx *ctx, const char *name, int wide);
  * variable LPMB_NO_PEER is set or a rank cannot map another (then all ranks stay on NCCL together); param
  * "peer_comm" = 0 switches the fast path off at run time. */
 int lpmb_dist_mode(lpmb_ctx *ctx);
+/* The selection step of updateBrittleDamage (constitutive.c:1489-1520) on k candidates listed in the reference's scan order
+ * (keys ascending): sorts keys / strains in place with the reference's shell sort when k > nbreak; the bonds to break are
+ * [*first, k).  Pure host arithmetic (no device); lpmb_update_damage(ctx, 6, ...) uses it, in slab runs on the all-gathered
+ * candidates of all ranks. */
+int lpmb_brittle_select(int k, long long *keys, double *strains, int nbreak, int *first);
 /* The multigrid levels of the fast mode (param cg_precond) for a full simple-cubic block of nx x ny x sum(owned) sites split
  * into z-slabs of owned[r] layers: pure host arithmetic, no device.  plan[8 l + k], k = 0: level distributed over the ranks
  * (else whole on every rank), 1 / 2: nx, ny of the level, 3: layers of THIS rank's block of it, 4: global z of its layer 0,

@@ -84,6 +84,7 @@ lib.lpmb_dist_unique_id.argtypes = [c_vp]
 lib.lpmb_dist_init.argtypes = [c_vp, c_vp, C.c_int, C.c_int]
 lib.lpmb_dist_set_slab.argtypes = [c_vp] + [C.c_int] * 8
 lib.lpmb_dist_exchange_field.argtypes = [c_vp, C.c_char_p, C.c_int]
+lib.lpmb_brittle_select.argtypes = [C.c_int, c_vp, c_vp, C.c_int, c_vp]
 lib.lpmb_mg_slab_plan.argtypes = [C.c_int, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
 lib.lpmb_synchronize.argtypes = [c_vp]
 lib.lpmb_set_schmid_tensor.argtypes = [c_vp, c_vp, C.c_int]
@@ -100,6 +101,15 @@ def declared_symbols() -> list[str]:
     text = HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(lpmb_[a-z0-9_]+)\s*\(", text)))
+
+
+def brittle_select(keys, strains, nbreak: int):
+    """lpmb_brittle_select: (keys, strains) of the bonds that break, in the reference's order (host arithmetic, no GPU)"""
+    keys = np.ascontiguousarray(keys, dtype=np.int64).copy()
+    strains = np.ascontiguousarray(strains, dtype=np.float64).copy()
+    first = C.c_int()
+    _check(lib.lpmb_brittle_select(len(keys), keys.ctypes.data, strains.ctypes.data, int(nbreak), C.addressof(first)))
+    return keys[first.value:], strains[first.value:]
 
 
 def mg_slab_plan(world: int, rank: int, owned, nx: int, ny: int, nz_local0: int, ghost_lo0: int, max_levels: int = 12):

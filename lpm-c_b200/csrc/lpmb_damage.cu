@@ -347,6 +347,35 @@ __global__ void brittle_apply_kernel(int nbreak, int nn, int Np, const int *__re
     broken[e] = 0.0;
 }
 
+// The selection of updateBrittleDamage (constitutive.c:1489-1520) on a candidate list in the reference's scan order
+// (particle, then slot ascending == key ascending): all k candidates break if k <= nbreak, else the nbreak largest strains
+// after the reference's shell sort -- reproduced verbatim in behaviour (it is not stable: ties are resolved exactly as
+// there).  Sorts keys / strains in place; the bonds to break are [first, k).  Pure host arithmetic: in slab runs every rank
+// runs it on the same all-gathered list (tests/test_oracle_port.py checks it against the oracle's restatement, also with
+// the list assembled from per-rank pieces).
+extern "C" int lpmb_brittle_select(int k, long long *keys, double *strains, int nbreak, int *first)
+{
+    LPMB_REQUIRE(k >= 0 && first && (k == 0 || (keys && strains)), LPMB_ERR_ARG, "lpmb_brittle_select: bad argument");
+    *first = 0;
+    if (k > nbreak) {
+        for (int r = k / 2; r >= 1; r = r / 2)
+            for (int a2 = r; a2 < k; ++a2) {
+                const long long ti = keys[a2];
+                const double tb = strains[a2];
+                int b2 = a2 - r;
+                while (b2 >= 0 && strains[b2] > tb) {
+                    strains[b2 + r] = strains[b2];
+                    keys[b2 + r] = keys[b2];
+                    b2 = b2 - r;
+                }
+                strains[b2 + r] = tb;
+                keys[b2 + r] = ti;
+            }
+        *first = k - (nbreak > 0 ? nbreak : 0);
+    }
+    return LPMB_OK;
+}
+
 extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int *pairs, int max_pairs)
 {
     LPMB_REQUIRE(c && broken_out, LPMB_ERR_ARG, "lpmb_update_damage: null argument");
@@ -526,25 +555,8 @@ extern "C" int lpmb_update_damage(lpmb_ctx *c, int plmode, int *broken_out, int 
         }
         *broken_out = k;  // the reference returns the candidate count even when it breaks only nbreak of them
         if (k > 0) {
-            const int nbreak = (int)param(c, "nbreak");
             int first = 0;
-            if (k > nbreak) {
-                // the reference's shell sort, verbatim in behaviour (not stable: ties resolved exactly as there)
-                for (int r = k / 2; r >= 1; r = r / 2)
-                    for (int a2 = r; a2 < k; ++a2) {
-                        const long long ti = bi[a2];
-                        const double tb = bs[a2];
-                        int b2 = a2 - r;
-                        while (b2 >= 0 && bs[b2] > tb) {
-                            bs[b2 + r] = bs[b2];
-                            bi[b2 + r] = bi[b2];
-                            b2 = b2 - r;
-                        }
-                        bs[b2 + r] = tb;
-                        bi[b2 + r] = ti;
-                    }
-                first = k - nbreak;
-            }
+            LPMB_TRY(lpmb_brittle_select(k, bi.data(), bs.data(), (int)param(c, "nbreak"), &first));
             const int nb = k - first;
             // winners on this rank: owned particles and the ghosts whose stars are complete (same slot order as on their owner)
             const int lo = c->world > 1 ? lpmb_own0(c) - c->narrow_recv_lo : 0, hi = c->world > 1 ? lpmb_own1(c) + c->narrow_recv_hi : N;

@@ -726,3 +726,45 @@ def test_reciprocal_quotient_of_the_fd_kernel_is_the_ieee_quotient(tmp_path):
     subprocess.run([gcc, "-O2", "-march=native", "-ffp-contract=off", str(src), "-o", str(exe), "-lm"], check=True, env=env)
     r = subprocess.run([str(exe), "2000000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().startswith("bad 0 of"), r.stdout[-500:]
+
+
+def test_brittle_selection_of_the_library_equals_the_oracle():
+    """lpmb_brittle_select (host arithmetic of liblpmb200.so: the selection step of updateBrittleDamage, used on one GPU and
+    -- on the all-gathered candidates of all ranks -- in slab runs) against the oracle's restatement of constitutive.c:1437-1526
+    on synthetic candidate sets with MANY ties (the reference's shell sort is not stable: which of the tied bonds break is part
+    of the behaviour): same bonds, same order, for nbreak below / at / above the candidate count, also when the global list is
+    assembled from per-rank pieces in rank order."""
+    import ctypes as C
+    import importlib
+    from oracle.port import SO
+    capi = importlib.import_module("lpm-c_b200.capi")
+    lib = C.CDLL(str(SO))
+    lib.oracle_damage_brittle.restype = C.c_int
+    rng = np.random.default_rng(5)
+    N, nn, crit = 60, 8, 1.0
+    nbr = np.tile(np.arange(nn, dtype=np.int32), (N, 1))          # "neighbour" of slot j is j: the pairs give the key back
+    nbi = np.full(N, nn, dtype=np.int32)
+    L0 = np.ones((N, nn))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for k in (1, 3, 10, 57, 200, 390):
+        for levels in (2, 5, 1000):
+            flat = rng.choice(N * nn, size=k, replace=False)
+            dL = np.zeros((N, nn))
+            dL.ravel()[flat] = crit + rng.integers(0, levels, size=k) * 0.125          # exact binary fractions: true ties
+            keys = np.sort(flat).astype(np.int64)
+            strains = dL.ravel()[keys].copy()
+            for nbreak in (1, 2, 7, k, k + 5):
+                broken, dD0, w = np.ones((N, nn)), np.zeros((N, nn)), np.ones((N, nn))
+                pairs = np.full((400, 2), -1, np.int32)
+                kk = lib.oracle_damage_brittle(N, nn, C.c_double(crit), nbreak, p(nbr), p(nbi), p(dL), p(L0), p(broken), p(dD0), p(w), p(pairs), 400)
+                assert kk == k
+                want = [int(a) * nn + int(b) for a, b in pairs[: min(k, nbreak)]]
+                got_k, got_s = capi.brittle_select(keys, strains, nbreak)
+                assert list(got_k) == want, (k, levels, nbreak)
+                assert np.array_equal(got_s, dL.ravel()[got_k])
+                # slab runs: every rank lists the candidates of its own particle range; rank order = ascending keys
+                cuts = [0, 17 * nn, 41 * nn, N * nn]
+                pieces = [keys[(keys >= a) & (keys < b)] for a, b in zip(cuts[:-1], cuts[1:])]
+                merged = np.concatenate(pieces)
+                assert np.array_equal(merged, keys)
+                assert list(capi.brittle_select(merged, dL.ravel()[merged], nbreak)[0]) == want
