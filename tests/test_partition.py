@@ -482,3 +482,132 @@ def test_distributed_vcycle_schedule_reproduces_the_global_vcycle():
             assert nlev == nlev1 and 1 <= lrep < nlev
             assert np.isfinite(got).all() and np.abs(got).max() < 1e6, "a poisoned (never exchanged) value reached the result"
             assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max(), (world, nz, dirichlet, np.abs(got - ref).max())
+
+
+def _worker_round2(rank, world, port, q):
+    """the N > 1 host logic added in round 2, over gloo: (a) the brittle law's global selection -- every rank lists the
+    candidates of its own particle range, the lists are all-gathered, every rank runs lpmb_brittle_select on the same global
+    list; (b) the preconditioned CG of the fast mode on slabs -- halo exchange of p before every product, THREE all-reduced dot
+    products per iteration (p.Ap, r.r for the stop rule on the true residual, r.z), every rank taking the same decisions."""
+    import torch
+    import torch.distributed as dist
+    import scipy.sparse as sp
+    sys.path.insert(0, str(ROOT))
+    capi = importlib.import_module("lpm-c_b200.capi")
+    lpm_lat = importlib.import_module("lpm-c_b200.lattice")
+    part = importlib.import_module("lpm-c_b200.partition")
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 10
+    lat = lpm_lat.sc_block(n)
+    N, nn = n ** 3, 18
+    s = part.make_slab(n, n * n, rank, world)
+    g0 = s.first_global
+    # ---- (a) brittle selection: strains = a hash of the global bond key with many ties
+    key = np.arange(N * nn, dtype=np.int64)
+    strain_all = ((key * 2654435761) % 97).astype(np.float64) / 8.0
+    crit, nbreak = 11.5, 9
+    mine_lo, mine_hi = (g0 + s.own0) * nn, (g0 + s.own1) * nn
+    mk = key[mine_lo:mine_hi][strain_all[mine_lo:mine_hi] >= crit]
+    lists = [None] * world
+    dist.all_gather_object(lists, (mk.tolist(), strain_all[mk].tolist()))
+    gk = np.array(sum((l[0] for l in lists), []), dtype=np.int64)        # rank order = ascending keys
+    gs = np.array(sum((l[1] for l in lists), []))
+    picked, _ = capi.brittle_select(gk, gs, nbreak)
+    ref_keys = key[strain_all >= crit]
+    ref_picked, _ = capi.brittle_select(ref_keys, strain_all[ref_keys], nbreak)
+    sel_ok = np.array_equal(gk, ref_keys) and np.array_equal(picked, ref_picked) and len(picked) == nbreak
+    # ---- (b) preconditioned CG on slabs (block-diagonal preconditioner = distributed trivially; same stop rule as pcg_run)
+    conn = lat["conn"]
+    rows = np.repeat(np.arange(N), conn.shape[1])[conn.ravel() >= 0]
+    cols = conn.ravel()[conn.ravel() >= 0]
+    vals = np.where(rows == cols, 70.0 + (rows % 7), -1.0 - ((rows + cols) % 5) / 5.0)
+    A = sp.csr_matrix((vals, (rows, cols)), shape=(N, N))
+    dinv = 1.0 / A.diagonal()
+    b = np.cos(3e-2 * np.arange(N))
+    loc = slice(g0, g0 + s.n_local)
+    Al = A[loc, loc].tocsr()
+    own = np.zeros(s.n_local, dtype=bool)
+    own[s.own0:s.own1] = True
+    L = s.layer_size
+    n_lo, n_hi = s.narrow_lo * L, s.narrow_hi * L
+
+    def exchange(v):
+        reqs = []
+        if rank > 0:
+            reqs.append(dist.isend(torch.from_numpy(v[s.own0:s.own0 + s.send_narrow_lo * L].copy()), rank - 1))
+            rl = torch.empty(n_lo, dtype=torch.float64)
+            reqs.append(dist.irecv(rl, rank - 1))
+        if rank < world - 1:
+            reqs.append(dist.isend(torch.from_numpy(v[s.own1 - s.send_narrow_hi * L:s.own1].copy()), rank + 1))
+            rh = torch.empty(n_hi, dtype=torch.float64)
+            reqs.append(dist.irecv(rh, rank + 1))
+        for r in reqs:
+            r.wait()
+        if rank > 0:
+            v[s.own0 - n_lo:s.own0] = rl.numpy()
+        if rank < world - 1:
+            v[s.own1:s.own1 + n_hi] = rh.numpy()
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def pcg(matvec, rhs, mask, dot):
+        x = np.zeros_like(rhs)
+        r = rhs * mask
+        rr0 = dot(r, r)
+        thresh = 1e-8 * rr0 + 1e-12
+        z = dinv_l * r if matvec is not global_mv else dinv * r
+        rho = dot(r, z)
+        p = z.copy()
+        it = 0
+        while it < 500:
+            ap = matvec(p) * mask
+            alpha = rho / dot(p, ap)
+            x += alpha * p
+            r -= alpha * ap
+            it += 1
+            if dot(r, r) <= thresh:
+                break
+            z = (dinv_l if matvec is not global_mv else dinv) * r
+            rho_new = dot(r, z)
+            p = z + (rho_new / rho) * p
+            rho = rho_new
+        return x, it
+
+    dinv_l = dinv[loc]
+
+    def local_mv(p):
+        exchange(p)
+        return Al @ p
+
+    def global_mv(p):
+        return A @ p
+
+    x, it = pcg(local_mv, b[loc].copy(), own.astype(float), lambda u, v: allsum(u @ v))
+    xr, itr = pcg(global_mv, b.copy(), np.ones(N), lambda u, v: float(u @ v))
+    err = np.abs(x[s.own0:s.own1] - xr[g0 + s.own0:g0 + s.own1]).max() / np.abs(xr).max()
+    errs = [None] * world
+    dist.all_gather_object(errs, (it, float(err), bool(sel_ok)))
+    if rank == 0:
+        q.put((itr, errs))
+    dist.destroy_process_group()
+
+
+def test_round2_slab_logic_with_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30400 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker_round2, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    itr, errs = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(sel for _, _, sel in errs), "ranks disagree with the single-list brittle selection"
+    assert all(it == itr for it, _, _ in errs) and 0 < itr < 100, (itr, errs)
+    assert all(e <= 1e-12 for _, e, _ in errs), errs
